@@ -1,0 +1,124 @@
+"""ctypes front-end of the CPU test oracle (oracle/pairhmm_oracle.c).
+
+TEST INFRASTRUCTURE ONLY: importable from tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs.  The product package (gatk_b200) never imports this module.
+
+Parity status: PINNED against the reference's fixtures by tests/test_oracle_golden.py.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libphmm_oracle.so")
+_lib = None
+
+_u8p = ctypes.POINTER(ctypes.c_uint8)
+_i32p = ctypes.POINTER(ctypes.c_int32)
+_f64p = ctypes.POINTER(ctypes.c_double)
+
+
+def build(force=False):
+    """Compile the oracle with the committed Makefile (gcc, -ffp-contract=off)."""
+    src = os.path.join(_HERE, "pairhmm_oracle.c")
+    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "-s", "-B", "libphmm_oracle.so"])
+    return _LIB_PATH
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = ctypes.CDLL(_LIB_PATH)
+        L.phmm_oracle_init.restype = None
+        L.phmm_oracle_qual_to_error_prob.restype = ctypes.c_double
+        L.phmm_oracle_qual_to_error_prob.argtypes = [ctypes.c_int]
+        L.phmm_oracle_match_to_match_prob.restype = ctypes.c_double
+        L.phmm_oracle_match_to_match_prob.argtypes = [ctypes.c_int, ctypes.c_int]
+        L.phmm_oracle_qual_to_trans_probs.restype = ctypes.c_int
+        L.phmm_oracle_qual_to_trans_probs.argtypes = [_f64p, ctypes.c_uint8, ctypes.c_uint8, ctypes.c_uint8]
+        pair_args = [_u8p, ctypes.c_int, _u8p, _u8p, _u8p, _u8p, _u8p, ctypes.c_int]
+        L.phmm_oracle_logless.restype = ctypes.c_int
+        L.phmm_oracle_logless.argtypes = pair_args + [ctypes.c_int, _f64p]
+        L.phmm_oracle_log10.restype = ctypes.c_int
+        L.phmm_oracle_log10.argtypes = pair_args + [ctypes.c_int, ctypes.c_int, _f64p]
+        L.phmm_oracle_unit.restype = ctypes.c_int
+        L.phmm_oracle_unit.argtypes = [_u8p, _u8p, _u8p, _u8p, _u8p, _i32p, ctypes.c_int,
+                                       _u8p, _i32p, ctypes.c_int, ctypes.c_int, ctypes.c_int, _f64p]
+        L.phmm_oracle_max_threads.restype = ctypes.c_int
+        L.phmm_oracle_init()
+        _lib = L
+    return _lib
+
+
+def _u8(a):
+    a = np.ascontiguousarray(np.frombuffer(a, dtype=np.uint8) if isinstance(a, (bytes, bytearray)) else a, dtype=np.uint8)
+    return a, a.ctypes.data_as(_u8p)
+
+
+def _pair(fn, hap, read, base_q, ins_q, del_q, gcp, *extra):
+    hap_a, hap_p = _u8(hap)
+    rd_a, rd_p = _u8(read)
+    arrs = [_u8(x) for x in (base_q, ins_q, del_q, gcp)]
+    for a, _ in arrs:
+        if len(a) != len(rd_a):
+            # PairHMM.java:286-292 (IllegalArgumentException)
+            raise ValueError("read bases and quals aren't the same size")
+    out = ctypes.c_double(float("nan"))
+    rc = fn(hap_p, len(hap_a), rd_p, arrs[0][1], arrs[1][1], arrs[2][1], arrs[3][1], len(rd_a), *extra, ctypes.byref(out))
+    if rc != 0:
+        raise ValueError("oracle error %d" % rc)
+    return out.value
+
+
+def logless(hap, read, base_q, ins_q, del_q, gcp, tristate_off=False):
+    """LoglessPairHMM (Java double) log10 likelihood of one (read, haplotype) pair."""
+    return _pair(lib().phmm_oracle_logless, hap, read, base_q, ins_q, del_q, gcp, int(tristate_off))
+
+
+def log10hmm(hap, read, base_q, ins_q, del_q, gcp, exact=True, tristate_off=False):
+    """Log10PairHMM: EXACT (exact=True) or ORIGINAL (exact=False)."""
+    return _pair(lib().phmm_oracle_log10, hap, read, base_q, ins_q, del_q, gcp, int(exact), int(tristate_off))
+
+
+def qual_to_error_prob(q):
+    return lib().phmm_oracle_qual_to_error_prob(int(q))
+
+
+def match_to_match_prob(i, d):
+    return lib().phmm_oracle_match_to_match_prob(int(i), int(d))
+
+
+def qual_to_trans_probs(ins_q, del_q, gcp):
+    dest = (ctypes.c_double * 6)()
+    rc = lib().phmm_oracle_qual_to_trans_probs(dest, ins_q, del_q, gcp)
+    if rc != 0:
+        raise ValueError("oracle error %d" % rc)
+    return list(dest)
+
+
+def max_threads():
+    return lib().phmm_oracle_max_threads()
+
+
+def unit(read_bases, base_q, ins_q, del_q, gcp, read_off, hap_bases, hap_off, tristate_off=False, threads=1):
+    """One (region, sample) unit, flat SoA in, read-major double[nReads*nHaps] out."""
+    rb, rbp = _u8(read_bases)
+    bq, bqp = _u8(base_q)
+    iq, iqp = _u8(ins_q)
+    dq, dqp = _u8(del_q)
+    gc, gcp_p = _u8(gcp)
+    hb, hbp = _u8(hap_bases)
+    ro = np.ascontiguousarray(read_off, dtype=np.int32)
+    ho = np.ascontiguousarray(hap_off, dtype=np.int32)
+    n_reads, n_haps = len(ro) - 1, len(ho) - 1
+    out = np.full(n_reads * n_haps, np.nan, dtype=np.float64)
+    rc = lib().phmm_oracle_unit(rbp, bqp, iqp, dqp, gcp_p, ro.ctypes.data_as(_i32p), n_reads,
+                                hbp, ho.ctypes.data_as(_i32p), n_haps, int(tristate_off), int(threads),
+                                out.ctypes.data_as(_f64p))
+    if rc != 0:
+        raise ValueError("oracle error %d" % rc)
+    return out
