@@ -1,0 +1,1076 @@
+// gpuphmm.cu -- host side of libgpuphmm.so: C ABI (include/gpuphmm.h), chunk planner, pinned staging,
+// per-device stream slots, multi-GPU work queue, async submit/wait queue.
+//
+// Mirrors the role of the native library behind PairHMMNativeBinding in the reference
+// (call sites: src/main/java/org/broadinstitute/hellbender/utils/pairhmm/VectorLoglessPairHMM.java:63,81,138,164).
+// No CPU compute path exists here: every likelihood comes from the CUDA kernels in phmm_kernels.cuh.
+#include "../../include/gpuphmm.h"
+#include "phmm_kernels.cuh"
+
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <cmath>
+#include <condition_variable>
+#include <cstdio>
+#include <cstring>
+#include <deque>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <stdexcept>
+#include <string>
+#include <thread>
+#include <vector>
+
+using namespace phmm_dev;
+
+namespace {
+
+struct Error : std::runtime_error {
+    int code;
+    Error(int c, const std::string &m) : std::runtime_error(m), code(c) {}
+};
+
+#define CK(call)                                                                                      \
+    do {                                                                                              \
+        cudaError_t e_ = (call);                                                                      \
+        if (e_ != cudaSuccess) {                                                                      \
+            char buf_[512];                                                                           \
+            snprintf(buf_, sizeof buf_, "%s failed at %s:%d: %s", #call, __FILE__, __LINE__,          \
+                     cudaGetErrorString(e_));                                                         \
+            throw Error(e_ == cudaErrorMemoryAllocation ? GPHMM_ERR_NOMEM : GPHMM_ERR_CUDA, buf_);    \
+        }                                                                                             \
+    } while (0)
+
+double now_ms() {
+    using namespace std::chrono;
+    return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
+}
+
+// ---- tables (PairHMMModel.java:86-94, QualityUtils.java:51-57, MathUtils.java:406-423,467-480) ----
+struct Tables {
+    std::vector<double> eps;  // 256 entries, [255] unused
+    std::vector<double> m2m;  // triangular, (MAX_QUAL+1)(MAX_QUAL+2)/2
+    Tables() : eps(256, 0.0), m2m(((MAX_QUAL + 1) * (MAX_QUAL + 2)) >> 1) {
+        for (int q = 0; q <= MAX_QUAL; ++q) eps[q] = std::pow(10.0, (double)q / -10.0);
+        // Jacobian-logarithm table: step 1e-4, cut-off 8.0 log10 units
+        const double step = 0.0001, inv_step = 1.0 / step, tol = 8.0;
+        const int n = (int)(tol / step) + 1;
+        std::vector<double> jac(n);
+        for (int k = 0; k < n; ++k) jac[k] = std::log10(1.0 + std::pow(10.0, -k * step));
+        auto approx_sum = [&](double a, double b) {
+            if (a > b) std::swap(a, b);
+            if (a == -INFINITY) return b;
+            const double diff = b - a;
+            if (!(diff < tol)) return b;
+            const double d = diff * inv_step;
+            const int idx = d > 0.0 ? (int)(d + 0.5) : (int)(d - 0.5);
+            return b + jac[idx];
+        };
+        const double inv_ln10 = 1.0 / std::log(10.0);
+        for (int i = 0, off = 0; i <= MAX_QUAL; off += ++i)
+            for (int j = 0; j <= i; ++j) {
+                const double ls = approx_sum(-0.1 * i, -0.1 * j);
+                const double l10 = std::log1p(-std::min(1.0, std::pow(10.0, ls))) * inv_ln10;
+                m2m[off + j] = std::pow(10.0, l10);
+            }
+    }
+};
+const Tables &tables() {
+    static Tables t;
+    return t;
+}
+
+// ---- a growable device / pinned buffer ----
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    void reserve(size_t n) {
+        if (n <= cap) return;
+        if (p) CK(cudaFree(p));
+        p = nullptr; cap = 0;
+        size_t want = std::max(n, (size_t)1 << 16);
+        want += want / 4;
+        CK(cudaMalloc(&p, want));
+        cap = want;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+struct PinBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    void reserve(size_t n) {
+        if (n <= cap) return;
+        if (p) CK(cudaFreeHost(p));
+        p = nullptr; cap = 0;
+        size_t want = std::max(n, (size_t)1 << 16);
+        want += want / 4;
+        CK(cudaMallocHost(&p, want));
+        cap = want;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+constexpr int N_FP32_BUCKETS = 9;  // K = 1..8 plain, bucket 8 = striped K=8 (reads of 256+ bases)
+constexpr int N_COUNTERS = 16;     // [0..8] fp32 buckets, [9] fp64 queue, [10] n_rescue, [11] forced fp64 queue
+
+// Host-side plan of one device chunk: which units, and every metadata array the kernels need.
+struct ChunkPlan {
+    int64_t u0 = 0, u1 = 0;          // unit range in the batch
+    int64_t r_lo = 0, r_hi = 0;      // read span in the batch
+    int64_t base_lo = 0, base_hi = 0;  // byte span of the five per-base arrays
+    uint32_t n_pairs = 0;
+    int64_t cells = 0;
+    uint32_t max_stream_len = 0, max_hap_len = 0;
+    int n_codes = 7;
+    uint8_t code_byte[MAX_CODES];
+    std::vector<uint32_t> read_off;        // span-local, n_reads_span + 1
+    std::vector<uint8_t> streams;
+    std::vector<uint32_t> hap_len, hap_stream_off;
+    std::vector<UnitDesc> units;
+    std::vector<Task> tasks;               // bucket-sorted
+    uint32_t bucket_begin[N_FP32_BUCKETS + 1];
+};
+
+int ceil_log2(uint32_t v) {
+    int lg = 0;
+    while ((1u << lg) < v) ++lg;
+    return lg;
+}
+
+void validate_batch(const gphmm_batch *b) {
+    if (!b) throw Error(GPHMM_ERR_INVALID_ARG, "batch is null");
+    if (b->n_units < 0 || b->n_reads < 0 || b->n_haps < 0) throw Error(GPHMM_ERR_INVALID_ARG, "negative count");
+    if (b->n_units == 0) return;
+    if (!b->units || !b->read_off || !b->hap_off) throw Error(GPHMM_ERR_INVALID_ARG, "null offsets/units");
+    for (int64_t r = 0; r < b->n_reads; ++r)
+        if (b->read_off[r + 1] < b->read_off[r]) throw Error(GPHMM_ERR_INVALID_ARG, "read_off not monotone");
+    for (int64_t h = 0; h < b->n_haps; ++h)
+        if (b->hap_off[h + 1] <= b->hap_off[h])
+            throw Error(GPHMM_ERR_INVALID_ARG, "zero-length haplotype (PairHMM.initialize requires haplotypeMaxLength > 0)");
+    for (int64_t u = 0; u < b->n_units; ++u) {
+        const gphmm_unit &un = b->units[u];
+        if (un.read_begin < 0 || un.read_end < un.read_begin || un.read_end > b->n_reads || un.hap_begin < 0 ||
+            un.hap_end < un.hap_begin || un.hap_end > b->n_haps || un.out_off < 0)
+            throw Error(GPHMM_ERR_INVALID_ARG, "unit range out of bounds");
+    }
+    if (b->n_reads > 0 && b->read_off[b->n_reads] > 0 &&
+        (!b->read_bases || !b->base_q || !b->ins_q || !b->del_q || !b->gcp))
+        throw Error(GPHMM_ERR_INVALID_ARG, "null read array");
+    if (b->n_haps > 0 && !b->hap_bases) throw Error(GPHMM_ERR_INVALID_ARG, "null hap_bases");
+}
+
+// Greedy split of the unit list into chunks bounded by cells and staged bytes.
+std::vector<std::pair<int64_t, int64_t>> split_units(const gphmm_batch *b, int64_t chunk_cells, int64_t chunk_bytes) {
+    std::vector<std::pair<int64_t, int64_t>> out;
+    int64_t u = 0;
+    while (u < b->n_units) {
+        int64_t cells = 0, bytes = 0, pairs = 0, u_end = u;
+        int64_t r_lo = INT64_MAX, r_hi = 0;
+        while (u_end < b->n_units) {
+            const gphmm_unit &un = b->units[u_end];
+            const int64_t nr = un.read_end - un.read_begin, nh = un.hap_end - un.hap_begin;
+            const int64_t rb = nr ? b->read_off[un.read_end] - b->read_off[un.read_begin] : 0;
+            const int64_t hb = nh ? b->hap_off[un.hap_end] - b->hap_off[un.hap_begin] : 0;
+            const int64_t n_lo = std::min(r_lo, nr ? un.read_begin : r_lo), n_hi = std::max(r_hi, nr ? un.read_end : r_hi);
+            const int64_t span = n_hi > n_lo ? b->read_off[n_hi] - b->read_off[n_lo] : 0;
+            const int64_t c = rb * hb;
+            if (u_end > u && (cells + c > chunk_cells || span * 5 + bytes + hb > chunk_bytes || pairs + nr * nh > (int64_t)1 << 25))
+                break;
+            cells += c; bytes += hb + nh; pairs += nr * nh;
+            r_lo = n_lo; r_hi = n_hi;
+            ++u_end;
+        }
+        const int64_t span = r_hi > r_lo ? b->read_off[r_hi] - b->read_off[r_lo] : 0;
+        if (span >= ((int64_t)1 << 31) || bytes >= ((int64_t)1 << 31) || pairs >= ((int64_t)1 << 28))
+            throw Error(GPHMM_ERR_TOO_LARGE, "a single unit exceeds the per-chunk device budget");
+        out.emplace_back(u, u_end);
+        u = u_end;
+    }
+    return out;
+}
+
+void plan_chunk(const gphmm_batch *b, int64_t u0, int64_t u1, bool force_fp64, ChunkPlan &c) {
+    c.u0 = u0; c.u1 = u1;
+    c.r_lo = INT64_MAX; c.r_hi = 0;
+    for (int64_t u = u0; u < u1; ++u) {
+        const gphmm_unit &un = b->units[u];
+        if (un.read_end > un.read_begin) { c.r_lo = std::min(c.r_lo, un.read_begin); c.r_hi = std::max(c.r_hi, un.read_end); }
+    }
+    if (c.r_hi <= c.r_lo) { c.r_lo = c.r_hi = 0; }
+    c.base_lo = b->n_reads ? b->read_off[c.r_lo] : 0;
+    c.base_hi = b->n_reads ? b->read_off[c.r_hi] : 0;
+    const int64_t n_span = c.r_hi - c.r_lo;
+    c.read_off.resize(n_span + 1);
+    for (int64_t r = 0; r <= n_span; ++r) c.read_off[r] = (uint32_t)(b->read_off[c.r_lo + r] - c.base_lo);
+
+    // haplotype alphabet of the chunk: A C G T N are fixed codes, any other byte value gets the next free code
+    int16_t lut[256];
+    for (int i = 0; i < 256; ++i) lut[i] = -1;
+    memset(c.code_byte, 0, sizeof c.code_byte);
+    const char fixed[5] = {'A', 'C', 'G', 'T', 'N'};
+    for (int i = 0; i < 5; ++i) { lut[(uint8_t)fixed[i]] = (int16_t)(CODE_FIRST_BASE + i); c.code_byte[CODE_FIRST_BASE + i] = (uint8_t)fixed[i]; }
+    c.n_codes = CODE_FIRST_BASE + 5;
+
+    c.streams.clear(); c.hap_len.clear(); c.hap_stream_off.clear(); c.units.clear(); c.tasks.clear();
+    c.n_pairs = 0; c.cells = 0; c.max_stream_len = 0; c.max_hap_len = 0;
+    std::vector<Task> raw;
+    std::vector<uint8_t> bucket_of;
+    uint32_t bucket_count[N_FP32_BUCKETS] = {0};
+    for (int64_t u = u0; u < u1; ++u) {
+        const gphmm_unit &un = b->units[u];
+        const uint32_t nr = (uint32_t)(un.read_end - un.read_begin), nh = (uint32_t)(un.hap_end - un.hap_begin);
+        UnitDesc d;
+        d.read_first = nr ? (uint32_t)(un.read_begin - c.r_lo) : 0;
+        d.n_reads = nr;
+        d.hap_first = (uint32_t)c.hap_len.size();
+        d.n_haps = nh;
+        d.out_base = c.n_pairs;
+        d.pad0 = d.pad1 = 0;
+        const uint32_t stream_off = (uint32_t)c.streams.size();
+        uint32_t max_h = 1;
+        int64_t sum_h = 0;
+        for (int64_t h = un.hap_begin; h < un.hap_end; ++h) {
+            const int64_t ho = b->hap_off[h];
+            const uint32_t H = (uint32_t)(b->hap_off[h + 1] - ho);
+            c.hap_len.push_back(H);
+            c.hap_stream_off.push_back((uint32_t)c.streams.size());
+            for (uint32_t j = 0; j < H; ++j) {
+                const uint8_t y = b->hap_bases[ho + j];
+                if (lut[y] < 0) {
+                    if (c.n_codes >= MAX_CODES) throw Error(GPHMM_ERR_ALPHABET, "too many distinct haplotype byte values");
+                    lut[y] = (int16_t)c.n_codes;
+                    c.code_byte[c.n_codes++] = y;
+                }
+                c.streams.push_back((uint8_t)lut[y]);
+            }
+            c.streams.push_back((uint8_t)CODE_END);
+            max_h = std::max(max_h, H);
+            sum_h += H;
+        }
+        const uint32_t stream_len = (uint32_t)c.streams.size() - stream_off;
+        c.max_stream_len = std::max(c.max_stream_len, stream_len);
+        c.max_hap_len = std::max(c.max_hap_len, max_h);
+        d.c0_exp = (force_fp64 ? C0_BASE_EXP_F64 : C0_BASE_EXP_F32) - ceil_log2(max_h);
+        c.units.push_back(d);
+        if (nh == 0) continue;
+        for (uint32_t r = 0; r < nr; ++r) {
+            const uint32_t rl = d.read_first + r;
+            const uint32_t R = c.read_off[rl + 1] - c.read_off[rl];
+            Task t;
+            t.read = rl; t.stream_off = stream_off; t.stream_len = stream_len;
+            t.out_base = d.out_base + r * nh; t.c0_exp = d.c0_exp; t.n_haps = nh; t.pad0 = t.pad1 = 0;
+            const uint32_t k = R / 32 + 1;
+            const uint8_t bucket = force_fp64 ? 0 : (k <= 8 ? (uint8_t)(k - 1) : (uint8_t)8);
+            raw.push_back(t);
+            bucket_of.push_back(bucket);
+            ++bucket_count[bucket];
+            c.cells += (int64_t)R * sum_h;
+        }
+        c.n_pairs += nr * nh;
+    }
+    // counting sort by bucket (stable: unit order is kept inside a bucket)
+    c.bucket_begin[0] = 0;
+    for (int k = 0; k < N_FP32_BUCKETS; ++k) c.bucket_begin[k + 1] = c.bucket_begin[k] + bucket_count[k];
+    c.tasks.resize(raw.size());
+    uint32_t cursor[N_FP32_BUCKETS];
+    for (int k = 0; k < N_FP32_BUCKETS; ++k) cursor[k] = c.bucket_begin[k];
+    for (size_t i = 0; i < raw.size(); ++i) c.tasks[cursor[bucket_of[i]]++] = raw[i];
+}
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// Device-side image of a chunk: one metadata blob + the five read arrays + work buffers.
+struct DeviceChunk {
+    DevBuf reads;   // 5 * span bytes (each array padded to 16 B)
+    DevBuf meta;    // read_off | streams | hap_len | hap_stream_off | units | tasks
+    DevBuf work;    // sums(float or double) | out(double) | rescue tasks | rescue sums | counters | err
+    DevBuf bnd;     // boundary rows of striped kernels
+    PinBuf h_meta;  // pinned image of meta
+    PinBuf h_reads; // pinned bounce buffer when the caller's arrays are pageable
+    PinBuf h_out;   // pinned result buffer (out doubles + counters + err)
+    size_t read_stride = 0;
+    size_t off_read_off = 0, off_streams = 0, off_hap_len = 0, off_hap_stream_off = 0, off_units = 0, off_tasks = 0, meta_bytes = 0;
+    size_t off_sums = 0, off_out = 0, off_rtasks = 0, off_rsums = 0, off_counters = 0, off_err = 0, work_bytes = 0;
+    cudaEvent_t ev_start = nullptr, ev_f32 = nullptr, ev_f64 = nullptr, ev_done = nullptr;
+    bool busy = false;
+    void release() {
+        reads.release(); meta.release(); work.release(); bnd.release(); h_meta.release(); h_reads.release(); h_out.release();
+        if (ev_start) cudaEventDestroy(ev_start);
+        if (ev_f32) cudaEventDestroy(ev_f32);
+        if (ev_f64) cudaEventDestroy(ev_f64);
+        if (ev_done) cudaEventDestroy(ev_done);
+        ev_start = ev_f32 = ev_f64 = ev_done = nullptr;
+    }
+};
+
+struct KernelInfo {
+    const void *fn = nullptr;
+    int ctas_per_sm = 0;
+    size_t smem = 0;
+};
+
+template <typename T, int K, bool S> KernelInfo kernel_info(int n_codes) {
+    KernelInfo ki;
+    auto fn = phmm_forward_kernel<T, K, S>;
+    ki.fn = (const void *)fn;
+    ki.smem = prior_table_bytes<T, K>(n_codes);
+    if (ki.smem > 48 * 1024) CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ki.smem));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ki.ctas_per_sm, fn, 32, ki.smem));
+    if (ki.ctas_per_sm < 1) throw Error(GPHMM_ERR_ALPHABET, "prior table does not fit in shared memory");
+    return ki;
+}
+
+KernelInfo fp32_kernel(int bucket, int n_codes) {
+    switch (bucket) {
+        case 0: return kernel_info<float, 1, false>(n_codes);
+        case 1: return kernel_info<float, 2, false>(n_codes);
+        case 2: return kernel_info<float, 3, false>(n_codes);
+        case 3: return kernel_info<float, 4, false>(n_codes);
+        case 4: return kernel_info<float, 5, false>(n_codes);
+        case 5: return kernel_info<float, 6, false>(n_codes);
+        case 6: return kernel_info<float, 7, false>(n_codes);
+        case 7: return kernel_info<float, 8, false>(n_codes);
+        default: return kernel_info<float, 8, true>(n_codes);
+    }
+}
+KernelInfo fp64_kernel(int n_codes) { return kernel_info<double, 4, true>(n_codes); }
+
+struct Stats {
+    std::mutex mu;
+    gphmm_stats s{};
+};
+
+struct Device {
+    int ordinal = 0;
+    int n_sms = 0;
+    std::map<int, KernelInfo> kinfo;  // (bucket, n_codes) -> occupancy / smem, queried once
+    const KernelInfo &info(int bucket, int n_codes) {
+        const int key = bucket * 1024 + n_codes;
+        auto it = kinfo.find(key);
+        if (it == kinfo.end()) it = kinfo.emplace(key, bucket < N_FP32_BUCKETS ? fp32_kernel(bucket, n_codes) : fp64_kernel(n_codes)).first;
+        return it->second;
+    }
+    cudaStream_t streams[2] = {nullptr, nullptr};
+    DeviceChunk slots[2];
+    DevBuf m2m;
+    cudaEvent_t ev_step0 = nullptr, ev_step1 = nullptr;  // bracket a whole run_prepared step on streams[0]
+    void init(int ord) {
+        ordinal = ord;
+        CK(cudaSetDevice(ord));
+        cudaDeviceProp prop;
+        CK(cudaGetDeviceProperties(&prop, ord));
+        if (prop.major != 10) throw Error(GPHMM_ERR_NO_DEVICE, "device is not compute capability 10.x (sm_100a kernels only)");
+        n_sms = prop.multiProcessorCount;
+        const Tables &t = tables();
+        CK(cudaMemcpyToSymbol(c_eps, t.eps.data(), 256 * sizeof(double)));
+        m2m.reserve(t.m2m.size() * sizeof(double));
+        CK(cudaMemcpy(m2m.p, t.m2m.data(), t.m2m.size() * sizeof(double), cudaMemcpyHostToDevice));
+        CK(cudaEventCreate(&ev_step0));
+        CK(cudaEventCreate(&ev_step1));
+        for (int i = 0; i < 2; ++i) {
+            CK(cudaStreamCreateWithFlags(&streams[i], cudaStreamNonBlocking));
+            CK(cudaEventCreate(&slots[i].ev_start));
+            CK(cudaEventCreate(&slots[i].ev_f32));
+            CK(cudaEventCreate(&slots[i].ev_f64));
+            CK(cudaEventCreate(&slots[i].ev_done));
+        }
+    }
+    void release() {
+        cudaSetDevice(ordinal);
+        for (int i = 0; i < 2; ++i) {
+            slots[i].release();
+            if (streams[i]) cudaStreamDestroy(streams[i]);
+            streams[i] = nullptr;
+        }
+        m2m.release();
+        if (ev_step0) cudaEventDestroy(ev_step0);
+        if (ev_step1) cudaEventDestroy(ev_step1);
+        ev_step0 = ev_step1 = nullptr;
+    }
+};
+
+bool is_pinned(const void *p) {
+    if (!p) return false;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+
+struct RunOptions {
+    bool force_fp64 = false;
+    bool tristate_off = false;
+};
+
+// Lay the chunk out on the device and copy its inputs (async on `st`).
+void upload_chunk(Device &dev, DeviceChunk &dc, const gphmm_batch *b, const ChunkPlan &c, cudaStream_t st, bool force_fp64,
+                  Stats &stats) {
+    const double t0 = now_ms();
+    const size_t span = (size_t)(c.base_hi - c.base_lo);
+    dc.read_stride = align_up(span, 16);
+    dc.reads.reserve(std::max<size_t>(dc.read_stride * 5, 16));
+    // metadata blob
+    size_t o = 0;
+    dc.off_read_off = o; o = align_up(o + c.read_off.size() * 4, 16);
+    dc.off_streams = o; o = align_up(o + c.streams.size() + 64, 16);
+    dc.off_hap_len = o; o = align_up(o + c.hap_len.size() * 4, 16);
+    dc.off_hap_stream_off = o; o = align_up(o + c.hap_stream_off.size() * 4, 16);
+    dc.off_units = o; o = align_up(o + c.units.size() * sizeof(UnitDesc), 16);
+    dc.off_tasks = o; o = align_up(o + c.tasks.size() * sizeof(Task), 16);
+    dc.meta_bytes = std::max<size_t>(o, 16);
+    dc.meta.reserve(dc.meta_bytes);
+    dc.h_meta.reserve(dc.meta_bytes);
+    uint8_t *hm = (uint8_t *)dc.h_meta.p;
+    memcpy(hm + dc.off_read_off, c.read_off.data(), c.read_off.size() * 4);
+    memcpy(hm + dc.off_streams, c.streams.data(), c.streams.size());
+    memset(hm + dc.off_streams + c.streams.size(), CODE_NULL, 64);
+    memcpy(hm + dc.off_hap_len, c.hap_len.data(), c.hap_len.size() * 4);
+    memcpy(hm + dc.off_hap_stream_off, c.hap_stream_off.data(), c.hap_stream_off.size() * 4);
+    memcpy(hm + dc.off_units, c.units.data(), c.units.size() * sizeof(UnitDesc));
+    memcpy(hm + dc.off_tasks, c.tasks.data(), c.tasks.size() * sizeof(Task));
+    // work buffers
+    const size_t np = std::max<uint32_t>(c.n_pairs, 1);
+    o = 0;
+    dc.off_sums = o; o = align_up(o + np * (force_fp64 ? 8 : 4), 16);
+    dc.off_out = o; o = align_up(o + np * 8, 16);
+    dc.off_counters = o; o = align_up(o + N_COUNTERS * 4, 16);
+    dc.off_err = o; o = align_up(o + 16, 16);
+    const size_t d2h_bytes = o;  // out | counters | err are contiguous and downloaded together
+    dc.off_rtasks = o; o = align_up(o + (force_fp64 ? 0 : np * sizeof(Task)), 16);
+    dc.off_rsums = o; o = align_up(o + (force_fp64 ? 0 : np * 8), 16);
+    dc.work_bytes = o;
+    dc.work.reserve(dc.work_bytes);
+    dc.h_out.reserve(d2h_bytes);
+
+    const uint8_t *src[5] = {b->read_bases, b->base_q, b->ins_q, b->del_q, b->gcp};
+    int64_t h2d = 0;
+    if (span > 0) {
+        bool pinned = true;
+        for (int a = 0; a < 5; ++a) pinned = pinned && is_pinned(src[a] + c.base_lo);
+        if (!pinned) dc.h_reads.reserve(dc.read_stride * 5);
+        for (int a = 0; a < 5; ++a) {
+            const void *from = src[a] + c.base_lo;
+            if (!pinned) {
+                memcpy((uint8_t *)dc.h_reads.p + a * dc.read_stride, from, span);
+                from = (uint8_t *)dc.h_reads.p + a * dc.read_stride;
+            }
+            CK(cudaMemcpyAsync((uint8_t *)dc.reads.p + a * dc.read_stride, from, span, cudaMemcpyHostToDevice, st));
+            h2d += (int64_t)span;
+        }
+    }
+    CK(cudaMemcpyAsync(dc.meta.p, dc.h_meta.p, dc.meta_bytes, cudaMemcpyHostToDevice, st));
+    h2d += (int64_t)dc.meta_bytes;
+    {
+        std::lock_guard<std::mutex> lk(stats.mu);
+        stats.s.h2d_bytes += h2d;
+        stats.s.host_stage_ms += now_ms() - t0;
+    }
+    (void)dev;
+}
+
+// Queue every kernel of the chunk on `st` (no host sync).  Returns the number of launches.
+int launch_chunk(Device &dev, DeviceChunk &dc, const ChunkPlan &c, cudaStream_t st, const RunOptions &opt, bool download) {
+    int launches = 0;
+    uint8_t *meta = (uint8_t *)dc.meta.p, *work = (uint8_t *)dc.work.p;
+    uint32_t *counters = (uint32_t *)(work + dc.off_counters);
+    CK(cudaMemsetAsync(work + dc.off_counters, 0, (dc.off_err + 16) - dc.off_counters, st));
+    CK(cudaEventRecord(dc.ev_start, st));
+
+    KernelArgs ka;
+    memset(&ka, 0, sizeof ka);
+    ka.rd_bases = (const uint8_t *)dc.reads.p;
+    ka.rd_q = ka.rd_bases + dc.read_stride;
+    ka.rd_i = ka.rd_q + dc.read_stride;
+    ka.rd_d = ka.rd_i + dc.read_stride;
+    ka.rd_c = ka.rd_d + dc.read_stride;
+    ka.read_off = (const uint32_t *)(meta + dc.off_read_off);
+    ka.streams = meta + dc.off_streams;
+    ka.m2m = (const double *)dev.m2m.p;
+    ka.err = (int *)(work + dc.off_err);
+    ka.n_codes = c.n_codes;
+    ka.tristate_off = opt.tristate_off ? 1 : 0;
+    memcpy(ka.code_byte, c.code_byte, sizeof ka.code_byte);
+
+    EpilogueArgs ea;
+    memset(&ea, 0, sizeof ea);
+    ea.units = (const UnitDesc *)(meta + dc.off_units);
+    ea.n_units = (uint32_t)c.units.size();
+    ea.hap_len = (const uint32_t *)(meta + dc.off_hap_len);
+    ea.hap_stream_off = (const uint32_t *)(meta + dc.off_hap_stream_off);
+    ea.sums = work + dc.off_sums;
+    ea.out = (double *)(work + dc.off_out);
+    ea.rescue_tasks = (Task *)(work + dc.off_rtasks);
+    ea.n_rescue = counters + 10;
+    ea.rescue_capacity = std::max<uint32_t>(c.n_pairs, 1);
+
+    const uint32_t n_tasks_total = (uint32_t)c.tasks.size();
+    constexpr int FP64_BUCKET = N_FP32_BUCKETS;  // key of the <double, 4, striped> kernel in Device::info
+
+    // Size the boundary buffer for every striped launch of this chunk before anything is queued.
+    {
+        size_t need = 16;
+        if (!opt.force_fp64) {
+            const uint32_t n8 = c.bucket_begin[9] - c.bucket_begin[8];
+            if (n8) {
+                const KernelInfo &ki = dev.info(8, c.n_codes);
+                need = std::max(need, (size_t)std::min<uint32_t>(n8, (uint32_t)(dev.n_sms * ki.ctas_per_sm)) * c.max_stream_len * sizeof(Bnd<float>));
+            }
+            if (n_tasks_total) {
+                const KernelInfo &ki = dev.info(FP64_BUCKET, c.n_codes);
+                need = std::max(need, (size_t)std::min<uint32_t>(c.n_pairs, (uint32_t)(dev.n_sms * ki.ctas_per_sm)) * (c.max_hap_len + 1) * sizeof(Bnd<double>));
+            }
+        } else if (n_tasks_total) {
+            const KernelInfo &ki = dev.info(FP64_BUCKET, c.n_codes);
+            need = std::max(need, (size_t)std::min<uint32_t>(n_tasks_total, (uint32_t)(dev.n_sms * ki.ctas_per_sm)) * c.max_stream_len * sizeof(Bnd<double>));
+        }
+        dc.bnd.reserve(need);
+    }
+
+    if (!opt.force_fp64) {
+        for (int k = 0; k < N_FP32_BUCKETS; ++k) {
+            const uint32_t n = c.bucket_begin[k + 1] - c.bucket_begin[k];
+            if (!n) continue;
+            const KernelInfo &ki = dev.info(k, c.n_codes);
+            const uint32_t grid = std::min<uint32_t>(n, (uint32_t)(dev.n_sms * ki.ctas_per_sm));
+            ka.tasks = (const Task *)(meta + dc.off_tasks) + c.bucket_begin[k];
+            ka.n_tasks = n;
+            ka.n_tasks_ptr = nullptr;
+            ka.counter = counters + k;
+            ka.sums = work + dc.off_sums;
+            ka.bnd = k == 8 ? dc.bnd.p : nullptr;
+            ka.bnd_stride = k == 8 ? c.max_stream_len : 0;
+            void *args[] = {&ka};
+            CK(cudaLaunchKernel(ki.fn, dim3(grid), dim3(32), args, ki.smem, st));
+            ++launches;
+        }
+        CK(cudaEventRecord(dc.ev_f32, st));
+        if (ea.n_units) {
+            phmm_epilogue_f32<<<std::min<uint32_t>(ea.n_units, 4096), 128, 0, st>>>(ea);
+            CK(cudaGetLastError());
+            ++launches;
+        }
+        // fp64 redo of the rescue list: persistent grid, task count read on the device
+        if (n_tasks_total) {
+            const KernelInfo &ki = dev.info(FP64_BUCKET, c.n_codes);
+            const uint32_t grid = std::min<uint32_t>(c.n_pairs, (uint32_t)(dev.n_sms * ki.ctas_per_sm));
+            ka.tasks = (const Task *)(work + dc.off_rtasks);
+            ka.n_tasks = 0;
+            ka.n_tasks_ptr = counters + 10;
+            ka.counter = counters + 9;
+            ka.sums = work + dc.off_rsums;
+            ka.bnd = dc.bnd.p;
+            ka.bnd_stride = c.max_hap_len + 1;
+            void *args[] = {&ka};
+            CK(cudaLaunchKernel(ki.fn, dim3(grid), dim3(32), args, ki.smem, st));
+            ++launches;
+            phmm_epilogue_rescue<<<std::min<uint32_t>((c.n_pairs + 127) / 128, 1024), 128, 0, st>>>(
+                (const Task *)(work + dc.off_rtasks), counters + 10, ea.rescue_capacity, (const double *)(work + dc.off_rsums), ea.out);
+            CK(cudaGetLastError());
+            ++launches;
+        }
+        CK(cudaEventRecord(dc.ev_f64, st));
+    } else {
+        CK(cudaEventRecord(dc.ev_f32, st));
+        if (n_tasks_total) {
+            const KernelInfo &ki = dev.info(FP64_BUCKET, c.n_codes);
+            const uint32_t grid = std::min<uint32_t>(n_tasks_total, (uint32_t)(dev.n_sms * ki.ctas_per_sm));
+            ka.tasks = (const Task *)(meta + dc.off_tasks);
+            ka.n_tasks = n_tasks_total;
+            ka.n_tasks_ptr = nullptr;
+            ka.counter = counters + 11;
+            ka.sums = work + dc.off_sums;
+            ka.bnd = dc.bnd.p;
+            ka.bnd_stride = c.max_stream_len;
+            void *args[] = {&ka};
+            CK(cudaLaunchKernel(ki.fn, dim3(grid), dim3(32), args, ki.smem, st));
+            ++launches;
+        }
+        if (ea.n_units) {
+            phmm_epilogue_f64_units<<<std::min<uint32_t>(ea.n_units, 4096), 128, 0, st>>>(ea);
+            CK(cudaGetLastError());
+            ++launches;
+        }
+        CK(cudaEventRecord(dc.ev_f64, st));
+    }
+    if (download) {
+        const size_t bytes = (dc.off_err + 16) - dc.off_out;
+        CK(cudaMemcpyAsync(dc.h_out.p, work + dc.off_out, bytes, cudaMemcpyDeviceToHost, st));
+    }
+    CK(cudaEventRecord(dc.ev_done, st));
+    return launches;
+}
+
+// After the chunk's stream work completed: check the error flag, scatter results, account stats.
+void finish_chunk(DeviceChunk &dc, const gphmm_batch *b, const ChunkPlan &c, double *out, Stats &stats, bool downloaded,
+                  bool count_device_ms = true) {
+    CK(cudaEventSynchronize(dc.ev_done));
+    float ms32 = 0, ms64 = 0, msall = 0;
+    CK(cudaEventElapsedTime(&ms32, dc.ev_start, dc.ev_f32));
+    CK(cudaEventElapsedTime(&ms64, dc.ev_f32, dc.ev_f64));
+    CK(cudaEventElapsedTime(&msall, dc.ev_start, dc.ev_done));
+    int64_t rescued = 0;
+    if (downloaded) {
+        const uint8_t *ho = (const uint8_t *)dc.h_out.p;
+        const uint32_t *counters = (const uint32_t *)(ho + (dc.off_counters - dc.off_out));
+        const int err = *(const int *)(ho + (dc.off_err - dc.off_out));
+        if (err) throw Error(GPHMM_ERR_BAD_QUAL, "quality score out of range: ins/del/gcp > 127 or base qual 255");
+        rescued = counters[10];
+        if (out) {
+            const double *res = (const double *)ho;
+            for (int64_t u = c.u0; u < c.u1; ++u) {
+                const UnitDesc &d = c.units[u - c.u0];
+                const size_t n = (size_t)d.n_reads * d.n_haps;
+                if (n) memcpy(out + b->units[u].out_off, res + d.out_base, n * sizeof(double));
+            }
+        }
+    }
+    std::lock_guard<std::mutex> lk(stats.mu);
+    stats.s.pairs += c.n_pairs;
+    stats.s.cells += c.cells;
+    stats.s.rescued_pairs += rescued;
+    stats.s.fp32_kernel_ms += ms32;
+    stats.s.fp64_kernel_ms += ms64;
+    if (count_device_ms) stats.s.device_ms += msall;
+    if (downloaded) stats.s.d2h_bytes += (int64_t)((dc.off_err + 16) - dc.off_out);
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+struct gphmm_prepared {
+    struct Part {
+        int device_index;
+        ChunkPlan plan;
+        DeviceChunk dc;
+    };
+    std::vector<std::unique_ptr<Part>> parts;
+    // out_off per unit is the only thing run_prepared needs from the original batch
+    std::vector<gphmm_unit> units;
+};
+
+struct gphmm {
+    gphmm_config cfg{};
+    std::vector<int> ordinals;
+    std::vector<std::unique_ptr<Device>> devices;
+    std::string last_error = "";
+    Stats stats;
+    std::mutex run_mu;  // one batch at a time per handle (compute vs. the async worker)
+    // async queue
+    struct Job {
+        uint64_t ticket;
+        std::vector<uint8_t> read_bases, base_q, ins_q, del_q, gcp, hap_bases;
+        std::vector<int64_t> read_off, hap_off;
+        std::vector<gphmm_unit> units;
+        double *out;
+        int rc = 1;  // 1 = pending
+        std::string err;
+    };
+    std::mutex q_mu;
+    std::condition_variable q_cv, done_cv;
+    std::deque<std::shared_ptr<Job>> queue;
+    std::vector<std::shared_ptr<Job>> finished;
+    uint64_t next_ticket = 1;
+    std::thread worker;
+    bool stop = false;
+
+    int64_t chunk_cells() const { return cfg.chunk_cells > 0 ? cfg.chunk_cells : (int64_t)100000000000LL; }
+    int64_t chunk_bytes() const { return cfg.chunk_bytes > 0 ? cfg.chunk_bytes : (int64_t)256 << 20; }
+};
+
+namespace {
+
+// Process chunks [ci, ...) of a batch on one device with two stream slots; chunks are claimed from a
+// shared cursor so that several devices drain the same batch (the host-side work queue of SURVEY 8e).
+void device_loop(gphmm *h, Device &dev, const gphmm_batch *b, const std::vector<std::pair<int64_t, int64_t>> &chunks,
+                 std::atomic<size_t> &cursor, double *out, std::string &err, int &rc) {
+    try {
+        CK(cudaSetDevice(dev.ordinal));
+        RunOptions opt;
+        opt.force_fp64 = h->cfg.force_fp64 != 0;
+        opt.tristate_off = h->cfg.tristate_off != 0;
+        ChunkPlan plans[2];
+        bool inflight[2] = {false, false};
+        int slot = 0;
+        int launches = 0;
+        for (;;) {
+            const size_t ci = cursor.fetch_add(1);
+            if (ci >= chunks.size()) break;
+            if (inflight[slot]) {
+                finish_chunk(dev.slots[slot], b, plans[slot], out, h->stats, true);
+                inflight[slot] = false;
+            }
+            plan_chunk(b, chunks[ci].first, chunks[ci].second, opt.force_fp64, plans[slot]);
+            upload_chunk(dev, dev.slots[slot], b, plans[slot], dev.streams[slot], opt.force_fp64, h->stats);
+            launches += launch_chunk(dev, dev.slots[slot], plans[slot], dev.streams[slot], opt, true);
+            inflight[slot] = true;
+            slot ^= 1;
+        }
+        for (int s = 0; s < 2; ++s) {
+            if (inflight[slot]) {
+                finish_chunk(dev.slots[slot], b, plans[slot], out, h->stats, true);
+                inflight[slot] = false;
+            }
+            slot ^= 1;
+        }
+        std::lock_guard<std::mutex> lk(h->stats.mu);
+        h->stats.s.kernel_launches += launches;
+    } catch (const Error &e) {
+        rc = e.code;
+        err = e.what();
+        // leave the device in a clean state for the next call
+        cudaDeviceSynchronize();
+        cudaGetLastError();
+    }
+}
+
+int run_batch(gphmm *h, const gphmm_batch *b, double *out) {
+    std::lock_guard<std::mutex> run_lk(h->run_mu);
+    const double t0 = now_ms();
+    validate_batch(b);
+    if (b->n_units == 0) return GPHMM_OK;
+    if (!out) throw Error(GPHMM_ERR_INVALID_ARG, "out is null");
+    auto chunks = split_units(b, h->chunk_cells(), h->chunk_bytes());
+    std::atomic<size_t> cursor{0};
+    const size_t nd = h->devices.size();
+    std::vector<std::string> errs(nd);
+    std::vector<int> rcs(nd, GPHMM_OK);
+    if (nd == 1 || chunks.size() == 1) {
+        device_loop(h, *h->devices[0], b, chunks, cursor, out, errs[0], rcs[0]);
+    } else {
+        std::vector<std::thread> th;
+        for (size_t d = 0; d < nd; ++d)
+            th.emplace_back(device_loop, h, std::ref(*h->devices[d]), b, std::cref(chunks), std::ref(cursor), out,
+                            std::ref(errs[d]), std::ref(rcs[d]));
+        for (auto &t : th) t.join();
+    }
+    {
+        std::lock_guard<std::mutex> lk(h->stats.mu);
+        h->stats.s.wall_ms += now_ms() - t0;
+    }
+    for (size_t d = 0; d < nd; ++d)
+        if (rcs[d] != GPHMM_OK) throw Error(rcs[d], errs[d]);
+    return GPHMM_OK;
+}
+
+void worker_main(gphmm *h) {
+    for (;;) {
+        std::shared_ptr<gphmm::Job> job;
+        {
+            std::unique_lock<std::mutex> lk(h->q_mu);
+            h->q_cv.wait(lk, [&] { return h->stop || !h->queue.empty(); });
+            if (h->queue.empty()) return;
+            job = h->queue.front();
+        }
+        gphmm_batch b;
+        memset(&b, 0, sizeof b);
+        b.read_bases = job->read_bases.data(); b.base_q = job->base_q.data(); b.ins_q = job->ins_q.data();
+        b.del_q = job->del_q.data(); b.gcp = job->gcp.data(); b.read_off = job->read_off.data();
+        b.n_reads = (int64_t)job->read_off.size() - 1;
+        b.hap_bases = job->hap_bases.data(); b.hap_off = job->hap_off.data(); b.n_haps = (int64_t)job->hap_off.size() - 1;
+        b.units = job->units.data(); b.n_units = (int64_t)job->units.size();
+        int rc = GPHMM_OK;
+        std::string err;
+        try {
+            rc = run_batch(h, &b, job->out);
+        } catch (const Error &e) {
+            rc = e.code; err = e.what();
+        } catch (const std::exception &e) {
+            rc = GPHMM_ERR_CUDA; err = e.what();
+        }
+        {
+            std::lock_guard<std::mutex> lk(h->q_mu);
+            job->rc = rc; job->err = err;
+            h->queue.pop_front();
+            h->finished.push_back(job);
+        }
+        h->done_cv.notify_all();
+    }
+}
+
+template <typename F> int guarded(gphmm *h, F &&f) {
+    try {
+        return f();
+    } catch (const Error &e) {
+        if (h) h->last_error = e.what();
+        return e.code;
+    } catch (const std::bad_alloc &) {
+        if (h) h->last_error = "host allocation failed";
+        return GPHMM_ERR_NOMEM;
+    } catch (const std::exception &e) {
+        if (h) h->last_error = e.what();
+        return GPHMM_ERR_CUDA;
+    }
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+int gphmm_abi_version(void) { return GPHMM_ABI_VERSION; }
+
+int gphmm_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    int ok = 0;
+    for (int i = 0; i < n; ++i) {
+        int major = 0;
+        if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, i) == cudaSuccess && major == 10) ++ok;
+    }
+    return ok;
+}
+
+const char *gphmm_strerror(int code) {
+    switch (code) {
+        case GPHMM_OK: return "ok";
+        case GPHMM_ERR_INVALID_ARG: return "invalid argument";
+        case GPHMM_ERR_NO_DEVICE: return "no usable CUDA device (need compute capability 10.x)";
+        case GPHMM_ERR_CUDA: return "CUDA error";
+        case GPHMM_ERR_BAD_QUAL: return "quality score out of range";
+        case GPHMM_ERR_ALPHABET: return "haplotype alphabet too large";
+        case GPHMM_ERR_NOMEM: return "out of memory";
+        case GPHMM_ERR_BAD_TICKET: return "unknown ticket";
+        case GPHMM_ERR_TOO_LARGE: return "unit too large for one device chunk";
+        default: return "unknown error";
+    }
+}
+
+int gphmm_create(const gphmm_config *cfg, gphmm_t **out) {
+    if (!out) return GPHMM_ERR_INVALID_ARG;
+    *out = nullptr;
+    gphmm *h = nullptr;
+    try {
+        h = new gphmm();
+    } catch (...) {
+        return GPHMM_ERR_NOMEM;
+    }
+    int rc = guarded(h, [&]() -> int {
+        if (cfg) {
+            size_t n = std::min<size_t>(sizeof(gphmm_config), cfg->struct_size > 0 ? (size_t)cfg->struct_size : sizeof(gphmm_config));
+            memcpy(&h->cfg, cfg, n);
+        }
+        int n_dev = 0;
+        if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) {
+            cudaGetLastError();
+            throw Error(GPHMM_ERR_NO_DEVICE, "no CUDA device visible");
+        }
+        if (h->cfg.n_devices > 0) {
+            if (!h->cfg.devices) throw Error(GPHMM_ERR_INVALID_ARG, "devices is null");
+            for (int i = 0; i < h->cfg.n_devices; ++i) {
+                if (h->cfg.devices[i] < 0 || h->cfg.devices[i] >= n_dev) throw Error(GPHMM_ERR_NO_DEVICE, "device ordinal out of range");
+                h->ordinals.push_back(h->cfg.devices[i]);
+            }
+        } else {
+            int cur = 0;
+            CK(cudaGetDevice(&cur));
+            h->ordinals.push_back(cur);
+        }
+        h->cfg.devices = nullptr;
+        for (int ord : h->ordinals) {
+            h->devices.emplace_back(new Device());
+            h->devices.back()->init(ord);
+        }
+        CK(cudaSetDevice(h->ordinals[0]));
+        h->worker = std::thread(worker_main, h);
+        return GPHMM_OK;
+    });
+    if (rc != GPHMM_OK) {
+        for (auto &d : h->devices) d->release();
+        delete h;
+        return rc;
+    }
+    *out = h;
+    return GPHMM_OK;
+}
+
+void gphmm_destroy(gphmm_t *h) {
+    if (!h) return;
+    {
+        std::lock_guard<std::mutex> lk(h->q_mu);
+        h->stop = true;
+    }
+    h->q_cv.notify_all();
+    if (h->worker.joinable()) h->worker.join();
+    for (auto &d : h->devices) d->release();
+    delete h;
+}
+
+const char *gphmm_last_error(const gphmm_t *h) { return h ? h->last_error.c_str() : "null handle"; }
+
+int gphmm_compute(gphmm_t *h, const gphmm_batch *batch, double *out) {
+    if (!h) return GPHMM_ERR_INVALID_ARG;
+    return guarded(h, [&]() -> int { return run_batch(h, batch, out); });
+}
+
+int gphmm_submit(gphmm_t *h, const gphmm_batch *b, double *out, uint64_t *ticket) {
+    if (!h || !ticket) return GPHMM_ERR_INVALID_ARG;
+    return guarded(h, [&]() -> int {
+        validate_batch(b);
+        if (b->n_units > 0 && !out) throw Error(GPHMM_ERR_INVALID_ARG, "out is null");
+        auto job = std::make_shared<gphmm::Job>();
+        const int64_t nb = b->n_reads ? b->read_off[b->n_reads] : 0, hb = b->n_haps ? b->hap_off[b->n_haps] : 0;
+        if (b->n_units > 0) {
+            job->read_bases.assign(b->read_bases, b->read_bases + nb);
+            job->base_q.assign(b->base_q, b->base_q + nb);
+            job->ins_q.assign(b->ins_q, b->ins_q + nb);
+            job->del_q.assign(b->del_q, b->del_q + nb);
+            job->gcp.assign(b->gcp, b->gcp + nb);
+            job->hap_bases.assign(b->hap_bases, b->hap_bases + hb);
+            job->read_off.assign(b->read_off, b->read_off + b->n_reads + 1);
+            job->hap_off.assign(b->hap_off, b->hap_off + b->n_haps + 1);
+            job->units.assign(b->units, b->units + b->n_units);
+        } else {
+            job->read_off.assign(1, 0);
+            job->hap_off.assign(1, 0);
+        }
+        job->out = out;
+        {
+            std::lock_guard<std::mutex> lk(h->q_mu);
+            job->ticket = h->next_ticket++;
+            h->queue.push_back(job);
+            *ticket = job->ticket;
+        }
+        h->q_cv.notify_all();
+        return GPHMM_OK;
+    });
+}
+
+int gphmm_wait(gphmm_t *h, uint64_t ticket) {
+    if (!h) return GPHMM_ERR_INVALID_ARG;
+    std::unique_lock<std::mutex> lk(h->q_mu);
+    if (ticket == 0 || ticket >= h->next_ticket) { h->last_error = "unknown ticket"; return GPHMM_ERR_BAD_TICKET; }
+    for (;;) {
+        for (size_t i = 0; i < h->finished.size(); ++i)
+            if (h->finished[i]->ticket == ticket) {
+                auto job = h->finished[i];
+                h->finished.erase(h->finished.begin() + i);
+                if (job->rc != GPHMM_OK) h->last_error = job->err;
+                return job->rc;
+            }
+        bool pending = false;
+        for (auto &j : h->queue) pending = pending || j->ticket == ticket;
+        if (!pending) { h->last_error = "ticket already waited for"; return GPHMM_ERR_BAD_TICKET; }
+        h->done_cv.wait(lk);
+    }
+}
+
+int gphmm_prepare(gphmm_t *h, const gphmm_batch *b, gphmm_prepared_t **out) {
+    if (!h || !out) return GPHMM_ERR_INVALID_ARG;
+    *out = nullptr;
+    return guarded(h, [&]() -> int {
+        validate_batch(b);
+        std::unique_ptr<gphmm_prepared> p(new gphmm_prepared());
+        p->units.assign(b->units, b->units + b->n_units);
+        auto chunks = split_units(b, h->chunk_cells(), h->chunk_bytes());
+        const bool f64 = h->cfg.force_fp64 != 0;
+        for (size_t ci = 0; ci < chunks.size(); ++ci) {
+            std::unique_ptr<gphmm_prepared::Part> part(new gphmm_prepared::Part());
+            part->device_index = (int)(ci % h->devices.size());
+            Device &dev = *h->devices[part->device_index];
+            CK(cudaSetDevice(dev.ordinal));
+            plan_chunk(b, chunks[ci].first, chunks[ci].second, f64, part->plan);
+            CK(cudaEventCreate(&part->dc.ev_start));
+            CK(cudaEventCreate(&part->dc.ev_f32));
+            CK(cudaEventCreate(&part->dc.ev_f64));
+            CK(cudaEventCreate(&part->dc.ev_done));
+            upload_chunk(dev, part->dc, b, part->plan, dev.streams[0], f64, h->stats);
+            CK(cudaStreamSynchronize(dev.streams[0]));
+            part->dc.h_reads.release();
+            p->parts.push_back(std::move(part));
+        }
+        CK(cudaSetDevice(h->ordinals[0]));
+        *out = p.release();
+        return GPHMM_OK;
+    });
+}
+
+int gphmm_run_prepared(gphmm_t *h, gphmm_prepared_t *p, double *out) {
+    if (!h || !p) return GPHMM_ERR_INVALID_ARG;
+    return guarded(h, [&]() -> int {
+        const double t0 = now_ms();
+        RunOptions opt;
+        opt.force_fp64 = h->cfg.force_fp64 != 0;
+        opt.tristate_off = h->cfg.tristate_off != 0;
+        gphmm_batch b;
+        memset(&b, 0, sizeof b);
+        b.units = p->units.data();
+        b.n_units = (int64_t)p->units.size();
+        int launches = 0;
+        std::vector<char> used(h->devices.size(), 0);
+        for (auto &part : p->parts) {
+            Device &dev = *h->devices[part->device_index];
+            CK(cudaSetDevice(dev.ordinal));
+            if (!used[part->device_index]) {
+                CK(cudaEventRecord(dev.ev_step0, dev.streams[0]));
+                used[part->device_index] = 1;
+            }
+            launches += launch_chunk(dev, part->dc, part->plan, dev.streams[0], opt, out != nullptr);
+        }
+        for (size_t d = 0; d < h->devices.size(); ++d)
+            if (used[d]) {
+                CK(cudaSetDevice(h->devices[d]->ordinal));
+                CK(cudaEventRecord(h->devices[d]->ev_step1, h->devices[d]->streams[0]));
+            }
+        for (auto &part : p->parts) {
+            Device &dev = *h->devices[part->device_index];
+            CK(cudaSetDevice(dev.ordinal));
+            finish_chunk(part->dc, &b, part->plan, out, h->stats, out != nullptr, false);
+        }
+        // device time of the step = slowest device, first launch to last download
+        float step_ms = 0.f;
+        for (size_t d = 0; d < h->devices.size(); ++d)
+            if (used[d]) {
+                CK(cudaSetDevice(h->devices[d]->ordinal));
+                CK(cudaEventSynchronize(h->devices[d]->ev_step1));
+                float ms = 0.f;
+                CK(cudaEventElapsedTime(&ms, h->devices[d]->ev_step0, h->devices[d]->ev_step1));
+                step_ms = std::max(step_ms, ms);
+            }
+        {
+            std::lock_guard<std::mutex> lk(h->stats.mu);
+            h->stats.s.device_ms += step_ms;
+        }
+        CK(cudaSetDevice(h->ordinals[0]));
+        std::lock_guard<std::mutex> lk(h->stats.mu);
+        h->stats.s.kernel_launches += launches;
+        h->stats.s.wall_ms += now_ms() - t0;
+        return GPHMM_OK;
+    });
+}
+
+void gphmm_release_prepared(gphmm_t *h, gphmm_prepared_t *p) {
+    if (!p) return;
+    for (auto &part : p->parts) {
+        if (h) cudaSetDevice(h->devices[part->device_index]->ordinal);
+        part->dc.release();
+    }
+    if (h) cudaSetDevice(h->ordinals[0]);
+    delete p;
+}
+
+int gphmm_get_stats(const gphmm_t *h, gphmm_stats *out) {
+    if (!h || !out) return GPHMM_ERR_INVALID_ARG;
+    gphmm *hh = const_cast<gphmm *>(h);
+    std::lock_guard<std::mutex> lk(hh->stats.mu);
+    *out = hh->stats.s;
+    return GPHMM_OK;
+}
+
+void gphmm_reset_stats(gphmm_t *h) {
+    if (!h) return;
+    std::lock_guard<std::mutex> lk(h->stats.mu);
+    memset(&h->stats.s, 0, sizeof h->stats.s);
+}
+
+void *gphmm_host_alloc(size_t bytes) {
+    void *p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+
+void gphmm_host_free(void *p) {
+    if (p) cudaFreeHost(p);
+}
+
+}  // extern "C"

@@ -1,0 +1,348 @@
+// phmm_kernels.cuh -- PairHMM forward kernels for sm_100a (B200).
+//
+// Computes what LoglessPairHMM.subComputeReadLikelihoodGivenHaplotypeLog10 computes
+// (reference: src/main/java/org/broadinstitute/hellbender/utils/pairhmm/LoglessPairHMM.java:20-68,
+// priors :79-93, transitions PairHMMModel.java:107-117) but laid out for a GPU warp:
+//
+//  * One warp = one task = one read against the back-to-back stream of all haplotypes of its
+//    region.  Lane l owns K consecutive read rows (l*K+1 .. l*K+K); their M/I/D state lives in
+//    registers.  The warp sweeps the haplotype stream one column per step; lane l works on
+//    column (step - l), so every step hands the last row of each lane to the next lane with three
+//    __shfl_up_sync -- the anti-diagonal wavefront.
+//  * The recurrence is re-scaled so a cell costs 6 FP instructions (DESIGN.md "Kernel recurrence"):
+//        I~ = I / tMI_i ,  D~ = D / tMD_i
+//        M[i][j]  = prior(i,j) * ( a_i*M[i-1][j-1] + b_i*I~[i-1][j-1] + c_i*D~[i-1][j-1] )
+//        D~[i][j] = M[i][j-1] + tDD_i * D~[i][j-1]
+//        I~[i][j] = M[i-1][j] + g_i  * I~[i-1][j]
+//    with a=tMM_i, b=tIM_i*tMI_{i-1}, c=tIM_i*tMD_{i-1}, g=tII_i*tMI_{i-1}/tMI_i, tMI_0=tMD_0=1.
+//  * prior(i,j) comes from a per-task shared-memory table indexed by the haplotype code of the
+//    column: one 16-byte LDS returns the priors of 4 (fp32) / 2 (fp64) rows of the lane.
+//  * Rows below the read are pad rows (a=b=c=tDD=0, prior=0, g=tMI_R then 1): they carry
+//    (M+I)[R][j] down to the last row of the last lane, which adds it to the haplotype's sum.
+//  * Haplotypes are separated by an END column (prior 0): M and I~ vanish there by themselves, D~ is
+//    zeroed, lane 31 flushes the finished haplotype's sum.  No pipeline drain between haplotypes.
+//  * STRIPED kernels cover reads longer than 32*K-1 rows in several passes; the last row of a pass
+//    is parked in a per-CTA boundary buffer in global memory (L2 resident) and fed to lane 0 of the
+//    next pass.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace phmm_dev {
+
+constexpr uint32_t CODE_END = 0;   // column after the last base of a haplotype
+constexpr uint32_t CODE_NULL = 1;  // outside the stream (pipeline fill / drain)
+constexpr uint32_t CODE_FIRST_BASE = 2;  // A C G T N = 2..6, further byte values 7..
+constexpr int MAX_CODES = 64;
+constexpr int MAX_QUAL = 254;      // QualityUtils.java:43
+constexpr float RESCUE_THRESHOLD_F32 = 1e-28f;
+
+// D[0][j] of the reference is 2^1020/H (LoglessPairHMM.java:8,31).  The kernels use a power of two
+// 2^(BASE - ceil(log2 H)) <= that leaves headroom for the scaled states I~ and D~.
+constexpr int C0_BASE_EXP_F32 = 116;
+constexpr int C0_BASE_EXP_F64 = 960;
+
+struct __align__(16) Task {
+    uint32_t read;        // chunk-local read index
+    uint32_t stream_off;  // first column of the haplotype stream in `streams`
+    uint32_t stream_len;  // columns in the stream, one END per haplotype included
+    uint32_t out_base;    // slot of the stream's first haplotype in `sums`
+    int32_t c0_exp;       // D[0][j] = 2^c0_exp
+    uint32_t n_haps;      // haplotypes in the stream (diagnostic)
+    uint32_t pad0, pad1;
+};
+
+struct KernelArgs {
+    const uint8_t *rd_bases, *rd_q, *rd_i, *rd_d, *rd_c;  // raw per-base read arrays of the chunk
+    const uint32_t *read_off;                             // chunk-local, n_reads+1
+    const uint8_t *streams;                               // haplotype code streams
+    const Task *tasks;
+    const uint32_t *n_tasks_ptr;  // device-side task count (rescue lists) or nullptr
+    uint32_t n_tasks;             // host-side task count when n_tasks_ptr == nullptr
+    uint32_t *counter;            // work-queue cursor, zeroed before the launch
+    void *sums;                   // float* or double*: raw last-row sums per (task, haplotype)
+    void *bnd;                    // STRIPED: boundary buffer, bnd_stride columns per CTA
+    uint32_t bnd_stride;
+    const double *m2m;            // triangular matchToMatch table (PairHMMModel.java:71,86-94)
+    int *err;                     // device error flag (GPHMM_ERR_BAD_QUAL)
+    int32_t n_codes;
+    int32_t tristate_off;
+    uint8_t code_byte[MAX_CODES];  // code -> haplotype byte value
+};
+
+__constant__ double c_eps[256];  // QualityUtils.qualToErrorProb cache: 10^(-q/10), q = 0..254
+
+template <typename T> struct Vec16;
+template <> struct Vec16<float> { using type = float4; static constexpr int W = 4; };
+template <> struct Vec16<double> { using type = double2; static constexpr int W = 2; };
+
+template <typename T> struct __align__(16) Bnd { T m, i, d, pad; };
+
+__device__ __forceinline__ float fma_(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+__device__ __forceinline__ double fma_(double a, double b, double c) { return __fma_rn(a, b, c); }
+
+template <typename T, int W> __device__ __forceinline__ void unpack(const typename Vec16<T>::type &v, T *dst);
+template <> __device__ __forceinline__ void unpack<float, 4>(const float4 &v, float *dst) { dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w; }
+template <> __device__ __forceinline__ void unpack<double, 2>(const double2 &v, double *dst) { dst[0] = v.x; dst[1] = v.y; }
+
+// Dynamic shared memory a CTA (one warp) needs for its prior table.
+template <typename T, int K> constexpr size_t prior_table_bytes(int n_codes) {
+    return (size_t)n_codes * ((K + Vec16<T>::W - 1) / Vec16<T>::W) * 32 * 16;
+}
+
+template <typename T, int K, bool STRIPED>
+__global__ void __launch_bounds__(32) phmm_forward_kernel(const KernelArgs g)
+{
+    using V = typename Vec16<T>::type;
+    constexpr int W = Vec16<T>::W;
+    constexpr int NV = (K + W - 1) / W;
+    constexpr int KT = NV * W;
+    constexpr unsigned FULL = 0xffffffffu;
+    constexpr int ROWS_PER_STRIP = 32 * K;
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    V *tab = reinterpret_cast<V *>(smem_raw);
+    T *tab_s = reinterpret_cast<T *>(smem_raw);
+
+    const int lane = threadIdx.x;
+    T *const sums = reinterpret_cast<T *>(g.sums);
+    Bnd<T> *const bnd = STRIPED ? reinterpret_cast<Bnd<T> *>(g.bnd) + (size_t)blockIdx.x * g.bnd_stride : nullptr;
+    const uint32_t n_tasks = g.n_tasks_ptr ? *g.n_tasks_ptr : g.n_tasks;
+    const int n_codes = g.n_codes;
+
+    for (;;) {
+        uint32_t ti = 0;
+        if (lane == 0) ti = atomicAdd(g.counter, 1u);
+        ti = __shfl_sync(FULL, ti, 0);
+        if (ti >= n_tasks) break;
+        const Task t = g.tasks[ti];
+        const uint32_t ro = g.read_off[t.read];
+        const int R = (int)(g.read_off[t.read + 1] - ro);
+        const int P = (int)t.stream_len;
+        const uint8_t *__restrict__ stream = g.streams + t.stream_off;
+        const T c0 = (T)scalbn(1.0, t.c0_exp);
+        // The last strip must hold at least one pad row, hence R / ROWS + 1 strips.
+        const int n_strips = STRIPED ? R / ROWS_PER_STRIP + 1 : 1;
+
+        for (int strip = 0; strip < n_strips; ++strip) {
+            const bool first_strip = !STRIPED || strip == 0;
+            const bool last_strip = !STRIPED || strip == n_strips - 1;
+            // ---- per-strip setup: transition coefficients into registers, priors into shared memory ----
+            T ca[K], cb[K], cc[K], cg[K], cd[K];
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                const int i = strip * ROWS_PER_STRIP + lane * K + k + 1;  // 1-based read row
+                double A = 0.0, B = 0.0, C = 0.0, G = 1.0, DD = 0.0, pm = 0.0, px = 0.0;
+                uint32_t x = 0;
+                const bool real = i <= R;
+                if (real) {
+                    uint32_t q = g.rd_q[ro + i - 1], qi = g.rd_i[ro + i - 1], qd = g.rd_d[ro + i - 1], qc = g.rd_c[ro + i - 1];
+                    x = g.rd_bases[ro + i - 1];
+                    if (q > (uint32_t)MAX_QUAL || qi > 127u || qd > 127u || qc > 127u) {
+                        atomicExch(g.err, 1);
+                        q = min(q, (uint32_t)MAX_QUAL); qi = min(qi, 127u); qd = min(qd, 127u); qc = min(qc, 127u);
+                    }
+                    double tmi_prev = 1.0, tmd_prev = 1.0;
+                    if (i > 1) {
+                        tmi_prev = c_eps[min((uint32_t)g.rd_i[ro + i - 2], 127u)];
+                        tmd_prev = c_eps[min((uint32_t)g.rd_d[ro + i - 2], 127u)];
+                    }
+                    const double ei = c_eps[qi], ec = c_eps[qc];
+                    const uint32_t mn = min(qi, qd), mx = max(qi, qd);
+                    const double tIM = 1.0 - ec;
+                    A = __ldg(g.m2m + ((mx * (mx + 1)) >> 1) + mn);
+                    B = tIM * tmi_prev;
+                    C = tIM * tmd_prev;
+                    G = ec * tmi_prev / ei;
+                    DD = ec;
+                    const double e = c_eps[q];
+                    pm = 1.0 - e;
+                    px = g.tristate_off ? e : e / 3.0;
+                } else if (i == R + 1) {
+                    G = R >= 1 ? c_eps[min((uint32_t)g.rd_i[ro + R - 1], 127u)] : 1.0;
+                }
+                ca[k] = (T)A; cb[k] = (T)B; cc[k] = (T)C; cg[k] = (T)G; cd[k] = (T)DD;
+                const T pmT = (T)pm, pxT = (T)px;
+                for (int y = 0; y < n_codes; ++y) {
+                    T v = (T)0;
+                    if (real && y >= (int)CODE_FIRST_BASE) {
+                        const uint32_t hb = g.code_byte[y];
+                        v = (x == hb || x == (uint32_t)'N' || hb == (uint32_t)'N') ? pmT : pxT;  // LoglessPairHMM.java:89
+                    }
+                    tab_s[((y * NV + k / W) * 32 + lane) * W + (k % W)] = v;
+                }
+            }
+            __syncwarp();
+
+            // ---- the sweep ----
+            T M[K], I[K], D[K];
+#pragma unroll
+            for (int k = 0; k < K; ++k) { M[k] = (T)0; I[k] = (T)0; D[k] = (T)0; }
+            T dgm = (T)0, dgi = (T)0, dgd = first_strip ? c0 : (T)0;  // row above, previous column
+            T sum = (T)0;
+            uint32_t hap_idx = 0;
+            int p = 1 - lane;  // this lane's column in the current step (1-based)
+            uint32_t y = ((unsigned)(p - 1) < (unsigned)P) ? (uint32_t)__ldg(stream + p - 1) : CODE_NULL;
+            Bnd<T> up_next;  // lane 0 of strips > 0: row above at column p, prefetched
+            up_next.m = up_next.i = up_next.d = (T)0;
+            if (STRIPED && !first_strip && lane == 0 && P > 0) up_next = bnd[0];
+
+            const int n_steps = P + 31;
+            for (int s = 1; s <= n_steps; ++s) {
+                // prefetch the next column's code (and boundary row)
+                const uint32_t y_next = ((unsigned)p < (unsigned)P) ? (uint32_t)__ldg(stream + p) : CODE_NULL;
+                T mu = __shfl_up_sync(FULL, M[K - 1], 1);
+                T iu = __shfl_up_sync(FULL, I[K - 1], 1);
+                T du = __shfl_up_sync(FULL, D[K - 1], 1);
+                if (lane == 0) {
+                    if (first_strip) { mu = (T)0; iu = (T)0; du = c0; }
+                    else { mu = up_next.m; iu = up_next.i; du = up_next.d; }
+                }
+                if (STRIPED && !first_strip && lane == 0) {
+                    if ((unsigned)p < (unsigned)P) up_next = bnd[p];
+                    else { up_next.m = (T)0; up_next.i = (T)0; up_next.d = (T)0; }
+                }
+                // priors of this lane's K rows for haplotype code y
+                T pr[KT];
+                {
+                    const V *tp = tab + (size_t)y * (NV * 32) + lane;
+#pragma unroll
+                    for (int v = 0; v < NV; ++v) unpack<T, W>(tp[v * 32], pr + v * W);
+                }
+                // M of column p from column p-1 (old M/I/D of the row above)
+                T Mn[K];
+                {
+                    T u = cc[0] * dgd;
+                    u = fma_(cb[0], dgi, u);
+                    u = fma_(ca[0], dgm, u);
+                    Mn[0] = pr[0] * u;
+                }
+#pragma unroll
+                for (int k = 1; k < K; ++k) {
+                    T u = cc[k] * D[k - 1];
+                    u = fma_(cb[k], I[k - 1], u);
+                    u = fma_(ca[k], M[k - 1], u);
+                    Mn[k] = pr[k] * u;
+                }
+                // D~ of column p from column p-1 of the same row
+#pragma unroll
+                for (int k = 0; k < K; ++k) D[k] = fma_(cd[k], D[k], M[k]);
+                // I~ of column p: chain down the column
+                I[0] = fma_(cg[0], iu, mu);
+#pragma unroll
+                for (int k = 1; k < K; ++k) I[k] = fma_(cg[k], I[k - 1], Mn[k - 1]);
+#pragma unroll
+                for (int k = 0; k < K; ++k) M[k] = Mn[k];
+                dgm = mu; dgi = iu; dgd = du;
+                sum += I[K - 1];  // meaningful on lane 31 of the last strip: (M+I)[R][p]
+
+                if (y == CODE_END) {
+#pragma unroll
+                    for (int k = 0; k < K; ++k) D[k] = (T)0;
+                    if (last_strip && lane == 31) sums[t.out_base + hap_idx] = sum;
+                    ++hap_idx;
+                    sum = (T)0;
+                }
+                if (STRIPED && !last_strip && lane == 31 && (unsigned)(p - 1) < (unsigned)P) {
+                    Bnd<T> o;
+                    o.m = M[K - 1]; o.i = I[K - 1]; o.d = D[K - 1]; o.pad = (T)0;
+                    bnd[p - 1] = o;
+                }
+                y = y_next;
+                ++p;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Epilogue: raw sums -> log10 likelihoods (LoglessPairHMM.java:67), rescue-list construction.
+// ---------------------------------------------------------------------------------------------
+struct UnitDesc {
+    uint32_t read_first, n_reads;  // chunk-local
+    uint32_t hap_first, n_haps;    // chunk-local
+    uint32_t out_base;             // chunk-local output slot of (read 0, hap 0)
+    int32_t c0_exp;                // fp32 (or forced-fp64) initial-condition exponent of this unit
+    uint32_t pad0, pad1;
+};
+
+struct EpilogueArgs {
+    const UnitDesc *units;
+    uint32_t n_units;
+    const uint32_t *hap_len;         // chunk-local haplotype lengths
+    const uint32_t *hap_stream_off;  // chunk-local: first column of each haplotype in `streams`
+    const void *sums;                // float* (fp32 pass) or double* (forced fp64)
+    double *out;                     // chunk-local log10 likelihoods
+    Task *rescue_tasks;              // filled when the fp32 sum is unusable
+    uint32_t *n_rescue;
+    uint32_t rescue_capacity;
+};
+
+__device__ __forceinline__ double log10_c0H(int c0_exp, uint32_t H) {
+    return (double)c0_exp * 0.30102999566398119521 + log10((double)H);
+}
+
+// One CTA per unit; threads stride over the unit's (read, haplotype) pairs.
+__global__ void __launch_bounds__(128) phmm_epilogue_f32(const EpilogueArgs e)
+{
+    const float *sums = reinterpret_cast<const float *>(e.sums);
+    for (uint32_t u = blockIdx.x; u < e.n_units; u += gridDim.x) {
+        const UnitDesc d = e.units[u];
+        const uint32_t n = d.n_reads * d.n_haps;
+        for (uint32_t k = threadIdx.x; k < n; k += blockDim.x) {
+            const uint32_t r = k / d.n_haps, h = k - r * d.n_haps;
+            const float s = sums[d.out_base + k];
+            const uint32_t H = e.hap_len[d.hap_first + h];
+            // !(s >= thr) also catches NaN; +inf means the scaled states overflowed
+            if (!(s >= RESCUE_THRESHOLD_F32) || s > 3.0e38f) {
+                const uint32_t slot = atomicAdd(e.n_rescue, 1u);
+                if (slot < e.rescue_capacity) {
+                    Task t;
+                    t.read = d.read_first + r;
+                    t.stream_off = e.hap_stream_off[d.hap_first + h];
+                    t.stream_len = H + 1;
+                    t.out_base = slot;  // fp64 sums are indexed by rescue slot
+                    int lg = 0;
+                    while ((1u << lg) < H) ++lg;
+                    t.c0_exp = C0_BASE_EXP_F64 - lg;
+                    t.n_haps = 1;
+                    t.pad0 = d.out_base + k;  // final output slot
+                    t.pad1 = H;
+                    e.rescue_tasks[slot] = t;
+                }
+                e.out[d.out_base + k] = __longlong_as_double(0x7ff8000000000000LL);  // placeholder NaN
+            } else {
+                e.out[d.out_base + k] = log10((double)s) - log10_c0H(d.c0_exp, H);
+            }
+        }
+    }
+}
+
+// forced-fp64 mode: sums are doubles in the unit layout
+__global__ void __launch_bounds__(128) phmm_epilogue_f64_units(const EpilogueArgs e)
+{
+    const double *sums = reinterpret_cast<const double *>(e.sums);
+    for (uint32_t u = blockIdx.x; u < e.n_units; u += gridDim.x) {
+        const UnitDesc d = e.units[u];
+        const uint32_t n = d.n_reads * d.n_haps;
+        for (uint32_t k = threadIdx.x; k < n; k += blockDim.x) {
+            const uint32_t h = k % d.n_haps;
+            const uint32_t H = e.hap_len[d.hap_first + h];
+            e.out[d.out_base + k] = log10(sums[d.out_base + k]) - log10_c0H(d.c0_exp, H);
+        }
+    }
+}
+
+// rescue pass: one double sum per rescue slot -> its final output slot
+__global__ void __launch_bounds__(128) phmm_epilogue_rescue(const Task *tasks, const uint32_t *n_rescue, uint32_t capacity,
+                                                            const double *sums, double *out)
+{
+    const uint32_t n = min(*n_rescue, capacity);
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        const Task t = tasks[k];
+        out[t.pad0] = log10(sums[k]) - log10_c0H(t.c0_exp, t.pad1);
+    }
+}
+
+}  // namespace phmm_dev

@@ -1,0 +1,296 @@
+"""ctypes binding of libgpuphmm.so (include/gpuphmm.h).  No arithmetic happens in Python."""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+_u8p = ctypes.POINTER(ctypes.c_uint8)
+_i64p = ctypes.POINTER(ctypes.c_int64)
+_i32p = ctypes.POINTER(ctypes.c_int32)
+_f64p = ctypes.POINTER(ctypes.c_double)
+
+ERR_INVALID_ARG, ERR_NO_DEVICE, ERR_CUDA, ERR_BAD_QUAL, ERR_ALPHABET, ERR_NOMEM, ERR_BAD_TICKET, ERR_TOO_LARGE = range(-1, -9, -1)
+
+
+class GpuPhmmError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("gpuphmm error %d: %s" % (code, msg))
+        self.code = code
+
+
+class _Config(ctypes.Structure):
+    _fields_ = [("struct_size", ctypes.c_int32), ("n_devices", ctypes.c_int32), ("devices", _i32p),
+                ("force_fp64", ctypes.c_int32), ("host_threads", ctypes.c_int32), ("tristate_off", ctypes.c_int32),
+                ("reserved0", ctypes.c_int32), ("chunk_cells", ctypes.c_int64), ("chunk_bytes", ctypes.c_int64)]
+
+
+class _Unit(ctypes.Structure):
+    _fields_ = [("read_begin", ctypes.c_int64), ("read_end", ctypes.c_int64), ("hap_begin", ctypes.c_int64),
+                ("hap_end", ctypes.c_int64), ("out_off", ctypes.c_int64)]
+
+
+class _Batch(ctypes.Structure):
+    _fields_ = [("read_bases", ctypes.c_void_p), ("base_q", ctypes.c_void_p), ("ins_q", ctypes.c_void_p),
+                ("del_q", ctypes.c_void_p), ("gcp", ctypes.c_void_p), ("read_off", ctypes.c_void_p),
+                ("n_reads", ctypes.c_int64), ("hap_bases", ctypes.c_void_p), ("hap_off", ctypes.c_void_p),
+                ("n_haps", ctypes.c_int64), ("units", ctypes.c_void_p), ("n_units", ctypes.c_int64)]
+
+
+class Stats(ctypes.Structure):
+    _fields_ = [("pairs", ctypes.c_int64), ("cells", ctypes.c_int64), ("rescued_pairs", ctypes.c_int64),
+                ("rescued_cells", ctypes.c_int64), ("h2d_bytes", ctypes.c_int64), ("d2h_bytes", ctypes.c_int64),
+                ("kernel_launches", ctypes.c_int64), ("fp32_kernel_ms", ctypes.c_double), ("fp64_kernel_ms", ctypes.c_double),
+                ("device_ms", ctypes.c_double), ("host_stage_ms", ctypes.c_double), ("wall_ms", ctypes.c_double)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+UNIT_DTYPE = np.dtype([("read_begin", "<i8"), ("read_end", "<i8"), ("hap_begin", "<i8"), ("hap_end", "<i8"), ("out_off", "<i8")])
+
+EXPORTS = ["gphmm_abi_version", "gphmm_device_count", "gphmm_strerror", "gphmm_create", "gphmm_destroy",
+           "gphmm_last_error", "gphmm_compute", "gphmm_submit", "gphmm_wait", "gphmm_prepare", "gphmm_run_prepared",
+           "gphmm_release_prepared", "gphmm_get_stats", "gphmm_reset_stats", "gphmm_host_alloc", "gphmm_host_free"]
+
+
+def lib_path():
+    return os.path.join(_HERE, "lib", "libgpuphmm.so")
+
+
+def load_library():
+    """Loads the CUDA library.  Fails loudly when it has not been built -- there is no fallback."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = lib_path()
+    if not os.path.exists(path):
+        raise GpuPhmmError(ERR_NO_DEVICE, "%s is missing: run `python -m gatk_b200.build` (or __graft_entry__.build())" % path)
+    L = ctypes.CDLL(path)
+    L.gphmm_abi_version.restype = ctypes.c_int
+    L.gphmm_device_count.restype = ctypes.c_int
+    L.gphmm_strerror.restype = ctypes.c_char_p
+    L.gphmm_strerror.argtypes = [ctypes.c_int]
+    L.gphmm_create.restype = ctypes.c_int
+    L.gphmm_create.argtypes = [ctypes.POINTER(_Config), ctypes.POINTER(ctypes.c_void_p)]
+    L.gphmm_destroy.restype = None
+    L.gphmm_destroy.argtypes = [ctypes.c_void_p]
+    L.gphmm_last_error.restype = ctypes.c_char_p
+    L.gphmm_last_error.argtypes = [ctypes.c_void_p]
+    L.gphmm_compute.restype = ctypes.c_int
+    L.gphmm_compute.argtypes = [ctypes.c_void_p, ctypes.POINTER(_Batch), ctypes.c_void_p]
+    L.gphmm_submit.restype = ctypes.c_int
+    L.gphmm_submit.argtypes = [ctypes.c_void_p, ctypes.POINTER(_Batch), ctypes.c_void_p, ctypes.POINTER(ctypes.c_uint64)]
+    L.gphmm_wait.restype = ctypes.c_int
+    L.gphmm_wait.argtypes = [ctypes.c_void_p, ctypes.c_uint64]
+    L.gphmm_prepare.restype = ctypes.c_int
+    L.gphmm_prepare.argtypes = [ctypes.c_void_p, ctypes.POINTER(_Batch), ctypes.POINTER(ctypes.c_void_p)]
+    L.gphmm_run_prepared.restype = ctypes.c_int
+    L.gphmm_run_prepared.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+    L.gphmm_release_prepared.restype = None
+    L.gphmm_release_prepared.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+    L.gphmm_get_stats.restype = ctypes.c_int
+    L.gphmm_get_stats.argtypes = [ctypes.c_void_p, ctypes.POINTER(Stats)]
+    L.gphmm_reset_stats.restype = None
+    L.gphmm_reset_stats.argtypes = [ctypes.c_void_p]
+    L.gphmm_host_alloc.restype = ctypes.c_void_p
+    L.gphmm_host_alloc.argtypes = [ctypes.c_size_t]
+    L.gphmm_host_free.restype = None
+    L.gphmm_host_free.argtypes = [ctypes.c_void_p]
+    _LIB = L
+    return L
+
+
+class Batch:
+    """Flat SoA batch (gphmm_batch).  Arrays are numpy; `pinned=True` places the big per-base arrays in
+    CUDA pinned host memory obtained from the library so that staging is a straight DMA."""
+
+    def __init__(self, read_bases, base_q, ins_q, del_q, gcp, read_off, hap_bases, hap_off, units, pinned=False):
+        self._pinned_ptrs = []
+        conv = (lambda a: self._pin(np.ascontiguousarray(a, dtype=np.uint8))) if pinned else (lambda a: np.ascontiguousarray(a, dtype=np.uint8))
+        self.read_bases, self.base_q, self.ins_q, self.del_q, self.gcp = (conv(a) for a in (read_bases, base_q, ins_q, del_q, gcp))
+        self.hap_bases = np.ascontiguousarray(hap_bases, dtype=np.uint8)
+        self.read_off = np.ascontiguousarray(read_off, dtype=np.int64)
+        self.hap_off = np.ascontiguousarray(hap_off, dtype=np.int64)
+        u = np.asarray(units)
+        if u.dtype != UNIT_DTYPE:
+            uu = np.zeros(len(u), dtype=UNIT_DTYPE)
+            u = np.asarray(u, dtype=np.int64).reshape(-1, 5)
+            for k, name in enumerate(UNIT_DTYPE.names):
+                uu[name] = u[:, k]
+            u = uu
+        self.units = np.ascontiguousarray(u)
+        n = len(self.read_bases)
+        for a in (self.base_q, self.ins_q, self.del_q, self.gcp):
+            if len(a) != n:
+                raise ValueError("per-base read arrays differ in length")  # PairHMM.java:286-292
+        if len(self.read_off) < 1 or self.read_off[-1] != n:
+            raise ValueError("read_off does not cover the read arrays")
+        if len(self.hap_off) < 1 or self.hap_off[-1] != len(self.hap_bases):
+            raise ValueError("hap_off does not cover hap_bases")
+
+    def _pin(self, a):
+        L = load_library()
+        nbytes = max(a.nbytes, 1)
+        ptr = L.gphmm_host_alloc(nbytes)
+        if not ptr:
+            raise GpuPhmmError(ERR_NOMEM, "pinned allocation failed")
+        self._pinned_ptrs.append(ptr)
+        buf = (ctypes.c_uint8 * nbytes).from_address(ptr)
+        out = np.frombuffer(buf, dtype=np.uint8, count=a.size)
+        out[:] = a
+        return out
+
+    def __del__(self):
+        try:
+            L = load_library()
+            for p in self._pinned_ptrs:
+                L.gphmm_host_free(p)
+        except Exception:
+            pass
+        self._pinned_ptrs = []
+
+    @property
+    def n_reads(self):
+        return len(self.read_off) - 1
+
+    @property
+    def n_haps(self):
+        return len(self.hap_off) - 1
+
+    @property
+    def n_out(self):
+        if len(self.units) == 0:
+            return 0
+        nr = self.units["read_end"] - self.units["read_begin"]
+        nh = self.units["hap_end"] - self.units["hap_begin"]
+        return int(np.max(self.units["out_off"] + nr * nh))
+
+    def cells(self):
+        rl = np.diff(self.read_off)
+        hl = np.diff(self.hap_off)
+        rc = np.concatenate([[0], np.cumsum(rl)])
+        hc = np.concatenate([[0], np.cumsum(hl)])
+        u = self.units
+        return int(np.sum((rc[u["read_end"]] - rc[u["read_begin"]]) * (hc[u["hap_end"]] - hc[u["hap_begin"]])))
+
+    def pairs(self):
+        u = self.units
+        return int(np.sum((u["read_end"] - u["read_begin"]) * (u["hap_end"] - u["hap_begin"])))
+
+    def input_bytes(self):
+        return 5 * int(self.read_off[-1]) + int(self.hap_off[-1])
+
+    def c_struct(self):
+        b = _Batch()
+        b.read_bases, b.base_q, b.ins_q, b.del_q, b.gcp = (a.ctypes.data for a in (self.read_bases, self.base_q, self.ins_q, self.del_q, self.gcp))
+        b.read_off = self.read_off.ctypes.data
+        b.n_reads = self.n_reads
+        b.hap_bases = self.hap_bases.ctypes.data
+        b.hap_off = self.hap_off.ctypes.data
+        b.n_haps = self.n_haps
+        b.units = self.units.ctypes.data
+        b.n_units = len(self.units)
+        return b
+
+    @staticmethod
+    def single_unit(reads, haps):
+        """reads: list of (bases, base_q, ins_q, del_q, gcp); haps: list of bytes."""
+        as_u8 = lambda x: np.frombuffer(x, dtype=np.uint8) if isinstance(x, (bytes, bytearray)) else np.asarray(x, dtype=np.uint8)
+        cols = [[as_u8(r[k]) for r in reads] for k in range(5)]
+        cat = lambda xs: np.concatenate(xs) if xs else np.zeros(0, np.uint8)
+        read_off = np.concatenate([[0], np.cumsum([len(x) for x in cols[0]])]).astype(np.int64)
+        hs = [as_u8(h) for h in haps]
+        hap_off = np.concatenate([[0], np.cumsum([len(h) for h in hs])]).astype(np.int64)
+        units = np.array([(0, len(reads), 0, len(haps), 0)], dtype=UNIT_DTYPE)
+        return Batch(cat(cols[0]), cat(cols[1]), cat(cols[2]), cat(cols[3]), cat(cols[4]), read_off, cat(hs), hap_off, units)
+
+
+class GpuPhmm:
+    """RAII wrapper of a gphmm_t handle."""
+
+    def __init__(self, devices=None, force_fp64=False, host_threads=0, tristate_off=False, chunk_cells=0, chunk_bytes=0):
+        self._L = load_library()
+        self._h = ctypes.c_void_p()
+        cfg = _Config()
+        cfg.struct_size = ctypes.sizeof(_Config)
+        self._dev_arr = None
+        if devices:
+            self._dev_arr = (ctypes.c_int32 * len(devices))(*devices)
+            cfg.n_devices = len(devices)
+            cfg.devices = ctypes.cast(self._dev_arr, _i32p)
+        cfg.force_fp64 = int(force_fp64)
+        cfg.host_threads = int(host_threads)
+        cfg.tristate_off = int(tristate_off)
+        cfg.chunk_cells = int(chunk_cells)
+        cfg.chunk_bytes = int(chunk_bytes)
+        rc = self._L.gphmm_create(ctypes.byref(cfg), ctypes.byref(self._h))
+        if rc != 0:
+            raise GpuPhmmError(rc, self._L.gphmm_strerror(rc).decode())
+        self._pending = {}
+
+    def _check(self, rc):
+        if rc != 0:
+            raise GpuPhmmError(rc, self._L.gphmm_last_error(self._h).decode() or self._L.gphmm_strerror(rc).decode())
+
+    def close(self):
+        if self._h:
+            self._L.gphmm_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def compute(self, batch, out=None):
+        if out is None:
+            out = np.full(batch.n_out, np.nan, dtype=np.float64)
+        b = batch.c_struct()
+        self._check(self._L.gphmm_compute(self._h, ctypes.byref(b), out.ctypes.data))
+        return out
+
+    def submit(self, batch, out=None):
+        if out is None:
+            out = np.full(batch.n_out, np.nan, dtype=np.float64)
+        b = batch.c_struct()
+        t = ctypes.c_uint64(0)
+        self._check(self._L.gphmm_submit(self._h, ctypes.byref(b), out.ctypes.data, ctypes.byref(t)))
+        self._pending[t.value] = out
+        return t.value
+
+    def wait(self, ticket):
+        rc = self._L.gphmm_wait(self._h, ctypes.c_uint64(ticket))
+        out = self._pending.pop(ticket, None)
+        self._check(rc)
+        return out
+
+    def prepare(self, batch):
+        b = batch.c_struct()
+        p = ctypes.c_void_p()
+        self._check(self._L.gphmm_prepare(self._h, ctypes.byref(b), ctypes.byref(p)))
+        return p
+
+    def run_prepared(self, prepared, out=None):
+        self._check(self._L.gphmm_run_prepared(self._h, prepared, out.ctypes.data if out is not None else None))
+        return out
+
+    def release_prepared(self, prepared):
+        self._L.gphmm_release_prepared(self._h, prepared)
+
+    def stats(self):
+        s = Stats()
+        self._check(self._L.gphmm_get_stats(self._h, ctypes.byref(s)))
+        return s.as_dict()
+
+    def reset_stats(self):
+        self._L.gphmm_reset_stats(self._h)

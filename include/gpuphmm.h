@@ -1,0 +1,139 @@
+/*
+ * gpuphmm.h -- C ABI of libgpuphmm.so, the B200 (sm_100a) PairHMM forward engine behind GATK's
+ *              `-pairHMM CUDA_LOGLESS_CACHING`.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++/torch types, no globals, no
+ * callbacks.  It is what a JNI shim for GATK's native PairHMM binding calls; the shim is
+ * gatk_b200/csrc/gpuphmm_jni.cpp and the Java side is under java/ (see INTEGRATION.md).
+ *
+ * Reference interfaces replaced (paths under /root/reference/src/main/java/org/broadinstitute/hellbender/):
+ *   utils/pairhmm/VectorLoglessPairHMM.java:63      PairHMMNativeBinding.load(File)            -> gphmm_device_count / gphmm_create
+ *   utils/pairhmm/VectorLoglessPairHMM.java:81      PairHMMNativeBinding.initialize(args)       -> gphmm_create(gphmm_config)
+ *   utils/pairhmm/VectorLoglessPairHMM.java:138     PairHMMNativeBinding.computeLikelihoods(ReadDataHolder[], HaplotypeDataHolder[], double[])
+ *                                                                                                -> gphmm_compute (one unit) / gphmm_submit + gphmm_wait (many units)
+ *   utils/pairhmm/VectorLoglessPairHMM.java:164     PairHMMNativeBinding.done()                 -> gphmm_destroy
+ *   tools/walkers/haplotypecaller/PairHMMNativeArgumentCollection.java:11-23 (maxNumberOfThreads, useDoublePrecision)
+ *                                                                                                -> gphmm_config.host_threads / force_fp64
+ *   utils/pairhmm/PairHMM.java:196-247 / :236       result layout out[r * nHaps + h] (log10)    -> gphmm_unit.out_off + r*nHaps + h
+ *
+ * Semantics: for every unit u (one sample's reads against one region's haplotypes) and every read r and
+ * haplotype h of the unit, out[u.out_off + r*nHaps + h] = log10 P(read r | haplotype h) as defined by
+ * utils/pairhmm/LoglessPairHMM.java:20-68.  Computation is fp32 on the GPU with an fp64 redo on the GPU of
+ * every pair whose fp32 sum under-/overflows (or everything in fp64 when force_fp64 is set).  There is no CPU
+ * fallback: without a usable CUDA device gphmm_create fails.
+ *
+ * Thread safety: a gphmm_t may be used from one thread at a time; several gphmm_t may coexist in a process.
+ */
+#ifndef GPUPHMM_H
+#define GPUPHMM_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GPHMM_ABI_VERSION 1
+
+/* error codes (0 = success, negative = failure) */
+#define GPHMM_OK 0
+#define GPHMM_ERR_INVALID_ARG (-1) /* null pointer, bad offsets, zero-length haplotype (PairHMM.java:139,284-292) */
+#define GPHMM_ERR_NO_DEVICE (-2)   /* no CUDA device / not sm_100 (-> UserException.HardwareFeatureException) */
+#define GPHMM_ERR_CUDA (-3)        /* a CUDA call failed; gphmm_last_error() has the text (-> GATKException) */
+#define GPHMM_ERR_BAD_QUAL (-4)    /* ins/del/gcp qual > 127 or base qual 255 (PairHMMModel.java:109-111, QualityUtils.java:157) */
+#define GPHMM_ERR_ALPHABET (-5)    /* more distinct haplotype byte values than the prior table supports */
+#define GPHMM_ERR_NOMEM (-6)
+#define GPHMM_ERR_BAD_TICKET (-7)
+#define GPHMM_ERR_TOO_LARGE (-8)   /* a single unit exceeds the per-chunk device budget */
+
+typedef struct gphmm gphmm_t;
+typedef struct gphmm_prepared gphmm_prepared_t;
+
+typedef struct gphmm_config {
+    int32_t struct_size;      /* sizeof(gphmm_config); lets the struct grow compatibly */
+    int32_t n_devices;        /* 0: use the current CUDA device only; >0: devices[0..n) */
+    const int32_t *devices;   /* CUDA ordinals, may be NULL when n_devices == 0 */
+    int32_t force_fp64;       /* PairHMMNativeArguments.useDoublePrecision */
+    int32_t host_threads;     /* PairHMMNativeArguments.maxNumberOfThreads: staging threads, 0 = default */
+    int32_t tristate_off;     /* PairHMM.doNotUseTristateCorrection() (tests only) */
+    int32_t reserved0;
+    int64_t chunk_cells;      /* target DP cells per device chunk, 0 = default */
+    int64_t chunk_bytes;      /* max staged input bytes per device chunk, 0 = default */
+} gphmm_config;
+
+/* One (region, sample) unit: reads [read_begin, read_end) against haplotypes [hap_begin, hap_end). */
+typedef struct gphmm_unit {
+    int64_t read_begin, read_end; /* indices into read_off */
+    int64_t hap_begin, hap_end;   /* indices into hap_off */
+    int64_t out_off;              /* first output slot of this unit */
+} gphmm_unit;
+
+/* Flat structure-of-arrays batch.  All pointers are host memory (pageable or pinned). */
+typedef struct gphmm_batch {
+    const uint8_t *read_bases; /* ReadDataHolder.readBases    (VectorLoglessPairHMM.java:123) */
+    const uint8_t *base_q;     /* ReadDataHolder.readQuals    (:124) raw phred, not ASCII */
+    const uint8_t *ins_q;      /* ReadDataHolder.insertionGOP (:125) */
+    const uint8_t *del_q;      /* ReadDataHolder.deletionGOP  (:126) */
+    const uint8_t *gcp;        /* ReadDataHolder.overallGCP   (:127) */
+    const int64_t *read_off;   /* n_reads + 1 offsets shared by the five arrays above */
+    int64_t n_reads;
+    const uint8_t *hap_bases;  /* HaplotypeDataHolder.haplotypeBases (:98), concatenated */
+    const int64_t *hap_off;    /* n_haps + 1 */
+    int64_t n_haps;
+    const gphmm_unit *units;
+    int64_t n_units;
+} gphmm_batch;
+
+typedef struct gphmm_stats {
+    int64_t pairs;           /* (read, haplotype) pairs computed */
+    int64_t cells;           /* sum of R*H over pairs (LoglessPairHMM.java:47-49, no padding) */
+    int64_t rescued_pairs;   /* pairs redone in fp64 */
+    int64_t rescued_cells;
+    int64_t h2d_bytes;
+    int64_t d2h_bytes;
+    int64_t kernel_launches; /* CUDA kernels launched by this library */
+    double fp32_kernel_ms;   /* CUDA-event time of the fp32 forward kernels */
+    double fp64_kernel_ms;   /* CUDA-event time of the fp64 forward kernels */
+    double device_ms;        /* CUDA-event time of everything queued on the compute streams */
+    double host_stage_ms;    /* wall time spent packing staging buffers */
+    double wall_ms;          /* wall time inside compute/submit/wait/run_prepared */
+} gphmm_stats;
+
+int gphmm_abi_version(void);
+/* Number of usable devices (compute capability 10.x); 0 when there is none or the driver is absent. */
+int gphmm_device_count(void);
+const char *gphmm_strerror(int code);
+
+int gphmm_create(const gphmm_config *cfg, gphmm_t **out);
+void gphmm_destroy(gphmm_t *h);
+/* Text of the last failure on this handle (never NULL). */
+const char *gphmm_last_error(const gphmm_t *h);
+
+/* Synchronous: returns when every out[] slot of the batch is written. */
+int gphmm_compute(gphmm_t *h, const gphmm_batch *batch, double *out);
+
+/* Asynchronous cross-region batching queue.  submit copies the batch into staging buffers before it
+ * returns (the caller may reuse its input arrays at once, as JNI requires) and queues it; `out` must stay
+ * valid until gphmm_wait(ticket) returns.  Tickets complete in submission order. */
+int gphmm_submit(gphmm_t *h, const gphmm_batch *batch, double *out, uint64_t *ticket);
+int gphmm_wait(gphmm_t *h, uint64_t ticket);
+
+/* Device-resident path (benchmarks, repeated evaluation): prepare uploads and plans a batch once,
+ * run_prepared executes only the GPU work (kernels + result download when out != NULL). */
+int gphmm_prepare(gphmm_t *h, const gphmm_batch *batch, gphmm_prepared_t **out);
+int gphmm_run_prepared(gphmm_t *h, gphmm_prepared_t *p, double *out);
+void gphmm_release_prepared(gphmm_t *h, gphmm_prepared_t *p);
+
+/* Statistics accumulate over calls until reset. */
+int gphmm_get_stats(const gphmm_t *h, gphmm_stats *out);
+void gphmm_reset_stats(gphmm_t *h);
+
+/* Pinned host memory for callers that want zero-copy staging. */
+void *gphmm_host_alloc(size_t bytes);
+void gphmm_host_free(void *p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GPUPHMM_H */

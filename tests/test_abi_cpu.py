@@ -1,0 +1,86 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library builds, loads and exports every symbol that
+include/gpuphmm.h declares, and refuses to run without a GPU (no fallback).  No compute calls here."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from gatk_b200 import build as gbuild
+from gatk_b200 import native, synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    gbuild.build()
+    return native.load_library()
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "gpuphmm.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(gphmm_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_all_exported(lib):
+    names = _declared_symbols()
+    assert set(names) == set(native.EXPORTS)
+    for n in names:
+        assert getattr(lib, n) is not None
+
+
+def test_abi_version_and_strerror(lib):
+    assert lib.gphmm_abi_version() == 1
+    assert lib.gphmm_strerror(0) == b"ok"
+    for code in range(-8, 0):
+        assert len(lib.gphmm_strerror(code)) > 0
+
+
+def test_struct_layouts_match_header():
+    assert ctypes.sizeof(native._Unit) == 40 == native.UNIT_DTYPE.itemsize
+    assert ctypes.sizeof(native._Batch) == 96
+    assert ctypes.sizeof(native._Config) == 48
+    assert ctypes.sizeof(native.Stats) == 12 * 8
+
+
+def test_no_gpu_means_loud_failure(lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    assert lib.gphmm_device_count() == 0
+    with pytest.raises(native.GpuPhmmError) as e:
+        native.GpuPhmm()
+    assert e.value.code == native.ERR_NO_DEVICE
+
+
+def test_product_does_not_import_oracle():
+    # the product path must never route through the CPU oracle
+    pkg = os.path.join(ROOT, "gatk_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".java")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in text and "from oracle" not in text and "phmm_oracle" not in text, f
+
+
+def test_synthetic_shapes():
+    b = synth.config1()
+    assert b.n_reads == 128 and b.n_haps == 8 and b.pairs() == 1024
+    assert np.all(np.diff(b.read_off) == 150)
+    assert np.all((np.diff(b.hap_off) >= 190) & (np.diff(b.hap_off) <= 320))
+    b2 = synth.config2(20)
+    assert len(b2.units) == 20
+    nh = b2.units["hap_end"] - b2.units["hap_begin"]
+    assert nh.min() >= 4 and nh.max() <= 16
+    assert np.diff(b2.read_off).max() == 250 and np.diff(b2.read_off).min() >= 100
+    assert set(np.unique(b2.read_bases)) <= set(b"ACGT")
+    assert b2.n_out == b2.pairs()
+
+
+def test_batch_validation():
+    b = synth.config1()
+    with pytest.raises(ValueError):
+        native.Batch(b.read_bases, b.base_q[:-1], b.ins_q, b.del_q, b.gcp, b.read_off, b.hap_bases, b.hap_off, b.units)

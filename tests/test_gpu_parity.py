@@ -1,0 +1,272 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle and the reference's golden vectors.
+All tests here need a B200 (`-m gpu`)."""
+import math
+
+import numpy as np
+import pytest
+
+from gatk_b200 import native, synth
+from gatk_b200.native import Batch, GpuPhmm
+from phmm_testutil import const_quals, load_hmmresults, load_testdata, oracle_batch, records_to_batch
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-4  # BASELINE.json north_star: |log10 lk - LoglessPairHMM(double)| <= 1e-4
+
+
+@pytest.fixture(scope="module")
+def hmm():
+    h = GpuPhmm()
+    yield h
+    h.close()
+
+
+@pytest.fixture(scope="module")
+def hmm64():
+    h = GpuPhmm(force_fp64=True)
+    yield h
+    h.close()
+
+
+def _check(got, want, tol):
+    assert got.shape == want.shape
+    fin = np.isfinite(want)
+    assert np.array_equal(np.isfinite(got), fin)
+    assert np.array_equal(got[~fin], want[~fin])
+    err = np.abs(got[fin] - want[fin])
+    assert err.size == 0 or err.max() <= tol, "max err %.3g at %d" % (err.max(), int(np.argmax(err)))
+    assert np.all(got[fin] <= 1e-9)  # PairHMM.java:305: a log10 probability is never > 0
+
+
+def test_golden_pairhmm_testdata(hmm):
+    # VectorPairHMMUnitTest.java:100 : 1e-5 against the file's expected column
+    recs = load_testdata()
+    got = hmm.compute(records_to_batch(recs))
+    want = np.array([r["expected"] for r in recs])
+    assert np.abs(got - want).max() <= 1e-5
+
+
+def test_golden_hmmresults(hmm, hmm64):
+    recs = load_hmmresults()
+    b = records_to_batch(recs)
+    java = np.array([r["java"] for r in recs])
+    got = hmm.compute(b)
+    assert np.abs(got - java).max() <= 1e-5
+    got64 = hmm64.compute(b)
+    assert np.abs(got64 - java).max() <= 1e-6  # print precision of the fixture
+    assert all(("%e" % v) == r["java_text"] for v, r in zip(got64, recs))  # fp64 mode reproduces the text dump
+
+
+def test_golden_hmmresults_as_one_region(hmm):
+    # the same 284 pairs come from one region: 20 reads x ... ; group by haplotype set instead of 1x1 units
+    recs = load_hmmresults()
+    haps = sorted({r["hap"] for r in recs})
+    reads = {}
+    for r in recs:
+        reads.setdefault((r["read"], r["base_q"].tobytes(), r["ins_q"].tobytes(), r["del_q"].tobytes(), r["gcp"].tobytes()), r)
+    rl = list(reads.values())
+    b = Batch.single_unit([(r["read"], r["base_q"], r["ins_q"], r["del_q"], r["gcp"]) for r in rl], haps)
+    got = hmm.compute(b)
+    _check(got, oracle_batch(b), 1e-5)
+    # and every fixture row is reproduced at its (read, hap) slot
+    idx = {k: i for i, k in enumerate(reads.keys())}
+    for r in recs:
+        ri = idx[(r["read"], r["base_q"].tobytes(), r["ins_q"].tobytes(), r["del_q"].tobytes(), r["gcp"].tobytes())]
+        assert abs(got[ri * len(haps) + haps.index(r["hap"])] - r["java"]) <= 1e-5
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_random_ragged_batches(hmm, seed):
+    b = synth.random_batch(100 + seed, n_units=5, wild_quals=bool(seed % 2))
+    _check(hmm.compute(b), oracle_batch(b), TOL)
+
+
+@pytest.mark.parametrize("seed", range(3))
+def test_random_ragged_batches_fp64(hmm64, seed):
+    b = synth.random_batch(200 + seed, n_units=4, wild_quals=True)
+    _check(hmm64.compute(b), oracle_batch(b), 1e-9)
+
+
+def test_every_read_length_bucket(hmm):
+    # one read per length 1..300 exercises every rows-per-lane kernel, the bucket edges (31/32, 254/255/256)
+    # and the striped kernel for reads of 255+ bases
+    rng = np.random.default_rng(5)
+    hap = rng.integers(0, 4, 320, dtype=np.uint8)
+    letters = np.frombuffer(b"ACGT", dtype=np.uint8)
+    reads = []
+    for R in list(range(1, 301)):
+        off = int(rng.integers(0, 320 - R + 1))
+        rd = letters[hap[off:off + R]].copy()
+        if R > 3:
+            rd[R // 2] = ord("A") if rd[R // 2] != ord("A") else ord("C")
+        reads.append((rd, const_quals(R, 30), const_quals(R, 45), const_quals(R, 45), const_quals(R, 10)))
+    b = Batch.single_unit(reads, [letters[hap], letters[hap[:200]], letters[hap[7:]]])
+    _check(hmm.compute(b), oracle_batch(b), TOL)
+
+
+def test_config1_matches_oracle(hmm):
+    b = synth.config1()
+    got = hmm.compute(b)
+    _check(got, oracle_batch(b), TOL)
+    s = hmm.stats()
+    assert s["cells"] >= b.cells()
+
+
+def test_config2_sample_matches_oracle(hmm):
+    b = synth.config2(40)
+    _check(hmm.compute(b), oracle_batch(b), TOL)
+
+
+def test_fp64_rescue_path(hmm):
+    # indel-heavy reads under-flow fp32 and must come back from the fp64 redo with double accuracy
+    b = synth.config5(hap_len=600, n_regions=4, reads_per_region=24, n_haps=4, bad_fraction=0.5)
+    hmm.reset_stats()
+    got = hmm.compute(b)
+    want = oracle_batch(b)
+    s = hmm.stats()
+    assert s["rescued_pairs"] > 0
+    assert want.min() < -70  # the workload really leaves the fp32 range
+    _check(got, want, TOL)
+    low = want < -70
+    assert np.abs(got[low] - want[low]).max() <= 1e-9  # rescued pairs carry fp64 accuracy
+
+
+def test_really_big_reads(hmm, hmm64):
+    # PairHMMUnitTest.java:420-457 : reads up to 800 bp x haplotypes up to 2000 bp
+    read1, ref1 = b"ACCAAGTAGTCACCGT", b"ACCAAGTAGTCACCGTAACG"
+    reads, haps = [], []
+    for n in (1, 2, 10, 20, 50):
+        rd = read1 * n
+        reads.append((rd, const_quals(len(rd), 30), const_quals(len(rd), 40), const_quals(len(rd), 40), const_quals(len(rd), 10)))
+    for n in (2, 10, 20, 100):
+        haps.append(ref1 * n)
+    b = Batch.single_unit(reads, haps)
+    want = oracle_batch(b)
+    _check(hmm.compute(b), want, TOL)
+    _check(hmm64.compute(b), want, 1e-9)
+
+
+def test_basic_likelihoods_tristate_off():
+    # PairHMMUnitTest.java:148-199 : substitution / insertion / deletion micro-reads, tristate correction off
+    CONTEXT, LEFT = b"ACGTAATGACGATTGCA", b"GATTTATCATCGAGTCTGC"
+    reads, haps, expect = [], [], []
+    h = GpuPhmm(tristate_off=True)
+    try:
+        units_reads, units_haps = [], []
+        for base_q in (10, 30, 50):
+            for indel_q in (20, 40):
+                for gcp in (8, 10, 20):
+                    for ref, read, eq in ((b"A", b"A", 0), (b"A", b"C", base_q), (b"G", b"GGG", indel_q + gcp), (b"GGGGG", b"G", indel_q + 3 * gcp)):
+                        hap = LEFT + CONTEXT + ref + CONTEXT
+                        rd = CONTEXT + read + CONTEXT
+                        L = len(rd)
+                        bq = const_quals(L, 100); bq[17:17 + len(read)] = base_q
+                        iq = const_quals(L, 100); iq[17] = indel_q
+                        dq = const_quals(L, 100); dq[17] = indel_q
+                        gq = const_quals(L, 100); gq[17:17 + len(read)] = gcp
+                        units_reads.append((rd, bq, iq, dq, gq))
+                        units_haps.append(hap)
+                        expect.append(eq / -10.0 + 0.03 + math.log10(1.0 / len(hap)))
+        recs = [dict(read=r[0], base_q=r[1], ins_q=r[2], del_q=r[3], gcp=r[4], hap=hp) for r, hp in zip(units_reads, units_haps)]
+        b = records_to_batch(recs)
+        got = h.compute(b)
+        assert np.abs(got - np.array(expect)).max() <= 0.2
+        _check(got, oracle_batch(b, tristate_off=True), TOL)
+    finally:
+        h.close()
+
+
+def test_n_bases_and_exotic_bytes(hmm):
+    # LoglessPairHMM.java:89 : N in the read or the haplotype matches anything; other bytes compare exactly
+    hap = b"ACGTNACGTRRACGTacgtACGT"
+    reads = []
+    for rd in (b"ACGTAACGT", b"NNNNNNNNN", b"ACGTRRACG", b"acgtACGT", b"ACGTYACGT", b"ACGTNACGTRRACGTacgtACGT"):
+        n = len(rd)
+        reads.append((rd, const_quals(n, 30), const_quals(n, 45), const_quals(n, 45), const_quals(n, 10)))
+    b = Batch.single_unit(reads, [hap, b"ACGTACGTACGT", b"NNNNNNNNNNNNNNNN", b"RRRRYYYYKKKKMMMMSSSSWWWW"])
+    _check(hmm.compute(b), oracle_batch(b), TOL)
+
+
+def test_edge_shapes(hmm):
+    # reads longer than the haplotype (PairHMMUnitTest.java:24), 1-base reads/haps, empty units, zero-length read
+    e = np.zeros(0, np.uint8)
+    reads = [(b"A", const_quals(1, 30), const_quals(1, 45), const_quals(1, 45), const_quals(1, 10)),
+             (b"ACGTACGTACGTACGTACGTACGTACGTACGTACGT", const_quals(36, 25), const_quals(36, 40), const_quals(36, 40), const_quals(36, 10)),
+             (b"", e, e, e, e)]
+    b = Batch.single_unit(reads, [b"A", b"ACGT", b"ACGTACGTACGTACGTACGTACGTACGTACGTACGTACGTACGT"])
+    got = hmm.compute(b)
+    want = oracle_batch(b)
+    assert np.all(np.isneginf(want[6:9]))  # zero-length read: log10(0) (LoglessPairHMM.java:47 never runs)
+    _check(got, want, TOL)
+    # a unit without reads and a unit without haplotypes produce no output and no error
+    u = np.array([(0, 0, 0, 3, 0), (0, 3, 0, 0, 0), (0, 2, 1, 3, 0)], dtype=native.UNIT_DTYPE)
+    b2 = Batch(b.read_bases, b.base_q, b.ins_q, b.del_q, b.gcp, b.read_off, b.hap_bases, b.hap_off, u)
+    got2 = hmm.compute(b2)
+    _check(got2, oracle_batch(b2), TOL)
+    empty = Batch(e, e, e, e, e, [0], e, [0], np.zeros(0, dtype=native.UNIT_DTYPE))
+    assert hmm.compute(empty).size == 0  # VectorLoglessPairHMM.java:110-112 early return
+
+
+def test_error_conventions(hmm):
+    b = synth.config1()
+    bad = Batch(b.read_bases, b.base_q, b.ins_q.copy(), b.del_q, b.gcp, b.read_off, b.hap_bases, b.hap_off, b.units)
+    bad.ins_q[5] = 200  # negative as a Java byte: PairHMMModel.java:109 IllegalArgumentException
+    with pytest.raises(native.GpuPhmmError) as e:
+        hmm.compute(bad)
+    assert e.value.code == native.ERR_BAD_QUAL
+    bad2 = Batch(b.read_bases, b.base_q.copy(), b.ins_q, b.del_q, b.gcp, b.read_off, b.hap_bases, b.hap_off, b.units)
+    bad2.base_q[0] = 255  # QualityUtils.java:157 cache index out of bounds
+    with pytest.raises(native.GpuPhmmError):
+        hmm.compute(bad2)
+    # zero-length haplotype: PairHMM.java:139
+    hoff = b.hap_off.copy(); hoff[1] = hoff[0]
+    with pytest.raises(native.GpuPhmmError) as e:
+        hmm.compute(Batch(b.read_bases, b.base_q, b.ins_q, b.del_q, b.gcp, b.read_off, b.hap_bases, hoff, b.units))
+    assert e.value.code == native.ERR_INVALID_ARG
+    # the handle stays usable after an error
+    _check(hmm.compute(b), oracle_batch(b), TOL)
+
+
+def test_async_queue_and_prepared(hmm):
+    batches = [synth.random_batch(300 + k, n_units=3) for k in range(4)]
+    tickets = [hmm.submit(b) for b in batches]
+    for t, b in zip(tickets, batches):
+        _check(hmm.wait(t), oracle_batch(b), TOL)
+    with pytest.raises(native.GpuPhmmError):
+        hmm.wait(tickets[0])  # already collected
+    b = synth.config2(16, pinned=True)
+    p = hmm.prepare(b)
+    out = np.full(b.n_out, np.nan)
+    hmm.run_prepared(p, out)
+    out2 = np.full(b.n_out, np.nan)
+    hmm.run_prepared(p, out2)
+    hmm.release_prepared(p)
+    assert np.array_equal(out, out2)  # idempotent, deterministic
+    _check(out, oracle_batch(b), TOL)
+    assert np.array_equal(out, hmm.compute(b))  # staged path == prepared path, bit for bit
+
+
+def test_chunking_is_invisible():
+    b = synth.config2(24)
+    with GpuPhmm() as big, GpuPhmm(chunk_cells=30_000_000, chunk_bytes=200_000) as small:
+        a, c = big.compute(b), small.compute(b)
+    assert np.array_equal(a, c)
+
+
+def test_invariants_at_scale(hmm):
+    # size-independent properties on a larger slice of configs[1]:
+    #  - permutation invariance: shuffling the unit order permutes the outputs, bit for bit
+    #  - a read's likelihood against a haplotype does not depend on the other haplotypes streamed with it
+    b = synth.config2(300)
+    got = hmm.compute(b)
+    assert np.all(np.isfinite(got)) and np.all(got <= 1e-9)
+    perm = np.random.default_rng(3).permutation(len(b.units))
+    b2 = Batch(b.read_bases, b.base_q, b.ins_q, b.del_q, b.gcp, b.read_off, b.hap_bases, b.hap_off, b.units[perm])
+    assert np.array_equal(hmm.compute(b2), got)
+    u = b.units[7]
+    nh = int(u["hap_end"] - u["hap_begin"]); nr = int(u["read_end"] - u["read_begin"])
+    solo = np.array([(u["read_begin"], u["read_end"], u["hap_begin"] + k, u["hap_begin"] + k + 1, k * nr) for k in range(nh)], dtype=native.UNIT_DTYPE)
+    b3 = Batch(b.read_bases, b.base_q, b.ins_q, b.del_q, b.gcp, b.read_off, b.hap_bases, b.hap_off, solo)
+    g3 = hmm.compute(b3).reshape(nh, nr)
+    ref = got[int(u["out_off"]):int(u["out_off"]) + nr * nh].reshape(nr, nh)
+    assert np.abs(g3.T - ref).max() <= 2e-6  # different c0 exponent per unit => not bit-equal, but float-noise close
