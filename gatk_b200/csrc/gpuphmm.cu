@@ -228,6 +228,7 @@ void plan_chunk(const gphmm_batch *b, int64_t u0, int64_t u1, bool force_fp64, C
         d.n_haps = nh;
         d.out_base = c.n_pairs;
         d.pad0 = d.pad1 = 0;
+        c.streams.insert(c.streams.end(), STREAM_PAD, (uint8_t)CODE_NULL);  // fill/drain codes of the fast kernels
         const uint32_t stream_off = (uint32_t)c.streams.size();
         uint32_t max_h = 1;
         int64_t sum_h = 0;
@@ -260,8 +261,9 @@ void plan_chunk(const gphmm_batch *b, int64_t u0, int64_t u1, bool force_fp64, C
             const uint32_t R = c.read_off[rl + 1] - c.read_off[rl];
             Task t;
             t.read = rl; t.stream_off = stream_off; t.stream_len = stream_len;
-            t.out_base = d.out_base + r * nh; t.c0_exp = d.c0_exp; t.n_haps = nh; t.pad0 = t.pad1 = 0;
-            const uint32_t k = R / 32 + 1;
+            t.out_base = d.out_base + r * nh; t.c0_exp = d.c0_exp; t.n_haps = nh; t.hap_first = d.hap_first; t.pad1 = 0;
+            // fast kernels need two spare rows below the read (accumulator row + row-0 carrier): R + 2 <= 32 K
+            const uint32_t k = (R + 1) / 32 + 1;
             const uint8_t bucket = force_fp64 ? 0 : (k <= 8 ? (uint8_t)(k - 1) : (uint8_t)8);
             raw.push_back(t);
             bucket_of.push_back(bucket);
@@ -294,6 +296,7 @@ struct DeviceChunk {
     size_t off_read_off = 0, off_streams = 0, off_hap_len = 0, off_hap_stream_off = 0, off_units = 0, off_tasks = 0, meta_bytes = 0;
     size_t off_sums = 0, off_out = 0, off_rtasks = 0, off_rsums = 0, off_counters = 0, off_err = 0, work_bytes = 0;
     cudaEvent_t ev_start = nullptr, ev_f32 = nullptr, ev_f64 = nullptr, ev_done = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join[N_FP32_BUCKETS] = {nullptr};  // bucket kernels run on side streams
     bool busy = false;
     void release() {
         reads.release(); meta.release(); work.release(); bnd.release(); h_meta.release(); h_reads.release(); h_out.release();
@@ -301,7 +304,9 @@ struct DeviceChunk {
         if (ev_f32) cudaEventDestroy(ev_f32);
         if (ev_f64) cudaEventDestroy(ev_f64);
         if (ev_done) cudaEventDestroy(ev_done);
-        ev_start = ev_f32 = ev_f64 = ev_done = nullptr;
+        if (ev_fork) cudaEventDestroy(ev_fork);
+        for (auto &e : ev_join) { if (e) cudaEventDestroy(e); e = nullptr; }
+        ev_start = ev_f32 = ev_f64 = ev_done = ev_fork = nullptr;
     }
 };
 
@@ -322,17 +327,28 @@ template <typename T, int K, bool S> KernelInfo kernel_info(int n_codes) {
     return ki;
 }
 
+template <int K> KernelInfo fast_kernel_info(int n_codes) {
+    KernelInfo ki;
+    auto fn = phmm_fast_f32_kernel<K>;
+    ki.fn = (const void *)fn;
+    ki.smem = prior_table_bytes<float, K>(n_codes);
+    if (ki.smem > 48 * 1024) CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ki.smem));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ki.ctas_per_sm, fn, 32, ki.smem));
+    if (ki.ctas_per_sm < 1) throw Error(GPHMM_ERR_ALPHABET, "prior table does not fit in shared memory");
+    return ki;
+}
+
 KernelInfo fp32_kernel(int bucket, int n_codes) {
     switch (bucket) {
-        case 0: return kernel_info<float, 1, false>(n_codes);
-        case 1: return kernel_info<float, 2, false>(n_codes);
-        case 2: return kernel_info<float, 3, false>(n_codes);
-        case 3: return kernel_info<float, 4, false>(n_codes);
-        case 4: return kernel_info<float, 5, false>(n_codes);
-        case 5: return kernel_info<float, 6, false>(n_codes);
-        case 6: return kernel_info<float, 7, false>(n_codes);
-        case 7: return kernel_info<float, 8, false>(n_codes);
-        default: return kernel_info<float, 8, true>(n_codes);
+        case 0: return fast_kernel_info<1>(n_codes);
+        case 1: return fast_kernel_info<2>(n_codes);
+        case 2: return fast_kernel_info<3>(n_codes);
+        case 3: return fast_kernel_info<4>(n_codes);
+        case 4: return fast_kernel_info<5>(n_codes);
+        case 5: return fast_kernel_info<6>(n_codes);
+        case 6: return fast_kernel_info<7>(n_codes);
+        case 7: return fast_kernel_info<8>(n_codes);
+        default: return kernel_info<float, 8, true>(n_codes);  // reads of 255+ bases: striped
     }
 }
 KernelInfo fp64_kernel(int n_codes) { return kernel_info<double, 4, true>(n_codes); }
@@ -353,6 +369,7 @@ struct Device {
         return it->second;
     }
     cudaStream_t streams[2] = {nullptr, nullptr};
+    cudaStream_t aux[2][N_FP32_BUCKETS] = {{nullptr}};  // side streams: the K buckets of a chunk overlap their tails
     DeviceChunk slots[2];
     DevBuf m2m;
     cudaEvent_t ev_step0 = nullptr, ev_step1 = nullptr;  // bracket a whole run_prepared step on streams[0]
@@ -371,6 +388,7 @@ struct Device {
         CK(cudaEventCreate(&ev_step1));
         for (int i = 0; i < 2; ++i) {
             CK(cudaStreamCreateWithFlags(&streams[i], cudaStreamNonBlocking));
+            for (int k = 0; k < N_FP32_BUCKETS; ++k) CK(cudaStreamCreateWithFlags(&aux[i][k], cudaStreamNonBlocking));
             CK(cudaEventCreate(&slots[i].ev_start));
             CK(cudaEventCreate(&slots[i].ev_f32));
             CK(cudaEventCreate(&slots[i].ev_f64));
@@ -383,6 +401,7 @@ struct Device {
             slots[i].release();
             if (streams[i]) cudaStreamDestroy(streams[i]);
             streams[i] = nullptr;
+            for (int k = 0; k < N_FP32_BUCKETS; ++k) { if (aux[i][k]) cudaStreamDestroy(aux[i][k]); aux[i][k] = nullptr; }
         }
         m2m.release();
         if (ev_step0) cudaEventDestroy(ev_step0);
@@ -413,7 +432,7 @@ void upload_chunk(Device &dev, DeviceChunk &dc, const gphmm_batch *b, const Chun
     // metadata blob
     size_t o = 0;
     dc.off_read_off = o; o = align_up(o + c.read_off.size() * 4, 16);
-    dc.off_streams = o; o = align_up(o + c.streams.size() + 64, 16);
+    dc.off_streams = o; o = align_up(o + c.streams.size() + 64, 16);  // + trailing NULL pad
     dc.off_hap_len = o; o = align_up(o + c.hap_len.size() * 4, 16);
     dc.off_hap_stream_off = o; o = align_up(o + c.hap_stream_off.size() * 4, 16);
     dc.off_units = o; o = align_up(o + c.units.size() * sizeof(UnitDesc), 16);
@@ -470,7 +489,7 @@ void upload_chunk(Device &dev, DeviceChunk &dc, const gphmm_batch *b, const Chun
 }
 
 // Queue every kernel of the chunk on `st` (no host sync).  Returns the number of launches.
-int launch_chunk(Device &dev, DeviceChunk &dc, const ChunkPlan &c, cudaStream_t st, const RunOptions &opt, bool download) {
+int launch_chunk(Device &dev, DeviceChunk &dc, const ChunkPlan &c, cudaStream_t st, cudaStream_t *aux, const RunOptions &opt, bool download) {
     int launches = 0;
     uint8_t *meta = (uint8_t *)dc.meta.p, *work = (uint8_t *)dc.work.p;
     uint32_t *counters = (uint32_t *)(work + dc.off_counters);
@@ -486,6 +505,7 @@ int launch_chunk(Device &dev, DeviceChunk &dc, const ChunkPlan &c, cudaStream_t 
     ka.rd_c = ka.rd_d + dc.read_stride;
     ka.read_off = (const uint32_t *)(meta + dc.off_read_off);
     ka.streams = meta + dc.off_streams;
+    ka.hap_len = (const uint32_t *)(meta + dc.off_hap_len);
     ka.m2m = (const double *)dev.m2m.p;
     ka.err = (int *)(work + dc.off_err);
     ka.n_codes = c.n_codes;
@@ -528,22 +548,46 @@ int launch_chunk(Device &dev, DeviceChunk &dc, const ChunkPlan &c, cudaStream_t 
     }
 
     if (!opt.force_fp64) {
+        // The largest bucket runs on the chunk's own stream; the others fork onto side streams so that their
+        // (short, under-filled) grids overlap its tail instead of serialising in front of it.
+        int n_active = 0, main_bucket = -1;
+        uint32_t main_n = 0;
         for (int k = 0; k < N_FP32_BUCKETS; ++k) {
             const uint32_t n = c.bucket_begin[k + 1] - c.bucket_begin[k];
-            if (!n) continue;
-            const KernelInfo &ki = dev.info(k, c.n_codes);
-            const uint32_t grid = std::min<uint32_t>(n, (uint32_t)(dev.n_sms * ki.ctas_per_sm));
-            ka.tasks = (const Task *)(meta + dc.off_tasks) + c.bucket_begin[k];
-            ka.n_tasks = n;
-            ka.n_tasks_ptr = nullptr;
-            ka.counter = counters + k;
-            ka.sums = work + dc.off_sums;
-            ka.bnd = k == 8 ? dc.bnd.p : nullptr;
-            ka.bnd_stride = k == 8 ? c.max_stream_len : 0;
-            void *args[] = {&ka};
-            CK(cudaLaunchKernel(ki.fn, dim3(grid), dim3(32), args, ki.smem, st));
-            ++launches;
+            if (n) ++n_active;
+            if (n > main_n) { main_n = n; main_bucket = k; }
         }
+        if (n_active > 1) {
+            if (!dc.ev_fork) CK(cudaEventCreateWithFlags(&dc.ev_fork, cudaEventDisableTiming));
+            CK(cudaEventRecord(dc.ev_fork, st));
+        }
+        for (int pass = 0; pass < 2; ++pass)
+            for (int k = 0; k < N_FP32_BUCKETS; ++k) {
+                const uint32_t n = c.bucket_begin[k + 1] - c.bucket_begin[k];
+                if (!n || (pass == 0) != (k == main_bucket)) continue;
+                const KernelInfo &ki = dev.info(k, c.n_codes);
+                const uint32_t grid = std::min<uint32_t>(n, (uint32_t)(dev.n_sms * ki.ctas_per_sm));
+                ka.tasks = (const Task *)(meta + dc.off_tasks) + c.bucket_begin[k];
+                ka.n_tasks = n;
+                ka.n_tasks_ptr = nullptr;
+                ka.counter = counters + k;
+                ka.sums = work + dc.off_sums;
+                ka.bnd = k == 8 ? dc.bnd.p : nullptr;
+                ka.bnd_stride = k == 8 ? c.max_stream_len : 0;
+                void *args[] = {&ka};
+                cudaStream_t ks = st;
+                if (k != main_bucket) {
+                    ks = aux[k];
+                    CK(cudaStreamWaitEvent(ks, dc.ev_fork, 0));
+                }
+                CK(cudaLaunchKernel(ki.fn, dim3(grid), dim3(32), args, ki.smem, ks));
+                ++launches;
+                if (k != main_bucket) {
+                    if (!dc.ev_join[k]) CK(cudaEventCreateWithFlags(&dc.ev_join[k], cudaEventDisableTiming));
+                    CK(cudaEventRecord(dc.ev_join[k], ks));
+                    CK(cudaStreamWaitEvent(st, dc.ev_join[k], 0));
+                }
+            }
         CK(cudaEventRecord(dc.ev_f32, st));
         if (ea.n_units) {
             phmm_epilogue_f32<<<std::min<uint32_t>(ea.n_units, 4096), 128, 0, st>>>(ea);
@@ -702,7 +746,7 @@ void device_loop(gphmm *h, Device &dev, const gphmm_batch *b, const std::vector<
             }
             plan_chunk(b, chunks[ci].first, chunks[ci].second, opt.force_fp64, plans[slot]);
             upload_chunk(dev, dev.slots[slot], b, plans[slot], dev.streams[slot], opt.force_fp64, h->stats);
-            launches += launch_chunk(dev, dev.slots[slot], plans[slot], dev.streams[slot], opt, true);
+            launches += launch_chunk(dev, dev.slots[slot], plans[slot], dev.streams[slot], dev.aux[slot], opt, true);
             inflight[slot] = true;
             slot ^= 1;
         }
@@ -1005,7 +1049,7 @@ int gphmm_run_prepared(gphmm_t *h, gphmm_prepared_t *p, double *out) {
                 CK(cudaEventRecord(dev.ev_step0, dev.streams[0]));
                 used[part->device_index] = 1;
             }
-            launches += launch_chunk(dev, part->dc, part->plan, dev.streams[0], opt, out != nullptr);
+            launches += launch_chunk(dev, part->dc, part->plan, dev.streams[0], dev.aux[0], opt, out != nullptr);
         }
         for (size_t d = 0; d < h->devices.size(); ++d)
             if (used[d]) {

@@ -48,14 +48,16 @@ struct __align__(16) Task {
     uint32_t stream_len;  // columns in the stream, one END per haplotype included
     uint32_t out_base;    // slot of the stream's first haplotype in `sums`
     int32_t c0_exp;       // D[0][j] = 2^c0_exp
-    uint32_t n_haps;      // haplotypes in the stream (diagnostic)
-    uint32_t pad0, pad1;
+    uint32_t n_haps;      // haplotypes in the stream
+    uint32_t hap_first;   // chunk-local index of the stream's first haplotype (hap_len[]); rescue: final output slot
+    uint32_t pad1;        // rescue: haplotype length
 };
 
 struct KernelArgs {
     const uint8_t *rd_bases, *rd_q, *rd_i, *rd_d, *rd_c;  // raw per-base read arrays of the chunk
     const uint32_t *read_off;                             // chunk-local, n_reads+1
     const uint8_t *streams;                               // haplotype code streams
+    const uint32_t *hap_len;                              // chunk-local haplotype lengths
     const Task *tasks;
     const uint32_t *n_tasks_ptr;  // device-side task count (rescue lists) or nullptr
     uint32_t n_tasks;             // host-side task count when n_tasks_ptr == nullptr
@@ -257,6 +259,220 @@ __global__ void __launch_bounds__(32) phmm_forward_kernel(const KernelArgs g)
 }
 
 // ---------------------------------------------------------------------------------------------
+// Fast fp32 kernel for reads of up to 32*K-2 bases (one strip).  Same recurrence as above, with the
+// per-step overhead stripped:
+//  * haplotype streams are physically padded with STREAM_PAD NULL codes on both sides, so the
+//    column code is one unguarded byte load;
+//  * the hand-off between lanes is a rotation (lane 0 reads lane 31): the last row of lane 31 is a
+//    pad row that holds (M, I~, D~) = (0, *, c0), which is exactly the virtual row 0 lane 0 needs
+//    (its b and g coefficients are 0 because I~ of row 0 is 0) -- no per-step lane-0 selects;
+//  * the row below the read (row R+1) is an accumulator row: a=1, b=tMI_R, prior=1, tDD=1 make
+//        M[R+1][j]  = (M+I)[R][j-1]          D~[R+1][j] = sum_{j' < j-1} (M+I)[R][j']
+//    so the haplotype's likelihood sum is M+D~ of that row at the END column -- no per-step add;
+//  * the prior table is addressed with one IMAD from a precomputed 32-bit shared address.
+// ---------------------------------------------------------------------------------------------
+constexpr int STREAM_PAD = 32;
+
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+
+__device__ __forceinline__ uint32_t ldg_u8(const uint8_t *p) {
+    uint32_t v;
+    asm volatile("ld.global.nc.u8 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+
+// Per-warp register state of the fast kernel.
+template <int K> struct FastState {
+    float M[K], I[K], D[K];
+    float dgm, dgi, dgd;  // row above this lane's first row, previous column
+    uint32_t y;           // haplotype code of this lane's current column
+    const uint8_t *sp;    // points at that code
+    uint32_t hap_idx;
+};
+
+// One wavefront step.  CHECKED steps handle the END column (haplotype boundary); unchecked steps may only
+// run while no lane of the warp sits on an END column, which the caller guarantees from the haplotype
+// lengths -- that loop is branch-free.
+template <int K, bool CHECKED>
+__device__ __forceinline__ void fast_step(FastState<K> &st, const float (&ca)[K], const float (&cb)[K], const float (&cc)[K],
+                                          const float (&cg)[K], const float (&cd)[K], uint32_t tab_lane, int src_lane, int lane,
+                                          int acc_lane, int acc_slot, float c0, float *sums_task)
+{
+    constexpr int NV = (K + 3) / 4;
+    constexpr unsigned FULL = 0xffffffffu;
+    constexpr uint32_t CODE_STRIDE = NV * 32 * 16;
+    ++st.sp;
+    const uint32_t y_next = ldg_u8(st.sp);
+    const float mu = __shfl_sync(FULL, st.M[K - 1], src_lane);
+    const float iu = __shfl_sync(FULL, st.I[K - 1], src_lane);
+    const float du = __shfl_sync(FULL, st.D[K - 1], src_lane);
+    float pr[NV * 4];
+    {
+        const uint32_t addr = st.y * CODE_STRIDE + tab_lane;
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+            const float4 q = lds128(addr + v * 512);
+            pr[v * 4 + 0] = q.x; pr[v * 4 + 1] = q.y; pr[v * 4 + 2] = q.z; pr[v * 4 + 3] = q.w;
+        }
+    }
+    float Mn[K];
+    {
+        float u = cc[0] * st.dgd;
+        u = __fmaf_rn(cb[0], st.dgi, u);
+        u = __fmaf_rn(ca[0], st.dgm, u);
+        Mn[0] = pr[0] * u;
+    }
+#pragma unroll
+    for (int k = 1; k < K; ++k) {
+        float u = cc[k] * st.D[k - 1];
+        u = __fmaf_rn(cb[k], st.I[k - 1], u);
+        u = __fmaf_rn(ca[k], st.M[k - 1], u);
+        Mn[k] = pr[k] * u;
+    }
+#pragma unroll
+    for (int k = 0; k < K; ++k) st.D[k] = __fmaf_rn(cd[k], st.D[k], st.M[k]);
+    st.I[0] = __fmaf_rn(cg[0], iu, mu);
+#pragma unroll
+    for (int k = 1; k < K; ++k) st.I[k] = __fmaf_rn(cg[k], st.I[k - 1], Mn[k - 1]);
+#pragma unroll
+    for (int k = 0; k < K; ++k) st.M[k] = Mn[k];
+    st.dgm = mu; st.dgi = iu; st.dgd = du;
+    if (CHECKED) {
+        if (st.y == CODE_END) {
+            if (lane == acc_lane) {
+                float v = 0.f;
+#pragma unroll
+                for (int k = 0; k < K; ++k)
+                    if (k == acc_slot) v = st.M[k] + st.D[k];
+                sums_task[st.hap_idx] = v;
+            }
+            ++st.hap_idx;
+#pragma unroll
+            for (int k = 0; k < K; ++k) { st.M[k] = 0.f; st.D[k] = 0.f; }
+            if (lane == 31) st.D[K - 1] = c0;
+        }
+    }
+    st.y = y_next;
+}
+
+template <int K>
+__global__ void __launch_bounds__(32) phmm_fast_f32_kernel(const KernelArgs g)
+{
+    constexpr int NV = (K + 3) / 4;
+    constexpr unsigned FULL = 0xffffffffu;
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float *tab_s = reinterpret_cast<float *>(smem_raw);
+    int lane, src_lane;
+    // opaque to the optimiser: keeps lane / rotation source in registers instead of re-deriving them every step
+    asm volatile("mov.u32 %0, %%laneid;" : "=r"(lane));
+    asm volatile("{ .reg .u32 t; add.u32 t, %1, 31; and.b32 %0, t, 31; }" : "=r"(src_lane) : "r"(lane));
+    const uint32_t tab_lane = (uint32_t)__cvta_generic_to_shared(smem_raw) + lane * 16;
+    float *const sums = reinterpret_cast<float *>(g.sums);
+    const uint32_t n_tasks = g.n_tasks;
+    const int n_codes = g.n_codes;
+
+    for (;;) {
+        uint32_t ti = 0;
+        if (lane == 0) ti = atomicAdd(g.counter, 1u);
+        ti = __shfl_sync(FULL, ti, 0);
+        if (ti >= n_tasks) break;
+        const Task t = g.tasks[ti];
+        const uint32_t ro = g.read_off[t.read];
+        const int R = (int)(g.read_off[t.read + 1] - ro);  // host guarantees R + 2 <= 32 * K
+        const float c0 = (float)scalbn(1.0, t.c0_exp);
+        const int acc_lane = R / K, acc_slot = R % K;  // accumulator row = 0-based row R
+
+        float ca[K], cb[K], cc[K], cg[K], cd[K];
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const int i = lane * K + k + 1;  // 1-based read row
+            double A = 0.0, B = 0.0, C = 0.0, G = 0.0, DD = 0.0, pm = 0.0, px = 0.0;
+            uint32_t x = 0;
+            const bool real = i <= R;
+            if (real) {
+                uint32_t q = g.rd_q[ro + i - 1], qi = g.rd_i[ro + i - 1], qd = g.rd_d[ro + i - 1], qc = g.rd_c[ro + i - 1];
+                x = g.rd_bases[ro + i - 1];
+                if (q > (uint32_t)MAX_QUAL || qi > 127u || qd > 127u || qc > 127u) {
+                    atomicExch(g.err, 1);
+                    q = min(q, (uint32_t)MAX_QUAL); qi = min(qi, 127u); qd = min(qd, 127u); qc = min(qc, 127u);
+                }
+                const double ei = c_eps[qi], ec = c_eps[qc];
+                const uint32_t mn = min(qi, qd), mx = max(qi, qd);
+                const double tIM = 1.0 - ec;
+                A = __ldg(g.m2m + ((mx * (mx + 1)) >> 1) + mn);
+                if (i > 1) {
+                    const double tmi_prev = c_eps[min((uint32_t)g.rd_i[ro + i - 2], 127u)];
+                    const double tmd_prev = c_eps[min((uint32_t)g.rd_d[ro + i - 2], 127u)];
+                    B = tIM * tmi_prev;
+                    C = tIM * tmd_prev;
+                    G = ec * tmi_prev / ei;
+                } else {
+                    C = tIM;  // row 0: D~ = c0 (tMD_0 = 1); I~ of row 0 is 0, so b = g = 0 and the rotated-in value is ignored
+                }
+                DD = ec;
+                const double e = c_eps[q];
+                pm = 1.0 - e;
+                px = g.tristate_off ? e : e / 3.0;
+            } else if (i == R + 1) {  // accumulator row
+                A = 1.0;
+                B = R >= 1 ? c_eps[min((uint32_t)g.rd_i[ro + R - 1], 127u)] : 0.0;
+                DD = 1.0;
+            }
+            if (lane == 31 && k == K - 1) DD = 1.0;  // carrier of the virtual row 0: keeps D~ = c0
+            ca[k] = (float)A; cb[k] = (float)B; cc[k] = (float)C; cg[k] = (float)G; cd[k] = (float)DD;
+            const float pmf = (float)pm, pxf = (float)px;
+            for (int y = 0; y < n_codes; ++y) {
+                float v = 0.f;
+                if (real) {
+                    if (y >= (int)CODE_FIRST_BASE) {
+                        const uint32_t hb = g.code_byte[y];
+                        v = (x == hb || x == (uint32_t)'N' || hb == (uint32_t)'N') ? pmf : pxf;  // LoglessPairHMM.java:89
+                    }
+                } else if (i == R + 1) {
+                    v = 1.f;
+                }
+                tab_s[((y * NV + k / 4) * 32 + lane) * 4 + (k % 4)] = v;
+            }
+        }
+        __syncwarp();
+
+        FastState<K> st;
+#pragma unroll
+        for (int k = 0; k < K; ++k) { st.M[k] = 0.f; st.I[k] = 0.f; st.D[k] = 0.f; }
+        if (lane == 31) st.D[K - 1] = c0;
+        st.dgm = 0.f; st.dgi = 0.f; st.dgd = lane == 0 ? c0 : 0.f;
+        st.hap_idx = 0;
+        // lane l works on column (step - l); columns <= 0 and > P read the NULL padding around the stream
+        st.sp = g.streams + t.stream_off - lane;
+        st.y = ldg_u8(st.sp);
+        float *const sums_task = sums + t.out_base;
+
+        // Step s (1-based) puts lane l on column s - l.  Haplotype h ends with an END column at stream position
+        // e_h; some lane sits on it during steps e_h .. e_h + 31.  Everything else runs the branch-free loop.
+        int step = 1, e = 0;
+        for (uint32_t h = 0; h < t.n_haps; ++h) {
+            e += (int)g.hap_len[t.hap_first + h] + 1;
+            const int n_free = e - step;
+#pragma unroll 2
+            for (int s = 0; s < n_free; ++s)
+                fast_step<K, false>(st, ca, cb, cc, cg, cd, tab_lane, src_lane, lane, acc_lane, acc_slot, c0, sums_task);
+            if (n_free > 0) step = e;
+            const int n_chk = e + 32 - step;
+#pragma unroll 1
+            for (int s = 0; s < n_chk; ++s)
+                fast_step<K, true>(st, ca, cb, cc, cg, cd, tab_lane, src_lane, lane, acc_lane, acc_slot, c0, sums_task);
+            step = e + 32;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Epilogue: raw sums -> log10 likelihoods (LoglessPairHMM.java:67), rescue-list construction.
 // ---------------------------------------------------------------------------------------------
 struct UnitDesc {
@@ -307,7 +523,7 @@ __global__ void __launch_bounds__(128) phmm_epilogue_f32(const EpilogueArgs e)
                     while ((1u << lg) < H) ++lg;
                     t.c0_exp = C0_BASE_EXP_F64 - lg;
                     t.n_haps = 1;
-                    t.pad0 = d.out_base + k;  // final output slot
+                    t.hap_first = d.out_base + k;  // final output slot
                     t.pad1 = H;
                     e.rescue_tasks[slot] = t;
                 }
@@ -341,7 +557,7 @@ __global__ void __launch_bounds__(128) phmm_epilogue_rescue(const Task *tasks, c
     const uint32_t n = min(*n_rescue, capacity);
     for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
         const Task t = tasks[k];
-        out[t.pad0] = log10(sums[k]) - log10_c0H(t.c0_exp, t.pad1);
+        out[t.hap_first] = log10(sums[k]) - log10_c0H(t.c0_exp, t.pad1);
     }
 }
 
