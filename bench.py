@@ -148,6 +148,7 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from gatk_b200 import sharding
     from gatk_b200.native import GpuPhmm
 
     def barrier():
@@ -157,7 +158,8 @@ def main():
         torch.cuda.synchronize()
 
     t_gen = time.time()
-    batch = synth.config2(args.regions, pinned=True, first_region=rank * args.regions)
+    first_region, n_regions = sharding.region_slice(rank, world, args.regions)
+    batch = synth.config2(n_regions, pinned=True, first_region=first_region)
     t_gen = time.time() - t_gen
     cells, pairs = batch.cells(), batch.pairs()
     out = np.full(batch.n_out, np.nan, dtype=np.float64)
@@ -195,13 +197,8 @@ def main():
     e2e_wall = time.perf_counter() - t0
     st2 = hmm.stats()
 
-    tm = torch.tensor([dev_s, wall, e2e_wall, f32_s], dtype=torch.float64, device="cuda")
-    tot = torch.tensor([float(cells), float(pairs), float(st["rescued_pairs"])], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-    dev_s, wall, e2e_wall, f32_s_max = (float(x) for x in tm.tolist())
-    cells_all, pairs_all, rescued_all = (float(x) for x in tot.tolist())
+    (dev_s, wall, e2e_wall, f32_s_max), (cells_all, pairs_all, rescued_all) = sharding.reduce_timing(
+        [dev_s, wall, e2e_wall, f32_s], [float(cells), float(pairs), float(st["rescued_pairs"])], device="cuda")
 
     if rank == 0:
         steps = args.steps

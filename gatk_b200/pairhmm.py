@@ -1,0 +1,136 @@
+"""Host-side mirror of the reference's PairHMM plugin surface for the CUDA path, used by tests and examples.
+
+The real plugin is Java (java/org/broadinstitute/hellbender/utils/pairhmm/CudaLoglessPairHMM.java); this image
+has no JVM, so this module restates the same surface -- names, argument meaning, error behaviour -- over the
+same C ABI, without any arithmetic of its own:
+
+  PairHMM.Implementation.makeNewHMM(args)                    PairHMM.java:40-109
+  PairHMMNativeArguments{maxNumberOfThreads,useDoublePrecision}   PairHMMNativeArgumentCollection.java:18-23
+  initialize(haplotypes, perSampleReadList, readMaxLength, haplotypeMaxLength)   VectorLoglessPairHMM.java:89-102
+  computeLog10Likelihoods(logLikelihoods, processedReads, inputScoreImputator)   VectorLoglessPairHMM.java:108-159
+  getLogLikelihoodArray() / close()                          PairHMM.java:357-359,391-402
+"""
+import enum
+from dataclasses import dataclass
+from typing import Callable, Dict, List, Optional, Sequence
+
+import numpy as np
+
+from .native import Batch, GpuPhmm, GpuPhmmError, ERR_NO_DEVICE
+
+
+class HardwareFeatureException(RuntimeError):
+    """UserException.HardwareFeatureException (exceptions/UserException.java:435-445)."""
+
+
+@dataclass
+class PairHMMNativeArguments:
+    maxNumberOfThreads: int = 4          # --native-pair-hmm-threads
+    useDoublePrecision: bool = False     # --native-pair-hmm-use-double-precision
+
+
+@dataclass
+class Read:
+    """The five per-base arrays the binding reads from a GATKRead + its imputed scores (VectorLoglessPairHMM.java:120-129)."""
+    bases: bytes
+    base_quals: Sequence[int]
+    ins_quals: Optional[Sequence[int]] = None   # BI tag or the flat default
+    del_quals: Optional[Sequence[int]] = None   # BD tag or the flat default
+
+
+class StandardPairHMMInputScoreImputator:
+    """StandardPairHMMInputScoreImputator.java:27-47: BI/BD tags if present else flat Q45 (ReadUtils.java:44,838-862),
+    flat gap-continuation penalty (--pair-hmm-gap-continuation-penalty, default 10)."""
+    DEFAULT_INSERTION_DELETION_QUAL = 45
+
+    def __init__(self, constant_gcp=10):
+        self.constant_gcp = constant_gcp
+
+    def impute(self, read: Read):
+        n = len(read.bases)
+        flat = np.full(n, self.DEFAULT_INSERTION_DELETION_QUAL, dtype=np.uint8)
+        ins = flat if read.ins_quals is None else np.asarray(read.ins_quals, dtype=np.uint8)
+        dele = flat if read.del_quals is None else np.asarray(read.del_quals, dtype=np.uint8)
+        return ins, dele, np.full(n, self.constant_gcp, dtype=np.uint8)
+
+
+class LikelihoodMatrix:
+    """Minimal LikelihoodMatrix: values[allele][read] (AlleleLikelihoods.java:71-74,1418-1421 is allele-major)."""
+
+    def __init__(self, alleles: List[bytes], n_reads: int):
+        self._alleles = list(alleles)
+        self.values = np.full((len(alleles), n_reads), np.nan)
+
+    def alleles(self):
+        return self._alleles
+
+    def numberOfAlleles(self):
+        return len(self._alleles)
+
+    def set(self, allele_index, read_index, value):
+        self.values[allele_index, read_index] = value
+
+
+class CudaLoglessPairHMM:
+    """Mirror of CudaLoglessPairHMM.java / VectorLoglessPairHMM.java over libgpuphmm."""
+
+    def __init__(self, args: Optional[PairHMMNativeArguments] = None, devices=None):
+        args = args or PairHMMNativeArguments()
+        try:
+            self._hmm = GpuPhmm(devices=devices, force_fp64=args.useDoublePrecision, host_threads=args.maxNumberOfThreads)
+        except GpuPhmmError as e:
+            if e.code == ERR_NO_DEVICE:
+                raise HardwareFeatureException("Machine does not support the CUDA PairHMM.") from e
+            raise
+        self._haps: List[bytes] = []
+        self._hap_index: Dict[bytes, int] = {}
+        self.mLogLikelihoodArray = None
+        self._initialized = False
+
+    def initialize(self, haplotypes: List[bytes], perSampleReadList=None, readMaxLength=0, haplotypeMaxLength=0):
+        self._haps = [bytes(h) for h in haplotypes]
+        self._hap_index = {h: i for i, h in enumerate(self._haps)}
+        self._initialized = True
+
+    def computeLog10Likelihoods(self, logLikelihoods: LikelihoodMatrix, processedReads: List[Read], inputScoreImputator):
+        if not processedReads:
+            return  # VectorLoglessPairHMM.java:110-112
+        if not self._initialized:
+            raise RuntimeError("Must call initialize before calling computeLog10Likelihoods")  # PairHMM.java:284
+        rows = []
+        for r in processedReads:
+            ins, dele, gcp = inputScoreImputator.impute(r)
+            q = np.asarray(r.base_quals, dtype=np.uint8)
+            if not (len(q) == len(ins) == len(dele) == len(gcp) == len(r.bases)):
+                raise ValueError("Read bases and read quals aren't the same size")  # PairHMM.java:286-292
+            rows.append((r.bases, q, ins, dele, gcp))
+        batch = Batch.single_unit(rows, self._haps)
+        self.mLogLikelihoodArray = self._hmm.compute(batch)
+        n_haps = len(self._haps)
+        for r in range(len(processedReads)):
+            for hap_idx, hap in enumerate(logLikelihoods.alleles()):
+                logLikelihoods.set(hap_idx, r, self.mLogLikelihoodArray[r * n_haps + self._hap_index[bytes(hap)]])
+
+    def getLogLikelihoodArray(self):
+        return self.mLogLikelihoodArray
+
+    def close(self):
+        self._hmm.close()
+
+
+class Implementation(enum.Enum):
+    """PairHMM.Implementation (PairHMM.java:40-109).  Only the CUDA entry is constructible here; the Java/AVX entries
+    belong to the reference and are listed so that the registry reads the same.  FASTEST_AVAILABLE does not include
+    CUDA_LOGLESS_CACHING."""
+    EXACT = "EXACT"
+    ORIGINAL = "ORIGINAL"
+    LOGLESS_CACHING = "LOGLESS_CACHING"
+    AVX_LOGLESS_CACHING = "AVX_LOGLESS_CACHING"
+    AVX_LOGLESS_CACHING_OMP = "AVX_LOGLESS_CACHING_OMP"
+    CUDA_LOGLESS_CACHING = "CUDA_LOGLESS_CACHING"
+    FASTEST_AVAILABLE = "FASTEST_AVAILABLE"
+
+    def makeNewHMM(self, args: Optional[PairHMMNativeArguments] = None):
+        if self is Implementation.CUDA_LOGLESS_CACHING:
+            return CudaLoglessPairHMM(args)
+        raise NotImplementedError("%s is implemented by the reference (Java / GKL), not by this package" % self.name)

@@ -84,3 +84,40 @@ def test_batch_validation():
     b = synth.config1()
     with pytest.raises(ValueError):
         native.Batch(b.read_bases, b.base_q[:-1], b.ins_q, b.del_q, b.gcp, b.read_off, b.hap_bases, b.hap_off, b.units)
+
+
+def test_jni_shim_syntax_and_symbols():
+    # no JDK in this image: compile the shim against the minimal stub header (syntax + types only)
+    import subprocess
+    src = os.path.join(ROOT, "gatk_b200", "csrc", "gpuphmm_jni.cpp")
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    subprocess.run([cxx, "-std=c++17", "-fsyntax-only", "-Wall", "-I", os.path.join(ROOT, "tests", "jni_stub"), src], check=True)
+    # every native method of the Java binding has its JNI export, and vice versa
+    java = open(os.path.join(ROOT, "java/org/broadinstitute/hellbender/utils/pairhmm/CudaPairHMMBinding.java")).read()
+    natives = set(re.findall(r"private static native [\w\[\]]+ (\w+)\(", java))
+    exported = set(re.findall(r"JNIFN\((\w+)\)\(", open(src).read()))
+    assert natives == exported and len(natives) == 8
+
+
+def test_java_plugin_sources_present():
+    hmm = open(os.path.join(ROOT, "java/org/broadinstitute/hellbender/utils/pairhmm/CudaLoglessPairHMM.java")).read()
+    assert "extends LoglessPairHMM" in hmm and "HardwareFeatureException" in hmm
+    for method in ("initialize(final List<Haplotype>", "computeLog10Likelihoods(final LikelihoodMatrix<GATKRead, Haplotype>", "public void close()"):
+        assert method in hmm
+    patch = open(os.path.join(ROOT, "java/patches/PairHMM.Implementation.patch")).read()
+    assert "CUDA_LOGLESS_CACHING(args ->" in patch
+    added = [l for l in patch.splitlines() if l.startswith("+") and not l.startswith("+++")]
+    assert not any("FASTEST_AVAILABLE" in l for l in added)  # the default chain is untouched
+
+
+def test_plugin_mirror_without_gpu():
+    import torch
+    from gatk_b200 import pairhmm
+    assert [e.name for e in pairhmm.Implementation] == ["EXACT", "ORIGINAL", "LOGLESS_CACHING", "AVX_LOGLESS_CACHING",
+                                                         "AVX_LOGLESS_CACHING_OMP", "CUDA_LOGLESS_CACHING", "FASTEST_AVAILABLE"]
+    if not torch.cuda.is_available():
+        with pytest.raises(pairhmm.HardwareFeatureException):  # VectorLoglessPairHMM.java:63-66 convention: throw, no fallback
+            pairhmm.Implementation.CUDA_LOGLESS_CACHING.makeNewHMM(pairhmm.PairHMMNativeArguments())
+    imp = pairhmm.StandardPairHMMInputScoreImputator(10)
+    ins, dele, gcp = imp.impute(pairhmm.Read(b"ACGT", [30, 30, 30, 30]))
+    assert list(ins) == [45] * 4 and list(dele) == [45] * 4 and list(gcp) == [10] * 4

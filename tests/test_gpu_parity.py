@@ -270,3 +270,47 @@ def test_invariants_at_scale(hmm):
     g3 = hmm.compute(b3).reshape(nh, nr)
     ref = got[int(u["out_off"]):int(u["out_off"]) + nr * nh].reshape(nr, nh)
     assert np.abs(g3.T - ref).max() <= 2e-6  # different c0 exponent per unit => not bit-equal, but float-noise close
+
+
+def test_plugin_surface_like_vector_pairhmm_unit_test():
+    # VectorPairHMMUnitTest.java:31-106 through the mirrored plugin surface: one haplotype x one read per call,
+    # initialize() + computeLog10Likelihoods() + getLogLikelihoodArray(), tolerance 1e-5 (:100)
+    from gatk_b200 import pairhmm
+    args = pairhmm.PairHMMNativeArguments(maxNumberOfThreads=1, useDoublePrecision=False)
+    hmm = pairhmm.Implementation.CUDA_LOGLESS_CACHING.makeNewHMM(args)
+    try:
+        for r in load_testdata():
+            hap = r["hap"]
+            read = pairhmm.Read(r["read"], r["base_q"], r["ins_q"], r["del_q"])
+
+            class Imputator:
+                def impute(self, read_):
+                    return r["ins_q"], r["del_q"], r["gcp"]
+
+            hmm.initialize([hap], None, 0, 0)
+            m = pairhmm.LikelihoodMatrix([hap], 1)
+            hmm.computeLog10Likelihoods(m, [read], Imputator())
+            la = hmm.getLogLikelihoodArray()
+            assert abs(la[0] - r["expected"]) <= 1e-5
+            assert m.values[0, 0] == la[0]
+        # PairHMMUnitTest.java:510-536 testLikelihoodsFromHaplotypes: empty read list leaves the array untouched
+        hmm2 = pairhmm.CudaLoglessPairHMM(args)
+        hmm2.initialize([b"A" * 20])
+        hmm2.computeLog10Likelihoods(pairhmm.LikelihoodMatrix([b"A" * 20], 0), [], pairhmm.StandardPairHMMInputScoreImputator(100))
+        assert hmm2.getLogLikelihoodArray() is None
+        rd = pairhmm.Read(b"A" * 10, [20] * 10, [100] * 10, [100] * 10)
+        m = pairhmm.LikelihoodMatrix([b"A" * 20], 1)
+        hmm2.computeLog10Likelihoods(m, [rd], pairhmm.StandardPairHMMInputScoreImputator(100))
+        expected = math.log10((abs(20 - 10 + 1) / 20.0) * 0.99 ** 10)
+        assert abs(hmm2.getLogLikelihoodArray()[0] - expected) <= 1e-3
+        # haplotype order of the matrix may differ from initialize() order (VectorLoglessPairHMM.java:141-153)
+        haps = [b"ACGTACGTACGTAAAC", b"ACGTACGTACGTCCCA", b"TTGTACGTACGTCCCA"]
+        hmm2.initialize(haps)
+        m = pairhmm.LikelihoodMatrix(haps[::-1], 1)
+        rd = pairhmm.Read(b"ACGTACGTACGTA", [30] * 13)
+        hmm2.computeLog10Likelihoods(m, [rd], pairhmm.StandardPairHMMInputScoreImputator(10))
+        la = hmm2.getLogLikelihoodArray()
+        assert [m.values[k, 0] for k in range(3)] == [la[2], la[1], la[0]]
+        hmm2.close()
+    finally:
+        hmm.close()
