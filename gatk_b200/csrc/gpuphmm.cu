@@ -113,7 +113,9 @@ struct PinBuf {
 };
 
 constexpr int N_FP32_BUCKETS = 9;  // K = 1..8 plain, bucket 8 = striped K=8 (reads of 256+ bases)
-constexpr int N_COUNTERS = 16;     // [0..8] fp32 buckets, [9] fp64 queue, [10] n_rescue, [11] forced fp64 queue
+constexpr int N_AUX = N_FP32_BUCKETS + 8 * MAX_FLAT_CLASSES;  // side streams: general buckets + flat (class, bucket)
+constexpr int N_COUNTERS = 64;     // [0..8] general fp32 buckets, [9] fp64 queue, [10] n_rescue, [11] forced fp64 queue,
+                                   // [16 + 8*c + k] flat-quality kernels: class c, bucket k
 
 // Host-side plan of one device chunk: which units, and every metadata array the kernels need.
 struct ChunkPlan {
@@ -131,6 +133,8 @@ struct ChunkPlan {
     std::vector<UnitDesc> units;
     std::vector<Task> tasks;               // bucket-sorted
     uint32_t bucket_begin[N_FP32_BUCKETS + 1];
+    int n_classes = 0;                     // flat-quality classes sampled from the chunk's reads
+    uint8_t class_qi[MAX_FLAT_CLASSES], class_qd[MAX_FLAT_CLASSES], class_qc[MAX_FLAT_CLASSES];
 };
 
 int ceil_log2(uint32_t v) {
@@ -204,6 +208,22 @@ void plan_chunk(const gphmm_batch *b, int64_t u0, int64_t u1, bool force_fp64, C
     const int64_t n_span = c.r_hi - c.r_lo;
     c.read_off.resize(n_span + 1);
     for (int64_t r = 0; r <= n_span; ++r) c.read_off[r] = (uint32_t)(b->read_off[c.r_lo + r] - c.base_lo);
+
+    // flat-quality classes: (ins, del, gcp) triples seen on the first base of a sample of the chunk's reads; the
+    // device decides per read whether it really is flat (phmm_classify_kernel)
+    c.n_classes = 0;
+    if (!force_fp64 && n_span > 0) {
+        const int64_t stride = std::max<int64_t>(1, n_span / 256);
+        for (int64_t r = 0; r < n_span && c.n_classes < MAX_FLAT_CLASSES; r += stride) {
+            const int64_t o = b->read_off[c.r_lo + r];
+            if (b->read_off[c.r_lo + r + 1] == o) continue;
+            const uint8_t qi = b->ins_q[o], qd = b->del_q[o], qc = b->gcp[o];
+            if (qi > 127 || qd > 127 || qc > 127) continue;
+            bool seen = false;
+            for (int k = 0; k < c.n_classes; ++k) seen = seen || (c.class_qi[k] == qi && c.class_qd[k] == qd && c.class_qc[k] == qc);
+            if (!seen) { c.class_qi[c.n_classes] = qi; c.class_qd[c.n_classes] = qd; c.class_qc[c.n_classes] = qc; ++c.n_classes; }
+        }
+    }
 
     // haplotype alphabet of the chunk: A C G T N are fixed codes, any other byte value gets the next free code
     int16_t lut[256];
@@ -294,9 +314,9 @@ struct DeviceChunk {
     PinBuf h_out;   // pinned result buffer (out doubles + counters + err)
     size_t read_stride = 0;
     size_t off_read_off = 0, off_streams = 0, off_hap_len = 0, off_hap_stream_off = 0, off_units = 0, off_tasks = 0, meta_bytes = 0;
-    size_t off_sums = 0, off_out = 0, off_rtasks = 0, off_rsums = 0, off_counters = 0, off_err = 0, work_bytes = 0;
+    size_t off_sums = 0, off_out = 0, off_rtasks = 0, off_rsums = 0, off_counters = 0, off_err = 0, off_class = 0, work_bytes = 0;
     cudaEvent_t ev_start = nullptr, ev_f32 = nullptr, ev_f64 = nullptr, ev_done = nullptr;
-    cudaEvent_t ev_fork = nullptr, ev_join[N_FP32_BUCKETS] = {nullptr};  // bucket kernels run on side streams
+    cudaEvent_t ev_fork = nullptr, ev_join[N_AUX] = {nullptr};  // bucket kernels run on side streams
     bool busy = false;
     void release() {
         reads.release(); meta.release(); work.release(); bnd.release(); h_meta.release(); h_reads.release(); h_out.release();
@@ -351,12 +371,38 @@ KernelInfo fp32_kernel(int bucket, int n_codes) {
         default: return kernel_info<float, 8, true>(n_codes);  // reads of 255+ bases: striped
     }
 }
+template <int K> KernelInfo flat_kernel_info(int n_codes) {
+    KernelInfo ki;
+    auto fn = phmm_flat_f32_kernel<K>;
+    ki.fn = (const void *)fn;
+    ki.smem = prior_table_bytes<float, K>(n_codes);
+    if (ki.smem > 48 * 1024) CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ki.smem));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ki.ctas_per_sm, fn, 32, ki.smem));
+    if (ki.ctas_per_sm < 1) throw Error(GPHMM_ERR_ALPHABET, "prior table does not fit in shared memory");
+    return ki;
+}
+
+KernelInfo flat_kernel(int bucket, int n_codes) {
+    switch (bucket) {
+        case 0: return flat_kernel_info<1>(n_codes);
+        case 1: return flat_kernel_info<2>(n_codes);
+        case 2: return flat_kernel_info<3>(n_codes);
+        case 3: return flat_kernel_info<4>(n_codes);
+        case 4: return flat_kernel_info<5>(n_codes);
+        case 5: return flat_kernel_info<6>(n_codes);
+        case 6: return flat_kernel_info<7>(n_codes);
+        default: return flat_kernel_info<8>(n_codes);
+    }
+}
+
 KernelInfo fp64_kernel(int n_codes) { return kernel_info<double, 4, true>(n_codes); }
 
 struct Stats {
     std::mutex mu;
     gphmm_stats s{};
 };
+
+constexpr int FLAT_KEY = 16;  // Device::info key of the flat-quality kernel of bucket k is FLAT_KEY + k
 
 struct Device {
     int ordinal = 0;
@@ -365,11 +411,13 @@ struct Device {
     const KernelInfo &info(int bucket, int n_codes) {
         const int key = bucket * 1024 + n_codes;
         auto it = kinfo.find(key);
-        if (it == kinfo.end()) it = kinfo.emplace(key, bucket < N_FP32_BUCKETS ? fp32_kernel(bucket, n_codes) : fp64_kernel(n_codes)).first;
+        if (it == kinfo.end())
+            it = kinfo.emplace(key, bucket < N_FP32_BUCKETS ? fp32_kernel(bucket, n_codes)
+                                    : bucket == N_FP32_BUCKETS ? fp64_kernel(n_codes) : flat_kernel(bucket - FLAT_KEY, n_codes)).first;
         return it->second;
     }
     cudaStream_t streams[2] = {nullptr, nullptr};
-    cudaStream_t aux[2][N_FP32_BUCKETS] = {{nullptr}};  // side streams: the K buckets of a chunk overlap their tails
+    cudaStream_t aux[2][N_AUX] = {{nullptr}};  // side streams: the kernels of a chunk overlap their tails
     DeviceChunk slots[2];
     DevBuf m2m;
     cudaEvent_t ev_step0 = nullptr, ev_step1 = nullptr;  // bracket a whole run_prepared step on streams[0]
@@ -388,7 +436,7 @@ struct Device {
         CK(cudaEventCreate(&ev_step1));
         for (int i = 0; i < 2; ++i) {
             CK(cudaStreamCreateWithFlags(&streams[i], cudaStreamNonBlocking));
-            for (int k = 0; k < N_FP32_BUCKETS; ++k) CK(cudaStreamCreateWithFlags(&aux[i][k], cudaStreamNonBlocking));
+            for (int k = 0; k < N_AUX; ++k) CK(cudaStreamCreateWithFlags(&aux[i][k], cudaStreamNonBlocking));
             CK(cudaEventCreate(&slots[i].ev_start));
             CK(cudaEventCreate(&slots[i].ev_f32));
             CK(cudaEventCreate(&slots[i].ev_f64));
@@ -401,7 +449,7 @@ struct Device {
             slots[i].release();
             if (streams[i]) cudaStreamDestroy(streams[i]);
             streams[i] = nullptr;
-            for (int k = 0; k < N_FP32_BUCKETS; ++k) { if (aux[i][k]) cudaStreamDestroy(aux[i][k]); aux[i][k] = nullptr; }
+            for (int k = 0; k < N_AUX; ++k) { if (aux[i][k]) cudaStreamDestroy(aux[i][k]); aux[i][k] = nullptr; }
         }
         m2m.release();
         if (ev_step0) cudaEventDestroy(ev_step0);
@@ -458,6 +506,7 @@ void upload_chunk(Device &dev, DeviceChunk &dc, const gphmm_batch *b, const Chun
     const size_t d2h_bytes = o;  // out | counters | err are contiguous and downloaded together
     dc.off_rtasks = o; o = align_up(o + (force_fp64 ? 0 : np * sizeof(Task)), 16);
     dc.off_rsums = o; o = align_up(o + (force_fp64 ? 0 : np * 8), 16);
+    dc.off_class = o; o = align_up(o + c.read_off.size(), 16);
     dc.work_bytes = o;
     dc.work.reserve(dc.work_bytes);
     dc.h_out.reserve(d2h_bytes);
@@ -548,46 +597,87 @@ int launch_chunk(Device &dev, DeviceChunk &dc, const ChunkPlan &c, cudaStream_t 
     }
 
     if (!opt.force_fp64) {
-        // The largest bucket runs on the chunk's own stream; the others fork onto side streams so that their
-        // (short, under-filled) grids overlap its tail instead of serialising in front of it.
-        int n_active = 0, main_bucket = -1;
-        uint32_t main_n = 0;
-        for (int k = 0; k < N_FP32_BUCKETS; ++k) {
-            const uint32_t n = c.bucket_begin[k + 1] - c.bucket_begin[k];
-            if (n) ++n_active;
-            if (n > main_n) { main_n = n; main_bucket = k; }
-        }
-        if (n_active > 1) {
-            if (!dc.ev_fork) CK(cudaEventCreateWithFlags(&dc.ev_fork, cudaEventDisableTiming));
-            CK(cudaEventRecord(dc.ev_fork, st));
-        }
-        for (int pass = 0; pass < 2; ++pass)
-            for (int k = 0; k < N_FP32_BUCKETS; ++k) {
-                const uint32_t n = c.bucket_begin[k + 1] - c.bucket_begin[k];
-                if (!n || (pass == 0) != (k == main_bucket)) continue;
-                const KernelInfo &ki = dev.info(k, c.n_codes);
-                const uint32_t grid = std::min<uint32_t>(n, (uint32_t)(dev.n_sms * ki.ctas_per_sm));
-                ka.tasks = (const Task *)(meta + dc.off_tasks) + c.bucket_begin[k];
-                ka.n_tasks = n;
-                ka.n_tasks_ptr = nullptr;
-                ka.counter = counters + k;
-                ka.sums = work + dc.off_sums;
-                ka.bnd = k == 8 ? dc.bnd.p : nullptr;
-                ka.bnd_stride = k == 8 ? c.max_stream_len : 0;
-                void *args[] = {&ka};
-                cudaStream_t ks = st;
-                if (k != main_bucket) {
-                    ks = aux[k];
-                    CK(cudaStreamWaitEvent(ks, dc.ev_fork, 0));
-                }
-                CK(cudaLaunchKernel(ki.fn, dim3(grid), dim3(32), args, ki.smem, ks));
+        // 1. per-read flat-quality classification (device side; the host only sampled candidate classes)
+        const uint32_t n_span_reads = (uint32_t)c.read_off.size() - 1;
+        {
+            ClassifyArgs ca;
+            memset(&ca, 0, sizeof ca);
+            ca.rd_i = ka.rd_i; ca.rd_d = ka.rd_d; ca.rd_c = ka.rd_c;
+            ca.read_off = ka.read_off;
+            ca.n_reads = n_span_reads;
+            ca.read_class = (uint8_t *)(work + dc.off_class);
+            ca.n_classes = (uint32_t)c.n_classes;
+            for (int k = 0; k < c.n_classes; ++k) { ca.qi[k] = c.class_qi[k]; ca.qd[k] = c.class_qd[k]; ca.qc[k] = c.class_qc[k]; }
+            if (n_span_reads) {
+                phmm_classify_kernel<<<std::min<uint32_t>((n_span_reads + 3) / 4, 148 * 16), 128, 0, st>>>(ca);
+                CK(cudaGetLastError());
                 ++launches;
-                if (k != main_bucket) {
-                    if (!dc.ev_join[k]) CK(cudaEventCreateWithFlags(&dc.ev_join[k], cudaEventDisableTiming));
-                    CK(cudaEventRecord(dc.ev_join[k], ks));
-                    CK(cudaStreamWaitEvent(st, dc.ev_join[k], 0));
+            }
+        }
+        ka.read_class = (const uint8_t *)(work + dc.off_class);
+
+        // 2. forward kernels.  Every (bucket) task list is visited by the flat kernel of each class and by the general
+        // kernel; each kernel only runs the tasks whose read it owns.  The first launch stays on the chunk's stream,
+        // the others fork onto side streams so that short grids overlap the tail of the big one.
+        if (!dc.ev_fork) CK(cudaEventCreateWithFlags(&dc.ev_fork, cudaEventDisableTiming));
+        CK(cudaEventRecord(dc.ev_fork, st));
+        const Tables &tb = tables();
+        int order[N_FP32_BUCKETS];
+        for (int k = 0; k < N_FP32_BUCKETS; ++k) order[k] = k;
+        std::sort(order, order + N_FP32_BUCKETS, [&](int x, int y) {
+            return c.bucket_begin[x + 1] - c.bucket_begin[x] > c.bucket_begin[y + 1] - c.bucket_begin[y];
+        });
+        bool first_launch = true;
+        auto launch_on = [&](const KernelInfo &ki, uint32_t n, int aux_idx, void **args) {
+            const uint32_t grid = std::min<uint32_t>(n, (uint32_t)(dev.n_sms * ki.ctas_per_sm));
+            cudaStream_t ks = st;
+            if (!first_launch) {
+                ks = aux[aux_idx];
+                CK(cudaStreamWaitEvent(ks, dc.ev_fork, 0));
+            }
+            CK(cudaLaunchKernel(ki.fn, dim3(grid), dim3(32), args, ki.smem, ks));
+            ++launches;
+            if (!first_launch) {
+                if (!dc.ev_join[aux_idx]) CK(cudaEventCreateWithFlags(&dc.ev_join[aux_idx], cudaEventDisableTiming));
+                CK(cudaEventRecord(dc.ev_join[aux_idx], ks));
+                CK(cudaStreamWaitEvent(st, dc.ev_join[aux_idx], 0));
+            }
+            first_launch = false;
+        };
+        for (int oi = 0; oi < N_FP32_BUCKETS; ++oi) {
+            const int k = order[oi];
+            const uint32_t n = c.bucket_begin[k + 1] - c.bucket_begin[k];
+            if (!n) continue;
+            ka.tasks = (const Task *)(meta + dc.off_tasks) + c.bucket_begin[k];
+            ka.n_tasks = n;
+            ka.n_tasks_ptr = nullptr;
+            ka.sums = work + dc.off_sums;
+            ka.bnd = k == 8 ? dc.bnd.p : nullptr;
+            ka.bnd_stride = k == 8 ? c.max_stream_len : 0;
+            if (k < 8) {
+                for (int cl = 0; cl < c.n_classes; ++cl) {
+                    FlatCoef fc;
+                    const int qi = c.class_qi[cl], qd = c.class_qd[cl], qc = c.class_qc[cl];
+                    const double ei = tb.eps[qi], ed = tb.eps[qd], ec = tb.eps[qc], tIM = 1.0 - ec;
+                    const int mn = std::min(qi, qd), mx = std::max(qi, qd);
+                    fc.a = (float)tb.m2m[((mx * (mx + 1)) >> 1) + mn];
+                    fc.b = (float)(tIM * ei);
+                    fc.c = (float)(tIM * ed);
+                    fc.g = (float)ec;
+                    fc.d = (float)ec;
+                    fc.tmi = (float)ei;
+                    fc.tim = (float)tIM;
+                    fc.class_id = (uint32_t)cl;
+                    fc.qi = qi; fc.qd = qd; fc.qc = qc;
+                    ka.counter = counters + 16 + 8 * cl + k;
+                    void *args[] = {&ka, &fc};
+                    launch_on(dev.info(FLAT_KEY + k, c.n_codes), n, N_FP32_BUCKETS + 8 * cl + k, args);
                 }
             }
+            ka.counter = counters + k;
+            void *args[] = {&ka};
+            launch_on(dev.info(k, c.n_codes), n, k, args);
+        }
         CK(cudaEventRecord(dc.ev_f32, st));
         if (ea.n_units) {
             phmm_epilogue_f32<<<std::min<uint32_t>(ea.n_units, 4096), 128, 0, st>>>(ea);

@@ -67,6 +67,7 @@ struct KernelArgs {
     uint32_t bnd_stride;
     const double *m2m;            // triangular matchToMatch table (PairHMMModel.java:71,86-94)
     int *err;                     // device error flag (GPHMM_ERR_BAD_QUAL)
+    const uint8_t *read_class;    // per read: flat-quality class id (phmm_classify_kernel) or CLASS_GENERAL
     int32_t n_codes;
     int32_t tristate_off;
     uint8_t code_byte[MAX_CODES];  // code -> haplotype byte value
@@ -272,6 +273,8 @@ __global__ void __launch_bounds__(32) phmm_forward_kernel(const KernelArgs g)
 //  * the prior table is addressed with one IMAD from a precomputed 32-bit shared address.
 // ---------------------------------------------------------------------------------------------
 constexpr int STREAM_PAD = 32;
+constexpr uint8_t CLASS_GENERAL = 0xff;
+constexpr int MAX_FLAT_CLASSES = 4;
 
 __device__ __forceinline__ float4 lds128(uint32_t addr) {
     float4 v;
@@ -382,6 +385,7 @@ __global__ void __launch_bounds__(32) phmm_fast_f32_kernel(const KernelArgs g)
         ti = __shfl_sync(FULL, ti, 0);
         if (ti >= n_tasks) break;
         const Task t = g.tasks[ti];
+        if (g.read_class[t.read] != CLASS_GENERAL) continue;  // a flat-quality kernel owns this read
         const uint32_t ro = g.read_off[t.read];
         const int R = (int)(g.read_off[t.read + 1] - ro);  // host guarantees R + 2 <= 32 * K
         const float c0 = (float)scalbn(1.0, t.c0_exp);
@@ -469,6 +473,221 @@ __global__ void __launch_bounds__(32) phmm_fast_f32_kernel(const KernelArgs g)
                 fast_step<K, true>(st, ca, cb, cc, cg, cd, tab_lane, src_lane, lane, acc_lane, acc_slot, c0, sums_task);
             step = e + 32;
         }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Flat-quality fp32 kernel.  When a read has the same insertion, deletion and gap-continuation quality on
+// every base (HaplotypeCaller's default: flat Q45/Q45 unless BI/BD tags exist, flat GCP 10 --
+// StandardPairHMMInputScoreImputator.java:27-47) the transition coefficients a,b,c,g,d are the same for every
+// row, so they are passed as KERNEL PARAMETERS and reach the FMA pipe as constant-bank operands.  That cuts the
+// register-file reads per cell from 16 to 11, which is what limits the general kernel (ncu: dispatch_stall;
+// profiles/r01_microbench_issue_rates.txt: the same instruction mix issues at 3.8/clk/SM with constant
+// coefficients against 2.7 with register coefficients).
+//  * row 1 is slot 0 of lane 0: slot 0 keeps per-lane registers B0, G0 (0 on lane 0: I~ of row 0 is 0) and an
+//    addend E0 = tIM*c0 on lane 0 (the c*D~[0] term), so the rotated-in garbage of lane 31 is ignored for free;
+//  * rows below the read are plain pads (prior 0);  lane 31's last row is always a pad, so the rotation feeds
+//    lane 0 with M = 0;
+//  * the likelihood sum is taken from row R directly: acc += M[slot] + tMI*I~[slot] with the slot a template
+//    parameter (the task's R picks the loop instance; warp-uniform switch outside the loops).
+// ---------------------------------------------------------------------------------------------
+struct FlatCoef {
+    float a, b, c, g, d;  // tMM, tIM*tMI, tIM*tMD, tII (= tII*tMI/tMI), tDD
+    float tmi;            // tMI: I = tMI * I~
+    float tim;            // tIM: row 1 sees c = tIM (tMD_0 = 1)
+    uint32_t class_id;    // reads whose read_class equals this are ours
+    uint32_t qi, qd, qc;
+};
+
+struct ClassifyArgs {
+    const uint8_t *rd_i, *rd_d, *rd_c;
+    const uint32_t *read_off;
+    uint32_t n_reads;
+    uint8_t *read_class;
+    uint32_t n_classes;
+    uint8_t qi[MAX_FLAT_CLASSES], qd[MAX_FLAT_CLASSES], qc[MAX_FLAT_CLASSES];
+};
+
+// one warp per read: flat iff every base carries the class's (ins, del, gcp) triple
+__global__ void __launch_bounds__(128) phmm_classify_kernel(const ClassifyArgs a)
+{
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t r = warp; r < a.n_reads; r += n_warps) {
+        const uint32_t ro = a.read_off[r], R = a.read_off[r + 1] - ro;
+        uint8_t cls = CLASS_GENERAL;
+        if (R > 0) {
+            const uint32_t qi0 = a.rd_i[ro], qd0 = a.rd_d[ro], qc0 = a.rd_c[ro];
+            bool same = true;
+            for (uint32_t i = lane; i < R; i += 32) same = same && a.rd_i[ro + i] == qi0 && a.rd_d[ro + i] == qd0 && a.rd_c[ro + i] == qc0;
+            if (__all_sync(0xffffffffu, same))
+                for (uint32_t k = 0; k < a.n_classes; ++k)
+                    if (a.qi[k] == qi0 && a.qd[k] == qd0 && a.qc[k] == qc0) cls = (uint8_t)k;
+        }
+        if (lane == 0) a.read_class[r] = cls;
+    }
+}
+
+template <int K> struct FlatState {
+    float M[K], I[K], D[K];
+    float dgm, dgi, dgd;
+    float acc;
+    uint32_t y;
+    const uint8_t *sp;
+    uint32_t hap_idx;
+};
+
+template <int K, int SLOT, bool CHECKED>
+__device__ __forceinline__ void flat_step(FlatState<K> &st, const FlatCoef &f, float B0, float G0, float E0, uint32_t tab_lane,
+                                          int src_lane, int lane, int acc_lane, float *sums_task)
+{
+    constexpr int NV = (K + 3) / 4;
+    constexpr unsigned FULL = 0xffffffffu;
+    constexpr uint32_t CODE_STRIDE = NV * 32 * 16;
+    ++st.sp;
+    const uint32_t y_next = ldg_u8(st.sp);
+    const float mu = __shfl_sync(FULL, st.M[K - 1], src_lane);
+    const float iu = __shfl_sync(FULL, st.I[K - 1], src_lane);
+    const float du = __shfl_sync(FULL, st.D[K - 1], src_lane);
+    float pr[NV * 4];
+    {
+        const uint32_t addr = st.y * CODE_STRIDE + tab_lane;
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+            const float4 q = lds128(addr + v * 512);
+            pr[v * 4 + 0] = q.x; pr[v * 4 + 1] = q.y; pr[v * 4 + 2] = q.z; pr[v * 4 + 3] = q.w;
+        }
+    }
+    float Mn[K];
+    {
+        float u = __fmaf_rn(f.c, st.dgd, E0);
+        u = __fmaf_rn(B0, st.dgi, u);
+        u = __fmaf_rn(f.a, st.dgm, u);
+        Mn[0] = pr[0] * u;
+    }
+#pragma unroll
+    for (int k = 1; k < K; ++k) {
+        float u = f.c * st.D[k - 1];
+        u = __fmaf_rn(f.b, st.I[k - 1], u);
+        u = __fmaf_rn(f.a, st.M[k - 1], u);
+        Mn[k] = pr[k] * u;
+    }
+#pragma unroll
+    for (int k = 0; k < K; ++k) st.D[k] = __fmaf_rn(f.d, st.D[k], st.M[k]);
+    st.I[0] = __fmaf_rn(G0, iu, mu);
+#pragma unroll
+    for (int k = 1; k < K; ++k) st.I[k] = __fmaf_rn(f.g, st.I[k - 1], Mn[k - 1]);
+#pragma unroll
+    for (int k = 0; k < K; ++k) st.M[k] = Mn[k];
+    st.dgm = mu; st.dgi = iu; st.dgd = du;
+    st.acc += st.M[SLOT];
+    st.acc = __fmaf_rn(f.tmi, st.I[SLOT], st.acc);
+    if (CHECKED) {
+        if (st.y == CODE_END) {
+            if (lane == acc_lane) sums_task[st.hap_idx] = st.acc;
+            ++st.hap_idx;
+            st.acc = 0.f;
+#pragma unroll
+            for (int k = 0; k < K; ++k) st.D[k] = 0.f;
+        }
+    }
+    st.y = y_next;
+}
+
+template <int K, int SLOT>
+__device__ __forceinline__ void flat_sweep(FlatState<K> &st, const FlatCoef &f, float B0, float G0, float E0, uint32_t tab_lane,
+                                        int src_lane, int lane, int acc_lane, float *sums_task, const uint32_t *hap_len, uint32_t n_haps)
+{
+    int step = 1, e = 0;
+    for (uint32_t h = 0; h < n_haps; ++h) {
+        e += (int)hap_len[h] + 1;
+        const int n_free = e - step;
+#pragma unroll 2
+        for (int s = 0; s < n_free; ++s) flat_step<K, SLOT, false>(st, f, B0, G0, E0, tab_lane, src_lane, lane, acc_lane, sums_task);
+        if (n_free > 0) step = e;
+        const int n_chk = e + 32 - step;
+#pragma unroll 1
+        for (int s = 0; s < n_chk; ++s) flat_step<K, SLOT, true>(st, f, B0, G0, E0, tab_lane, src_lane, lane, acc_lane, sums_task);
+        step = e + 32;
+    }
+}
+
+template <int K, int SLOT>
+__device__ __forceinline__ void flat_dispatch(int slot, FlatState<K> &st, const FlatCoef &f, float B0, float G0, float E0, uint32_t tab_lane,
+                                              int src_lane, int lane, int acc_lane, float *sums_task, const uint32_t *hap_len, uint32_t n_haps)
+{
+    if (slot == SLOT) flat_sweep<K, SLOT>(st, f, B0, G0, E0, tab_lane, src_lane, lane, acc_lane, sums_task, hap_len, n_haps);
+    else if constexpr (SLOT + 1 < K) flat_dispatch<K, SLOT + 1>(slot, st, f, B0, G0, E0, tab_lane, src_lane, lane, acc_lane, sums_task, hap_len, n_haps);
+}
+
+template <int K>
+__global__ void __launch_bounds__(32) phmm_flat_f32_kernel(const KernelArgs g, const FlatCoef f)
+{
+    constexpr int NV = (K + 3) / 4;
+    constexpr unsigned FULL = 0xffffffffu;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float *tab_s = reinterpret_cast<float *>(smem_raw);
+    int lane, src_lane;
+    asm volatile("mov.u32 %0, %%laneid;" : "=r"(lane));
+    asm volatile("{ .reg .u32 t; add.u32 t, %1, 31; and.b32 %0, t, 31; }" : "=r"(src_lane) : "r"(lane));
+    const uint32_t tab_lane = (uint32_t)__cvta_generic_to_shared(smem_raw) + lane * 16;
+    float *const sums = reinterpret_cast<float *>(g.sums);
+    const uint32_t n_tasks = g.n_tasks;
+    const int n_codes = g.n_codes;
+
+    for (;;) {
+        uint32_t ti = 0;
+        if (lane == 0) ti = atomicAdd(g.counter, 1u);
+        ti = __shfl_sync(FULL, ti, 0);
+        if (ti >= n_tasks) break;
+        const Task t = g.tasks[ti];
+        if (g.read_class[t.read] != (uint8_t)f.class_id) continue;
+        const uint32_t ro = g.read_off[t.read];
+        const int R = (int)(g.read_off[t.read + 1] - ro);  // 1 <= R <= 32 * K - 1 (flat reads are never empty)
+        const float c0 = (float)scalbn(1.0, t.c0_exp);
+
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const int i = lane * K + k + 1;
+            const bool real = i <= R;
+            float pmf = 0.f, pxf = 0.f;
+            uint32_t x = 0;
+            if (real) {
+                uint32_t q = g.rd_q[ro + i - 1];
+                x = g.rd_bases[ro + i - 1];
+                if (q > (uint32_t)MAX_QUAL) { atomicExch(g.err, 1); q = MAX_QUAL; }
+                const double e = c_eps[q];
+                pmf = (float)(1.0 - e);
+                pxf = (float)(g.tristate_off ? e : e / 3.0);
+            }
+            for (int y = 0; y < n_codes; ++y) {
+                float v = 0.f;
+                if (real && y >= (int)CODE_FIRST_BASE) {
+                    const uint32_t hb = g.code_byte[y];
+                    v = (x == hb || x == (uint32_t)'N' || hb == (uint32_t)'N') ? pmf : pxf;  // LoglessPairHMM.java:89
+                }
+                tab_s[((y * NV + k / 4) * 32 + lane) * 4 + (k % 4)] = v;
+            }
+        }
+        if (f.qi > 127u || f.qd > 127u || f.qc > 127u) atomicExch(g.err, 1);
+        __syncwarp();
+
+        FlatState<K> st;
+#pragma unroll
+        for (int k = 0; k < K; ++k) { st.M[k] = 0.f; st.I[k] = 0.f; st.D[k] = 0.f; }
+        st.dgm = 0.f; st.dgi = 0.f; st.dgd = 0.f;
+        st.acc = 0.f;
+        st.hap_idx = 0;
+        st.sp = g.streams + t.stream_off - lane;
+        st.y = ldg_u8(st.sp);
+        // slot 0: lane 0 holds row 1 (virtual row 0 above it: M = I~ = 0, c*D~ = tIM*c0)
+        const float B0 = lane == 0 ? 0.f : f.b;
+        const float G0 = lane == 0 ? 0.f : f.g;
+        const float E0 = lane == 0 ? f.tim * c0 : 0.f;
+        const int acc_lane = (R - 1) / K, acc_slot = (R - 1) % K;
+        flat_dispatch<K, 0>(acc_slot, st, f, B0, G0, E0, tab_lane, src_lane, lane, acc_lane, sums + t.out_base,
+                            g.hap_len + t.hap_first, t.n_haps);
     }
 }
 

@@ -3,7 +3,7 @@
 // Each kernel runs ITER iterations of an unrolled body of independent chains; reports warp-instr/clk/SM.
 #include <cstdio>
 #include <cuda_runtime.h>
-#define ITER 4096
+#define ITER 16384
 #define CHK(x) do{cudaError_t e=(x); if(e!=cudaSuccess){printf("%s: %s\n",#x,cudaGetErrorString(e));return 1;}}while(0)
 
 template <int ILP> __global__ void k_ffma(float *out, float a, float b) {
@@ -31,6 +31,68 @@ template <int ILP> __global__ void k_ffma3(float *out, const float *in) {
     float s = 0;
 #pragma unroll
     for (int i = 0; i < ILP; ++i) s += x[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+// 2 register sources + 1 constant-bank operand (kernel parameter): x = x*c + z
+template <int ILP> __global__ void k_ffma2r1c(float *out, const float *in, float c0, float c1, float c2, float c3) {
+    float x[ILP], z[ILP];
+    const float cs[4] = {c0, c1, c2, c3};
+#pragma unroll
+    for (int i = 0; i < ILP; ++i) { x[i] = in[i] + threadIdx.x; z[i] = in[i + 64] + threadIdx.x * 1e-9f; }
+    for (int it = 0; it < ITER; ++it) {
+#pragma unroll
+        for (int i = 0; i < ILP; ++i) x[i] = fmaf(x[i], cs[i & 3], z[(i + 1) % ILP]);
+    }
+    float s = 0;
+#pragma unroll
+    for (int i = 0; i < ILP; ++i) s += x[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+// the PairHMM cell mix with constant-bank coefficients: per "cell" FMUL(c,r) FFMA(c,r,r) FFMA(c,r,r) FMUL(r,r) FFMA(c,r,r) FFMA(c,r,r)
+template <int ILP> __global__ void k_cellmix_const(float *out, const float *in, float ca, float cb, float cc, float cd, float cg) {
+    float M[ILP], I[ILP], D[ILP], pr[ILP];
+#pragma unroll
+    for (int i = 0; i < ILP; ++i) { M[i] = in[i] + threadIdx.x; I[i] = in[i + 8]; D[i] = in[i + 16] + threadIdx.x * 1e-9f; pr[i] = in[i + 32] + threadIdx.x * 1e-9f; }
+    for (int it = 0; it < ITER; ++it) {
+        float Mn[ILP];
+#pragma unroll
+        for (int i = 1; i < ILP; ++i) { float u = cc * D[i - 1]; u = fmaf(cb, I[i - 1], u); u = fmaf(ca, M[i - 1], u); Mn[i] = pr[i] * u; }
+        { float u = cc * D[ILP - 1]; u = fmaf(cb, I[ILP - 1], u); u = fmaf(ca, M[ILP - 1], u); Mn[0] = pr[0] * u; }
+#pragma unroll
+        for (int i = 0; i < ILP; ++i) D[i] = fmaf(cd, D[i], M[i]);
+#pragma unroll
+        for (int i = 1; i < ILP; ++i) I[i] = fmaf(cg, I[i - 1], Mn[i - 1]);
+        I[0] = fmaf(cg, I[ILP - 1], Mn[ILP - 1]);
+#pragma unroll
+        for (int i = 0; i < ILP; ++i) M[i] = Mn[i];
+    }
+    float s = 0;
+#pragma unroll
+    for (int i = 0; i < ILP; ++i) s += M[i] + I[i] + D[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+// same mix with per-thread register coefficients (what the current kernel does)
+template <int ILP> __global__ void k_cellmix_reg(float *out, const float *in) {
+    float M[ILP], I[ILP], D[ILP], pr[ILP], ca[ILP], cb[ILP], cc[ILP], cd[ILP], cg[ILP];
+#pragma unroll
+    for (int i = 0; i < ILP; ++i) { M[i] = in[i] + threadIdx.x; I[i] = in[i + 8]; D[i] = in[i + 16] + threadIdx.x * 1e-9f; pr[i] = in[i + 32] + threadIdx.x * 1e-9f;
+        ca[i] = in[i + 40] + threadIdx.x * 1e-9f; cb[i] = in[i + 48] + threadIdx.x * 1e-9f; cc[i] = in[i + 56] + threadIdx.x * 1e-9f; cd[i] = in[i + 64] + threadIdx.x * 1e-9f; cg[i] = in[i + 72] + threadIdx.x * 1e-9f; }
+    for (int it = 0; it < ITER; ++it) {
+        float Mn[ILP];
+#pragma unroll
+        for (int i = 1; i < ILP; ++i) { float u = cc[i] * D[i - 1]; u = fmaf(cb[i], I[i - 1], u); u = fmaf(ca[i], M[i - 1], u); Mn[i] = pr[i] * u; }
+        { float u = cc[0] * D[ILP - 1]; u = fmaf(cb[0], I[ILP - 1], u); u = fmaf(ca[0], M[ILP - 1], u); Mn[0] = pr[0] * u; }
+#pragma unroll
+        for (int i = 0; i < ILP; ++i) D[i] = fmaf(cd[i], D[i], M[i]);
+#pragma unroll
+        for (int i = 1; i < ILP; ++i) I[i] = fmaf(cg[i], I[i - 1], Mn[i - 1]);
+        I[0] = fmaf(cg[0], I[ILP - 1], Mn[ILP - 1]);
+#pragma unroll
+        for (int i = 0; i < ILP; ++i) M[i] = Mn[i];
+    }
+    float s = 0;
+#pragma unroll
+    for (int i = 0; i < ILP; ++i) s += M[i] + I[i] + D[i];
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 template <int ILP> __global__ void k_ffma2(float *out, const float *in) {
@@ -146,6 +208,9 @@ int main() {
         };
         rep("FFMA imm/const operands", time_kernel([&] { k_ffma<ILP><<<blocks, threads>>>(out, 1.0001f, 0.5f); }), 1);
         rep("FFMA 3 distinct regs", time_kernel([&] { k_ffma3<ILP><<<blocks, threads>>>(out, in); }), 1);
+        rep("FFMA 2 regs + 1 const", time_kernel([&] { k_ffma2r1c<ILP><<<blocks, threads>>>(out, in, 0.999f, 0.998f, 0.997f, 0.996f); }), 1);
+        rep("cell mix, const coeffs (x6)", time_kernel([&] { k_cellmix_const<ILP><<<blocks, threads>>>(out, in, 0.9f, 1e-5f, 1e-5f, 0.1f, 0.1f); }), 6);
+        rep("cell mix, reg coeffs (x6)", time_kernel([&] { k_cellmix_reg<ILP><<<blocks, threads>>>(out, in); }), 6);
         rep("FFMA2 (fma.rn.f32x2)", time_kernel([&] { k_ffma2<ILP><<<blocks, threads>>>(out, in); }), 1);
         rep("FFMA + LOP3 interleaved", time_kernel([&] { k_ffma_alu<ILP><<<blocks, threads>>>(out, in); }), 2);
         rep("FFMA2 + LOP3 interleaved", time_kernel([&] { k_ffma2_alu<ILP><<<blocks, threads>>>(out, in); }), 2);
