@@ -112,6 +112,7 @@ struct PinBuf {
     void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
 };
 
+constexpr int N_SLOTS = 3;         // chunks in flight per device: one computing, one finishing (epilogue/D2H), one being staged
 constexpr int N_FP32_BUCKETS = 9;  // K = 1..8 plain, bucket 8 = striped K=8 (reads of 256+ bases)
 constexpr int N_AUX = N_FP32_BUCKETS + 8 * MAX_FLAT_CLASSES;  // side streams: general buckets + flat (class, bucket)
 constexpr int N_COUNTERS = 64;     // [0..8] general fp32 buckets, [9] fp64 queue, [10] n_rescue, [11] forced fp64 queue,
@@ -169,7 +170,11 @@ void validate_batch(const gphmm_batch *b) {
 std::vector<std::pair<int64_t, int64_t>> split_units(const gphmm_batch *b, int64_t chunk_cells, int64_t chunk_bytes) {
     std::vector<std::pair<int64_t, int64_t>> out;
     int64_t u = 0;
+    const int64_t full_cells = chunk_cells;
     while (u < b->n_units) {
+        // ramp up: the first chunks are small so that the GPU starts early while the host is still staging
+        const size_t ci = out.size();
+        chunk_cells = ci >= 3 ? full_cells : std::max<int64_t>(full_cells >> (3 - ci), 1);
         int64_t cells = 0, bytes = 0, pairs = 0, u_end = u;
         int64_t r_lo = INT64_MAX, r_hi = 0;
         while (u_end < b->n_units) {
@@ -237,6 +242,9 @@ void plan_chunk(const gphmm_batch *b, int64_t u0, int64_t u1, bool force_fp64, C
     c.n_pairs = 0; c.cells = 0; c.max_stream_len = 0; c.max_hap_len = 0;
     std::vector<Task> raw;
     std::vector<uint8_t> bucket_of;
+    raw.reserve((size_t)(c.r_hi - c.r_lo));
+    bucket_of.reserve((size_t)(c.r_hi - c.r_lo));
+    c.streams.reserve((size_t)(u1 - u0) * 64);
     uint32_t bucket_count[N_FP32_BUCKETS] = {0};
     for (int64_t u = u0; u < u1; ++u) {
         const gphmm_unit &un = b->units[u];
@@ -252,23 +260,31 @@ void plan_chunk(const gphmm_batch *b, int64_t u0, int64_t u1, bool force_fp64, C
         const uint32_t stream_off = (uint32_t)c.streams.size();
         uint32_t max_h = 1;
         int64_t sum_h = 0;
-        for (int64_t h = un.hap_begin; h < un.hap_end; ++h) {
-            const int64_t ho = b->hap_off[h];
-            const uint32_t H = (uint32_t)(b->hap_off[h + 1] - ho);
-            c.hap_len.push_back(H);
-            c.hap_stream_off.push_back((uint32_t)c.streams.size());
-            for (uint32_t j = 0; j < H; ++j) {
-                const uint8_t y = b->hap_bases[ho + j];
-                if (lut[y] < 0) {
-                    if (c.n_codes >= MAX_CODES) throw Error(GPHMM_ERR_ALPHABET, "too many distinct haplotype byte values");
-                    lut[y] = (int16_t)c.n_codes;
-                    c.code_byte[c.n_codes++] = y;
+        {
+            const int64_t hap_bytes = nh ? b->hap_off[un.hap_end] - b->hap_off[un.hap_begin] : 0;
+            size_t w = c.streams.size();
+            c.streams.resize(w + (size_t)hap_bytes + nh);
+            uint8_t *dst = c.streams.data();
+            for (int64_t h = un.hap_begin; h < un.hap_end; ++h) {
+                const int64_t ho = b->hap_off[h];
+                const uint32_t H = (uint32_t)(b->hap_off[h + 1] - ho);
+                c.hap_len.push_back(H);
+                c.hap_stream_off.push_back((uint32_t)w);
+                const uint8_t *src = b->hap_bases + ho;
+                for (uint32_t j = 0; j < H; ++j) {
+                    int16_t code = lut[src[j]];
+                    if (code < 0) {
+                        if (c.n_codes >= MAX_CODES) throw Error(GPHMM_ERR_ALPHABET, "too many distinct haplotype byte values");
+                        code = lut[src[j]] = (int16_t)c.n_codes;
+                        c.code_byte[c.n_codes++] = src[j];
+                    }
+                    dst[w + j] = (uint8_t)code;
                 }
-                c.streams.push_back((uint8_t)lut[y]);
+                w += H;
+                dst[w++] = (uint8_t)CODE_END;
+                max_h = std::max(max_h, H);
+                sum_h += H;
             }
-            c.streams.push_back((uint8_t)CODE_END);
-            max_h = std::max(max_h, H);
-            sum_h += H;
         }
         const uint32_t stream_len = (uint32_t)c.streams.size() - stream_off;
         c.max_stream_len = std::max(c.max_stream_len, stream_len);
@@ -416,9 +432,9 @@ struct Device {
                                     : bucket == N_FP32_BUCKETS ? fp64_kernel(n_codes) : flat_kernel(bucket - FLAT_KEY, n_codes)).first;
         return it->second;
     }
-    cudaStream_t streams[2] = {nullptr, nullptr};
-    cudaStream_t aux[2][N_AUX] = {{nullptr}};  // side streams: the kernels of a chunk overlap their tails
-    DeviceChunk slots[2];
+    cudaStream_t streams[N_SLOTS] = {nullptr};
+    cudaStream_t aux[N_SLOTS][N_AUX] = {{nullptr}};  // side streams: the kernels of a chunk overlap their tails
+    DeviceChunk slots[N_SLOTS];
     DevBuf m2m;
     cudaEvent_t ev_step0 = nullptr, ev_step1 = nullptr;  // bracket a whole run_prepared step on streams[0]
     void init(int ord) {
@@ -434,7 +450,7 @@ struct Device {
         CK(cudaMemcpy(m2m.p, t.m2m.data(), t.m2m.size() * sizeof(double), cudaMemcpyHostToDevice));
         CK(cudaEventCreate(&ev_step0));
         CK(cudaEventCreate(&ev_step1));
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < N_SLOTS; ++i) {
             CK(cudaStreamCreateWithFlags(&streams[i], cudaStreamNonBlocking));
             for (int k = 0; k < N_AUX; ++k) CK(cudaStreamCreateWithFlags(&aux[i][k], cudaStreamNonBlocking));
             CK(cudaEventCreate(&slots[i].ev_start));
@@ -445,7 +461,7 @@ struct Device {
     }
     void release() {
         cudaSetDevice(ordinal);
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < N_SLOTS; ++i) {
             slots[i].release();
             if (streams[i]) cudaStreamDestroy(streams[i]);
             streams[i] = nullptr;
@@ -823,8 +839,8 @@ void device_loop(gphmm *h, Device &dev, const gphmm_batch *b, const std::vector<
         RunOptions opt;
         opt.force_fp64 = h->cfg.force_fp64 != 0;
         opt.tristate_off = h->cfg.tristate_off != 0;
-        ChunkPlan plans[2];
-        bool inflight[2] = {false, false};
+        std::vector<ChunkPlan> plans(N_SLOTS);
+        bool inflight[N_SLOTS] = {false};
         int slot = 0;
         int launches = 0;
         for (;;) {
@@ -834,18 +850,23 @@ void device_loop(gphmm *h, Device &dev, const gphmm_batch *b, const std::vector<
                 finish_chunk(dev.slots[slot], b, plans[slot], out, h->stats, true);
                 inflight[slot] = false;
             }
-            plan_chunk(b, chunks[ci].first, chunks[ci].second, opt.force_fp64, plans[slot]);
+            {
+                const double tp = now_ms();
+                plan_chunk(b, chunks[ci].first, chunks[ci].second, opt.force_fp64, plans[slot]);
+                std::lock_guard<std::mutex> lk(h->stats.mu);
+                h->stats.s.host_stage_ms += now_ms() - tp;
+            }
             upload_chunk(dev, dev.slots[slot], b, plans[slot], dev.streams[slot], opt.force_fp64, h->stats);
             launches += launch_chunk(dev, dev.slots[slot], plans[slot], dev.streams[slot], dev.aux[slot], opt, true);
             inflight[slot] = true;
-            slot ^= 1;
+            slot = (slot + 1) % N_SLOTS;
         }
-        for (int s = 0; s < 2; ++s) {
+        for (int s = 0; s < N_SLOTS; ++s) {
             if (inflight[slot]) {
                 finish_chunk(dev.slots[slot], b, plans[slot], out, h->stats, true);
                 inflight[slot] = false;
             }
-            slot ^= 1;
+            slot = (slot + 1) % N_SLOTS;
         }
         std::lock_guard<std::mutex> lk(h->stats.mu);
         h->stats.s.kernel_launches += launches;
