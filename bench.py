@@ -112,6 +112,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-prefix-sharing", action="store_true", help="A/B switch: recompute every haplotype from column 1")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -163,7 +164,7 @@ def main():
     t_gen = time.time() - t_gen
     cells, pairs = batch.cells(), batch.pairs()
     out = np.full(batch.n_out, np.nan, dtype=np.float64)
-    hmm = GpuPhmm(devices=[local_rank])
+    hmm = GpuPhmm(devices=[local_rank], no_prefix_sharing=args.no_prefix_sharing)
     prepared = hmm.prepare(batch)
     props = torch.cuda.get_device_properties(local_rank)
 
@@ -182,7 +183,7 @@ def main():
     st = hmm.stats()
     clocks = sampler.stop()
     dev_s = st["device_ms"] / 1e3
-    f32_s = st["fp32_kernel_ms"] / 1e3
+    f32_s = st["device_ms"] / 1e3  # whole device step (forward kernels are > 99 % of it); per-chunk kernel events overlap across streams
     assert np.all(np.isfinite(out)) and np.all(out <= 1e-9), "kernel output is not a valid log10 probability"
 
     # ---- e2e: host buffers in, host results out, through the public C-ABI call ----

@@ -134,6 +134,11 @@ struct ChunkPlan {
     std::vector<UnitDesc> units;
     std::vector<Task> tasks;               // bucket-sorted
     uint32_t bucket_begin[N_FP32_BUCKETS + 1];
+    std::vector<uint8_t> sstreams;         // prefix-compressed streams of the fast kernels
+    std::vector<PassInfo> pass_info;
+    std::vector<Segment> segments;
+    std::vector<UnitSched> unit_sched;
+    int64_t skipped_cells = 0;
     int n_classes = 0;                     // flat-quality classes sampled from the chunk's reads
     uint8_t class_qi[MAX_FLAT_CLASSES], class_qd[MAX_FLAT_CLASSES], class_qc[MAX_FLAT_CLASSES];
 };
@@ -167,14 +172,14 @@ void validate_batch(const gphmm_batch *b) {
 }
 
 // Greedy split of the unit list into chunks bounded by cells and staged bytes.
-std::vector<std::pair<int64_t, int64_t>> split_units(const gphmm_batch *b, int64_t chunk_cells, int64_t chunk_bytes) {
+std::vector<std::pair<int64_t, int64_t>> split_units(const gphmm_batch *b, int64_t chunk_cells, int64_t chunk_bytes, bool ramp_up) {
     std::vector<std::pair<int64_t, int64_t>> out;
     int64_t u = 0;
     const int64_t full_cells = chunk_cells;
     while (u < b->n_units) {
         // ramp up: the first chunks are small so that the GPU starts early while the host is still staging
         const size_t ci = out.size();
-        chunk_cells = ci >= 3 ? full_cells : std::max<int64_t>(full_cells >> (3 - ci), 1);
+        chunk_cells = (!ramp_up || ci >= 3) ? full_cells : std::max<int64_t>(full_cells >> (3 - ci), 1);
         int64_t cells = 0, bytes = 0, pairs = 0, u_end = u;
         int64_t r_lo = INT64_MAX, r_hi = 0;
         while (u_end < b->n_units) {
@@ -200,7 +205,149 @@ std::vector<std::pair<int64_t, int64_t>> split_units(const gphmm_batch *b, int64
     return out;
 }
 
-void plan_chunk(const gphmm_batch *b, int64_t u0, int64_t u1, bool force_fp64, ChunkPlan &c) {
+// Plans the shared (prefix-compressed) stream of one unit: haplotypes sorted lexicographically, pass i+1 resumes
+// from a snapshot taken at the last column it shares with its predecessors.  Appends to c.sstreams / pass_info /
+// segments and returns the unit's schedule.  With share == false every pass starts from column 1 in input order.
+UnitSched plan_unit_sharing(const gphmm_batch *b, const gphmm_unit &un, const int16_t *lut, bool share, ChunkPlan &c,
+                            int64_t sum_read_len) {
+    constexpr uint32_t MIN_DEPTH = 32, SPACING = 32;
+    UnitSched us;
+    memset(&us, 0, sizeof us);
+    const int n = (int)(un.hap_end - un.hap_begin);
+    us.pass_first = (uint32_t)c.pass_info.size();
+    us.n_passes = (uint32_t)n;
+    us.seg_first = (uint32_t)c.segments.size();
+    c.sstreams.insert(c.sstreams.end(), STREAM_PAD, (uint8_t)CODE_NULL);
+    us.sstream_off = (uint32_t)c.sstreams.size();
+    if (n == 0) return us;
+    auto hap_ptr = [&](int k) { return b->hap_bases + b->hap_off[un.hap_begin + k]; };
+    auto hap_len = [&](int k) { return (uint32_t)(b->hap_off[un.hap_begin + k + 1] - b->hap_off[un.hap_begin + k]); };
+    std::vector<int> order(n);
+    for (int k = 0; k < n; ++k) order[k] = k;
+    if (share)
+        std::sort(order.begin(), order.end(), [&](int x, int y) {
+            const uint32_t lx = hap_len(x), ly = hap_len(y);
+            const int cmp = memcmp(hap_ptr(x), hap_ptr(y), std::min(lx, ly));
+            if (cmp != 0) return cmp < 0;
+            if (lx != ly) return lx < ly;
+            return x < y;
+        });
+    struct Snap { int pass; uint32_t depth, pos; int slot; uint32_t free_after; };
+    std::vector<Snap> snaps;
+    int slot_owner[MAX_SNAP_SLOTS];
+    for (int k = 0; k < MAX_SNAP_SLOTS; ++k) slot_owner[k] = -1;
+    std::vector<uint32_t> r(n, 0), pass_start(n + 1, 1), end_pos(n, 0);
+    std::vector<int> snap_of_pass(n, -1);
+    std::vector<uint32_t> lcp(n, 0), n_pad(n, 0);
+    for (int i = 0; i < n; ++i) {
+        const uint32_t H = hap_len(order[i]);
+        // every pass spans at least 32 stream positions (NULL columns before its END if it is shorter), so that the
+        // 32-step END windows of consecutive passes never overlap
+        n_pad[i] = (H - r[i]) < 32u ? 32u - (H - r[i]) : 0u;
+        end_pos[i] = pass_start[i] + (H - r[i]) + n_pad[i];
+        pass_start[i + 1] = end_pos[i] + 1;
+        if (i + 1 >= n || !share) continue;
+        // longest common prefix with the next haplotype in sorted order
+        const uint8_t *x = hap_ptr(order[i]), *y = hap_ptr(order[i + 1]);
+        const uint32_t m = std::min(H, hap_len(order[i + 1]));
+        uint32_t d = 0;
+        while (d < m && x[d] == y[d]) ++d;
+        lcp[i] = d;
+        if (d < MIN_DEPTH) continue;
+        int k = -1;
+        {
+            // preferred: a snapshot at exactly the shared depth, taken by the latest pass that computed column d
+            int j = i;
+            while (r[j] >= d) --j;  // r[0] = 0 < d
+            const uint32_t pos = pass_start[j] + (d - r[j]) - 1;
+            for (size_t q = 0; q < snaps.size(); ++q)
+                if (snaps[q].pass == j && snaps[q].depth == d && slot_owner[snaps[q].slot] == (int)q) k = (int)q;
+            if (k < 0) {
+                bool ok = true;
+                for (const Snap &sn : snaps) ok = ok && (sn.pos + SPACING <= pos || pos + SPACING <= sn.pos);
+                int slot = -1;
+                for (int q = 0; q < MAX_SNAP_SLOTS && ok && slot < 0; ++q)
+                    if (slot_owner[q] < 0 || snaps[slot_owner[q]].free_after < pos) slot = q;
+                if (ok && slot >= 0) {
+                    snaps.push_back({j, d, pos, slot, 0});
+                    k = (int)snaps.size() - 1;
+                    slot_owner[slot] = k;
+                }
+            }
+        }
+        if (k < 0) {
+            // fallback: the deepest live snapshot whose prefix the next haplotype still shares
+            uint32_t best = 0;
+            for (size_t q = 0; q < snaps.size(); ++q) {
+                if (slot_owner[snaps[q].slot] != (int)q || snaps[q].depth < MIN_DEPTH || snaps[q].depth <= best) continue;
+                uint32_t shared_len = UINT32_MAX;  // LCP(haplotype of snaps[q].pass, haplotype i+1) = min lcp[pass..i]
+                for (int t = snaps[q].pass; t <= i; ++t) shared_len = std::min(shared_len, lcp[t]);
+                if (shared_len >= snaps[q].depth) { best = snaps[q].depth; k = (int)q; }
+            }
+            if (k < 0) continue;
+        }
+        snaps[k].free_after = end_pos[i];  // restored at the END column of pass i
+        r[i + 1] = snaps[k].depth;
+        snap_of_pass[i + 1] = k;
+    }
+    // stream + pass table
+    for (int i = 0; i < n; ++i) {
+        const uint8_t *src = hap_ptr(order[i]);
+        const uint32_t H = hap_len(order[i]);
+        const size_t w = c.sstreams.size();
+        c.sstreams.resize(w + (H - r[i]) + n_pad[i] + 1);
+        uint8_t *dst = c.sstreams.data() + w;
+        for (uint32_t q = r[i]; q < H; ++q) dst[q - r[i]] = (uint8_t)lut[src[q]];
+        for (uint32_t q = 0; q < n_pad[i]; ++q) dst[H - r[i] + q] = (uint8_t)CODE_NULL;  // prior 0: no effect on the sum
+        dst[H - r[i] + n_pad[i]] = (uint8_t)CODE_END;
+        PassInfo pi;
+        pi.out_idx = (uint16_t)order[i];
+        pi.restore_slot = (int16_t)(snap_of_pass[i] >= 0 ? snaps[snap_of_pass[i]].slot : -1);
+        c.pass_info.push_back(pi);
+        c.skipped_cells += (int64_t)r[i] * sum_read_len;
+    }
+    // schedule.  Lane l meets stream position q at step q + l, so an END column at e keeps some lane busy with it
+    // during steps [e, e+32) and a snapshot position s during [s, s+32).  END windows never overlap each other
+    // (passes span >= 32 positions), snapshot windows never overlap each other (SPACING), so at any step at most one
+    // of each is active.  A segment = branch-free steps, then checked steps with one constant (END, snapshot) pair.
+    std::vector<uint32_t> pts;
+    pts.push_back(1);
+    for (int i = 0; i < n; ++i) { pts.push_back(end_pos[i]); pts.push_back(end_pos[i] + 32); }
+    for (const Snap &sn : snaps) { pts.push_back(sn.pos); pts.push_back(sn.pos + 32); }
+    std::sort(pts.begin(), pts.end());
+    pts.erase(std::unique(pts.begin(), pts.end()), pts.end());
+    std::vector<int> snap_by_pos(snaps.size());
+    for (size_t q = 0; q < snaps.size(); ++q) snap_by_pos[q] = (int)q;
+    std::sort(snap_by_pos.begin(), snap_by_pos.end(), [&](int x, int y) { return snaps[x].pos < snaps[y].pos; });
+    Segment seg;
+    auto clear_seg = [&]() { seg.n_free = 0; seg.n_chk = 0; seg.snap_pos = INT32_MIN; seg.snap_slot = 0; seg.end_restore = MAX_SNAP_SLOTS; seg.end_out = 0; };
+    clear_seg();
+    size_t ie = 0, is = 0;  // first END / snapshot whose window has not expired yet
+    for (size_t k = 0; k + 1 < pts.size(); ++k) {
+        const uint32_t x = pts[k], y = pts[k + 1];
+        while (ie < (size_t)n && end_pos[ie] + 32 <= x) ++ie;
+        while (is < snaps.size() && snaps[snap_by_pos[is]].pos + 32 <= x) ++is;
+        const bool end_on = ie < (size_t)n && end_pos[ie] <= x;
+        const bool snap_on = is < snaps.size() && snaps[snap_by_pos[is]].pos <= x;
+        if (!end_on && !snap_on) {
+            if (seg.n_chk) { c.segments.push_back(seg); clear_seg(); }
+            seg.n_free += y - x;
+            continue;
+        }
+        if (seg.n_chk) { c.segments.push_back(seg); clear_seg(); }
+        seg.n_chk = y - x;
+        if (snap_on) { seg.snap_pos = (int32_t)snaps[snap_by_pos[is]].pos; seg.snap_slot = (uint8_t)snaps[snap_by_pos[is]].slot; }
+        if (end_on) {
+            seg.end_out = (uint16_t)order[ie];
+            seg.end_restore = (int8_t)(ie + 1 < (size_t)n && snap_of_pass[ie + 1] >= 0 ? snaps[snap_of_pass[ie + 1]].slot : MAX_SNAP_SLOTS);  // MAX_SNAP_SLOTS = pass-start state
+        }
+    }
+    if (seg.n_free || seg.n_chk) c.segments.push_back(seg);
+    us.n_segs = (uint32_t)c.segments.size() - us.seg_first;
+    return us;
+}
+
+void plan_chunk(const gphmm_batch *b, int64_t u0, int64_t u1, bool force_fp64, bool share, ChunkPlan &c) {
     c.u0 = u0; c.u1 = u1;
     c.r_lo = INT64_MAX; c.r_hi = 0;
     for (int64_t u = u0; u < u1; ++u) {
@@ -239,6 +386,7 @@ void plan_chunk(const gphmm_batch *b, int64_t u0, int64_t u1, bool force_fp64, C
     c.n_codes = CODE_FIRST_BASE + 5;
 
     c.streams.clear(); c.hap_len.clear(); c.hap_stream_off.clear(); c.units.clear(); c.tasks.clear();
+    c.sstreams.clear(); c.pass_info.clear(); c.segments.clear(); c.unit_sched.clear(); c.skipped_cells = 0;
     c.n_pairs = 0; c.cells = 0; c.max_stream_len = 0; c.max_hap_len = 0;
     std::vector<Task> raw;
     std::vector<uint8_t> bucket_of;
@@ -291,13 +439,22 @@ void plan_chunk(const gphmm_batch *b, int64_t u0, int64_t u1, bool force_fp64, C
         c.max_hap_len = std::max(c.max_hap_len, max_h);
         d.c0_exp = (force_fp64 ? C0_BASE_EXP_F64 : C0_BASE_EXP_F32) - ceil_log2(max_h);
         c.units.push_back(d);
+        {
+            // reads of 255+ bases run the striped kernel on the full stream: only shorter reads profit from sharing
+            int64_t fast_read_len = 0;
+            for (uint32_t r = 0; r < nr && nh; ++r) {
+                const uint32_t R = c.read_off[d.read_first + r + 1] - c.read_off[d.read_first + r];
+                if ((R + 1) / 32 + 1 <= 8) fast_read_len += R;
+            }
+            c.unit_sched.push_back(plan_unit_sharing(b, un, lut, share && !force_fp64, c, fast_read_len));
+        }
         if (nh == 0) continue;
         for (uint32_t r = 0; r < nr; ++r) {
             const uint32_t rl = d.read_first + r;
             const uint32_t R = c.read_off[rl + 1] - c.read_off[rl];
             Task t;
             t.read = rl; t.stream_off = stream_off; t.stream_len = stream_len;
-            t.out_base = d.out_base + r * nh; t.c0_exp = d.c0_exp; t.n_haps = nh; t.hap_first = d.hap_first; t.pad1 = 0;
+            t.out_base = d.out_base + r * nh; t.c0_exp = d.c0_exp; t.n_haps = nh; t.hap_first = d.hap_first; t.unit = (uint32_t)c.units.size() - 1;
             // fast kernels need two spare rows below the read (accumulator row + row-0 carrier): R + 2 <= 32 K
             const uint32_t k = (R + 1) / 32 + 1;
             const uint8_t bucket = force_fp64 ? 0 : (k <= 8 ? (uint8_t)(k - 1) : (uint8_t)8);
@@ -330,12 +487,14 @@ struct DeviceChunk {
     PinBuf h_out;   // pinned result buffer (out doubles + counters + err)
     size_t read_stride = 0;
     size_t off_read_off = 0, off_streams = 0, off_hap_len = 0, off_hap_stream_off = 0, off_units = 0, off_tasks = 0, meta_bytes = 0;
+    size_t off_sstreams = 0, off_pass = 0, off_segs = 0, off_sched = 0;
+    DevBuf snap;    // snapshot slabs of the fast kernels (prefix sharing)
     size_t off_sums = 0, off_out = 0, off_rtasks = 0, off_rsums = 0, off_counters = 0, off_err = 0, off_class = 0, work_bytes = 0;
     cudaEvent_t ev_start = nullptr, ev_f32 = nullptr, ev_f64 = nullptr, ev_done = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join[N_AUX] = {nullptr};  // bucket kernels run on side streams
     bool busy = false;
     void release() {
-        reads.release(); meta.release(); work.release(); bnd.release(); h_meta.release(); h_reads.release(); h_out.release();
+        reads.release(); meta.release(); work.release(); bnd.release(); snap.release(); h_meta.release(); h_reads.release(); h_out.release();
         if (ev_start) cudaEventDestroy(ev_start);
         if (ev_f32) cudaEventDestroy(ev_f32);
         if (ev_f64) cudaEventDestroy(ev_f64);
@@ -437,6 +596,7 @@ struct Device {
     DeviceChunk slots[N_SLOTS];
     DevBuf m2m;
     cudaEvent_t ev_step0 = nullptr, ev_step1 = nullptr;  // bracket a whole run_prepared step on streams[0]
+    cudaEvent_t ev_slot_done[N_SLOTS] = {nullptr};
     void init(int ord) {
         ordinal = ord;
         CK(cudaSetDevice(ord));
@@ -450,6 +610,7 @@ struct Device {
         CK(cudaMemcpy(m2m.p, t.m2m.data(), t.m2m.size() * sizeof(double), cudaMemcpyHostToDevice));
         CK(cudaEventCreate(&ev_step0));
         CK(cudaEventCreate(&ev_step1));
+        for (int i = 0; i < N_SLOTS; ++i) CK(cudaEventCreateWithFlags(&ev_slot_done[i], cudaEventDisableTiming));
         for (int i = 0; i < N_SLOTS; ++i) {
             CK(cudaStreamCreateWithFlags(&streams[i], cudaStreamNonBlocking));
             for (int k = 0; k < N_AUX; ++k) CK(cudaStreamCreateWithFlags(&aux[i][k], cudaStreamNonBlocking));
@@ -470,6 +631,7 @@ struct Device {
         m2m.release();
         if (ev_step0) cudaEventDestroy(ev_step0);
         if (ev_step1) cudaEventDestroy(ev_step1);
+        for (auto &e : ev_slot_done) { if (e) cudaEventDestroy(e); e = nullptr; }
         ev_step0 = ev_step1 = nullptr;
     }
 };
@@ -501,6 +663,10 @@ void upload_chunk(Device &dev, DeviceChunk &dc, const gphmm_batch *b, const Chun
     dc.off_hap_stream_off = o; o = align_up(o + c.hap_stream_off.size() * 4, 16);
     dc.off_units = o; o = align_up(o + c.units.size() * sizeof(UnitDesc), 16);
     dc.off_tasks = o; o = align_up(o + c.tasks.size() * sizeof(Task), 16);
+    dc.off_sstreams = o; o = align_up(o + c.sstreams.size() + 64, 16);
+    dc.off_pass = o; o = align_up(o + c.pass_info.size() * sizeof(PassInfo), 16);
+    dc.off_segs = o; o = align_up(o + c.segments.size() * sizeof(Segment), 16);
+    dc.off_sched = o; o = align_up(o + c.unit_sched.size() * sizeof(UnitSched), 16);
     dc.meta_bytes = std::max<size_t>(o, 16);
     dc.meta.reserve(dc.meta_bytes);
     dc.h_meta.reserve(dc.meta_bytes);
@@ -512,6 +678,11 @@ void upload_chunk(Device &dev, DeviceChunk &dc, const gphmm_batch *b, const Chun
     memcpy(hm + dc.off_hap_stream_off, c.hap_stream_off.data(), c.hap_stream_off.size() * 4);
     memcpy(hm + dc.off_units, c.units.data(), c.units.size() * sizeof(UnitDesc));
     memcpy(hm + dc.off_tasks, c.tasks.data(), c.tasks.size() * sizeof(Task));
+    memcpy(hm + dc.off_sstreams, c.sstreams.data(), c.sstreams.size());
+    memset(hm + dc.off_sstreams + c.sstreams.size(), CODE_NULL, 64);
+    memcpy(hm + dc.off_pass, c.pass_info.data(), c.pass_info.size() * sizeof(PassInfo));
+    memcpy(hm + dc.off_segs, c.segments.data(), c.segments.size() * sizeof(Segment));
+    memcpy(hm + dc.off_sched, c.unit_sched.data(), c.unit_sched.size() * sizeof(UnitSched));
     // work buffers
     const size_t np = std::max<uint32_t>(c.n_pairs, 1);
     o = 0;
@@ -571,6 +742,10 @@ int launch_chunk(Device &dev, DeviceChunk &dc, const ChunkPlan &c, cudaStream_t 
     ka.read_off = (const uint32_t *)(meta + dc.off_read_off);
     ka.streams = meta + dc.off_streams;
     ka.hap_len = (const uint32_t *)(meta + dc.off_hap_len);
+    ka.sstreams = meta + dc.off_sstreams;
+    ka.unit_sched = (const UnitSched *)(meta + dc.off_sched);
+    ka.pass_info = (const PassInfo *)(meta + dc.off_pass);
+    ka.segments = (const Segment *)(meta + dc.off_segs);
     ka.m2m = (const double *)dev.m2m.p;
     ka.err = (int *)(work + dc.off_err);
     ka.n_codes = c.n_codes;
@@ -643,6 +818,20 @@ int launch_chunk(Device &dev, DeviceChunk &dc, const ChunkPlan &c, cudaStream_t 
         std::sort(order, order + N_FP32_BUCKETS, [&](int x, int y) {
             return c.bucket_begin[x + 1] - c.bucket_begin[x] > c.bucket_begin[y + 1] - c.bucket_begin[y];
         });
+        // every concurrently running fast/flat launch gets its own snapshot slab (one region per CTA)
+        constexpr size_t SLAB_PER_CTA = (size_t)(MAX_SNAP_SLOTS + 1) * SNAP_REGS * 32 * sizeof(float);
+        {
+            size_t need = 0;
+            for (int k = 0; k < 8; ++k) {
+                const uint32_t n = c.bucket_begin[k + 1] - c.bucket_begin[k];
+                if (!n) continue;
+                need += (size_t)std::min<uint32_t>(n, (uint32_t)(dev.n_sms * dev.info(k, c.n_codes).ctas_per_sm)) * SLAB_PER_CTA;
+                for (int cl = 0; cl < c.n_classes; ++cl)
+                    need += (size_t)std::min<uint32_t>(n, (uint32_t)(dev.n_sms * dev.info(FLAT_KEY + k, c.n_codes).ctas_per_sm)) * SLAB_PER_CTA;
+            }
+            dc.snap.reserve(std::max<size_t>(need, 16));
+        }
+        size_t slab_cursor = 0;
         bool first_launch = true;
         auto launch_on = [&](const KernelInfo &ki, uint32_t n, int aux_idx, void **args) {
             const uint32_t grid = std::min<uint32_t>(n, (uint32_t)(dev.n_sms * ki.ctas_per_sm));
@@ -686,11 +875,17 @@ int launch_chunk(Device &dev, DeviceChunk &dc, const ChunkPlan &c, cudaStream_t 
                     fc.class_id = (uint32_t)cl;
                     fc.qi = qi; fc.qd = qd; fc.qc = qc;
                     ka.counter = counters + 16 + 8 * cl + k;
+                    ka.snap = (float *)((uint8_t *)dc.snap.p + slab_cursor);
+                    slab_cursor += (size_t)std::min<uint32_t>(n, (uint32_t)(dev.n_sms * dev.info(FLAT_KEY + k, c.n_codes).ctas_per_sm)) * SLAB_PER_CTA;
                     void *args[] = {&ka, &fc};
                     launch_on(dev.info(FLAT_KEY + k, c.n_codes), n, N_FP32_BUCKETS + 8 * cl + k, args);
                 }
             }
             ka.counter = counters + k;
+            if (k < 8) {
+                ka.snap = (float *)((uint8_t *)dc.snap.p + slab_cursor);
+                slab_cursor += (size_t)std::min<uint32_t>(n, (uint32_t)(dev.n_sms * dev.info(k, c.n_codes).ctas_per_sm)) * SLAB_PER_CTA;
+            }
             void *args[] = {&ka};
             launch_on(dev.info(k, c.n_codes), n, k, args);
         }
@@ -778,6 +973,7 @@ void finish_chunk(DeviceChunk &dc, const gphmm_batch *b, const ChunkPlan &c, dou
     std::lock_guard<std::mutex> lk(stats.mu);
     stats.s.pairs += c.n_pairs;
     stats.s.cells += c.cells;
+    stats.s.skipped_cells += c.skipped_cells;
     stats.s.rescued_pairs += rescued;
     stats.s.fp32_kernel_ms += ms32;
     stats.s.fp64_kernel_ms += ms64;
@@ -852,7 +1048,7 @@ void device_loop(gphmm *h, Device &dev, const gphmm_batch *b, const std::vector<
             }
             {
                 const double tp = now_ms();
-                plan_chunk(b, chunks[ci].first, chunks[ci].second, opt.force_fp64, plans[slot]);
+                plan_chunk(b, chunks[ci].first, chunks[ci].second, opt.force_fp64, h->cfg.no_prefix_sharing == 0, plans[slot]);
                 std::lock_guard<std::mutex> lk(h->stats.mu);
                 h->stats.s.host_stage_ms += now_ms() - tp;
             }
@@ -885,7 +1081,7 @@ int run_batch(gphmm *h, const gphmm_batch *b, double *out) {
     validate_batch(b);
     if (b->n_units == 0) return GPHMM_OK;
     if (!out) throw Error(GPHMM_ERR_INVALID_ARG, "out is null");
-    auto chunks = split_units(b, h->chunk_cells(), h->chunk_bytes());
+    auto chunks = split_units(b, h->chunk_cells(), h->chunk_bytes(), true);
     std::atomic<size_t> cursor{0};
     const size_t nd = h->devices.size();
     std::vector<std::string> errs(nd);
@@ -1117,14 +1313,14 @@ int gphmm_prepare(gphmm_t *h, const gphmm_batch *b, gphmm_prepared_t **out) {
         validate_batch(b);
         std::unique_ptr<gphmm_prepared> p(new gphmm_prepared());
         p->units.assign(b->units, b->units + b->n_units);
-        auto chunks = split_units(b, h->chunk_cells(), h->chunk_bytes());
+        auto chunks = split_units(b, h->chunk_cells(), h->chunk_bytes(), false);  // inputs are resident: no staging to hide
         const bool f64 = h->cfg.force_fp64 != 0;
         for (size_t ci = 0; ci < chunks.size(); ++ci) {
             std::unique_ptr<gphmm_prepared::Part> part(new gphmm_prepared::Part());
             part->device_index = (int)(ci % h->devices.size());
             Device &dev = *h->devices[part->device_index];
             CK(cudaSetDevice(dev.ordinal));
-            plan_chunk(b, chunks[ci].first, chunks[ci].second, f64, part->plan);
+            plan_chunk(b, chunks[ci].first, chunks[ci].second, f64, h->cfg.no_prefix_sharing == 0, part->plan);
             CK(cudaEventCreate(&part->dc.ev_start));
             CK(cudaEventCreate(&part->dc.ev_f32));
             CK(cudaEventCreate(&part->dc.ev_f64));
@@ -1153,19 +1349,28 @@ int gphmm_run_prepared(gphmm_t *h, gphmm_prepared_t *p, double *out) {
         b.n_units = (int64_t)p->units.size();
         int launches = 0;
         std::vector<char> used(h->devices.size(), 0);
+        std::vector<int> n_on_dev(h->devices.size(), 0);
         for (auto &part : p->parts) {
             Device &dev = *h->devices[part->device_index];
             CK(cudaSetDevice(dev.ordinal));
             if (!used[part->device_index]) {
                 CK(cudaEventRecord(dev.ev_step0, dev.streams[0]));
+                for (int sl = 1; sl < N_SLOTS; ++sl) CK(cudaStreamWaitEvent(dev.streams[sl], dev.ev_step0, 0));
                 used[part->device_index] = 1;
             }
-            launches += launch_chunk(dev, part->dc, part->plan, dev.streams[0], dev.aux[0], opt, out != nullptr);
+            // consecutive chunks go to different streams so that the tail of one overlaps the head of the next
+            const int sl = n_on_dev[part->device_index]++ % N_SLOTS;
+            launches += launch_chunk(dev, part->dc, part->plan, dev.streams[sl], dev.aux[sl], opt, out != nullptr);
         }
         for (size_t d = 0; d < h->devices.size(); ++d)
             if (used[d]) {
-                CK(cudaSetDevice(h->devices[d]->ordinal));
-                CK(cudaEventRecord(h->devices[d]->ev_step1, h->devices[d]->streams[0]));
+                Device &dev = *h->devices[d];
+                CK(cudaSetDevice(dev.ordinal));
+                for (int sl = 1; sl < N_SLOTS; ++sl) {
+                    CK(cudaEventRecord(dev.ev_slot_done[sl], dev.streams[sl]));
+                    CK(cudaStreamWaitEvent(dev.streams[0], dev.ev_slot_done[sl], 0));
+                }
+                CK(cudaEventRecord(dev.ev_step1, dev.streams[0]));
             }
         for (auto &part : p->parts) {
             Device &dev = *h->devices[part->device_index];
@@ -1216,6 +1421,38 @@ void gphmm_reset_stats(gphmm_t *h) {
     if (!h) return;
     std::lock_guard<std::mutex> lk(h->stats.mu);
     memset(&h->stats.s, 0, sizeof h->stats.s);
+}
+
+int gphmm_plan_stats(const gphmm_batch *b, int prefix_sharing, int64_t out[10]) {
+    if (!out) return GPHMM_ERR_INVALID_ARG;
+    return guarded(nullptr, [&]() -> int {
+        for (int k = 0; k < 10; ++k) out[k] = 0;
+        validate_batch(b);
+        auto chunks = split_units(b, (int64_t)100000000000LL, (int64_t)256 << 20, false);
+        ChunkPlan c;
+        for (auto &ch : chunks) {
+            plan_chunk(b, ch.first, ch.second, false, prefix_sharing != 0, c);
+            out[0] += (int64_t)c.units.size();
+            out[1] += (int64_t)c.pass_info.size();
+            out[2] += (int64_t)c.segments.size();
+            for (const Segment &sg : c.segments) {
+                out[3] += sg.n_free;
+                out[4] += sg.n_chk;
+                out[5] += sg.snap_pos != INT32_MIN;
+            }
+            for (size_t u = 0; u < c.units.size(); ++u) {
+                int64_t cols = 0;
+                for (uint32_t k = 0; k < c.units[u].n_haps; ++k) cols += c.hap_len[c.units[u].hap_first + k];
+                out[7] += cols;
+            }
+            // sstreams holds STREAM_PAD NULLs per unit, then the computed columns and one END per pass
+            out[6] -= (int64_t)c.sstreams.size() - (int64_t)c.units.size() * STREAM_PAD - (int64_t)c.pass_info.size();
+            out[8] += 1;
+            out[9] += (int64_t)c.tasks.size();
+        }
+        out[6] += out[7];
+        return GPHMM_OK;
+    });
 }
 
 void *gphmm_host_alloc(size_t bytes) {

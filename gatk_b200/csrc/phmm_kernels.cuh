@@ -50,8 +50,37 @@ struct __align__(16) Task {
     int32_t c0_exp;       // D[0][j] = 2^c0_exp
     uint32_t n_haps;      // haplotypes in the stream
     uint32_t hap_first;   // chunk-local index of the stream's first haplotype (hap_len[]); rescue: final output slot
-    uint32_t pad1;        // rescue: haplotype length
+    uint32_t unit;        // chunk-local unit index (unit_sched[]); rescue: haplotype length
 };
+
+// ---- prefix sharing between the haplotypes of a unit ("LOGLESS_CACHING": PairHMM.java:296-313,341-352) ----
+// The host sorts a unit's haplotypes lexicographically; consecutive haplotypes share a prefix whose DP columns
+// are identical (same read, same initial condition), so a pass over haplotype i+1 starts from a register
+// SNAPSHOT taken at the last shared column during an earlier pass instead of column 1.  The fast kernels run a
+// host-planned schedule of segments: n_free branch-free steps, then n_chk checked steps during which each lane
+// (a) snapshots its state when it has just finished stream position snap_pos, (b) handles END columns: write
+// the haplotype's sum, then restore the next pass's snapshot (or start from zero).  The planner makes every pass
+// at least 32 stream positions long (NULL columns before END if needed), so the 32-step windows of two END columns
+// never overlap and everything a lane needs at an END is uniform per segment.
+struct PassInfo {
+    uint16_t out_idx;      // haplotype index inside the unit = output column of this pass
+    int16_t restore_slot;  // snapshot restored BEFORE this pass starts; -1 = fresh start
+};
+struct Segment {
+    uint32_t n_free, n_chk;
+    int32_t snap_pos;      // stream position (1-based) whose completion triggers a snapshot in this segment, INT32_MIN = none
+    uint8_t snap_slot;
+    int8_t end_restore;    // the (single) END column met in this segment: snapshot slot the next pass restores, -1 = fresh start
+    uint16_t end_out;      // ... and the output column of the pass that ends there
+};
+struct UnitSched {
+    uint32_t pass_first, n_passes;  // into pass_info
+    uint32_t seg_first, n_segs;     // into segments
+    uint32_t sstream_off;           // first column of the unit's shared (prefix-compressed) stream
+    uint32_t pad0, pad1, pad2;
+};
+constexpr int MAX_SNAP_SLOTS = 8;      // + 1 slot per CTA for the pass-start state
+constexpr int SNAP_REGS = 3 * 8 + 4;  // M, I~, D~ of up to 8 rows + hand-off triple + accumulator
 
 struct KernelArgs {
     const uint8_t *rd_bases, *rd_q, *rd_i, *rd_d, *rd_c;  // raw per-base read arrays of the chunk
@@ -68,6 +97,11 @@ struct KernelArgs {
     const double *m2m;            // triangular matchToMatch table (PairHMMModel.java:71,86-94)
     int *err;                     // device error flag (GPHMM_ERR_BAD_QUAL)
     const uint8_t *read_class;    // per read: flat-quality class id (phmm_classify_kernel) or CLASS_GENERAL
+    const uint8_t *sstreams;      // shared (prefix-compressed) haplotype streams of the fast kernels
+    const UnitSched *unit_sched;
+    const PassInfo *pass_info;
+    const Segment *segments;
+    float *snap;                  // snapshot slab: per CTA MAX_SNAP_SLOTS x SNAP_REGS x 32 floats
     int32_t n_codes;
     int32_t tristate_off;
     uint8_t code_byte[MAX_CODES];  // code -> haplotype byte value
@@ -292,10 +326,41 @@ __device__ __forceinline__ uint32_t ldg_u8(const uint8_t *p) {
 template <int K> struct FastState {
     float M[K], I[K], D[K];
     float dgm, dgi, dgd;  // row above this lane's first row, previous column
+    float acc;            // flat kernel only: running sum of (M+I)[R][.]
     uint32_t y;           // haplotype code of this lane's current column
     const uint8_t *sp;    // points at that code
-    uint32_t hap_idx;
+    int p;                // checked steps only: stream position of this lane's current column
 };
+
+// snapshot slab layout: [slot][lane][SNAP_REGS]: only one lane saves / restores in any given step (lanes reach a
+// stream position one step apart), so each lane moves its own 112-byte record with 128-bit accesses.  `rec` is the
+// lane's record of slot 0; slot MAX_SNAP_SLOTS holds the pass-start state (all zero except the row-0 carrier), so
+// that "start from scratch" and "resume from a snapshot" are the same seven loads.
+constexpr int ZERO_SLOT = MAX_SNAP_SLOTS;
+constexpr int SLOT_STRIDE = 32 * SNAP_REGS;  // floats between two slots of the same lane
+template <int K> __device__ __forceinline__ void snap_save(const FastState<K> &st, float *rec, int slot) {
+    float v[SNAP_REGS];
+#pragma unroll
+    for (int k = 0; k < SNAP_REGS; ++k) v[k] = 0.f;
+#pragma unroll
+    for (int k = 0; k < K; ++k) { v[3 * k + 0] = st.M[k]; v[3 * k + 1] = st.I[k]; v[3 * k + 2] = st.D[k]; }
+    v[3 * K + 0] = st.dgm; v[3 * K + 1] = st.dgi; v[3 * K + 2] = st.dgd; v[3 * K + 3] = st.acc;
+    float4 *q = reinterpret_cast<float4 *>(rec + (size_t)slot * SLOT_STRIDE);
+#pragma unroll
+    for (int k = 0; k < (3 * K + 4 + 3) / 4; ++k) q[k] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+}
+template <int K> __device__ __forceinline__ void snap_restore(FastState<K> &st, const float *rec, int slot) {
+    float v[SNAP_REGS];
+    const float4 *q = reinterpret_cast<const float4 *>(rec + (size_t)slot * SLOT_STRIDE);
+#pragma unroll
+    for (int k = 0; k < (3 * K + 4 + 3) / 4; ++k) {
+        const float4 t = q[k];
+        v[4 * k] = t.x; v[4 * k + 1] = t.y; v[4 * k + 2] = t.z; v[4 * k + 3] = t.w;
+    }
+#pragma unroll
+    for (int k = 0; k < K; ++k) { st.M[k] = v[3 * k + 0]; st.I[k] = v[3 * k + 1]; st.D[k] = v[3 * k + 2]; }
+    st.dgm = v[3 * K + 0]; st.dgi = v[3 * K + 1]; st.dgd = v[3 * K + 2]; st.acc = v[3 * K + 3];
+}
 
 // One wavefront step.  CHECKED steps handle the END column (haplotype boundary); unchecked steps may only
 // run while no lane of the warp sits on an END column, which the caller guarantees from the haplotype
@@ -303,7 +368,8 @@ template <int K> struct FastState {
 template <int K, bool CHECKED>
 __device__ __forceinline__ void fast_step(FastState<K> &st, const float (&ca)[K], const float (&cb)[K], const float (&cc)[K],
                                           const float (&cg)[K], const float (&cd)[K], uint32_t tab_lane, int src_lane, int lane,
-                                          int acc_lane, int acc_slot, float c0, float *sums_task)
+                                          int acc_lane, int acc_slot, float c0, float *sums_task, float *slab, int snap_pos,
+                                          int snap_slot, int end_restore, uint32_t end_out)
 {
     constexpr int NV = (K + 3) / 4;
     constexpr unsigned FULL = 0xffffffffu;
@@ -345,19 +411,18 @@ __device__ __forceinline__ void fast_step(FastState<K> &st, const float (&ca)[K]
     for (int k = 0; k < K; ++k) st.M[k] = Mn[k];
     st.dgm = mu; st.dgi = iu; st.dgd = du;
     if (CHECKED) {
-        if (st.y == CODE_END) {
+        if (__builtin_expect(st.p == snap_pos, 0)) snap_save<K>(st, slab, snap_slot);
+        if (__builtin_expect(st.y == CODE_END, 0)) {
             if (lane == acc_lane) {
                 float v = 0.f;
 #pragma unroll
                 for (int k = 0; k < K; ++k)
                     if (k == acc_slot) v = st.M[k] + st.D[k];
-                sums_task[st.hap_idx] = v;
+                sums_task[end_out] = v;
             }
-            ++st.hap_idx;
-#pragma unroll
-            for (int k = 0; k < K; ++k) { st.M[k] = 0.f; st.D[k] = 0.f; }
-            if (lane == 31) st.D[K - 1] = c0;
+            snap_restore<K>(st, slab, end_restore);  // ZERO_SLOT = fresh start
         }
+        ++st.p;
     }
     st.y = y_next;
 }
@@ -451,27 +516,29 @@ __global__ void __launch_bounds__(32) phmm_fast_f32_kernel(const KernelArgs g)
         for (int k = 0; k < K; ++k) { st.M[k] = 0.f; st.I[k] = 0.f; st.D[k] = 0.f; }
         if (lane == 31) st.D[K - 1] = c0;
         st.dgm = 0.f; st.dgi = 0.f; st.dgd = lane == 0 ? c0 : 0.f;
-        st.hap_idx = 0;
-        // lane l works on column (step - l); columns <= 0 and > P read the NULL padding around the stream
-        st.sp = g.streams + t.stream_off - lane;
+        st.acc = 0.f;
+        st.p = 0;
+        const UnitSched us = g.unit_sched[t.unit];
+        // lane l works on stream position (step - l); positions <= 0 and > P read the NULL padding around the stream
+        st.sp = g.sstreams + us.sstream_off - lane;
         st.y = ldg_u8(st.sp);
         float *const sums_task = sums + t.out_base;
+        float *const slab = g.snap + (size_t)blockIdx.x * ((MAX_SNAP_SLOTS + 1) * SLOT_STRIDE) + lane * SNAP_REGS;
+        snap_save<K>(st, slab, ZERO_SLOT);  // the pass-start state, restored at every END that begins a fresh pass
 
-        // Step s (1-based) puts lane l on column s - l.  Haplotype h ends with an END column at stream position
-        // e_h; some lane sits on it during steps e_h .. e_h + 31.  Everything else runs the branch-free loop.
-        int step = 1, e = 0;
-        for (uint32_t h = 0; h < t.n_haps; ++h) {
-            e += (int)g.hap_len[t.hap_first + h] + 1;
-            const int n_free = e - step;
+        int step = 1;
+        for (uint32_t sg = 0; sg < us.n_segs; ++sg) {
+            const Segment seg = g.segments[us.seg_first + sg];
 #pragma unroll 2
-            for (int s = 0; s < n_free; ++s)
-                fast_step<K, false>(st, ca, cb, cc, cg, cd, tab_lane, src_lane, lane, acc_lane, acc_slot, c0, sums_task);
-            if (n_free > 0) step = e;
-            const int n_chk = e + 32 - step;
+            for (uint32_t s = 0; s < seg.n_free; ++s)
+                fast_step<K, false>(st, ca, cb, cc, cg, cd, tab_lane, src_lane, lane, acc_lane, acc_slot, c0, sums_task, slab, 0, 0, 0, 0);
+            step += (int)seg.n_free;
+            st.p = step - lane;
 #pragma unroll 1
-            for (int s = 0; s < n_chk; ++s)
-                fast_step<K, true>(st, ca, cb, cc, cg, cd, tab_lane, src_lane, lane, acc_lane, acc_slot, c0, sums_task);
-            step = e + 32;
+            for (uint32_t s = 0; s < seg.n_chk; ++s)
+                fast_step<K, true>(st, ca, cb, cc, cg, cd, tab_lane, src_lane, lane, acc_lane, acc_slot, c0, sums_task, slab, seg.snap_pos,
+                                   seg.snap_slot, seg.end_restore, seg.end_out);
+            step += (int)seg.n_chk;
         }
     }
 }
@@ -528,18 +595,10 @@ __global__ void __launch_bounds__(128) phmm_classify_kernel(const ClassifyArgs a
     }
 }
 
-template <int K> struct FlatState {
-    float M[K], I[K], D[K];
-    float dgm, dgi, dgd;
-    float acc;
-    uint32_t y;
-    const uint8_t *sp;
-    uint32_t hap_idx;
-};
-
 template <int K, int SLOT, bool CHECKED>
-__device__ __forceinline__ void flat_step(FlatState<K> &st, const FlatCoef &f, float B0, float G0, float E0, uint32_t tab_lane,
-                                          int src_lane, int lane, int acc_lane, float *sums_task)
+__device__ __forceinline__ void flat_step(FastState<K> &st, const FlatCoef &f, float B0, float G0, float E0, uint32_t tab_lane,
+                                          int src_lane, int lane, int acc_lane, float *sums_task, float *slab, int snap_pos,
+                                          int snap_slot, int end_restore, uint32_t end_out)
 {
     constexpr int NV = (K + 3) / 4;
     constexpr unsigned FULL = 0xffffffffu;
@@ -580,48 +639,56 @@ __device__ __forceinline__ void flat_step(FlatState<K> &st, const FlatCoef &f, f
 #pragma unroll
     for (int k = 0; k < K; ++k) st.M[k] = Mn[k];
     st.dgm = mu; st.dgi = iu; st.dgd = du;
+    // The END column contributes nothing to the sum by construction (prior 0), but when the next pass restores a
+    // snapshot the lane above has ALREADY restored it one step ago, so the I~ chain of this END column sees foreign
+    // values: the haplotype's sum is therefore the accumulator BEFORE this step.
+    const float acc_before = st.acc;
     st.acc += st.M[SLOT];
     st.acc = __fmaf_rn(f.tmi, st.I[SLOT], st.acc);
     if (CHECKED) {
-        if (st.y == CODE_END) {
-            if (lane == acc_lane) sums_task[st.hap_idx] = st.acc;
-            ++st.hap_idx;
-            st.acc = 0.f;
-#pragma unroll
-            for (int k = 0; k < K; ++k) st.D[k] = 0.f;
+        if (__builtin_expect(st.p == snap_pos, 0)) snap_save<K>(st, slab, snap_slot);
+        if (__builtin_expect(st.y == CODE_END, 0)) {
+            if (lane == acc_lane) sums_task[end_out] = acc_before;
+            snap_restore<K>(st, slab, end_restore);  // ZERO_SLOT = fresh start
         }
+        ++st.p;
     }
     st.y = y_next;
 }
 
 template <int K, int SLOT>
-__device__ __forceinline__ void flat_sweep(FlatState<K> &st, const FlatCoef &f, float B0, float G0, float E0, uint32_t tab_lane,
-                                        int src_lane, int lane, int acc_lane, float *sums_task, const uint32_t *hap_len, uint32_t n_haps)
+__device__ __forceinline__ void flat_sweep(FastState<K> &st, const FlatCoef &f, float B0, float G0, float E0, uint32_t tab_lane,
+                                           int src_lane, int lane, int acc_lane, float *sums_task, float *slab, const Segment *segs,
+                                           uint32_t n_segs)
 {
-    int step = 1, e = 0;
-    for (uint32_t h = 0; h < n_haps; ++h) {
-        e += (int)hap_len[h] + 1;
-        const int n_free = e - step;
+    int step = 1;
+    for (uint32_t sg = 0; sg < n_segs; ++sg) {
+        const Segment seg = segs[sg];
 #pragma unroll 2
-        for (int s = 0; s < n_free; ++s) flat_step<K, SLOT, false>(st, f, B0, G0, E0, tab_lane, src_lane, lane, acc_lane, sums_task);
-        if (n_free > 0) step = e;
-        const int n_chk = e + 32 - step;
+        for (uint32_t s = 0; s < seg.n_free; ++s)
+            flat_step<K, SLOT, false>(st, f, B0, G0, E0, tab_lane, src_lane, lane, acc_lane, sums_task, slab, 0, 0, 0, 0);
+        step += (int)seg.n_free;
+        st.p = step - lane;
 #pragma unroll 1
-        for (int s = 0; s < n_chk; ++s) flat_step<K, SLOT, true>(st, f, B0, G0, E0, tab_lane, src_lane, lane, acc_lane, sums_task);
-        step = e + 32;
+        for (uint32_t s = 0; s < seg.n_chk; ++s)
+            flat_step<K, SLOT, true>(st, f, B0, G0, E0, tab_lane, src_lane, lane, acc_lane, sums_task, slab, seg.snap_pos, seg.snap_slot,
+                                     seg.end_restore, seg.end_out);
+        step += (int)seg.n_chk;
     }
 }
 
 template <int K, int SLOT>
-__device__ __forceinline__ void flat_dispatch(int slot, FlatState<K> &st, const FlatCoef &f, float B0, float G0, float E0, uint32_t tab_lane,
-                                              int src_lane, int lane, int acc_lane, float *sums_task, const uint32_t *hap_len, uint32_t n_haps)
+__device__ __forceinline__ void flat_dispatch(int slot, FastState<K> &st, const FlatCoef &f, float B0, float G0, float E0, uint32_t tab_lane,
+                                              int src_lane, int lane, int acc_lane, float *sums_task, float *slab, const Segment *segs,
+                                              uint32_t n_segs)
 {
-    if (slot == SLOT) flat_sweep<K, SLOT>(st, f, B0, G0, E0, tab_lane, src_lane, lane, acc_lane, sums_task, hap_len, n_haps);
-    else if constexpr (SLOT + 1 < K) flat_dispatch<K, SLOT + 1>(slot, st, f, B0, G0, E0, tab_lane, src_lane, lane, acc_lane, sums_task, hap_len, n_haps);
+    if (slot == SLOT) flat_sweep<K, SLOT>(st, f, B0, G0, E0, tab_lane, src_lane, lane, acc_lane, sums_task, slab, segs, n_segs);
+    else if constexpr (SLOT + 1 < K) flat_dispatch<K, SLOT + 1>(slot, st, f, B0, G0, E0, tab_lane, src_lane, lane, acc_lane, sums_task, slab, segs, n_segs);
 }
 
+// 28 one-warp CTAs per SM (the shared-memory limit of the K=8 prior table) need <= 73 registers per thread
 template <int K>
-__global__ void __launch_bounds__(32) phmm_flat_f32_kernel(const KernelArgs g, const FlatCoef f)
+__global__ void __launch_bounds__(32, 28) phmm_flat_f32_kernel(const KernelArgs g, const FlatCoef f)
 {
     constexpr int NV = (K + 3) / 4;
     constexpr unsigned FULL = 0xffffffffu;
@@ -673,21 +740,24 @@ __global__ void __launch_bounds__(32) phmm_flat_f32_kernel(const KernelArgs g, c
         if (f.qi > 127u || f.qd > 127u || f.qc > 127u) atomicExch(g.err, 1);
         __syncwarp();
 
-        FlatState<K> st;
+        FastState<K> st;
 #pragma unroll
         for (int k = 0; k < K; ++k) { st.M[k] = 0.f; st.I[k] = 0.f; st.D[k] = 0.f; }
         st.dgm = 0.f; st.dgi = 0.f; st.dgd = 0.f;
         st.acc = 0.f;
-        st.hap_idx = 0;
-        st.sp = g.streams + t.stream_off - lane;
+        st.p = 0;
+        const UnitSched us = g.unit_sched[t.unit];
+        st.sp = g.sstreams + us.sstream_off - lane;
         st.y = ldg_u8(st.sp);
         // slot 0: lane 0 holds row 1 (virtual row 0 above it: M = I~ = 0, c*D~ = tIM*c0)
         const float B0 = lane == 0 ? 0.f : f.b;
         const float G0 = lane == 0 ? 0.f : f.g;
         const float E0 = lane == 0 ? f.tim * c0 : 0.f;
         const int acc_lane = (R - 1) / K, acc_slot = (R - 1) % K;
-        flat_dispatch<K, 0>(acc_slot, st, f, B0, G0, E0, tab_lane, src_lane, lane, acc_lane, sums + t.out_base,
-                            g.hap_len + t.hap_first, t.n_haps);
+        float *const slab = g.snap + (size_t)blockIdx.x * ((MAX_SNAP_SLOTS + 1) * SLOT_STRIDE) + lane * SNAP_REGS;
+        snap_save<K>(st, slab, ZERO_SLOT);  // the pass-start state (all zero), restored at every END that begins a fresh pass
+        flat_dispatch<K, 0>(acc_slot, st, f, B0, G0, E0, tab_lane, src_lane, lane, acc_lane, sums + t.out_base, slab,
+                            g.segments + us.seg_first, us.n_segs);
     }
 }
 
@@ -743,7 +813,7 @@ __global__ void __launch_bounds__(128) phmm_epilogue_f32(const EpilogueArgs e)
                     t.c0_exp = C0_BASE_EXP_F64 - lg;
                     t.n_haps = 1;
                     t.hap_first = d.out_base + k;  // final output slot
-                    t.pad1 = H;
+                    t.unit = H;
                     e.rescue_tasks[slot] = t;
                 }
                 e.out[d.out_base + k] = __longlong_as_double(0x7ff8000000000000LL);  // placeholder NaN
@@ -776,7 +846,7 @@ __global__ void __launch_bounds__(128) phmm_epilogue_rescue(const Task *tasks, c
     const uint32_t n = min(*n_rescue, capacity);
     for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
         const Task t = tasks[k];
-        out[t.hap_first] = log10(sums[k]) - log10_c0H(t.c0_exp, t.pad1);
+        out[t.hap_first] = log10(sums[k]) - log10_c0H(t.c0_exp, t.unit);
     }
 }
 

@@ -24,7 +24,7 @@ class GpuPhmmError(RuntimeError):
 class _Config(ctypes.Structure):
     _fields_ = [("struct_size", ctypes.c_int32), ("n_devices", ctypes.c_int32), ("devices", _i32p),
                 ("force_fp64", ctypes.c_int32), ("host_threads", ctypes.c_int32), ("tristate_off", ctypes.c_int32),
-                ("reserved0", ctypes.c_int32), ("chunk_cells", ctypes.c_int64), ("chunk_bytes", ctypes.c_int64)]
+                ("no_prefix_sharing", ctypes.c_int32), ("chunk_cells", ctypes.c_int64), ("chunk_bytes", ctypes.c_int64)]
 
 
 class _Unit(ctypes.Structure):
@@ -41,7 +41,7 @@ class _Batch(ctypes.Structure):
 
 class Stats(ctypes.Structure):
     _fields_ = [("pairs", ctypes.c_int64), ("cells", ctypes.c_int64), ("rescued_pairs", ctypes.c_int64),
-                ("rescued_cells", ctypes.c_int64), ("h2d_bytes", ctypes.c_int64), ("d2h_bytes", ctypes.c_int64),
+                ("skipped_cells", ctypes.c_int64), ("h2d_bytes", ctypes.c_int64), ("d2h_bytes", ctypes.c_int64),
                 ("kernel_launches", ctypes.c_int64), ("fp32_kernel_ms", ctypes.c_double), ("fp64_kernel_ms", ctypes.c_double),
                 ("device_ms", ctypes.c_double), ("host_stage_ms", ctypes.c_double), ("wall_ms", ctypes.c_double)]
 
@@ -53,7 +53,7 @@ UNIT_DTYPE = np.dtype([("read_begin", "<i8"), ("read_end", "<i8"), ("hap_begin",
 
 EXPORTS = ["gphmm_abi_version", "gphmm_device_count", "gphmm_strerror", "gphmm_create", "gphmm_destroy",
            "gphmm_last_error", "gphmm_compute", "gphmm_submit", "gphmm_wait", "gphmm_prepare", "gphmm_run_prepared",
-           "gphmm_release_prepared", "gphmm_get_stats", "gphmm_reset_stats", "gphmm_host_alloc", "gphmm_host_free"]
+           "gphmm_release_prepared", "gphmm_get_stats", "gphmm_reset_stats", "gphmm_plan_stats", "gphmm_host_alloc", "gphmm_host_free"]
 
 
 def lib_path():
@@ -95,6 +95,8 @@ def load_library():
     L.gphmm_get_stats.argtypes = [ctypes.c_void_p, ctypes.POINTER(Stats)]
     L.gphmm_reset_stats.restype = None
     L.gphmm_reset_stats.argtypes = [ctypes.c_void_p]
+    L.gphmm_plan_stats.restype = ctypes.c_int
+    L.gphmm_plan_stats.argtypes = [ctypes.POINTER(_Batch), ctypes.c_int, ctypes.POINTER(ctypes.c_int64)]
     L.gphmm_host_alloc.restype = ctypes.c_void_p
     L.gphmm_host_alloc.argtypes = [ctypes.c_size_t]
     L.gphmm_host_free.restype = None
@@ -208,10 +210,23 @@ class Batch:
         return Batch(cat(cols[0]), cat(cols[1]), cat(cols[2]), cat(cols[3]), cat(cols[4]), read_off, cat(hs), hap_off, units)
 
 
+def plan_stats(batch, prefix_sharing=True):
+    """Host-only planning totals (gphmm_plan_stats); works without a GPU."""
+    L = load_library()
+    out = (ctypes.c_int64 * 10)()
+    b = batch.c_struct()
+    rc = L.gphmm_plan_stats(ctypes.byref(b), int(prefix_sharing), out)
+    if rc != 0:
+        raise GpuPhmmError(rc, L.gphmm_strerror(rc).decode())
+    keys = ("units", "passes", "segments", "free_steps", "checked_steps", "snapshots", "skipped_columns", "total_columns", "chunks", "tasks")
+    return dict(zip(keys, [int(x) for x in out]))
+
+
 class GpuPhmm:
     """RAII wrapper of a gphmm_t handle."""
 
-    def __init__(self, devices=None, force_fp64=False, host_threads=0, tristate_off=False, chunk_cells=0, chunk_bytes=0):
+    def __init__(self, devices=None, force_fp64=False, host_threads=0, tristate_off=False, chunk_cells=0, chunk_bytes=0,
+                 no_prefix_sharing=False):
         self._L = load_library()
         self._h = ctypes.c_void_p()
         cfg = _Config()
@@ -224,6 +239,7 @@ class GpuPhmm:
         cfg.force_fp64 = int(force_fp64)
         cfg.host_threads = int(host_threads)
         cfg.tristate_off = int(tristate_off)
+        cfg.no_prefix_sharing = int(no_prefix_sharing)
         cfg.chunk_cells = int(chunk_cells)
         cfg.chunk_bytes = int(chunk_bytes)
         rc = self._L.gphmm_create(ctypes.byref(cfg), ctypes.byref(self._h))

@@ -57,7 +57,7 @@ typedef struct gphmm_config {
     int32_t force_fp64;       /* PairHMMNativeArguments.useDoublePrecision */
     int32_t host_threads;     /* PairHMMNativeArguments.maxNumberOfThreads: staging threads, 0 = default */
     int32_t tristate_off;     /* PairHMM.doNotUseTristateCorrection() (tests only) */
-    int32_t reserved0;
+    int32_t no_prefix_sharing; /* 1: recompute every haplotype from column 1 (A/B switch; results are bit-identical) */
     int64_t chunk_cells;      /* target DP cells per device chunk, 0 = default */
     int64_t chunk_bytes;      /* max staged input bytes per device chunk, 0 = default */
 } gphmm_config;
@@ -89,7 +89,7 @@ typedef struct gphmm_stats {
     int64_t pairs;           /* (read, haplotype) pairs computed */
     int64_t cells;           /* sum of R*H over pairs (LoglessPairHMM.java:47-49, no padding) */
     int64_t rescued_pairs;   /* pairs redone in fp64 */
-    int64_t rescued_cells;
+    int64_t skipped_cells;   /* cells NOT executed thanks to haplotype-prefix sharing (still counted in `cells`) */
     int64_t h2d_bytes;
     int64_t d2h_bytes;
     int64_t kernel_launches; /* CUDA kernels launched by this library */
@@ -128,6 +128,13 @@ void gphmm_release_prepared(gphmm_t *h, gphmm_prepared_t *p);
 /* Statistics accumulate over calls until reset. */
 int gphmm_get_stats(const gphmm_t *h, gphmm_stats *out);
 void gphmm_reset_stats(gphmm_t *h);
+
+/* Host-only: plans the batch exactly as gphmm_compute would (chunking, haplotype sorting, prefix-sharing snapshots,
+ * step schedule) without touching a GPU and reports the totals:
+ *   out[0] units, out[1] haplotype passes, out[2] schedule segments, out[3] branch-free steps, out[4] checked steps,
+ *   out[5] snapshots, out[6] haplotype columns skipped by prefix sharing, out[7] haplotype columns in total,
+ *   out[8] chunks, out[9] tasks.  Used by tests and for sizing; needs no device. */
+int gphmm_plan_stats(const gphmm_batch *batch, int prefix_sharing, int64_t out[10]);
 
 /* Pinned host memory for callers that want zero-copy staging. */
 void *gphmm_host_alloc(size_t bytes);

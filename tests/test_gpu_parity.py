@@ -314,3 +314,50 @@ def test_plugin_surface_like_vector_pairhmm_unit_test():
         hmm2.close()
     finally:
         hmm.close()
+
+
+def _nested_haplotype_unit(seed):
+    """haplotypes built to stress prefix sharing: duplicates, nested prefixes, branches at many depths, short haps"""
+    rng = np.random.default_rng(seed)
+    L = np.frombuffer(b"ACGT", dtype=np.uint8)
+    base = L[rng.integers(0, 4, 420)]
+    haps = [base.tobytes(), base.tobytes(), base[:300].tobytes(), base[:31].tobytes(), base[:33].tobytes()]
+    for d in (1, 20, 31, 32, 33, 47, 64, 65, 100, 200, 250, 399, 419):
+        h = base.copy()
+        h[d] = L[(np.searchsorted(L, h[d]) + 1) % 4]
+        haps.append(h.tobytes())
+        h2 = h.copy()
+        if d + 40 < 420:
+            h2[d + 40] = L[(np.searchsorted(L, h2[d + 40]) + 2) % 4]
+            haps.append(h2[: 300 + d // 4].tobytes())
+    order = rng.permutation(len(haps))
+    haps = [haps[k] for k in order]
+    reads = []
+    for R in (10, 31, 62, 100, 151, 250, 254, 255, 300):
+        off = int(rng.integers(0, 420 - R))
+        rd = base[off:off + R].copy()
+        rd[R // 2] = ord("A") if rd[R // 2] != ord("A") else ord("G")
+        q = np.clip(rng.normal(32, 6, R), 6, 41).astype(np.uint8)
+        reads.append((rd, q, const_quals(R, 45), const_quals(R, 45), const_quals(R, 10)))
+        reads.append((rd, q, rng.integers(20, 50, R).astype(np.uint8), rng.integers(20, 50, R).astype(np.uint8), rng.integers(5, 30, R).astype(np.uint8)))
+    return Batch.single_unit(reads, haps)
+
+
+def test_prefix_sharing_is_bit_identical_and_correct():
+    # haplotype-prefix caching (PairHMMUnitTest.java:607-677 testHaplotypeIndexing pins caching == full recompute)
+    with GpuPhmm() as shared, GpuPhmm(no_prefix_sharing=True) as plain:
+        for seed in range(4):
+            b = _nested_haplotype_unit(seed)
+            shared.reset_stats()
+            a = shared.compute(b)
+            c = plain.compute(b)
+            assert np.array_equal(a, c)
+            assert shared.stats()["skipped_cells"] > 0.15 * shared.stats()["cells"]
+            _check(a, oracle_batch(b), TOL)
+        b = synth.config2(60)
+        a, c = shared.compute(b), plain.compute(b)
+        assert np.array_equal(a, c)
+        assert plain.stats()["skipped_cells"] == 0
+        for seed in range(3):
+            b = synth.random_batch(500 + seed, n_units=6, max_haps=12, hap_len=(60, 400), wild_quals=bool(seed % 2))
+            assert np.array_equal(shared.compute(b), plain.compute(b))
