@@ -1020,7 +1020,7 @@ struct gphmm {
     std::thread worker;
     bool stop = false;
 
-    int64_t chunk_cells() const { return cfg.chunk_cells > 0 ? cfg.chunk_cells : (int64_t)100000000000LL; }
+    int64_t chunk_cells() const { return cfg.chunk_cells > 0 ? cfg.chunk_cells : (int64_t)30000000000LL; }
     int64_t chunk_bytes() const { return cfg.chunk_bytes > 0 ? cfg.chunk_bytes : (int64_t)256 << 20; }
 };
 
@@ -1028,14 +1028,91 @@ namespace {
 
 // Process chunks [ci, ...) of a batch on one device with two stream slots; chunks are claimed from a
 // shared cursor so that several devices drain the same batch (the host-side work queue of SURVEY 8e).
+// Host-side planning pool: chunk plans are built ahead of the GPU by a few threads (PairHMMNativeArguments.
+// maxNumberOfThreads -> gphmm_config.host_threads) and handed to the device loops in chunk order.
+struct PlanPool {
+    const gphmm_batch *b;
+    const std::vector<std::pair<int64_t, int64_t>> &chunks;
+    bool f64, share;
+    Stats &stats;
+    std::vector<std::unique_ptr<ChunkPlan>> ready;
+    std::vector<char> done;
+    std::vector<int> err_code;
+    std::vector<std::string> err_text;
+    std::mutex mu;
+    std::condition_variable cv;
+    size_t next_plan = 0, consumed = 0, lookahead;
+    bool cancel = false;
+    std::vector<std::thread> threads;
+
+    PlanPool(const gphmm_batch *b_, const std::vector<std::pair<int64_t, int64_t>> &c, bool f64_, bool share_, int n_threads, Stats &st)
+        : b(b_), chunks(c), f64(f64_), share(share_), stats(st), ready(c.size()), done(c.size(), 0), err_code(c.size(), 0),
+          err_text(c.size()) {
+        n_threads = std::max(1, std::min<int>(n_threads, (int)c.size()));
+        lookahead = (size_t)n_threads + N_SLOTS;
+        for (int t = 0; t < n_threads; ++t) threads.emplace_back([this] { work(); });
+    }
+    ~PlanPool() {
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            cancel = true;
+        }
+        cv.notify_all();
+        for (auto &t : threads) t.join();
+    }
+    void work() {
+        for (;;) {
+            size_t ci;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return cancel || next_plan >= chunks.size() || next_plan < consumed + lookahead; });
+                if (cancel || next_plan >= chunks.size()) return;
+                ci = next_plan++;
+            }
+            std::unique_ptr<ChunkPlan> p(new ChunkPlan());
+            int code = 0;
+            std::string text;
+            const double t0 = now_ms();
+            try {
+                plan_chunk(b, chunks[ci].first, chunks[ci].second, f64, share, *p);
+            } catch (const Error &e) {
+                code = e.code; text = e.what();
+            } catch (const std::exception &e) {
+                code = GPHMM_ERR_NOMEM; text = e.what();
+            }
+            {
+                std::lock_guard<std::mutex> lk(stats.mu);
+                stats.s.host_stage_ms += now_ms() - t0;
+            }
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                ready[ci] = std::move(p);
+                err_code[ci] = code; err_text[ci] = text;
+                done[ci] = 1;
+            }
+            cv.notify_all();
+        }
+    }
+    std::unique_ptr<ChunkPlan> take(size_t ci) {
+        std::unique_lock<std::mutex> lk(mu);
+        cv.wait(lk, [&] { return done[ci] != 0; });
+        consumed = std::max(consumed, ci + 1);
+        cv.notify_all();
+        if (err_code[ci]) throw Error(err_code[ci], err_text[ci]);
+        return std::move(ready[ci]);
+    }
+};
+
+// Process chunks of a batch on one device with N_SLOTS stream slots; chunks are claimed from a shared cursor so
+// that several devices drain the same batch (the host-side work queue of SURVEY 8e).
 void device_loop(gphmm *h, Device &dev, const gphmm_batch *b, const std::vector<std::pair<int64_t, int64_t>> &chunks,
-                 std::atomic<size_t> &cursor, double *out, std::string &err, int &rc) {
+                 PlanPool &pool, std::atomic<size_t> &cursor, double *out, std::string &err, int &rc) {
     try {
         CK(cudaSetDevice(dev.ordinal));
         RunOptions opt;
         opt.force_fp64 = h->cfg.force_fp64 != 0;
         opt.tristate_off = h->cfg.tristate_off != 0;
-        std::vector<ChunkPlan> plans(N_SLOTS);
+        std::unique_ptr<ChunkPlan> plans[N_SLOTS];
         bool inflight[N_SLOTS] = {false};
         int slot = 0;
         int launches = 0;
@@ -1043,23 +1120,18 @@ void device_loop(gphmm *h, Device &dev, const gphmm_batch *b, const std::vector<
             const size_t ci = cursor.fetch_add(1);
             if (ci >= chunks.size()) break;
             if (inflight[slot]) {
-                finish_chunk(dev.slots[slot], b, plans[slot], out, h->stats, true);
+                finish_chunk(dev.slots[slot], b, *plans[slot], out, h->stats, true);
                 inflight[slot] = false;
             }
-            {
-                const double tp = now_ms();
-                plan_chunk(b, chunks[ci].first, chunks[ci].second, opt.force_fp64, h->cfg.no_prefix_sharing == 0, plans[slot]);
-                std::lock_guard<std::mutex> lk(h->stats.mu);
-                h->stats.s.host_stage_ms += now_ms() - tp;
-            }
-            upload_chunk(dev, dev.slots[slot], b, plans[slot], dev.streams[slot], opt.force_fp64, h->stats);
-            launches += launch_chunk(dev, dev.slots[slot], plans[slot], dev.streams[slot], dev.aux[slot], opt, true);
+            plans[slot] = pool.take(ci);
+            upload_chunk(dev, dev.slots[slot], b, *plans[slot], dev.streams[slot], opt.force_fp64, h->stats);
+            launches += launch_chunk(dev, dev.slots[slot], *plans[slot], dev.streams[slot], dev.aux[slot], opt, true);
             inflight[slot] = true;
             slot = (slot + 1) % N_SLOTS;
         }
         for (int s = 0; s < N_SLOTS; ++s) {
             if (inflight[slot]) {
-                finish_chunk(dev.slots[slot], b, plans[slot], out, h->stats, true);
+                finish_chunk(dev.slots[slot], b, *plans[slot], out, h->stats, true);
                 inflight[slot] = false;
             }
             slot = (slot + 1) % N_SLOTS;
@@ -1086,14 +1158,18 @@ int run_batch(gphmm *h, const gphmm_batch *b, double *out) {
     const size_t nd = h->devices.size();
     std::vector<std::string> errs(nd);
     std::vector<int> rcs(nd, GPHMM_OK);
-    if (nd == 1 || chunks.size() == 1) {
-        device_loop(h, *h->devices[0], b, chunks, cursor, out, errs[0], rcs[0]);
-    } else {
-        std::vector<std::thread> th;
-        for (size_t d = 0; d < nd; ++d)
-            th.emplace_back(device_loop, h, std::ref(*h->devices[d]), b, std::cref(chunks), std::ref(cursor), out,
-                            std::ref(errs[d]), std::ref(rcs[d]));
-        for (auto &t : th) t.join();
+    {
+        const int n_threads = h->cfg.host_threads > 0 ? h->cfg.host_threads : 4;  // GATK's --native-pair-hmm-threads default
+        PlanPool pool(b, chunks, h->cfg.force_fp64 != 0, h->cfg.no_prefix_sharing == 0, n_threads, h->stats);
+        if (nd == 1 || chunks.size() == 1) {
+            device_loop(h, *h->devices[0], b, chunks, pool, cursor, out, errs[0], rcs[0]);
+        } else {
+            std::vector<std::thread> th;
+            for (size_t d = 0; d < nd; ++d)
+                th.emplace_back(device_loop, h, std::ref(*h->devices[d]), b, std::cref(chunks), std::ref(pool), std::ref(cursor), out,
+                                std::ref(errs[d]), std::ref(rcs[d]));
+            for (auto &t : th) t.join();
+        }
     }
     {
         std::lock_guard<std::mutex> lk(h->stats.mu);
