@@ -139,6 +139,7 @@ struct ChunkPlan {
     std::vector<Segment> segments;
     std::vector<UnitSched> unit_sched;
     int64_t skipped_cells = 0;
+    int64_t computed_columns = 0;          // haplotype columns the fast kernels really sweep (after prefix sharing)
     int n_classes = 0;                     // flat-quality classes sampled from the chunk's reads
     uint8_t class_qi[MAX_FLAT_CLASSES], class_qd[MAX_FLAT_CLASSES], class_qc[MAX_FLAT_CLASSES];
 };
@@ -208,18 +209,9 @@ std::vector<std::pair<int64_t, int64_t>> split_units(const gphmm_batch *b, int64
 // Plans the shared (prefix-compressed) stream of one unit: haplotypes sorted lexicographically, pass i+1 resumes
 // from a snapshot taken at the last column it shares with its predecessors.  Appends to c.sstreams / pass_info /
 // segments and returns the unit's schedule.  With share == false every pass starts from column 1 in input order.
-UnitSched plan_unit_sharing(const gphmm_batch *b, const gphmm_unit &un, const int16_t *lut, bool share, ChunkPlan &c,
-                            int64_t sum_read_len) {
-    constexpr uint32_t MIN_DEPTH = 32, SPACING = 32;
-    UnitSched us;
-    memset(&us, 0, sizeof us);
+// Lexicographic order of a unit's haplotypes (input order when sharing is off).
+std::vector<int> sorted_hap_order(const gphmm_batch *b, const gphmm_unit &un, bool share) {
     const int n = (int)(un.hap_end - un.hap_begin);
-    us.pass_first = (uint32_t)c.pass_info.size();
-    us.n_passes = (uint32_t)n;
-    us.seg_first = (uint32_t)c.segments.size();
-    c.sstreams.insert(c.sstreams.end(), STREAM_PAD, (uint8_t)CODE_NULL);
-    us.sstream_off = (uint32_t)c.sstreams.size();
-    if (n == 0) return us;
     auto hap_ptr = [&](int k) { return b->hap_bases + b->hap_off[un.hap_begin + k]; };
     auto hap_len = [&](int k) { return (uint32_t)(b->hap_off[un.hap_begin + k + 1] - b->hap_off[un.hap_begin + k]); };
     std::vector<int> order(n);
@@ -232,6 +224,24 @@ UnitSched plan_unit_sharing(const gphmm_batch *b, const gphmm_unit &un, const in
             if (lx != ly) return lx < ly;
             return x < y;
         });
+    return order;
+}
+
+UnitSched plan_unit_sharing(const gphmm_batch *b, const gphmm_unit &un, const int16_t *lut, bool share, ChunkPlan &c,
+                            int64_t sum_read_len, const std::vector<int> &full_order, int g_first, int g_count) {
+    constexpr uint32_t MIN_DEPTH = 32, SPACING = 32;
+    UnitSched us;
+    memset(&us, 0, sizeof us);
+    const int n = g_count;  // haplotypes of this group: full_order[g_first .. g_first + g_count)
+    us.pass_first = (uint32_t)c.pass_info.size();
+    us.n_passes = (uint32_t)n;
+    us.seg_first = (uint32_t)c.segments.size();
+    c.sstreams.insert(c.sstreams.end(), STREAM_PAD, (uint8_t)CODE_NULL);
+    us.sstream_off = (uint32_t)c.sstreams.size();
+    if (n == 0) return us;
+    auto hap_ptr = [&](int k) { return b->hap_bases + b->hap_off[un.hap_begin + k]; };
+    auto hap_len = [&](int k) { return (uint32_t)(b->hap_off[un.hap_begin + k + 1] - b->hap_off[un.hap_begin + k]); };
+    std::vector<int> order(full_order.begin() + g_first, full_order.begin() + g_first + g_count);
     struct Snap { int pass; uint32_t depth, pos; int slot; uint32_t free_after; };
     std::vector<Snap> snaps;
     int slot_owner[MAX_SNAP_SLOTS];
@@ -305,6 +315,7 @@ UnitSched plan_unit_sharing(const gphmm_batch *b, const gphmm_unit &un, const in
         pi.restore_slot = (int16_t)(snap_of_pass[i] >= 0 ? snaps[snap_of_pass[i]].slot : -1);
         c.pass_info.push_back(pi);
         c.skipped_cells += (int64_t)r[i] * sum_read_len;
+        c.computed_columns += H - r[i];
     }
     // schedule.  Lane l meets stream position q at step q + l, so an END column at e keeps some lane busy with it
     // during steps [e, e+32) and a snapshot position s during [s, s+32).  END windows never overlap each other
@@ -347,6 +358,10 @@ UnitSched plan_unit_sharing(const gphmm_batch *b, const gphmm_unit &un, const in
     return us;
 }
 
+// When a chunk has too few reads to fill the GPU with one warp per read (a single HaplotypeCaller region is ~100 reads),
+// each unit's haplotypes are split into groups and every (read, group) pair becomes a task of its own.
+constexpr int64_t TARGET_TASKS = 148 * 28 * 2;
+
 void plan_chunk(const gphmm_batch *b, int64_t u0, int64_t u1, bool force_fp64, bool share, ChunkPlan &c) {
     c.u0 = u0; c.u1 = u1;
     c.r_lo = INT64_MAX; c.r_hi = 0;
@@ -386,8 +401,12 @@ void plan_chunk(const gphmm_batch *b, int64_t u0, int64_t u1, bool force_fp64, b
     c.n_codes = CODE_FIRST_BASE + 5;
 
     c.streams.clear(); c.hap_len.clear(); c.hap_stream_off.clear(); c.units.clear(); c.tasks.clear();
-    c.sstreams.clear(); c.pass_info.clear(); c.segments.clear(); c.unit_sched.clear(); c.skipped_cells = 0;
+    c.sstreams.clear(); c.pass_info.clear(); c.segments.clear(); c.unit_sched.clear(); c.skipped_cells = 0; c.computed_columns = 0;
     c.n_pairs = 0; c.cells = 0; c.max_stream_len = 0; c.max_hap_len = 0;
+    int64_t n_reads_with_work = 0;
+    for (int64_t u = u0; u < u1; ++u)
+        if (b->units[u].hap_end > b->units[u].hap_begin) n_reads_with_work += b->units[u].read_end - b->units[u].read_begin;
+    const int64_t want_groups = n_reads_with_work > 0 ? (TARGET_TASKS + n_reads_with_work - 1) / n_reads_with_work : 1;
     std::vector<Task> raw;
     std::vector<uint8_t> bucket_of;
     raw.reserve((size_t)(c.r_hi - c.r_lo));
@@ -439,14 +458,20 @@ void plan_chunk(const gphmm_batch *b, int64_t u0, int64_t u1, bool force_fp64, b
         c.max_hap_len = std::max(c.max_hap_len, max_h);
         d.c0_exp = (force_fp64 ? C0_BASE_EXP_F64 : C0_BASE_EXP_F32) - ceil_log2(max_h);
         c.units.push_back(d);
+        // reads of 255+ bases run the striped kernel on the full stream: only shorter reads use the shared streams
+        int64_t fast_read_len = 0;
+        for (uint32_t r = 0; r < nr && nh; ++r) {
+            const uint32_t R = c.read_off[d.read_first + r + 1] - c.read_off[d.read_first + r];
+            if ((R + 1) / 32 + 1 <= 8) fast_read_len += R;
+        }
+        const int n_groups = force_fp64 ? 1 : (int)std::max<int64_t>(1, std::min<int64_t>(want_groups, nh));
+        const uint32_t sched_first = (uint32_t)c.unit_sched.size();
         {
-            // reads of 255+ bases run the striped kernel on the full stream: only shorter reads profit from sharing
-            int64_t fast_read_len = 0;
-            for (uint32_t r = 0; r < nr && nh; ++r) {
-                const uint32_t R = c.read_off[d.read_first + r + 1] - c.read_off[d.read_first + r];
-                if ((R + 1) / 32 + 1 <= 8) fast_read_len += R;
+            const std::vector<int> order = sorted_hap_order(b, un, share && !force_fp64);
+            for (int gi = 0; gi < n_groups; ++gi) {
+                const int g0 = (int)((int64_t)nh * gi / n_groups), g1 = (int)((int64_t)nh * (gi + 1) / n_groups);
+                c.unit_sched.push_back(plan_unit_sharing(b, un, lut, share && !force_fp64, c, fast_read_len, order, g0, g1 - g0));
             }
-            c.unit_sched.push_back(plan_unit_sharing(b, un, lut, share && !force_fp64, c, fast_read_len));
         }
         if (nh == 0) continue;
         for (uint32_t r = 0; r < nr; ++r) {
@@ -454,13 +479,18 @@ void plan_chunk(const gphmm_batch *b, int64_t u0, int64_t u1, bool force_fp64, b
             const uint32_t R = c.read_off[rl + 1] - c.read_off[rl];
             Task t;
             t.read = rl; t.stream_off = stream_off; t.stream_len = stream_len;
-            t.out_base = d.out_base + r * nh; t.c0_exp = d.c0_exp; t.n_haps = nh; t.hap_first = d.hap_first; t.unit = (uint32_t)c.units.size() - 1;
+            t.out_base = d.out_base + r * nh; t.c0_exp = d.c0_exp; t.n_haps = nh; t.hap_first = d.hap_first; t.unit = sched_first;
             // fast kernels need two spare rows below the read (accumulator row + row-0 carrier): R + 2 <= 32 K
             const uint32_t k = (R + 1) / 32 + 1;
             const uint8_t bucket = force_fp64 ? 0 : (k <= 8 ? (uint8_t)(k - 1) : (uint8_t)8);
-            raw.push_back(t);
-            bucket_of.push_back(bucket);
-            ++bucket_count[bucket];
+            // one task per haplotype group for the fast kernels; the striped / fp64 kernels sweep the full stream once
+            const int n_t = bucket < 8 && !force_fp64 ? n_groups : 1;
+            for (int gi = 0; gi < n_t; ++gi) {
+                t.unit = sched_first + (uint32_t)gi;
+                raw.push_back(t);
+                bucket_of.push_back(bucket);
+                ++bucket_count[bucket];
+            }
             c.cells += (int64_t)R * sum_h;
         }
         c.n_pairs += nr * nh;
@@ -1048,7 +1078,7 @@ struct PlanPool {
     PlanPool(const gphmm_batch *b_, const std::vector<std::pair<int64_t, int64_t>> &c, bool f64_, bool share_, int n_threads, Stats &st)
         : b(b_), chunks(c), f64(f64_), share(share_), stats(st), ready(c.size()), done(c.size(), 0), err_code(c.size(), 0),
           err_text(c.size()) {
-        n_threads = std::max(1, std::min<int>(n_threads, (int)c.size()));
+        n_threads = c.size() <= 1 ? 0 : std::max(1, std::min<int>(n_threads, (int)c.size()));  // one chunk: plan inline, no threads
         lookahead = (size_t)n_threads + N_SLOTS;
         for (int t = 0; t < n_threads; ++t) threads.emplace_back([this] { work(); });
     }
@@ -1094,6 +1124,14 @@ struct PlanPool {
         }
     }
     std::unique_ptr<ChunkPlan> take(size_t ci) {
+        if (threads.empty()) {  // synchronous planning (single-chunk batches: the per-region JNI call)
+            std::unique_ptr<ChunkPlan> p(new ChunkPlan());
+            const double t0 = now_ms();
+            plan_chunk(b, chunks[ci].first, chunks[ci].second, f64, share, *p);
+            std::lock_guard<std::mutex> lk(stats.mu);
+            stats.s.host_stage_ms += now_ms() - t0;
+            return p;
+        }
         std::unique_lock<std::mutex> lk(mu);
         cv.wait(lk, [&] { return done[ci] != 0; });
         consumed = std::max(consumed, ci + 1);
@@ -1180,36 +1218,83 @@ int run_batch(gphmm *h, const gphmm_batch *b, double *out) {
     return GPHMM_OK;
 }
 
+// The asynchronous cross-region batching queue: everything that is queued when the worker wakes up is merged into ONE
+// batch, so that many small (region, sample) units fill the GPU together instead of running one launch set each.
 void worker_main(gphmm *h) {
+    constexpr size_t MAX_COALESCE = 4096;
     for (;;) {
-        std::shared_ptr<gphmm::Job> job;
+        std::vector<std::shared_ptr<gphmm::Job>> jobs;
         {
             std::unique_lock<std::mutex> lk(h->q_mu);
             h->q_cv.wait(lk, [&] { return h->stop || !h->queue.empty(); });
             if (h->queue.empty()) return;
-            job = h->queue.front();
+            for (size_t k = 0; k < h->queue.size() && k < MAX_COALESCE; ++k) jobs.push_back(h->queue[k]);
         }
         gphmm_batch b;
         memset(&b, 0, sizeof b);
-        b.read_bases = job->read_bases.data(); b.base_q = job->base_q.data(); b.ins_q = job->ins_q.data();
-        b.del_q = job->del_q.data(); b.gcp = job->gcp.data(); b.read_off = job->read_off.data();
-        b.n_reads = (int64_t)job->read_off.size() - 1;
-        b.hap_bases = job->hap_bases.data(); b.hap_off = job->hap_off.data(); b.n_haps = (int64_t)job->hap_off.size() - 1;
-        b.units = job->units.data(); b.n_units = (int64_t)job->units.size();
+        std::vector<uint8_t> rb, bq, iq, dq, gq, hb;
+        std::vector<int64_t> ro(1, 0), ho(1, 0);
+        std::vector<gphmm_unit> units;
+        std::vector<double> merged_out;
+        std::vector<int64_t> job_out_base(jobs.size(), 0), job_out_len(jobs.size(), 0);
+        double *out = nullptr;
+        if (jobs.size() == 1) {
+            gphmm::Job &j = *jobs[0];
+            b.read_bases = j.read_bases.data(); b.base_q = j.base_q.data(); b.ins_q = j.ins_q.data();
+            b.del_q = j.del_q.data(); b.gcp = j.gcp.data(); b.read_off = j.read_off.data();
+            b.n_reads = (int64_t)j.read_off.size() - 1;
+            b.hap_bases = j.hap_bases.data(); b.hap_off = j.hap_off.data(); b.n_haps = (int64_t)j.hap_off.size() - 1;
+            b.units = j.units.data(); b.n_units = (int64_t)j.units.size();
+            out = j.out;
+        } else {
+            int64_t out_cursor = 0;
+            for (size_t q = 0; q < jobs.size(); ++q) {
+                gphmm::Job &j = *jobs[q];
+                const int64_t r0 = (int64_t)ro.size() - 1, h0 = (int64_t)ho.size() - 1, base0 = ro.back(), hbase0 = ho.back();
+                rb.insert(rb.end(), j.read_bases.begin(), j.read_bases.end());
+                bq.insert(bq.end(), j.base_q.begin(), j.base_q.end());
+                iq.insert(iq.end(), j.ins_q.begin(), j.ins_q.end());
+                dq.insert(dq.end(), j.del_q.begin(), j.del_q.end());
+                gq.insert(gq.end(), j.gcp.begin(), j.gcp.end());
+                hb.insert(hb.end(), j.hap_bases.begin(), j.hap_bases.end());
+                for (size_t k = 1; k < j.read_off.size(); ++k) ro.push_back(base0 + j.read_off[k]);
+                for (size_t k = 1; k < j.hap_off.size(); ++k) ho.push_back(hbase0 + j.hap_off[k]);
+                int64_t len = 0;
+                for (const gphmm_unit &u : j.units) len = std::max(len, u.out_off + (u.read_end - u.read_begin) * (u.hap_end - u.hap_begin));
+                job_out_base[q] = out_cursor; job_out_len[q] = len;
+                for (gphmm_unit u : j.units) {
+                    u.read_begin += r0; u.read_end += r0; u.hap_begin += h0; u.hap_end += h0; u.out_off += out_cursor;
+                    units.push_back(u);
+                }
+                out_cursor += len;
+            }
+            merged_out.assign((size_t)out_cursor, 0.0);
+            b.read_bases = rb.data(); b.base_q = bq.data(); b.ins_q = iq.data(); b.del_q = dq.data(); b.gcp = gq.data();
+            b.read_off = ro.data(); b.n_reads = (int64_t)ro.size() - 1;
+            b.hap_bases = hb.data(); b.hap_off = ho.data(); b.n_haps = (int64_t)ho.size() - 1;
+            b.units = units.data(); b.n_units = (int64_t)units.size();
+            out = merged_out.data();
+        }
         int rc = GPHMM_OK;
         std::string err;
         try {
-            rc = run_batch(h, &b, job->out);
+            rc = run_batch(h, &b, out);
         } catch (const Error &e) {
             rc = e.code; err = e.what();
         } catch (const std::exception &e) {
             rc = GPHMM_ERR_CUDA; err = e.what();
         }
+        if (jobs.size() > 1 && rc == GPHMM_OK)
+            for (size_t q = 0; q < jobs.size(); ++q)
+                if (job_out_len[q]) memcpy(jobs[q]->out, merged_out.data() + job_out_base[q], (size_t)job_out_len[q] * sizeof(double));
+        // an error in a merged batch is reported on every ticket of the batch
         {
             std::lock_guard<std::mutex> lk(h->q_mu);
-            job->rc = rc; job->err = err;
-            h->queue.pop_front();
-            h->finished.push_back(job);
+            for (auto &j : jobs) {
+                j->rc = rc; j->err = err;
+                h->queue.pop_front();
+                h->finished.push_back(j);
+            }
         }
         h->done_cv.notify_all();
     }
@@ -1521,8 +1606,7 @@ int gphmm_plan_stats(const gphmm_batch *b, int prefix_sharing, int64_t out[10]) 
                 for (uint32_t k = 0; k < c.units[u].n_haps; ++k) cols += c.hap_len[c.units[u].hap_first + k];
                 out[7] += cols;
             }
-            // sstreams holds STREAM_PAD NULLs per unit, then the computed columns and one END per pass
-            out[6] -= (int64_t)c.sstreams.size() - (int64_t)c.units.size() * STREAM_PAD - (int64_t)c.pass_info.size();
+            out[6] -= c.computed_columns;
             out[8] += 1;
             out[9] += (int64_t)c.tasks.size();
         }

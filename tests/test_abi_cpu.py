@@ -121,3 +121,24 @@ def test_plugin_mirror_without_gpu():
     imp = pairhmm.StandardPairHMMInputScoreImputator(10)
     ins, dele, gcp = imp.impute(pairhmm.Read(b"ACGT", [30, 30, 30, 30]))
     assert list(ins) == [45] * 4 and list(dele) == [45] * 4 and list(gcp) == [10] * 4
+
+
+def test_planner_host_only():
+    # gphmm_plan_stats runs the real chunk planner without a GPU: schedule totals are consistent
+    b = synth.config2(40)
+    plain = native.plan_stats(b, False)
+    shared = native.plan_stats(b, True)
+    nh = int(np.sum(b.units["hap_end"] - b.units["hap_begin"]))
+    assert plain["units"] == shared["units"] == 40 and plain["total_columns"] == int(b.hap_off[-1])
+    assert plain["skipped_columns"] == 0 and plain["snapshots"] == 0
+    # a small chunk is split into haplotype groups: one pass and one schedule per haplotype, no sharing lost or gained
+    assert plain["passes"] == nh
+    big = synth.config2(400)
+    sp, ss = native.plan_stats(big, False), native.plan_stats(big, True)
+    assert sp["tasks"] == big.n_reads and ss["tasks"] == big.n_reads       # enough reads: one task per read
+    steps = lambda st: st["free_steps"] + st["checked_steps"]
+    # every computed column is one step of lane 0; each unit's sweep drains 31 more steps
+    assert steps(sp) == sp["total_columns"] + sp["passes"] + 31 * sp["units"]
+    assert 0.15 < ss["skipped_columns"] / ss["total_columns"] < 0.6
+    assert steps(ss) < 0.9 * steps(sp)
+    assert ss["checked_steps"] <= 32 * (ss["passes"] + ss["snapshots"]) + ss["units"]

@@ -343,17 +343,36 @@ def _nested_haplotype_unit(seed):
     return Batch.single_unit(reads, haps)
 
 
+def _replicate(b, copies):
+    """the same unit `copies` times (same read / haplotype ranges, separate output slots): enough reads per chunk for
+    the planner to keep whole haplotype sets together (small chunks are split into haplotype groups instead)"""
+    n = b.n_out
+    u = np.zeros(copies, dtype=native.UNIT_DTYPE)
+    for name in ("read_begin", "read_end", "hap_begin", "hap_end"):
+        u[name] = b.units[name][0]
+    u["out_off"] = np.arange(copies) * n
+    return Batch(b.read_bases, b.base_q, b.ins_q, b.del_q, b.gcp, b.read_off, b.hap_bases, b.hap_off, u), n
+
+
 def test_prefix_sharing_is_bit_identical_and_correct():
     # haplotype-prefix caching (PairHMMUnitTest.java:607-677 testHaplotypeIndexing pins caching == full recompute)
     with GpuPhmm() as shared, GpuPhmm(no_prefix_sharing=True) as plain:
-        for seed in range(4):
-            b = _nested_haplotype_unit(seed)
+        for seed in range(3):
+            one = _nested_haplotype_unit(seed)
+            b, n = _replicate(one, 600)
             shared.reset_stats()
             a = shared.compute(b)
             c = plain.compute(b)
             assert np.array_equal(a, c)
             assert shared.stats()["skipped_cells"] > 0.15 * shared.stats()["cells"]
-            _check(a, oracle_batch(b), TOL)
+            assert native.plan_stats(b, True)["snapshots"] > 0
+            want = oracle_batch(one)
+            for k in (0, 1, 311, 599):
+                _check(a[k * n:(k + 1) * n], want, TOL)
+            assert np.array_equal(a.reshape(600, n), np.tile(a[:n], (600, 1)))
+            # a single small unit is split into haplotype groups instead (fills the GPU): same numbers to float noise
+            solo = shared.compute(one)
+            _check(solo, want, TOL)
         b = synth.config2(60)
         a, c = shared.compute(b), plain.compute(b)
         assert np.array_equal(a, c)
