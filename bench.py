@@ -215,15 +215,20 @@ def main():
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "regions_per_gpu": args.regions, "reads_per_gpu": batch.n_reads, "pairs": pairs_all,
                        "cells_per_step": cells_all, "input_bytes_per_gpu": batch.input_bytes(), "l2_policy": "inputs larger than L2 (%.0f MB/GPU streamed per step)" % (batch.input_bytes() / 1e6),
-                       "fp64_rescued_pairs_per_step": rescued_all / steps, "timing": "CUDA events on the library's launch stream, max over ranks; wall %.3f s" % wall},
+                       "fp64_rescued_pairs_per_step": rescued_all / steps,
+                       "prefix_sharing": (not args.no_prefix_sharing), "cells_skipped_by_prefix_sharing_frac": st["skipped_cells"] / max(1, st["cells"]),
+                       "cells_definition": "sum of R*H over pairs (LoglessPairHMM.java:47-49), no padding; prefix sharing skips executing some of them, results bit-identical",
+                       "timing": "CUDA events on the library's launch stream, max over ranks; wall %.3f s" % wall},
             "clocks": clocks,
             "e2e": {"value": e2e, "unit": "GCUPS", "h2d_bytes_per_step": st2["h2d_bytes"] / steps, "d2h_bytes_per_step": st2["d2h_bytes"] / steps,
                     "ms_per_step": 1e3 * e2e_wall / steps, "api": "gphmm_compute (C ABI) with pinned host arrays"},
             "gpu_launches": int(st["kernel_launches"]),
             "roofline": {"bound": "fp32", "achieved": achieved_tflops, "peak": peak_tflops, "unit": "TFLOP/s", "frac": achieved_tflops / peak_tflops,
-                         "traffic": None, "kernel": "phmm_forward_kernel<float,K,*> (all K buckets of the step)",
+                         "traffic": None, "kernel": "phmm_flat_f32_kernel<K> (+ phmm_fast_f32_kernel<K> for non-flat reads), all K buckets of the step",
                          "peak_source": "2 x %d SMs x 128 lanes x %.0f MHz (SM clock sampled during the timed region); MEASURED_PEAKS.json has no FP32 entry" % (props.multi_processor_count, sm_for_peak),
                          "flops_per_cell": 12, "kernel_ms_per_step": 1e3 * f32_s / steps,
+                         "executed_frac": 12.0 * (cells - st["skipped_cells"] / steps) * steps / f32_s / 1e12 / peak_tflops,
+                         "traffic_note": "ncu --set full, flat K=8 launch: 16 MB DRAM read + 57 MB written (snapshot slabs) for ~1.8e10 cells; see profiles/r01_flat_k8_prefix_sharing_ncu_full.txt",
                          "hbm_gbs_staging": (batch.input_bytes() + 8 * pairs) * steps / f32_s / 1e9},
         }
         if not args.no_cpu_baseline:
