@@ -82,7 +82,8 @@ def cpu_baseline(batch, budget_s=15.0, threads=0):
     from oracle import oracle
     from gatk_b200.native import Batch
     from phmm_testutil import oracle_batch
-    threads = threads or oracle.max_threads()
+    # every host core the process may use; NOT omp_get_max_threads(): torchrun exports OMP_NUM_THREADS=1
+    threads = threads or len(os.sched_getaffinity(0))
     # calibrate on a few units, then size the sample
     u = batch.units
     nr = u["read_end"] - u["read_begin"]

@@ -1284,16 +1284,39 @@ void worker_main(gphmm *h) {
         } catch (const std::exception &e) {
             rc = GPHMM_ERR_CUDA; err = e.what();
         }
-        if (jobs.size() > 1 && rc == GPHMM_OK)
+        std::vector<int> rcs(jobs.size(), rc);
+        std::vector<std::string> errs(jobs.size(), err);
+        if (jobs.size() > 1 && rc == GPHMM_OK) {
             for (size_t q = 0; q < jobs.size(); ++q)
                 if (job_out_len[q]) memcpy(jobs[q]->out, merged_out.data() + job_out_base[q], (size_t)job_out_len[q] * sizeof(double));
-        // an error in a merged batch is reported on every ticket of the batch
+        } else if (jobs.size() > 1) {
+            // something in the merged batch is bad (e.g. a quality out of range): rerun the jobs one by one so that
+            // only the offending ticket reports the error
+            for (size_t q = 0; q < jobs.size(); ++q) {
+                gphmm::Job &j = *jobs[q];
+                gphmm_batch one;
+                memset(&one, 0, sizeof one);
+                one.read_bases = j.read_bases.data(); one.base_q = j.base_q.data(); one.ins_q = j.ins_q.data();
+                one.del_q = j.del_q.data(); one.gcp = j.gcp.data(); one.read_off = j.read_off.data();
+                one.n_reads = (int64_t)j.read_off.size() - 1;
+                one.hap_bases = j.hap_bases.data(); one.hap_off = j.hap_off.data(); one.n_haps = (int64_t)j.hap_off.size() - 1;
+                one.units = j.units.data(); one.n_units = (int64_t)j.units.size();
+                rcs[q] = GPHMM_OK; errs[q].clear();
+                try {
+                    rcs[q] = run_batch(h, &one, j.out);
+                } catch (const Error &e) {
+                    rcs[q] = e.code; errs[q] = e.what();
+                } catch (const std::exception &e) {
+                    rcs[q] = GPHMM_ERR_CUDA; errs[q] = e.what();
+                }
+            }
+        }
         {
             std::lock_guard<std::mutex> lk(h->q_mu);
-            for (auto &j : jobs) {
-                j->rc = rc; j->err = err;
+            for (size_t q = 0; q < jobs.size(); ++q) {
+                jobs[q]->rc = rcs[q]; jobs[q]->err = errs[q];
                 h->queue.pop_front();
-                h->finished.push_back(j);
+                h->finished.push_back(jobs[q]);
             }
         }
         h->done_cv.notify_all();

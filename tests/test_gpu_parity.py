@@ -380,3 +380,32 @@ def test_prefix_sharing_is_bit_identical_and_correct():
         for seed in range(3):
             b = synth.random_batch(500 + seed, n_units=6, max_haps=12, hap_len=(60, 400), wild_quals=bool(seed % 2))
             assert np.array_equal(shared.compute(b), plain.compute(b))
+
+
+def test_async_queue_coalesces_and_isolates_errors(hmm):
+    # many small regions queued at once are merged into one GPU batch; a bad region fails only its own ticket
+    good = [synth.config1(seed=synth.SEED + k) for k in range(12)]
+    bad = synth.config1(seed=99)
+    bad = Batch(bad.read_bases, bad.base_q, bad.ins_q.copy(), bad.del_q, bad.gcp, bad.read_off, bad.hap_bases, bad.hap_off, bad.units)
+    bad.ins_q[3] = 222
+    order = good[:5] + [bad] + good[5:]
+    tickets = [hmm.submit(b) for b in order]
+    results = []
+    for t, b in zip(tickets, order):
+        if b is bad:
+            with pytest.raises(native.GpuPhmmError) as e:
+                hmm.wait(t)
+            assert e.value.code == native.ERR_BAD_QUAL
+        else:
+            results.append((hmm.wait(t), b))
+    for got, b in results:
+        _check(got, oracle_batch(b), TOL)
+
+
+def test_two_devices_one_process():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    b = synth.config2(200)
+    with GpuPhmm(devices=[0]) as one, GpuPhmm(devices=[0, 1], chunk_cells=2_000_000_000) as two:
+        assert np.array_equal(one.compute(b), two.compute(b))
