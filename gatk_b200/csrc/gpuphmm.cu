@@ -13,6 +13,7 @@
 #include <cmath>
 #include <condition_variable>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <deque>
 #include <map>
@@ -541,6 +542,23 @@ struct KernelInfo {
     size_t smem = 0;
 };
 
+// Forward kernels are persistent and several of them (the K buckets of a chunk, the next chunk) are in flight at once;
+// the hardware would pack them until no SM has room for the small kernels that CLOSE a chunk (epilogue, rescue), so
+// chunks would only complete in groups and the host pipeline would stall.  Every forward CTA therefore asks for
+// 1/(occ-2) of the SM's shared memory: any mix of forward kernels then leaves >= 2 CTAs' worth of registers, warps
+// and CTA slots free on every SM.
+void reserve_headroom(KernelInfo &ki, const void *fn) {
+    const int occ = ki.ctas_per_sm;
+    if (occ < 4) return;
+    const size_t want = (size_t)(227 * 1024) / (size_t)(occ - 2) - 1024;  // 1 KB per CTA is reserved by the system
+    if (want > ki.smem) {
+        ki.smem = want & ~(size_t)15;
+        if (ki.smem > 48 * 1024) CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ki.smem));
+    }
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ki.ctas_per_sm, fn, 32, ki.smem));
+    if (ki.ctas_per_sm < 1) ki.ctas_per_sm = 1;
+}
+
 template <typename T, int K, bool S> KernelInfo kernel_info(int n_codes) {
     KernelInfo ki;
     auto fn = phmm_forward_kernel<T, K, S>;
@@ -549,6 +567,7 @@ template <typename T, int K, bool S> KernelInfo kernel_info(int n_codes) {
     if (ki.smem > 48 * 1024) CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ki.smem));
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ki.ctas_per_sm, fn, 32, ki.smem));
     if (ki.ctas_per_sm < 1) throw Error(GPHMM_ERR_ALPHABET, "prior table does not fit in shared memory");
+    reserve_headroom(ki, (const void *)fn);
     return ki;
 }
 
@@ -560,6 +579,7 @@ template <int K> KernelInfo fast_kernel_info(int n_codes) {
     if (ki.smem > 48 * 1024) CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ki.smem));
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ki.ctas_per_sm, fn, 32, ki.smem));
     if (ki.ctas_per_sm < 1) throw Error(GPHMM_ERR_ALPHABET, "prior table does not fit in shared memory");
+    reserve_headroom(ki, (const void *)fn);
     return ki;
 }
 
@@ -584,6 +604,7 @@ template <int K> KernelInfo flat_kernel_info(int n_codes) {
     if (ki.smem > 48 * 1024) CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ki.smem));
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ki.ctas_per_sm, fn, 32, ki.smem));
     if (ki.ctas_per_sm < 1) throw Error(GPHMM_ERR_ALPHABET, "prior table does not fit in shared memory");
+    reserve_headroom(ki, (const void *)fn);
     return ki;
 }
 
@@ -609,6 +630,11 @@ struct Stats {
 
 constexpr int FLAT_KEY = 16;  // Device::info key of the flat-quality kernel of bucket k is FLAT_KEY + k
 
+// One CTA per resident slot (the occupancy already includes the headroom of reserve_headroom()).
+inline uint32_t persistent_grid(uint32_t n_tasks, int n_sms, int ctas_per_sm) {
+    return std::min<uint32_t>(n_tasks, (uint32_t)(n_sms * ctas_per_sm));
+}
+
 struct Device {
     int ordinal = 0;
     int n_sms = 0;
@@ -622,6 +648,7 @@ struct Device {
         return it->second;
     }
     cudaStream_t streams[N_SLOTS] = {nullptr};
+    cudaStream_t tails[N_SLOTS] = {nullptr};  // high priority: the small kernels + download that close a chunk
     cudaStream_t aux[N_SLOTS][N_AUX] = {{nullptr}};  // side streams: the kernels of a chunk overlap their tails
     DeviceChunk slots[N_SLOTS];
     DevBuf m2m;
@@ -638,12 +665,15 @@ struct Device {
         CK(cudaMemcpyToSymbol(c_eps, t.eps.data(), 256 * sizeof(double)));
         m2m.reserve(t.m2m.size() * sizeof(double));
         CK(cudaMemcpy(m2m.p, t.m2m.data(), t.m2m.size() * sizeof(double), cudaMemcpyHostToDevice));
+        int prio_lo = 0, prio_hi = 0;  // numerically lower = higher priority
+        CK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
         CK(cudaEventCreate(&ev_step0));
         CK(cudaEventCreate(&ev_step1));
         for (int i = 0; i < N_SLOTS; ++i) CK(cudaEventCreateWithFlags(&ev_slot_done[i], cudaEventDisableTiming));
         for (int i = 0; i < N_SLOTS; ++i) {
-            CK(cudaStreamCreateWithFlags(&streams[i], cudaStreamNonBlocking));
-            for (int k = 0; k < N_AUX; ++k) CK(cudaStreamCreateWithFlags(&aux[i][k], cudaStreamNonBlocking));
+            CK(cudaStreamCreateWithPriority(&streams[i], cudaStreamNonBlocking, prio_lo));
+            CK(cudaStreamCreateWithPriority(&tails[i], cudaStreamNonBlocking, prio_hi));
+            for (int k = 0; k < N_AUX; ++k) CK(cudaStreamCreateWithPriority(&aux[i][k], cudaStreamNonBlocking, prio_lo));
             CK(cudaEventCreate(&slots[i].ev_start));
             CK(cudaEventCreate(&slots[i].ev_f32));
             CK(cudaEventCreate(&slots[i].ev_f64));
@@ -655,7 +685,8 @@ struct Device {
         for (int i = 0; i < N_SLOTS; ++i) {
             slots[i].release();
             if (streams[i]) cudaStreamDestroy(streams[i]);
-            streams[i] = nullptr;
+            if (tails[i]) cudaStreamDestroy(tails[i]);
+            streams[i] = nullptr; tails[i] = nullptr;
             for (int k = 0; k < N_AUX; ++k) { if (aux[i][k]) cudaStreamDestroy(aux[i][k]); aux[i][k] = nullptr; }
         }
         m2m.release();
@@ -755,7 +786,7 @@ void upload_chunk(Device &dev, DeviceChunk &dc, const gphmm_batch *b, const Chun
 }
 
 // Queue every kernel of the chunk on `st` (no host sync).  Returns the number of launches.
-int launch_chunk(Device &dev, DeviceChunk &dc, const ChunkPlan &c, cudaStream_t st, cudaStream_t *aux, const RunOptions &opt, bool download) {
+int launch_chunk(Device &dev, DeviceChunk &dc, const ChunkPlan &c, cudaStream_t st, cudaStream_t tail, cudaStream_t *aux, const RunOptions &opt, bool download) {
     int launches = 0;
     uint8_t *meta = (uint8_t *)dc.meta.p, *work = (uint8_t *)dc.work.p;
     uint32_t *counters = (uint32_t *)(work + dc.off_counters);
@@ -855,16 +886,16 @@ int launch_chunk(Device &dev, DeviceChunk &dc, const ChunkPlan &c, cudaStream_t 
             for (int k = 0; k < 8; ++k) {
                 const uint32_t n = c.bucket_begin[k + 1] - c.bucket_begin[k];
                 if (!n) continue;
-                need += (size_t)std::min<uint32_t>(n, (uint32_t)(dev.n_sms * dev.info(k, c.n_codes).ctas_per_sm)) * SLAB_PER_CTA;
+                need += (size_t)persistent_grid(n, dev.n_sms, dev.info(k, c.n_codes).ctas_per_sm) * SLAB_PER_CTA;
                 for (int cl = 0; cl < c.n_classes; ++cl)
-                    need += (size_t)std::min<uint32_t>(n, (uint32_t)(dev.n_sms * dev.info(FLAT_KEY + k, c.n_codes).ctas_per_sm)) * SLAB_PER_CTA;
+                    need += (size_t)persistent_grid(n, dev.n_sms, dev.info(FLAT_KEY + k, c.n_codes).ctas_per_sm) * SLAB_PER_CTA;
             }
             dc.snap.reserve(std::max<size_t>(need, 16));
         }
         size_t slab_cursor = 0;
         bool first_launch = true;
         auto launch_on = [&](const KernelInfo &ki, uint32_t n, int aux_idx, void **args) {
-            const uint32_t grid = std::min<uint32_t>(n, (uint32_t)(dev.n_sms * ki.ctas_per_sm));
+            const uint32_t grid = persistent_grid(n, dev.n_sms, ki.ctas_per_sm);
             cudaStream_t ks = st;
             if (!first_launch) {
                 ks = aux[aux_idx];
@@ -906,7 +937,7 @@ int launch_chunk(Device &dev, DeviceChunk &dc, const ChunkPlan &c, cudaStream_t 
                     fc.qi = qi; fc.qd = qd; fc.qc = qc;
                     ka.counter = counters + 16 + 8 * cl + k;
                     ka.snap = (float *)((uint8_t *)dc.snap.p + slab_cursor);
-                    slab_cursor += (size_t)std::min<uint32_t>(n, (uint32_t)(dev.n_sms * dev.info(FLAT_KEY + k, c.n_codes).ctas_per_sm)) * SLAB_PER_CTA;
+                    slab_cursor += (size_t)persistent_grid(n, dev.n_sms, dev.info(FLAT_KEY + k, c.n_codes).ctas_per_sm) * SLAB_PER_CTA;
                     void *args[] = {&ka, &fc};
                     launch_on(dev.info(FLAT_KEY + k, c.n_codes), n, N_FP32_BUCKETS + 8 * cl + k, args);
                 }
@@ -914,14 +945,15 @@ int launch_chunk(Device &dev, DeviceChunk &dc, const ChunkPlan &c, cudaStream_t 
             ka.counter = counters + k;
             if (k < 8) {
                 ka.snap = (float *)((uint8_t *)dc.snap.p + slab_cursor);
-                slab_cursor += (size_t)std::min<uint32_t>(n, (uint32_t)(dev.n_sms * dev.info(k, c.n_codes).ctas_per_sm)) * SLAB_PER_CTA;
+                slab_cursor += (size_t)persistent_grid(n, dev.n_sms, dev.info(k, c.n_codes).ctas_per_sm) * SLAB_PER_CTA;
             }
             void *args[] = {&ka};
             launch_on(dev.info(k, c.n_codes), n, k, args);
         }
         CK(cudaEventRecord(dc.ev_f32, st));
+        CK(cudaStreamWaitEvent(tail, dc.ev_f32, 0));  // the closing kernels run at high priority in the reserved headroom
         if (ea.n_units) {
-            phmm_epilogue_f32<<<std::min<uint32_t>(ea.n_units, 4096), 128, 0, st>>>(ea);
+            phmm_epilogue_f32<<<std::min<uint32_t>(ea.n_units, 4096), 128, 0, tail>>>(ea);
             CK(cudaGetLastError());
             ++launches;
         }
@@ -937,14 +969,14 @@ int launch_chunk(Device &dev, DeviceChunk &dc, const ChunkPlan &c, cudaStream_t 
             ka.bnd = dc.bnd.p;
             ka.bnd_stride = c.max_hap_len + 1;
             void *args[] = {&ka};
-            CK(cudaLaunchKernel(ki.fn, dim3(grid), dim3(32), args, ki.smem, st));
+            CK(cudaLaunchKernel(ki.fn, dim3(grid), dim3(32), args, ki.smem, tail));
             ++launches;
-            phmm_epilogue_rescue<<<std::min<uint32_t>((c.n_pairs + 127) / 128, 1024), 128, 0, st>>>(
+            phmm_epilogue_rescue<<<std::min<uint32_t>((c.n_pairs + 127) / 128, 1024), 128, 0, tail>>>(
                 (const Task *)(work + dc.off_rtasks), counters + 10, ea.rescue_capacity, (const double *)(work + dc.off_rsums), ea.out);
             CK(cudaGetLastError());
             ++launches;
         }
-        CK(cudaEventRecord(dc.ev_f64, st));
+        CK(cudaEventRecord(dc.ev_f64, tail));
     } else {
         CK(cudaEventRecord(dc.ev_f32, st));
         if (n_tasks_total) {
@@ -961,18 +993,21 @@ int launch_chunk(Device &dev, DeviceChunk &dc, const ChunkPlan &c, cudaStream_t 
             CK(cudaLaunchKernel(ki.fn, dim3(grid), dim3(32), args, ki.smem, st));
             ++launches;
         }
+        if (!dc.ev_fork) CK(cudaEventCreateWithFlags(&dc.ev_fork, cudaEventDisableTiming));
+        CK(cudaEventRecord(dc.ev_fork, st));
+        CK(cudaStreamWaitEvent(tail, dc.ev_fork, 0));
         if (ea.n_units) {
-            phmm_epilogue_f64_units<<<std::min<uint32_t>(ea.n_units, 4096), 128, 0, st>>>(ea);
+            phmm_epilogue_f64_units<<<std::min<uint32_t>(ea.n_units, 4096), 128, 0, tail>>>(ea);
             CK(cudaGetLastError());
             ++launches;
         }
-        CK(cudaEventRecord(dc.ev_f64, st));
+        CK(cudaEventRecord(dc.ev_f64, tail));
     }
     if (download) {
         const size_t bytes = (dc.off_err + 16) - dc.off_out;
-        CK(cudaMemcpyAsync(dc.h_out.p, work + dc.off_out, bytes, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(dc.h_out.p, work + dc.off_out, bytes, cudaMemcpyDeviceToHost, tail));
     }
-    CK(cudaEventRecord(dc.ev_done, st));
+    CK(cudaEventRecord(dc.ev_done, tail));
     return launches;
 }
 
@@ -1152,18 +1187,27 @@ void device_loop(gphmm *h, Device &dev, const gphmm_batch *b, const std::vector<
         opt.tristate_off = h->cfg.tristate_off != 0;
         std::unique_ptr<ChunkPlan> plans[N_SLOTS];
         bool inflight[N_SLOTS] = {false};
+        const bool trace = getenv("GPHMM_TRACE") != nullptr;  // per-chunk host timeline on stderr
+        const double t_start = now_ms();
         int slot = 0;
         int launches = 0;
         for (;;) {
             const size_t ci = cursor.fetch_add(1);
             if (ci >= chunks.size()) break;
+            const double t_f = now_ms();
             if (inflight[slot]) {
                 finish_chunk(dev.slots[slot], b, *plans[slot], out, h->stats, true);
                 inflight[slot] = false;
             }
+            const double t_a = now_ms();
             plans[slot] = pool.take(ci);
+            const double t_b = now_ms();
             upload_chunk(dev, dev.slots[slot], b, *plans[slot], dev.streams[slot], opt.force_fp64, h->stats);
-            launches += launch_chunk(dev, dev.slots[slot], *plans[slot], dev.streams[slot], dev.aux[slot], opt, true);
+            const double t_c = now_ms();
+            launches += launch_chunk(dev, dev.slots[slot], *plans[slot], dev.streams[slot], dev.tails[slot], dev.aux[slot], opt, true);
+            if (trace)
+                fprintf(stderr, "[gpuphmm] chunk %zu dev %d slot %d: t=%.2f ms  wait-finish %.2f  wait-plan %.2f  upload %.2f  launch %.2f  (cells %.3g)\n",
+                        ci, dev.ordinal, slot, t_a - t_start, t_a - t_f, t_b - t_a, t_c - t_b, now_ms() - t_c, (double)plans[slot]->cells);
             inflight[slot] = true;
             slot = (slot + 1) % N_SLOTS;
         }
@@ -1174,6 +1218,7 @@ void device_loop(gphmm *h, Device &dev, const gphmm_batch *b, const std::vector<
             }
             slot = (slot + 1) % N_SLOTS;
         }
+        if (trace) fprintf(stderr, "[gpuphmm] dev %d drained at t=%.2f ms\n", dev.ordinal, now_ms() - t_start);
         std::lock_guard<std::mutex> lk(h->stats.mu);
         h->stats.s.kernel_launches += launches;
     } catch (const Error &e) {
@@ -1544,7 +1589,7 @@ int gphmm_run_prepared(gphmm_t *h, gphmm_prepared_t *p, double *out) {
             }
             // consecutive chunks go to different streams so that the tail of one overlaps the head of the next
             const int sl = n_on_dev[part->device_index]++ % N_SLOTS;
-            launches += launch_chunk(dev, part->dc, part->plan, dev.streams[sl], dev.aux[sl], opt, out != nullptr);
+            launches += launch_chunk(dev, part->dc, part->plan, dev.streams[sl], dev.tails[sl], dev.aux[sl], opt, out != nullptr);
         }
         for (size_t d = 0; d < h->devices.size(); ++d)
             if (used[d]) {
@@ -1554,6 +1599,8 @@ int gphmm_run_prepared(gphmm_t *h, gphmm_prepared_t *p, double *out) {
                     CK(cudaEventRecord(dev.ev_slot_done[sl], dev.streams[sl]));
                     CK(cudaStreamWaitEvent(dev.streams[0], dev.ev_slot_done[sl], 0));
                 }
+                for (auto &part : p->parts)
+                    if ((size_t)part->device_index == d) CK(cudaStreamWaitEvent(dev.streams[0], part->dc.ev_done, 0));
                 CK(cudaEventRecord(dev.ev_step1, dev.streams[0]));
             }
         for (auto &part : p->parts) {
