@@ -549,8 +549,9 @@ struct KernelInfo {
 // and CTA slots free on every SM.
 void reserve_headroom(KernelInfo &ki, const void *fn) {
     const int occ = ki.ctas_per_sm;
-    if (occ < 4) return;
-    const size_t want = (size_t)(227 * 1024) / (size_t)(occ - 2) - 1024;  // 1 KB per CTA is reserved by the system
+    static const int headroom = getenv("GPHMM_HEADROOM") ? std::max(1, atoi(getenv("GPHMM_HEADROOM"))) : 2;  // tuning knob
+    if (occ < headroom + 2) return;
+    const size_t want = (size_t)(227 * 1024) / (size_t)(occ - headroom) - 1024;  // 1 KB per CTA is reserved by the system
     if (want > ki.smem) {
         ki.smem = want & ~(size_t)15;
         if (ki.smem > 48 * 1024) CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ki.smem));
@@ -623,12 +624,24 @@ KernelInfo flat_kernel(int bucket, int n_codes) {
 
 KernelInfo fp64_kernel(int n_codes) { return kernel_info<double, 4, true>(n_codes); }
 
+KernelInfo flat_fp64_kernel(int n_codes) {
+    KernelInfo ki;
+    auto fn = phmm_flat_f64_kernel;
+    ki.fn = (const void *)fn;
+    ki.smem = prior_table_bytes<double, 8>(n_codes);
+    if (ki.smem > 48 * 1024) CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ki.smem));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ki.ctas_per_sm, fn, 32, ki.smem));
+    if (ki.ctas_per_sm < 1) throw Error(GPHMM_ERR_ALPHABET, "prior table does not fit in shared memory");
+    return ki;
+}
+
 struct Stats {
     std::mutex mu;
     gphmm_stats s{};
 };
 
-constexpr int FLAT_KEY = 16;  // Device::info key of the flat-quality kernel of bucket k is FLAT_KEY + k
+constexpr int FLAT_KEY = 16;      // Device::info key of the flat-quality kernel of bucket k is FLAT_KEY + k
+constexpr int FLAT_F64_KEY = 32;  // ... and of phmm_flat_f64_kernel
 
 // One CTA per resident slot (the occupancy already includes the headroom of reserve_headroom()).
 inline uint32_t persistent_grid(uint32_t n_tasks, int n_sms, int ctas_per_sm) {
@@ -644,7 +657,8 @@ struct Device {
         auto it = kinfo.find(key);
         if (it == kinfo.end())
             it = kinfo.emplace(key, bucket < N_FP32_BUCKETS ? fp32_kernel(bucket, n_codes)
-                                    : bucket == N_FP32_BUCKETS ? fp64_kernel(n_codes) : flat_kernel(bucket - FLAT_KEY, n_codes)).first;
+                                    : bucket == N_FP32_BUCKETS ? fp64_kernel(n_codes)
+                                    : bucket == FLAT_F64_KEY ? flat_fp64_kernel(n_codes) : flat_kernel(bucket - FLAT_KEY, n_codes)).first;
         return it->second;
     }
     cudaStream_t streams[N_SLOTS] = {nullptr};
@@ -964,8 +978,24 @@ int launch_chunk(Device &dev, DeviceChunk &dc, const ChunkPlan &c, cudaStream_t 
             ka.tasks = (const Task *)(work + dc.off_rtasks);
             ka.n_tasks = 0;
             ka.n_tasks_ptr = counters + 10;
-            ka.counter = counters + 9;
             ka.sums = work + dc.off_rsums;
+            // flat-quality reads: constant-coefficient fp64 kernel, one launch per class
+            for (int cl = 0; cl < c.n_classes; ++cl) {
+                const Tables &tb2 = tables();
+                FlatCoefD fd;
+                const int qi = c.class_qi[cl], qd = c.class_qd[cl], qc = c.class_qc[cl];
+                const double ei = tb2.eps[qi], ed = tb2.eps[qd], ec = tb2.eps[qc], tIM = 1.0 - ec;
+                const int mn = std::min(qi, qd), mx = std::max(qi, qd);
+                fd.a = tb2.m2m[((mx * (mx + 1)) >> 1) + mn];
+                fd.b = tIM * ei; fd.c = tIM * ed; fd.g = ec; fd.d = ec; fd.tmi = ei; fd.tim = tIM;
+                fd.class_id = (uint32_t)cl; fd.qi = qi; fd.qd = qd; fd.qc = qc;
+                const KernelInfo &kf = dev.info(FLAT_F64_KEY, c.n_codes);
+                ka.counter = counters + 12 + cl;
+                void *fargs[] = {&ka, &fd};
+                CK(cudaLaunchKernel(kf.fn, dim3(std::min<uint32_t>(c.n_pairs, (uint32_t)(dev.n_sms * kf.ctas_per_sm))), dim3(32), fargs, kf.smem, tail));
+                ++launches;
+            }
+            ka.counter = counters + 9;
             ka.bnd = dc.bnd.p;
             ka.bnd_stride = c.max_hap_len + 1;
             void *args[] = {&ka};

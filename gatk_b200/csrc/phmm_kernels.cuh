@@ -36,6 +36,9 @@ constexpr uint32_t CODE_FIRST_BASE = 2;  // A C G T N = 2..6, further byte value
 constexpr int MAX_CODES = 64;
 constexpr int MAX_QUAL = 254;      // QualityUtils.java:43
 constexpr float RESCUE_THRESHOLD_F32 = 1e-28f;
+constexpr int STREAM_PAD = 32;            // NULL codes around every haplotype stream (pipeline fill / drain)
+constexpr uint8_t CLASS_GENERAL = 0xff;   // read_class of reads without a flat-quality class
+constexpr int MAX_FLAT_CLASSES = 4;
 
 // D[0][j] of the reference is 2^1020/H (LoglessPairHMM.java:8,31).  The kernels use a power of two
 // 2^(BASE - ceil(log2 H)) <= that leaves headroom for the scaled states I~ and D~.
@@ -155,6 +158,8 @@ __global__ void __launch_bounds__(32) phmm_forward_kernel(const KernelArgs g)
         const Task t = g.tasks[ti];
         const uint32_t ro = g.read_off[t.read];
         const int R = (int)(g.read_off[t.read + 1] - ro);
+        // fp64 rescue lists: flat-quality reads of up to 254 bases belong to phmm_flat_f64_kernel
+        if (g.read_class != nullptr && g.read_class[t.read] != CLASS_GENERAL && R <= 254) continue;
         const int P = (int)t.stream_len;
         const uint8_t *__restrict__ stream = g.streams + t.stream_off;
         const T c0 = (T)scalbn(1.0, t.c0_exp);
@@ -306,9 +311,6 @@ __global__ void __launch_bounds__(32) phmm_forward_kernel(const KernelArgs g)
 //    so the haplotype's likelihood sum is M+D~ of that row at the END column -- no per-step add;
 //  * the prior table is addressed with one IMAD from a precomputed 32-bit shared address.
 // ---------------------------------------------------------------------------------------------
-constexpr int STREAM_PAD = 32;
-constexpr uint8_t CLASS_GENERAL = 0xff;
-constexpr int MAX_FLAT_CLASSES = 4;
 
 __device__ __forceinline__ float4 lds128(uint32_t addr) {
     float4 v;
@@ -758,6 +760,166 @@ __global__ void __launch_bounds__(32, 28) phmm_flat_f32_kernel(const KernelArgs 
         snap_save<K>(st, slab, ZERO_SLOT);  // the pass-start state (all zero), restored at every END that begins a fresh pass
         flat_dispatch<K, 0>(acc_slot, st, f, B0, G0, E0, tab_lane, src_lane, lane, acc_lane, sums + t.out_base, slab,
                             g.segments + us.seg_first, us.n_segs);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// fp64 redo of flat-quality reads (the rescue list of a chunk).  Same formulation as phmm_flat_f32_kernel in
+// double: 8 rows per lane, transition coefficients as kernel parameters (constant-bank operands of DFMA), prior
+// table in shared memory (one LDS.128 = 2 rows).  A rescue task is ONE read against ONE haplotype, so there is no
+// prefix sharing and no schedule: H branch-free steps, then 32 steps in which the lane holding row R writes the sum
+// when it reaches the END position.  Reads of 255+ bases and non-flat reads stay with phmm_forward_kernel<double>.
+// ---------------------------------------------------------------------------------------------
+struct FlatCoefD {
+    double a, b, c, g, d, tmi, tim;
+    uint32_t class_id, qi, qd, qc;
+};
+
+__device__ __forceinline__ double2 lds128d(uint32_t addr) {
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+    return v;
+}
+
+struct F64State {
+    double M[8], I[8], D[8];
+    double dgm, dgi, dgd, acc;
+    uint32_t y;
+    const uint8_t *sp;
+};
+
+template <int SLOT, bool CHECKED>
+__device__ __forceinline__ void flat64_step(F64State &st, const FlatCoefD &f, double B0, double G0, double E0, uint32_t tab_lane,
+                                            int src_lane, bool is_acc_lane, int &p, int end_pos, double *out)
+{
+    constexpr int K = 8, NV = 4;
+    constexpr unsigned FULL = 0xffffffffu;
+    constexpr uint32_t CODE_STRIDE = NV * 32 * 16;
+    ++st.sp;
+    const uint32_t y_next = ldg_u8(st.sp);
+    const double mu = __shfl_sync(FULL, st.M[K - 1], src_lane);
+    const double iu = __shfl_sync(FULL, st.I[K - 1], src_lane);
+    const double du = __shfl_sync(FULL, st.D[K - 1], src_lane);
+    double pr[K];
+    {
+        const uint32_t addr = st.y * CODE_STRIDE + tab_lane;
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+            const double2 q = lds128d(addr + v * 512);
+            pr[2 * v] = q.x; pr[2 * v + 1] = q.y;
+        }
+    }
+    double Mn[K];
+    {
+        double u = __fma_rn(f.c, st.dgd, E0);
+        u = __fma_rn(B0, st.dgi, u);
+        u = __fma_rn(f.a, st.dgm, u);
+        Mn[0] = pr[0] * u;
+    }
+#pragma unroll
+    for (int k = 1; k < K; ++k) {
+        double u = f.c * st.D[k - 1];
+        u = __fma_rn(f.b, st.I[k - 1], u);
+        u = __fma_rn(f.a, st.M[k - 1], u);
+        Mn[k] = pr[k] * u;
+    }
+#pragma unroll
+    for (int k = 0; k < K; ++k) st.D[k] = __fma_rn(f.d, st.D[k], st.M[k]);
+    st.I[0] = __fma_rn(G0, iu, mu);
+#pragma unroll
+    for (int k = 1; k < K; ++k) st.I[k] = __fma_rn(f.g, st.I[k - 1], Mn[k - 1]);
+#pragma unroll
+    for (int k = 0; k < K; ++k) st.M[k] = Mn[k];
+    st.dgm = mu; st.dgi = iu; st.dgd = du;
+    const double acc_before = st.acc;
+    st.acc += st.M[SLOT];
+    st.acc = __fma_rn(f.tmi, st.I[SLOT], st.acc);
+    if (CHECKED) {
+        if (p == end_pos && is_acc_lane) *out = acc_before;  // position based: codes after this END belong to other haplotypes
+        ++p;
+    }
+    st.y = y_next;
+}
+
+template <int SLOT>
+__device__ __forceinline__ void flat64_sweep(int slot, F64State &st, const FlatCoefD &f, double B0, double G0, double E0,
+                                             uint32_t tab_lane, int src_lane, int lane, bool is_acc_lane, int H, double *out)
+{
+    if (slot == SLOT) {
+        int p = 0;
+#pragma unroll 2
+        for (int s = 0; s < H; ++s) flat64_step<SLOT, false>(st, f, B0, G0, E0, tab_lane, src_lane, is_acc_lane, p, 0, out);
+        p = H + 1 - lane;
+#pragma unroll 1
+        for (int s = 0; s < 32; ++s) flat64_step<SLOT, true>(st, f, B0, G0, E0, tab_lane, src_lane, is_acc_lane, p, H + 1, out);
+    } else if constexpr (SLOT + 1 < 8) {
+        flat64_sweep<SLOT + 1>(slot, st, f, B0, G0, E0, tab_lane, src_lane, lane, is_acc_lane, H, out);
+    }
+}
+
+__global__ void __launch_bounds__(32) phmm_flat_f64_kernel(const KernelArgs g, const FlatCoefD f)
+{
+    constexpr int K = 8, NV = 4;
+    constexpr unsigned FULL = 0xffffffffu;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *tab_s = reinterpret_cast<double *>(smem_raw);
+    int lane, src_lane;
+    asm volatile("mov.u32 %0, %%laneid;" : "=r"(lane));
+    asm volatile("{ .reg .u32 t; add.u32 t, %1, 31; and.b32 %0, t, 31; }" : "=r"(src_lane) : "r"(lane));
+    const uint32_t tab_lane = (uint32_t)__cvta_generic_to_shared(smem_raw) + lane * 16;
+    double *const sums = reinterpret_cast<double *>(g.sums);
+    const uint32_t n_tasks = g.n_tasks_ptr ? *g.n_tasks_ptr : g.n_tasks;
+    const int n_codes = g.n_codes;
+
+    for (;;) {
+        uint32_t ti = 0;
+        if (lane == 0) ti = atomicAdd(g.counter, 1u);
+        ti = __shfl_sync(FULL, ti, 0);
+        if (ti >= n_tasks) break;
+        const Task t = g.tasks[ti];
+        if (g.read_class[t.read] != (uint8_t)f.class_id) continue;
+        const uint32_t ro = g.read_off[t.read];
+        const int R = (int)(g.read_off[t.read + 1] - ro);
+        if (R > 254) continue;  // phmm_forward_kernel<double, 4, striped> takes these
+        const int H = (int)t.stream_len - 1;
+        const double c0 = scalbn(1.0, t.c0_exp);
+
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const int i = lane * K + k + 1;
+            const bool real = i <= R;
+            double pm = 0.0, px = 0.0;
+            uint32_t x = 0;
+            if (real) {
+                const uint32_t q = min((uint32_t)g.rd_q[ro + i - 1], (uint32_t)MAX_QUAL);  // range errors were flagged by the fp32 pass
+                x = g.rd_bases[ro + i - 1];
+                const double e = c_eps[q];
+                pm = 1.0 - e;
+                px = g.tristate_off ? e : e / 3.0;
+            }
+            for (int y = 0; y < n_codes; ++y) {
+                double v = 0.0;
+                if (real && y >= (int)CODE_FIRST_BASE) {
+                    const uint32_t hb = g.code_byte[y];
+                    v = (x == hb || x == (uint32_t)'N' || hb == (uint32_t)'N') ? pm : px;  // LoglessPairHMM.java:89
+                }
+                tab_s[((y * NV + k / 2) * 32 + lane) * 2 + (k % 2)] = v;
+            }
+        }
+        __syncwarp();
+
+        F64State st;
+#pragma unroll
+        for (int k = 0; k < K; ++k) { st.M[k] = 0.0; st.I[k] = 0.0; st.D[k] = 0.0; }
+        st.dgm = 0.0; st.dgi = 0.0; st.dgd = 0.0; st.acc = 0.0;
+        st.sp = g.streams + t.stream_off - lane;
+        st.y = ldg_u8(st.sp);
+        const double B0 = lane == 0 ? 0.0 : f.b;
+        const double G0 = lane == 0 ? 0.0 : f.g;
+        const double E0 = lane == 0 ? f.tim * c0 : 0.0;
+        const int acc_lane = (R - 1) / K, acc_slot = (R - 1) % K;
+        flat64_sweep<0>(acc_slot, st, f, B0, G0, E0, tab_lane, src_lane, lane, lane == acc_lane, H, sums + t.out_base);
     }
 }
 
