@@ -845,24 +845,19 @@ int launch_chunk(Device &dev, DeviceChunk &dc, const ChunkPlan &c, cudaStream_t 
     // Size the boundary buffer for every striped launch of this chunk before anything is queued.
     {
         size_t need = 16;
-        if (!opt.force_fp64) {
-            const uint32_t n8 = c.bucket_begin[9] - c.bucket_begin[8];
-            if (n8) {
-                const KernelInfo &ki = dev.info(8, c.n_codes);
-                need = std::max(need, (size_t)std::min<uint32_t>(n8, (uint32_t)(dev.n_sms * ki.ctas_per_sm)) * c.max_stream_len * sizeof(Bnd<float>));
-            }
-            if (n_tasks_total) {
-                const KernelInfo &ki = dev.info(FP64_BUCKET, c.n_codes);
-                need = std::max(need, (size_t)std::min<uint32_t>(c.n_pairs, (uint32_t)(dev.n_sms * ki.ctas_per_sm)) * (c.max_hap_len + 1) * sizeof(Bnd<double>));
-            }
-        } else if (n_tasks_total) {
+        const uint32_t n8 = c.bucket_begin[9] - c.bucket_begin[8];
+        if (n8) {
+            const KernelInfo &ki = dev.info(8, c.n_codes);
+            need = std::max(need, (size_t)std::min<uint32_t>(n8, (uint32_t)(dev.n_sms * ki.ctas_per_sm)) * c.max_stream_len * sizeof(Bnd<float>));
+        }
+        if (n_tasks_total) {
             const KernelInfo &ki = dev.info(FP64_BUCKET, c.n_codes);
-            need = std::max(need, (size_t)std::min<uint32_t>(n_tasks_total, (uint32_t)(dev.n_sms * ki.ctas_per_sm)) * c.max_stream_len * sizeof(Bnd<double>));
+            need = std::max(need, (size_t)std::min<uint32_t>(c.n_pairs, (uint32_t)(dev.n_sms * ki.ctas_per_sm)) * (c.max_hap_len + 1) * sizeof(Bnd<double>));
         }
         dc.bnd.reserve(need);
     }
 
-    if (!opt.force_fp64) {
+    {
         // 1. per-read flat-quality classification (device side; the host only sampled candidate classes)
         const uint32_t n_span_reads = (uint32_t)c.read_off.size() - 1;
         {
@@ -882,6 +877,11 @@ int launch_chunk(Device &dev, DeviceChunk &dc, const ChunkPlan &c, cudaStream_t 
         }
         ka.read_class = (const uint8_t *)(work + dc.off_class);
 
+        if (opt.force_fp64) {
+            // --native-pair-hmm-use-double-precision: no fp32 pass at all.  NaN sums make the epilogue put EVERY pair on
+            // the fp64 list, which the two fp64 kernels below then compute.
+            CK(cudaMemsetAsync(work + dc.off_sums, 0xff, std::max<size_t>((size_t)c.n_pairs, 1) * sizeof(float), st));
+        } else {
         // 2. forward kernels.  Every (bucket) task list is visited by the flat kernel of each class and by the general
         // kernel; each kernel only runs the tasks whose read it owns.  The first launch stays on the chunk's stream,
         // the others fork onto side streams so that short grids overlap the tail of the big one.
@@ -964,6 +964,7 @@ int launch_chunk(Device &dev, DeviceChunk &dc, const ChunkPlan &c, cudaStream_t 
             void *args[] = {&ka};
             launch_on(dev.info(k, c.n_codes), n, k, args);
         }
+        }
         CK(cudaEventRecord(dc.ev_f32, st));
         CK(cudaStreamWaitEvent(tail, dc.ev_f32, 0));  // the closing kernels run at high priority in the reserved headroom
         if (ea.n_units) {
@@ -1003,31 +1004,6 @@ int launch_chunk(Device &dev, DeviceChunk &dc, const ChunkPlan &c, cudaStream_t 
             ++launches;
             phmm_epilogue_rescue<<<std::min<uint32_t>((c.n_pairs + 127) / 128, 1024), 128, 0, tail>>>(
                 (const Task *)(work + dc.off_rtasks), counters + 10, ea.rescue_capacity, (const double *)(work + dc.off_rsums), ea.out);
-            CK(cudaGetLastError());
-            ++launches;
-        }
-        CK(cudaEventRecord(dc.ev_f64, tail));
-    } else {
-        CK(cudaEventRecord(dc.ev_f32, st));
-        if (n_tasks_total) {
-            const KernelInfo &ki = dev.info(FP64_BUCKET, c.n_codes);
-            const uint32_t grid = std::min<uint32_t>(n_tasks_total, (uint32_t)(dev.n_sms * ki.ctas_per_sm));
-            ka.tasks = (const Task *)(meta + dc.off_tasks);
-            ka.n_tasks = n_tasks_total;
-            ka.n_tasks_ptr = nullptr;
-            ka.counter = counters + 11;
-            ka.sums = work + dc.off_sums;
-            ka.bnd = dc.bnd.p;
-            ka.bnd_stride = c.max_stream_len;
-            void *args[] = {&ka};
-            CK(cudaLaunchKernel(ki.fn, dim3(grid), dim3(32), args, ki.smem, st));
-            ++launches;
-        }
-        if (!dc.ev_fork) CK(cudaEventCreateWithFlags(&dc.ev_fork, cudaEventDisableTiming));
-        CK(cudaEventRecord(dc.ev_fork, st));
-        CK(cudaStreamWaitEvent(tail, dc.ev_fork, 0));
-        if (ea.n_units) {
-            phmm_epilogue_f64_units<<<std::min<uint32_t>(ea.n_units, 4096), 128, 0, tail>>>(ea);
             CK(cudaGetLastError());
             ++launches;
         }
@@ -1232,7 +1208,7 @@ void device_loop(gphmm *h, Device &dev, const gphmm_batch *b, const std::vector<
             const double t_a = now_ms();
             plans[slot] = pool.take(ci);
             const double t_b = now_ms();
-            upload_chunk(dev, dev.slots[slot], b, *plans[slot], dev.streams[slot], opt.force_fp64, h->stats);
+            upload_chunk(dev, dev.slots[slot], b, *plans[slot], dev.streams[slot], false, h->stats);
             const double t_c = now_ms();
             launches += launch_chunk(dev, dev.slots[slot], *plans[slot], dev.streams[slot], dev.tails[slot], dev.aux[slot], opt, true);
             if (trace)
@@ -1273,7 +1249,7 @@ int run_batch(gphmm *h, const gphmm_batch *b, double *out) {
     std::vector<int> rcs(nd, GPHMM_OK);
     {
         const int n_threads = h->cfg.host_threads > 0 ? h->cfg.host_threads : 4;  // GATK's --native-pair-hmm-threads default
-        PlanPool pool(b, chunks, h->cfg.force_fp64 != 0, h->cfg.no_prefix_sharing == 0, n_threads, h->stats);
+        PlanPool pool(b, chunks, false, h->cfg.no_prefix_sharing == 0, n_threads, h->stats);
         if (nd == 1 || chunks.size() == 1) {
             device_loop(h, *h->devices[0], b, chunks, pool, cursor, out, errs[0], rcs[0]);
         } else {
@@ -1573,7 +1549,7 @@ int gphmm_prepare(gphmm_t *h, const gphmm_batch *b, gphmm_prepared_t **out) {
         std::unique_ptr<gphmm_prepared> p(new gphmm_prepared());
         p->units.assign(b->units, b->units + b->n_units);
         auto chunks = split_units(b, h->chunk_cells(), h->chunk_bytes(), false);  // inputs are resident: no staging to hide
-        const bool f64 = h->cfg.force_fp64 != 0;
+        const bool f64 = false;  // forced fp64 only changes which kernels launch_chunk queues
         for (size_t ci = 0; ci < chunks.size(); ++ci) {
             std::unique_ptr<gphmm_prepared::Part> part(new gphmm_prepared::Part());
             part->device_index = (int)(ci % h->devices.size());

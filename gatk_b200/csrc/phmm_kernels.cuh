@@ -986,21 +986,6 @@ __global__ void __launch_bounds__(128) phmm_epilogue_f32(const EpilogueArgs e)
     }
 }
 
-// forced-fp64 mode: sums are doubles in the unit layout
-__global__ void __launch_bounds__(128) phmm_epilogue_f64_units(const EpilogueArgs e)
-{
-    const double *sums = reinterpret_cast<const double *>(e.sums);
-    for (uint32_t u = blockIdx.x; u < e.n_units; u += gridDim.x) {
-        const UnitDesc d = e.units[u];
-        const uint32_t n = d.n_reads * d.n_haps;
-        for (uint32_t k = threadIdx.x; k < n; k += blockDim.x) {
-            const uint32_t h = k % d.n_haps;
-            const uint32_t H = e.hap_len[d.hap_first + h];
-            e.out[d.out_base + k] = log10(sums[d.out_base + k]) - log10_c0H(d.c0_exp, H);
-        }
-    }
-}
-
 // rescue pass: one double sum per rescue slot -> its final output slot
 __global__ void __launch_bounds__(128) phmm_epilogue_rescue(const Task *tasks, const uint32_t *n_rescue, uint32_t capacity,
                                                             const double *sums, double *out)
