@@ -232,7 +232,7 @@ def main():
                          "traffic_note": "ncu --set full, flat K=8 launch: 16 MB DRAM read + 57 MB written (snapshot slabs) for ~1.8e10 cells; see profiles/r01_flat_k8_prefix_sharing_ncu_full.txt",
                          "hbm_gbs_staging": (batch.input_bytes() + 8 * pairs) * steps / f32_s / 1e9},
         }
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:  # rank 0 at N=1 only
             small = synth.config2(min(args.regions, 400))
             res["cpu_baseline"], _, _ = cpu_baseline(small, budget_s=args.cpu_budget)
         print(json.dumps(res))

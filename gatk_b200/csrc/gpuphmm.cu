@@ -166,6 +166,7 @@ void validate_batch(const gphmm_batch *b) {
         if (un.read_begin < 0 || un.read_end < un.read_begin || un.read_end > b->n_reads || un.hap_begin < 0 ||
             un.hap_end < un.hap_begin || un.hap_end > b->n_haps || un.out_off < 0)
             throw Error(GPHMM_ERR_INVALID_ARG, "unit range out of bounds");
+        if (un.hap_end - un.hap_begin > 65535) throw Error(GPHMM_ERR_TOO_LARGE, "more than 65535 haplotypes in one unit");
     }
     if (b->n_reads > 0 && b->read_off[b->n_reads] > 0 &&
         (!b->read_bases || !b->base_q || !b->ins_q || !b->del_q || !b->gcp))
@@ -228,7 +229,7 @@ std::vector<int> sorted_hap_order(const gphmm_batch *b, const gphmm_unit &un, bo
     return order;
 }
 
-UnitSched plan_unit_sharing(const gphmm_batch *b, const gphmm_unit &un, const int16_t *lut, bool share, ChunkPlan &c,
+UnitSched plan_unit_sharing(const gphmm_batch *b, const gphmm_unit &un, uint32_t hap_first_local, bool share, ChunkPlan &c,
                             int64_t sum_read_len, const std::vector<int> &full_order, int g_first, int g_count) {
     constexpr uint32_t MIN_DEPTH = 32, SPACING = 32;
     UnitSched us;
@@ -303,12 +304,12 @@ UnitSched plan_unit_sharing(const gphmm_batch *b, const gphmm_unit &un, const in
     }
     // stream + pass table
     for (int i = 0; i < n; ++i) {
-        const uint8_t *src = hap_ptr(order[i]);
         const uint32_t H = hap_len(order[i]);
         const size_t w = c.sstreams.size();
         c.sstreams.resize(w + (H - r[i]) + n_pad[i] + 1);
         uint8_t *dst = c.sstreams.data() + w;
-        for (uint32_t q = r[i]; q < H; ++q) dst[q - r[i]] = (uint8_t)lut[src[q]];
+        // the full stream of this unit was encoded a moment ago: copy the columns behind the shared prefix
+        memcpy(dst, c.streams.data() + c.hap_stream_off[hap_first_local + order[i]] + r[i], H - r[i]);
         for (uint32_t q = 0; q < n_pad[i]; ++q) dst[H - r[i] + q] = (uint8_t)CODE_NULL;  // prior 0: no effect on the sum
         dst[H - r[i] + n_pad[i]] = (uint8_t)CODE_END;
         PassInfo pi;
@@ -471,7 +472,7 @@ void plan_chunk(const gphmm_batch *b, int64_t u0, int64_t u1, bool force_fp64, b
             const std::vector<int> order = sorted_hap_order(b, un, share && !force_fp64);
             for (int gi = 0; gi < n_groups; ++gi) {
                 const int g0 = (int)((int64_t)nh * gi / n_groups), g1 = (int)((int64_t)nh * (gi + 1) / n_groups);
-                c.unit_sched.push_back(plan_unit_sharing(b, un, lut, share && !force_fp64, c, fast_read_len, order, g0, g1 - g0));
+                c.unit_sched.push_back(plan_unit_sharing(b, un, d.hap_first, share && !force_fp64, c, fast_read_len, order, g0, g1 - g0));
             }
         }
         if (nh == 0) continue;
