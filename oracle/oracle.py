@@ -22,8 +22,8 @@ _f64p = ctypes.POINTER(ctypes.c_double)
 
 def build(force=False):
     """Compile the oracle with the committed Makefile (gcc, -ffp-contract=off)."""
-    src = os.path.join(_HERE, "pairhmm_oracle.c")
-    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src):
+    srcs = [os.path.join(_HERE, f) for f in ("pairhmm_oracle.c", "pairhmm_simd_baseline.c", "Makefile")]
+    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < max(os.path.getmtime(x) for x in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-s", "-B", "libphmm_oracle.so"])
     return _LIB_PATH
 
@@ -49,6 +49,10 @@ def lib():
         L.phmm_oracle_unit.argtypes = [_u8p, _u8p, _u8p, _u8p, _u8p, _i32p, ctypes.c_int,
                                        _u8p, _i32p, ctypes.c_int, ctypes.c_int, ctypes.c_int, _f64p]
         L.phmm_oracle_max_threads.restype = ctypes.c_int
+        L.phmm_simd_isa.restype = ctypes.c_int
+        L.phmm_simd_batch.restype = ctypes.c_long
+        L.phmm_simd_batch.argtypes = [_u8p, _u8p, _u8p, _u8p, _u8p, ctypes.POINTER(ctypes.c_int64), _u8p, ctypes.POINTER(ctypes.c_int64),
+                                      ctypes.POINTER(ctypes.c_int64), ctypes.c_long, ctypes.c_int, _f64p]
         L.phmm_oracle_init()
         _lib = L
     return _lib
@@ -122,3 +126,23 @@ def unit(read_bases, base_q, ins_q, del_q, gcp, read_off, hap_bases, hap_off, tr
     if rc != 0:
         raise ValueError("oracle error %d" % rc)
     return out
+
+
+def simd_isa():
+    """512 (AVX-512), 256 (AVX2) or 0 (generic): the vector ISA the SIMD baseline uses on this host."""
+    return lib().phmm_simd_isa()
+
+
+def simd_batch(read_bases, base_q, ins_q, del_q, gcp, read_off, hap_bases, hap_off, units, n_out, threads=1):
+    """Vectorised fp32 CPU baseline (pairhmm_simd_baseline.c) over a whole batch; units = int64[n,5] rows of
+    (read_begin, read_end, hap_begin, hap_end, out_off).  Returns (log10 likelihoods, pairs redone in double)."""
+    arrs = [_u8(x) for x in (read_bases, base_q, ins_q, del_q, gcp)]
+    hb, hbp = _u8(hap_bases)
+    ro = np.ascontiguousarray(read_off, dtype=np.int64)
+    ho = np.ascontiguousarray(hap_off, dtype=np.int64)
+    un = np.ascontiguousarray(units, dtype=np.int64).reshape(-1, 5)
+    out = np.full(n_out, np.nan, dtype=np.float64)
+    i64p = ctypes.POINTER(ctypes.c_int64)
+    rescued = lib().phmm_simd_batch(arrs[0][1], arrs[1][1], arrs[2][1], arrs[3][1], arrs[4][1], ro.ctypes.data_as(i64p), hbp,
+                                    ho.ctypes.data_as(i64p), un.ctypes.data_as(i64p), len(un), int(threads), out.ctypes.data_as(_f64p))
+    return out, int(rescued)

@@ -176,3 +176,18 @@ def test_unit_layout_read_major():
         for ri, r in enumerate(reads):
             for hi, h in enumerate(haps):
                 assert out[ri * 3 + hi] == oracle.logless(h, r["read"], r["base_q"], r["ins_q"], r["del_q"], r["gcp"])
+
+
+def test_simd_baseline_matches_oracle():
+    # the vectorised fp32 CPU baseline that bench.py reports (not the oracle) agrees with the oracle to float noise,
+    # including reads of different lengths in one vector and pairs that need the double redo
+    from gatk_b200 import synth
+    from phmm_testutil import oracle_batch
+    for b in (synth.config2(6), synth.random_batch(11, n_units=4, wild_quals=True), synth.config5(hap_len=400, n_regions=2, reads_per_region=20, n_haps=3, bad_fraction=0.5)):
+        u = np.stack([b.units[k] for k in ("read_begin", "read_end", "hap_begin", "hap_end", "out_off")], axis=1)
+        got, _ = oracle.simd_batch(b.read_bases, b.base_q, b.ins_q, b.del_q, b.gcp, b.read_off, b.hap_bases, b.hap_off, u, b.n_out, threads=2)
+        want = oracle_batch(b)
+        fin = np.isfinite(want)
+        assert np.array_equal(np.isfinite(got), fin)
+        assert np.abs(got[fin] - want[fin]).max() <= 2e-5
+    assert oracle.simd_isa() in (0, 256, 512)
