@@ -10,135 +10,163 @@ import org.broadinstitute.hellbender.utils.genotyper.LikelihoodMatrix;
 import org.broadinstitute.hellbender.utils.haplotype.Haplotype;
 import org.broadinstitute.hellbender.utils.read.GATKRead;
 
-import java.util.LinkedHashMap;
+import java.util.HashMap;
 import java.util.List;
 import java.util.Map;
 
 /**
- * {@code -pairHMM CUDA_LOGLESS_CACHING}: the PairHMM forward algorithm on NVIDIA B200 GPUs.
+ * {@code -pairHMM CUDA_LOGLESS_CACHING}: the PairHMM forward algorithm on NVIDIA B200 GPUs (libgpuphmm).
  *
- * Drop-in sibling of {@link VectorLoglessPairHMM} (same parent, same overrides, same result layout): haplotypes are
- * staged once per region in {@link #initialize}, every per-sample call packs the reads into {@link ReadDataHolder}s,
- * makes ONE native call, and scatters the read-major {@code double[]} into the {@link LikelihoodMatrix}.
- * Likelihoods are computed in fp32 on the GPU with a GPU fp64 redo of under-flowing pairs
- * ({@code --native-pair-hmm-use-double-precision} forces fp64 for every pair).  There is no CPU fallback: when no
- * usable GPU is present the constructor throws {@link UserException.HardwareFeatureException}, exactly like the AVX
- * implementations do when AVX is missing, and the entry is NOT part of FASTEST_AVAILABLE.
+ * <p>Fulfils the contract of the other native implementation, {@link VectorLoglessPairHMM}: haplotypes are handed
+ * over once per region in {@link #initialize(List, Map, int, int)}; each per-sample
+ * {@link #computeLog10Likelihoods} call gathers the five per-base arrays of every read, makes ONE native call and
+ * copies the read-major result {@code lk[read * nHaplotypes + haplotype]} into the {@link LikelihoodMatrix}; the
+ * flat array stays available through {@link #getLogLikelihoodArray()}; {@code --pair-hmm-results-file} is honoured.</p>
+ *
+ * <p>Likelihoods are computed in fp32 on the GPU; pairs whose fp32 sum leaves the float range are recomputed in fp64
+ * on the GPU. {@code --native-pair-hmm-use-double-precision} computes everything in fp64.
+ * {@code --native-pair-hmm-threads} sizes the host-side staging pool. The GPUs to use come from the environment
+ * variable {@code GATK_CUDA_PAIRHMM_DEVICES} (comma separated ordinals; unset = the current device).</p>
+ *
+ * <p>There is no CPU fallback. Without a usable GPU or library the constructor throws
+ * {@link UserException.HardwareFeatureException}, and the implementation is not part of FASTEST_AVAILABLE.</p>
  */
 public final class CudaLoglessPairHMM extends LoglessPairHMM {
-    private static final Logger logger = LogManager.getLogger(CudaLoglessPairHMM.class);
+    private static final Logger cudaLogger = LogManager.getLogger(CudaLoglessPairHMM.class);
+    private static final String DEVICES_ENV = "GATK_CUDA_PAIRHMM_DEVICES";
 
-    private long threadLocalSetupTimeDiff = 0;
-    private long pairHMMSetupTime = 0;
+    private final CudaPairHMMBinding gpu = new CudaPairHMMBinding();
 
-    private final CudaPairHMMBinding pairHmm;
+    /** Haplotypes of the current region in the order the native side sees them. */
+    private HaplotypeDataHolder[] nativeHaplotypes = new HaplotypeDataHolder[0];
+    /** Position of each haplotype (bases + reference flag, i.e. {@link Haplotype#equals}) in {@link #nativeHaplotypes}. */
+    private final Map<Haplotype, Integer> nativeIndexOf = new HashMap<>();
 
-    // Haplotype -> index in the list passed to initialize(); keyed by Haplotype.equals (bases + isReference)
-    private final Map<Haplotype, Integer> haplotypeToHaplotypeListIdxMap = new LinkedHashMap<>();
-    private HaplotypeDataHolder[] mHaplotypeDataArray;
+    private long nanosInSetup = 0L;
 
     public CudaLoglessPairHMM(final PairHMMNativeArguments args) throws UserException.HardwareFeatureException {
-        pairHmm = new CudaPairHMMBinding();
-        final String deviceList = System.getenv("GATK_CUDA_PAIRHMM_DEVICES");   // e.g. "0,1,2,3"; unset = current device
-        if (deviceList != null && !deviceList.trim().isEmpty()) {
-            final String[] tok = deviceList.split(",");
-            final int[] devices = new int[tok.length];
-            for (int i = 0; i < tok.length; i++) {
-                devices[i] = Integer.parseInt(tok[i].trim());
-            }
-            pairHmm.setDevices(devices);
+        gpu.setDevices(parseDeviceList(System.getenv(DEVICES_ENV)));
+        if (!gpu.load(null)) {
+            throw new UserException.HardwareFeatureException(
+                    "Machine does not support the CUDA PairHMM: libgpuphmm could not be loaded or no compute-capability 10.x GPU is visible.");
         }
-        if (!pairHmm.load(null)) {
-            throw new UserException.HardwareFeatureException("Machine does not support the CUDA PairHMM (no compute-capability 10.x GPU or libgpuphmm could not be loaded).");
+        gpu.initialize(args);
+    }
+
+    static int[] parseDeviceList(final String spec) {
+        if (spec == null || spec.trim().isEmpty()) {
+            return null;
         }
-        pairHmm.initialize(args);
+        final String[] fields = spec.split(",");
+        final int[] ordinals = new int[fields.length];
+        for (int k = 0; k < fields.length; k++) {
+            ordinals[k] = Integer.parseInt(fields[k].trim());
+        }
+        return ordinals;
     }
 
     /**
-     * {@inheritDoc}
+     * Stages the region's haplotypes for all the per-sample calls that follow. The Java DP matrices of the parent class
+     * are never allocated: {@code readMaxLength} and {@code haplotypeMaxLength} are not needed on this path.
      */
     @Override
     public void initialize(final List<Haplotype> haplotypes, final Map<String, List<GATKRead>> perSampleReadList,
                            final int readMaxLength, final int haplotypeMaxLength) {
-        // like VectorLoglessPairHMM: the Java matrices of the parent are never allocated
-        final int numHaplotypes = haplotypes.size();
-        mHaplotypeDataArray = new HaplotypeDataHolder[numHaplotypes];
-        int idx = 0;
-        haplotypeToHaplotypeListIdxMap.clear();
-        for (final Haplotype currHaplotype : haplotypes) {
-            mHaplotypeDataArray[idx] = new HaplotypeDataHolder();
-            mHaplotypeDataArray[idx].haplotypeBases = currHaplotype.getBases();
-            haplotypeToHaplotypeListIdxMap.put(currHaplotype, idx);
-            ++idx;
+        nativeIndexOf.clear();
+        nativeHaplotypes = new HaplotypeDataHolder[haplotypes.size()];
+        int next = 0;
+        for (final Haplotype haplotype : haplotypes) {
+            final HaplotypeDataHolder holder = new HaplotypeDataHolder();
+            holder.haplotypeBases = haplotype.getBases();
+            nativeHaplotypes[next] = holder;
+            nativeIndexOf.put(haplotype, next);
+            next++;
         }
     }
 
-    /**
-     * {@inheritDoc}
-     */
     @Override
     public void computeLog10Likelihoods(final LikelihoodMatrix<GATKRead, Haplotype> logLikelihoods,
                                         final List<GATKRead> processedReads,
                                         final PairHMMInputScoreImputator inputScoreImputator) {
         if (processedReads.isEmpty()) {
-            return;
+            return;   // nothing to do; getLogLikelihoodArray() keeps its previous value, as in the other implementations
         }
-        if (doProfiling) {
-            startTime = System.nanoTime();
-        }
-        final int readListSize = processedReads.size();
-        final int numHaplotypes = logLikelihoods.numberOfAlleles();
-        final ReadDataHolder[] readDataArray = new ReadDataHolder[readListSize];
-        int idx = 0;
-        for (final GATKRead read : processedReads) {
-            final PairHMMInputScoreImputation inputScoreImputation = inputScoreImputator.impute(read);
-            readDataArray[idx] = new ReadDataHolder();
-            readDataArray[idx].readBases = read.getBases();
-            readDataArray[idx].readQuals = read.getBaseQualities();
-            readDataArray[idx].insertionGOP = inputScoreImputation.insOpenPenalties();
-            readDataArray[idx].deletionGOP = inputScoreImputation.delOpenPenalties();
-            readDataArray[idx].overallGCP = inputScoreImputation.gapContinuationPenalties();
-            ++idx;
-        }
+        final long callStart = doProfiling ? System.nanoTime() : 0L;
 
-        mLogLikelihoodArray = new double[readListSize * numHaplotypes];
-        if (doProfiling) {
-            threadLocalSetupTimeDiff = (System.nanoTime() - startTime);
-        }
+        final ReadDataHolder[] nativeReads = gatherReads(processedReads, inputScoreImputator);
+        final int nHaplotypes = nativeHaplotypes.length;
+        final double[] flat = new double[nativeReads.length * nHaplotypes];
+        final long setupDone = doProfiling ? System.nanoTime() : 0L;
 
-        pairHmm.computeLikelihoods(readDataArray, mHaplotypeDataArray, mLogLikelihoodArray);
+        gpu.computeLikelihoods(nativeReads, nativeHaplotypes, flat);   // the only native call
 
-        int readIdx = 0;
-        for (int r = 0; r < readListSize; r++) {
-            int hapIdx = 0;
-            for (final Haplotype haplotype : logLikelihoods.alleles()) {
-                // the matrix's allele order may differ from the order given to initialize()
-                final int idxInsideHaplotypeList = haplotypeToHaplotypeListIdxMap.get(haplotype);
-                final double lk = mLogLikelihoodArray[readIdx + idxInsideHaplotypeList];
-                logLikelihoods.set(hapIdx, r, lk);
-                writeToResultsFileIfApplicable(readDataArray[r].readBases, readDataArray[r].readQuals, readDataArray[r].insertionGOP,
-                        readDataArray[r].deletionGOP, readDataArray[r].overallGCP, haplotype.getBases(), lk);
-                ++hapIdx;
-            }
-            readIdx += numHaplotypes;
-        }
+        mLogLikelihoodArray = flat;
+        scatter(flat, nativeReads, logLikelihoods);
+
         if (doProfiling) {
-            threadLocalPairHMMComputeTimeDiff = (System.nanoTime() - startTime);
+            threadLocalPairHMMComputeTimeDiff = System.nanoTime() - callStart;
             pairHMMComputeTime += threadLocalPairHMMComputeTimeDiff;
-            pairHMMSetupTime += threadLocalSetupTimeDiff;
+            nanosInSetup += setupDone - callStart;
+        }
+    }
+
+    /** One {@link ReadDataHolder} per read: bases, base qualities and the imputed gap-open / gap-continuation penalties. */
+    private static ReadDataHolder[] gatherReads(final List<GATKRead> reads, final PairHMMInputScoreImputator imputator) {
+        final ReadDataHolder[] holders = new ReadDataHolder[reads.size()];
+        int r = 0;
+        for (final GATKRead read : reads) {
+            final PairHMMInputScoreImputation scores = imputator.impute(read);
+            final ReadDataHolder holder = new ReadDataHolder();
+            holder.readBases = read.getBases();
+            holder.readQuals = read.getBaseQualities();
+            holder.insertionGOP = scores.insOpenPenalties();
+            holder.deletionGOP = scores.delOpenPenalties();
+            holder.overallGCP = scores.gapContinuationPenalties();
+            holders[r++] = holder;
+        }
+        return holders;
+    }
+
+    /**
+     * Copies the read-major native result into the allele-major matrix. The matrix may list the haplotypes in another
+     * order than {@link #initialize} received them, so the column of each matrix allele is looked up once per call.
+     */
+    private void scatter(final double[] flat, final ReadDataHolder[] nativeReads,
+                         final LikelihoodMatrix<GATKRead, Haplotype> matrix) {
+        final List<Haplotype> matrixAlleles = matrix.alleles();
+        final int nHaplotypes = nativeHaplotypes.length;
+        final int[] column = new int[matrixAlleles.size()];
+        for (int a = 0; a < column.length; a++) {
+            final Integer idx = nativeIndexOf.get(matrixAlleles.get(a));
+            if (idx == null) {
+                throw new IllegalStateException("haplotype of the likelihood matrix was not passed to initialize()");
+            }
+            column[a] = idx;
+        }
+        for (int r = 0; r < nativeReads.length; r++) {
+            final ReadDataHolder read = nativeReads[r];
+            final int row = r * nHaplotypes;
+            for (int a = 0; a < column.length; a++) {
+                final double lk = flat[row + column[a]];
+                matrix.set(a, r, lk);
+                writeToResultsFileIfApplicable(read.readBases, read.readQuals, read.insertionGOP, read.deletionGOP,
+                        read.overallGCP, matrixAlleles.get(a).getBases(), lk);
+            }
         }
     }
 
     @Override
     public void close() {
         if (doProfiling) {
-            final long[] c = pairHmm.counters();
-            final double[] t = pairHmm.timers();
-            logger.info("Time spent in setup for JNI call : " + (pairHMMSetupTime * 1e-9));
-            logger.info(String.format("CUDA PairHMM: %d pairs, %d cells, %d pairs redone in fp64, %d kernel launches; fp32 kernels %.3f s, fp64 kernels %.3f s, H2D %d bytes, D2H %d bytes",
-                    c[0], c[1], c[2], c[5], t[0] * 1e-3, t[1] * 1e-3, c[3], c[4]));
+            final long[] n = gpu.counters();
+            final double[] ms = gpu.timers();
+            cudaLogger.info("Time spent in setup for JNI call : " + (nanosInSetup * 1e-9));
+            cudaLogger.info(String.format(
+                    "CUDA PairHMM: %d pairs, %d cells, %d pairs recomputed in fp64, %d kernel launches; "
+                            + "GPU fp32 %.3f s, GPU fp64 %.3f s, host staging %.3f s, H2D %d bytes, D2H %d bytes",
+                    n[0], n[1], n[2], n[5], ms[0] * 1e-3, ms[1] * 1e-3, ms[3] * 1e-3, n[3], n[4]));
         }
-        pairHmm.done();
+        gpu.done();
         super.close();
     }
 }

@@ -102,7 +102,8 @@ def test_jni_shim_syntax_and_symbols():
 def test_java_plugin_sources_present():
     hmm = open(os.path.join(ROOT, "java/org/broadinstitute/hellbender/utils/pairhmm/CudaLoglessPairHMM.java")).read()
     assert "extends LoglessPairHMM" in hmm and "HardwareFeatureException" in hmm
-    for method in ("initialize(final List<Haplotype>", "computeLog10Likelihoods(final LikelihoodMatrix<GATKRead, Haplotype>", "public void close()"):
+    for method in ("initialize(final List<Haplotype>", "computeLog10Likelihoods(final LikelihoodMatrix<GATKRead, Haplotype>", "public void close()",
+                   "writeToResultsFileIfApplicable(", "mLogLikelihoodArray = flat"):
         assert method in hmm
     patch = open(os.path.join(ROOT, "java/patches/PairHMM.Implementation.patch")).read()
     assert "CUDA_LOGLESS_CACHING(args ->" in patch

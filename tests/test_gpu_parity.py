@@ -409,3 +409,32 @@ def test_two_devices_one_process():
     b = synth.config2(200)
     with GpuPhmm(devices=[0]) as one, GpuPhmm(devices=[0, 1], chunk_cells=2_000_000_000) as two:
         assert np.array_equal(one.compute(b), two.compute(b))
+
+
+def test_many_flat_quality_classes(hmm):
+    # reads with flat (ins, del, gcp) triples: four classes get the constant-coefficient kernel, the rest and the
+    # per-base reads fall back to the general kernel; every route must agree with the oracle
+    rng = np.random.default_rng(77)
+    L = np.frombuffer(b"ACGT", dtype=np.uint8)
+    hap = L[rng.integers(0, 4, 300)]
+    triples = [(45, 45, 10), (40, 42, 10), (30, 30, 8), (45, 40, 20), (35, 45, 12), (20, 25, 6), (50, 50, 3)]
+    reads = []
+    for k in range(70):
+        R = int(rng.integers(20, 255))
+        off = int(rng.integers(0, 300 - R + 1))
+        rd = hap[off:off + R].copy()
+        rd[R // 3] = ord("T") if rd[R // 3] != ord("T") else ord("A")
+        q = np.clip(rng.normal(30, 8, R), 6, 41).astype(np.uint8)
+        if k % 8 == 7:
+            iq, dq, gq = (rng.integers(20, 50, R).astype(np.uint8) for _ in range(3))
+        else:
+            t = triples[k % len(triples)]
+            iq, dq, gq = const_quals(R, t[0]), const_quals(R, t[1]), const_quals(R, t[2])
+        reads.append((rd, q, iq, dq, gq))
+    one = Batch.single_unit(reads, [hap.tobytes(), hap[:250].tobytes(), hap[10:].tobytes(), hap[::-1].copy().tobytes()])
+    want = oracle_batch(one)
+    _check(hmm.compute(one), want, TOL)
+    big, n = _replicate(one, 200)   # enough reads for whole-unit tasks with prefix sharing
+    got = hmm.compute(big)
+    _check(got[:n], want, TOL)
+    assert np.array_equal(got.reshape(200, n), np.tile(got[:n], (200, 1)))
