@@ -231,7 +231,8 @@ std::vector<int> sorted_hap_order(const gphmm_batch *b, const gphmm_unit &un, bo
 
 UnitSched plan_unit_sharing(const gphmm_batch *b, const gphmm_unit &un, uint32_t hap_first_local, bool share, ChunkPlan &c,
                             int64_t sum_read_len, const std::vector<int> &full_order, int g_first, int g_count) {
-    constexpr uint32_t MIN_DEPTH = 32, SPACING = 32;
+    constexpr uint32_t SPACING = 32;
+    static const uint32_t MIN_DEPTH = getenv("GPHMM_MIN_DEPTH") ? (uint32_t)std::max(32, atoi(getenv("GPHMM_MIN_DEPTH"))) : 32u;  // tuning knob
     UnitSched us;
     memset(&us, 0, sizeof us);
     const int n = g_count;  // haplotypes of this group: full_order[g_first .. g_first + g_count)
