@@ -892,7 +892,8 @@ __global__ void __launch_bounds__(32) phmm_flat_f64_kernel(const KernelArgs g, c
             double pm = 0.0, px = 0.0;
             uint32_t x = 0;
             if (real) {
-                const uint32_t q = min((uint32_t)g.rd_q[ro + i - 1], (uint32_t)MAX_QUAL);  // range errors were flagged by the fp32 pass
+                uint32_t q = g.rd_q[ro + i - 1];
+                if (q > (uint32_t)MAX_QUAL) { atomicExch(g.err, 1); q = MAX_QUAL; }  // QualityUtils.java:157 (forced-fp64 mode has no fp32 pass to flag it)
                 x = g.rd_bases[ro + i - 1];
                 const double e = c_eps[q];
                 pm = 1.0 - e;

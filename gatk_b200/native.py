@@ -67,7 +67,12 @@ def load_library():
         return _LIB
     path = lib_path()
     if not os.path.exists(path):
-        raise GpuPhmmError(ERR_NO_DEVICE, "%s is missing: run `python -m gatk_b200.build` (or __graft_entry__.build())" % path)
+        # not built yet: compile it in-tree (nvcc, sm_100a).  There is still no fallback -- if this fails we raise.
+        try:
+            from . import build as _build
+            _build.build()
+        except Exception as e:
+            raise GpuPhmmError(ERR_NO_DEVICE, "%s is missing and could not be built (%s): run `python -m gatk_b200.build`" % (path, e))
     L = ctypes.CDLL(path)
     L.gphmm_abi_version.restype = ctypes.c_int
     L.gphmm_device_count.restype = ctypes.c_int

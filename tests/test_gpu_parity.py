@@ -225,6 +225,12 @@ def test_error_conventions(hmm):
     assert e.value.code == native.ERR_INVALID_ARG
     # the handle stays usable after an error
     _check(hmm.compute(b), oracle_batch(b), TOL)
+    # same conventions without an fp32 pass (--native-pair-hmm-use-double-precision)
+    with GpuPhmm(force_fp64=True) as h64:
+        for broken in (bad, bad2):
+            with pytest.raises(native.GpuPhmmError) as e:
+                h64.compute(broken)
+            assert e.value.code == native.ERR_BAD_QUAL
 
 
 def test_async_queue_and_prepared(hmm):
