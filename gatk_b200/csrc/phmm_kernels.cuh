@@ -4,11 +4,11 @@
 // (reference: src/main/java/org/broadinstitute/hellbender/utils/pairhmm/LoglessPairHMM.java:20-68,
 // priors :79-93, transitions PairHMMModel.java:107-117) but laid out for a GPU warp:
 //
-//  * One warp = one task = one read against the back-to-back stream of all haplotypes of its
-//    region.  Lane l owns K consecutive read rows (l*K+1 .. l*K+K); their M/I/D state lives in
-//    registers.  The warp sweeps the haplotype stream one column per step; lane l works on
-//    column (step - l), so every step hands the last row of each lane to the next lane with three
-//    __shfl_up_sync -- the anti-diagonal wavefront.
+//  * One warp = one task = one read against a back-to-back stream of haplotypes of its region.
+//    Lane l owns K consecutive read rows (l*K+1 .. l*K+K); their M/I/D state lives in registers.
+//    The warp sweeps the stream one column per step; lane l works on column (step - l), so every
+//    step hands the last row of each lane to the next lane with three shuffles -- the anti-diagonal
+//    wavefront.
 //  * The recurrence is re-scaled so a cell costs 6 FP instructions (DESIGN.md "Kernel recurrence"):
 //        I~ = I / tMI_i ,  D~ = D / tMD_i
 //        M[i][j]  = prior(i,j) * ( a_i*M[i-1][j-1] + b_i*I~[i-1][j-1] + c_i*D~[i-1][j-1] )
@@ -17,13 +17,20 @@
 //    with a=tMM_i, b=tIM_i*tMI_{i-1}, c=tIM_i*tMD_{i-1}, g=tII_i*tMI_{i-1}/tMI_i, tMI_0=tMD_0=1.
 //  * prior(i,j) comes from a per-task shared-memory table indexed by the haplotype code of the
 //    column: one 16-byte LDS returns the priors of 4 (fp32) / 2 (fp64) rows of the lane.
-//  * Rows below the read are pad rows (a=b=c=tDD=0, prior=0, g=tMI_R then 1): they carry
-//    (M+I)[R][j] down to the last row of the last lane, which adds it to the haplotype's sum.
-//  * Haplotypes are separated by an END column (prior 0): M and I~ vanish there by themselves, D~ is
-//    zeroed, lane 31 flushes the finished haplotype's sum.  No pipeline drain between haplotypes.
-//  * STRIPED kernels cover reads longer than 32*K-1 rows in several passes; the last row of a pass
-//    is parked in a per-CTA boundary buffer in global memory (L2 resident) and fed to lane 0 of the
-//    next pass.
+//  * Haplotypes are separated by an END column (prior 0): M and I~ vanish there by themselves.  There is no
+//    pipeline drain between haplotypes.
+//
+// Kernels in this file:
+//   phmm_forward_kernel<T,K,STRIPED>  general reference kernel: explicit lane-0 selects, running sum carried down pad
+//                                     rows, reads of any length in strips.  Used for reads of 255+ bases (fp32) and for
+//                                     the fp64 redo of reads that are not flat-quality.
+//   phmm_fast_f32_kernel<K>           per-base qualities, reads <= 254 bases: rotation hand-off, accumulator row,
+//                                     branch-free step loop, host-planned schedule with haplotype-prefix sharing.
+//   phmm_flat_f32_kernel<K>           the same for reads with flat insertion/deletion/GCP qualities: transition
+//                                     coefficients are kernel parameters (constant / uniform-register operands).
+//   phmm_flat_f64_kernel              fp64 redo of flat-quality reads (one read x one haplotype per task).
+//   phmm_classify_kernel              per read: flat-quality class or general.
+//   phmm_epilogue_f32 / _rescue       raw sums -> log10 likelihoods; builds / consumes the fp64 redo list.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
