@@ -444,3 +444,24 @@ def test_many_flat_quality_classes(hmm):
     got = hmm.compute(big)
     _check(got[:n], want, TOL)
     assert np.array_equal(got.reshape(200, n), np.tile(got[:n], (200, 1)))
+
+
+def test_full_size_config2_sample_against_oracle(hmm):
+    # BASELINE.json configs[1] at full size (10 000 regions, ~6 M pairs, 5.8e11 cells): every output is a valid
+    # log10 probability, the staged and the device-resident paths agree bit for bit, and a random sample of whole
+    # regions matches the double-precision oracle.
+    b = synth.config2(10000)
+    got = hmm.compute(b)
+    assert got.shape == (b.pairs(),)
+    assert np.all(np.isfinite(got)) and np.all(got <= 1e-9)
+    p = hmm.prepare(b)
+    res = np.full(b.n_out, np.nan)
+    hmm.run_prepared(p, res)
+    hmm.release_prepared(p)
+    assert np.array_equal(res, got)
+    pick = np.random.default_rng(12).choice(len(b.units), 24, replace=False)
+    sub = Batch(b.read_bases, b.base_q, b.ins_q, b.del_q, b.gcp, b.read_off, b.hap_bases, b.hap_off, b.units[pick])
+    want = oracle_batch(sub)
+    for u in sub.units:
+        lo = int(u["out_off"]); n = int((u["read_end"] - u["read_begin"]) * (u["hap_end"] - u["hap_begin"]))
+        assert np.abs(got[lo:lo + n] - want[lo:lo + n]).max() <= TOL
