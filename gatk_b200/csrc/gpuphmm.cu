@@ -115,8 +115,8 @@ struct PinBuf {
 
 constexpr int N_SLOTS = 3;         // chunks in flight per device: one computing, one finishing (epilogue/D2H), one being staged
 constexpr int N_FP32_BUCKETS = 9;  // K = 1..8 plain, bucket 8 = striped K=8 (reads of 256+ bases)
-constexpr int N_AUX = N_FP32_BUCKETS + 8 * MAX_FLAT_CLASSES;  // side streams: general buckets + flat (class, bucket)
-constexpr int N_COUNTERS = 64;     // [0..8] general fp32 buckets, [9] fp64 queue, [10] n_rescue, [11] forced fp64 queue,
+constexpr int N_AUX = N_FP32_BUCKETS + 8 * (MAX_FLAT_CLASSES + MAX_SYM_CLASSES);  // side streams: general buckets + flat (class, bucket)
+constexpr int N_COUNTERS = 128;    // [0..8] general fp32 buckets, [9] fp64 queue, [10] n_rescue, [11] forced fp64 queue,
                                    // [16 + 8*c + k] flat-quality kernels: class c, bucket k
 
 // Host-side plan of one device chunk: which units, and every metadata array the kernels need.
@@ -143,6 +143,8 @@ struct ChunkPlan {
     int64_t computed_columns = 0;          // haplotype columns the fast kernels really sweep (after prefix sharing)
     int n_classes = 0;                     // flat-quality classes sampled from the chunk's reads
     uint8_t class_qi[MAX_FLAT_CLASSES], class_qd[MAX_FLAT_CLASSES], class_qc[MAX_FLAT_CLASSES];
+    int n_sym = 0;                         // symmetric-quality classes (ins == del per base, flat gcp): their gcp values
+    uint8_t sym_qc[MAX_SYM_CLASSES];
 };
 
 int ceil_log2(uint32_t v) {
@@ -379,19 +381,37 @@ void plan_chunk(const gphmm_batch *b, int64_t u0, int64_t u1, bool force_fp64, b
     c.read_off.resize(n_span + 1);
     for (int64_t r = 0; r <= n_span; ++r) c.read_off[r] = (uint32_t)(b->read_off[c.r_lo + r] - c.base_lo);
 
-    // flat-quality classes: (ins, del, gcp) triples seen on the first base of a sample of the chunk's reads; the
-    // device decides per read whether it really is flat (phmm_classify_kernel)
+    // quality classes from a sample of the chunk's reads: flat (one (ins, del, gcp) triple on every base) and
+    // symmetric (ins == del per base, flat gcp).  The device decides per read which class it really belongs to
+    // (phmm_classify_kernel); a class that is missed here only means those reads take the general kernel.
     c.n_classes = 0;
+    c.n_sym = 0;
     if (!force_fp64 && n_span > 0) {
         const int64_t stride = std::max<int64_t>(1, n_span / 256);
-        for (int64_t r = 0; r < n_span && c.n_classes < MAX_FLAT_CLASSES; r += stride) {
-            const int64_t o = b->read_off[c.r_lo + r];
-            if (b->read_off[c.r_lo + r + 1] == o) continue;
+        for (int64_t r = 0; r < n_span; r += stride) {
+            const int64_t o = b->read_off[c.r_lo + r], e = b->read_off[c.r_lo + r + 1];
+            if (e == o) continue;
             const uint8_t qi = b->ins_q[o], qd = b->del_q[o], qc = b->gcp[o];
             if (qi > 127 || qd > 127 || qc > 127) continue;
-            bool seen = false;
-            for (int k = 0; k < c.n_classes; ++k) seen = seen || (c.class_qi[k] == qi && c.class_qd[k] == qd && c.class_qc[k] == qc);
-            if (!seen) { c.class_qi[c.n_classes] = qi; c.class_qd[c.n_classes] = qd; c.class_qc[c.n_classes] = qc; ++c.n_classes; }
+            bool flat = true, sym = true;
+            for (int64_t i = o; i < e; ++i) {
+                flat = flat && b->ins_q[i] == qi && b->del_q[i] == qd && b->gcp[i] == qc;
+                sym = sym && b->ins_q[i] == b->del_q[i] && b->gcp[i] == qc && b->ins_q[i] <= SYM_MAX_GAP_QUAL;
+            }
+            if (flat) {
+                bool seen = false;
+                for (int k = 0; k < c.n_classes; ++k) seen = seen || (c.class_qi[k] == qi && c.class_qd[k] == qd && c.class_qc[k] == qc);
+                if (seen) continue;
+                if (c.n_classes < MAX_FLAT_CLASSES) {
+                    c.class_qi[c.n_classes] = qi; c.class_qd[c.n_classes] = qd; c.class_qc[c.n_classes] = qc; ++c.n_classes;
+                    continue;
+                }
+            }
+            if (sym) {  // includes flat reads that found no free flat class
+                bool seen = false;
+                for (int k = 0; k < c.n_sym; ++k) seen = seen || c.sym_qc[k] == qc;
+                if (!seen && c.n_sym < MAX_SYM_CLASSES) c.sym_qc[c.n_sym++] = qc;
+            }
         }
     }
 
@@ -599,9 +619,9 @@ KernelInfo fp32_kernel(int bucket, int n_codes) {
         default: return kernel_info<float, 8, true>(n_codes);  // reads of 255+ bases: striped
     }
 }
-template <int K> KernelInfo flat_kernel_info(int n_codes) {
+template <int K, bool SYM> KernelInfo flat_kernel_info(int n_codes) {
     KernelInfo ki;
-    auto fn = phmm_flat_f32_kernel<K>;
+    auto fn = phmm_flat_f32_kernel<K, SYM>;
     ki.fn = (const void *)fn;
     ki.smem = prior_table_bytes<float, K>(n_codes);
     if (ki.smem > 48 * 1024) CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ki.smem));
@@ -613,14 +633,27 @@ template <int K> KernelInfo flat_kernel_info(int n_codes) {
 
 KernelInfo flat_kernel(int bucket, int n_codes) {
     switch (bucket) {
-        case 0: return flat_kernel_info<1>(n_codes);
-        case 1: return flat_kernel_info<2>(n_codes);
-        case 2: return flat_kernel_info<3>(n_codes);
-        case 3: return flat_kernel_info<4>(n_codes);
-        case 4: return flat_kernel_info<5>(n_codes);
-        case 5: return flat_kernel_info<6>(n_codes);
-        case 6: return flat_kernel_info<7>(n_codes);
-        default: return flat_kernel_info<8>(n_codes);
+        case 0: return flat_kernel_info<1, false>(n_codes);
+        case 1: return flat_kernel_info<2, false>(n_codes);
+        case 2: return flat_kernel_info<3, false>(n_codes);
+        case 3: return flat_kernel_info<4, false>(n_codes);
+        case 4: return flat_kernel_info<5, false>(n_codes);
+        case 5: return flat_kernel_info<6, false>(n_codes);
+        case 6: return flat_kernel_info<7, false>(n_codes);
+        default: return flat_kernel_info<8, false>(n_codes);
+    }
+}
+
+KernelInfo sym_kernel(int bucket, int n_codes) {
+    switch (bucket) {
+        case 0: return flat_kernel_info<1, true>(n_codes);
+        case 1: return flat_kernel_info<2, true>(n_codes);
+        case 2: return flat_kernel_info<3, true>(n_codes);
+        case 3: return flat_kernel_info<4, true>(n_codes);
+        case 4: return flat_kernel_info<5, true>(n_codes);
+        case 5: return flat_kernel_info<6, true>(n_codes);
+        case 6: return flat_kernel_info<7, true>(n_codes);
+        default: return flat_kernel_info<8, true>(n_codes);
     }
 }
 
@@ -644,6 +677,7 @@ struct Stats {
 
 constexpr int FLAT_KEY = 16;      // Device::info key of the flat-quality kernel of bucket k is FLAT_KEY + k
 constexpr int FLAT_F64_KEY = 32;  // ... and of phmm_flat_f64_kernel
+constexpr int SYM_KEY = 48;       // symmetric-quality kernel of bucket k is SYM_KEY + k
 
 // One CTA per resident slot (the occupancy already includes the headroom of reserve_headroom()).
 inline uint32_t persistent_grid(uint32_t n_tasks, int n_sms, int ctas_per_sm) {
@@ -660,7 +694,8 @@ struct Device {
         if (it == kinfo.end())
             it = kinfo.emplace(key, bucket < N_FP32_BUCKETS ? fp32_kernel(bucket, n_codes)
                                     : bucket == N_FP32_BUCKETS ? fp64_kernel(n_codes)
-                                    : bucket == FLAT_F64_KEY ? flat_fp64_kernel(n_codes) : flat_kernel(bucket - FLAT_KEY, n_codes)).first;
+                                    : bucket == FLAT_F64_KEY ? flat_fp64_kernel(n_codes)
+                                    : bucket >= SYM_KEY ? sym_kernel(bucket - SYM_KEY, n_codes) : flat_kernel(bucket - FLAT_KEY, n_codes)).first;
         return it->second;
     }
     cudaStream_t streams[N_SLOTS] = {nullptr};
@@ -871,6 +906,8 @@ int launch_chunk(Device &dev, DeviceChunk &dc, const ChunkPlan &c, cudaStream_t 
             ca.read_class = (uint8_t *)(work + dc.off_class);
             ca.n_classes = (uint32_t)c.n_classes;
             for (int k = 0; k < c.n_classes; ++k) { ca.qi[k] = c.class_qi[k]; ca.qd[k] = c.class_qd[k]; ca.qc[k] = c.class_qc[k]; }
+            ca.n_sym = (uint32_t)c.n_sym;
+            for (int k = 0; k < c.n_sym; ++k) ca.sym_qc[k] = c.sym_qc[k];
             if (n_span_reads) {
                 phmm_classify_kernel<<<std::min<uint32_t>((n_span_reads + 3) / 4, 148 * 16), 128, 0, st>>>(ca);
                 CK(cudaGetLastError());
@@ -905,6 +942,8 @@ int launch_chunk(Device &dev, DeviceChunk &dc, const ChunkPlan &c, cudaStream_t 
                 need += (size_t)persistent_grid(n, dev.n_sms, dev.info(k, c.n_codes).ctas_per_sm) * SLAB_PER_CTA;
                 for (int cl = 0; cl < c.n_classes; ++cl)
                     need += (size_t)persistent_grid(n, dev.n_sms, dev.info(FLAT_KEY + k, c.n_codes).ctas_per_sm) * SLAB_PER_CTA;
+                for (int cl = 0; cl < c.n_sym; ++cl)
+                    need += (size_t)persistent_grid(n, dev.n_sms, dev.info(SYM_KEY + k, c.n_codes).ctas_per_sm) * SLAB_PER_CTA;
             }
             dc.snap.reserve(std::max<size_t>(need, 16));
         }
@@ -956,6 +995,25 @@ int launch_chunk(Device &dev, DeviceChunk &dc, const ChunkPlan &c, cudaStream_t 
                     slab_cursor += (size_t)persistent_grid(n, dev.n_sms, dev.info(FLAT_KEY + k, c.n_codes).ctas_per_sm) * SLAB_PER_CTA;
                     void *args[] = {&ka, &fc};
                     launch_on(dev.info(FLAT_KEY + k, c.n_codes), n, N_FP32_BUCKETS + 8 * cl + k, args);
+                }
+                for (int cl = 0; cl < c.n_sym; ++cl) {
+                    // symmetric-quality reads (ins == del per base, flat gcp): b = tIM, g = d = eps(gcp), tmi = kappa
+                    FlatCoef fc;
+                    const int qc = c.sym_qc[cl];
+                    const double ec = tb.eps[qc];
+                    fc.a = 0.f; fc.c = 0.f;
+                    fc.b = (float)(1.0 - ec);
+                    fc.g = (float)ec;
+                    fc.d = (float)ec;
+                    fc.tmi = 1.f / 1024.f;  // kappa: exact power of two; M^ = M eps/kappa ~ M/10 at Q40 and (true sum)/kappa never overflows
+                    fc.tim = 1.f;
+                    fc.class_id = (uint32_t)(MAX_FLAT_CLASSES + cl);
+                    fc.qi = 0; fc.qd = 0; fc.qc = qc;
+                    ka.counter = counters + 16 + 8 * (MAX_FLAT_CLASSES + cl) + k;
+                    ka.snap = (float *)((uint8_t *)dc.snap.p + slab_cursor);
+                    slab_cursor += (size_t)persistent_grid(n, dev.n_sms, dev.info(SYM_KEY + k, c.n_codes).ctas_per_sm) * SLAB_PER_CTA;
+                    void *args[] = {&ka, &fc};
+                    launch_on(dev.info(SYM_KEY + k, c.n_codes), n, N_FP32_BUCKETS + 8 * (MAX_FLAT_CLASSES + cl) + k, args);
                 }
             }
             ka.counter = counters + k;

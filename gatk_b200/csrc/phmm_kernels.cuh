@@ -46,6 +46,8 @@ constexpr float RESCUE_THRESHOLD_F32 = 1e-28f;
 constexpr int STREAM_PAD = 32;            // NULL codes around every haplotype stream (pipeline fill / drain)
 constexpr uint8_t CLASS_GENERAL = 0xff;   // read_class of reads without a flat-quality class
 constexpr int MAX_FLAT_CLASSES = 4;
+constexpr int MAX_SYM_CLASSES = 4;        // read_class MAX_FLAT_CLASSES + k: ins == del per base, flat gcp (PCR indel model)
+constexpr uint32_t SYM_MAX_GAP_QUAL = 70; // gap-open quals above this go to the general kernel (M^ = M * 2^10 * eps would lose range)
 
 // D[0][j] of the reference is 2^1020/H (LoglessPairHMM.java:8,31).  The kernels use a power of two
 // 2^(BASE - ceil(log2 H)) <= that leaves headroom for the scaled states I~ and D~.
@@ -166,7 +168,7 @@ __global__ void __launch_bounds__(32) phmm_forward_kernel(const KernelArgs g)
         const uint32_t ro = g.read_off[t.read];
         const int R = (int)(g.read_off[t.read + 1] - ro);
         // fp64 rescue lists: flat-quality reads of up to 254 bases belong to phmm_flat_f64_kernel
-        if (g.read_class != nullptr && g.read_class[t.read] != CLASS_GENERAL && R <= 254) continue;
+        if (g.read_class != nullptr && g.read_class[t.read] < MAX_FLAT_CLASSES && R <= 254) continue;
         const int P = (int)t.stream_len;
         const uint8_t *__restrict__ stream = g.streams + t.stream_off;
         const T c0 = (T)scalbn(1.0, t.c0_exp);
@@ -582,6 +584,8 @@ struct ClassifyArgs {
     uint8_t *read_class;
     uint32_t n_classes;
     uint8_t qi[MAX_FLAT_CLASSES], qd[MAX_FLAT_CLASSES], qc[MAX_FLAT_CLASSES];
+    uint32_t n_sym;                  // symmetric classes: ins == del on every base, flat gcp == sym_qc[k]
+    uint8_t sym_qc[MAX_SYM_CLASSES];
 };
 
 // one warp per read: flat iff every base carries the class's (ins, del, gcp) triple
@@ -594,20 +598,29 @@ __global__ void __launch_bounds__(128) phmm_classify_kernel(const ClassifyArgs a
         uint8_t cls = CLASS_GENERAL;
         if (R > 0) {
             const uint32_t qi0 = a.rd_i[ro], qd0 = a.rd_d[ro], qc0 = a.rd_c[ro];
-            bool same = true;
-            for (uint32_t i = lane; i < R; i += 32) same = same && a.rd_i[ro + i] == qi0 && a.rd_d[ro + i] == qd0 && a.rd_c[ro + i] == qc0;
-            if (__all_sync(0xffffffffu, same))
+            bool same = true, sym = true;
+            for (uint32_t i = lane; i < R; i += 32) {
+                const uint32_t qi = a.rd_i[ro + i], qd = a.rd_d[ro + i], qc = a.rd_c[ro + i];
+                same = same && qi == qi0 && qd == qd0 && qc == qc0;
+                sym = sym && qi == qd && qc == qc0 && qi <= SYM_MAX_GAP_QUAL;
+            }
+            if (__all_sync(0xffffffffu, same)) {
                 for (uint32_t k = 0; k < a.n_classes; ++k)
                     if (a.qi[k] == qi0 && a.qd[k] == qd0 && a.qc[k] == qc0) cls = (uint8_t)k;
+            }
+            if (cls == CLASS_GENERAL && __all_sync(0xffffffffu, sym)) {
+                for (uint32_t k = 0; k < a.n_sym; ++k)
+                    if (a.sym_qc[k] == qc0) cls = (uint8_t)(MAX_FLAT_CLASSES + k);
+            }
         }
         if (lane == 0) a.read_class[r] = cls;
     }
 }
 
-template <int K, int SLOT, bool CHECKED>
-__device__ __forceinline__ void flat_step(FastState<K> &st, const FlatCoef &f, float B0, float G0, float E0, uint32_t tab_lane,
-                                          int src_lane, int lane, int acc_lane, float *sums_task, float *slab, int snap_pos,
-                                          int snap_slot, int end_restore, uint32_t end_out)
+template <int K, int SLOT, bool CHECKED, bool SYM>
+__device__ __forceinline__ void flat_step(FastState<K> &st, const FlatCoef &f, const float (&A)[K], const float (&C)[K], float B0, float G0,
+                                          float E0, uint32_t tab_lane, int src_lane, int lane, int acc_lane, float *sums_task,
+                                          float *slab, int snap_pos, int snap_slot, int end_restore, uint32_t end_out)
 {
     constexpr int NV = (K + 3) / 4;
     constexpr unsigned FULL = 0xffffffffu;
@@ -628,16 +641,17 @@ __device__ __forceinline__ void flat_step(FastState<K> &st, const FlatCoef &f, f
     }
     float Mn[K];
     {
-        float u = __fmaf_rn(f.c, st.dgd, E0);
+        // SYM: the coefficients of M^ and D^ are per-row registers (A, C); everything else stays a constant operand
+        float u = __fmaf_rn(SYM ? C[0] : f.c, st.dgd, E0);
         u = __fmaf_rn(B0, st.dgi, u);
-        u = __fmaf_rn(f.a, st.dgm, u);
+        u = __fmaf_rn(SYM ? A[0] : f.a, st.dgm, u);
         Mn[0] = pr[0] * u;
     }
 #pragma unroll
     for (int k = 1; k < K; ++k) {
-        float u = f.c * st.D[k - 1];
+        float u = (SYM ? C[k] : f.c) * st.D[k - 1];
         u = __fmaf_rn(f.b, st.I[k - 1], u);
-        u = __fmaf_rn(f.a, st.M[k - 1], u);
+        u = __fmaf_rn(SYM ? A[k] : f.a, st.M[k - 1], u);
         Mn[k] = pr[k] * u;
     }
 #pragma unroll
@@ -665,39 +679,40 @@ __device__ __forceinline__ void flat_step(FastState<K> &st, const FlatCoef &f, f
     st.y = y_next;
 }
 
-template <int K, int SLOT>
-__device__ __forceinline__ void flat_sweep(FastState<K> &st, const FlatCoef &f, float B0, float G0, float E0, uint32_t tab_lane,
-                                           int src_lane, int lane, int acc_lane, float *sums_task, float *slab, const Segment *segs,
-                                           uint32_t n_segs)
+template <int K, int SLOT, bool SYM>
+__device__ __forceinline__ void flat_sweep(FastState<K> &st, const FlatCoef &f, const float (&A)[K], const float (&C)[K], float B0, float G0,
+                                           float E0, uint32_t tab_lane, int src_lane, int lane, int acc_lane, float *sums_task,
+                                           float *slab, const Segment *segs, uint32_t n_segs)
 {
     int step = 1;
     for (uint32_t sg = 0; sg < n_segs; ++sg) {
         const Segment seg = segs[sg];
 #pragma unroll 2
         for (uint32_t s = 0; s < seg.n_free; ++s)
-            flat_step<K, SLOT, false>(st, f, B0, G0, E0, tab_lane, src_lane, lane, acc_lane, sums_task, slab, 0, 0, 0, 0);
+            flat_step<K, SLOT, false, SYM>(st, f, A, C, B0, G0, E0, tab_lane, src_lane, lane, acc_lane, sums_task, slab, 0, 0, 0, 0);
         step += (int)seg.n_free;
         st.p = step - lane;
 #pragma unroll 1
         for (uint32_t s = 0; s < seg.n_chk; ++s)
-            flat_step<K, SLOT, true>(st, f, B0, G0, E0, tab_lane, src_lane, lane, acc_lane, sums_task, slab, seg.snap_pos, seg.snap_slot,
-                                     seg.end_restore, seg.end_out);
+            flat_step<K, SLOT, true, SYM>(st, f, A, C, B0, G0, E0, tab_lane, src_lane, lane, acc_lane, sums_task, slab, seg.snap_pos,
+                                          seg.snap_slot, seg.end_restore, seg.end_out);
         step += (int)seg.n_chk;
     }
 }
 
-template <int K, int SLOT>
-__device__ __forceinline__ void flat_dispatch(int slot, FastState<K> &st, const FlatCoef &f, float B0, float G0, float E0, uint32_t tab_lane,
-                                              int src_lane, int lane, int acc_lane, float *sums_task, float *slab, const Segment *segs,
-                                              uint32_t n_segs)
+template <int K, int SLOT, bool SYM>
+__device__ __forceinline__ void flat_dispatch(int slot, FastState<K> &st, const FlatCoef &f, const float (&A)[K], const float (&C)[K],
+                                              float B0, float G0, float E0, uint32_t tab_lane, int src_lane, int lane, int acc_lane,
+                                              float *sums_task, float *slab, const Segment *segs, uint32_t n_segs)
 {
-    if (slot == SLOT) flat_sweep<K, SLOT>(st, f, B0, G0, E0, tab_lane, src_lane, lane, acc_lane, sums_task, slab, segs, n_segs);
-    else if constexpr (SLOT + 1 < K) flat_dispatch<K, SLOT + 1>(slot, st, f, B0, G0, E0, tab_lane, src_lane, lane, acc_lane, sums_task, slab, segs, n_segs);
+    if (slot == SLOT) flat_sweep<K, SLOT, SYM>(st, f, A, C, B0, G0, E0, tab_lane, src_lane, lane, acc_lane, sums_task, slab, segs, n_segs);
+    else if constexpr (SLOT + 1 < K)
+        flat_dispatch<K, SLOT + 1, SYM>(slot, st, f, A, C, B0, G0, E0, tab_lane, src_lane, lane, acc_lane, sums_task, slab, segs, n_segs);
 }
 
 // 28 one-warp CTAs per SM (the shared-memory limit of the K=8 prior table) need <= 73 registers per thread
-template <int K>
-__global__ void __launch_bounds__(32, 28) phmm_flat_f32_kernel(const KernelArgs g, const FlatCoef f)
+template <int K, bool SYM>
+__global__ void __launch_bounds__(32, SYM ? 22 : 28) phmm_flat_f32_kernel(const KernelArgs g, const FlatCoef f)
 {
     constexpr int NV = (K + 3) / 4;
     constexpr unsigned FULL = 0xffffffffu;
@@ -722,6 +737,7 @@ __global__ void __launch_bounds__(32, 28) phmm_flat_f32_kernel(const KernelArgs 
         const int R = (int)(g.read_off[t.read + 1] - ro);  // 1 <= R <= 32 * K - 1 (flat reads are never empty)
         const float c0 = (float)scalbn(1.0, t.c0_exp);
 
+        float A[K], C[K];  // SYM only: per-row coefficients of M^ and D^
         __syncwarp();
 #pragma unroll
         for (int k = 0; k < K; ++k) {
@@ -729,13 +745,32 @@ __global__ void __launch_bounds__(32, 28) phmm_flat_f32_kernel(const KernelArgs 
             const bool real = i <= R;
             float pmf = 0.f, pxf = 0.f;
             uint32_t x = 0;
+            A[k] = 0.f; C[k] = 0.f;
             if (real) {
                 uint32_t q = g.rd_q[ro + i - 1];
                 x = g.rd_bases[ro + i - 1];
                 if (q > (uint32_t)MAX_QUAL) { atomicExch(g.err, 1); q = MAX_QUAL; }
                 const double e = c_eps[q];
-                pmf = (float)(1.0 - e);
-                pxf = (float)(g.tristate_off ? e : e / 3.0);
+                double pm = 1.0 - e, px = g.tristate_off ? e : e / 3.0;
+                if (SYM) {
+                    // ins == del = e_i on every base, flat gcp (DESIGN.md "Symmetric-quality kernel"):
+                    //   M^_i = M_i eps_{i+1}/kappa,  I^_i = I_i/kappa,  D^_i = D_i eps_{i+1}/(eps_i kappa),  eps_{R+1} := kappa
+                    //   M^_i = (p_ij eps_{i+1}) (A_i M^_{i-1} + T I^_{i-1} + C_i D^_{i-1}),  A_i = tMM_i/eps_i,  C_i = T eps_{i-1}/eps_i
+                    //   I^_i = M^_up + Gc I^_up,  D^_i = M^_left + Gc D^_left,  sum = M^_R + kappa I^_R.
+                    // kappa = f.tmi = 2^-10 is a pure scale: the bracket above is (true value)/kappa <= 2^10 c0 < FLT_MAX.
+                    const uint32_t qe = min((uint32_t)g.rd_i[ro + i - 1], 127u);
+                    const double kappa = (double)f.tmi, T = (double)f.b;
+                    const double eps_i = c_eps[qe];
+                    const double eps_prev = i > 1 ? c_eps[min((uint32_t)g.rd_i[ro + i - 2], 127u)] : 1.0;
+                    const double eps_next = i < R ? c_eps[min((uint32_t)g.rd_i[ro + i], 127u)] : kappa;
+                    A[k] = (float)(__ldg(g.m2m + ((qe * (qe + 1)) >> 1) + qe) / eps_i);
+                    C[k] = (float)(T * eps_prev / eps_i);
+                    double scale = eps_next;
+                    if (i == 1) scale *= T / kappa;  // row 1: u is the injected constant E0 = c0 = kappa/T * (C_1 D^_0)
+                    pm *= scale; px *= scale;
+                }
+                pmf = (float)pm;
+                pxf = (float)px;
             }
             for (int y = 0; y < n_codes; ++y) {
                 float v = 0.f;
@@ -758,14 +793,14 @@ __global__ void __launch_bounds__(32, 28) phmm_flat_f32_kernel(const KernelArgs 
         const UnitSched us = g.unit_sched[t.unit];
         st.sp = g.sstreams + us.sstream_off - lane;
         st.y = ldg_u8(st.sp);
-        // slot 0: lane 0 holds row 1 (virtual row 0 above it: M = I~ = 0, c*D~ = tIM*c0)
+        // slot 0: lane 0 holds row 1 (virtual row 0 above it: M = I~ = 0, c*D~ = tIM*c0; SYM: f.tim = 1, the rest is in row 1's table)
         const float B0 = lane == 0 ? 0.f : f.b;
         const float G0 = lane == 0 ? 0.f : f.g;
         const float E0 = lane == 0 ? f.tim * c0 : 0.f;
         const int acc_lane = (R - 1) / K, acc_slot = (R - 1) % K;
         float *const slab = g.snap + (size_t)blockIdx.x * ((MAX_SNAP_SLOTS + 1) * SLOT_STRIDE) + lane * SNAP_REGS;
         snap_save<K>(st, slab, ZERO_SLOT);  // the pass-start state (all zero), restored at every END that begins a fresh pass
-        flat_dispatch<K, 0>(acc_slot, st, f, B0, G0, E0, tab_lane, src_lane, lane, acc_lane, sums + t.out_base, slab,
+        flat_dispatch<K, 0, SYM>(acc_slot, st, f, A, C, B0, G0, E0, tab_lane, src_lane, lane, acc_lane, sums + t.out_base, slab,
                             g.segments + us.seg_first, us.n_segs);
     }
 }

@@ -446,6 +446,47 @@ def test_many_flat_quality_classes(hmm):
     assert np.array_equal(got.reshape(200, n), np.tile(got[:n], (200, 1)))
 
 
+def test_symmetric_quality_reads(hmm):
+    # per-base gap-open penalties with ins == del and a flat gcp (what the PCR indel model produces,
+    # PairHMMLikelihoodCalculationEngine.java:394-416 / StandardPairHMMInputScoreImputator) take the symmetric-quality
+    # kernel; several gcp classes, the overflow to the general kernel, extreme quals and prefix sharing on/off
+    rng = np.random.default_rng(78)
+    L = np.frombuffer(b"ACGT", dtype=np.uint8)
+    hap = L[rng.integers(0, 4, 320)]
+    gcps = [10, 10, 10, 12, 8, 20, 3, 10]   # 6 distinct values: more than the kernel has classes
+    reads = []
+    for k in range(90):
+        R = int(rng.integers(1, 300))
+        off = int(rng.integers(0, 320 - R + 1))
+        rd = hap[off:off + R].copy()
+        rd[R // 3] = ord("T") if rd[R // 3] != ord("T") else ord("A")
+        q = np.clip(rng.normal(30, 8, R), 6, 41).astype(np.uint8)
+        g = np.full(R, 40, np.uint8)
+        u = rng.random(R)
+        g[u < 0.3] = rng.integers(1, 60, int((u < 0.3).sum())).astype(np.uint8)
+        if k % 9 == 0:
+            g[:] = rng.integers(0, 128, R).astype(np.uint8)   # the whole legal range, quality 0 included
+        if k % 11 == 5:
+            g[0] = 2
+            g[-1] = 127
+        reads.append((rd, q, g, g.copy(), const_quals(R, gcps[k % len(gcps)])))
+    haps = [hap.tobytes(), hap[:250].tobytes(), hap[10:].tobytes(), hap[::-1].copy().tobytes(), hap[:33].tobytes()]
+    one = Batch.single_unit(reads, haps)
+    want = oracle_batch(one)
+    _check(hmm.compute(one), want, TOL)
+    big, n = _replicate(one, 200)
+    with GpuPhmm(no_prefix_sharing=True) as plain:
+        got = hmm.compute(big)
+        ref = plain.compute(big)
+    # bit-identical, except where the wild-quality reads overflow fp32 in one mode only (state left behind by the
+    # previous haplotype differs) and are redone in fp64: those agree to float rounding
+    differs = got != ref
+    assert differs.mean() < 0.005
+    assert not differs.any() or np.abs(got - ref)[differs].max() < 1e-5
+    _check(got[:n], want, TOL)
+    assert np.array_equal(got.reshape(200, n), np.tile(got[:n], (200, 1)))
+
+
 def test_full_size_config2_sample_against_oracle(hmm):
     # BASELINE.json configs[1] at full size (10 000 regions, ~6 M pairs, 5.8e11 cells): every output is a valid
     # log10 probability, the staged and the device-resident paths agree bit for bit, and a random sample of whole
