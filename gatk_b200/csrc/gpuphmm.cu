@@ -6,6 +6,7 @@
 // No CPU compute path exists here: every likelihood comes from the CUDA kernels in phmm_kernels.cuh.
 #include "../../include/gpuphmm.h"
 #include "phmm_kernels.cuh"
+#include "region_steps.cuh"
 
 #include <algorithm>
 #include <atomic>
@@ -143,6 +144,7 @@ struct ChunkPlan {
     int64_t computed_columns = 0;          // haplotype columns the fast kernels really sweep (after prefix sharing)
     int n_classes = 0;                     // flat-quality classes sampled from the chunk's reads
     uint8_t class_qi[MAX_FLAT_CLASSES], class_qd[MAX_FLAT_CLASSES], class_qc[MAX_FLAT_CLASSES];
+    uint32_t n_keep = 0;                   // region steps: keep flags of the chunk (sum of n_reads over its units)
     int n_sym = 0;                         // symmetric-quality classes (ins == del per base, flat gcp): their gcp values
     uint8_t sym_qc[MAX_SYM_CLASSES];
 };
@@ -367,7 +369,7 @@ UnitSched plan_unit_sharing(const gphmm_batch *b, const gphmm_unit &un, uint32_t
 // each unit's haplotypes are split into groups and every (read, group) pair becomes a task of its own.
 constexpr int64_t TARGET_TASKS = 148 * 28 * 2;
 
-void plan_chunk(const gphmm_batch *b, int64_t u0, int64_t u1, bool force_fp64, bool share, ChunkPlan &c) {
+void plan_chunk(const gphmm_batch *b, int64_t u0, int64_t u1, bool force_fp64, bool share, ChunkPlan &c, bool pcr_hint = false) {
     c.u0 = u0; c.u1 = u1;
     c.r_lo = INT64_MAX; c.r_hi = 0;
     for (int64_t u = u0; u < u1; ++u) {
@@ -398,7 +400,7 @@ void plan_chunk(const gphmm_batch *b, int64_t u0, int64_t u1, bool force_fp64, b
                 flat = flat && b->ins_q[i] == qi && b->del_q[i] == qd && b->gcp[i] == qc;
                 sym = sym && b->ins_q[i] == b->del_q[i] && b->gcp[i] == qc && b->ins_q[i] <= SYM_MAX_GAP_QUAL;
             }
-            if (flat) {
+            if (flat && !(pcr_hint && qi == qd)) {  // the PCR indel model (region steps) will lower ins and del together
                 bool seen = false;
                 for (int k = 0; k < c.n_classes; ++k) seen = seen || (c.class_qi[k] == qi && c.class_qd[k] == qd && c.class_qc[k] == qc);
                 if (seen) continue;
@@ -424,7 +426,7 @@ void plan_chunk(const gphmm_batch *b, int64_t u0, int64_t u1, bool force_fp64, b
     c.n_codes = CODE_FIRST_BASE + 5;
 
     c.streams.clear(); c.hap_len.clear(); c.hap_stream_off.clear(); c.units.clear(); c.tasks.clear();
-    c.sstreams.clear(); c.pass_info.clear(); c.segments.clear(); c.unit_sched.clear(); c.skipped_cells = 0; c.computed_columns = 0;
+    c.sstreams.clear(); c.pass_info.clear(); c.segments.clear(); c.unit_sched.clear(); c.skipped_cells = 0; c.computed_columns = 0; c.n_keep = 0;
     c.n_pairs = 0; c.cells = 0; c.max_stream_len = 0; c.max_hap_len = 0;
     int64_t n_reads_with_work = 0;
     for (int64_t u = u0; u < u1; ++u)
@@ -445,7 +447,9 @@ void plan_chunk(const gphmm_batch *b, int64_t u0, int64_t u1, bool force_fp64, b
         d.hap_first = (uint32_t)c.hap_len.size();
         d.n_haps = nh;
         d.out_base = c.n_pairs;
-        d.pad0 = d.pad1 = 0;
+        d.ref_hap = -1;
+        d.keep_base = c.n_keep;
+        c.n_keep += nr;
         c.streams.insert(c.streams.end(), STREAM_PAD, (uint8_t)CODE_NULL);  // fill/drain codes of the fast kernels
         const uint32_t stream_off = (uint32_t)c.streams.size();
         uint32_t max_h = 1;
@@ -537,17 +541,18 @@ struct DeviceChunk {
     DevBuf bnd;     // boundary rows of striped kernels
     PinBuf h_meta;  // pinned image of meta
     PinBuf h_reads; // pinned bounce buffer when the caller's arrays are pageable
-    PinBuf h_out;   // pinned result buffer (out doubles + counters + err)
+    PinBuf h_out;   // pinned result buffer (out doubles + [keep flags] + counters + err)
+    PinBuf h_modq;  // region steps: pinned image of the modified base/ins/del qualities (only when the caller wants them)
     size_t read_stride = 0;
     size_t off_read_off = 0, off_streams = 0, off_hap_len = 0, off_hap_stream_off = 0, off_units = 0, off_tasks = 0, meta_bytes = 0;
-    size_t off_sstreams = 0, off_pass = 0, off_segs = 0, off_sched = 0;
+    size_t off_sstreams = 0, off_pass = 0, off_segs = 0, off_sched = 0, off_mapq = 0;
     DevBuf snap;    // snapshot slabs of the fast kernels (prefix sharing)
-    size_t off_sums = 0, off_out = 0, off_rtasks = 0, off_rsums = 0, off_counters = 0, off_err = 0, off_class = 0, work_bytes = 0;
+    size_t off_sums = 0, off_out = 0, off_rtasks = 0, off_rsums = 0, off_counters = 0, off_err = 0, off_class = 0, off_raw = 0, off_keep = 0, work_bytes = 0;
     cudaEvent_t ev_start = nullptr, ev_f32 = nullptr, ev_f64 = nullptr, ev_done = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join[N_AUX] = {nullptr};  // bucket kernels run on side streams
     bool busy = false;
     void release() {
-        reads.release(); meta.release(); work.release(); bnd.release(); snap.release(); h_meta.release(); h_reads.release(); h_out.release();
+        reads.release(); meta.release(); work.release(); bnd.release(); snap.release(); h_meta.release(); h_reads.release(); h_out.release(); h_modq.release();
         if (ev_start) cudaEventDestroy(ev_start);
         if (ev_f32) cudaEventDestroy(ev_f32);
         if (ev_f64) cudaEventDestroy(ev_f64);
@@ -758,11 +763,12 @@ bool is_pinned(const void *p) {
 struct RunOptions {
     bool force_fp64 = false;
     bool tristate_off = false;
+    const gphmm_region_steps *rs = nullptr;  // gphmm_compute_regions: the steps either side of the kernel
 };
 
 // Lay the chunk out on the device and copy its inputs (async on `st`).
 void upload_chunk(Device &dev, DeviceChunk &dc, const gphmm_batch *b, const ChunkPlan &c, cudaStream_t st, bool force_fp64,
-                  Stats &stats) {
+                  Stats &stats, const gphmm_region_steps *rs = nullptr) {
     const double t0 = now_ms();
     const size_t span = (size_t)(c.base_hi - c.base_lo);
     dc.read_stride = align_up(span, 16);
@@ -779,6 +785,7 @@ void upload_chunk(Device &dev, DeviceChunk &dc, const gphmm_batch *b, const Chun
     dc.off_pass = o; o = align_up(o + c.pass_info.size() * sizeof(PassInfo), 16);
     dc.off_segs = o; o = align_up(o + c.segments.size() * sizeof(Segment), 16);
     dc.off_sched = o; o = align_up(o + c.unit_sched.size() * sizeof(UnitSched), 16);
+    dc.off_mapq = o; o = align_up(o + (rs ? c.read_off.size() : 0), 16);
     dc.meta_bytes = std::max<size_t>(o, 16);
     dc.meta.reserve(dc.meta_bytes);
     dc.h_meta.reserve(dc.meta_bytes);
@@ -795,14 +802,23 @@ void upload_chunk(Device &dev, DeviceChunk &dc, const gphmm_batch *b, const Chun
     memcpy(hm + dc.off_pass, c.pass_info.data(), c.pass_info.size() * sizeof(PassInfo));
     memcpy(hm + dc.off_segs, c.segments.data(), c.segments.size() * sizeof(Segment));
     memcpy(hm + dc.off_sched, c.unit_sched.data(), c.unit_sched.size() * sizeof(UnitSched));
+    if (rs) {
+        if (c.r_hi > c.r_lo) memcpy(hm + dc.off_mapq, rs->mapq + c.r_lo, (size_t)(c.r_hi - c.r_lo));
+        if (rs->ref_hap) {
+            UnitDesc *ud = (UnitDesc *)(hm + dc.off_units);
+            for (int64_t u = c.u0; u < c.u1; ++u) ud[u - c.u0].ref_hap = rs->ref_hap[u];
+        }
+    }
     // work buffers
     const size_t np = std::max<uint32_t>(c.n_pairs, 1);
     o = 0;
     dc.off_sums = o; o = align_up(o + np * (force_fp64 ? 8 : 4), 16);
+    dc.off_raw = o; if (rs) o = align_up(o + np * 8, 16);  // region steps: raw read-major likelihoods; `out` is then the normalised matrix
     dc.off_out = o; o = align_up(o + np * 8, 16);
+    dc.off_keep = o; o = align_up(o + (rs ? std::max<uint32_t>(c.n_keep, 1) : 0), 16);
     dc.off_counters = o; o = align_up(o + N_COUNTERS * 4, 16);
     dc.off_err = o; o = align_up(o + 16, 16);
-    const size_t d2h_bytes = o;  // out | counters | err are contiguous and downloaded together
+    const size_t d2h_bytes = o - dc.off_out;  // out | [keep] | counters | err are contiguous and downloaded together
     dc.off_rtasks = o; o = align_up(o + (force_fp64 ? 0 : np * sizeof(Task)), 16);
     dc.off_rsums = o; o = align_up(o + (force_fp64 ? 0 : np * 8), 16);
     dc.off_class = o; o = align_up(o + c.read_off.size(), 16);
@@ -871,7 +887,7 @@ int launch_chunk(Device &dev, DeviceChunk &dc, const ChunkPlan &c, cudaStream_t 
     ea.hap_len = (const uint32_t *)(meta + dc.off_hap_len);
     ea.hap_stream_off = (const uint32_t *)(meta + dc.off_hap_stream_off);
     ea.sums = work + dc.off_sums;
-    ea.out = (double *)(work + dc.off_out);
+    ea.out = (double *)(work + (opt.rs ? dc.off_raw : dc.off_out));
     ea.rescue_tasks = (Task *)(work + dc.off_rtasks);
     ea.n_rescue = counters + 10;
     ea.rescue_capacity = std::max<uint32_t>(c.n_pairs, 1);
@@ -895,8 +911,35 @@ int launch_chunk(Device &dev, DeviceChunk &dc, const ChunkPlan &c, cudaStream_t 
     }
 
     {
-        // 1. per-read flat-quality classification (device side; the host only sampled candidate classes)
         const uint32_t n_span_reads = (uint32_t)c.read_off.size() - 1;
+        // 0. region steps: modifyReadQualities in place on the chunk's read arrays
+        if (opt.rs && n_span_reads) {
+            ModifyArgs ma;
+            memset(&ma, 0, sizeof ma);
+            ma.rd_bases = ka.rd_bases;
+            ma.rd_q = (uint8_t *)ka.rd_q; ma.rd_i = (uint8_t *)ka.rd_i; ma.rd_d = (uint8_t *)ka.rd_d;
+            ma.read_off = ka.read_off;
+            ma.n_reads = n_span_reads;
+            ma.mapq = meta + dc.off_mapq;
+            ma.has_pcr = opt.rs->pcr_rate_factor != 0.0;
+            if (ma.has_pcr)
+                for (int i = 0; i <= RS_MAX_REPEAT; ++i) {
+                    // getErrorModelAdjustedQual (HC/PairHMMLikelihoodCalculationEngine.java:356-358; MathUtils.fastRound)
+                    const double d = 40.0 - std::exp(i / (opt.rs->pcr_rate_factor * M_PI)) + 1.0;
+                    const int r = d > 0.0 ? (int)(d + 0.5) : (int)(d - 0.5);
+                    ma.pcr_cache[i] = (uint8_t)(int8_t)std::max(10, r);
+                }
+            ma.bq_threshold = opt.rs->base_quality_score_threshold;
+            ma.disable_cap_to_mapq = (opt.rs->flags & GPHMM_RS_DISABLE_CAP_TO_MAPQ) != 0;
+            phmm_modify_quals_kernel<<<std::min<uint32_t>((n_span_reads + 3) / 4, 148 * 16), 128, 0, st>>>(ma);
+            CK(cudaGetLastError());
+            ++launches;
+            if (opt.rs->hmm_base_q || opt.rs->hmm_ins_q || opt.rs->hmm_del_q) {
+                dc.h_modq.reserve(dc.read_stride * 3);
+                CK(cudaMemcpyAsync(dc.h_modq.p, (uint8_t *)dc.reads.p + dc.read_stride, dc.read_stride * 3, cudaMemcpyDeviceToHost, st));
+            }
+        }
+        // 1. per-read flat-quality classification (device side; the host only sampled candidate classes)
         {
             ClassifyArgs ca;
             memset(&ca, 0, sizeof ca);
@@ -1068,6 +1111,27 @@ int launch_chunk(Device &dev, DeviceChunk &dc, const ChunkPlan &c, cudaStream_t 
             ++launches;
         }
         CK(cudaEventRecord(dc.ev_f64, tail));
+        // region steps: normalizeLikelihoods + filterPoorlyModeledEvidence, read-major -> allele-major
+        if (opt.rs && ea.n_units) {
+            PostArgs pa;
+            memset(&pa, 0, sizeof pa);
+            pa.units = ea.units;
+            pa.n_units = ea.n_units;
+            pa.lk = ea.out;
+            pa.out = (double *)(work + dc.off_out);
+            pa.keep = work + dc.off_keep;
+            pa.rd_q = ka.rd_q;
+            pa.read_off = ka.read_off;
+            pa.max_diff_cap = opt.rs->log10_global_read_mismapping_rate;
+            pa.max_error_per_base = opt.rs->expected_error_rate_per_base;
+            pa.dynamic_scale = opt.rs->read_disqualification_scale;
+            pa.symmetric = (opt.rs->flags & GPHMM_RS_SYMMETRIC_NORMALIZE) != 0;
+            pa.filter = (opt.rs->flags & GPHMM_RS_FILTER_POORLY) != 0;
+            pa.dynamic = (opt.rs->flags & GPHMM_RS_DYNAMIC_DISQ) != 0;
+            phmm_normalize_filter_kernel<<<std::min<uint32_t>(ea.n_units, 148 * 8), 128, 0, tail>>>(pa);
+            CK(cudaGetLastError());
+            ++launches;
+        }
     }
     if (download) {
         const size_t bytes = (dc.off_err + 16) - dc.off_out;
@@ -1079,7 +1143,7 @@ int launch_chunk(Device &dev, DeviceChunk &dc, const ChunkPlan &c, cudaStream_t 
 
 // After the chunk's stream work completed: check the error flag, scatter results, account stats.
 void finish_chunk(DeviceChunk &dc, const gphmm_batch *b, const ChunkPlan &c, double *out, Stats &stats, bool downloaded,
-                  bool count_device_ms = true) {
+                  bool count_device_ms = true, const gphmm_region_steps *rs = nullptr) {
     CK(cudaEventSynchronize(dc.ev_done));
     float ms32 = 0, ms64 = 0, msall = 0;
     CK(cudaEventElapsedTime(&ms32, dc.ev_start, dc.ev_f32));
@@ -1099,6 +1163,19 @@ void finish_chunk(DeviceChunk &dc, const gphmm_batch *b, const ChunkPlan &c, dou
                 const size_t n = (size_t)d.n_reads * d.n_haps;
                 if (n) memcpy(out + b->units[u].out_off, res + d.out_base, n * sizeof(double));
             }
+        }
+        if (rs) {
+            if (rs->keep) {
+                const uint8_t *dk = ho + (dc.off_keep - dc.off_out);
+                for (int64_t u = c.u0; u < c.u1; ++u) {
+                    const UnitDesc &d = c.units[u - c.u0];
+                    if (d.n_reads) memcpy(rs->keep + b->units[u].read_begin, dk + d.keep_base, d.n_reads);
+                }
+            }
+            uint8_t *dst[3] = {rs->hmm_base_q, rs->hmm_ins_q, rs->hmm_del_q};
+            const size_t span = (size_t)(c.base_hi - c.base_lo);
+            for (int a = 0; a < 3; ++a)
+                if (dst[a] && span) memcpy(dst[a] + c.base_lo, (const uint8_t *)dc.h_modq.p + a * dc.read_stride, span);
         }
     }
     std::lock_guard<std::mutex> lk(stats.mu);
@@ -1164,7 +1241,7 @@ namespace {
 struct PlanPool {
     const gphmm_batch *b;
     const std::vector<std::pair<int64_t, int64_t>> &chunks;
-    bool f64, share;
+    bool f64, share, pcr_hint;
     Stats &stats;
     std::vector<std::unique_ptr<ChunkPlan>> ready;
     std::vector<char> done;
@@ -1176,8 +1253,9 @@ struct PlanPool {
     bool cancel = false;
     std::vector<std::thread> threads;
 
-    PlanPool(const gphmm_batch *b_, const std::vector<std::pair<int64_t, int64_t>> &c, bool f64_, bool share_, int n_threads, Stats &st)
-        : b(b_), chunks(c), f64(f64_), share(share_), stats(st), ready(c.size()), done(c.size(), 0), err_code(c.size(), 0),
+    PlanPool(const gphmm_batch *b_, const std::vector<std::pair<int64_t, int64_t>> &c, bool f64_, bool share_, int n_threads, Stats &st,
+             bool pcr_hint_ = false)
+        : b(b_), chunks(c), f64(f64_), share(share_), pcr_hint(pcr_hint_), stats(st), ready(c.size()), done(c.size(), 0), err_code(c.size(), 0),
           err_text(c.size()) {
         n_threads = c.size() <= 1 ? 0 : std::max(1, std::min<int>(n_threads, (int)c.size()));  // one chunk: plan inline, no threads
         lookahead = (size_t)n_threads + N_SLOTS;
@@ -1205,7 +1283,7 @@ struct PlanPool {
             std::string text;
             const double t0 = now_ms();
             try {
-                plan_chunk(b, chunks[ci].first, chunks[ci].second, f64, share, *p);
+                plan_chunk(b, chunks[ci].first, chunks[ci].second, f64, share, *p, pcr_hint);
             } catch (const Error &e) {
                 code = e.code; text = e.what();
             } catch (const std::exception &e) {
@@ -1228,7 +1306,7 @@ struct PlanPool {
         if (threads.empty()) {  // synchronous planning (single-chunk batches: the per-region JNI call)
             std::unique_ptr<ChunkPlan> p(new ChunkPlan());
             const double t0 = now_ms();
-            plan_chunk(b, chunks[ci].first, chunks[ci].second, f64, share, *p);
+            plan_chunk(b, chunks[ci].first, chunks[ci].second, f64, share, *p, pcr_hint);
             std::lock_guard<std::mutex> lk(stats.mu);
             stats.s.host_stage_ms += now_ms() - t0;
             return p;
@@ -1245,12 +1323,14 @@ struct PlanPool {
 // Process chunks of a batch on one device with N_SLOTS stream slots; chunks are claimed from a shared cursor so
 // that several devices drain the same batch (the host-side work queue of SURVEY 8e).
 void device_loop(gphmm *h, Device &dev, const gphmm_batch *b, const std::vector<std::pair<int64_t, int64_t>> &chunks,
-                 PlanPool &pool, std::atomic<size_t> &cursor, double *out, std::string &err, int &rc) {
+                 PlanPool &pool, std::atomic<size_t> &cursor, double *out, std::string &err, int &rc,
+                 const gphmm_region_steps *rs = nullptr) {
     try {
         CK(cudaSetDevice(dev.ordinal));
         RunOptions opt;
         opt.force_fp64 = h->cfg.force_fp64 != 0;
         opt.tristate_off = h->cfg.tristate_off != 0;
+        opt.rs = rs;
         std::unique_ptr<ChunkPlan> plans[N_SLOTS];
         bool inflight[N_SLOTS] = {false};
         const bool trace = getenv("GPHMM_TRACE") != nullptr;  // per-chunk host timeline on stderr
@@ -1262,13 +1342,13 @@ void device_loop(gphmm *h, Device &dev, const gphmm_batch *b, const std::vector<
             if (ci >= chunks.size()) break;
             const double t_f = now_ms();
             if (inflight[slot]) {
-                finish_chunk(dev.slots[slot], b, *plans[slot], out, h->stats, true);
+                finish_chunk(dev.slots[slot], b, *plans[slot], out, h->stats, true, true, rs);
                 inflight[slot] = false;
             }
             const double t_a = now_ms();
             plans[slot] = pool.take(ci);
             const double t_b = now_ms();
-            upload_chunk(dev, dev.slots[slot], b, *plans[slot], dev.streams[slot], false, h->stats);
+            upload_chunk(dev, dev.slots[slot], b, *plans[slot], dev.streams[slot], false, h->stats, rs);
             const double t_c = now_ms();
             launches += launch_chunk(dev, dev.slots[slot], *plans[slot], dev.streams[slot], dev.tails[slot], dev.aux[slot], opt, true);
             if (trace)
@@ -1279,7 +1359,7 @@ void device_loop(gphmm *h, Device &dev, const gphmm_batch *b, const std::vector<
         }
         for (int s = 0; s < N_SLOTS; ++s) {
             if (inflight[slot]) {
-                finish_chunk(dev.slots[slot], b, *plans[slot], out, h->stats, true);
+                finish_chunk(dev.slots[slot], b, *plans[slot], out, h->stats, true, true, rs);
                 inflight[slot] = false;
             }
             slot = (slot + 1) % N_SLOTS;
@@ -1296,7 +1376,7 @@ void device_loop(gphmm *h, Device &dev, const gphmm_batch *b, const std::vector<
     }
 }
 
-int run_batch(gphmm *h, const gphmm_batch *b, double *out) {
+int run_batch(gphmm *h, const gphmm_batch *b, double *out, const gphmm_region_steps *rs = nullptr) {
     std::lock_guard<std::mutex> run_lk(h->run_mu);
     const double t0 = now_ms();
     validate_batch(b);
@@ -1309,14 +1389,14 @@ int run_batch(gphmm *h, const gphmm_batch *b, double *out) {
     std::vector<int> rcs(nd, GPHMM_OK);
     {
         const int n_threads = h->cfg.host_threads > 0 ? h->cfg.host_threads : 4;  // GATK's --native-pair-hmm-threads default
-        PlanPool pool(b, chunks, false, h->cfg.no_prefix_sharing == 0, n_threads, h->stats);
+        PlanPool pool(b, chunks, false, h->cfg.no_prefix_sharing == 0, n_threads, h->stats, rs && rs->pcr_rate_factor != 0.0);
         if (nd == 1 || chunks.size() == 1) {
-            device_loop(h, *h->devices[0], b, chunks, pool, cursor, out, errs[0], rcs[0]);
+            device_loop(h, *h->devices[0], b, chunks, pool, cursor, out, errs[0], rcs[0], rs);
         } else {
             std::vector<std::thread> th;
             for (size_t d = 0; d < nd; ++d)
                 th.emplace_back(device_loop, h, std::ref(*h->devices[d]), b, std::cref(chunks), std::ref(pool), std::ref(cursor), out,
-                                std::ref(errs[d]), std::ref(rcs[d]));
+                                std::ref(errs[d]), std::ref(rcs[d]), rs);
             for (auto &t : th) t.join();
         }
     }
@@ -1547,6 +1627,25 @@ const char *gphmm_last_error(const gphmm_t *h) { return h ? h->last_error.c_str(
 int gphmm_compute(gphmm_t *h, const gphmm_batch *batch, double *out) {
     if (!h) return GPHMM_ERR_INVALID_ARG;
     return guarded(h, [&]() -> int { return run_batch(h, batch, out); });
+}
+
+int gphmm_compute_regions(gphmm_t *h, const gphmm_batch *batch, const gphmm_region_steps *steps, double *out) {
+    if (!h) return GPHMM_ERR_INVALID_ARG;
+    return guarded(h, [&]() -> int {
+        if (!steps || steps->struct_size != (int32_t)sizeof(gphmm_region_steps)) throw Error(GPHMM_ERR_INVALID_ARG, "steps is null or has the wrong struct_size");
+        if (!batch) throw Error(GPHMM_ERR_INVALID_ARG, "batch is null");
+        if (batch->n_reads > 0 && !steps->mapq) throw Error(GPHMM_ERR_INVALID_ARG, "steps.mapq is null");
+        // AlleleLikelihoods.java:417-418: the cap must be negative and not NaN
+        if (!(steps->log10_global_read_mismapping_rate < 0.0)) throw Error(GPHMM_ERR_INVALID_ARG, "log10_global_read_mismapping_rate must be negative");
+        if (steps->pcr_rate_factor < 0.0 || !(steps->expected_error_rate_per_base >= 0.0)) throw Error(GPHMM_ERR_INVALID_ARG, "negative rate in steps");
+        if (steps->base_quality_score_threshold < -128 || steps->base_quality_score_threshold > 127) throw Error(GPHMM_ERR_INVALID_ARG, "base_quality_score_threshold is a Java byte");
+        if (steps->ref_hap)
+            for (int64_t u = 0; u < batch->n_units; ++u) {
+                const int64_t nh = batch->units[u].hap_end - batch->units[u].hap_begin;
+                if (steps->ref_hap[u] < -1 || steps->ref_hap[u] >= nh) throw Error(GPHMM_ERR_INVALID_ARG, "ref_hap out of range");
+            }
+        return run_batch(h, batch, out, steps);
+    });
 }
 
 int gphmm_submit(gphmm_t *h, const gphmm_batch *b, double *out, uint64_t *ticket) {

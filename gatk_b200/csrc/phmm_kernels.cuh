@@ -974,7 +974,8 @@ struct UnitDesc {
     uint32_t hap_first, n_haps;    // chunk-local
     uint32_t out_base;             // chunk-local output slot of (read 0, hap 0)
     int32_t c0_exp;                // fp32 (or forced-fp64) initial-condition exponent of this unit
-    uint32_t pad0, pad1;
+    int32_t ref_hap;               // region steps: unit-local index of the reference haplotype, -1 = none
+    uint32_t keep_base;            // region steps: chunk-local slot of this unit's first keep flag
 };
 
 struct EpilogueArgs {

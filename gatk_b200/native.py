@@ -49,10 +49,22 @@ class Stats(ctypes.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
+class _RegionSteps(ctypes.Structure):
+    """gphmm_region_steps (include/gpuphmm.h)"""
+    _fields_ = [("struct_size", ctypes.c_int32), ("flags", ctypes.c_int32), ("pcr_rate_factor", ctypes.c_double),
+                ("base_quality_score_threshold", ctypes.c_int32), ("reserved", ctypes.c_int32),
+                ("log10_global_read_mismapping_rate", ctypes.c_double), ("expected_error_rate_per_base", ctypes.c_double),
+                ("read_disqualification_scale", ctypes.c_double), ("mapq", ctypes.c_void_p), ("ref_hap", ctypes.c_void_p),
+                ("keep", ctypes.c_void_p), ("hmm_base_q", ctypes.c_void_p), ("hmm_ins_q", ctypes.c_void_p),
+                ("hmm_del_q", ctypes.c_void_p)]
+
+
+RS_DISABLE_CAP_TO_MAPQ, RS_SYMMETRIC_NORMALIZE, RS_FILTER_POORLY, RS_DYNAMIC_DISQ = 1, 2, 4, 8
+
 UNIT_DTYPE = np.dtype([("read_begin", "<i8"), ("read_end", "<i8"), ("hap_begin", "<i8"), ("hap_end", "<i8"), ("out_off", "<i8")])
 
 EXPORTS = ["gphmm_abi_version", "gphmm_device_count", "gphmm_strerror", "gphmm_create", "gphmm_destroy",
-           "gphmm_last_error", "gphmm_compute", "gphmm_submit", "gphmm_wait", "gphmm_prepare", "gphmm_run_prepared",
+           "gphmm_last_error", "gphmm_compute", "gphmm_compute_regions", "gphmm_submit", "gphmm_wait", "gphmm_prepare", "gphmm_run_prepared",
            "gphmm_release_prepared", "gphmm_get_stats", "gphmm_reset_stats", "gphmm_plan_stats", "gphmm_host_alloc", "gphmm_host_free"]
 
 
@@ -86,6 +98,8 @@ def load_library():
     L.gphmm_last_error.argtypes = [ctypes.c_void_p]
     L.gphmm_compute.restype = ctypes.c_int
     L.gphmm_compute.argtypes = [ctypes.c_void_p, ctypes.POINTER(_Batch), ctypes.c_void_p]
+    L.gphmm_compute_regions.restype = ctypes.c_int
+    L.gphmm_compute_regions.argtypes = [ctypes.c_void_p, ctypes.POINTER(_Batch), ctypes.POINTER(_RegionSteps), ctypes.c_void_p]
     L.gphmm_submit.restype = ctypes.c_int
     L.gphmm_submit.argtypes = [ctypes.c_void_p, ctypes.POINTER(_Batch), ctypes.c_void_p, ctypes.POINTER(ctypes.c_uint64)]
     L.gphmm_wait.restype = ctypes.c_int
@@ -214,6 +228,28 @@ class Batch:
         units = np.array([(0, len(reads), 0, len(haps), 0)], dtype=UNIT_DTYPE)
         return Batch(cat(cols[0]), cat(cols[1]), cat(cols[2]), cat(cols[3]), cat(cols[4]), read_off, cat(hs), hap_off, units)
 
+    @staticmethod
+    def from_units(regions):
+        """regions: list of (reads, haps) as in single_unit; one unit per entry, outputs back to back."""
+        as_u8 = lambda x: np.frombuffer(x, dtype=np.uint8) if isinstance(x, (bytes, bytearray)) else np.asarray(x, dtype=np.uint8)
+        cols = [[], [], [], [], []]
+        hs, units = [], []
+        n_reads = n_haps = n_out = 0
+        for reads, haps in regions:
+            for r in reads:
+                for k in range(5):
+                    cols[k].append(as_u8(r[k]))
+            hs.extend(as_u8(h) for h in haps)
+            units.append((n_reads, n_reads + len(reads), n_haps, n_haps + len(haps), n_out))
+            n_reads += len(reads)
+            n_haps += len(haps)
+            n_out += len(reads) * len(haps)
+        cat = lambda xs: np.concatenate(xs) if xs else np.zeros(0, np.uint8)
+        read_off = np.concatenate([[0], np.cumsum([len(x) for x in cols[0]])]).astype(np.int64)
+        hap_off = np.concatenate([[0], np.cumsum([len(h) for h in hs])]).astype(np.int64)
+        return Batch(cat(cols[0]), cat(cols[1]), cat(cols[2]), cat(cols[3]), cat(cols[4]), read_off, cat(hs), hap_off,
+                     np.array(units, dtype=UNIT_DTYPE))
+
 
 def plan_stats(batch, prefix_sharing=True):
     """Host-only planning totals (gphmm_plan_stats); works without a GPU."""
@@ -279,6 +315,46 @@ class GpuPhmm:
         b = batch.c_struct()
         self._check(self._L.gphmm_compute(self._h, ctypes.byref(b), out.ctypes.data))
         return out
+
+    def compute_regions(self, batch, mapq, ref_hap=None, pcr_rate_factor=3.0, base_quality_score_threshold=18,
+                        disable_cap_to_mapq=False, log10_global_read_mismapping_rate=-4.5, symmetric=False,
+                        filter_poorly=True, expected_error_rate_per_base=0.02, dynamic_disqualification=False,
+                        read_disqualification_scale=1.0, want_quals=True):
+        """gphmm_compute_regions: modifyReadQualities -> PairHMM -> normalizeLikelihoods -> filterPoorlyModeledEvidence
+        on the device.  Returns a dict: lk (flat, per unit allele-major [h*nReads + r]), keep (per read),
+        base_q / ins_q / del_q (the qualities the kernel used, when want_quals)."""
+        n_reads = len(batch.read_off) - 1
+        mapq = np.ascontiguousarray(mapq, dtype=np.uint8)
+        if len(mapq) != n_reads:
+            raise ValueError("mapq needs one entry per read")
+        out = np.full(batch.n_out, np.nan, dtype=np.float64)
+        keep = np.full(max(n_reads, 1), 255, dtype=np.uint8)
+        rs = _RegionSteps()
+        rs.struct_size = ctypes.sizeof(_RegionSteps)
+        rs.flags = ((RS_DISABLE_CAP_TO_MAPQ if disable_cap_to_mapq else 0) | (RS_SYMMETRIC_NORMALIZE if symmetric else 0)
+                    | (RS_FILTER_POORLY if filter_poorly else 0) | (RS_DYNAMIC_DISQ if dynamic_disqualification else 0))
+        rs.pcr_rate_factor = float(pcr_rate_factor)
+        rs.base_quality_score_threshold = int(base_quality_score_threshold)
+        rs.log10_global_read_mismapping_rate = float(log10_global_read_mismapping_rate)
+        rs.expected_error_rate_per_base = float(expected_error_rate_per_base)
+        rs.read_disqualification_scale = float(read_disqualification_scale)
+        rs.mapq = mapq.ctypes.data if n_reads else None
+        if ref_hap is not None:
+            ref_hap = np.ascontiguousarray(ref_hap, dtype=np.int32)
+            if len(ref_hap) != len(batch.units):
+                raise ValueError("ref_hap needs one entry per unit")
+            rs.ref_hap = ref_hap.ctypes.data
+        rs.keep = keep.ctypes.data
+        res = {"lk": out, "keep": keep[:n_reads]}
+        if want_quals:
+            n = len(batch.read_bases)
+            for name, field in (("base_q", "hmm_base_q"), ("ins_q", "hmm_ins_q"), ("del_q", "hmm_del_q")):
+                a = np.zeros(max(n, 1), dtype=np.uint8)
+                setattr(rs, field, a.ctypes.data)
+                res[name] = a[:n]
+        b = batch.c_struct()
+        self._check(self._L.gphmm_compute_regions(self._h, ctypes.byref(b), ctypes.byref(rs), out.ctypes.data))
+        return res
 
     def submit(self, batch, out=None):
         if out is None:

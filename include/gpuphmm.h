@@ -125,6 +125,40 @@ int gphmm_prepare(gphmm_t *h, const gphmm_batch *batch, gphmm_prepared_t **out);
 int gphmm_run_prepared(gphmm_t *h, gphmm_prepared_t *p, double *out);
 void gphmm_release_prepared(gphmm_t *h, gphmm_prepared_t *p);
 
+/* ---- Region steps: the per-read steps either side of the kernel, on the device ----------------
+ * Replaces, for one call over many (region, sample) units,
+ *   tools/walkers/haplotypecaller/PairHMMLikelihoodCalculationEngine.java:283-316,361-371  modifyReadQualities
+ *       (applyPCRErrorModel with ReadLikelihoodCalculationEngine.findTandemRepeatUnits :193-253, capMinimumReadQualities)
+ *   utils/genotyper/AlleleLikelihoods.java:416-458   normalizeLikelihoods(log10globalReadMismappingRate, symmetric)
+ *   utils/genotyper/AlleleLikelihoods.java:1351-1376 filterPoorlyModeledEvidence (the keep/drop decision;
+ *       thresholds ReadLikelihoodCalculationEngine.java:66-151)
+ * The batch carries the reads as modifyReadQualities receives them (soft clips already hard-clipped by the caller,
+ * PairHMMLikelihoodCalculationEngine.java:287; ins/del = BI/BD tags or flat Q45, ReadUtils.java:838-862). */
+#define GPHMM_RS_DISABLE_CAP_TO_MAPQ 1  /* disableCapReadQualitiesToMapQ */
+#define GPHMM_RS_SYMMETRIC_NORMALIZE 2  /* symmetricallyNormalizeAllelesToReference */
+#define GPHMM_RS_FILTER_POORLY 4        /* computeReadLikelihoods(..., filterPoorly = true) */
+#define GPHMM_RS_DYNAMIC_DISQ 8         /* dynamicDisqualification (DRAGEN-GATK) */
+
+typedef struct gphmm_region_steps {
+    int32_t struct_size;                      /* sizeof(gphmm_region_steps) */
+    int32_t flags;                            /* GPHMM_RS_* */
+    double pcr_rate_factor;                   /* PCRErrorModel.getRateFactor(): 0 NONE, 1 HOSTILE, 2 AGGRESSIVE, 3 CONSERVATIVE */
+    int32_t base_quality_score_threshold;     /* baseQualityScoreThreshold, default 18 */
+    int32_t reserved;
+    double log10_global_read_mismapping_rate; /* default -4.5; must be < 0; -inf: no capping */
+    double expected_error_rate_per_base;      /* default 0.02 */
+    double read_disqualification_scale;       /* dynamic model only, default 1.0 */
+    const uint8_t *mapq;                      /* n_reads mapping qualities (GATKRead.getMappingQuality) */
+    const int32_t *ref_hap;                   /* per unit: index of the reference haplotype within the unit, -1 none; NULL = none */
+    uint8_t *keep;                            /* out, n_reads: 1 kept, 0 removed as poorly modeled (units must not share reads) */
+    uint8_t *hmm_base_q;                      /* out, optional: modified base qualities (HMM_BASE_QUALITIES_TAG), layout of base_q */
+    uint8_t *hmm_ins_q, *hmm_del_q;           /* out, optional: the insertion / deletion qualities the kernel used */
+} gphmm_region_steps;
+
+/* Like gphmm_compute with the steps above fused in.  out[u.out_off + h*nReads + r] is the NORMALISED log10 likelihood,
+ * allele-major like AlleleLikelihoods.valuesBySampleIndex[s][a][r] (AlleleLikelihoods.java:71-74). */
+int gphmm_compute_regions(gphmm_t *h, const gphmm_batch *batch, const gphmm_region_steps *steps, double *out);
+
 /* Statistics accumulate over calls until reset. */
 int gphmm_get_stats(const gphmm_t *h, gphmm_stats *out);
 void gphmm_reset_stats(gphmm_t *h);

@@ -22,7 +22,7 @@ _f64p = ctypes.POINTER(ctypes.c_double)
 
 def build(force=False):
     """Compile the oracle with the committed Makefile (gcc, -ffp-contract=off)."""
-    srcs = [os.path.join(_HERE, f) for f in ("pairhmm_oracle.c", "pairhmm_simd_baseline.c", "Makefile")]
+    srcs = [os.path.join(_HERE, f) for f in ("pairhmm_oracle.c", "pairhmm_simd_baseline.c", "region_steps_oracle.c", "Makefile")]
     if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < max(os.path.getmtime(x) for x in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-s", "-B", "libphmm_oracle.so"])
     return _LIB_PATH
@@ -53,6 +53,21 @@ def lib():
         L.phmm_simd_batch.restype = ctypes.c_long
         L.phmm_simd_batch.argtypes = [_u8p, _u8p, _u8p, _u8p, _u8p, ctypes.POINTER(ctypes.c_int64), _u8p, ctypes.POINTER(ctypes.c_int64),
                                       ctypes.POINTER(ctypes.c_int64), ctypes.c_long, ctypes.c_int, _f64p]
+        L.region_oracle_find_repetitions.restype = ctypes.c_int
+        L.region_oracle_find_repetitions.argtypes = [_u8p, ctypes.c_int, ctypes.c_int, _u8p, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+        L.region_oracle_tandem_repeat_length.restype = ctypes.c_int
+        L.region_oracle_tandem_repeat_length.argtypes = [_u8p, ctypes.c_int, ctypes.c_int]
+        L.region_oracle_pcr_cache.restype = None
+        L.region_oracle_pcr_cache.argtypes = [ctypes.c_double, _u8p]
+        L.region_oracle_modify_read.restype = None
+        L.region_oracle_modify_read.argtypes = [_u8p, _u8p, _u8p, _u8p, ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_int, ctypes.c_int]
+        L.region_oracle_normalize.restype = None
+        L.region_oracle_normalize.argtypes = [_f64p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_int, _f64p]
+        L.region_oracle_min_true_likelihood.restype = ctypes.c_double
+        L.region_oracle_min_true_likelihood.argtypes = [_u8p, ctypes.c_int, ctypes.c_double, ctypes.c_int, ctypes.c_double]
+        L.region_oracle_filter.restype = None
+        L.region_oracle_filter.argtypes = [_f64p, ctypes.c_int, ctypes.c_int, _u8p, ctypes.POINTER(ctypes.c_int64), ctypes.c_double,
+                                           ctypes.c_int, ctypes.c_double, _u8p]
         L.phmm_oracle_init()
         _lib = L
     return _lib
@@ -146,3 +161,74 @@ def simd_batch(read_bases, base_q, ins_q, del_q, gcp, read_off, hap_bases, hap_o
     rescued = lib().phmm_simd_batch(arrs[0][1], arrs[1][1], arrs[2][1], arrs[3][1], arrs[4][1], ro.ctypes.data_as(i64p), hbp,
                                     ho.ctypes.data_as(i64p), un.ctypes.data_as(i64p), len(un), int(threads), out.ctypes.data_as(_f64p))
     return out, int(rescued)
+
+
+# ---- steps either side of the kernel (oracle/region_steps_oracle.c) -------------------------------------------------
+def _bytes(x):
+    return np.ascontiguousarray(np.frombuffer(x, dtype=np.uint8) if isinstance(x, (bytes, bytearray)) else x, dtype=np.uint8)
+
+
+def find_repetitions(unit, test, leading, unit_off=0, unit_len=None, test_off=0, test_len=None):
+    """GATKVariantContextUtils.findNumberOfRepetitions (both overloads)"""
+    u, t = _bytes(unit), _bytes(test)
+    if unit_len is None:
+        unit_len = len(u)
+    if test_len is None:
+        test_len = len(t)
+    if len(t) == 0:
+        t = np.zeros(1, np.uint8)
+    return lib().region_oracle_find_repetitions(u.ctypes.data_as(_u8p), unit_off, unit_len, t.ctypes.data_as(_u8p), test_off, test_len,
+                                                1 if leading else 0)
+
+
+def tandem_repeat_length(bases, offset):
+    b = _bytes(bases)
+    return lib().region_oracle_tandem_repeat_length(b.ctypes.data_as(_u8p), len(b), offset)
+
+
+def pcr_cache(rate_factor):
+    out = np.zeros(21, np.uint8)
+    lib().region_oracle_pcr_cache(float(rate_factor), out.ctypes.data_as(_u8p))
+    return out
+
+
+def modify_reads(read_bases, base_q, ins_q, del_q, read_off, mapq, rate_factor=3.0, bq_threshold=18, disable_cap_to_mapq=False):
+    """modifyReadQualities on every read of flat arrays; returns new (base_q, ins_q, del_q)"""
+    L = lib()
+    rb = _bytes(read_bases)
+    q, i, d = (np.array(x, dtype=np.uint8, copy=True) for x in (base_q, ins_q, del_q))
+    for r in range(len(read_off) - 1):
+        o, n = int(read_off[r]), int(read_off[r + 1] - read_off[r])
+        if n == 0:
+            continue
+        L.region_oracle_modify_read(rb[o:].ctypes.data_as(_u8p), q[o:].ctypes.data_as(_u8p), i[o:].ctypes.data_as(_u8p),
+                                    d[o:].ctypes.data_as(_u8p), n, int(mapq[r]), float(rate_factor), int(bq_threshold),
+                                    1 if disable_cap_to_mapq else 0)
+    return q, i, d
+
+
+def normalize(lk, n_reads, n_haps, ref_hap=-1, max_diff_cap=-4.5, symmetric=False):
+    """read-major lk -> normalised allele-major matrix (flat)"""
+    a = np.ascontiguousarray(lk, dtype=np.float64)
+    out = np.zeros(n_reads * n_haps, np.float64)
+    lib().region_oracle_normalize(a.ctypes.data_as(_f64p), n_reads, n_haps, ref_hap, float(max_diff_cap), 1 if symmetric else 0,
+                                  out.ctypes.data_as(_f64p))
+    return out
+
+
+def min_true_likelihood(hmm_base_q, max_error_per_base=0.02, dynamic=False, dynamic_scale=1.0):
+    q = _bytes(hmm_base_q)
+    p = q if len(q) else np.zeros(1, np.uint8)
+    return lib().region_oracle_min_true_likelihood(p.ctypes.data_as(_u8p), len(q), float(max_error_per_base), 1 if dynamic else 0,
+                                                   float(dynamic_scale))
+
+
+def filter_poorly_modeled(lk_allele_major, n_reads, n_haps, hmm_base_q, read_off, max_error_per_base=0.02, dynamic=False,
+                          dynamic_scale=1.0):
+    a = np.ascontiguousarray(lk_allele_major, dtype=np.float64)
+    q = _bytes(hmm_base_q)
+    ro = np.ascontiguousarray(read_off, dtype=np.int64)
+    keep = np.zeros(max(n_reads, 1), np.uint8)
+    lib().region_oracle_filter(a.ctypes.data_as(_f64p), n_reads, n_haps, q.ctypes.data_as(_u8p), ro.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)),
+                               float(max_error_per_base), 1 if dynamic else 0, float(dynamic_scale), keep.ctypes.data_as(_u8p))
+    return keep[:n_reads]

@@ -42,3 +42,50 @@ def logless(hap, read, base_q, ins_q, del_q, gcp, tristate_off=False):
     for j in range(1, H + 1):
         s += Mp[j] + Ip[j]
     return (math.log10(s) if s > 0.0 else -math.inf) - INITIAL_CONDITION_LOG10
+
+
+# ---- second, independent restatement of the tandem-repeat scan (strings instead of index arithmetic) -----------------
+def find_number_of_repetitions(unit, test, leading):
+    """GATKVariantContextUtils.findNumberOfRepetitions(byte[], byte[], boolean), utils/variant/GATKVariantContextUtils.java:949-957"""
+    if len(test) == 0:
+        return 0
+    n = 0
+    if leading:
+        while test.startswith(unit):
+            n += 1
+            test = test[len(unit):]
+    else:
+        while test.endswith(unit):
+            n += 1
+            test = test[:len(test) - len(unit)]
+    return n
+
+
+def find_tandem_repeat_units(read, offset, max_unit=8, max_repeat=20):
+    """ReadLikelihoodCalculationEngine.findTandemRepeatUnits (tools/walkers/haplotypecaller/ReadLikelihoodCalculationEngine.java:193-253);
+    returns (unit, repeat length) like the Java Pair"""
+    read = bytes(read)
+    best_bw, max_bw = read[offset:offset + 1], 0
+    for k in range(1, max_unit + 1):
+        if offset + 1 - k < 0:
+            break
+        max_bw = find_number_of_repetitions(read[offset - k + 1:offset + 1], read[:offset + 1], False)
+        if max_bw > 1:
+            best_bw = read[offset - k + 1:offset + 1]
+            break
+    best, max_rl = best_bw, max_bw
+    if offset < len(read) - 1:
+        best_fw, max_fw = read[offset + 1:offset + 2], 0
+        for k in range(1, max_unit + 1):
+            if offset + k + 1 > len(read):
+                break
+            max_fw = find_number_of_repetitions(read[offset + 1:offset + k + 1], read[offset + 1:], True)
+            if max_fw > 1:
+                best_fw = read[offset + 1:offset + k + 1]
+                break
+        if best_fw == best_bw:
+            max_rl = max_bw + max_fw
+        else:
+            max_rl = max_fw + find_number_of_repetitions(best_fw, read[:offset + 1], False)
+        best = best_fw
+    return best, min(max_rl, max_repeat)
