@@ -217,6 +217,57 @@ JNIEXPORT void JNICALL JNIFN(nativeCompute)(JNIEnv *env, jclass, jlong handle, j
     env->SetDoubleArrayRegion(out, 0, need, res.data());
 }
 
+// Region steps (include/gpuphmm.h gphmm_compute_regions): the reads arrive as modifyReadQualities receives them.
+// iparams = {flags, baseQualityScoreThreshold, refHaplotypeIndex}, dparams = {pcrRateFactor,
+// log10GlobalReadMismappingRate, expectedErrorRatePerBase, readDisqualificationScale}.  out is allele-major
+// (out[h * nReads + r], normalised), keep[r] = 0 for reads filterPoorlyModeledEvidence removes, hmmBaseQuals (nullable)
+// receives the modified base qualities of all reads back to back (HMM_BASE_QUALITIES_TAG).
+JNIEXPORT void JNICALL JNIFN(nativeComputeRegion)(JNIEnv *env, jclass, jlong handle, jobjectArray reads, jbyteArray mapq,
+                                                  jobjectArray haps, jintArray iparams, jdoubleArray dparams, jdoubleArray out,
+                                                  jbyteArray keep, jbyteArray hmmBaseQuals) {
+    Session *s = reinterpret_cast<Session *>(handle);
+    gphmm_batch b;
+    gphmm_unit unit;
+    if (!pack(env, s, reads, haps, &b, &unit)) return;
+    const jsize n_reads = static_cast<jsize>(b.n_reads), need = static_cast<jsize>(b.n_reads * b.n_haps);
+    if (env->GetArrayLength(iparams) < 3 || env->GetArrayLength(dparams) < 4 || env->GetArrayLength(mapq) < n_reads ||
+        env->GetArrayLength(keep) < n_reads || env->GetArrayLength(out) < need ||
+        (hmmBaseQuals && env->GetArrayLength(hmmBaseQuals) < static_cast<jsize>(s->read_off.back()))) {
+        throw_java(env, "java/lang/IllegalArgumentException", "region-step arrays are too small");
+        return;
+    }
+    jint ip[3];
+    jdouble dp[4];
+    env->GetIntArrayRegion(iparams, 0, 3, ip);
+    env->GetDoubleArrayRegion(dparams, 0, 4, dp);
+    std::vector<uint8_t> mq(static_cast<size_t>(n_reads) + 1), kp(static_cast<size_t>(n_reads) + 1, 1);
+    std::vector<uint8_t> hq(hmmBaseQuals ? static_cast<size_t>(s->read_off.back()) + 1 : 0);
+    if (n_reads) env->GetByteArrayRegion(mapq, 0, n_reads, reinterpret_cast<jbyte *>(mq.data()));
+    const int32_t ref = ip[2];
+    gphmm_region_steps rs;
+    std::memset(&rs, 0, sizeof rs);
+    rs.struct_size = static_cast<int32_t>(sizeof rs);
+    rs.flags = ip[0];
+    rs.base_quality_score_threshold = ip[1];
+    rs.pcr_rate_factor = dp[0];
+    rs.log10_global_read_mismapping_rate = dp[1];
+    rs.expected_error_rate_per_base = dp[2];
+    rs.read_disqualification_scale = dp[3];
+    rs.mapq = mq.data();
+    rs.ref_hap = &ref;
+    rs.keep = kp.data();
+    rs.hmm_base_q = hmmBaseQuals ? hq.data() : nullptr;
+    std::vector<double> res(static_cast<size_t>(need) + 1);
+    const int rc = gphmm_compute_regions(s->h, &b, &rs, res.data());
+    if (rc != GPHMM_OK) {
+        throw_for(env, s, rc);
+        return;
+    }
+    if (need) env->SetDoubleArrayRegion(out, 0, need, res.data());
+    if (n_reads) env->SetByteArrayRegion(keep, 0, n_reads, reinterpret_cast<const jbyte *>(kp.data()));
+    if (hmmBaseQuals && s->read_off.back()) env->SetByteArrayRegion(hmmBaseQuals, 0, static_cast<jsize>(s->read_off.back()), reinterpret_cast<const jbyte *>(hq.data()));
+}
+
 JNIEXPORT jlong JNICALL JNIFN(nativeSubmit)(JNIEnv *env, jclass, jlong handle, jobjectArray reads, jobjectArray haps) {
     Session *s = reinterpret_cast<Session *>(handle);
     gphmm_batch b;

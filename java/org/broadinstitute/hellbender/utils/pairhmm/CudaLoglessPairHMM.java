@@ -9,7 +9,9 @@ import org.broadinstitute.hellbender.exceptions.UserException;
 import org.broadinstitute.hellbender.utils.genotyper.LikelihoodMatrix;
 import org.broadinstitute.hellbender.utils.haplotype.Haplotype;
 import org.broadinstitute.hellbender.utils.read.GATKRead;
+import org.broadinstitute.hellbender.utils.read.ReadUtils;
 
+import java.util.Arrays;
 import java.util.HashMap;
 import java.util.List;
 import java.util.Map;
@@ -153,6 +155,94 @@ public final class CudaLoglessPairHMM extends LoglessPairHMM {
                         read.overallGCP, matrixAlleles.get(a).getBases(), lk);
             }
         }
+    }
+
+    /** The fields of PairHMMLikelihoodCalculationEngine that parameterise the steps fused around the kernel. */
+    public static final class RegionSteps {
+        public double pcrRateFactor = 3.0;                       // PCRErrorModel.getRateFactor(); 0 = NONE
+        public byte baseQualityScoreThreshold = 18;
+        public boolean disableCapReadQualitiesToMapQ = false;
+        public double log10GlobalReadMismappingRate = -4.5;
+        public boolean symmetricallyNormalizeAllelesToReference = false;
+        public boolean filterPoorly = true;
+        public double expectedErrorRatePerBase = 0.02;
+        public boolean dynamicDisqualification = false;
+        public double readDisqualificationScale = 1.0;
+    }
+
+    /**
+     * One sample of a region with modifyReadQualities, normalizeLikelihoods and the filterPoorlyModeledEvidence decision
+     * done on the GPU (see java/patches/PairHMMLikelihoodCalculationEngine.regionSteps.patch for the caller).
+     * Standard input-score imputation only (flat GCP, BI/BD or Q45 gap-open penalties); with DRAGstr parameters the
+     * caller keeps using {@link #computeLog10Likelihoods}.
+     *
+     * @param clippedReads the sample's reads after ReadClipper.hardClipSoftClippedBases (or as they are when
+     *                     modifySoftclippedBases is set), in matrix order
+     * @return indexes (in matrix order) of the reads to remove as poorly modeled; the matrix holds the normalised
+     *         likelihoods of all reads
+     */
+    public int[] computeRegionLikelihoods(final LikelihoodMatrix<GATKRead, Haplotype> logLikelihoods,
+                                          final List<GATKRead> clippedReads, final byte constantGCP, final RegionSteps steps,
+                                          final String hmmBaseQualitiesTag) {
+        final int nReads = clippedReads.size();
+        if (nReads == 0) {
+            return new int[0];
+        }
+        final ReadDataHolder[] nativeReads = new ReadDataHolder[nReads];
+        final byte[] mapq = new byte[nReads];
+        int totalBases = 0;
+        for (int r = 0; r < nReads; r++) {
+            final GATKRead read = clippedReads.get(r);
+            final ReadDataHolder holder = new ReadDataHolder();
+            holder.readBases = read.getBases();
+            holder.readQuals = read.getBaseQualities();
+            holder.insertionGOP = ReadUtils.getBaseInsertionQualities(read);
+            holder.deletionGOP = ReadUtils.getBaseDeletionQualities(read);
+            holder.overallGCP = new byte[holder.readBases.length];
+            Arrays.fill(holder.overallGCP, constantGCP);
+            nativeReads[r] = holder;
+            mapq[r] = (byte) Math.min(255, read.getMappingQuality());
+            totalBases += holder.readBases.length;
+        }
+        int referenceIndex = -1;
+        for (final Map.Entry<Haplotype, Integer> entry : nativeIndexOf.entrySet()) {
+            if (entry.getKey().isReference()) {
+                referenceIndex = entry.getValue();
+            }
+        }
+        final int flags = (steps.disableCapReadQualitiesToMapQ ? 1 : 0) | (steps.symmetricallyNormalizeAllelesToReference ? 2 : 0)
+                | (steps.filterPoorly ? 4 : 0) | (steps.dynamicDisqualification ? 8 : 0);
+        final int nHaplotypes = nativeHaplotypes.length;
+        final double[] alleleMajor = new double[nReads * nHaplotypes];
+        final byte[] keep = new byte[nReads];
+        final byte[] hmmBaseQualities = new byte[totalBases];
+        gpu.computeRegion(nativeReads, mapq, nativeHaplotypes, new int[]{flags, steps.baseQualityScoreThreshold, referenceIndex},
+                new double[]{steps.pcrRateFactor, steps.log10GlobalReadMismappingRate, steps.expectedErrorRatePerBase, steps.readDisqualificationScale},
+                alleleMajor, keep, hmmBaseQualities);
+
+        final List<Haplotype> matrixAlleles = logLikelihoods.alleles();
+        for (int a = 0; a < matrixAlleles.size(); a++) {
+            final int column = nativeIndexOf.get(matrixAlleles.get(a)) * nReads;   // one contiguous row of the native result per allele
+            for (int r = 0; r < nReads; r++) {
+                logLikelihoods.set(a, r, alleleMajor[column + r]);
+            }
+        }
+        int dropped = 0;
+        int offset = 0;
+        for (int r = 0; r < nReads; r++) {
+            final int length = nativeReads[r].readBases.length;
+            // PairHMMLikelihoodCalculationEngine.java:302: the qualities the HMM used, for the DRAGEN filters downstream
+            logLikelihoods.evidence().get(r).setTransientAttribute(hmmBaseQualitiesTag, Arrays.copyOfRange(hmmBaseQualities, offset, offset + length));
+            offset += length;
+            dropped += keep[r] == 0 ? 1 : 0;
+        }
+        final int[] toRemove = new int[dropped];
+        for (int r = 0, k = 0; r < nReads; r++) {
+            if (keep[r] == 0) {
+                toRemove[k++] = r;
+            }
+        }
+        return toRemove;
     }
 
     @Override

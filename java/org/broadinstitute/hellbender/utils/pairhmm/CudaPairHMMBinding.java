@@ -85,6 +85,29 @@ public final class CudaPairHMMBinding implements PairHMMNativeBinding {
         nativeAwait(handle, ticket, likelihoodArray);
     }
 
+    /**
+     * One (region, sample) unit with the steps either side of the kernel fused in on the GPU (gphmm_compute_regions):
+     * PairHMMLikelihoodCalculationEngine.modifyReadQualities before, AlleleLikelihoods.normalizeLikelihoods and the
+     * keep/drop decision of filterPoorlyModeledEvidence after.
+     *
+     * @param readDataArray   reads as modifyReadQualities receives them (soft clips already removed; raw base qualities;
+     *                        BI/BD or flat Q45 in insertionGOP/deletionGOP; flat GCP)
+     * @param mappingQualities one MAPQ per read
+     * @param intParams       {flags (GPHMM_RS_*), baseQualityScoreThreshold, index of the reference haplotype or -1}
+     * @param doubleParams    {PCR rate factor (0 = NONE), log10GlobalReadMismappingRate, expectedErrorRatePerBase, readDisqualificationScale}
+     * @param likelihoods     out, allele-major: {@code likelihoods[h * nReads + r]}, normalised
+     * @param keep            out, per read: 0 = the read is removed as poorly modeled
+     * @param hmmBaseQualities out, nullable: modified base qualities of all reads back to back (HMM_BASE_QUALITIES_TAG)
+     */
+    public void computeRegion(final ReadDataHolder[] readDataArray, final byte[] mappingQualities,
+                              final HaplotypeDataHolder[] haplotypeDataArray, final int[] intParams, final double[] doubleParams,
+                              final double[] likelihoods, final byte[] keep, final byte[] hmmBaseQualities) {
+        if (handle == 0L) {
+            throw new IllegalStateException("CudaPairHMMBinding.initialize() has not been called");
+        }
+        nativeComputeRegion(handle, readDataArray, mappingQualities, haplotypeDataArray, intParams, doubleParams, likelihoods, keep, hmmBaseQualities);
+    }
+
     @Override
     public void done() {
         if (handle != 0L) {
@@ -106,6 +129,8 @@ public final class CudaPairHMMBinding implements PairHMMNativeBinding {
     private static native int nativeDeviceCount();
     private static native long nativeCreate(int[] devices, boolean forceFp64, int hostThreads);
     private static native void nativeCompute(long handle, ReadDataHolder[] reads, HaplotypeDataHolder[] haps, double[] out);
+    private static native void nativeComputeRegion(long handle, ReadDataHolder[] reads, byte[] mapq, HaplotypeDataHolder[] haps,
+                                                   int[] intParams, double[] doubleParams, double[] out, byte[] keep, byte[] hmmBaseQuals);
     private static native long nativeSubmit(long handle, ReadDataHolder[] reads, HaplotypeDataHolder[] haps);
     private static native void nativeAwait(long handle, long ticket, double[] out);
     private static native void nativeDestroy(long handle);

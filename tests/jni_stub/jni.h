@@ -43,7 +43,9 @@ struct JNIEnv {
     void DeleteLocalRef(jobject);
     void GetByteArrayRegion(jbyteArray, jsize, jsize, jbyte *);
     void GetIntArrayRegion(jintArray, jsize, jsize, jint *);
+    void GetDoubleArrayRegion(jdoubleArray, jsize, jsize, jdouble *);
     void SetDoubleArrayRegion(jdoubleArray, jsize, jsize, const jdouble *);
+    void SetByteArrayRegion(jbyteArray, jsize, jsize, const jbyte *);
     void SetLongArrayRegion(jlongArray, jsize, jsize, const jlong *);
     jlongArray NewLongArray(jsize);
     jdoubleArray NewDoubleArray(jsize);
