@@ -9,6 +9,8 @@ same C ABI, without any arithmetic of its own:
   initialize(haplotypes, perSampleReadList, readMaxLength, haplotypeMaxLength)   VectorLoglessPairHMM.java:89-102
   computeLog10Likelihoods(logLikelihoods, processedReads, inputScoreImputator)   VectorLoglessPairHMM.java:108-159
   getLogLikelihoodArray() / close()                          PairHMM.java:357-359,391-402
+  computeRegionLikelihoods(matrix, clippedReads, constantGCP, steps)   the fused region steps (CudaLoglessPairHMM.java;
+      replaces PairHMMLikelihoodCalculationEngine.java:194-203,283-316 + AlleleLikelihoods.java:416-458,1351-1376)
 """
 import enum
 from dataclasses import dataclass
@@ -36,6 +38,22 @@ class Read:
     base_quals: Sequence[int]
     ins_quals: Optional[Sequence[int]] = None   # BI tag or the flat default
     del_quals: Optional[Sequence[int]] = None   # BD tag or the flat default
+    mapping_quality: int = 60                   # GATKRead.getMappingQuality (region steps only)
+    hmm_base_qualities: Optional[np.ndarray] = None   # HMM_BASE_QUALITIES_TAG, set by computeRegionLikelihoods
+
+
+@dataclass
+class RegionSteps:
+    """CudaLoglessPairHMM.RegionSteps: the PairHMMLikelihoodCalculationEngine fields behind the fused steps."""
+    pcrRateFactor: float = 3.0                  # PCRErrorModel CONSERVATIVE; 0 = NONE
+    baseQualityScoreThreshold: int = 18
+    disableCapReadQualitiesToMapQ: bool = False
+    log10GlobalReadMismappingRate: float = -4.5
+    symmetricallyNormalizeAllelesToReference: bool = False
+    filterPoorly: bool = True
+    expectedErrorRatePerBase: float = 0.02
+    dynamicDisqualification: bool = False
+    readDisqualificationScale: float = 1.0
 
 
 class StandardPairHMMInputScoreImputator:
@@ -110,6 +128,36 @@ class CudaLoglessPairHMM:
         for r in range(len(processedReads)):
             for hap_idx, hap in enumerate(logLikelihoods.alleles()):
                 logLikelihoods.set(hap_idx, r, self.mLogLikelihoodArray[r * n_haps + self._hap_index[bytes(hap)]])
+
+    def computeRegionLikelihoods(self, logLikelihoods: LikelihoodMatrix, clippedReads: List[Read], constantGCP: int,
+                                 steps: RegionSteps, referenceHaplotype: Optional[bytes] = None):
+        """modifyReadQualities -> PairHMM -> normalizeLikelihoods -> filterPoorlyModeledEvidence in one GPU call.
+        Fills the matrix with the normalised likelihoods of all reads and returns the indexes of the reads to remove."""
+        if not clippedReads:
+            return []
+        if not self._initialized:
+            raise RuntimeError("Must call initialize before calling computeRegionLikelihoods")
+        imputator = StandardPairHMMInputScoreImputator(constantGCP)
+        rows = []
+        for r in clippedReads:
+            ins, dele, gcp = imputator.impute(r)
+            rows.append((r.bases, np.asarray(r.base_quals, dtype=np.uint8), ins, dele, gcp))
+        batch = Batch.single_unit(rows, self._haps)
+        ref = -1 if referenceHaplotype is None else self._hap_index[bytes(referenceHaplotype)]
+        res = self._hmm.compute_regions(
+            batch, [min(255, r.mapping_quality) for r in clippedReads], [ref], pcr_rate_factor=steps.pcrRateFactor,
+            base_quality_score_threshold=steps.baseQualityScoreThreshold, disable_cap_to_mapq=steps.disableCapReadQualitiesToMapQ,
+            log10_global_read_mismapping_rate=steps.log10GlobalReadMismappingRate,
+            symmetric=steps.symmetricallyNormalizeAllelesToReference, filter_poorly=steps.filterPoorly,
+            expected_error_rate_per_base=steps.expectedErrorRatePerBase, dynamic_disqualification=steps.dynamicDisqualification,
+            read_disqualification_scale=steps.readDisqualificationScale)
+        n_reads = len(clippedReads)
+        for hap_idx, hap in enumerate(logLikelihoods.alleles()):
+            column = self._hap_index[bytes(hap)] * n_reads
+            logLikelihoods.values[hap_idx, :] = res["lk"][column:column + n_reads]
+        for k, r in enumerate(clippedReads):
+            r.hmm_base_qualities = res["base_q"][batch.read_off[k]:batch.read_off[k + 1]].copy()
+        return [int(k) for k in np.nonzero(res["keep"] == 0)[0]]
 
     def getLogLikelihoodArray(self):
         return self.mLogLikelihoodArray

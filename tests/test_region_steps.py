@@ -258,3 +258,36 @@ def test_region_steps_argument_errors():
         assert e.value.code == native.ERR_INVALID_ARG
         # and the handle still works
         assert np.isfinite(hmm.compute_regions(b, mapq, None)["lk"]).all()
+
+
+@pytest.mark.gpu
+def test_region_steps_through_the_plugin_mirror():
+    # the call PairHMMLikelihoodCalculationEngine.computeReadLikelihoods would make (java/patches/...regionSteps.patch)
+    from gatk_b200.pairhmm import Implementation, LikelihoodMatrix, PairHMMNativeArguments, Read, RegionSteps
+    rng = np.random.default_rng(12)
+    hap = np.frombuffer(_low_complexity(rng, 200), dtype=np.uint8)
+    alt = hap.copy()
+    alt[100] = ord("A") if alt[100] != ord("A") else ord("C")
+    haps = [hap.tobytes(), alt.tobytes()]
+    reads = []
+    for k in range(30):
+        off = int(rng.integers(0, 100))
+        src = alt if k % 2 else hap
+        bases = src[off:off + 100].copy()
+        if k % 10 == 9:
+            bases = np.frombuffer(bytes(rng.choice(list(b"ACGT"), 100).astype(np.uint8)), dtype=np.uint8)   # garbage read: must be dropped
+        reads.append(Read(bases.tobytes(), np.full(100, 30, np.uint8), mapping_quality=60 if k % 7 else 10))
+    hmm = Implementation.CUDA_LOGLESS_CACHING.makeNewHMM(PairHMMNativeArguments())
+    try:
+        hmm.initialize(haps)
+        matrix = LikelihoodMatrix(list(reversed(haps)), len(reads))     # the matrix may order the alleles differently
+        drop = hmm.computeRegionLikelihoods(matrix, reads, 10, RegionSteps(), referenceHaplotype=haps[0])
+    finally:
+        hmm.close()
+    b = Batch.single_unit([(r.bases, r.base_quals, np.full(100, 45, np.uint8), np.full(100, 45, np.uint8), np.full(100, 10, np.uint8)) for r in reads], haps)
+    want = _oracle_regions(b, np.array([r.mapping_quality for r in reads], np.uint8), np.array([0], np.int32))
+    assert np.abs(matrix.values[::-1].ravel() - want["lk"]).max() <= 1e-4
+    # garbage reads and the MAPQ-10 reads (every base quality floored to 6: 0.75^100 < 1e-8) are dropped
+    assert drop == [int(k) for k in np.nonzero(want["keep"] == 0)[0]] == [0, 7, 9, 14, 19, 21, 28, 29]
+    assert all(np.array_equal(r.hmm_base_qualities, want["base_q"][k * 100:(k + 1) * 100]) for k, r in enumerate(reads))
+    assert (reads[0].hmm_base_qualities == 6).all() and (reads[1].hmm_base_qualities == 30).all()   # MAPQ 10 < threshold 18 -> 6
