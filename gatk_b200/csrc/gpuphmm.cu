@@ -1217,6 +1217,10 @@ struct gphmm {
         std::vector<int64_t> read_off, hap_off;
         std::vector<gphmm_unit> units;
         double *out;
+        bool has_rs = false;             // gphmm_submit_regions: region steps (parameters + caller-owned output arrays)
+        gphmm_region_steps rs{};
+        std::vector<uint8_t> mapq;
+        std::vector<int32_t> ref_hap;
         int rc = 1;  // 1 = pending
         std::string err;
     };
@@ -1419,7 +1423,20 @@ void worker_main(gphmm *h) {
             std::unique_lock<std::mutex> lk(h->q_mu);
             h->q_cv.wait(lk, [&] { return h->stop || !h->queue.empty(); });
             if (h->queue.empty()) return;
-            for (size_t k = 0; k < h->queue.size() && k < MAX_COALESCE; ++k) jobs.push_back(h->queue[k]);
+            // merge the longest prefix of the queue that asks for the same thing (plain, or region steps with equal parameters)
+            auto same_request = [](const gphmm::Job &a, const gphmm::Job &b) {
+                if (a.has_rs != b.has_rs) return false;
+                if (!a.has_rs) return true;
+                return a.rs.flags == b.rs.flags && a.rs.pcr_rate_factor == b.rs.pcr_rate_factor &&
+                       a.rs.base_quality_score_threshold == b.rs.base_quality_score_threshold &&
+                       a.rs.log10_global_read_mismapping_rate == b.rs.log10_global_read_mismapping_rate &&
+                       a.rs.expected_error_rate_per_base == b.rs.expected_error_rate_per_base &&
+                       a.rs.read_disqualification_scale == b.rs.read_disqualification_scale;
+            };
+            for (size_t k = 0; k < h->queue.size() && k < MAX_COALESCE; ++k) {
+                if (k && !same_request(*h->queue[0], *h->queue[k])) break;
+                jobs.push_back(h->queue[k]);
+            }
         }
         gphmm_batch b;
         memset(&b, 0, sizeof b);
@@ -1427,8 +1444,13 @@ void worker_main(gphmm *h) {
         std::vector<int64_t> ro(1, 0), ho(1, 0);
         std::vector<gphmm_unit> units;
         std::vector<double> merged_out;
-        std::vector<int64_t> job_out_base(jobs.size(), 0), job_out_len(jobs.size(), 0);
+        std::vector<int64_t> job_out_base(jobs.size(), 0), job_out_len(jobs.size(), 0), job_read0(jobs.size(), 0), job_base0(jobs.size(), 0);
         double *out = nullptr;
+        // region steps of the (merged) batch: parameters of the first job, inputs/outputs concatenated like the reads
+        const bool has_rs = jobs[0]->has_rs;
+        gphmm_region_steps rs = jobs[0]->rs;
+        std::vector<uint8_t> m_mapq, m_keep, m_hq, m_hi, m_hd;
+        std::vector<int32_t> m_ref;
         if (jobs.size() == 1) {
             gphmm::Job &j = *jobs[0];
             b.read_bases = j.read_bases.data(); b.base_q = j.base_q.data(); b.ins_q = j.ins_q.data();
@@ -1437,11 +1459,20 @@ void worker_main(gphmm *h) {
             b.hap_bases = j.hap_bases.data(); b.hap_off = j.hap_off.data(); b.n_haps = (int64_t)j.hap_off.size() - 1;
             b.units = j.units.data(); b.n_units = (int64_t)j.units.size();
             out = j.out;
+            if (has_rs) {
+                rs.mapq = j.mapq.data();
+                rs.ref_hap = j.ref_hap.empty() ? nullptr : j.ref_hap.data();
+            }
         } else {
             int64_t out_cursor = 0;
             for (size_t q = 0; q < jobs.size(); ++q) {
                 gphmm::Job &j = *jobs[q];
                 const int64_t r0 = (int64_t)ro.size() - 1, h0 = (int64_t)ho.size() - 1, base0 = ro.back(), hbase0 = ho.back();
+                job_read0[q] = r0; job_base0[q] = base0;
+                if (has_rs) {
+                    m_mapq.insert(m_mapq.end(), j.mapq.begin(), j.mapq.begin() + (j.read_off.size() - 1));  // without the sentinel
+                    for (size_t k = 0; k < j.units.size(); ++k) m_ref.push_back(j.ref_hap.empty() ? -1 : j.ref_hap[k]);
+                }
                 rb.insert(rb.end(), j.read_bases.begin(), j.read_bases.end());
                 bq.insert(bq.end(), j.base_q.begin(), j.base_q.end());
                 iq.insert(iq.end(), j.ins_q.begin(), j.ins_q.end());
@@ -1465,11 +1496,28 @@ void worker_main(gphmm *h) {
             b.hap_bases = hb.data(); b.hap_off = ho.data(); b.n_haps = (int64_t)ho.size() - 1;
             b.units = units.data(); b.n_units = (int64_t)units.size();
             out = merged_out.data();
+            if (has_rs) {
+                bool want_keep = false, want_q = false, want_i = false, want_d = false;
+                for (auto &j : jobs) {
+                    want_keep = want_keep || j->rs.keep; want_q = want_q || j->rs.hmm_base_q;
+                    want_i = want_i || j->rs.hmm_ins_q; want_d = want_d || j->rs.hmm_del_q;
+                }
+                m_keep.assign(want_keep ? (size_t)b.n_reads + 1 : 0, 1);
+                m_hq.assign(want_q ? rb.size() + 1 : 0, 0); m_hi.assign(want_i ? rb.size() + 1 : 0, 0); m_hd.assign(want_d ? rb.size() + 1 : 0, 0);
+                m_mapq.push_back(0);
+                m_ref.push_back(-1);
+                rs.mapq = m_mapq.data();
+                rs.ref_hap = m_ref.data();
+                rs.keep = want_keep ? m_keep.data() : nullptr;
+                rs.hmm_base_q = want_q ? m_hq.data() : nullptr;
+                rs.hmm_ins_q = want_i ? m_hi.data() : nullptr;
+                rs.hmm_del_q = want_d ? m_hd.data() : nullptr;
+            }
         }
         int rc = GPHMM_OK;
         std::string err;
         try {
-            rc = run_batch(h, &b, out);
+            rc = run_batch(h, &b, out, has_rs ? &rs : nullptr);
         } catch (const Error &e) {
             rc = e.code; err = e.what();
         } catch (const std::exception &e) {
@@ -1479,7 +1527,16 @@ void worker_main(gphmm *h) {
         std::vector<std::string> errs(jobs.size(), err);
         if (jobs.size() > 1 && rc == GPHMM_OK) {
             for (size_t q = 0; q < jobs.size(); ++q)
+            {
                 if (job_out_len[q]) memcpy(jobs[q]->out, merged_out.data() + job_out_base[q], (size_t)job_out_len[q] * sizeof(double));
+                if (!has_rs) continue;
+                const gphmm::Job &j = *jobs[q];
+                const size_t nr = j.read_off.size() - 1, nb = (size_t)j.read_off.back();
+                if (j.rs.keep && nr) memcpy(j.rs.keep, m_keep.data() + job_read0[q], nr);
+                if (j.rs.hmm_base_q && nb) memcpy(j.rs.hmm_base_q, m_hq.data() + job_base0[q], nb);
+                if (j.rs.hmm_ins_q && nb) memcpy(j.rs.hmm_ins_q, m_hi.data() + job_base0[q], nb);
+                if (j.rs.hmm_del_q && nb) memcpy(j.rs.hmm_del_q, m_hd.data() + job_base0[q], nb);
+            }
         } else if (jobs.size() > 1) {
             // something in the merged batch is bad (e.g. a quality out of range): rerun the jobs one by one so that
             // only the offending ticket reports the error
@@ -1493,8 +1550,11 @@ void worker_main(gphmm *h) {
                 one.hap_bases = j.hap_bases.data(); one.hap_off = j.hap_off.data(); one.n_haps = (int64_t)j.hap_off.size() - 1;
                 one.units = j.units.data(); one.n_units = (int64_t)j.units.size();
                 rcs[q] = GPHMM_OK; errs[q].clear();
+                gphmm_region_steps one_rs = j.rs;
+                one_rs.mapq = j.mapq.data();
+                one_rs.ref_hap = j.ref_hap.empty() ? nullptr : j.ref_hap.data();
                 try {
-                    rcs[q] = run_batch(h, &one, j.out);
+                    rcs[q] = run_batch(h, &one, j.out, j.has_rs ? &one_rs : nullptr);
                 } catch (const Error &e) {
                     rcs[q] = e.code; errs[q] = e.what();
                 } catch (const std::exception &e) {
@@ -1512,6 +1572,20 @@ void worker_main(gphmm *h) {
         }
         h->done_cv.notify_all();
     }
+}
+
+void validate_region_steps(const gphmm_batch *batch, const gphmm_region_steps *steps) {
+    if (!steps || steps->struct_size != (int32_t)sizeof(gphmm_region_steps)) throw Error(GPHMM_ERR_INVALID_ARG, "steps is null or has the wrong struct_size");
+    if (batch->n_reads > 0 && !steps->mapq) throw Error(GPHMM_ERR_INVALID_ARG, "steps.mapq is null");
+    // AlleleLikelihoods.java:417-418: the cap must be negative and not NaN
+    if (!(steps->log10_global_read_mismapping_rate < 0.0)) throw Error(GPHMM_ERR_INVALID_ARG, "log10_global_read_mismapping_rate must be negative");
+    if (!(steps->pcr_rate_factor >= 0.0) || !(steps->expected_error_rate_per_base >= 0.0)) throw Error(GPHMM_ERR_INVALID_ARG, "negative rate in steps");
+    if (steps->base_quality_score_threshold < -128 || steps->base_quality_score_threshold > 127) throw Error(GPHMM_ERR_INVALID_ARG, "base_quality_score_threshold is a Java byte");
+    if (steps->ref_hap)
+        for (int64_t u = 0; u < batch->n_units; ++u) {
+            const int64_t nh = batch->units[u].hap_end - batch->units[u].hap_begin;
+            if (steps->ref_hap[u] < -1 || steps->ref_hap[u] >= nh) throw Error(GPHMM_ERR_INVALID_ARG, "ref_hap out of range");
+        }
 }
 
 template <typename F> int guarded(gphmm *h, F &&f) {
@@ -1632,26 +1706,17 @@ int gphmm_compute(gphmm_t *h, const gphmm_batch *batch, double *out) {
 int gphmm_compute_regions(gphmm_t *h, const gphmm_batch *batch, const gphmm_region_steps *steps, double *out) {
     if (!h) return GPHMM_ERR_INVALID_ARG;
     return guarded(h, [&]() -> int {
-        if (!steps || steps->struct_size != (int32_t)sizeof(gphmm_region_steps)) throw Error(GPHMM_ERR_INVALID_ARG, "steps is null or has the wrong struct_size");
         if (!batch) throw Error(GPHMM_ERR_INVALID_ARG, "batch is null");
-        if (batch->n_reads > 0 && !steps->mapq) throw Error(GPHMM_ERR_INVALID_ARG, "steps.mapq is null");
-        // AlleleLikelihoods.java:417-418: the cap must be negative and not NaN
-        if (!(steps->log10_global_read_mismapping_rate < 0.0)) throw Error(GPHMM_ERR_INVALID_ARG, "log10_global_read_mismapping_rate must be negative");
-        if (steps->pcr_rate_factor < 0.0 || !(steps->expected_error_rate_per_base >= 0.0)) throw Error(GPHMM_ERR_INVALID_ARG, "negative rate in steps");
-        if (steps->base_quality_score_threshold < -128 || steps->base_quality_score_threshold > 127) throw Error(GPHMM_ERR_INVALID_ARG, "base_quality_score_threshold is a Java byte");
-        if (steps->ref_hap)
-            for (int64_t u = 0; u < batch->n_units; ++u) {
-                const int64_t nh = batch->units[u].hap_end - batch->units[u].hap_begin;
-                if (steps->ref_hap[u] < -1 || steps->ref_hap[u] >= nh) throw Error(GPHMM_ERR_INVALID_ARG, "ref_hap out of range");
-            }
+        validate_region_steps(batch, steps);
         return run_batch(h, batch, out, steps);
     });
 }
 
-int gphmm_submit(gphmm_t *h, const gphmm_batch *b, double *out, uint64_t *ticket) {
+static int submit_job(gphmm_t *h, const gphmm_batch *b, const gphmm_region_steps *steps, double *out, uint64_t *ticket) {
     if (!h || !ticket) return GPHMM_ERR_INVALID_ARG;
     return guarded(h, [&]() -> int {
         validate_batch(b);
+        if (steps) validate_region_steps(b, steps);
         if (b->n_units > 0 && !out) throw Error(GPHMM_ERR_INVALID_ARG, "out is null");
         auto job = std::make_shared<gphmm::Job>();
         const int64_t nb = b->n_reads ? b->read_off[b->n_reads] : 0, hb = b->n_haps ? b->hap_off[b->n_haps] : 0;
@@ -1669,6 +1734,16 @@ int gphmm_submit(gphmm_t *h, const gphmm_batch *b, double *out, uint64_t *ticket
             job->read_off.assign(1, 0);
             job->hap_off.assign(1, 0);
         }
+        if (steps) {
+            job->has_rs = true;
+            job->rs = *steps;  // parameters and the caller-owned output arrays (valid until gphmm_wait, like `out`)
+            if (b->n_units > 0) {
+                job->mapq.assign(steps->mapq, steps->mapq + b->n_reads);
+                if (steps->ref_hap) job->ref_hap.assign(steps->ref_hap, steps->ref_hap + b->n_units);
+            }
+            job->mapq.push_back(0);  // never an empty vector: data() stays a valid pointer
+            job->rs.mapq = nullptr; job->rs.ref_hap = nullptr;
+        }
         job->out = out;
         {
             std::lock_guard<std::mutex> lk(h->q_mu);
@@ -1679,6 +1754,13 @@ int gphmm_submit(gphmm_t *h, const gphmm_batch *b, double *out, uint64_t *ticket
         h->q_cv.notify_all();
         return GPHMM_OK;
     });
+}
+
+int gphmm_submit(gphmm_t *h, const gphmm_batch *b, double *out, uint64_t *ticket) { return submit_job(h, b, nullptr, out, ticket); }
+
+int gphmm_submit_regions(gphmm_t *h, const gphmm_batch *b, const gphmm_region_steps *steps, double *out, uint64_t *ticket) {
+    if (!steps) return GPHMM_ERR_INVALID_ARG;
+    return submit_job(h, b, steps, out, ticket);
 }
 
 int gphmm_wait(gphmm_t *h, uint64_t ticket) {

@@ -64,7 +64,7 @@ RS_DISABLE_CAP_TO_MAPQ, RS_SYMMETRIC_NORMALIZE, RS_FILTER_POORLY, RS_DYNAMIC_DIS
 UNIT_DTYPE = np.dtype([("read_begin", "<i8"), ("read_end", "<i8"), ("hap_begin", "<i8"), ("hap_end", "<i8"), ("out_off", "<i8")])
 
 EXPORTS = ["gphmm_abi_version", "gphmm_device_count", "gphmm_strerror", "gphmm_create", "gphmm_destroy",
-           "gphmm_last_error", "gphmm_compute", "gphmm_compute_regions", "gphmm_submit", "gphmm_wait", "gphmm_prepare", "gphmm_run_prepared",
+           "gphmm_last_error", "gphmm_compute", "gphmm_compute_regions", "gphmm_submit_regions", "gphmm_submit", "gphmm_wait", "gphmm_prepare", "gphmm_run_prepared",
            "gphmm_release_prepared", "gphmm_get_stats", "gphmm_reset_stats", "gphmm_plan_stats", "gphmm_host_alloc", "gphmm_host_free"]
 
 
@@ -100,6 +100,9 @@ def load_library():
     L.gphmm_compute.argtypes = [ctypes.c_void_p, ctypes.POINTER(_Batch), ctypes.c_void_p]
     L.gphmm_compute_regions.restype = ctypes.c_int
     L.gphmm_compute_regions.argtypes = [ctypes.c_void_p, ctypes.POINTER(_Batch), ctypes.POINTER(_RegionSteps), ctypes.c_void_p]
+    L.gphmm_submit_regions.restype = ctypes.c_int
+    L.gphmm_submit_regions.argtypes = [ctypes.c_void_p, ctypes.POINTER(_Batch), ctypes.POINTER(_RegionSteps), ctypes.c_void_p,
+                                       ctypes.POINTER(ctypes.c_uint64)]
     L.gphmm_submit.restype = ctypes.c_int
     L.gphmm_submit.argtypes = [ctypes.c_void_p, ctypes.POINTER(_Batch), ctypes.c_void_p, ctypes.POINTER(ctypes.c_uint64)]
     L.gphmm_wait.restype = ctypes.c_int
@@ -316,13 +319,12 @@ class GpuPhmm:
         self._check(self._L.gphmm_compute(self._h, ctypes.byref(b), out.ctypes.data))
         return out
 
-    def compute_regions(self, batch, mapq, ref_hap=None, pcr_rate_factor=3.0, base_quality_score_threshold=18,
-                        disable_cap_to_mapq=False, log10_global_read_mismapping_rate=-4.5, symmetric=False,
-                        filter_poorly=True, expected_error_rate_per_base=0.02, dynamic_disqualification=False,
-                        read_disqualification_scale=1.0, want_quals=True):
-        """gphmm_compute_regions: modifyReadQualities -> PairHMM -> normalizeLikelihoods -> filterPoorlyModeledEvidence
-        on the device.  Returns a dict: lk (flat, per unit allele-major [h*nReads + r]), keep (per read),
-        base_q / ins_q / del_q (the qualities the kernel used, when want_quals)."""
+    @staticmethod
+    def _region_steps(batch, mapq, ref_hap, pcr_rate_factor=3.0, base_quality_score_threshold=18, disable_cap_to_mapq=False,
+                      log10_global_read_mismapping_rate=-4.5, symmetric=False, filter_poorly=True,
+                      expected_error_rate_per_base=0.02, dynamic_disqualification=False, read_disqualification_scale=1.0,
+                      want_quals=True):
+        """-> (gphmm_region_steps, result dict, arrays to keep alive)"""
         n_reads = len(batch.read_off) - 1
         mapq = np.ascontiguousarray(mapq, dtype=np.uint8)
         if len(mapq) != n_reads:
@@ -352,9 +354,26 @@ class GpuPhmm:
                 a = np.zeros(max(n, 1), dtype=np.uint8)
                 setattr(rs, field, a.ctypes.data)
                 res[name] = a[:n]
+        return rs, res, (mapq, ref_hap, keep)
+
+    def compute_regions(self, batch, mapq, ref_hap=None, **params):
+        """gphmm_compute_regions: modifyReadQualities -> PairHMM -> normalizeLikelihoods -> filterPoorlyModeledEvidence
+        on the device.  Returns a dict: lk (flat, per unit allele-major [h*nReads + r]), keep (per read),
+        base_q / ins_q / del_q (the qualities the kernel used, when want_quals).  params: see _region_steps."""
+        rs, res, _alive = self._region_steps(batch, mapq, ref_hap, **params)
         b = batch.c_struct()
-        self._check(self._L.gphmm_compute_regions(self._h, ctypes.byref(b), ctypes.byref(rs), out.ctypes.data))
+        self._check(self._L.gphmm_compute_regions(self._h, ctypes.byref(b), ctypes.byref(rs), res["lk"].ctypes.data))
         return res
+
+    def submit_regions(self, batch, mapq, ref_hap=None, **params):
+        """gphmm_submit_regions; wait(ticket) returns the result dict of compute_regions"""
+        rs, res, alive = self._region_steps(batch, mapq, ref_hap, **params)
+        b = batch.c_struct()
+        t = ctypes.c_uint64(0)
+        self._check(self._L.gphmm_submit_regions(self._h, ctypes.byref(b), ctypes.byref(rs), res["lk"].ctypes.data, ctypes.byref(t)))
+        res["_alive"] = alive
+        self._pending[t.value] = res
+        return t.value
 
     def submit(self, batch, out=None):
         if out is None:

@@ -158,6 +158,10 @@ typedef struct gphmm_region_steps {
 /* Like gphmm_compute with the steps above fused in.  out[u.out_off + h*nReads + r] is the NORMALISED log10 likelihood,
  * allele-major like AlleleLikelihoods.valuesBySampleIndex[s][a][r] (AlleleLikelihoods.java:71-74). */
 int gphmm_compute_regions(gphmm_t *h, const gphmm_batch *batch, const gphmm_region_steps *steps, double *out);
+/* Asynchronous form, same queue and ticket space as gphmm_submit: inputs (mapq and ref_hap included) are copied before
+ * the call returns; out and the output arrays named in `steps` must stay valid until gphmm_wait(ticket) returns.
+ * Queued requests with equal parameters are merged into one GPU batch. */
+int gphmm_submit_regions(gphmm_t *h, const gphmm_batch *batch, const gphmm_region_steps *steps, double *out, uint64_t *ticket);
 
 /* Statistics accumulate over calls until reset. */
 int gphmm_get_stats(const gphmm_t *h, gphmm_stats *out);

@@ -291,3 +291,32 @@ def test_region_steps_through_the_plugin_mirror():
     assert drop == [int(k) for k in np.nonzero(want["keep"] == 0)[0]] == [0, 7, 9, 14, 19, 21, 28, 29]
     assert all(np.array_equal(r.hmm_base_qualities, want["base_q"][k * 100:(k + 1) * 100]) for k, r in enumerate(reads))
     assert (reads[0].hmm_base_qualities == 6).all() and (reads[1].hmm_base_qualities == 30).all()   # MAPQ 10 < threshold 18 -> 6
+
+
+@pytest.mark.gpu
+def test_region_steps_async_queue_merges_equal_requests():
+    # gphmm_submit_regions: requests with equal parameters are merged into one GPU batch, others run on their own,
+    # plain submits can be interleaved, every ticket gets exactly the synchronous result
+    with GpuPhmm() as hmm:
+        jobs = []
+        for k in range(10):
+            b, mapq = _raw_batch(100 + k, n_units=2)
+            ref = np.zeros(len(b.units), np.int32)
+            params = dict(pcr_rate_factor=1.0) if k in (4, 5) else {}
+            jobs.append((b, mapq, ref, params))
+        tickets = []
+        for k, (b, mapq, ref, params) in enumerate(jobs):
+            if k == 7:
+                tickets.append(("plain", hmm.submit(b)))
+            else:
+                tickets.append(("regions", hmm.submit_regions(b, mapq, ref, **params)))
+        for (kind, t), (b, mapq, ref, params) in zip(tickets, jobs):
+            got = hmm.wait(t)
+            if kind == "plain":
+                assert np.array_equal(got, hmm.compute(b))
+                continue
+            want = hmm.compute_regions(b, mapq, ref, **params)
+            for name in ("keep", "base_q", "ins_q", "del_q"):
+                assert np.array_equal(got[name], want[name]), name
+            # merged batches may split haplotype groups differently (bigger chunk): same numbers to float rounding
+            assert np.abs(got["lk"] - want["lk"]).max() < 1e-5
