@@ -186,7 +186,8 @@ std::vector<std::pair<int64_t, int64_t>> split_units(const gphmm_batch *b, int64
     while (u < b->n_units) {
         // ramp up: the first chunks are small so that the GPU starts early while the host is still staging
         const size_t ci = out.size();
-        chunk_cells = (!ramp_up || ci >= 3) ? full_cells : std::max<int64_t>(full_cells >> (3 - ci), 1);
+        // (2.5e8 cells = a handful of regions, then doubling: the planner threads stay ahead of the GPU from there on)
+        chunk_cells = (!ramp_up || ci >= 16) ? full_cells : std::min<int64_t>(full_cells, (int64_t)250000000 << ci);
         int64_t cells = 0, bytes = 0, pairs = 0, u_end = u;
         int64_t r_lo = INT64_MAX, r_hi = 0;
         while (u_end < b->n_units) {
@@ -347,7 +348,8 @@ UnitSched plan_unit_sharing(const gphmm_batch *b, const gphmm_unit &un, uint32_t
         while (is < snaps.size() && snaps[snap_by_pos[is]].pos + 32 <= x) ++is;
         const bool end_on = ie < (size_t)n && end_pos[ie] <= x;
         const bool snap_on = is < snaps.size() && snaps[snap_by_pos[is]].pos <= x;
-        if (!end_on && !snap_on) {
+        static const bool all_checked = getenv("GPHMM_ALL_CHECKED") != nullptr;  // experiment: cost of the checked loop
+        if (!end_on && !snap_on && !all_checked) {
             if (seg.n_chk) { c.segments.push_back(seg); clear_seg(); }
             seg.n_free += y - x;
             continue;
@@ -395,10 +397,17 @@ void plan_chunk(const gphmm_batch *b, int64_t u0, int64_t u1, bool force_fp64, b
             if (e == o) continue;
             const uint8_t qi = b->ins_q[o], qd = b->del_q[o], qc = b->gcp[o];
             if (qi > 127 || qd > 127 || qc > 127) continue;
-            bool flat = true, sym = true;
-            for (int64_t i = o; i < e; ++i) {
-                flat = flat && b->ins_q[i] == qi && b->del_q[i] == qd && b->gcp[i] == qc;
-                sym = sym && b->ins_q[i] == b->del_q[i] && b->gcp[i] == qc && b->ins_q[i] <= SYM_MAX_GAP_QUAL;
+            // an array is constant iff it equals itself shifted by one (memcmp is vectorised)
+            const size_t n1 = (size_t)(e - o - 1);
+            const bool flat_c = memcmp(b->gcp + o, b->gcp + o + 1, n1) == 0;
+            const bool flat = flat_c && memcmp(b->ins_q + o, b->ins_q + o + 1, n1) == 0 && memcmp(b->del_q + o, b->del_q + o + 1, n1) == 0;
+            bool sym = flat_c && memcmp(b->ins_q + o, b->del_q + o, n1 + 1) == 0;
+            if (sym && !flat) {
+                uint8_t mx = 0;
+                for (int64_t i = o; i < e; ++i) mx = std::max(mx, b->ins_q[i]);
+                sym = mx <= SYM_MAX_GAP_QUAL;
+            } else if (sym) {
+                sym = qi <= SYM_MAX_GAP_QUAL;
             }
             if (flat && !(pcr_hint && qi == qd)) {  // the PCR indel model (region steps) will lower ins and del together
                 bool seen = false;
@@ -1210,24 +1219,54 @@ struct gphmm {
     std::string last_error = "";
     Stats stats;
     std::mutex run_mu;  // one batch at a time per handle (compute vs. the async worker)
-    // async queue
-    struct Job {
+    // async queue.  gphmm_submit appends the caller's arrays to the open *arena* (pinned, reused, SoA like gphmm_batch);
+    // the worker takes a whole arena as ONE batch: one host copy per byte, no merge step, DMA straight from the arena.
+    struct PinVec {  // growable pinned byte array that keeps its contents
+        uint8_t *p = nullptr;
+        size_t size = 0, cap = 0;
+        void append(const uint8_t *src, size_t n) {
+            if (size + n > cap) {
+                const size_t want = std::max<size_t>((size + n) * 2, (size_t)4 << 20);
+                void *q = nullptr;
+                CK(cudaHostAlloc(&q, want, cudaHostAllocPortable));
+                if (p) { memcpy(q, p, size); cudaFreeHost(p); }
+                p = (uint8_t *)q; cap = want;
+            }
+            if (n) memcpy(p + size, src, n);
+            size += n;
+        }
+        ~PinVec() { if (p) cudaFreeHost(p); }
+    };
+    struct JobRef {
         uint64_t ticket;
-        std::vector<uint8_t> read_bases, base_q, ins_q, del_q, gcp, hap_bases;
-        std::vector<int64_t> read_off, hap_off;
-        std::vector<gphmm_unit> units;
         double *out;
-        bool has_rs = false;             // gphmm_submit_regions: region steps (parameters + caller-owned output arrays)
-        gphmm_region_steps rs{};
+        int64_t out_base, out_len, read0, n_reads, base0, n_bases, unit0, n_units;
+        gphmm_region_steps rs;  // region steps: the caller's output arrays (keep, hmm_*)
+    };
+    struct Arena {
+        PinVec rb, bq, iq, dq, gq, hb;
+        std::vector<int64_t> ro, ho;
+        std::vector<gphmm_unit> units;
         std::vector<uint8_t> mapq;
         std::vector<int32_t> ref_hap;
-        int rc = 1;  // 1 = pending
-        std::string err;
+        bool has_rs = false;
+        gphmm_region_steps rs{};  // parameters shared by every job of the arena
+        int64_t out_len = 0;
+        std::vector<JobRef> jobs;
+        void clear() {
+            rb.size = bq.size = iq.size = dq.size = gq.size = hb.size = 0;
+            ro.assign(1, 0); ho.assign(1, 0);
+            units.clear(); mapq.clear(); ref_hap.clear(); jobs.clear();
+            has_rs = false; out_len = 0;
+        }
     };
+    struct Done { uint64_t ticket; int rc; std::string err; };
     std::mutex q_mu;
     std::condition_variable q_cv, done_cv;
-    std::deque<std::shared_ptr<Job>> queue;
-    std::vector<std::shared_ptr<Job>> finished;
+    std::deque<std::unique_ptr<Arena>> pending;      // FIFO; only the back one accepts more jobs
+    std::vector<std::unique_ptr<Arena>> free_arenas;
+    std::vector<Done> finished;                      // completed, not yet waited for
+    uint64_t completed_upto = 0;                     // tickets complete in order
     uint64_t next_ticket = 1;
     std::thread worker;
     bool stop = false;
@@ -1413,162 +1452,108 @@ int run_batch(gphmm *h, const gphmm_batch *b, double *out, const gphmm_region_st
     return GPHMM_OK;
 }
 
-// The asynchronous cross-region batching queue: everything that is queued when the worker wakes up is merged into ONE
-// batch, so that many small (region, sample) units fill the GPU together instead of running one launch set each.
+// The asynchronous cross-region batching queue: every arena (= everything submitted with equal parameters while the
+// worker was busy) is ONE batch, so that many small (region, sample) units fill the GPU together.
 void worker_main(gphmm *h) {
-    constexpr size_t MAX_COALESCE = 4096;
+    static const bool trace = getenv("GPHMM_TRACE") != nullptr;
+    std::vector<double> merged_out;
+    std::vector<uint8_t> m_keep, m_hq, m_hi, m_hd;
     for (;;) {
-        std::vector<std::shared_ptr<gphmm::Job>> jobs;
+        std::unique_ptr<gphmm::Arena> ar;
         {
             std::unique_lock<std::mutex> lk(h->q_mu);
-            h->q_cv.wait(lk, [&] { return h->stop || !h->queue.empty(); });
-            if (h->queue.empty()) return;
-            // merge the longest prefix of the queue that asks for the same thing (plain, or region steps with equal parameters)
-            auto same_request = [](const gphmm::Job &a, const gphmm::Job &b) {
-                if (a.has_rs != b.has_rs) return false;
-                if (!a.has_rs) return true;
-                return a.rs.flags == b.rs.flags && a.rs.pcr_rate_factor == b.rs.pcr_rate_factor &&
-                       a.rs.base_quality_score_threshold == b.rs.base_quality_score_threshold &&
-                       a.rs.log10_global_read_mismapping_rate == b.rs.log10_global_read_mismapping_rate &&
-                       a.rs.expected_error_rate_per_base == b.rs.expected_error_rate_per_base &&
-                       a.rs.read_disqualification_scale == b.rs.read_disqualification_scale;
-            };
-            for (size_t k = 0; k < h->queue.size() && k < MAX_COALESCE; ++k) {
-                if (k && !same_request(*h->queue[0], *h->queue[k])) break;
-                jobs.push_back(h->queue[k]);
-            }
+            h->q_cv.wait(lk, [&] { return h->stop || !h->pending.empty(); });
+            if (h->pending.empty()) return;
+            ar = std::move(h->pending.front());
+            h->pending.pop_front();
         }
+        const double t_wake = now_ms();
+        const size_t nj = ar->jobs.size();
         gphmm_batch b;
         memset(&b, 0, sizeof b);
-        std::vector<uint8_t> rb, bq, iq, dq, gq, hb;
-        std::vector<int64_t> ro(1, 0), ho(1, 0);
-        std::vector<gphmm_unit> units;
-        std::vector<double> merged_out;
-        std::vector<int64_t> job_out_base(jobs.size(), 0), job_out_len(jobs.size(), 0), job_read0(jobs.size(), 0), job_base0(jobs.size(), 0);
-        double *out = nullptr;
-        // region steps of the (merged) batch: parameters of the first job, inputs/outputs concatenated like the reads
-        const bool has_rs = jobs[0]->has_rs;
-        gphmm_region_steps rs = jobs[0]->rs;
-        std::vector<uint8_t> m_mapq, m_keep, m_hq, m_hi, m_hd;
-        std::vector<int32_t> m_ref;
-        if (jobs.size() == 1) {
-            gphmm::Job &j = *jobs[0];
-            b.read_bases = j.read_bases.data(); b.base_q = j.base_q.data(); b.ins_q = j.ins_q.data();
-            b.del_q = j.del_q.data(); b.gcp = j.gcp.data(); b.read_off = j.read_off.data();
-            b.n_reads = (int64_t)j.read_off.size() - 1;
-            b.hap_bases = j.hap_bases.data(); b.hap_off = j.hap_off.data(); b.n_haps = (int64_t)j.hap_off.size() - 1;
-            b.units = j.units.data(); b.n_units = (int64_t)j.units.size();
-            out = j.out;
-            if (has_rs) {
-                rs.mapq = j.mapq.data();
-                rs.ref_hap = j.ref_hap.empty() ? nullptr : j.ref_hap.data();
-            }
-        } else {
-            int64_t out_cursor = 0;
-            for (size_t q = 0; q < jobs.size(); ++q) {
-                gphmm::Job &j = *jobs[q];
-                const int64_t r0 = (int64_t)ro.size() - 1, h0 = (int64_t)ho.size() - 1, base0 = ro.back(), hbase0 = ho.back();
-                job_read0[q] = r0; job_base0[q] = base0;
-                if (has_rs) {
-                    m_mapq.insert(m_mapq.end(), j.mapq.begin(), j.mapq.begin() + (j.read_off.size() - 1));  // without the sentinel
-                    for (size_t k = 0; k < j.units.size(); ++k) m_ref.push_back(j.ref_hap.empty() ? -1 : j.ref_hap[k]);
-                }
-                rb.insert(rb.end(), j.read_bases.begin(), j.read_bases.end());
-                bq.insert(bq.end(), j.base_q.begin(), j.base_q.end());
-                iq.insert(iq.end(), j.ins_q.begin(), j.ins_q.end());
-                dq.insert(dq.end(), j.del_q.begin(), j.del_q.end());
-                gq.insert(gq.end(), j.gcp.begin(), j.gcp.end());
-                hb.insert(hb.end(), j.hap_bases.begin(), j.hap_bases.end());
-                for (size_t k = 1; k < j.read_off.size(); ++k) ro.push_back(base0 + j.read_off[k]);
-                for (size_t k = 1; k < j.hap_off.size(); ++k) ho.push_back(hbase0 + j.hap_off[k]);
-                int64_t len = 0;
-                for (const gphmm_unit &u : j.units) len = std::max(len, u.out_off + (u.read_end - u.read_begin) * (u.hap_end - u.hap_begin));
-                job_out_base[q] = out_cursor; job_out_len[q] = len;
-                for (gphmm_unit u : j.units) {
-                    u.read_begin += r0; u.read_end += r0; u.hap_begin += h0; u.hap_end += h0; u.out_off += out_cursor;
-                    units.push_back(u);
-                }
-                out_cursor += len;
-            }
-            merged_out.assign((size_t)out_cursor, 0.0);
-            b.read_bases = rb.data(); b.base_q = bq.data(); b.ins_q = iq.data(); b.del_q = dq.data(); b.gcp = gq.data();
-            b.read_off = ro.data(); b.n_reads = (int64_t)ro.size() - 1;
-            b.hap_bases = hb.data(); b.hap_off = ho.data(); b.n_haps = (int64_t)ho.size() - 1;
-            b.units = units.data(); b.n_units = (int64_t)units.size();
+        b.read_bases = ar->rb.p; b.base_q = ar->bq.p; b.ins_q = ar->iq.p; b.del_q = ar->dq.p; b.gcp = ar->gq.p;
+        b.read_off = ar->ro.data(); b.n_reads = (int64_t)ar->ro.size() - 1;
+        b.hap_bases = ar->hb.p; b.hap_off = ar->ho.data(); b.n_haps = (int64_t)ar->ho.size() - 1;
+        b.units = ar->units.data(); b.n_units = (int64_t)ar->units.size();
+        const bool direct = nj == 1;  // a single job writes straight into the caller's arrays
+        double *out = direct ? ar->jobs[0].out : nullptr;
+        gphmm_region_steps rs = ar->rs;
+        if (!direct) {
+            merged_out.resize((size_t)ar->out_len + 1);
             out = merged_out.data();
-            if (has_rs) {
+        }
+        if (ar->has_rs) {
+            ar->mapq.push_back(0); ar->ref_hap.push_back(-1);  // never empty: data() is a valid pointer
+            rs.mapq = ar->mapq.data();
+            rs.ref_hap = ar->ref_hap.data();
+            if (direct) {
+                rs.keep = ar->jobs[0].rs.keep; rs.hmm_base_q = ar->jobs[0].rs.hmm_base_q;
+                rs.hmm_ins_q = ar->jobs[0].rs.hmm_ins_q; rs.hmm_del_q = ar->jobs[0].rs.hmm_del_q;
+            } else {
                 bool want_keep = false, want_q = false, want_i = false, want_d = false;
-                for (auto &j : jobs) {
-                    want_keep = want_keep || j->rs.keep; want_q = want_q || j->rs.hmm_base_q;
-                    want_i = want_i || j->rs.hmm_ins_q; want_d = want_d || j->rs.hmm_del_q;
+                for (const auto &j : ar->jobs) {
+                    want_keep = want_keep || j.rs.keep; want_q = want_q || j.rs.hmm_base_q;
+                    want_i = want_i || j.rs.hmm_ins_q; want_d = want_d || j.rs.hmm_del_q;
                 }
-                m_keep.assign(want_keep ? (size_t)b.n_reads + 1 : 0, 1);
-                m_hq.assign(want_q ? rb.size() + 1 : 0, 0); m_hi.assign(want_i ? rb.size() + 1 : 0, 0); m_hd.assign(want_d ? rb.size() + 1 : 0, 0);
-                m_mapq.push_back(0);
-                m_ref.push_back(-1);
-                rs.mapq = m_mapq.data();
-                rs.ref_hap = m_ref.data();
+                if (want_keep) m_keep.resize((size_t)b.n_reads + 1);
+                if (want_q) m_hq.resize(ar->rb.size + 1);
+                if (want_i) m_hi.resize(ar->rb.size + 1);
+                if (want_d) m_hd.resize(ar->rb.size + 1);
                 rs.keep = want_keep ? m_keep.data() : nullptr;
                 rs.hmm_base_q = want_q ? m_hq.data() : nullptr;
                 rs.hmm_ins_q = want_i ? m_hi.data() : nullptr;
                 rs.hmm_del_q = want_d ? m_hd.data() : nullptr;
             }
         }
-        int rc = GPHMM_OK;
+        auto run = [&](const gphmm_batch &bb, const gphmm_region_steps &rr, std::string &err) -> int {
+            try {
+                return run_batch(h, &bb, out, ar->has_rs ? &rr : nullptr);
+            } catch (const Error &e) {
+                err = e.what();
+                return e.code;
+            } catch (const std::exception &e) {
+                err = e.what();
+                return GPHMM_ERR_CUDA;
+            }
+        };
         std::string err;
-        try {
-            rc = run_batch(h, &b, out, has_rs ? &rs : nullptr);
-        } catch (const Error &e) {
-            rc = e.code; err = e.what();
-        } catch (const std::exception &e) {
-            rc = GPHMM_ERR_CUDA; err = e.what();
-        }
-        std::vector<int> rcs(jobs.size(), rc);
-        std::vector<std::string> errs(jobs.size(), err);
-        if (jobs.size() > 1 && rc == GPHMM_OK) {
-            for (size_t q = 0; q < jobs.size(); ++q)
-            {
-                if (job_out_len[q]) memcpy(jobs[q]->out, merged_out.data() + job_out_base[q], (size_t)job_out_len[q] * sizeof(double));
-                if (!has_rs) continue;
-                const gphmm::Job &j = *jobs[q];
-                const size_t nr = j.read_off.size() - 1, nb = (size_t)j.read_off.back();
-                if (j.rs.keep && nr) memcpy(j.rs.keep, m_keep.data() + job_read0[q], nr);
-                if (j.rs.hmm_base_q && nb) memcpy(j.rs.hmm_base_q, m_hq.data() + job_base0[q], nb);
-                if (j.rs.hmm_ins_q && nb) memcpy(j.rs.hmm_ins_q, m_hi.data() + job_base0[q], nb);
-                if (j.rs.hmm_del_q && nb) memcpy(j.rs.hmm_del_q, m_hd.data() + job_base0[q], nb);
-            }
-        } else if (jobs.size() > 1) {
-            // something in the merged batch is bad (e.g. a quality out of range): rerun the jobs one by one so that
-            // only the offending ticket reports the error
-            for (size_t q = 0; q < jobs.size(); ++q) {
-                gphmm::Job &j = *jobs[q];
-                gphmm_batch one;
-                memset(&one, 0, sizeof one);
-                one.read_bases = j.read_bases.data(); one.base_q = j.base_q.data(); one.ins_q = j.ins_q.data();
-                one.del_q = j.del_q.data(); one.gcp = j.gcp.data(); one.read_off = j.read_off.data();
-                one.n_reads = (int64_t)j.read_off.size() - 1;
-                one.hap_bases = j.hap_bases.data(); one.hap_off = j.hap_off.data(); one.n_haps = (int64_t)j.hap_off.size() - 1;
-                one.units = j.units.data(); one.n_units = (int64_t)j.units.size();
-                rcs[q] = GPHMM_OK; errs[q].clear();
-                gphmm_region_steps one_rs = j.rs;
-                one_rs.mapq = j.mapq.data();
-                one_rs.ref_hap = j.ref_hap.empty() ? nullptr : j.ref_hap.data();
-                try {
-                    rcs[q] = run_batch(h, &one, j.out, j.has_rs ? &one_rs : nullptr);
-                } catch (const Error &e) {
-                    rcs[q] = e.code; errs[q] = e.what();
-                } catch (const std::exception &e) {
-                    rcs[q] = GPHMM_ERR_CUDA; errs[q] = e.what();
-                }
+        const int rc = nj ? run(b, rs, err) : GPHMM_OK;
+        std::vector<int> rcs(nj, rc);
+        std::vector<std::string> errs(nj, err);
+        if (!direct && rc != GPHMM_OK) {
+            // something in the merged batch is bad (e.g. a quality out of range): rerun the jobs one by one (each is a
+            // sub-range of the arena's units) so that only the offending ticket reports the error
+            for (size_t q = 0; q < nj; ++q) {
+                const gphmm::JobRef &j = ar->jobs[q];
+                gphmm_batch one = b;
+                one.units = ar->units.data() + j.unit0;
+                one.n_units = j.n_units;
+                gphmm_region_steps one_rs = rs;
+                one_rs.ref_hap = ar->ref_hap.data() + j.unit0;
+                errs[q].clear();
+                rcs[q] = run(one, one_rs, errs[q]);
             }
         }
+        if (!direct)
+            for (size_t q = 0; q < nj; ++q) {
+                const gphmm::JobRef &j = ar->jobs[q];
+                if (rcs[q] != GPHMM_OK) continue;
+                if (j.out_len) memcpy(j.out, merged_out.data() + j.out_base, (size_t)j.out_len * sizeof(double));
+                if (!ar->has_rs) continue;
+                if (j.rs.keep && j.n_reads) memcpy(j.rs.keep, m_keep.data() + j.read0, (size_t)j.n_reads);
+                if (j.rs.hmm_base_q && j.n_bases) memcpy(j.rs.hmm_base_q, m_hq.data() + j.base0, (size_t)j.n_bases);
+                if (j.rs.hmm_ins_q && j.n_bases) memcpy(j.rs.hmm_ins_q, m_hi.data() + j.base0, (size_t)j.n_bases);
+                if (j.rs.hmm_del_q && j.n_bases) memcpy(j.rs.hmm_del_q, m_hd.data() + j.base0, (size_t)j.n_bases);
+            }
+        if (trace) fprintf(stderr, "[gpuphmm] queue: batch of %zu jobs took %.3f ms\n", nj, now_ms() - t_wake);
         {
             std::lock_guard<std::mutex> lk(h->q_mu);
-            for (size_t q = 0; q < jobs.size(); ++q) {
-                jobs[q]->rc = rcs[q]; jobs[q]->err = errs[q];
-                h->queue.pop_front();
-                h->finished.push_back(jobs[q]);
+            for (size_t q = 0; q < nj; ++q) {
+                h->finished.push_back({ar->jobs[q].ticket, rcs[q], errs[q]});
+                h->completed_upto = ar->jobs[q].ticket;
             }
+            ar->clear();
+            h->free_arenas.push_back(std::move(ar));
         }
         h->done_cv.notify_all();
     }
@@ -1714,42 +1699,66 @@ int gphmm_compute_regions(gphmm_t *h, const gphmm_batch *batch, const gphmm_regi
 
 static int submit_job(gphmm_t *h, const gphmm_batch *b, const gphmm_region_steps *steps, double *out, uint64_t *ticket) {
     if (!h || !ticket) return GPHMM_ERR_INVALID_ARG;
+    constexpr size_t MAX_JOBS_PER_ARENA = 4096;
     return guarded(h, [&]() -> int {
         validate_batch(b);
         if (steps) validate_region_steps(b, steps);
         if (b->n_units > 0 && !out) throw Error(GPHMM_ERR_INVALID_ARG, "out is null");
-        auto job = std::make_shared<gphmm::Job>();
-        const int64_t nb = b->n_reads ? b->read_off[b->n_reads] : 0, hb = b->n_haps ? b->hap_off[b->n_haps] : 0;
-        if (b->n_units > 0) {
-            job->read_bases.assign(b->read_bases, b->read_bases + nb);
-            job->base_q.assign(b->base_q, b->base_q + nb);
-            job->ins_q.assign(b->ins_q, b->ins_q + nb);
-            job->del_q.assign(b->del_q, b->del_q + nb);
-            job->gcp.assign(b->gcp, b->gcp + nb);
-            job->hap_bases.assign(b->hap_bases, b->hap_bases + hb);
-            job->read_off.assign(b->read_off, b->read_off + b->n_reads + 1);
-            job->hap_off.assign(b->hap_off, b->hap_off + b->n_haps + 1);
-            job->units.assign(b->units, b->units + b->n_units);
-        } else {
-            job->read_off.assign(1, 0);
-            job->hap_off.assign(1, 0);
-        }
-        if (steps) {
-            job->has_rs = true;
-            job->rs = *steps;  // parameters and the caller-owned output arrays (valid until gphmm_wait, like `out`)
-            if (b->n_units > 0) {
-                job->mapq.assign(steps->mapq, steps->mapq + b->n_reads);
-                if (steps->ref_hap) job->ref_hap.assign(steps->ref_hap, steps->ref_hap + b->n_units);
-            }
-            job->mapq.push_back(0);  // never an empty vector: data() stays a valid pointer
-            job->rs.mapq = nullptr; job->rs.ref_hap = nullptr;
-        }
-        job->out = out;
+        const bool empty = b->n_units == 0;
+        const int64_t n_reads = empty ? 0 : b->n_reads, n_haps = empty ? 0 : b->n_haps;
+        const int64_t nb = n_reads ? b->read_off[n_reads] : 0, hb = n_haps ? b->hap_off[n_haps] : 0;
+        auto same_request = [&](const gphmm::Arena &a) {
+            if (a.has_rs != (steps != nullptr)) return false;
+            if (!steps) return true;
+            return a.rs.flags == steps->flags && a.rs.pcr_rate_factor == steps->pcr_rate_factor &&
+                   a.rs.base_quality_score_threshold == steps->base_quality_score_threshold &&
+                   a.rs.log10_global_read_mismapping_rate == steps->log10_global_read_mismapping_rate &&
+                   a.rs.expected_error_rate_per_base == steps->expected_error_rate_per_base &&
+                   a.rs.read_disqualification_scale == steps->read_disqualification_scale;
+        };
         {
             std::lock_guard<std::mutex> lk(h->q_mu);
-            job->ticket = h->next_ticket++;
-            h->queue.push_back(job);
-            *ticket = job->ticket;
+            CK(cudaSetDevice(h->devices[0]->ordinal));  // the arenas are pinned (portable) allocations
+            gphmm::Arena *ar = h->pending.empty() ? nullptr : h->pending.back().get();
+            if (!ar || ar->jobs.size() >= MAX_JOBS_PER_ARENA || (!ar->jobs.empty() && !same_request(*ar))) {
+                std::unique_ptr<gphmm::Arena> fresh;
+                if (!h->free_arenas.empty()) { fresh = std::move(h->free_arenas.back()); h->free_arenas.pop_back(); }
+                else fresh.reset(new gphmm::Arena());
+                fresh->clear();
+                h->pending.push_back(std::move(fresh));
+                ar = h->pending.back().get();
+            }
+            if (ar->jobs.empty()) {
+                ar->has_rs = steps != nullptr;
+                if (steps) ar->rs = *steps;
+            }
+            gphmm::JobRef j;
+            memset(&j.rs, 0, sizeof j.rs);
+            if (steps) j.rs = *steps;
+            j.out = out;
+            j.read0 = (int64_t)ar->ro.size() - 1; j.n_reads = n_reads;
+            j.base0 = ar->ro.back(); j.n_bases = nb;
+            j.unit0 = (int64_t)ar->units.size(); j.n_units = b->n_units;
+            j.out_base = ar->out_len; j.out_len = 0;
+            const int64_t h0 = (int64_t)ar->ho.size() - 1, hbase0 = ar->ho.back();
+            ar->rb.append(b->read_bases, (size_t)nb); ar->bq.append(b->base_q, (size_t)nb); ar->iq.append(b->ins_q, (size_t)nb);
+            ar->dq.append(b->del_q, (size_t)nb); ar->gq.append(b->gcp, (size_t)nb); ar->hb.append(b->hap_bases, (size_t)hb);
+            for (int64_t k = 1; k <= n_reads; ++k) ar->ro.push_back(j.base0 + b->read_off[k]);
+            for (int64_t k = 1; k <= n_haps; ++k) ar->ho.push_back(hbase0 + b->hap_off[k]);
+            for (int64_t k = 0; k < b->n_units; ++k) {
+                gphmm_unit u = b->units[k];
+                j.out_len = std::max(j.out_len, u.out_off + (u.read_end - u.read_begin) * (u.hap_end - u.hap_begin));
+                u.read_begin += j.read0; u.read_end += j.read0; u.hap_begin += h0; u.hap_end += h0; u.out_off += j.out_base;
+                ar->units.push_back(u);
+            }
+            if (steps) {
+                if (n_reads) ar->mapq.insert(ar->mapq.end(), steps->mapq, steps->mapq + n_reads);
+                for (int64_t k = 0; k < b->n_units; ++k) ar->ref_hap.push_back(steps->ref_hap ? steps->ref_hap[k] : -1);
+            }
+            ar->out_len += j.out_len;
+            j.ticket = h->next_ticket++;
+            ar->jobs.push_back(j);
+            *ticket = j.ticket;
         }
         h->q_cv.notify_all();
         return GPHMM_OK;
@@ -1769,15 +1778,13 @@ int gphmm_wait(gphmm_t *h, uint64_t ticket) {
     if (ticket == 0 || ticket >= h->next_ticket) { h->last_error = "unknown ticket"; return GPHMM_ERR_BAD_TICKET; }
     for (;;) {
         for (size_t i = 0; i < h->finished.size(); ++i)
-            if (h->finished[i]->ticket == ticket) {
-                auto job = h->finished[i];
+            if (h->finished[i].ticket == ticket) {
+                const int rc = h->finished[i].rc;
+                if (rc != GPHMM_OK) h->last_error = h->finished[i].err;
                 h->finished.erase(h->finished.begin() + i);
-                if (job->rc != GPHMM_OK) h->last_error = job->err;
-                return job->rc;
+                return rc;
             }
-        bool pending = false;
-        for (auto &j : h->queue) pending = pending || j->ticket == ticket;
-        if (!pending) { h->last_error = "ticket already waited for"; return GPHMM_ERR_BAD_TICKET; }
+        if (ticket <= h->completed_upto) { h->last_error = "ticket already waited for"; return GPHMM_ERR_BAD_TICKET; }
         h->done_cv.wait(lk);
     }
 }
