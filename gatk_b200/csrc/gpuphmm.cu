@@ -559,6 +559,15 @@ struct DeviceChunk {
     size_t off_sums = 0, off_out = 0, off_rtasks = 0, off_rsums = 0, off_counters = 0, off_err = 0, off_class = 0, off_raw = 0, off_keep = 0, work_bytes = 0;
     cudaEvent_t ev_start = nullptr, ev_f32 = nullptr, ev_f64 = nullptr, ev_done = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join[N_AUX] = {nullptr};  // bucket kernels run on side streams
+    // small chunks defer the fp64 redo: the rescue kernels are only launched (by finish_chunk) when the downloaded
+    // counter says some pair needs them -- three launches less on the latency path of a per-region call
+    bool lazy_rescue = false;
+    KernelArgs lazy_ka;
+    EpilogueArgs lazy_ea;
+    PostArgs lazy_pa;
+    bool lazy_post = false;
+    cudaStream_t lazy_tail = nullptr;
+    struct Device *lazy_dev = nullptr;
     bool busy = false;
     void release() {
         reads.release(); meta.release(); work.release(); bnd.release(); snap.release(); h_meta.release(); h_reads.release(); h_out.release(); h_modq.release();
@@ -861,6 +870,52 @@ void upload_chunk(Device &dev, DeviceChunk &dc, const gphmm_batch *b, const Chun
     (void)dev;
 }
 
+constexpr int64_t LAZY_RESCUE_CELLS = 2000000000;  // chunks below this defer the fp64 redo until the counter is known
+
+// fp64 redo of the chunk's rescue list on `tail`: persistent grids, task count read on the device.
+int launch_rescue(Device &dev, DeviceChunk &dc, const ChunkPlan &c, KernelArgs ka, const EpilogueArgs &ea, cudaStream_t tail) {
+    int launches = 0;
+    uint8_t *work = (uint8_t *)dc.work.p;
+    uint32_t *counters = (uint32_t *)(work + dc.off_counters);
+    constexpr int FP64_BUCKET = N_FP32_BUCKETS;
+    {
+        // fp64 redo of the rescue list: persistent grid, task count read on the device
+            const KernelInfo &ki = dev.info(FP64_BUCKET, c.n_codes);
+            const uint32_t grid = std::min<uint32_t>(c.n_pairs, (uint32_t)(dev.n_sms * ki.ctas_per_sm));
+            ka.tasks = (const Task *)(work + dc.off_rtasks);
+            ka.n_tasks = 0;
+            ka.n_tasks_ptr = counters + 10;
+            ka.sums = work + dc.off_rsums;
+            // flat-quality reads: constant-coefficient fp64 kernel, one launch per class
+            for (int cl = 0; cl < c.n_classes; ++cl) {
+                const Tables &tb2 = tables();
+                FlatCoefD fd;
+                const int qi = c.class_qi[cl], qd = c.class_qd[cl], qc = c.class_qc[cl];
+                const double ei = tb2.eps[qi], ed = tb2.eps[qd], ec = tb2.eps[qc], tIM = 1.0 - ec;
+                const int mn = std::min(qi, qd), mx = std::max(qi, qd);
+                fd.a = tb2.m2m[((mx * (mx + 1)) >> 1) + mn];
+                fd.b = tIM * ei; fd.c = tIM * ed; fd.g = ec; fd.d = ec; fd.tmi = ei; fd.tim = tIM;
+                fd.class_id = (uint32_t)cl; fd.qi = qi; fd.qd = qd; fd.qc = qc;
+                const KernelInfo &kf = dev.info(FLAT_F64_KEY, c.n_codes);
+                ka.counter = counters + 12 + cl;
+                void *fargs[] = {&ka, &fd};
+                CK(cudaLaunchKernel(kf.fn, dim3(std::min<uint32_t>(c.n_pairs, (uint32_t)(dev.n_sms * kf.ctas_per_sm))), dim3(32), fargs, kf.smem, tail));
+                ++launches;
+            }
+            ka.counter = counters + 9;
+            ka.bnd = dc.bnd.p;
+            ka.bnd_stride = c.max_hap_len + 1;
+            void *args[] = {&ka};
+            CK(cudaLaunchKernel(ki.fn, dim3(grid), dim3(32), args, ki.smem, tail));
+            ++launches;
+            phmm_epilogue_rescue<<<std::min<uint32_t>((c.n_pairs + 127) / 128, 1024), 128, 0, tail>>>(
+                (const Task *)(work + dc.off_rtasks), counters + 10, ea.rescue_capacity, (const double *)(work + dc.off_rsums), ea.out);
+            CK(cudaGetLastError());
+            ++launches;
+        }
+    return launches;
+}
+
 // Queue every kernel of the chunk on `st` (no host sync).  Returns the number of launches.
 int launch_chunk(Device &dev, DeviceChunk &dc, const ChunkPlan &c, cudaStream_t st, cudaStream_t tail, cudaStream_t *aux, const RunOptions &opt, bool download) {
     int launches = 0;
@@ -1080,45 +1135,17 @@ int launch_chunk(Device &dev, DeviceChunk &dc, const ChunkPlan &c, cudaStream_t 
         CK(cudaEventRecord(dc.ev_f32, st));
         CK(cudaStreamWaitEvent(tail, dc.ev_f32, 0));  // the closing kernels run at high priority in the reserved headroom
         if (ea.n_units) {
-            phmm_epilogue_f32<<<std::min<uint32_t>(ea.n_units, 4096), 128, 0, tail>>>(ea);
+            const uint32_t per_unit = (c.n_pairs / ea.n_units + 127) / 128;
+            const dim3 egrid(std::min<uint32_t>(ea.n_units, 4096), ea.n_units < 296 ? std::max<uint32_t>(1, std::min<uint32_t>(per_unit, 16)) : 1);
+            phmm_epilogue_f32<<<egrid, 128, 0, tail>>>(ea);
             CK(cudaGetLastError());
             ++launches;
         }
-        // fp64 redo of the rescue list: persistent grid, task count read on the device
-        if (n_tasks_total) {
-            const KernelInfo &ki = dev.info(FP64_BUCKET, c.n_codes);
-            const uint32_t grid = std::min<uint32_t>(c.n_pairs, (uint32_t)(dev.n_sms * ki.ctas_per_sm));
-            ka.tasks = (const Task *)(work + dc.off_rtasks);
-            ka.n_tasks = 0;
-            ka.n_tasks_ptr = counters + 10;
-            ka.sums = work + dc.off_rsums;
-            // flat-quality reads: constant-coefficient fp64 kernel, one launch per class
-            for (int cl = 0; cl < c.n_classes; ++cl) {
-                const Tables &tb2 = tables();
-                FlatCoefD fd;
-                const int qi = c.class_qi[cl], qd = c.class_qd[cl], qc = c.class_qc[cl];
-                const double ei = tb2.eps[qi], ed = tb2.eps[qd], ec = tb2.eps[qc], tIM = 1.0 - ec;
-                const int mn = std::min(qi, qd), mx = std::max(qi, qd);
-                fd.a = tb2.m2m[((mx * (mx + 1)) >> 1) + mn];
-                fd.b = tIM * ei; fd.c = tIM * ed; fd.g = ec; fd.d = ec; fd.tmi = ei; fd.tim = tIM;
-                fd.class_id = (uint32_t)cl; fd.qi = qi; fd.qd = qd; fd.qc = qc;
-                const KernelInfo &kf = dev.info(FLAT_F64_KEY, c.n_codes);
-                ka.counter = counters + 12 + cl;
-                void *fargs[] = {&ka, &fd};
-                CK(cudaLaunchKernel(kf.fn, dim3(std::min<uint32_t>(c.n_pairs, (uint32_t)(dev.n_sms * kf.ctas_per_sm))), dim3(32), fargs, kf.smem, tail));
-                ++launches;
-            }
-            ka.counter = counters + 9;
-            ka.bnd = dc.bnd.p;
-            ka.bnd_stride = c.max_hap_len + 1;
-            void *args[] = {&ka};
-            CK(cudaLaunchKernel(ki.fn, dim3(grid), dim3(32), args, ki.smem, tail));
-            ++launches;
-            phmm_epilogue_rescue<<<std::min<uint32_t>((c.n_pairs + 127) / 128, 1024), 128, 0, tail>>>(
-                (const Task *)(work + dc.off_rtasks), counters + 10, ea.rescue_capacity, (const double *)(work + dc.off_rsums), ea.out);
-            CK(cudaGetLastError());
-            ++launches;
-        }
+        // fp64 redo of the rescue list.  Large chunks queue it unconditionally (the list length is read on the device, no
+        // host round trip); small chunks look at the downloaded counter first (finish_chunk).
+        dc.lazy_rescue = download && !opt.force_fp64 && c.cells < LAZY_RESCUE_CELLS && n_tasks_total > 0;
+        dc.lazy_ka = ka; dc.lazy_ea = ea; dc.lazy_tail = tail; dc.lazy_dev = &dev;
+        if (n_tasks_total && !dc.lazy_rescue) launches += launch_rescue(dev, dc, c, ka, ea, tail);
         CK(cudaEventRecord(dc.ev_f64, tail));
         // region steps: normalizeLikelihoods + filterPoorlyModeledEvidence, read-major -> allele-major
         if (opt.rs && ea.n_units) {
@@ -1140,7 +1167,9 @@ int launch_chunk(Device &dev, DeviceChunk &dc, const ChunkPlan &c, cudaStream_t 
             phmm_normalize_filter_kernel<<<std::min<uint32_t>(ea.n_units, 148 * 8), 128, 0, tail>>>(pa);
             CK(cudaGetLastError());
             ++launches;
+            dc.lazy_pa = pa;
         }
+        dc.lazy_post = opt.rs && ea.n_units;
     }
     if (download) {
         const size_t bytes = (dc.off_err + 16) - dc.off_out;
@@ -1165,6 +1194,20 @@ void finish_chunk(DeviceChunk &dc, const gphmm_batch *b, const ChunkPlan &c, dou
         const int err = *(const int *)(ho + (dc.off_err - dc.off_out));
         if (err) throw Error(GPHMM_ERR_BAD_QUAL, "quality score out of range: ins/del/gcp > 127 or base qual 255");
         rescued = counters[10];
+        if (dc.lazy_rescue && rescued > 0) {
+            // deferred fp64 redo of a small chunk: now that the list is known to be non-empty, run it and download again
+            int n = launch_rescue(*dc.lazy_dev, dc, c, dc.lazy_ka, dc.lazy_ea, dc.lazy_tail);
+            if (dc.lazy_post) {
+                phmm_normalize_filter_kernel<<<std::min<uint32_t>(dc.lazy_pa.n_units, 148 * 8), 128, 0, dc.lazy_tail>>>(dc.lazy_pa);
+                CK(cudaGetLastError());
+                ++n;
+            }
+            CK(cudaMemcpyAsync(dc.h_out.p, (uint8_t *)dc.work.p + dc.off_out, (dc.off_err + 16) - dc.off_out, cudaMemcpyDeviceToHost, dc.lazy_tail));
+            CK(cudaStreamSynchronize(dc.lazy_tail));
+            std::lock_guard<std::mutex> lk(stats.mu);
+            stats.s.kernel_launches += n;
+            stats.s.d2h_bytes += (int64_t)((dc.off_err + 16) - dc.off_out);
+        }
         if (out) {
             const double *res = (const double *)ho;
             for (int64_t u = c.u0; u < c.u1; ++u) {

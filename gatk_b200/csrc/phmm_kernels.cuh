@@ -1001,7 +1001,8 @@ __global__ void __launch_bounds__(128) phmm_epilogue_f32(const EpilogueArgs e)
     for (uint32_t u = blockIdx.x; u < e.n_units; u += gridDim.x) {
         const UnitDesc d = e.units[u];
         const uint32_t n = d.n_reads * d.n_haps;
-        for (uint32_t k = threadIdx.x; k < n; k += blockDim.x) {
+        // gridDim.y CTAs share a unit (chunks with few units: a per-region call has one)
+        for (uint32_t k = blockIdx.y * blockDim.x + threadIdx.x; k < n; k += blockDim.x * gridDim.y) {
             const uint32_t r = k / d.n_haps, h = k - r * d.n_haps;
             const float s = sums[d.out_base + k];
             const uint32_t H = e.hap_len[d.hap_first + h];
