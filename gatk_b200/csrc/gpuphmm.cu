@@ -117,7 +117,7 @@ struct PinBuf {
 constexpr int N_SLOTS = 3;         // chunks in flight per device: one computing, one finishing (epilogue/D2H), one being staged
 constexpr int N_FP32_BUCKETS = 9;  // K = 1..8 plain, bucket 8 = striped K=8 (reads of 256+ bases)
 constexpr int N_AUX = N_FP32_BUCKETS + 8 * (MAX_FLAT_CLASSES + MAX_SYM_CLASSES);  // side streams: general buckets + flat (class, bucket)
-constexpr int N_COUNTERS = 128;    // [0..8] general fp32 buckets, [9] fp64 queue, [10] n_rescue, [11] forced fp64 queue,
+constexpr int N_COUNTERS = 128;    // [0..8] general fp32 buckets, [9] fp64 queue, [10] n_rescue, [11] n_deep, [120] deep cursor,
                                    // [16 + 8*c + k] flat-quality kernels: class c, bucket k
 
 // Host-side plan of one device chunk: which units, and every metadata array the kernels need.
@@ -552,11 +552,13 @@ struct DeviceChunk {
     PinBuf h_reads; // pinned bounce buffer when the caller's arrays are pageable
     PinBuf h_out;   // pinned result buffer (out doubles + [keep flags] + counters + err)
     PinBuf h_modq;  // region steps: pinned image of the modified base/ins/del qualities (only when the caller wants them)
+    PinBuf h_raw;   // region steps: pinned image of the un-normalised likelihoods (only when the caller wants them)
     size_t read_stride = 0;
     size_t off_read_off = 0, off_streams = 0, off_hap_len = 0, off_hap_stream_off = 0, off_units = 0, off_tasks = 0, meta_bytes = 0;
     size_t off_sstreams = 0, off_pass = 0, off_segs = 0, off_sched = 0, off_mapq = 0;
     DevBuf snap;    // snapshot slabs of the fast kernels (prefix sharing)
-    size_t off_sums = 0, off_out = 0, off_rtasks = 0, off_rsums = 0, off_counters = 0, off_err = 0, off_class = 0, off_raw = 0, off_keep = 0, work_bytes = 0;
+    DevBuf deep;    // DP rows of phmm_exact_f64_kernel (last rescue tier)
+    size_t off_sums = 0, off_out = 0, off_rtasks = 0, off_rsums = 0, off_counters = 0, off_err = 0, off_class = 0, off_raw = 0, off_keep = 0, off_deep = 0, work_bytes = 0;
     cudaEvent_t ev_start = nullptr, ev_f32 = nullptr, ev_f64 = nullptr, ev_done = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join[N_AUX] = {nullptr};  // bucket kernels run on side streams
     // small chunks defer the fp64 redo: the rescue kernels are only launched (by finish_chunk) when the downloaded
@@ -570,7 +572,7 @@ struct DeviceChunk {
     struct Device *lazy_dev = nullptr;
     bool busy = false;
     void release() {
-        reads.release(); meta.release(); work.release(); bnd.release(); snap.release(); h_meta.release(); h_reads.release(); h_out.release(); h_modq.release();
+        reads.release(); meta.release(); work.release(); bnd.release(); snap.release(); deep.release(); h_meta.release(); h_reads.release(); h_out.release(); h_modq.release(); h_raw.release();
         if (ev_start) cudaEventDestroy(ev_start);
         if (ev_f32) cudaEventDestroy(ev_f32);
         if (ev_f64) cudaEventDestroy(ev_f64);
@@ -840,6 +842,7 @@ void upload_chunk(Device &dev, DeviceChunk &dc, const gphmm_batch *b, const Chun
     dc.off_rtasks = o; o = align_up(o + (force_fp64 ? 0 : np * sizeof(Task)), 16);
     dc.off_rsums = o; o = align_up(o + (force_fp64 ? 0 : np * 8), 16);
     dc.off_class = o; o = align_up(o + c.read_off.size(), 16);
+    dc.off_deep = o; o = align_up(o + np * 4, 16);  // deep list: rescue slots whose fp64 sum is not trustworthy either
     dc.work_bytes = o;
     dc.work.reserve(dc.work_bytes);
     dc.h_out.reserve(d2h_bytes);
@@ -909,7 +912,22 @@ int launch_rescue(Device &dev, DeviceChunk &dc, const ChunkPlan &c, KernelArgs k
             CK(cudaLaunchKernel(ki.fn, dim3(grid), dim3(32), args, ki.smem, tail));
             ++launches;
             phmm_epilogue_rescue<<<std::min<uint32_t>((c.n_pairs + 127) / 128, 1024), 128, 0, tail>>>(
-                (const Task *)(work + dc.off_rtasks), counters + 10, ea.rescue_capacity, (const double *)(work + dc.off_rsums), ea.out);
+                (const Task *)(work + dc.off_rtasks), counters + 10, ea.rescue_capacity, (const double *)(work + dc.off_rsums), ea.out,
+                counters + 11, (uint32_t *)(work + dc.off_deep));
+            CK(cudaGetLastError());
+            ++launches;
+            // last tier: the reference's own arithmetic for the pairs on the deep list (usually none)
+            constexpr uint32_t EXACT_CTAS = 8;
+            ExactArgs xa;
+            xa.tasks = (const Task *)(work + dc.off_rtasks);
+            xa.deep_list = (const uint32_t *)(work + dc.off_deep);
+            xa.n_deep = counters + 11;
+            xa.cursor = counters + 120;
+            xa.row_len = c.max_hap_len + 1;
+            dc.deep.reserve((size_t)6 * xa.row_len * EXACT_CTAS * 32 * sizeof(double));
+            xa.scratch = (double *)dc.deep.p;
+            xa.out = ea.out;
+            phmm_exact_f64_kernel<<<EXACT_CTAS, 32, 0, tail>>>(ka, xa);
             CK(cudaGetLastError());
             ++launches;
         }
@@ -1171,6 +1189,10 @@ int launch_chunk(Device &dev, DeviceChunk &dc, const ChunkPlan &c, cudaStream_t 
         }
         dc.lazy_post = opt.rs && ea.n_units;
     }
+    if (download && opt.rs && opt.rs->raw_lk && c.n_pairs) {
+        dc.h_raw.reserve((size_t)c.n_pairs * 8);
+        CK(cudaMemcpyAsync(dc.h_raw.p, work + dc.off_raw, (size_t)c.n_pairs * 8, cudaMemcpyDeviceToHost, tail));
+    }
     if (download) {
         const size_t bytes = (dc.off_err + 16) - dc.off_out;
         CK(cudaMemcpyAsync(dc.h_out.p, work + dc.off_out, bytes, cudaMemcpyDeviceToHost, tail));
@@ -1202,6 +1224,8 @@ void finish_chunk(DeviceChunk &dc, const gphmm_batch *b, const ChunkPlan &c, dou
                 CK(cudaGetLastError());
                 ++n;
             }
+            if (rs && rs->raw_lk && c.n_pairs)
+                CK(cudaMemcpyAsync(dc.h_raw.p, (uint8_t *)dc.work.p + dc.off_raw, (size_t)c.n_pairs * 8, cudaMemcpyDeviceToHost, dc.lazy_tail));
             CK(cudaMemcpyAsync(dc.h_out.p, (uint8_t *)dc.work.p + dc.off_out, (dc.off_err + 16) - dc.off_out, cudaMemcpyDeviceToHost, dc.lazy_tail));
             CK(cudaStreamSynchronize(dc.lazy_tail));
             std::lock_guard<std::mutex> lk(stats.mu);
@@ -1217,6 +1241,14 @@ void finish_chunk(DeviceChunk &dc, const gphmm_batch *b, const ChunkPlan &c, dou
             }
         }
         if (rs) {
+            if (rs->raw_lk) {
+                const double *raw = (const double *)dc.h_raw.p;
+                for (int64_t u = c.u0; u < c.u1; ++u) {
+                    const UnitDesc &d = c.units[u - c.u0];
+                    const size_t n = (size_t)d.n_reads * d.n_haps;
+                    if (n) memcpy(rs->raw_lk + b->units[u].out_off, raw + d.out_base, n * sizeof(double));
+                }
+            }
             if (rs->keep) {
                 const uint8_t *dk = ho + (dc.off_keep - dc.off_out);
                 for (int64_t u = c.u0; u < c.u1; ++u) {
@@ -1499,7 +1531,7 @@ int run_batch(gphmm *h, const gphmm_batch *b, double *out, const gphmm_region_st
 // worker was busy) is ONE batch, so that many small (region, sample) units fill the GPU together.
 void worker_main(gphmm *h) {
     static const bool trace = getenv("GPHMM_TRACE") != nullptr;
-    std::vector<double> merged_out;
+    std::vector<double> merged_out, m_raw;
     std::vector<uint8_t> m_keep, m_hq, m_hi, m_hd;
     for (;;) {
         std::unique_ptr<gphmm::Arena> ar;
@@ -1532,9 +1564,11 @@ void worker_main(gphmm *h) {
             if (direct) {
                 rs.keep = ar->jobs[0].rs.keep; rs.hmm_base_q = ar->jobs[0].rs.hmm_base_q;
                 rs.hmm_ins_q = ar->jobs[0].rs.hmm_ins_q; rs.hmm_del_q = ar->jobs[0].rs.hmm_del_q;
+                rs.raw_lk = ar->jobs[0].rs.raw_lk;
             } else {
-                bool want_keep = false, want_q = false, want_i = false, want_d = false;
+                bool want_keep = false, want_q = false, want_i = false, want_d = false, want_raw = false;
                 for (const auto &j : ar->jobs) {
+                    want_raw = want_raw || j.rs.raw_lk;
                     want_keep = want_keep || j.rs.keep; want_q = want_q || j.rs.hmm_base_q;
                     want_i = want_i || j.rs.hmm_ins_q; want_d = want_d || j.rs.hmm_del_q;
                 }
@@ -1546,6 +1580,8 @@ void worker_main(gphmm *h) {
                 rs.hmm_base_q = want_q ? m_hq.data() : nullptr;
                 rs.hmm_ins_q = want_i ? m_hi.data() : nullptr;
                 rs.hmm_del_q = want_d ? m_hd.data() : nullptr;
+                if (want_raw) m_raw.resize((size_t)ar->out_len + 1);
+                rs.raw_lk = want_raw ? m_raw.data() : nullptr;
             }
         }
         auto run = [&](const gphmm_batch &bb, const gphmm_region_steps &rr, std::string &err) -> int {
@@ -1583,6 +1619,7 @@ void worker_main(gphmm *h) {
                 if (rcs[q] != GPHMM_OK) continue;
                 if (j.out_len) memcpy(j.out, merged_out.data() + j.out_base, (size_t)j.out_len * sizeof(double));
                 if (!ar->has_rs) continue;
+                if (j.rs.raw_lk && j.out_len) memcpy(j.rs.raw_lk, m_raw.data() + j.out_base, (size_t)j.out_len * sizeof(double));
                 if (j.rs.keep && j.n_reads) memcpy(j.rs.keep, m_keep.data() + j.read0, (size_t)j.n_reads);
                 if (j.rs.hmm_base_q && j.n_bases) memcpy(j.rs.hmm_base_q, m_hq.data() + j.base0, (size_t)j.n_bases);
                 if (j.rs.hmm_ins_q && j.n_bases) memcpy(j.rs.hmm_ins_q, m_hi.data() + j.base0, (size_t)j.n_bases);

@@ -257,6 +257,7 @@ JNIEXPORT void JNICALL JNIFN(nativeComputeRegion)(JNIEnv *env, jclass, jlong han
     rs.ref_hap = &ref;
     rs.keep = kp.data();
     rs.hmm_base_q = hmmBaseQuals ? hq.data() : nullptr;
+    rs.raw_lk = nullptr;  // the plugin writes --pair-hmm-results-file from the plain call only
     std::vector<double> res(static_cast<size_t>(need) + 1);
     const int rc = gphmm_compute_regions(s->h, &b, &rs, res.data());
     if (rc != GPHMM_OK) {

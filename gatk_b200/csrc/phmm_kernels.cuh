@@ -1031,14 +1031,86 @@ __global__ void __launch_bounds__(128) phmm_epilogue_f32(const EpilogueArgs e)
     }
 }
 
-// rescue pass: one double sum per rescue slot -> its final output slot
+// rescue pass: one double sum per rescue slot -> its final output slot.  A sum that is zero, not finite or closer than
+// 2^142 to the denormal range cannot be trusted (the scaled fp64 states start 2^60 lower than Java's 2^1020): those
+// pairs go on the deep list for phmm_exact_f64_kernel.
+constexpr double DEEP_THRESHOLD_F64 = 0x1p-880;
+
 __global__ void __launch_bounds__(128) phmm_epilogue_rescue(const Task *tasks, const uint32_t *n_rescue, uint32_t capacity,
-                                                            const double *sums, double *out)
+                                                            const double *sums, double *out, uint32_t *n_deep, uint32_t *deep_list)
 {
     const uint32_t n = min(*n_rescue, capacity);
     for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
         const Task t = tasks[k];
-        out[t.hap_first] = log10(sums[k]) - log10_c0H(t.c0_exp, t.unit);
+        const double s = sums[k];
+        if (!(s >= DEEP_THRESHOLD_F64) || s > 1.0e308) {
+            deep_list[atomicAdd(n_deep, 1u)] = k;
+            continue;
+        }
+        out[t.hap_first] = log10(s) - log10_c0H(t.c0_exp, t.unit);
+    }
+}
+
+// Last tier: the reference's arithmetic itself (LoglessPairHMM.java:20-68, unscaled M/I/D, initial value 2^1020/H,
+// same operation order, no fused multiply-add), one thread per pair with its two DP rows in global scratch.  Only
+// pairs whose likelihood is below ~1e-550 get here (Java still returns finite values down to ~1e-631); speed is
+// irrelevant, agreement with Java double in its own underflow regime is the point.
+struct ExactArgs {
+    const Task *tasks;          // the chunk's rescue list
+    const uint32_t *deep_list;  // indices into it
+    const uint32_t *n_deep;
+    uint32_t *cursor;
+    double *scratch;            // 6 rows x row_len columns x (gridDim.x * blockDim.x) workers, column-major per worker
+    uint32_t row_len;           // max haplotype length + 1
+    double *out;
+};
+
+__global__ void __launch_bounds__(32) phmm_exact_f64_kernel(const KernelArgs g, const ExactArgs e)
+{
+    const uint32_t W = gridDim.x * blockDim.x, w = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t n = *e.n_deep;
+    const size_t plane = (size_t)e.row_len * W;
+    double *Mp = e.scratch + w, *Ip = Mp + plane, *Dp = Ip + plane, *Mc = Dp + plane, *Ic = Mc + plane, *Dc = Ic + plane;
+    for (;;) {
+        const uint32_t idx = atomicAdd(e.cursor, 1u);
+        if (idx >= n) break;
+        const Task t = e.tasks[e.deep_list[idx]];
+        const uint32_t ro = g.read_off[t.read];
+        const int R = (int)(g.read_off[t.read + 1] - ro), H = (int)t.unit;
+        const uint8_t *hap = g.streams + t.stream_off;
+        const double init = 0x1p1020 / (double)H;  // LoglessPairHMM.java:8,31
+        for (int j = 0; j <= H; ++j) { Mp[(size_t)j * W] = 0.0; Ip[(size_t)j * W] = 0.0; Dp[(size_t)j * W] = init; }
+        for (int i = 1; i <= R; ++i) {
+            const uint32_t q = min((uint32_t)g.rd_q[ro + i - 1], (uint32_t)MAX_QUAL), qi = min((uint32_t)g.rd_i[ro + i - 1], 127u);
+            const uint32_t qd = min((uint32_t)g.rd_d[ro + i - 1], 127u), qc = min((uint32_t)g.rd_c[ro + i - 1], 127u);
+            const uint32_t mn = min(qi, qd), mx = max(qi, qd);
+            // PairHMMModel.java:107-117
+            const double tMM = g.m2m[((mx * (mx + 1)) >> 1) + mn], tIM = 1.0 - c_eps[qc], tMI = c_eps[qi], tII = c_eps[qc];
+            const double tMD = c_eps[qd], tDD = c_eps[qc];
+            const double err = c_eps[q], pm = 1.0 - err, px = g.tristate_off ? err : err / 3.0;
+            const uint32_t x = g.rd_bases[ro + i - 1];
+            Mc[0] = 0.0; Ic[0] = 0.0; Dc[0] = 0.0;
+            double m_left = 0.0, d_left = 0.0;
+            for (int j = 1; j <= H; ++j) {
+                const uint32_t y = g.code_byte[hap[j - 1]];
+                const double prior = (x == y || x == (uint32_t)'N' || y == (uint32_t)'N') ? pm : px;  // :89-91
+                const size_t a = (size_t)(j - 1) * W, b = (size_t)j * W;
+                // :51-55, evaluated left to right like Java, products and sums rounded separately
+                const double u = __dadd_rn(__dadd_rn(__dmul_rn(Mp[a], tMM), __dmul_rn(Ip[a], tIM)), __dmul_rn(Dp[a], tIM));
+                const double m = __dmul_rn(prior, u);
+                const double ins = __dadd_rn(__dmul_rn(Mp[b], tMI), __dmul_rn(Ip[b], tII));
+                const double del = __dadd_rn(__dmul_rn(m_left, tMD), __dmul_rn(d_left, tDD));
+                Mc[b] = m; Ic[b] = ins; Dc[b] = del;
+                m_left = m; d_left = del;
+            }
+            double *tmp;
+            tmp = Mp; Mp = Mc; Mc = tmp;
+            tmp = Ip; Ip = Ic; Ic = tmp;
+            tmp = Dp; Dp = Dc; Dc = tmp;
+        }
+        double sum = 0.0;
+        for (int j = 1; j <= H; ++j) sum = __dadd_rn(sum, __dadd_rn(Mp[(size_t)j * W], Ip[(size_t)j * W]));  // :62-65
+        e.out[t.hap_first] = log10(sum) - 307.0505955772608;  // Math.log10(Math.pow(2, 1020)), :9
     }
 }
 

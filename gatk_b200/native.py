@@ -56,7 +56,7 @@ class _RegionSteps(ctypes.Structure):
                 ("log10_global_read_mismapping_rate", ctypes.c_double), ("expected_error_rate_per_base", ctypes.c_double),
                 ("read_disqualification_scale", ctypes.c_double), ("mapq", ctypes.c_void_p), ("ref_hap", ctypes.c_void_p),
                 ("keep", ctypes.c_void_p), ("hmm_base_q", ctypes.c_void_p), ("hmm_ins_q", ctypes.c_void_p),
-                ("hmm_del_q", ctypes.c_void_p)]
+                ("hmm_del_q", ctypes.c_void_p), ("raw_lk", ctypes.c_void_p)]
 
 
 RS_DISABLE_CAP_TO_MAPQ, RS_SYMMETRIC_NORMALIZE, RS_FILTER_POORLY, RS_DYNAMIC_DISQ = 1, 2, 4, 8
@@ -323,7 +323,7 @@ class GpuPhmm:
     def _region_steps(batch, mapq, ref_hap, pcr_rate_factor=3.0, base_quality_score_threshold=18, disable_cap_to_mapq=False,
                       log10_global_read_mismapping_rate=-4.5, symmetric=False, filter_poorly=True,
                       expected_error_rate_per_base=0.02, dynamic_disqualification=False, read_disqualification_scale=1.0,
-                      want_quals=True):
+                      want_quals=True, want_raw=True):
         """-> (gphmm_region_steps, result dict, arrays to keep alive)"""
         n_reads = len(batch.read_off) - 1
         mapq = np.ascontiguousarray(mapq, dtype=np.uint8)
@@ -348,6 +348,9 @@ class GpuPhmm:
             rs.ref_hap = ref_hap.ctypes.data
         rs.keep = keep.ctypes.data
         res = {"lk": out, "keep": keep[:n_reads]}
+        if want_raw:
+            res["raw"] = np.full(batch.n_out, np.nan, dtype=np.float64)
+            rs.raw_lk = res["raw"].ctypes.data
         if want_quals:
             n = len(batch.read_bases)
             for name, field in (("base_q", "hmm_base_q"), ("ins_q", "hmm_ins_q"), ("del_q", "hmm_del_q")):
@@ -359,7 +362,8 @@ class GpuPhmm:
     def compute_regions(self, batch, mapq, ref_hap=None, **params):
         """gphmm_compute_regions: modifyReadQualities -> PairHMM -> normalizeLikelihoods -> filterPoorlyModeledEvidence
         on the device.  Returns a dict: lk (flat, per unit allele-major [h*nReads + r]), keep (per read),
-        base_q / ins_q / del_q (the qualities the kernel used, when want_quals).  params: see _region_steps."""
+        base_q / ins_q / del_q (the qualities the kernel used, when want_quals), raw (un-normalised read-major
+        likelihoods, when want_raw).  params: see _region_steps."""
         rs, res, _alive = self._region_steps(batch, mapq, ref_hap, **params)
         b = batch.c_struct()
         self._check(self._L.gphmm_compute_regions(self._h, ctypes.byref(b), ctypes.byref(rs), res["lk"].ctypes.data))

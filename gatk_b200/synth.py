@@ -23,7 +23,8 @@ def _mutate_hap(rng, hap, n_events):
     """1..n SNPs / short indels applied to a haplotype (uint8 codes 0..3)."""
     h = hap
     for _ in range(n_events):
-        pos = int(rng.integers(5, len(h) - 5))
+        # (short haplotypes only occur in the ragged test batches; longer ones keep their historical random stream)
+        pos = int(rng.integers(5, len(h) - 5)) if len(h) > 10 else int(rng.integers(0, max(1, len(h) - 1)))
         kind = int(rng.integers(0, 3))
         if kind == 0:
             h = h.copy()
@@ -32,6 +33,8 @@ def _mutate_hap(rng, hap, n_events):
             h = np.concatenate([h[:pos], rng.integers(0, 4, int(rng.integers(1, 6)), dtype=np.uint8), h[pos:]])
         else:
             h = np.concatenate([h[:pos], h[pos + int(rng.integers(1, 6)):]])
+            if len(h) == 0:
+                h = hap[:1].copy()
     return h
 
 

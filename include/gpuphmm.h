@@ -153,6 +153,8 @@ typedef struct gphmm_region_steps {
     uint8_t *keep;                            /* out, n_reads: 1 kept, 0 removed as poorly modeled (units must not share reads) */
     uint8_t *hmm_base_q;                      /* out, optional: modified base qualities (HMM_BASE_QUALITIES_TAG), layout of base_q */
     uint8_t *hmm_ins_q, *hmm_del_q;           /* out, optional: the insertion / deletion qualities the kernel used */
+    double *raw_lk;                           /* out, optional: the un-normalised likelihoods, layout of gphmm_compute's out
+                                                 (PairHMM.getLogLikelihoodArray / --pair-hmm-results-file) */
 } gphmm_region_steps;
 
 /* Like gphmm_compute with the steps above fused in.  out[u.out_off + h*nReads + r] is the NORMALISED log10 likelihood,

@@ -488,6 +488,30 @@ def test_symmetric_quality_reads(hmm):
     assert np.abs(got.reshape(200, n) - got[:n]).max() < 1e-5   # copies in differently sized chunks: float noise only
 
 
+def test_likelihoods_near_the_double_underflow_limit(hmm, hmm64):
+    # LoglessPairHMM starts from 2^1020/H and still returns finite values down to ~1e-631; the scaled fp64 kernels
+    # start 2^60 lower, so pairs below ~1e-550 take the last tier (phmm_exact_f64_kernel: Java's own arithmetic) and
+    # must agree with the double-precision oracle far beyond the 1e-4 bar, -inf included
+    A, C = ord("A"), ord("C")
+    hap = np.full(200, A, np.uint8)
+    reads = []
+    for n_mis in (100, 120, 128, 132, 136, 139, 141, 150, 153, 155, 156, 157, 158, 200):   # ~ -4 per base: -400 ... -inf
+        R = n_mis
+        reads.append((np.full(R, C, np.uint8), const_quals(R, 40), const_quals(R, 60), const_quals(R, 60), const_quals(R, 40)))
+        wild = np.random.default_rng(R)
+        reads.append((np.full(R, C, np.uint8), const_quals(R, 40), wild.integers(50, 70, R).astype(np.uint8),
+                      wild.integers(50, 70, R).astype(np.uint8), wild.integers(35, 45, R).astype(np.uint8)))
+    b = Batch.single_unit(reads, [hap.tobytes(), hap[:150].tobytes()])
+    want = oracle_batch(b)
+    assert np.isneginf(want).any() and (want[np.isfinite(want)] < -560).any() and (want > -500).any()
+    for h in (hmm, hmm64):
+        got = h.compute(b)
+        assert np.array_equal(np.isfinite(got), np.isfinite(want))
+        deep = np.isfinite(want) & (want < -560)
+        assert np.abs(got[deep] - want[deep]).max() < 1e-9
+        _check(got, want, TOL)
+
+
 def test_full_size_config2_sample_against_oracle(hmm):
     # BASELINE.json configs[1] at full size (10 000 regions, ~6 M pairs, 5.8e11 cells): every output is a valid
     # log10 probability, the staged and the device-resident paths agree bit for bit, and a random sample of whole

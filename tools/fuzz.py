@@ -1,0 +1,111 @@
+"""Differential fuzzing of the CUDA path against the double-precision oracle: random ragged batches with every
+quality regime (flat, symmetric, per-base wild), N / exotic bytes, tiny and long reads, forced small chunks, prefix
+sharing on/off, forced fp64, and the fused region steps.  Run on a GPU box: python tools/fuzz.py [seconds] [seed0]"""
+import sys
+import time
+
+sys.path.insert(0, ".")
+sys.path.insert(0, "tests")
+import numpy as np
+
+from gatk_b200 import synth
+from gatk_b200.native import Batch, GpuPhmm
+from oracle import oracle
+from phmm_testutil import oracle_batch
+
+budget = float(sys.argv[1]) if len(sys.argv) > 1 else 120.0
+seed0 = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+TOL = 1e-4
+
+
+def requalify(b, rng, mode):
+    n = len(b.read_bases)
+    ins, dele, gcp = b.ins_q.copy(), b.del_q.copy(), b.gcp.copy()
+    if mode == "sym":          # ins == del per base, flat gcp per read
+        ins = np.where(rng.random(n) < 0.3, rng.integers(1, 71, n), 40).astype(np.uint8)
+        dele = ins.copy()
+        for r in range(len(b.read_off) - 1):
+            gcp[b.read_off[r]:b.read_off[r + 1]] = int(rng.choice([10, 10, 12, 3, 30]))
+    elif mode == "flatmix":    # several flat triples
+        for r in range(len(b.read_off) - 1):
+            t = [(45, 45, 10), (40, 42, 10), (30, 30, 8), (45, 40, 20), (35, 45, 12), (20, 25, 6)][int(rng.integers(0, 6))]
+            s = slice(b.read_off[r], b.read_off[r + 1])
+            ins[s], dele[s], gcp[s] = t
+    elif mode == "extreme":    # the whole legal range
+        ins = rng.integers(0, 128, n).astype(np.uint8)
+        dele = rng.integers(0, 128, n).astype(np.uint8)
+        gcp = rng.integers(0, 128, n).astype(np.uint8)
+    return Batch(b.read_bases, b.base_q, ins, dele, gcp, b.read_off, b.hap_bases, b.hap_off, b.units)
+
+
+def check(got, want, what):
+    fin = np.isfinite(want)
+    assert np.array_equal(np.isfinite(got), fin), what
+    if fin.any():
+        err = np.abs(got[fin] - want[fin]).max()
+        assert err <= TOL, "%s: max err %.3g" % (what, err)
+        return err
+    return 0.0
+
+
+t_end = time.time() + budget
+n_batches = n_pairs = 0
+worst = 0.0
+handles = {
+    "default": GpuPhmm(),
+    "small-chunks": GpuPhmm(chunk_cells=3_000_000, host_threads=3),
+    "no-sharing": GpuPhmm(no_prefix_sharing=True),
+    "fp64": GpuPhmm(force_fp64=True),
+}
+seed = seed0
+try:
+    while time.time() < t_end:
+        rng = np.random.default_rng(seed)
+        shape = int(rng.integers(0, 4))
+        if shape == 0:
+            b = synth.random_batch(seed, n_units=int(rng.integers(1, 8)), max_reads=20, max_haps=9, wild_quals=bool(rng.integers(0, 2)))
+        elif shape == 1:
+            b = synth.random_batch(seed, n_units=2, max_reads=6, max_haps=4, read_len=(200, 700), hap_len=(300, 900))
+        elif shape == 2:
+            b = synth.random_batch(seed, n_units=int(rng.integers(1, 30)), max_reads=4, max_haps=3, read_len=(1, 40), hap_len=(1, 60))
+        else:
+            b = synth.random_batch(seed, n_units=3, max_reads=40, max_haps=16, read_len=(100, 254), hap_len=(250, 500))
+        mode = ["keep", "sym", "flatmix", "extreme"][int(rng.integers(0, 4))]
+        b = requalify(b, rng, mode)
+        if rng.random() < 0.2:   # exotic haplotype bytes
+            hb = b.hap_bases.copy()
+            hb[rng.random(len(hb)) < 0.01] = int(rng.choice([ord("R"), ord("n"), ord("a"), ord("*")]))
+            b = Batch(b.read_bases, b.base_q, b.ins_q, b.del_q, b.gcp, b.read_off, hb, b.hap_off, b.units)
+        want = oracle_batch(b)
+        for name, h in handles.items():
+            worst = max(worst, check(h.compute(b), want, "seed %d %s %s" % (seed, mode, name)))
+        if mode != "extreme":
+            # region steps: integer parts bit-exact, matrix/flags bit-exact given the device likelihoods
+            n_reads = len(b.read_off) - 1
+            mapq = rng.choice([0, 10, 25, 60, 255], n_reads).astype(np.uint8)
+            ref = rng.integers(-1, 1, len(b.units)).astype(np.int32)
+            kw = dict(pcr_rate_factor=float(rng.choice([0.0, 1.0, 2.0, 3.0])), symmetric=bool(rng.integers(0, 2)),
+                      dynamic_disqualification=bool(rng.integers(0, 2)))
+            got = handles["default"].compute_regions(b, mapq, ref, **kw)
+            q, i, d = oracle.modify_reads(b.read_bases, b.base_q, b.ins_q, b.del_q, b.read_off, mapq, kw["pcr_rate_factor"])
+            assert np.array_equal(got["base_q"], q) and np.array_equal(got["ins_q"], i) and np.array_equal(got["del_q"], d), "seed %d modify" % seed
+            mod = Batch(b.read_bases, q, i, d, b.gcp, b.read_off, b.hap_bases, b.hap_off, b.units)
+            raw = got["raw"]    # the un-normalised likelihoods of the same call
+            worst = max(worst, check(raw, oracle_batch(mod), "seed %d regions raw" % seed))
+            for k, u in enumerate(b.units):
+                r0, r1, h0, h1, o = (int(u[x]) for x in ("read_begin", "read_end", "hap_begin", "hap_end", "out_off"))
+                nr, nh = r1 - r0, h1 - h0
+                if nr == 0 or nh == 0:
+                    continue
+                norm = oracle.normalize(raw[o:o + nr * nh], nr, nh, int(ref[k]), -4.5, kw["symmetric"])
+                keep = oracle.filter_poorly_modeled(norm, nr, nh, q, b.read_off[r0:r1 + 1], 0.02, kw["dynamic_disqualification"], 1.0)
+                assert np.array_equal(norm, got["lk"][o:o + nr * nh]), "seed %d normalize unit %d" % (seed, k)
+                assert np.array_equal(keep, got["keep"][r0:r1]), "seed %d keep unit %d" % (seed, k)
+        n_batches += 1
+        n_pairs += b.n_out
+        seed += 1
+finally:
+    for h in handles.values():
+        h.close()
+print("fuzz: %d batches (seeds %d..%d), %d pairs x 4 configurations + region steps, worst |err| %.3g (bar %g): OK" % (
+    n_batches, seed0, seed - 1, n_pairs, worst, TOL))
