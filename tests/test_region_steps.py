@@ -324,3 +324,18 @@ def test_region_steps_async_queue_merges_equal_requests():
             assert np.abs(got["raw"] - want["raw"]).max() < 1e-5
             # merged batches may split haplotype groups differently (bigger chunk): same numbers to float rounding
             assert np.abs(got["lk"] - want["lk"]).max() < 1e-5
+
+
+@pytest.mark.gpu
+def test_region_steps_with_forced_double_precision():
+    # --native-pair-hmm-use-double-precision: same steps around the fp64 kernels
+    b, mapq = _raw_batch(21, n_units=4)
+    ref = np.zeros(len(b.units), np.int32)
+    with GpuPhmm() as f32, GpuPhmm(force_fp64=True) as f64:
+        a, c = f32.compute_regions(b, mapq, ref), f64.compute_regions(b, mapq, ref)
+        assert f64.stats()["rescued_pairs"] == f64.stats()["pairs"] > 0
+    for name in ("base_q", "ins_q", "del_q"):
+        assert np.array_equal(a[name], c[name])
+    want = _oracle_regions(b, mapq, ref)
+    assert np.abs(c["lk"] - want["lk"]).max() < 1e-9 and np.array_equal(c["keep"], want["keep"])
+    assert np.abs(a["lk"] - c["lk"]).max() < 1e-4
