@@ -45,6 +45,8 @@ def lib():
         L.phmm_oracle_logless.argtypes = pair_args + [ctypes.c_int, _f64p]
         L.phmm_oracle_log10.restype = ctypes.c_int
         L.phmm_oracle_log10.argtypes = pair_args + [ctypes.c_int, ctypes.c_int, _f64p]
+        L.phmm_oracle_pd_logless.restype = ctypes.c_int
+        L.phmm_oracle_pd_logless.argtypes = [_u8p, _u8p, ctypes.c_int, _u8p, _u8p, _u8p, _u8p, _u8p, ctypes.c_int, ctypes.c_int, _f64p]
         L.phmm_oracle_unit.restype = ctypes.c_int
         L.phmm_oracle_unit.argtypes = [_u8p, _u8p, _u8p, _u8p, _u8p, _i32p, ctypes.c_int,
                                        _u8p, _i32p, ctypes.c_int, ctypes.c_int, ctypes.c_int, _f64p]
@@ -101,6 +103,17 @@ def logless(hap, read, base_q, ins_q, del_q, gcp, tristate_off=False):
 def log10hmm(hap, read, base_q, ins_q, del_q, gcp, exact=True, tristate_off=False):
     """Log10PairHMM: EXACT (exact=True) or ORIGINAL (exact=False)."""
     return _pair(lib().phmm_oracle_log10, hap, read, base_q, ins_q, del_q, gcp, int(exact), int(tristate_off))
+
+
+def pd_logless(hap, pd, read, base_q, ins_q, del_q, gcp, tristate_off=False):
+    """LoglessPDPairHMM for one (read, partially determined haplotype) pair; pd = PartiallyDeterminedHaplotype.getAlternateBases()"""
+    (h, hp), (f, fp), (r, rp), (q, qp), (i, ip), (d, dp), (g, gp) = (_u8(x) for x in (hap, pd, read, base_q, ins_q, del_q, gcp))
+    assert len(f) == len(h) and len(q) == len(i) == len(d) == len(g) == len(r)
+    out = ctypes.c_double(0.0)
+    rc = lib().phmm_oracle_pd_logless(hp, fp, len(h), rp, qp, ip, dp, gp, len(r), 1 if tristate_off else 0, ctypes.byref(out))
+    if rc != 0:
+        raise ValueError("oracle error %d" % rc)
+    return out.value
 
 
 def qual_to_error_prob(q):

@@ -222,6 +222,98 @@ int phmm_oracle_logless(const uint8_t *hap, int H, const uint8_t *read, const ui
 }
 
 /*
+ * LoglessPDPairHMM.subComputeReadLikelihoodGivenHaplotypeLog10 (PH/LoglessPDPairHMM.java:34-153), the
+ * "partially determined" PairHMM of DRAGEN-GATK mode, with hapStartIndex = 0 (PH/PDPairHMM.java:176,241).
+ * Parity status of THIS function: UNPINNED -- the reference's only fixture for it,
+ * src/test/resources/large/expected.PDHMM.hmmresults.txt (PDPairHMMLikelihoodCalculationEngineUnitTest.java:22),
+ * is a git-lfs stub in /root/reference.  It is anchored instead by (i) pd bases all 0 == phmm_oracle_logless
+ * exactly, (ii) an independent pure-Python restatement (oracle/pyoracle.py), (iii) hand-checked tiny cases.
+ *
+ *   :44-50   D[0][j] = 2^1020 / hapLen;  branch matrices row 0 / column 0 stay Java's 0.0
+ *   :60-147  per cell, by state: NORMAL / INSIDE_DEL copy or hold the branch values, AFTER_DEL merges them with
+ *            max(); the state advances along j from the PD flags DEL_START / DEL_END of column j and -- as written --
+ *            is NOT reset at the start of a row (it is declared outside the row loop, :59)
+ *   :170-181 priors: a SNP-flagged column also matches the alternative bases of its mask (:184-204)
+ * pd: one byte per haplotype base, utils/haplotype/PartiallyDeterminedHaplotype.java:59-65
+ *     SNP=1 DEL_START=2 DEL_END=4 A=8 C=16 G=32 T=64.
+ * Returns ORACLE_ERR_BAD_QUAL - 10 when a read base other than ACGTacgt meets a SNP column (Java throws, :202).
+ */
+int phmm_oracle_pd_logless(const uint8_t *hap, const uint8_t *pd, int H, const uint8_t *read, const uint8_t *baseQ,
+                           const uint8_t *insQ, const uint8_t *delQ, const uint8_t *gcp, int R,
+                           int tristate_off, double *out) {
+    phmm_oracle_init();
+    if (H <= 0) return ORACLE_ERR_BAD_LENGTH;
+    enum { PD_SNP = 1, PD_DEL_START = 2, PD_DEL_END = 4, PD_A = 8, PD_C = 16, PD_G = 32, PD_T = 64 };
+    enum { NORMAL, INSIDE_DEL, AFTER_DEL };
+    const double INITIAL_CONDITION = pow(2.0, 1020.0);
+    const double INITIAL_CONDITION_LOG10 = log10(INITIAL_CONDITION);
+    const int W = H + 1;
+    /* 6 matrices x 2 rolling rows */
+    double *buf = (double *)calloc((size_t)12 * W, sizeof(double));
+    double *Mp = buf, *Ip = Mp + W, *Dp = Ip + W, *bMp = Dp + W, *bIp = bMp + W, *bDp = bIp + W;
+    double *Mc = bDp + W, *Ic = Mc + W, *Dc = Ic + W, *bMc = Dc + W, *bIc = bMc + W, *bDc = bIc + W;
+    const double initialValue = INITIAL_CONDITION / H;
+    for (int j = 0; j < W; j++) Dp[j] = initialValue;
+    int rc = ORACLE_OK;
+    int state = NORMAL;
+    for (int i = 1; i <= R && rc == ORACLE_OK; i++) {
+        double t[TRANS_PROB_ARRAY_LENGTH];
+        rc = phmm_oracle_qual_to_trans_probs(t, insQ[i - 1], delQ[i - 1], gcp[i - 1]);
+        if (rc != ORACLE_OK) break;
+        if (baseQ[i - 1] > MAX_QUAL) { rc = ORACLE_ERR_BAD_QUAL; break; }
+        const uint8_t x = read[i - 1];
+        const double pMatch = qualToProb(baseQ[i - 1]);
+        const double pMis = qualToErrorProbCache[baseQ[i - 1]] / (tristate_off ? 1.0 : 3.0);
+        Mc[0] = Ic[0] = Dc[0] = bMc[0] = bIc[0] = bDc[0] = 0.0;
+        for (int j = 1; j < W; j++) {
+            const uint8_t y = hap[j - 1], f = pd[j - 1];
+            int match = x == y || x == (uint8_t)'N' || y == (uint8_t)'N';
+            if (!match && (f & PD_SNP)) {
+                switch (x) {
+                    case 'A': case 'a': match = (f & PD_A) != 0; break;
+                    case 'C': case 'c': match = (f & PD_C) != 0; break;
+                    case 'T': case 't': match = (f & PD_T) != 0; break;
+                    case 'G': case 'g': match = (f & PD_G) != 0; break;
+                    default: rc = ORACLE_ERR_BAD_QUAL - 10; break;
+                }
+            }
+            const double prior = match ? pMatch : pMis;
+            const int del_end = (f & PD_DEL_END) == PD_DEL_END;
+            double dm = Mp[j - 1], di = Ip[j - 1], dd = Dp[j - 1]; /* diagonal operands */
+            double lm = Mc[j - 1], ld = Dc[j - 1];                  /* left operands of D */
+            if (state == NORMAL) {
+                bMc[j] = Mc[j - 1]; bDc[j] = Dc[j - 1]; bIc[j] = Ic[j - 1];
+            } else if (state == INSIDE_DEL) {
+                bMc[j] = bMc[j - 1]; bDc[j] = bDc[j - 1]; bIc[j] = bIc[j - 1];
+            } else {
+                bMc[j] = fmax(bMc[j - 1], Mc[j - 1]); bDc[j] = fmax(bDc[j - 1], Dc[j - 1]); bIc[j] = fmax(bIc[j - 1], Ic[j - 1]);
+                dm = fmax(bMp[j - 1], Mp[j - 1]); di = fmax(bIp[j - 1], Ip[j - 1]); dd = fmax(bDp[j - 1], Dp[j - 1]);
+                lm = fmax(bMc[j - 1], Mc[j - 1]); ld = fmax(bDc[j - 1], Dc[j - 1]);
+            }
+            Mc[j] = prior * (dm * t[matchToMatch] + di * t[indelToMatch] + dd * t[indelToMatch]);
+            Dc[j] = lm * t[matchToDeletion] + ld * t[deletionToDeletion];
+            if (del_end)
+                Ic[j] = fmax(bMp[j], Mp[j]) * t[matchToInsertion] + fmax(bIp[j], Ip[j]) * t[insertionToInsertion];
+            else
+                Ic[j] = Mp[j] * t[matchToInsertion] + Ip[j] * t[insertionToInsertion];
+            if (state == AFTER_DEL) state = NORMAL;
+            if ((f & PD_DEL_START) == PD_DEL_START) state = INSIDE_DEL;
+            if (del_end) state = AFTER_DEL;
+        }
+        double *s;
+        s = Mp; Mp = Mc; Mc = s;    s = Ip; Ip = Ic; Ic = s;    s = Dp; Dp = Dc; Dc = s;
+        s = bMp; bMp = bMc; bMc = s; s = bIp; bIp = bIc; bIc = s; s = bDp; bDp = bDc; bDc = s;
+    }
+    if (rc == ORACLE_OK) {
+        double finalSumProbabilities = 0.0;
+        for (int j = 1; j < W; j++) finalSumProbabilities += Mp[j] + Ip[j];
+        *out = log10(finalSumProbabilities) - INITIAL_CONDITION_LOG10;
+    }
+    free(buf);
+    return rc;
+}
+
+/*
  * Log10PairHMM (EXACT when exact != 0, ORIGINAL otherwise).
  *   PH/Log10PairHMM.java:33-41   matrices start at -inf
  *   PH/Log10PairHMM.java:58-89   driver
