@@ -1,0 +1,229 @@
+// pdhmm_kernels.cuh -- the "partially determined" PairHMM of DRAGEN-GATK mode on the device.
+//
+// Reference: utils/pairhmm/LoglessPDPairHMM.java:34-153 (recurrence and state machine), :170-204 (priors with the
+// SNP mask of a column), utils/haplotype/PartiallyDeterminedHaplotype.java:59-65 (flag bits); native counterpart of
+// the reference: VectorLoglessPairPDHMM.java:71-147 (GKL PDHMM binding).
+//
+// Same wavefront as phmm_forward_kernel (one warp per (read, haplotype) pair, lane l owns K consecutive read rows,
+// lane l works on column step-l, last row handed down by shuffles, longer reads in strips through a boundary buffer),
+// but with the reference's UNSCALED M/I/D plus the three "branch" values per row, so that the max() merges of the
+// AFTER_DEL state act on exactly the quantities the Java code compares.  max(a x, a y) = a max(x, y) for a > 0, so the
+// result is still homogeneous in the initial value and the fp32 pass may start from 2^(125 - ceil log2 H);
+// pairs whose fp32 sum falls below 1e-28 are redone by the same kernel in double from Java's own 2^1020 / H.
+#pragma once
+#include <stdint.h>
+#include "phmm_kernels.cuh"
+
+namespace phmm_dev {
+
+// per haplotype column: bits 0-3 = alternative bases allowed by a SNP flag (A, C, G, T), bit 4 = DEL_END on this
+// column, bits 5-6 = state in which row 1 processes the column (0 NORMAL, 1 INSIDE_DEL, 2 AFTER_DEL), bit 7 = SNP flag
+constexpr uint32_t PD_MASK_BITS = 0x0f, PD_DEL_END_BIT = 0x10, PD_TYPE_SHIFT = 5, PD_TYPE_BITS = 3, PD_SNP_BIT = 0x80;
+constexpr uint32_t PD_NORMAL = 0, PD_INSIDE_DEL = 1, PD_AFTER_DEL = 2;
+
+struct PdTask {
+    uint32_t read;         // chunk-local read
+    uint32_t hap_off, H;   // chunk-local haplotype columns
+    uint32_t out_slot;     // chunk-local output slot
+    // LoglessPDPairHMM keeps its state variable across rows (:59): rows >= 2 start in the state the previous row ended
+    // in (`carry`) and keep it up to and including the first flagged column (`first_event`, H + 1 if none)
+    uint32_t first_event, carry;
+    int32_t c0_exp;        // fp32 pass: exponent of the initial value
+    uint32_t pad;
+};
+
+struct PdArgs {
+    const uint8_t *rd_bases, *rd_q, *rd_i, *rd_d, *rd_c;
+    const uint32_t *read_off;
+    const uint8_t *hap_bases, *hap_flags;
+    const PdTask *tasks;
+    const uint32_t *task_index;   // fp64 redo: indices into tasks (nullptr: tasks [first, first + n) directly)
+    const uint32_t *n_tasks_ptr;  // device-side count (redo list) or nullptr
+    uint32_t first, n_tasks;
+    uint32_t *counter;
+    void *sums;                   // float (per task) or double (per redo slot)
+    void *bnd;
+    uint32_t bnd_stride;
+    const double *m2m;
+    int *err;                     // 1: quality out of range, 2: read base other than ACGT on a SNP column (:202)
+    int32_t tristate_off;
+};
+
+template <typename T> struct __align__(16) BndPD { T m, i, d, bm, bi, bd, pad0, pad1; };
+
+template <typename T> __device__ __forceinline__ T pd_max(T a, T b) { return a > b ? a : b; }
+
+template <typename T, int K>
+__global__ void __launch_bounds__(32) phmm_pd_kernel(const PdArgs g)
+{
+    constexpr unsigned FULL = 0xffffffffu;
+    constexpr int ROWS = 32 * K;
+    const int lane = threadIdx.x;
+    T *const sums = reinterpret_cast<T *>(g.sums);
+    BndPD<T> *const bnd = reinterpret_cast<BndPD<T> *>(g.bnd) + (size_t)blockIdx.x * g.bnd_stride;
+    const uint32_t n_tasks = g.n_tasks_ptr ? *g.n_tasks_ptr : g.n_tasks;
+
+    for (;;) {
+        uint32_t ti = 0;
+        if (lane == 0) ti = atomicAdd(g.counter, 1u);
+        ti = __shfl_sync(FULL, ti, 0);
+        if (ti >= n_tasks) break;
+        const PdTask t = g.tasks[g.task_index ? g.task_index[ti] : g.first + ti];
+        const uint32_t ro = g.read_off[t.read];
+        const int R = (int)(g.read_off[t.read + 1] - ro), H = (int)t.H;
+        const uint8_t *__restrict__ hap = g.hap_bases + t.hap_off;
+        const uint8_t *__restrict__ flg = g.hap_flags + t.hap_off;
+        // fp64: the reference's own initial value 2^1020 / H (LoglessPDPairHMM.java:11,45); fp32: a power of two
+        const T c0 = sizeof(T) == 8 ? (T)(0x1p1020 / (double)H) : (T)scalbn(1.0, t.c0_exp);
+        const int n_strips = (R + ROWS - 1) / ROWS;
+        const int row_lane = R > 0 ? ((R - 1) % ROWS) / K : -1, row_k = R > 0 ? (R - 1) % K : -1;  // where row R lives in the last strip
+        T sum = (T)0;
+
+        for (int strip = 0; strip < n_strips; ++strip) {
+            const bool first_strip = strip == 0, last_strip = strip == n_strips - 1;
+            // ---- per-row constants (PairHMMModel.java:107-117, LoglessPDPairHMM.java:170-181) ----
+            T tMM[K], tIM[K], tMI[K], tII[K], tMD[K], pm[K], px[K];
+            uint32_t xb[K], abit[K];
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                const int i = strip * ROWS + lane * K + k + 1;
+                tMM[k] = tIM[k] = tMI[k] = tII[k] = tMD[k] = pm[k] = px[k] = (T)0;
+                xb[k] = 0x100u; abit[k] = 0;  // 0x100 never equals a haplotype byte
+                if (i <= R) {
+                    uint32_t q = g.rd_q[ro + i - 1], qi = g.rd_i[ro + i - 1], qd = g.rd_d[ro + i - 1], qc = g.rd_c[ro + i - 1];
+                    if (q > (uint32_t)MAX_QUAL || qi > 127u || qd > 127u || qc > 127u) {
+                        atomicExch(g.err, 1);
+                        q = min(q, (uint32_t)MAX_QUAL); qi = min(qi, 127u); qd = min(qd, 127u); qc = min(qc, 127u);
+                    }
+                    const uint32_t mn = min(qi, qd), mx = max(qi, qd);
+                    const double ec = c_eps[qc], e = c_eps[q];
+                    tMM[k] = (T)__ldg(g.m2m + ((mx * (mx + 1)) >> 1) + mn);
+                    tIM[k] = (T)(1.0 - ec); tMI[k] = (T)c_eps[qi]; tII[k] = (T)ec; tMD[k] = (T)c_eps[qd];
+                    pm[k] = (T)(1.0 - e); px[k] = (T)(g.tristate_off ? e : e / 3.0);
+                    const uint32_t x = g.rd_bases[ro + i - 1];
+                    xb[k] = x;
+                    switch (x) {  // LoglessPDPairHMM.isBasePDMatching :184-204
+                        case 'A': case 'a': abit[k] = 1; break;
+                        case 'C': case 'c': abit[k] = 2; break;
+                        case 'G': case 'g': abit[k] = 4; break;
+                        case 'T': case 't': abit[k] = 8; break;
+                        case 'N': abit[k] = 0; break;   // matches before the mask is looked at
+                        default: abit[k] = 0x80000000u; // the reference throws when such a base meets a SNP column
+                    }
+                }
+            }
+            T M[K], I[K], D[K], bM[K], bI[K], bD[K];
+#pragma unroll
+            for (int k = 0; k < K; ++k) M[k] = I[k] = D[k] = bM[k] = bI[k] = bD[k] = (T)0;
+            // row above at the previous column; D[0][0] is the initial value, branch row 0 is Java's 0.0
+            T dgm = (T)0, dgi = (T)0, dgd = (first_strip && lane == 0) ? c0 : (T)0, dgbm = (T)0, dgbi = (T)0, dgbd = (T)0;
+            int p = 1 - lane;  // 1-based column of this lane in the current step
+            const int n_steps = H + 31;
+            for (int s = 1; s <= n_steps; ++s, ++p) {
+                const bool valid = p >= 1 && p <= H;
+                uint32_t hb = 0x200u, fl = 0;
+                if (valid) { hb = hap[p - 1]; fl = flg[p - 1]; }
+                // row above at this column: last row of the lane above (its state before this step), strip boundary, or row 0
+                T mu = __shfl_up_sync(FULL, M[K - 1], 1), iu = __shfl_up_sync(FULL, I[K - 1], 1), du = __shfl_up_sync(FULL, D[K - 1], 1);
+                T bmu = __shfl_up_sync(FULL, bM[K - 1], 1), biu = __shfl_up_sync(FULL, bI[K - 1], 1), bdu = __shfl_up_sync(FULL, bD[K - 1], 1);
+                if (lane == 0) {
+                    mu = iu = bmu = biu = bdu = (T)0;
+                    du = first_strip ? c0 : (T)0;
+                    if (!first_strip && valid) {
+                        const BndPD<T> b = bnd[p];
+                        mu = b.m; iu = b.i; du = b.d; bmu = b.bm; biu = b.bi; bdu = b.bd;
+                    }
+                }
+                const uint32_t mask = fl & PD_MASK_BITS;
+                const bool del_end = (fl & PD_DEL_END_BIT) != 0;
+                const uint32_t t_row1 = (fl >> PD_TYPE_SHIFT) & PD_TYPE_BITS;
+                uint32_t t_rest = t_row1;
+                if (valid && (uint32_t)p <= t.first_event)
+                    t_rest = t.carry == PD_INSIDE_DEL ? PD_INSIDE_DEL : (t.carry == PD_AFTER_DEL && p == 1 ? PD_AFTER_DEL : PD_NORMAL);
+
+                T Mn[K], Dn[K], In[K], nbM[K], nbI[K], nbD[K];
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    const uint32_t ty = (first_strip && lane == 0 && k == 0) ? t_row1 : t_rest;
+                    // row above, previous column
+                    T am = k ? M[k - 1] : dgm, ai = k ? I[k - 1] : dgi, ad = k ? D[k - 1] : dgd;
+                    const T abm = k ? bM[k - 1] : dgbm, abi = k ? bI[k - 1] : dgbi, abd = k ? bD[k - 1] : dgbd;
+                    T lm = M[k], ld = D[k];  // this row, previous column
+                    if (ty == PD_NORMAL) {
+                        nbM[k] = M[k]; nbI[k] = I[k]; nbD[k] = D[k];
+                    } else if (ty == PD_INSIDE_DEL) {
+                        nbM[k] = bM[k]; nbI[k] = bI[k]; nbD[k] = bD[k];
+                    } else {
+                        nbM[k] = pd_max(bM[k], M[k]); nbI[k] = pd_max(bI[k], I[k]); nbD[k] = pd_max(bD[k], D[k]);
+                        am = pd_max(abm, am); ai = pd_max(abi, ai); ad = pd_max(abd, ad);
+                        lm = nbM[k]; ld = nbD[k];
+                    }
+                    bool match = xb[k] == hb || xb[k] == (uint32_t)'N' || hb == (uint32_t)'N';
+                    if (!match && (fl & PD_SNP_BIT)) {
+                        if (abit[k] & 0x80000000u) atomicExch(g.err, 2);
+                        match = (mask & abit[k]) != 0;
+                    }
+                    const T prior = valid ? (match ? pm[k] : px[k]) : (T)0;
+                    Mn[k] = prior * (am * tMM[k] + ai * tIM[k] + ad * tIM[k]);
+                    Dn[k] = lm * tMD[k] + ld * tII[k];  // deletionToDeletion = insertionToInsertion = eps(gcp)
+                }
+                // insertion: row above at THIS column -- chain down the lane's rows
+                {
+                    T um = mu, ui = iu, ubm = bmu, ubi = biu;
+#pragma unroll
+                    for (int k = 0; k < K; ++k) {
+                        const T xm = del_end ? pd_max(ubm, um) : um, xi = del_end ? pd_max(ubi, ui) : ui;
+                        In[k] = xm * tMI[k] + xi * tII[k];
+                        um = Mn[k]; ui = In[k]; ubm = nbM[k]; ubi = nbI[k];
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < K; ++k) { M[k] = Mn[k]; I[k] = In[k]; D[k] = Dn[k]; bM[k] = nbM[k]; bI[k] = nbI[k]; bD[k] = nbD[k]; }
+                dgm = mu; dgi = iu; dgd = du; dgbm = bmu; dgbi = biu; dgbd = bdu;
+                if (last_strip && lane == row_lane && valid) {
+#pragma unroll
+                    for (int k = 0; k < K; ++k)
+                        if (k == row_k) sum += M[k] + I[k];  // LoglessPDPairHMM.java:149-152
+                }
+                if (!last_strip && lane == 31 && valid) {
+                    BndPD<T> o;
+                    o.m = M[K - 1]; o.i = I[K - 1]; o.d = D[K - 1]; o.bm = bM[K - 1]; o.bi = bI[K - 1]; o.bd = bD[K - 1];
+                    o.pad0 = o.pad1 = (T)0;
+                    bnd[p] = o;
+                }
+            }
+        }
+        sum = __shfl_sync(FULL, sum, row_lane < 0 ? 0 : row_lane);
+        if (lane == 0) sums[ti] = sum;
+    }
+}
+
+constexpr float PD_RESCUE_THRESHOLD_F32 = 1e-28f;
+
+// fp32 sums -> log10 likelihoods, or onto the redo list
+__global__ void __launch_bounds__(128) phmm_pd_epilogue_f32(const PdTask *tasks, uint32_t n, const float *sums, double *out,
+                                                            uint32_t *redo, uint32_t *n_redo)
+{
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        const PdTask t = tasks[k];
+        const float s = sums[k];
+        if (!(s >= PD_RESCUE_THRESHOLD_F32) || s > 3.0e38f) {
+            redo[atomicAdd(n_redo, 1u)] = k;
+            continue;
+        }
+        out[t.out_slot] = log10((double)s) - log10_c0H(t.c0_exp, t.H);
+    }
+}
+
+__global__ void __launch_bounds__(128) phmm_pd_epilogue_f64(const PdTask *tasks, const uint32_t *redo, const uint32_t *n_redo,
+                                                            const double *sums, double *out)
+{
+    const uint32_t n = *n_redo;
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        const PdTask t = tasks[redo[k]];
+        out[t.out_slot] = log10(sums[k]) - 307.0505955772608;  // Math.log10(Math.pow(2, 1020)), LoglessPDPairHMM.java:12,153
+    }
+}
+
+}  // namespace phmm_dev

@@ -64,7 +64,7 @@ RS_DISABLE_CAP_TO_MAPQ, RS_SYMMETRIC_NORMALIZE, RS_FILTER_POORLY, RS_DYNAMIC_DIS
 UNIT_DTYPE = np.dtype([("read_begin", "<i8"), ("read_end", "<i8"), ("hap_begin", "<i8"), ("hap_end", "<i8"), ("out_off", "<i8")])
 
 EXPORTS = ["gphmm_abi_version", "gphmm_device_count", "gphmm_strerror", "gphmm_create", "gphmm_destroy",
-           "gphmm_last_error", "gphmm_compute", "gphmm_compute_regions", "gphmm_submit_regions", "gphmm_submit", "gphmm_wait", "gphmm_prepare", "gphmm_run_prepared",
+           "gphmm_last_error", "gphmm_compute", "gphmm_compute_regions", "gphmm_submit_regions", "gphmm_pd_compute", "gphmm_submit", "gphmm_wait", "gphmm_prepare", "gphmm_run_prepared",
            "gphmm_release_prepared", "gphmm_get_stats", "gphmm_reset_stats", "gphmm_plan_stats", "gphmm_host_alloc", "gphmm_host_free"]
 
 
@@ -100,6 +100,8 @@ def load_library():
     L.gphmm_compute.argtypes = [ctypes.c_void_p, ctypes.POINTER(_Batch), ctypes.c_void_p]
     L.gphmm_compute_regions.restype = ctypes.c_int
     L.gphmm_compute_regions.argtypes = [ctypes.c_void_p, ctypes.POINTER(_Batch), ctypes.POINTER(_RegionSteps), ctypes.c_void_p]
+    L.gphmm_pd_compute.restype = ctypes.c_int
+    L.gphmm_pd_compute.argtypes = [ctypes.c_void_p, ctypes.POINTER(_Batch), ctypes.c_void_p, ctypes.c_void_p]
     L.gphmm_submit_regions.restype = ctypes.c_int
     L.gphmm_submit_regions.argtypes = [ctypes.c_void_p, ctypes.POINTER(_Batch), ctypes.POINTER(_RegionSteps), ctypes.c_void_p,
                                        ctypes.POINTER(ctypes.c_uint64)]
@@ -368,6 +370,17 @@ class GpuPhmm:
         b = batch.c_struct()
         self._check(self._L.gphmm_compute_regions(self._h, ctypes.byref(b), ctypes.byref(rs), res["lk"].ctypes.data))
         return res
+
+    def pd_compute(self, batch, hap_pd_bases, out=None):
+        """gphmm_pd_compute: LoglessPDPairHMM; hap_pd_bases is parallel to batch.hap_bases"""
+        pd = np.ascontiguousarray(hap_pd_bases, dtype=np.uint8)
+        if len(pd) != len(batch.hap_bases):
+            raise ValueError("hap_pd_bases needs one byte per haplotype base")
+        if out is None:
+            out = np.full(batch.n_out, np.nan, dtype=np.float64)
+        b = batch.c_struct()
+        self._check(self._L.gphmm_pd_compute(self._h, ctypes.byref(b), pd.ctypes.data if len(pd) else None, out.ctypes.data))
+        return out
 
     def submit_regions(self, batch, mapq, ref_hap=None, **params):
         """gphmm_submit_regions; wait(ticket) returns the result dict of compute_regions"""

@@ -165,6 +165,14 @@ int gphmm_compute_regions(gphmm_t *h, const gphmm_batch *batch, const gphmm_regi
  * Queued requests with equal parameters are merged into one GPU batch. */
 int gphmm_submit_regions(gphmm_t *h, const gphmm_batch *batch, const gphmm_region_steps *steps, double *out, uint64_t *ticket);
 
+/* ---- PD-HMM: the "partially determined" PairHMM of DRAGEN-GATK mode ------------------------------
+ * Replaces PairPDHMMNativeBinding.computeLikelihoods(ReadDataHolder[], HaplotypeDataHolder[] with haplotypePDBases,
+ * double[]) as called at utils/pairhmm/VectorLoglessPairPDHMM.java:115; semantics of
+ * utils/pairhmm/LoglessPDPairHMM.java:34-153.  hap_pd_bases is parallel to batch->hap_bases (one flag byte per
+ * haplotype base, PartiallyDeterminedHaplotype.getAlternateBases(): SNP=1 DEL_START=2 DEL_END=4 A=8 C=16 G=32 T=64).
+ * Output layout as gphmm_compute.  The read-span filter of VectorLoglessPairPDHMM.java:129-137 stays with the caller. */
+int gphmm_pd_compute(gphmm_t *h, const gphmm_batch *batch, const uint8_t *hap_pd_bases, double *out);
+
 /* Statistics accumulate over calls until reset. */
 int gphmm_get_stats(const gphmm_t *h, gphmm_stats *out);
 void gphmm_reset_stats(gphmm_t *h);

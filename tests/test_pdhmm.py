@@ -87,3 +87,114 @@ def test_snp_and_deletion_semantics():
     pd[3] = SNP | A
     with pytest.raises(ValueError):
         oracle.pd_logless(hap, pd, np.frombuffer(b"ACGRACGT", dtype=np.uint8), q, i, i, g)
+
+
+# ---- device ---------------------------------------------------------------------------------------------------------
+def _pd_batch(seed, n_units, max_reads, max_haps, read_len, hap_len, modes=(0, 1, 2, 3)):
+    from gatk_b200.native import Batch
+    rng = np.random.default_rng(seed)
+    regions, pds = [], []
+    for _ in range(n_units):
+        H = int(rng.integers(hap_len[0], hap_len[1] + 1))
+        hap0 = L[rng.integers(0, 4, H)]
+        haps = []
+        for _ in range(int(rng.integers(1, max_haps + 1))):
+            h = hap0[: int(rng.integers(max(1, H - 30), H + 1))].copy()
+            haps.append(h)
+            pds.append(random_pd(rng, len(h), int(rng.choice(modes))))
+        reads = []
+        for _ in range(int(rng.integers(1, max_reads + 1))):
+            R = int(rng.integers(read_len[0], read_len[1] + 1))
+            rd = L[rng.integers(0, 4, R)]
+            if rng.random() < 0.8:
+                n = min(R, H)
+                off = int(rng.integers(0, H - n + 1))
+                rd[:n] = hap0[off:off + n]
+                err = rng.random(R) < 0.03
+                rd[err] = L[rng.integers(0, 4, int(err.sum()))]
+            if rng.random() < 0.1:
+                rd[int(rng.integers(0, R))] = ord("N")
+            reads.append((rd, rng.integers(6, 41, R).astype(np.uint8), rng.integers(10, 60, R).astype(np.uint8),
+                          rng.integers(10, 60, R).astype(np.uint8), rng.integers(5, 30, R).astype(np.uint8)))
+        regions.append((reads, [h.tobytes() for h in haps]))
+    return Batch.from_units(regions), np.concatenate(pds)
+
+
+def _pd_oracle(b, pd):
+    out = np.full(b.n_out, np.nan)
+    for u in b.units:
+        r0, r1, h0, h1, o = (int(u[x]) for x in ("read_begin", "read_end", "hap_begin", "hap_end", "out_off"))
+        for r in range(r0, r1):
+            s = slice(int(b.read_off[r]), int(b.read_off[r + 1]))
+            for k in range(h0, h1):
+                t = slice(int(b.hap_off[k]), int(b.hap_off[k + 1]))
+                out[o + (r - r0) * (h1 - h0) + (k - h0)] = oracle.pd_logless(b.hap_bases[t], pd[t], b.read_bases[s], b.base_q[s], b.ins_q[s],
+                                                                         b.del_q[s], b.gcp[s])
+    return out
+
+
+def _close(got, want, tol):
+    fin = np.isfinite(want)
+    assert np.array_equal(np.isfinite(got), fin)
+    assert np.array_equal(got[~fin], want[~fin])
+    assert np.abs(got[fin] - want[fin]).max() <= tol
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", [
+    dict(n_units=6, max_reads=12, max_haps=6, read_len=(1, 60), hap_len=(1, 80)),        # K = 2 rows per lane
+    dict(n_units=4, max_reads=10, max_haps=5, read_len=(64, 127), hap_len=(100, 200)),   # K = 4
+    dict(n_units=3, max_reads=8, max_haps=5, read_len=(128, 256), hap_len=(200, 400)),   # K = 8, one strip
+    dict(n_units=2, max_reads=5, max_haps=3, read_len=(257, 700), hap_len=(300, 500)),   # K = 8, several strips
+])
+def test_pdhmm_matches_oracle(shape):
+    from gatk_b200.native import GpuPhmm
+    with GpuPhmm() as hmm, GpuPhmm(force_fp64=True) as hmm64:
+        for seed in range(3):
+            b, pd = _pd_batch(seed, **shape)
+            want = _pd_oracle(b, pd)
+            _close(hmm.pd_compute(b, pd), want, 1e-4)
+            _close(hmm64.pd_compute(b, pd), want, 1e-9)
+            assert hmm64.stats()["rescued_pairs"] > 0
+
+
+@pytest.mark.gpu
+def test_pdhmm_special_cases():
+    from gatk_b200 import native
+    from gatk_b200.native import Batch, GpuPhmm
+    with GpuPhmm() as hmm:
+        # no flags at all: the plain PairHMM
+        b, pd = _pd_batch(11, 4, 10, 6, (20, 250), (150, 300), modes=(0,))
+        assert np.abs(hmm.pd_compute(b, pd) - hmm.compute(b)).max() < 1e-5
+        # a flag on the LAST haplotype base carries the state into the next row (LoglessPDPairHMM.java:59)
+        rng = np.random.default_rng(5)
+        for last in (DEL_START, DEL_END, DEL_START | DEL_END):
+            hap = L[rng.integers(0, 4, 50)]
+            pd = random_pd(rng, 50, 2)
+            pd[-1] |= last
+            reads = [(hap[5:45].copy(), np.full(40, 30, np.uint8), np.full(40, 45, np.uint8), np.full(40, 45, np.uint8), np.full(40, 10, np.uint8))]
+            b = Batch.single_unit(reads, [hap.tobytes()])
+            _close(hmm.pd_compute(b, pd), _pd_oracle(b, pd), 1e-4)
+        # hopeless pairs go through the fp64 redo, still Java's numbers
+        hap = np.full(300, ord("A"), np.uint8)
+        pd = np.zeros(300, np.uint8)
+        pd[100], pd[120] = DEL_START, DEL_END
+        reads = [(np.full(R, ord("C"), np.uint8), np.full(R, 40, np.uint8), np.full(R, 60, np.uint8), np.full(R, 60, np.uint8), np.full(R, 40, np.uint8))
+                 for R in (10, 40, 100, 150)]
+        b = Batch.single_unit(reads, [hap.tobytes()])
+        hmm.reset_stats()
+        got, want = hmm.pd_compute(b, pd), _pd_oracle(b, pd)
+        assert hmm.stats()["rescued_pairs"] >= 2 and want.min() < -300
+        _close(got, want, 1e-9 if False else 1e-4)
+        assert np.abs(got[want < -100] - want[want < -100]).max() < 1e-9
+        # a read base that is not ACGT on a SNP column: the reference throws (LoglessPDPairHMM.java:202)
+        hap = np.frombuffer(b"ACGTACGTAC", dtype=np.uint8)
+        pd = np.zeros(10, np.uint8)
+        pd[3] = SNP | A
+        bad = Batch.single_unit([(np.frombuffer(b"ACGRACGT", dtype=np.uint8), np.full(8, 30, np.uint8), np.full(8, 45, np.uint8),
+                                  np.full(8, 45, np.uint8), np.full(8, 10, np.uint8))], [hap.tobytes()])
+        with pytest.raises(native.GpuPhmmError) as e:
+            hmm.pd_compute(bad, pd)
+        assert e.value.code == native.ERR_INVALID_ARG
+        with pytest.raises(ValueError):
+            hmm.pd_compute(bad, pd[:5])
