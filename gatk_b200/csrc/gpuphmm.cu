@@ -1684,7 +1684,10 @@ int run_pd_batch(gphmm *h, const gphmm_batch *b, const uint8_t *hap_pd, double *
     Device &dev = *h->devices[0];
     CK(cudaSetDevice(dev.ordinal));
     cudaStream_t st = dev.streams[0];
-    static const KernelInfo kf[3] = {pd_kernel_info<float, 2>(), pd_kernel_info<float, 4>(), pd_kernel_info<float, 8>()};
+    // reads of 128+ bases: 4 rows per lane in strips of 128 rows keeps 18 warps per SM resident (113 registers) where the
+    // 8-row variant (181 registers) keeps 11; GPHMM_PD_K8=1 selects the latter for comparison
+    static const bool k8 = getenv("GPHMM_PD_K8") != nullptr;
+    static const KernelInfo kf[3] = {pd_kernel_info<float, 2>(), pd_kernel_info<float, 4>(), k8 ? pd_kernel_info<float, 8>() : pd_kernel_info<float, 4>()};
     static const KernelInfo kd = pd_kernel_info<double, 4>();
     const auto chunks = split_units(b, h->chunk_cells() / 4, h->chunk_bytes(), false);
     int64_t launches = 0, total_pairs = 0, total_cells = 0, total_redo = 0, h2d = 0, d2h = 0;

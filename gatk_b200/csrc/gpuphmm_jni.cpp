@@ -24,6 +24,7 @@ namespace {
 struct FieldIds {
     bool ready = false;
     jfieldID readBases, readQuals, insertionGOP, deletionGOP, overallGCP, haplotypeBases;
+    jfieldID haplotypePDBases = nullptr;  // present in the holders the PD-HMM binding uses (VectorLoglessPairPDHMM.java:104)
 };
 FieldIds g_ids;
 std::mutex g_mu;
@@ -51,7 +52,7 @@ struct Pending {
 
 struct Session {
     gphmm_t *h = nullptr;
-    Pinned bases, q, iq, dq, gcp, haps;
+    Pinned bases, q, iq, dq, gcp, haps, pd;
     std::vector<int64_t> read_off, hap_off;
     std::map<uint64_t, Pending> pending;
 };
@@ -267,6 +268,55 @@ JNIEXPORT void JNICALL JNIFN(nativeComputeRegion)(JNIEnv *env, jclass, jlong han
     if (need) env->SetDoubleArrayRegion(out, 0, need, res.data());
     if (n_reads) env->SetByteArrayRegion(keep, 0, n_reads, reinterpret_cast<const jbyte *>(kp.data()));
     if (hmmBaseQuals && s->read_off.back()) env->SetByteArrayRegion(hmmBaseQuals, 0, static_cast<jsize>(s->read_off.back()), reinterpret_cast<const jbyte *>(hq.data()));
+}
+
+// PD-HMM (include/gpuphmm.h gphmm_pd_compute): like nativeCompute, with HaplotypeDataHolder.haplotypePDBases
+// (VectorLoglessPairPDHMM.java:100-105) handed over as the flag array parallel to the haplotype bases.
+JNIEXPORT void JNICALL JNIFN(nativeComputePD)(JNIEnv *env, jclass, jlong handle, jobjectArray reads, jobjectArray haps, jdoubleArray out) {
+    Session *s = reinterpret_cast<Session *>(handle);
+    gphmm_batch b;
+    gphmm_unit unit;
+    if (!pack(env, s, reads, haps, &b, &unit)) return;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        if (!g_ids.haplotypePDBases) {
+            jclass hc = env->FindClass("org/broadinstitute/gatk/nativebindings/pairhmm/HaplotypeDataHolder");
+            if (hc) g_ids.haplotypePDBases = env->GetFieldID(hc, "haplotypePDBases", "[B");
+        }
+    }
+    if (!g_ids.haplotypePDBases) {
+        if (!env->ExceptionCheck()) throw_java(env, "java/lang/IllegalStateException", "HaplotypeDataHolder has no haplotypePDBases field");
+        return;
+    }
+    if (!s->pd.reserve(static_cast<size_t>(s->hap_off.back()) + 1)) {
+        throw_java(env, "java/lang/OutOfMemoryError", "pinned staging allocation failed");
+        return;
+    }
+    for (jsize h = 0; h < static_cast<jsize>(b.n_haps); ++h) {
+        jobject o = env->GetObjectArrayElement(haps, h);
+        jbyteArray pd = static_cast<jbyteArray>(env->GetObjectField(o, g_ids.haplotypePDBases));
+        env->DeleteLocalRef(o);
+        const jsize len = static_cast<jsize>(s->hap_off[h + 1] - s->hap_off[h]);
+        if (!pd || env->GetArrayLength(pd) != len) {
+            throw_java(env, "java/lang/IllegalArgumentException", "haplotypePDBases must have one byte per haplotype base");
+            return;
+        }
+        env->GetByteArrayRegion(pd, 0, len, reinterpret_cast<jbyte *>(s->pd.p + s->hap_off[h]));
+        env->DeleteLocalRef(pd);
+    }
+    const jsize need = static_cast<jsize>(b.n_reads * b.n_haps);
+    if (env->GetArrayLength(out) < need) {
+        throw_java(env, "java/lang/IllegalArgumentException", "likelihood array is too small");
+        return;
+    }
+    if (need == 0) return;
+    std::vector<double> res(static_cast<size_t>(need));
+    const int rc = gphmm_pd_compute(s->h, &b, s->pd.p, res.data());
+    if (rc != GPHMM_OK) {
+        throw_for(env, s, rc);
+        return;
+    }
+    env->SetDoubleArrayRegion(out, 0, need, res.data());
 }
 
 JNIEXPORT jlong JNICALL JNIFN(nativeSubmit)(JNIEnv *env, jclass, jlong handle, jobjectArray reads, jobjectArray haps) {

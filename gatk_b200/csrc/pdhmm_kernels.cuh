@@ -143,33 +143,53 @@ __global__ void __launch_bounds__(32) phmm_pd_kernel(const PdArgs g)
                     t_rest = t.carry == PD_INSIDE_DEL ? PD_INSIDE_DEL : (t.carry == PD_AFTER_DEL && p == 1 ? PD_AFTER_DEL : PD_NORMAL);
 
                 T Mn[K], Dn[K], In[K], nbM[K], nbI[K], nbD[K];
+                const bool row1_lane = first_strip && lane == 0;
+                // Most columns carry no flag: when every lane of the warp is on such a column (and row 1 agrees with the
+                // other rows), the update is the plain recurrence plus "branch = left neighbour".
+                const bool plain_col = !del_end && t_rest == PD_NORMAL && (!row1_lane || t_row1 == PD_NORMAL);
+                if (__all_sync(FULL, plain_col)) {
 #pragma unroll
-                for (int k = 0; k < K; ++k) {
-                    const uint32_t ty = (first_strip && lane == 0 && k == 0) ? t_row1 : t_rest;
-                    // row above, previous column
-                    T am = k ? M[k - 1] : dgm, ai = k ? I[k - 1] : dgi, ad = k ? D[k - 1] : dgd;
-                    const T abm = k ? bM[k - 1] : dgbm, abi = k ? bI[k - 1] : dgbi, abd = k ? bD[k - 1] : dgbd;
-                    T lm = M[k], ld = D[k];  // this row, previous column
-                    if (ty == PD_NORMAL) {
+                    for (int k = 0; k < K; ++k) {
+                        const T am = k ? M[k - 1] : dgm, ai = k ? I[k - 1] : dgi, ad = k ? D[k - 1] : dgd;
+                        bool match = xb[k] == hb || xb[k] == (uint32_t)'N' || hb == (uint32_t)'N';
+                        if (!match && (fl & PD_SNP_BIT)) {
+                            if (abit[k] & 0x80000000u) atomicExch(g.err, 2);
+                            match = (mask & abit[k]) != 0;
+                        }
+                        const T prior = valid ? (match ? pm[k] : px[k]) : (T)0;
                         nbM[k] = M[k]; nbI[k] = I[k]; nbD[k] = D[k];
-                    } else if (ty == PD_INSIDE_DEL) {
-                        nbM[k] = bM[k]; nbI[k] = bI[k]; nbD[k] = bD[k];
-                    } else {
-                        nbM[k] = pd_max(bM[k], M[k]); nbI[k] = pd_max(bI[k], I[k]); nbD[k] = pd_max(bD[k], D[k]);
-                        am = pd_max(abm, am); ai = pd_max(abi, ai); ad = pd_max(abd, ad);
-                        lm = nbM[k]; ld = nbD[k];
+                        Mn[k] = prior * (am * tMM[k] + ai * tIM[k] + ad * tIM[k]);
+                        Dn[k] = M[k] * tMD[k] + D[k] * tII[k];
                     }
-                    bool match = xb[k] == hb || xb[k] == (uint32_t)'N' || hb == (uint32_t)'N';
-                    if (!match && (fl & PD_SNP_BIT)) {
-                        if (abit[k] & 0x80000000u) atomicExch(g.err, 2);
-                        match = (mask & abit[k]) != 0;
+                    In[0] = mu * tMI[0] + iu * tII[0];
+#pragma unroll
+                    for (int k = 1; k < K; ++k) In[k] = Mn[k - 1] * tMI[k] + In[k - 1] * tII[k];
+                } else {
+#pragma unroll
+                    for (int k = 0; k < K; ++k) {
+                        const uint32_t ty = (row1_lane && k == 0) ? t_row1 : t_rest;
+                        const bool inside = ty == PD_INSIDE_DEL, after = ty == PD_AFTER_DEL;
+                        // row above, previous column
+                        T am = k ? M[k - 1] : dgm, ai = k ? I[k - 1] : dgi, ad = k ? D[k - 1] : dgd;
+                        const T abm = k ? bM[k - 1] : dgbm, abi = k ? bI[k - 1] : dgbi, abd = k ? bD[k - 1] : dgbd;
+                        // branch values: copy from the left (NORMAL), hold (INSIDE_DEL) or merge (AFTER_DEL); selects, no branches:
+                        // the lanes of a warp sit on different columns
+                        const T xm = pd_max(bM[k], M[k]), xi = pd_max(bI[k], I[k]), xd = pd_max(bD[k], D[k]);
+                        nbM[k] = inside ? bM[k] : (after ? xm : M[k]);
+                        nbI[k] = inside ? bI[k] : (after ? xi : I[k]);
+                        nbD[k] = inside ? bD[k] : (after ? xd : D[k]);
+                        am = after ? pd_max(abm, am) : am; ai = after ? pd_max(abi, ai) : ai; ad = after ? pd_max(abd, ad) : ad;
+                        const T lm = after ? xm : M[k], ld = after ? xd : D[k];  // this row, previous column
+                        bool match = xb[k] == hb || xb[k] == (uint32_t)'N' || hb == (uint32_t)'N';
+                        if (!match && (fl & PD_SNP_BIT)) {
+                            if (abit[k] & 0x80000000u) atomicExch(g.err, 2);
+                            match = (mask & abit[k]) != 0;
+                        }
+                        const T prior = valid ? (match ? pm[k] : px[k]) : (T)0;
+                        Mn[k] = prior * (am * tMM[k] + ai * tIM[k] + ad * tIM[k]);
+                        Dn[k] = lm * tMD[k] + ld * tII[k];  // deletionToDeletion = insertionToInsertion = eps(gcp)
                     }
-                    const T prior = valid ? (match ? pm[k] : px[k]) : (T)0;
-                    Mn[k] = prior * (am * tMM[k] + ai * tIM[k] + ad * tIM[k]);
-                    Dn[k] = lm * tMD[k] + ld * tII[k];  // deletionToDeletion = insertionToInsertion = eps(gcp)
-                }
-                // insertion: row above at THIS column -- chain down the lane's rows
-                {
+                    // insertion: row above at THIS column -- chain down the lane's rows
                     T um = mu, ui = iu, ubm = bmu, ubi = biu;
 #pragma unroll
                     for (int k = 0; k < K; ++k) {

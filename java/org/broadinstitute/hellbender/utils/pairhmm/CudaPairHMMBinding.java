@@ -108,6 +108,19 @@ public final class CudaPairHMMBinding implements PairHMMNativeBinding {
         nativeComputeRegion(handle, readDataArray, mappingQualities, haplotypeDataArray, intParams, doubleParams, likelihoods, keep, hmmBaseQualities);
     }
 
+    /**
+     * PD-HMM (DRAGEN-GATK partially determined haplotypes): the same call as {@link #computeLikelihoods} with
+     * {@code HaplotypeDataHolder.haplotypePDBases} filled in, as {@code PairPDHMMNativeBinding.computeLikelihoods} is
+     * called at VectorLoglessPairPDHMM.java:115.
+     */
+    public void computePDLikelihoods(final ReadDataHolder[] readDataArray, final HaplotypeDataHolder[] haplotypeDataArray,
+                                     final double[] likelihoodArray) {
+        if (handle == 0L) {
+            throw new IllegalStateException("CudaPairHMMBinding.initialize() has not been called");
+        }
+        nativeComputePD(handle, readDataArray, haplotypeDataArray, likelihoodArray);
+    }
+
     @Override
     public void done() {
         if (handle != 0L) {
@@ -131,6 +144,7 @@ public final class CudaPairHMMBinding implements PairHMMNativeBinding {
     private static native void nativeCompute(long handle, ReadDataHolder[] reads, HaplotypeDataHolder[] haps, double[] out);
     private static native void nativeComputeRegion(long handle, ReadDataHolder[] reads, byte[] mapq, HaplotypeDataHolder[] haps,
                                                    int[] intParams, double[] doubleParams, double[] out, byte[] keep, byte[] hmmBaseQuals);
+    private static native void nativeComputePD(long handle, ReadDataHolder[] reads, HaplotypeDataHolder[] haps, double[] out);
     private static native long nativeSubmit(long handle, ReadDataHolder[] reads, HaplotypeDataHolder[] haps);
     private static native void nativeAwait(long handle, long ticket, double[] out);
     private static native void nativeDestroy(long handle);

@@ -12,8 +12,17 @@ SNP, DEL_START, DEL_END, A, C, G, T = 1, 2, 4, 8, 16, 32, 64
 
 
 def random_pd(rng, H, mode):
-    """mode 0: no flags; 1: SNP sites; 2: SNPs + well-formed deletions; 3: arbitrary flag bytes"""
+    """mode 0: no flags; 1: SNP sites; 2: SNPs + well-formed deletions; 3: arbitrary flag bytes; 4: sparse (a handful of
+    undetermined sites per haplotype, like the partially determined haplotypes of one assembly region)"""
     pd = np.zeros(H, np.uint8)
+    if mode == 4:
+        for _ in range(int(rng.integers(1, 5))):
+            pd[int(rng.integers(0, H))] |= SNP | int(rng.choice([A, C, G, T]))
+        if H > 12 and rng.random() < 0.5:
+            j = int(rng.integers(0, H - 8))
+            pd[j] |= DEL_START
+            pd[j + int(rng.integers(0, 8))] |= DEL_END
+        return pd
     if mode == 3:
         return rng.integers(0, 128, H).astype(np.uint8)
     if mode >= 1:
