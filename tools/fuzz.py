@@ -12,6 +12,7 @@ from gatk_b200 import synth
 from gatk_b200.native import Batch, GpuPhmm
 from oracle import oracle
 from phmm_testutil import oracle_batch
+from test_pdhmm import _pd_oracle, random_pd
 
 budget = float(sys.argv[1]) if len(sys.argv) > 1 else 120.0
 seed0 = int(sys.argv[2]) if len(sys.argv) > 2 else 0
@@ -49,7 +50,7 @@ def check(got, want, what):
 
 
 t_end = time.time() + budget
-n_batches = n_pairs = 0
+n_batches = n_pairs = n_pd = 0
 worst = 0.0
 handles = {
     "default": GpuPhmm(),
@@ -101,11 +102,22 @@ try:
                 keep = oracle.filter_poorly_modeled(norm, nr, nh, q, b.read_off[r0:r1 + 1], 0.02, kw["dynamic_disqualification"], 1.0)
                 assert np.array_equal(norm, got["lk"][o:o + nr * nh]), "seed %d normalize unit %d" % (seed, k)
                 assert np.array_equal(keep, got["keep"][r0:r1]), "seed %d keep unit %d" % (seed, k)
+        if shape in (0, 2) and mode != "extreme" and b.n_out <= 400:
+            # PD-HMM against its oracle (per-pair Python loop: small batches only); exotic haplotype bytes are fine, a
+            # non-ACGT read base on a SNP column is the reference's exception -> strip the N's from the reads first
+            rb = b.read_bases.copy()
+            rb[rb == ord("N")] = ord("A")
+            bp = Batch(rb, b.base_q, b.ins_q, b.del_q, b.gcp, b.read_off, b.hap_bases, b.hap_off, b.units)
+            pd = np.concatenate([random_pd(rng, int(b.hap_off[k + 1] - b.hap_off[k]), int(rng.integers(0, 5))) for k in range(len(b.hap_off) - 1)])
+            want_pd = _pd_oracle(bp, pd)
+            for name in ("default", "fp64"):
+                worst = max(worst, check(handles[name].pd_compute(bp, pd), want_pd, "seed %d pd %s" % (seed, name)))
+            n_pd += 1
         n_batches += 1
         n_pairs += b.n_out
         seed += 1
 finally:
     for h in handles.values():
         h.close()
-print("fuzz: %d batches (seeds %d..%d), %d pairs x 4 configurations + region steps, worst |err| %.3g (bar %g): OK" % (
-    n_batches, seed0, seed - 1, n_pairs, worst, TOL))
+print("fuzz: %d batches (seeds %d..%d), %d pairs x 4 configurations + region steps, %d PD-HMM batches, worst |err| %.3g (bar %g): OK" % (
+    n_batches, seed0, seed - 1, n_pairs, n_pd, worst, TOL))
