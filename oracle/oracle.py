@@ -22,7 +22,7 @@ _f64p = ctypes.POINTER(ctypes.c_double)
 
 def build(force=False):
     """Compile the oracle with the committed Makefile (gcc, -ffp-contract=off)."""
-    srcs = [os.path.join(_HERE, f) for f in ("pairhmm_oracle.c", "pairhmm_simd_baseline.c", "region_steps_oracle.c", "Makefile")]
+    srcs = [os.path.join(_HERE, f) for f in ("pairhmm_oracle.c", "pairhmm_simd_baseline.c", "region_steps_oracle.c", "sw_oracle.c", "Makefile")]
     if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < max(os.path.getmtime(x) for x in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-s", "-B", "libphmm_oracle.so"])
     return _LIB_PATH
@@ -70,6 +70,9 @@ def lib():
         L.region_oracle_filter.restype = None
         L.region_oracle_filter.argtypes = [_f64p, ctypes.c_int, ctypes.c_int, _u8p, ctypes.POINTER(ctypes.c_int64), ctypes.c_double,
                                            ctypes.c_int, ctypes.c_double, _u8p]
+        L.sw_oracle_align.restype = ctypes.c_int
+        L.sw_oracle_align.argtypes = [_u8p, ctypes.c_int, _u8p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                      ctypes.c_int, ctypes.POINTER(ctypes.c_uint32), ctypes.c_int, ctypes.POINTER(ctypes.c_int)]
         L.phmm_oracle_init()
         _lib = L
     return _lib
@@ -245,3 +248,25 @@ def filter_poorly_modeled(lk_allele_major, n_reads, n_haps, hmm_base_q, read_off
     lib().region_oracle_filter(a.ctypes.data_as(_f64p), n_reads, n_haps, q.ctypes.data_as(_u8p), ro.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)),
                                float(max_error_per_base), 1 if dynamic else 0, float(dynamic_scale), keep.ctypes.data_as(_u8p))
     return keep[:n_reads]
+
+
+# ---- Smith-Waterman (oracle/sw_oracle.c) ---------------------------------------------------------------------------------
+SW_SOFTCLIP, SW_INDEL, SW_LEADING_INDEL, SW_IGNORE = 0, 1, 2, 3
+SW_OPS = "MIDS"
+
+
+def cigar_string(elems):
+    return "".join("%d%s" % (int(e) >> 4, SW_OPS[int(e) & 15]) for e in elems)
+
+
+def sw_align(ref, alt, params, strategy):
+    """SmithWatermanJavaAligner.align: params = (match, mismatch, gap open, gap extend) -> (offset, CIGAR string)"""
+    r, a = _bytes(ref), _bytes(alt)
+    cap = len(r) + len(a) + 4
+    elems = np.zeros(cap, np.uint32)
+    off = ctypes.c_int(0)
+    n = lib().sw_oracle_align(r.ctypes.data_as(_u8p), len(r), a.ctypes.data_as(_u8p), len(a), *[int(x) for x in params], int(strategy),
+                              elems.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32)), cap, ctypes.byref(off))
+    if n < 0:
+        raise ValueError("sw oracle error %d" % n)
+    return off.value, cigar_string(elems[:n])
