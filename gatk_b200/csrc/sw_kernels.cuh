@@ -1,0 +1,227 @@
+// sw_kernels.cuh -- GATK's Smith-Waterman aligner on the device.
+//
+// Reference: utils/smithwaterman/SmithWatermanJavaAligner.java  :60-92 align() with the exact-substring shortcut,
+// :105-215 calculateMatrix() (affine gaps through best-gap arrays, ties diag >= right >= down, floor -1e8),
+// :262-375 calculateCigar() (end point per overhang strategy, traceback, clips).  Native counterpart in the reference:
+// SmithWatermanIntelAligner (GKL) behind SWNativeAlignerWrapper.java:33-60.  Integer work: results are bit-exact.
+//
+// One warp per (reference, alternate) pair.  Lane l owns 4 consecutive reference rows of a 128-row strip and sweeps the
+// alternate's columns one per step, lane l on column step-l (the same anti-diagonal wavefront as the PairHMM kernels):
+// the row state (cell to the left, best horizontal gap and its length) stays in registers, the column state (cell
+// above, best vertical gap and its length) is handed down the lanes by three shuffles, strips hand it over through a
+// per-pair boundary row in global memory.  Backtrack entries are written in wavefront order (fully coalesced int16)
+// and lane 0 walks them back afterwards exactly like calculateCigar.
+#pragma once
+#include <stdint.h>
+
+namespace phmm_dev {
+
+constexpr int SW_K = 4, SW_ROWS = 32 * SW_K;
+constexpr int SW_SOFTCLIP = 0, SW_INDEL = 1, SW_LEADING_INDEL = 2, SW_IGNORE = 3;  // SWOverhangStrategy
+constexpr uint32_t SW_OP_M = 0, SW_OP_I = 1, SW_OP_D = 2, SW_OP_S = 3;
+constexpr int SW_MATRIX_MIN_CUTOFF = -100000000;   // SmithWatermanJavaAligner.java:114
+constexpr int SW_LOW_INIT = INT32_MIN / 2;          // :115
+
+struct SwTask {
+    uint32_t ref_off, n_ref, alt_off, n_alt;
+    uint64_t bt_off;     // first int16 of this pair's backtrack area
+    uint32_t aux_off;    // first int of: last column [n_ref + 1] | bottom row [n_alt + 1] | boundary [3 * (n_alt + 1)]
+    uint32_t out_off;    // first CIGAR element slot
+};
+
+struct SwArgs {
+    const uint8_t *ref_bases, *alt_bases;
+    const SwTask *tasks;
+    uint32_t n_tasks;
+    uint32_t *counter;
+    int16_t *bt;
+    int32_t *aux;
+    uint32_t *elems;     // out: (length << 4) | op, CIGAR order
+    int32_t *n_elems;    // out per pair; -1: more than `capacity` elements
+    int32_t *offsets;    // out per pair: alignment offset
+    uint32_t capacity;
+    int32_t w_match, w_mismatch, w_open, w_extend, strategy;
+};
+
+__device__ __forceinline__ int sw_edge(int idx, bool indel, int w_open, int w_extend) {
+    // sw[0][j] and sw[i][0]: 0, or the leading-gap penalties of the INDEL strategies (:125-140)
+    return (!indel || idx == 0) ? 0 : w_open + (idx - 1) * w_extend;
+}
+
+__global__ void __launch_bounds__(32) phmm_sw_kernel(const SwArgs g)
+{
+    constexpr unsigned FULL = 0xffffffffu;
+    constexpr int K = SW_K;
+    const int lane = threadIdx.x;
+    const bool indel = g.strategy == SW_INDEL || g.strategy == SW_LEADING_INDEL;
+    for (;;) {
+        uint32_t ti = 0;
+        if (lane == 0) ti = atomicAdd(g.counter, 1u);
+        ti = __shfl_sync(FULL, ti, 0);
+        if (ti >= g.n_tasks) break;
+        const SwTask t = g.tasks[ti];
+        const uint8_t *__restrict__ ref = g.ref_bases + t.ref_off;
+        const uint8_t *__restrict__ alt = g.alt_bases + t.alt_off;
+        const int n_ref = (int)t.n_ref, n_alt = (int)t.n_alt;
+        uint32_t *out = g.elems + t.out_off;
+
+        // ---- exact-substring shortcut (SmithWatermanJavaAligner.java:72-80, Utils.lastIndexOf) ----
+        if (g.strategy == SW_SOFTCLIP || g.strategy == SW_IGNORE) {
+            int found = -1;
+            for (int base = n_ref - n_alt; base >= 0 && found < 0; base -= 32) {
+                const int r = base - lane;
+                bool ok = r >= 0;
+                for (int q = 0; ok && q < n_alt; ++q) ok = ref[r + q] == alt[q];
+                const unsigned hit = __ballot_sync(FULL, ok);
+                if (hit) found = base - (__ffs(hit) - 1);  // the highest start wins
+            }
+            if (found >= 0) {
+                if (lane == 0) {
+                    if (g.capacity >= 1) { out[0] = ((uint32_t)n_alt << 4) | SW_OP_M; g.n_elems[ti] = 1; } else g.n_elems[ti] = -1;
+                    g.offsets[ti] = found;
+                }
+                continue;
+            }
+        }
+
+        // ---- the matrix ----
+        int32_t *lastcol = g.aux + t.aux_off, *bottom = lastcol + (n_ref + 1), *bnd = bottom + (n_alt + 1);
+        int16_t *bt = g.bt + t.bt_off;
+        const int n_strips = (n_ref + SW_ROWS - 1) / SW_ROWS, n_steps = n_alt + 31;
+        for (int strip = 0; strip < n_strips; ++strip) {
+            const bool first_strip = strip == 0, last_strip = strip == n_strips - 1;
+            const int row0 = strip * SW_ROWS + lane * K;  // row of k = 0 is row0 + 1
+            int a[K], left[K], bgh[K], gsh[K];
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                const int i = row0 + k + 1;
+                a[k] = i <= n_ref ? (int)ref[i - 1] : 0x100;
+                left[k] = sw_edge(i, indel, g.w_open, g.w_extend);  // sw[i][0]
+                bgh[k] = SW_LOW_INIT; gsh[k] = 0;
+            }
+            int last_sw = 0, last_bgv = SW_LOW_INIT, last_gsv = 0;  // this lane's bottom row at its current column (what the lane below needs)
+            int diag0 = sw_edge(row0, indel, g.w_open, g.w_extend); // sw[row0][0]: row above at column 0
+            __syncwarp();
+            int p = 1 - lane;
+            for (int s = 1; s <= n_steps; ++s, ++p) {
+                const bool valid = p >= 1 && p <= n_alt;
+                // row above at this column
+                int up = __shfl_up_sync(FULL, last_sw, 1), bgv = __shfl_up_sync(FULL, last_bgv, 1), gsv = __shfl_up_sync(FULL, last_gsv, 1);
+                if (lane == 0) {
+                    if (first_strip) { up = sw_edge(p, indel, g.w_open, g.w_extend); bgv = SW_LOW_INIT; gsv = 0; }
+                    else if (valid) { up = bnd[3 * p]; bgv = bnd[3 * p + 1]; gsv = bnd[3 * p + 2]; }
+                }
+                const int b = valid ? (int)alt[p - 1] : 0x200;
+                const int up_in = up;
+                int diag = diag0;
+                short4 btv;
+                int16_t *btk = reinterpret_cast<int16_t *>(&btv);
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    const int step_diag = diag + (a[k] == b ? g.w_match : g.w_mismatch);
+                    int prev_gap = up + g.w_open;
+                    bgv += g.w_extend;
+                    if (prev_gap > bgv) { bgv = prev_gap; gsv = 1; } else ++gsv;
+                    const int step_down = bgv, kd = gsv;
+                    prev_gap = left[k] + g.w_open;
+                    int nbgh = bgh[k] + g.w_extend, ngsh = gsh[k] + 1;
+                    if (prev_gap > nbgh) { nbgh = prev_gap; ngsh = 1; }
+                    const int step_right = nbgh, ki = ngsh;
+                    int cur, btr;
+                    if (step_diag >= step_down && step_diag >= step_right) { cur = step_diag; btr = 0; }
+                    else if (step_right >= step_down) { cur = step_right; btr = -ki; }
+                    else { cur = step_down; btr = kd; }
+                    cur = max(SW_MATRIX_MIN_CUTOFF, cur);
+                    btk[k] = (int16_t)btr;
+                    diag = left[k];          // sw[i][j-1] is the diagonal of the row below
+                    if (valid) { left[k] = cur; bgh[k] = nbgh; gsh[k] = ngsh; }
+                    up = cur;                // and this cell is "above" for the row below
+                    const int i = row0 + k + 1;
+                    if (valid && p == n_alt && i <= n_ref) lastcol[i] = cur;
+                    if (valid && i == n_ref) bottom[p] = cur;
+                }
+                if (valid) {
+                    *reinterpret_cast<short4 *>(bt + (((size_t)strip * n_steps + (s - 1)) * 32 + lane) * K) = btv;
+                    last_sw = up; last_bgv = bgv; last_gsv = gsv;
+                    diag0 = up_in;           // row above at this column = diagonal of k = 0 at the next column
+                    if (!last_strip && lane == 31) { bnd[3 * p] = up; bnd[3 * p + 1] = bgv; bnd[3 * p + 2] = gsv; }
+                }
+            }
+            __syncwarp();
+        }
+        __threadfence_block();
+        __syncwarp();
+
+        // ---- calculateCigar (:262-375), lane 0 ----
+        if (lane == 0) {
+            auto BT = [&](int i, int j) -> int {
+                const int strip = (i - 1) / SW_ROWS, ln = ((i - 1) % SW_ROWS) / K, k = (i - 1) % K;
+                return (int)bt[(((size_t)strip * n_steps + (j + ln - 1)) * 32 + ln) * K + k];
+            };
+            int p1 = 0, p2 = 0, maxscore = INT32_MIN, segment_length = 0;
+            if (g.strategy == SW_INDEL) {
+                p1 = n_ref; p2 = n_alt;
+            } else {
+                p2 = n_alt;
+                for (int i = 1; i <= n_ref; ++i) {
+                    const int cur = lastcol[i];
+                    if (cur >= maxscore) { p1 = i; maxscore = cur; }
+                }
+                if (g.strategy != SW_LEADING_INDEL) {
+                    for (int j = 1; j <= n_alt; ++j) {
+                        const int cur = bottom[j];
+                        if (cur > maxscore || (cur == maxscore && abs(n_ref - j) < abs(p1 - p2))) {
+                            p1 = n_ref; p2 = j; maxscore = cur; segment_length = n_alt - j;
+                        }
+                    }
+                }
+            }
+            uint32_t n = 0;
+            bool overflow = false;
+            auto push = [&](uint32_t op, int len) {
+                if (n < g.capacity) out[n] = ((uint32_t)len << 4) | op; else overflow = true;
+                ++n;
+            };
+            if (segment_length > 0 && g.strategy == SW_SOFTCLIP) { push(SW_OP_S, segment_length); segment_length = 0; }
+            uint32_t state = SW_OP_M;
+            do {
+                const int btr = BT(p1, p2);
+                uint32_t new_state;
+                int step_length = 1;
+                if (btr > 0) { new_state = SW_OP_D; step_length = btr; }
+                else if (btr < 0) { new_state = SW_OP_I; step_length = -btr; }
+                else new_state = SW_OP_M;
+                if (new_state == SW_OP_M) { --p1; --p2; } else if (new_state == SW_OP_I) p2 -= step_length; else p1 -= step_length;
+                if (new_state == state) segment_length += step_length;
+                else {
+                    if (segment_length > 0) push(state, segment_length);
+                    segment_length = step_length;
+                    state = new_state;
+                }
+            } while (p1 > 0 && p2 > 0);
+            int offset;
+            if (g.strategy == SW_SOFTCLIP) {
+                push(state, segment_length);
+                if (p2 > 0) push(SW_OP_S, p2);
+                offset = p1;
+            } else if (g.strategy == SW_IGNORE) {
+                push(state, segment_length + p2);
+                offset = p1 - p2;
+            } else {
+                push(state, segment_length);
+                if (p1 > 0) push(SW_OP_D, p1); else if (p2 > 0) push(SW_OP_I, p2);
+                offset = 0;
+            }
+            if (overflow) {
+                g.n_elems[ti] = -1;
+            } else {
+                for (uint32_t x = 0, y = n - 1; x < y; ++x, --y) { const uint32_t tmp = out[x]; out[x] = out[y]; out[y] = tmp; }  // Lists.reverse (:374)
+                g.n_elems[ti] = (int32_t)n;
+            }
+            g.offsets[ti] = offset;
+        }
+        __syncwarp();
+    }
+}
+
+}  // namespace phmm_dev

@@ -59,12 +59,25 @@ class _RegionSteps(ctypes.Structure):
                 ("hmm_del_q", ctypes.c_void_p), ("raw_lk", ctypes.c_void_p)]
 
 
+class _SwParams(ctypes.Structure):
+    _fields_ = [("struct_size", ctypes.c_int32), ("match_value", ctypes.c_int32), ("mismatch_penalty", ctypes.c_int32),
+                ("gap_open_penalty", ctypes.c_int32), ("gap_extend_penalty", ctypes.c_int32), ("overhang_strategy", ctypes.c_int32)]
+
+
+class _SwBatch(ctypes.Structure):
+    _fields_ = [("ref_bases", ctypes.c_void_p), ("ref_off", ctypes.c_void_p), ("alt_bases", ctypes.c_void_p),
+                ("alt_off", ctypes.c_void_p), ("n_pairs", ctypes.c_int64)]
+
+
+SW_SOFTCLIP, SW_INDEL, SW_LEADING_INDEL, SW_IGNORE = 0, 1, 2, 3
+ERR_TOO_LARGE = -8
+
 RS_DISABLE_CAP_TO_MAPQ, RS_SYMMETRIC_NORMALIZE, RS_FILTER_POORLY, RS_DYNAMIC_DISQ = 1, 2, 4, 8
 
 UNIT_DTYPE = np.dtype([("read_begin", "<i8"), ("read_end", "<i8"), ("hap_begin", "<i8"), ("hap_end", "<i8"), ("out_off", "<i8")])
 
 EXPORTS = ["gphmm_abi_version", "gphmm_device_count", "gphmm_strerror", "gphmm_create", "gphmm_destroy",
-           "gphmm_last_error", "gphmm_compute", "gphmm_compute_regions", "gphmm_submit_regions", "gphmm_pd_compute", "gphmm_submit", "gphmm_wait", "gphmm_prepare", "gphmm_run_prepared",
+           "gphmm_last_error", "gphmm_compute", "gphmm_compute_regions", "gphmm_submit_regions", "gphmm_pd_compute", "gphmm_sw_align", "gphmm_submit", "gphmm_wait", "gphmm_prepare", "gphmm_run_prepared",
            "gphmm_release_prepared", "gphmm_get_stats", "gphmm_reset_stats", "gphmm_plan_stats", "gphmm_host_alloc", "gphmm_host_free"]
 
 
@@ -102,6 +115,9 @@ def load_library():
     L.gphmm_compute_regions.argtypes = [ctypes.c_void_p, ctypes.POINTER(_Batch), ctypes.POINTER(_RegionSteps), ctypes.c_void_p]
     L.gphmm_pd_compute.restype = ctypes.c_int
     L.gphmm_pd_compute.argtypes = [ctypes.c_void_p, ctypes.POINTER(_Batch), ctypes.c_void_p, ctypes.c_void_p]
+    L.gphmm_sw_align.restype = ctypes.c_int
+    L.gphmm_sw_align.argtypes = [ctypes.c_void_p, ctypes.POINTER(_SwBatch), ctypes.POINTER(_SwParams), ctypes.c_int32, ctypes.c_void_p,
+                                 ctypes.c_void_p, ctypes.c_void_p]
     L.gphmm_submit_regions.restype = ctypes.c_int
     L.gphmm_submit_regions.argtypes = [ctypes.c_void_p, ctypes.POINTER(_Batch), ctypes.POINTER(_RegionSteps), ctypes.c_void_p,
                                        ctypes.POINTER(ctypes.c_uint64)]
@@ -381,6 +397,26 @@ class GpuPhmm:
         b = batch.c_struct()
         self._check(self._L.gphmm_pd_compute(self._h, ctypes.byref(b), pd.ctypes.data if len(pd) else None, out.ctypes.data))
         return out
+
+    def sw_align(self, refs, alts, params, strategy, cigar_capacity=64):
+        """gphmm_sw_align: refs / alts are lists of bytes (pair k aligns alts[k] to refs[k]); params = (match, mismatch, gap open,
+        gap extend).  Returns a list of (offset, CIGAR string)."""
+        n = len(refs)
+        assert len(alts) == n
+        cat = lambda xs: np.frombuffer(b"".join(bytes(x) for x in xs), dtype=np.uint8) if n else np.zeros(0, np.uint8)
+        rb, ab = cat(refs), cat(alts)
+        ro = np.concatenate([[0], np.cumsum([len(x) for x in refs])]).astype(np.int64)
+        ao = np.concatenate([[0], np.cumsum([len(x) for x in alts])]).astype(np.int64)
+        b = _SwBatch(rb.ctypes.data if len(rb) else None, ro.ctypes.data, ab.ctypes.data if len(ab) else None, ao.ctypes.data, n)
+        p = _SwParams(ctypes.sizeof(_SwParams), int(params[0]), int(params[1]), int(params[2]), int(params[3]), int(strategy))
+        offsets = np.zeros(max(n, 1), np.int32)
+        n_elems = np.zeros(max(n, 1), np.int32)
+        elems = np.zeros(max(n, 1) * cigar_capacity, np.uint32)
+        self._check(self._L.gphmm_sw_align(self._h, ctypes.byref(b), ctypes.byref(p), cigar_capacity, offsets.ctypes.data, n_elems.ctypes.data,
+                                           elems.ctypes.data))
+        ops = "MIDS"
+        return [(int(offsets[k]), "".join("%d%s" % (int(e) >> 4, ops[int(e) & 15]) for e in elems[k * cigar_capacity:k * cigar_capacity + n_elems[k]]))
+                for k in range(n)]
 
     def submit_regions(self, batch, mapq, ref_hap=None, **params):
         """gphmm_submit_regions; wait(ticket) returns the result dict of compute_regions"""

@@ -173,6 +173,38 @@ int gphmm_submit_regions(gphmm_t *h, const gphmm_batch *batch, const gphmm_regio
  * Output layout as gphmm_compute.  The read-span filter of VectorLoglessPairPDHMM.java:129-137 stays with the caller. */
 int gphmm_pd_compute(gphmm_t *h, const gphmm_batch *batch, const uint8_t *hap_pd_bases, double *out);
 
+/* ---- Smith-Waterman ---------------------------------------------------------------------------------
+ * Batched form of SmithWatermanAligner.align(reference, alternate, SWParameters, SWOverhangStrategy)
+ * (utils/smithwaterman/SmithWatermanJavaAligner.java:60-92; native counterpart SWNativeAlignerWrapper.java:33-60 over
+ * GKL's SWAlignerNativeBinding).  Pair k aligns alt k to ref k; all pairs share one parameter set.  Results are
+ * bit-identical with the Java aligner: offsets[k] = getAlignmentOffset(), elems[k*cigar_capacity .. +n_elems[k]) =
+ * the CIGAR, each element (length << 4) | op with op 0 M, 1 I, 2 D, 3 S.  A CIGAR longer than cigar_capacity sets
+ * n_elems[k] = -1 and the call returns GPHMM_ERR_TOO_LARGE (all other pairs are valid). */
+#define GPHMM_SW_SOFTCLIP 0
+#define GPHMM_SW_INDEL 1
+#define GPHMM_SW_LEADING_INDEL 2
+#define GPHMM_SW_IGNORE 3
+
+typedef struct gphmm_sw_params {
+    int32_t struct_size;        /* sizeof(gphmm_sw_params) */
+    int32_t match_value;        /* SWParameters.getMatchValue() */
+    int32_t mismatch_penalty;   /* getMismatchPenalty(), negative */
+    int32_t gap_open_penalty;   /* getGapOpenPenalty(), negative */
+    int32_t gap_extend_penalty; /* getGapExtendPenalty(), negative */
+    int32_t overhang_strategy;  /* GPHMM_SW_* */
+} gphmm_sw_params;
+
+typedef struct gphmm_sw_batch {
+    const uint8_t *ref_bases;   /* references, concatenated */
+    const int64_t *ref_off;     /* n_pairs + 1 */
+    const uint8_t *alt_bases;   /* alternates (reads / haplotypes), concatenated */
+    const int64_t *alt_off;     /* n_pairs + 1 */
+    int64_t n_pairs;
+} gphmm_sw_batch;
+
+int gphmm_sw_align(gphmm_t *h, const gphmm_sw_batch *batch, const gphmm_sw_params *params, int32_t cigar_capacity,
+                   int32_t *offsets, int32_t *n_elems, uint32_t *elems);
+
 /* Statistics accumulate over calls until reset. */
 int gphmm_get_stats(const gphmm_t *h, gphmm_stats *out);
 void gphmm_reset_stats(gphmm_t *h);

@@ -66,3 +66,80 @@ def test_oracle_identical_alignments_with_differing_flank_lengths():
 def test_oracle_rejects_empty_sequences():
     with pytest.raises(ValueError):
         O.sw_align(b"", b"ACGT", ORIGINAL_DEFAULT, O.SW_SOFTCLIP)    # SmithWatermanJavaAligner.java:64-66
+
+
+# ---- device ---------------------------------------------------------------------------------------------------------
+def _mutated(rng, seq, n_events):
+    s = bytearray(seq)
+    for _ in range(n_events):
+        if len(s) < 4:
+            break
+        pos = int(rng.integers(0, len(s)))
+        kind = int(rng.integers(0, 3))
+        if kind == 0:
+            s[pos] = b"ACGT"[int(rng.integers(0, 4))]
+        elif kind == 1:
+            s[pos:pos] = bytes(rng.choice(list(b"ACGT"), int(rng.integers(1, 12))).astype(np.uint8))
+        else:
+            del s[pos:pos + int(rng.integers(1, 12))]
+    return bytes(s) if len(s) else b"A"
+
+
+def _random_pairs(seed, n, ref_len, alt_len):
+    rng = np.random.default_rng(seed)
+    refs, alts = [], []
+    for _ in range(n):
+        nr = int(rng.integers(ref_len[0], ref_len[1] + 1))
+        ref = bytes(rng.choice(list(b"ACGT"), nr).astype(np.uint8))
+        na = int(rng.integers(alt_len[0], alt_len[1] + 1))
+        u = rng.random()
+        if u < 0.7 and nr >= 2:
+            a = int(rng.integers(0, nr - 1))
+            alt = _mutated(rng, ref[a:a + na], int(rng.integers(0, 6)))
+        elif u < 0.85:
+            alt = bytes(rng.choice(list(b"ACGT"), na).astype(np.uint8))
+        else:
+            alt = _mutated(rng, ref, int(rng.integers(0, 4)))     # haplotype-to-reference style
+        refs.append(ref)
+        alts.append(alt)
+    return refs, alts
+
+
+@pytest.mark.gpu
+def test_sw_known_answers_on_device():
+    from gatk_b200.native import GpuPhmm
+    with GpuPhmm() as hmm:
+        for ref, read, params, strategy, want_off, want_cigar in KATS:
+            assert hmm.sw_align([ref], [read], params, strategy) == [(want_off, want_cigar)], (read, strategy)
+        pad = b"N" * 10
+        got = hmm.sw_align([pad + PADDED_REF + pad, pad + NOT_PADDED_REF + pad], [pad + PADDED_HAP + pad, pad + NOT_PADDED_HAP + pad],
+                           NEW_SW_PARAMETERS, O.SW_SOFTCLIP)
+        assert _non_match_elements(got[0][1]) == _non_match_elements(got[1][1])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("strategy", [O.SW_SOFTCLIP, O.SW_INDEL, O.SW_LEADING_INDEL, O.SW_IGNORE])
+def test_sw_matches_oracle_bit_for_bit(strategy):
+    from gatk_b200.native import GpuPhmm
+    with GpuPhmm() as hmm:
+        for seed, (ref_len, alt_len, n) in enumerate([((1, 40), (1, 40), 300), ((100, 500), (20, 260), 200), ((400, 1100), (300, 1000), 40)]):
+            for params in (ORIGINAL_DEFAULT, STANDARD_NGS, NEW_SW_PARAMETERS, ALIGNMENT_TO_BEST_HAPLOTYPE):
+                refs, alts = _random_pairs(100 * seed + strategy, n, ref_len, alt_len)
+                got = hmm.sw_align(refs, alts, params, strategy, cigar_capacity=2200)
+                want = [O.sw_align(r, a, params, strategy) for r, a in zip(refs, alts)]
+                assert got == want
+
+
+@pytest.mark.gpu
+def test_sw_errors_and_capacity():
+    from gatk_b200 import native
+    from gatk_b200.native import GpuPhmm
+    with GpuPhmm() as hmm:
+        with pytest.raises(native.GpuPhmmError) as e:
+            hmm.sw_align([b"ACGT"], [b""], ORIGINAL_DEFAULT, O.SW_SOFTCLIP)       # SmithWatermanJavaAligner.java:64-66
+        assert e.value.code == native.ERR_INVALID_ARG
+        with pytest.raises(native.GpuPhmmError) as e:
+            hmm.sw_align([b"AAAGACTACTG"], [b"AACGGACACTG"], (50, -100, -220, -12), O.SW_SOFTCLIP, cigar_capacity=3)   # 2M2I3M1D4M needs 5
+        assert e.value.code == native.ERR_TOO_LARGE
+        assert hmm.sw_align([b"AAAGACTACTG"], [b"AACGGACACTG"], (50, -100, -220, -12), O.SW_SOFTCLIP, cigar_capacity=5) == [(1, "2M2I3M1D4M")]
+        assert hmm.sw_align([], [], ORIGINAL_DEFAULT, O.SW_SOFTCLIP) == []
