@@ -319,6 +319,58 @@ JNIEXPORT void JNICALL JNIFN(nativeComputePD)(JNIEnv *env, jclass, jlong handle,
     env->SetDoubleArrayRegion(out, 0, need, res.data());
 }
 
+// Smith-Waterman (include/gpuphmm.h gphmm_sw_align): pair k aligns alts[k] to refs[k].  params = {match, mismatch, gapOpen,
+// gapExtend, overhangStrategy ordinal as GPHMM_SW_*}.  offsets / nElems: one int per pair; elems: capacity ints per
+// pair, (length << 4) | op.  Returns false when some CIGAR needs more than `capacity` elements (nElems = -1 there).
+JNIEXPORT jboolean JNICALL JNIFN(nativeSwAlign)(JNIEnv *env, jclass, jlong handle, jobjectArray refs, jobjectArray alts, jintArray params,
+                                                jint capacity, jintArray offsets, jintArray nElems, jintArray elems) {
+    Session *s = reinterpret_cast<Session *>(handle);
+    const jsize n = env->GetArrayLength(refs);
+    if (env->GetArrayLength(alts) != n || env->GetArrayLength(params) < 5 || env->GetArrayLength(offsets) < n || env->GetArrayLength(nElems) < n ||
+        capacity < 1 || env->GetArrayLength(elems) < n * capacity) {
+        throw_java(env, "java/lang/IllegalArgumentException", "Smith-Waterman batch arrays have inconsistent sizes");
+        return JNI_FALSE;
+    }
+    std::vector<uint8_t> rb, ab;
+    std::vector<int64_t> ro(1, 0), ao(1, 0);
+    for (int side = 0; side < 2; ++side) {
+        std::vector<uint8_t> &bytes = side ? ab : rb;
+        std::vector<int64_t> &off = side ? ao : ro;
+        for (jsize k = 0; k < n; ++k) {
+            jbyteArray a = static_cast<jbyteArray>(env->GetObjectArrayElement(side ? alts : refs, k));
+            if (!a) {
+                throw_java(env, "java/lang/IllegalArgumentException", "Non-null, non-empty sequences are required for the Smith-Waterman calculation");
+                return JNI_FALSE;
+            }
+            const jsize len = env->GetArrayLength(a);
+            bytes.resize(bytes.size() + static_cast<size_t>(len));
+            if (len) env->GetByteArrayRegion(a, 0, len, reinterpret_cast<jbyte *>(bytes.data() + off.back()));
+            off.push_back(off.back() + len);
+            env->DeleteLocalRef(a);
+        }
+    }
+    jint p[5];
+    env->GetIntArrayRegion(params, 0, 5, p);
+    gphmm_sw_params prm;
+    prm.struct_size = static_cast<int32_t>(sizeof prm);
+    prm.match_value = p[0]; prm.mismatch_penalty = p[1]; prm.gap_open_penalty = p[2]; prm.gap_extend_penalty = p[3]; prm.overhang_strategy = p[4];
+    gphmm_sw_batch b;
+    b.ref_bases = rb.data(); b.ref_off = ro.data(); b.alt_bases = ab.data(); b.alt_off = ao.data(); b.n_pairs = n;
+    std::vector<int32_t> off_out(static_cast<size_t>(n) + 1), ne(static_cast<size_t>(n) + 1);
+    std::vector<uint32_t> el(static_cast<size_t>(n) * capacity + 1);
+    const int rc = gphmm_sw_align(s->h, &b, &prm, capacity, off_out.data(), ne.data(), el.data());
+    if (rc != GPHMM_OK && rc != GPHMM_ERR_TOO_LARGE) {
+        throw_for(env, s, rc);
+        return JNI_FALSE;
+    }
+    if (n) {
+        env->SetIntArrayRegion(offsets, 0, n, reinterpret_cast<const jint *>(off_out.data()));
+        env->SetIntArrayRegion(nElems, 0, n, reinterpret_cast<const jint *>(ne.data()));
+        env->SetIntArrayRegion(elems, 0, n * capacity, reinterpret_cast<const jint *>(el.data()));
+    }
+    return rc == GPHMM_OK ? JNI_TRUE : JNI_FALSE;
+}
+
 JNIEXPORT jlong JNICALL JNIFN(nativeSubmit)(JNIEnv *env, jclass, jlong handle, jobjectArray reads, jobjectArray haps) {
     Session *s = reinterpret_cast<Session *>(handle);
     gphmm_batch b;

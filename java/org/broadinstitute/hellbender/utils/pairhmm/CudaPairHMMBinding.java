@@ -121,6 +121,21 @@ public final class CudaPairHMMBinding implements PairHMMNativeBinding {
         nativeComputePD(handle, readDataArray, haplotypeDataArray, likelihoodArray);
     }
 
+    /**
+     * Batched Smith-Waterman (gphmm_sw_align): pair k aligns {@code alternates[k]} to {@code references[k]}.
+     * {@code params = {match, mismatch, gapOpen, gapExtend, strategy}} with strategy 0 SOFTCLIP, 1 INDEL, 2 LEADING_INDEL,
+     * 3 IGNORE; {@code elems[k * capacity + e] = (length << 4) | op} with op 0 M, 1 I, 2 D, 3 S.
+     *
+     * @return false when some CIGAR needs more than {@code capacity} elements ({@code nElems[k] == -1} for those pairs)
+     */
+    public boolean smithWatermanBatch(final byte[][] references, final byte[][] alternates, final int[] params, final int capacity,
+                                      final int[] offsets, final int[] nElems, final int[] elems) {
+        if (handle == 0L) {
+            throw new IllegalStateException("CudaPairHMMBinding.initialize() has not been called");
+        }
+        return nativeSwAlign(handle, references, alternates, params, capacity, offsets, nElems, elems);
+    }
+
     @Override
     public void done() {
         if (handle != 0L) {
@@ -145,6 +160,8 @@ public final class CudaPairHMMBinding implements PairHMMNativeBinding {
     private static native void nativeComputeRegion(long handle, ReadDataHolder[] reads, byte[] mapq, HaplotypeDataHolder[] haps,
                                                    int[] intParams, double[] doubleParams, double[] out, byte[] keep, byte[] hmmBaseQuals);
     private static native void nativeComputePD(long handle, ReadDataHolder[] reads, HaplotypeDataHolder[] haps, double[] out);
+    private static native boolean nativeSwAlign(long handle, byte[][] refs, byte[][] alts, int[] params, int capacity,
+                                                int[] offsets, int[] nElems, int[] elems);
     private static native long nativeSubmit(long handle, ReadDataHolder[] reads, HaplotypeDataHolder[] haps);
     private static native void nativeAwait(long handle, long ticket, double[] out);
     private static native void nativeDestroy(long handle);

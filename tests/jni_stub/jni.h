@@ -12,6 +12,8 @@ typedef int32_t jint;
 typedef int64_t jlong;
 typedef int8_t jbyte;
 typedef uint8_t jboolean;
+#define JNI_FALSE 0
+#define JNI_TRUE 1
 typedef double jdouble;
 typedef jint jsize;
 class _jobject {};
@@ -43,6 +45,7 @@ struct JNIEnv {
     void DeleteLocalRef(jobject);
     void GetByteArrayRegion(jbyteArray, jsize, jsize, jbyte *);
     void GetIntArrayRegion(jintArray, jsize, jsize, jint *);
+    void SetIntArrayRegion(jintArray, jsize, jsize, const jint *);
     void GetDoubleArrayRegion(jdoubleArray, jsize, jsize, jdouble *);
     void SetDoubleArrayRegion(jdoubleArray, jsize, jsize, const jdouble *);
     void SetByteArrayRegion(jbyteArray, jsize, jsize, const jbyte *);

@@ -97,7 +97,7 @@ def test_jni_shim_syntax_and_symbols():
     java = open(os.path.join(ROOT, "java/org/broadinstitute/hellbender/utils/pairhmm/CudaPairHMMBinding.java")).read()
     natives = set(re.findall(r"private static native [\w\[\]]+ (\w+)\(", java))
     exported = set(re.findall(r"JNIFN\((\w+)\)\(", open(src).read()))
-    assert natives == exported and len(natives) == 10
+    assert natives == exported and len(natives) == 11
 
 
 def test_java_plugin_sources_present():
