@@ -13,6 +13,7 @@ from gatk_b200.native import Batch, GpuPhmm
 from oracle import oracle
 from phmm_testutil import oracle_batch
 from test_pdhmm import _pd_oracle, random_pd
+from test_smith_waterman import _random_pairs
 
 budget = float(sys.argv[1]) if len(sys.argv) > 1 else 120.0
 seed0 = int(sys.argv[2]) if len(sys.argv) > 2 else 0
@@ -50,7 +51,7 @@ def check(got, want, what):
 
 
 t_end = time.time() + budget
-n_batches = n_pairs = n_pd = 0
+n_batches = n_pairs = n_pd = n_sw = 0
 worst = 0.0
 handles = {
     "default": GpuPhmm(),
@@ -113,11 +114,22 @@ try:
             for name in ("default", "fp64"):
                 worst = max(worst, check(handles[name].pd_compute(bp, pd), want_pd, "seed %d pd %s" % (seed, name)))
             n_pd += 1
+        if seed % 4 == 0:
+            # Smith-Waterman: offsets and CIGARs identical with the oracle
+            lens = [((1, 30), (1, 30)), ((50, 400), (10, 300)), ((200, 700), (150, 600))][int(rng.integers(0, 3))]
+            refs, alts = _random_pairs(seed, int(rng.integers(1, 40)), *lens)
+            params = [(3, -1, -4, -3), (25, -50, -110, -6), (200, -150, -260, -11), (10, -15, -30, -5),
+                      (int(rng.integers(1, 50)), -int(rng.integers(1, 60)), -int(rng.integers(1, 120)), -int(rng.integers(1, 20)))][int(rng.integers(0, 5))]
+            strategy = int(rng.integers(0, 4))
+            got_sw = handles["default"].sw_align(refs, alts, params, strategy, cigar_capacity=1400)
+            want_sw = [oracle.sw_align(r, a, params, strategy) for r, a in zip(refs, alts)]
+            assert got_sw == want_sw, "seed %d smith-waterman %s strategy %d" % (seed, params, strategy)
+            n_sw += len(refs)
         n_batches += 1
         n_pairs += b.n_out
         seed += 1
 finally:
     for h in handles.values():
         h.close()
-print("fuzz: %d batches (seeds %d..%d), %d pairs x 4 configurations + region steps, %d PD-HMM batches, worst |err| %.3g (bar %g): OK" % (
-    n_batches, seed0, seed - 1, n_pairs, n_pd, worst, TOL))
+print("fuzz: %d batches (seeds %d..%d), %d pairs x 4 configurations + region steps, %d PD-HMM batches, %d Smith-Waterman alignments (bit-exact), worst |err| %.3g (bar %g): OK" % (
+    n_batches, seed0, seed - 1, n_pairs, n_pd, n_sw, worst, TOL))
