@@ -143,3 +143,31 @@ def test_sw_errors_and_capacity():
         assert e.value.code == native.ERR_TOO_LARGE
         assert hmm.sw_align([b"AAAGACTACTG"], [b"AACGGACACTG"], (50, -100, -220, -12), O.SW_SOFTCLIP, cigar_capacity=5) == [(1, "2M2I3M1D4M")]
         assert hmm.sw_align([], [], ORIGINAL_DEFAULT, O.SW_SOFTCLIP) == []
+
+
+@pytest.mark.gpu
+def test_sw_plugin_surface_like_the_reference_unit_test():
+    # reads like SmithWatermanAlignerAbstractUnitTest.assertAlignmentMatchesExpected (:260-267) with getAligner() -> CUDA
+    from gatk_b200 import smithwaterman as sw
+    with sw.getAligner(sw.Implementation.CUDA) as aligner:
+        alignment = aligner.align(b"AAAGGACTGACTG", b"ACTGACTGACTG", sw.ORIGINAL_DEFAULT, sw.SWOverhangStrategy.SOFTCLIP)
+        assert alignment.getAlignmentOffset() == 1 and alignment.getCigar() == "12M"
+        # testIndelsAtStartAndEnd (:170-178)
+        alignment = aligner.align(b"AAACCCCC", b"CCCCCGGG", sw.ORIGINAL_DEFAULT, sw.SWOverhangStrategy.SOFTCLIP)
+        assert (alignment.getAlignmentOffset(), alignment.getCigar()) == (3, "5M3S")
+        # getSubstringMatchLong (:269-281), all four strategies in one batch per strategy
+        for strategy, want in ((sw.SWOverhangStrategy.SOFTCLIP, (359, "7M")), (sw.SWOverhangStrategy.INDEL, (0, "1M358D6M29D")),
+                               (sw.SWOverhangStrategy.LEADING_INDEL, (0, "1M1D6M")), (sw.SWOverhangStrategy.IGNORE, (359, "7M"))):
+            got = aligner.alignBatch([LONG_REF] * 3, [b"AAAAAAA"] * 3, sw.ORIGINAL_DEFAULT, strategy)
+            assert [(a.getAlignmentOffset(), a.getCigar()) for a in got] == [want] * 3
+        with pytest.raises(ValueError):
+            aligner.align(b"", b"ACGT", sw.ORIGINAL_DEFAULT, sw.SWOverhangStrategy.SOFTCLIP)
+        # a CIGAR with more than 32 elements: the mirror retries with a larger capacity
+        rng = np.random.default_rng(3)
+        ref = bytes(rng.choice(list(b"ACGT"), 900).astype(np.uint8))
+        alt = bytearray(ref)
+        for pos in range(880, 20, -20):
+            del alt[pos:pos + 3]
+        got = aligner.align(ref, bytes(alt), sw.NEW_SW_PARAMETERS, sw.SWOverhangStrategy.SOFTCLIP)
+        assert (got.getAlignmentOffset(), got.getCigar()) == O.sw_align(ref, bytes(alt), sw.NEW_SW_PARAMETERS.as_tuple(), O.SW_SOFTCLIP)
+        assert got.getCigar().count("D") > 32
