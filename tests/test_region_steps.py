@@ -339,3 +339,34 @@ def test_region_steps_with_forced_double_precision():
     want = _oracle_regions(b, mapq, ref)
     assert np.abs(c["lk"] - want["lk"]).max() < 1e-9 and np.array_equal(c["keep"], want["keep"])
     assert np.abs(a["lk"] - c["lk"]).max() < 1e-4
+
+
+@pytest.mark.gpu
+def test_region_pipeline_keeps_order_and_results():
+    # K regions in flight, finished strictly in order (HC/HaplotypeCaller.java:283-285), same numbers as one call per region
+    from gatk_b200.pipeline import RegionPipeline
+    regions = list(range(23))
+    data = {k: _raw_batch(300 + k, n_units=1) for k in regions}
+    fed, finished = [], []
+
+    def feed(k):
+        fed.append(k)
+        b, mapq = data[k]
+        return b, mapq, np.zeros(1, np.int32)
+
+    def drain(k, res):
+        finished.append((k, len(fed)))
+        return k, res
+
+    with GpuPhmm() as hmm:
+        out = list(RegionPipeline(hmm, lookahead=5).run(regions, feed, drain))
+        assert [k for k, _ in out] == regions
+        # region k was finished only after region k+4 had been fed (look-ahead), except at the end of the stream
+        assert all(n_fed >= min(k + 5, len(regions)) for k, n_fed in finished)
+        for k, res in out:
+            b, mapq = data[k]
+            want = hmm.compute_regions(b, mapq, np.zeros(1, np.int32))
+            assert np.array_equal(res["keep"], want["keep"]) and np.array_equal(res["base_q"], want["base_q"])
+            assert np.abs(res["lk"] - want["lk"]).max() < 1e-5
+        with pytest.raises(ValueError):
+            RegionPipeline(hmm, lookahead=0)
