@@ -11,7 +11,7 @@ def _stale():
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".cpp", ".h"))]
+    srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".inl", ".cpp", ".h"))]
     srcs.append(os.path.join(_HERE, "..", "include", "gpuphmm.h"))
     return any(os.path.getmtime(s) > t for s in srcs)
 

@@ -151,396 +151,7 @@ struct ChunkPlan {
     uint8_t sym_qc[MAX_SYM_CLASSES];
 };
 
-int ceil_log2(uint32_t v) {
-    int lg = 0;
-    while ((1u << lg) < v) ++lg;
-    return lg;
-}
-
-void validate_batch(const gphmm_batch *b) {
-    if (!b) throw Error(GPHMM_ERR_INVALID_ARG, "batch is null");
-    if (b->n_units < 0 || b->n_reads < 0 || b->n_haps < 0) throw Error(GPHMM_ERR_INVALID_ARG, "negative count");
-    if (b->n_units == 0) return;
-    if (!b->units || !b->read_off || !b->hap_off) throw Error(GPHMM_ERR_INVALID_ARG, "null offsets/units");
-    for (int64_t r = 0; r < b->n_reads; ++r)
-        if (b->read_off[r + 1] < b->read_off[r]) throw Error(GPHMM_ERR_INVALID_ARG, "read_off not monotone");
-    for (int64_t h = 0; h < b->n_haps; ++h)
-        if (b->hap_off[h + 1] <= b->hap_off[h])
-            throw Error(GPHMM_ERR_INVALID_ARG, "zero-length haplotype (PairHMM.initialize requires haplotypeMaxLength > 0)");
-    for (int64_t u = 0; u < b->n_units; ++u) {
-        const gphmm_unit &un = b->units[u];
-        if (un.read_begin < 0 || un.read_end < un.read_begin || un.read_end > b->n_reads || un.hap_begin < 0 ||
-            un.hap_end < un.hap_begin || un.hap_end > b->n_haps || un.out_off < 0)
-            throw Error(GPHMM_ERR_INVALID_ARG, "unit range out of bounds");
-        if (un.hap_end - un.hap_begin > 65535) throw Error(GPHMM_ERR_TOO_LARGE, "more than 65535 haplotypes in one unit");
-    }
-    if (b->n_reads > 0 && b->read_off[b->n_reads] > 0 &&
-        (!b->read_bases || !b->base_q || !b->ins_q || !b->del_q || !b->gcp))
-        throw Error(GPHMM_ERR_INVALID_ARG, "null read array");
-    if (b->n_haps > 0 && !b->hap_bases) throw Error(GPHMM_ERR_INVALID_ARG, "null hap_bases");
-}
-
-// Greedy split of the unit list into chunks bounded by cells and staged bytes.
-std::vector<std::pair<int64_t, int64_t>> split_units(const gphmm_batch *b, int64_t chunk_cells, int64_t chunk_bytes, bool ramp_up) {
-    std::vector<std::pair<int64_t, int64_t>> out;
-    int64_t u = 0;
-    const int64_t full_cells = chunk_cells;
-    while (u < b->n_units) {
-        // ramp up: the first chunks are small so that the GPU starts early while the host is still staging
-        const size_t ci = out.size();
-        // (2.5e8 cells = a handful of regions, then doubling: the planner threads stay ahead of the GPU from there on)
-        chunk_cells = (!ramp_up || ci >= 16) ? full_cells : std::min<int64_t>(full_cells, (int64_t)250000000 << ci);
-        int64_t cells = 0, bytes = 0, pairs = 0, u_end = u;
-        int64_t r_lo = INT64_MAX, r_hi = 0;
-        while (u_end < b->n_units) {
-            const gphmm_unit &un = b->units[u_end];
-            const int64_t nr = un.read_end - un.read_begin, nh = un.hap_end - un.hap_begin;
-            const int64_t rb = nr ? b->read_off[un.read_end] - b->read_off[un.read_begin] : 0;
-            const int64_t hb = nh ? b->hap_off[un.hap_end] - b->hap_off[un.hap_begin] : 0;
-            const int64_t n_lo = std::min(r_lo, nr ? un.read_begin : r_lo), n_hi = std::max(r_hi, nr ? un.read_end : r_hi);
-            const int64_t span = n_hi > n_lo ? b->read_off[n_hi] - b->read_off[n_lo] : 0;
-            const int64_t c = rb * hb;
-            if (u_end > u && (cells + c > chunk_cells || span * 5 + bytes + hb > chunk_bytes || pairs + nr * nh > (int64_t)1 << 25))
-                break;
-            cells += c; bytes += hb + nh; pairs += nr * nh;
-            r_lo = n_lo; r_hi = n_hi;
-            ++u_end;
-        }
-        const int64_t span = r_hi > r_lo ? b->read_off[r_hi] - b->read_off[r_lo] : 0;
-        if (span >= ((int64_t)1 << 31) || bytes >= ((int64_t)1 << 31) || pairs >= ((int64_t)1 << 28))
-            throw Error(GPHMM_ERR_TOO_LARGE, "a single unit exceeds the per-chunk device budget");
-        out.emplace_back(u, u_end);
-        u = u_end;
-    }
-    return out;
-}
-
-// Plans the shared (prefix-compressed) stream of one unit: haplotypes sorted lexicographically, pass i+1 resumes
-// from a snapshot taken at the last column it shares with its predecessors.  Appends to c.sstreams / pass_info /
-// segments and returns the unit's schedule.  With share == false every pass starts from column 1 in input order.
-// Lexicographic order of a unit's haplotypes (input order when sharing is off).
-std::vector<int> sorted_hap_order(const gphmm_batch *b, const gphmm_unit &un, bool share) {
-    const int n = (int)(un.hap_end - un.hap_begin);
-    auto hap_ptr = [&](int k) { return b->hap_bases + b->hap_off[un.hap_begin + k]; };
-    auto hap_len = [&](int k) { return (uint32_t)(b->hap_off[un.hap_begin + k + 1] - b->hap_off[un.hap_begin + k]); };
-    std::vector<int> order(n);
-    for (int k = 0; k < n; ++k) order[k] = k;
-    if (share)
-        std::sort(order.begin(), order.end(), [&](int x, int y) {
-            const uint32_t lx = hap_len(x), ly = hap_len(y);
-            const int cmp = memcmp(hap_ptr(x), hap_ptr(y), std::min(lx, ly));
-            if (cmp != 0) return cmp < 0;
-            if (lx != ly) return lx < ly;
-            return x < y;
-        });
-    return order;
-}
-
-UnitSched plan_unit_sharing(const gphmm_batch *b, const gphmm_unit &un, uint32_t hap_first_local, bool share, ChunkPlan &c,
-                            int64_t sum_read_len, const std::vector<int> &full_order, int g_first, int g_count) {
-    constexpr uint32_t SPACING = 32;
-    static const uint32_t MIN_DEPTH = getenv("GPHMM_MIN_DEPTH") ? (uint32_t)std::max(32, atoi(getenv("GPHMM_MIN_DEPTH"))) : 32u;  // tuning knob
-    UnitSched us;
-    memset(&us, 0, sizeof us);
-    const int n = g_count;  // haplotypes of this group: full_order[g_first .. g_first + g_count)
-    us.pass_first = (uint32_t)c.pass_info.size();
-    us.n_passes = (uint32_t)n;
-    us.seg_first = (uint32_t)c.segments.size();
-    c.sstreams.insert(c.sstreams.end(), STREAM_PAD, (uint8_t)CODE_NULL);
-    us.sstream_off = (uint32_t)c.sstreams.size();
-    if (n == 0) return us;
-    auto hap_ptr = [&](int k) { return b->hap_bases + b->hap_off[un.hap_begin + k]; };
-    auto hap_len = [&](int k) { return (uint32_t)(b->hap_off[un.hap_begin + k + 1] - b->hap_off[un.hap_begin + k]); };
-    std::vector<int> order(full_order.begin() + g_first, full_order.begin() + g_first + g_count);
-    struct Snap { int pass; uint32_t depth, pos; int slot; uint32_t free_after; };
-    std::vector<Snap> snaps;
-    int slot_owner[MAX_SNAP_SLOTS];
-    for (int k = 0; k < MAX_SNAP_SLOTS; ++k) slot_owner[k] = -1;
-    std::vector<uint32_t> r(n, 0), pass_start(n + 1, 1), end_pos(n, 0);
-    std::vector<int> snap_of_pass(n, -1);
-    std::vector<uint32_t> lcp(n, 0), n_pad(n, 0);
-    for (int i = 0; i < n; ++i) {
-        const uint32_t H = hap_len(order[i]);
-        // every pass spans at least 32 stream positions (NULL columns before its END if it is shorter), so that the
-        // 32-step END windows of consecutive passes never overlap
-        n_pad[i] = (H - r[i]) < 32u ? 32u - (H - r[i]) : 0u;
-        end_pos[i] = pass_start[i] + (H - r[i]) + n_pad[i];
-        pass_start[i + 1] = end_pos[i] + 1;
-        if (i + 1 >= n || !share) continue;
-        // longest common prefix with the next haplotype in sorted order
-        const uint8_t *x = hap_ptr(order[i]), *y = hap_ptr(order[i + 1]);
-        const uint32_t m = std::min(H, hap_len(order[i + 1]));
-        uint32_t d = 0;
-        while (d < m && x[d] == y[d]) ++d;
-        lcp[i] = d;
-        if (d < MIN_DEPTH) continue;
-        int k = -1;
-        {
-            // preferred: a snapshot at exactly the shared depth, taken by the latest pass that computed column d
-            int j = i;
-            while (r[j] >= d) --j;  // r[0] = 0 < d
-            const uint32_t pos = pass_start[j] + (d - r[j]) - 1;
-            for (size_t q = 0; q < snaps.size(); ++q)
-                if (snaps[q].pass == j && snaps[q].depth == d && slot_owner[snaps[q].slot] == (int)q) k = (int)q;
-            if (k < 0) {
-                bool ok = true;
-                for (const Snap &sn : snaps) ok = ok && (sn.pos + SPACING <= pos || pos + SPACING <= sn.pos);
-                int slot = -1;
-                for (int q = 0; q < MAX_SNAP_SLOTS && ok && slot < 0; ++q)
-                    if (slot_owner[q] < 0 || snaps[slot_owner[q]].free_after < pos) slot = q;
-                if (ok && slot >= 0) {
-                    snaps.push_back({j, d, pos, slot, 0});
-                    k = (int)snaps.size() - 1;
-                    slot_owner[slot] = k;
-                }
-            }
-        }
-        if (k < 0) {
-            // fallback: the deepest live snapshot whose prefix the next haplotype still shares
-            uint32_t best = 0;
-            for (size_t q = 0; q < snaps.size(); ++q) {
-                if (slot_owner[snaps[q].slot] != (int)q || snaps[q].depth < MIN_DEPTH || snaps[q].depth <= best) continue;
-                uint32_t shared_len = UINT32_MAX;  // LCP(haplotype of snaps[q].pass, haplotype i+1) = min lcp[pass..i]
-                for (int t = snaps[q].pass; t <= i; ++t) shared_len = std::min(shared_len, lcp[t]);
-                if (shared_len >= snaps[q].depth) { best = snaps[q].depth; k = (int)q; }
-            }
-            if (k < 0) continue;
-        }
-        snaps[k].free_after = end_pos[i];  // restored at the END column of pass i
-        r[i + 1] = snaps[k].depth;
-        snap_of_pass[i + 1] = k;
-    }
-    // stream + pass table
-    for (int i = 0; i < n; ++i) {
-        const uint32_t H = hap_len(order[i]);
-        const size_t w = c.sstreams.size();
-        c.sstreams.resize(w + (H - r[i]) + n_pad[i] + 1);
-        uint8_t *dst = c.sstreams.data() + w;
-        // the full stream of this unit was encoded a moment ago: copy the columns behind the shared prefix
-        memcpy(dst, c.streams.data() + c.hap_stream_off[hap_first_local + order[i]] + r[i], H - r[i]);
-        for (uint32_t q = 0; q < n_pad[i]; ++q) dst[H - r[i] + q] = (uint8_t)CODE_NULL;  // prior 0: no effect on the sum
-        dst[H - r[i] + n_pad[i]] = (uint8_t)CODE_END;
-        PassInfo pi;
-        pi.out_idx = (uint16_t)order[i];
-        pi.restore_slot = (int16_t)(snap_of_pass[i] >= 0 ? snaps[snap_of_pass[i]].slot : -1);
-        c.pass_info.push_back(pi);
-        c.skipped_cells += (int64_t)r[i] * sum_read_len;
-        c.computed_columns += H - r[i];
-    }
-    // schedule.  Lane l meets stream position q at step q + l, so an END column at e keeps some lane busy with it
-    // during steps [e, e+32) and a snapshot position s during [s, s+32).  END windows never overlap each other
-    // (passes span >= 32 positions), snapshot windows never overlap each other (SPACING), so at any step at most one
-    // of each is active.  A segment = branch-free steps, then checked steps with one constant (END, snapshot) pair.
-    std::vector<uint32_t> pts;
-    pts.push_back(1);
-    for (int i = 0; i < n; ++i) { pts.push_back(end_pos[i]); pts.push_back(end_pos[i] + 32); }
-    for (const Snap &sn : snaps) { pts.push_back(sn.pos); pts.push_back(sn.pos + 32); }
-    std::sort(pts.begin(), pts.end());
-    pts.erase(std::unique(pts.begin(), pts.end()), pts.end());
-    std::vector<int> snap_by_pos(snaps.size());
-    for (size_t q = 0; q < snaps.size(); ++q) snap_by_pos[q] = (int)q;
-    std::sort(snap_by_pos.begin(), snap_by_pos.end(), [&](int x, int y) { return snaps[x].pos < snaps[y].pos; });
-    Segment seg;
-    auto clear_seg = [&]() { seg.n_free = 0; seg.n_chk = 0; seg.snap_pos = INT32_MIN; seg.snap_slot = 0; seg.end_restore = MAX_SNAP_SLOTS; seg.end_out = 0; };
-    clear_seg();
-    size_t ie = 0, is = 0;  // first END / snapshot whose window has not expired yet
-    for (size_t k = 0; k + 1 < pts.size(); ++k) {
-        const uint32_t x = pts[k], y = pts[k + 1];
-        while (ie < (size_t)n && end_pos[ie] + 32 <= x) ++ie;
-        while (is < snaps.size() && snaps[snap_by_pos[is]].pos + 32 <= x) ++is;
-        const bool end_on = ie < (size_t)n && end_pos[ie] <= x;
-        const bool snap_on = is < snaps.size() && snaps[snap_by_pos[is]].pos <= x;
-        static const bool all_checked = getenv("GPHMM_ALL_CHECKED") != nullptr;  // experiment: cost of the checked loop
-        if (!end_on && !snap_on && !all_checked) {
-            if (seg.n_chk) { c.segments.push_back(seg); clear_seg(); }
-            seg.n_free += y - x;
-            continue;
-        }
-        if (seg.n_chk) { c.segments.push_back(seg); clear_seg(); }
-        seg.n_chk = y - x;
-        if (snap_on) { seg.snap_pos = (int32_t)snaps[snap_by_pos[is]].pos; seg.snap_slot = (uint8_t)snaps[snap_by_pos[is]].slot; }
-        if (end_on) {
-            seg.end_out = (uint16_t)order[ie];
-            seg.end_restore = (int8_t)(ie + 1 < (size_t)n && snap_of_pass[ie + 1] >= 0 ? snaps[snap_of_pass[ie + 1]].slot : MAX_SNAP_SLOTS);  // MAX_SNAP_SLOTS = pass-start state
-        }
-    }
-    if (seg.n_free || seg.n_chk) c.segments.push_back(seg);
-    us.n_segs = (uint32_t)c.segments.size() - us.seg_first;
-    return us;
-}
-
-// When a chunk has too few reads to fill the GPU with one warp per read (a single HaplotypeCaller region is ~100 reads),
-// each unit's haplotypes are split into groups and every (read, group) pair becomes a task of its own.
-constexpr int64_t TARGET_TASKS = 148 * 28 * 2;
-
-void plan_chunk(const gphmm_batch *b, int64_t u0, int64_t u1, bool force_fp64, bool share, ChunkPlan &c, bool pcr_hint = false) {
-    c.u0 = u0; c.u1 = u1;
-    c.r_lo = INT64_MAX; c.r_hi = 0;
-    for (int64_t u = u0; u < u1; ++u) {
-        const gphmm_unit &un = b->units[u];
-        if (un.read_end > un.read_begin) { c.r_lo = std::min(c.r_lo, un.read_begin); c.r_hi = std::max(c.r_hi, un.read_end); }
-    }
-    if (c.r_hi <= c.r_lo) { c.r_lo = c.r_hi = 0; }
-    c.base_lo = b->n_reads ? b->read_off[c.r_lo] : 0;
-    c.base_hi = b->n_reads ? b->read_off[c.r_hi] : 0;
-    const int64_t n_span = c.r_hi - c.r_lo;
-    c.read_off.resize(n_span + 1);
-    for (int64_t r = 0; r <= n_span; ++r) c.read_off[r] = (uint32_t)(b->read_off[c.r_lo + r] - c.base_lo);
-
-    // quality classes from a sample of the chunk's reads: flat (one (ins, del, gcp) triple on every base) and
-    // symmetric (ins == del per base, flat gcp).  The device decides per read which class it really belongs to
-    // (phmm_classify_kernel); a class that is missed here only means those reads take the general kernel.
-    c.n_classes = 0;
-    c.n_sym = 0;
-    if (!force_fp64 && n_span > 0) {
-        const int64_t stride = std::max<int64_t>(1, n_span / 256);
-        for (int64_t r = 0; r < n_span; r += stride) {
-            const int64_t o = b->read_off[c.r_lo + r], e = b->read_off[c.r_lo + r + 1];
-            if (e == o) continue;
-            const uint8_t qi = b->ins_q[o], qd = b->del_q[o], qc = b->gcp[o];
-            if (qi > 127 || qd > 127 || qc > 127) continue;
-            // an array is constant iff it equals itself shifted by one (memcmp is vectorised)
-            const size_t n1 = (size_t)(e - o - 1);
-            const bool flat_c = memcmp(b->gcp + o, b->gcp + o + 1, n1) == 0;
-            const bool flat = flat_c && memcmp(b->ins_q + o, b->ins_q + o + 1, n1) == 0 && memcmp(b->del_q + o, b->del_q + o + 1, n1) == 0;
-            bool sym = flat_c && memcmp(b->ins_q + o, b->del_q + o, n1 + 1) == 0;
-            if (sym && !flat) {
-                uint8_t mx = 0;
-                for (int64_t i = o; i < e; ++i) mx = std::max(mx, b->ins_q[i]);
-                sym = mx <= SYM_MAX_GAP_QUAL;
-            } else if (sym) {
-                sym = qi <= SYM_MAX_GAP_QUAL;
-            }
-            if (flat && !(pcr_hint && qi == qd)) {  // the PCR indel model (region steps) will lower ins and del together
-                bool seen = false;
-                for (int k = 0; k < c.n_classes; ++k) seen = seen || (c.class_qi[k] == qi && c.class_qd[k] == qd && c.class_qc[k] == qc);
-                if (seen) continue;
-                if (c.n_classes < MAX_FLAT_CLASSES) {
-                    c.class_qi[c.n_classes] = qi; c.class_qd[c.n_classes] = qd; c.class_qc[c.n_classes] = qc; ++c.n_classes;
-                    continue;
-                }
-            }
-            if (sym) {  // includes flat reads that found no free flat class
-                bool seen = false;
-                for (int k = 0; k < c.n_sym; ++k) seen = seen || c.sym_qc[k] == qc;
-                if (!seen && c.n_sym < MAX_SYM_CLASSES) c.sym_qc[c.n_sym++] = qc;
-            }
-        }
-    }
-
-    // haplotype alphabet of the chunk: A C G T N are fixed codes, any other byte value gets the next free code
-    int16_t lut[256];
-    for (int i = 0; i < 256; ++i) lut[i] = -1;
-    memset(c.code_byte, 0, sizeof c.code_byte);
-    const char fixed[5] = {'A', 'C', 'G', 'T', 'N'};
-    for (int i = 0; i < 5; ++i) { lut[(uint8_t)fixed[i]] = (int16_t)(CODE_FIRST_BASE + i); c.code_byte[CODE_FIRST_BASE + i] = (uint8_t)fixed[i]; }
-    c.n_codes = CODE_FIRST_BASE + 5;
-
-    c.streams.clear(); c.hap_len.clear(); c.hap_stream_off.clear(); c.units.clear(); c.tasks.clear();
-    c.sstreams.clear(); c.pass_info.clear(); c.segments.clear(); c.unit_sched.clear(); c.skipped_cells = 0; c.computed_columns = 0; c.n_keep = 0;
-    c.n_pairs = 0; c.cells = 0; c.max_stream_len = 0; c.max_hap_len = 0;
-    int64_t n_reads_with_work = 0;
-    for (int64_t u = u0; u < u1; ++u)
-        if (b->units[u].hap_end > b->units[u].hap_begin) n_reads_with_work += b->units[u].read_end - b->units[u].read_begin;
-    const int64_t want_groups = n_reads_with_work > 0 ? (TARGET_TASKS + n_reads_with_work - 1) / n_reads_with_work : 1;
-    std::vector<Task> raw;
-    std::vector<uint8_t> bucket_of;
-    raw.reserve((size_t)(c.r_hi - c.r_lo));
-    bucket_of.reserve((size_t)(c.r_hi - c.r_lo));
-    c.streams.reserve((size_t)(u1 - u0) * 64);
-    uint32_t bucket_count[N_FP32_BUCKETS] = {0};
-    for (int64_t u = u0; u < u1; ++u) {
-        const gphmm_unit &un = b->units[u];
-        const uint32_t nr = (uint32_t)(un.read_end - un.read_begin), nh = (uint32_t)(un.hap_end - un.hap_begin);
-        UnitDesc d;
-        d.read_first = nr ? (uint32_t)(un.read_begin - c.r_lo) : 0;
-        d.n_reads = nr;
-        d.hap_first = (uint32_t)c.hap_len.size();
-        d.n_haps = nh;
-        d.out_base = c.n_pairs;
-        d.ref_hap = -1;
-        d.keep_base = c.n_keep;
-        c.n_keep += nr;
-        c.streams.insert(c.streams.end(), STREAM_PAD, (uint8_t)CODE_NULL);  // fill/drain codes of the fast kernels
-        const uint32_t stream_off = (uint32_t)c.streams.size();
-        uint32_t max_h = 1;
-        int64_t sum_h = 0;
-        {
-            const int64_t hap_bytes = nh ? b->hap_off[un.hap_end] - b->hap_off[un.hap_begin] : 0;
-            size_t w = c.streams.size();
-            c.streams.resize(w + (size_t)hap_bytes + nh);
-            uint8_t *dst = c.streams.data();
-            for (int64_t h = un.hap_begin; h < un.hap_end; ++h) {
-                const int64_t ho = b->hap_off[h];
-                const uint32_t H = (uint32_t)(b->hap_off[h + 1] - ho);
-                c.hap_len.push_back(H);
-                c.hap_stream_off.push_back((uint32_t)w);
-                const uint8_t *src = b->hap_bases + ho;
-                for (uint32_t j = 0; j < H; ++j) {
-                    int16_t code = lut[src[j]];
-                    if (code < 0) {
-                        if (c.n_codes >= MAX_CODES) throw Error(GPHMM_ERR_ALPHABET, "too many distinct haplotype byte values");
-                        code = lut[src[j]] = (int16_t)c.n_codes;
-                        c.code_byte[c.n_codes++] = src[j];
-                    }
-                    dst[w + j] = (uint8_t)code;
-                }
-                w += H;
-                dst[w++] = (uint8_t)CODE_END;
-                max_h = std::max(max_h, H);
-                sum_h += H;
-            }
-        }
-        const uint32_t stream_len = (uint32_t)c.streams.size() - stream_off;
-        c.max_stream_len = std::max(c.max_stream_len, stream_len);
-        c.max_hap_len = std::max(c.max_hap_len, max_h);
-        d.c0_exp = (force_fp64 ? C0_BASE_EXP_F64 : C0_BASE_EXP_F32) - ceil_log2(max_h);
-        c.units.push_back(d);
-        // reads of 255+ bases run the striped kernel on the full stream: only shorter reads use the shared streams
-        int64_t fast_read_len = 0;
-        for (uint32_t r = 0; r < nr && nh; ++r) {
-            const uint32_t R = c.read_off[d.read_first + r + 1] - c.read_off[d.read_first + r];
-            if ((R + 1) / 32 + 1 <= 8) fast_read_len += R;
-        }
-        const int n_groups = force_fp64 ? 1 : (int)std::max<int64_t>(1, std::min<int64_t>(want_groups, nh));
-        const uint32_t sched_first = (uint32_t)c.unit_sched.size();
-        {
-            const std::vector<int> order = sorted_hap_order(b, un, share && !force_fp64);
-            for (int gi = 0; gi < n_groups; ++gi) {
-                const int g0 = (int)((int64_t)nh * gi / n_groups), g1 = (int)((int64_t)nh * (gi + 1) / n_groups);
-                c.unit_sched.push_back(plan_unit_sharing(b, un, d.hap_first, share && !force_fp64, c, fast_read_len, order, g0, g1 - g0));
-            }
-        }
-        if (nh == 0) continue;
-        for (uint32_t r = 0; r < nr; ++r) {
-            const uint32_t rl = d.read_first + r;
-            const uint32_t R = c.read_off[rl + 1] - c.read_off[rl];
-            Task t;
-            t.read = rl; t.stream_off = stream_off; t.stream_len = stream_len;
-            t.out_base = d.out_base + r * nh; t.c0_exp = d.c0_exp; t.n_haps = nh; t.hap_first = d.hap_first; t.unit = sched_first;
-            // fast kernels need two spare rows below the read (accumulator row + row-0 carrier): R + 2 <= 32 K
-            const uint32_t k = (R + 1) / 32 + 1;
-            const uint8_t bucket = force_fp64 ? 0 : (k <= 8 ? (uint8_t)(k - 1) : (uint8_t)8);
-            // one task per haplotype group for the fast kernels; the striped / fp64 kernels sweep the full stream once
-            const int n_t = bucket < 8 && !force_fp64 ? n_groups : 1;
-            for (int gi = 0; gi < n_t; ++gi) {
-                t.unit = sched_first + (uint32_t)gi;
-                raw.push_back(t);
-                bucket_of.push_back(bucket);
-                ++bucket_count[bucket];
-            }
-            c.cells += (int64_t)R * sum_h;
-        }
-        c.n_pairs += nr * nh;
-    }
-    // counting sort by bucket (stable: unit order is kept inside a bucket)
-    c.bucket_begin[0] = 0;
-    for (int k = 0; k < N_FP32_BUCKETS; ++k) c.bucket_begin[k + 1] = c.bucket_begin[k] + bucket_count[k];
-    c.tasks.resize(raw.size());
-    uint32_t cursor[N_FP32_BUCKETS];
-    for (int k = 0; k < N_FP32_BUCKETS; ++k) cursor[k] = c.bucket_begin[k];
-    for (size_t i = 0; i < raw.size(); ++i) c.tasks[cursor[bucket_of[i]]++] = raw[i];
-}
+#include "host_planner.inl"
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
@@ -1533,428 +1144,11 @@ int run_batch(gphmm *h, const gphmm_batch *b, double *out, const gphmm_region_st
     return GPHMM_OK;
 }
 
-// The asynchronous cross-region batching queue: every arena (= everything submitted with equal parameters while the
-// worker was busy) is ONE batch, so that many small (region, sample) units fill the GPU together.
-void worker_main(gphmm *h) {
-    static const bool trace = getenv("GPHMM_TRACE") != nullptr;
-    std::vector<double> merged_out, m_raw;
-    std::vector<uint8_t> m_keep, m_hq, m_hi, m_hd;
-    for (;;) {
-        std::unique_ptr<gphmm::Arena> ar;
-        {
-            std::unique_lock<std::mutex> lk(h->q_mu);
-            h->q_cv.wait(lk, [&] { return h->stop || !h->pending.empty(); });
-            if (h->pending.empty()) return;
-            ar = std::move(h->pending.front());
-            h->pending.pop_front();
-        }
-        const double t_wake = now_ms();
-        const size_t nj = ar->jobs.size();
-        gphmm_batch b;
-        memset(&b, 0, sizeof b);
-        b.read_bases = ar->rb.p; b.base_q = ar->bq.p; b.ins_q = ar->iq.p; b.del_q = ar->dq.p; b.gcp = ar->gq.p;
-        b.read_off = ar->ro.data(); b.n_reads = (int64_t)ar->ro.size() - 1;
-        b.hap_bases = ar->hb.p; b.hap_off = ar->ho.data(); b.n_haps = (int64_t)ar->ho.size() - 1;
-        b.units = ar->units.data(); b.n_units = (int64_t)ar->units.size();
-        const bool direct = nj == 1;  // a single job writes straight into the caller's arrays
-        double *out = direct ? ar->jobs[0].out : nullptr;
-        gphmm_region_steps rs = ar->rs;
-        if (!direct) {
-            merged_out.resize((size_t)ar->out_len + 1);
-            out = merged_out.data();
-        }
-        if (ar->has_rs) {
-            ar->mapq.push_back(0); ar->ref_hap.push_back(-1);  // never empty: data() is a valid pointer
-            rs.mapq = ar->mapq.data();
-            rs.ref_hap = ar->ref_hap.data();
-            if (direct) {
-                rs.keep = ar->jobs[0].rs.keep; rs.hmm_base_q = ar->jobs[0].rs.hmm_base_q;
-                rs.hmm_ins_q = ar->jobs[0].rs.hmm_ins_q; rs.hmm_del_q = ar->jobs[0].rs.hmm_del_q;
-                rs.raw_lk = ar->jobs[0].rs.raw_lk;
-            } else {
-                bool want_keep = false, want_q = false, want_i = false, want_d = false, want_raw = false;
-                for (const auto &j : ar->jobs) {
-                    want_raw = want_raw || j.rs.raw_lk;
-                    want_keep = want_keep || j.rs.keep; want_q = want_q || j.rs.hmm_base_q;
-                    want_i = want_i || j.rs.hmm_ins_q; want_d = want_d || j.rs.hmm_del_q;
-                }
-                if (want_keep) m_keep.resize((size_t)b.n_reads + 1);
-                if (want_q) m_hq.resize(ar->rb.size + 1);
-                if (want_i) m_hi.resize(ar->rb.size + 1);
-                if (want_d) m_hd.resize(ar->rb.size + 1);
-                rs.keep = want_keep ? m_keep.data() : nullptr;
-                rs.hmm_base_q = want_q ? m_hq.data() : nullptr;
-                rs.hmm_ins_q = want_i ? m_hi.data() : nullptr;
-                rs.hmm_del_q = want_d ? m_hd.data() : nullptr;
-                if (want_raw) m_raw.resize((size_t)ar->out_len + 1);
-                rs.raw_lk = want_raw ? m_raw.data() : nullptr;
-            }
-        }
-        auto run = [&](const gphmm_batch &bb, const gphmm_region_steps &rr, std::string &err) -> int {
-            try {
-                return run_batch(h, &bb, out, ar->has_rs ? &rr : nullptr);
-            } catch (const Error &e) {
-                err = e.what();
-                return e.code;
-            } catch (const std::exception &e) {
-                err = e.what();
-                return GPHMM_ERR_CUDA;
-            }
-        };
-        std::string err;
-        const int rc = nj ? run(b, rs, err) : GPHMM_OK;
-        std::vector<int> rcs(nj, rc);
-        std::vector<std::string> errs(nj, err);
-        if (!direct && rc != GPHMM_OK) {
-            // something in the merged batch is bad (e.g. a quality out of range): rerun the jobs one by one (each is a
-            // sub-range of the arena's units) so that only the offending ticket reports the error
-            for (size_t q = 0; q < nj; ++q) {
-                const gphmm::JobRef &j = ar->jobs[q];
-                gphmm_batch one = b;
-                one.units = ar->units.data() + j.unit0;
-                one.n_units = j.n_units;
-                gphmm_region_steps one_rs = rs;
-                one_rs.ref_hap = ar->ref_hap.data() + j.unit0;
-                errs[q].clear();
-                rcs[q] = run(one, one_rs, errs[q]);
-            }
-        }
-        if (!direct)
-            for (size_t q = 0; q < nj; ++q) {
-                const gphmm::JobRef &j = ar->jobs[q];
-                if (rcs[q] != GPHMM_OK) continue;
-                if (j.out_len) memcpy(j.out, merged_out.data() + j.out_base, (size_t)j.out_len * sizeof(double));
-                if (!ar->has_rs) continue;
-                if (j.rs.raw_lk && j.out_len) memcpy(j.rs.raw_lk, m_raw.data() + j.out_base, (size_t)j.out_len * sizeof(double));
-                if (j.rs.keep && j.n_reads) memcpy(j.rs.keep, m_keep.data() + j.read0, (size_t)j.n_reads);
-                if (j.rs.hmm_base_q && j.n_bases) memcpy(j.rs.hmm_base_q, m_hq.data() + j.base0, (size_t)j.n_bases);
-                if (j.rs.hmm_ins_q && j.n_bases) memcpy(j.rs.hmm_ins_q, m_hi.data() + j.base0, (size_t)j.n_bases);
-                if (j.rs.hmm_del_q && j.n_bases) memcpy(j.rs.hmm_del_q, m_hd.data() + j.base0, (size_t)j.n_bases);
-            }
-        if (trace) fprintf(stderr, "[gpuphmm] queue: batch of %zu jobs took %.3f ms\n", nj, now_ms() - t_wake);
-        {
-            std::lock_guard<std::mutex> lk(h->q_mu);
-            for (size_t q = 0; q < nj; ++q) {
-                h->finished.push_back({ar->jobs[q].ticket, rcs[q], errs[q]});
-                h->completed_upto = ar->jobs[q].ticket;
-            }
-            ar->clear();
-            h->free_arenas.push_back(std::move(ar));
-        }
-        h->done_cv.notify_all();
-    }
-}
+#include "host_queue.inl"
 
-// ---- PD-HMM (LoglessPDPairHMM, DRAGEN-GATK mode) ---------------------------------------------------------------------
-// Column flags of one partially determined haplotype: alternative-base mask, DEL_END, the state in which row 1
-// processes the column, plus how rows >= 2 start (LoglessPDPairHMM.java:59 keeps the state across rows).
-void encode_pd_columns(const uint8_t *pd, uint32_t H, uint8_t *flags, uint32_t &first_event, uint32_t &carry) {
-    enum { SNP = 1, DEL_START = 2, DEL_END = 4 };  // PartiallyDeterminedHaplotype.java:59-61; A, C, G, T = 8, 16, 32, 64
-    uint32_t state = PD_NORMAL;
-    first_event = H + 1;
-    for (uint32_t j = 1; j <= H; ++j) {
-        const uint8_t f = pd[j - 1];
-        uint8_t v = (uint8_t)(state << PD_TYPE_SHIFT);
-        if (f & SNP) v |= (uint8_t)(PD_SNP_BIT | ((f >> 3) & PD_MASK_BITS));
-        if (f & DEL_END) v |= (uint8_t)PD_DEL_END_BIT;
-        flags[j - 1] = v;
-        if (state == PD_AFTER_DEL) state = PD_NORMAL;
-        if (f & DEL_START) state = PD_INSIDE_DEL;
-        if (f & DEL_END) state = PD_AFTER_DEL;
-        if ((f & (DEL_START | DEL_END)) && first_event == H + 1) first_event = j;
-    }
-    carry = state;
-}
+#include "host_pdhmm.inl"
 
-template <typename T, int K> KernelInfo pd_kernel_info() {
-    KernelInfo ki;
-    auto fn = phmm_pd_kernel<T, K>;
-    ki.fn = (const void *)fn;
-    ki.smem = 0;
-    int occ = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, 32, 0));
-    ki.ctas_per_sm = std::max(1, occ);
-    return ki;
-}
-
-int run_pd_batch(gphmm *h, const gphmm_batch *b, const uint8_t *hap_pd, double *out) {
-    std::lock_guard<std::mutex> run_lk(h->run_mu);
-    const double t0 = now_ms();
-    validate_batch(b);
-    if (b->n_units == 0) return GPHMM_OK;
-    if (!out) throw Error(GPHMM_ERR_INVALID_ARG, "out is null");
-    if (!hap_pd) throw Error(GPHMM_ERR_INVALID_ARG, "hap_pd_bases is null");
-    Device &dev = *h->devices[0];
-    CK(cudaSetDevice(dev.ordinal));
-    cudaStream_t st = dev.streams[0];
-    // reads of 128+ bases: 4 rows per lane in strips of 128 rows keeps 18 warps per SM resident (113 registers) where the
-    // 8-row variant (181 registers) keeps 11; GPHMM_PD_K8=1 selects the latter for comparison
-    static const bool k8 = getenv("GPHMM_PD_K8") != nullptr;
-    static const KernelInfo kf[3] = {pd_kernel_info<float, 2>(), pd_kernel_info<float, 4>(), k8 ? pd_kernel_info<float, 8>() : pd_kernel_info<float, 4>()};
-    static const KernelInfo kd = pd_kernel_info<double, 4>();
-    const auto chunks = split_units(b, h->chunk_cells() / 4, h->chunk_bytes(), false);
-    int64_t launches = 0, total_pairs = 0, total_cells = 0, total_redo = 0, h2d = 0, d2h = 0;
-    double device_ms = 0;
-    std::vector<uint32_t> read_off;
-    std::vector<uint8_t> hap_bytes, hap_flags;
-    std::vector<PdTask> tasks[3], all;
-    std::vector<uint32_t> unit_out_base;
-    for (const auto &ch : chunks) {
-        int64_t r_lo = INT64_MAX, r_hi = 0;
-        for (int64_t u = ch.first; u < ch.second; ++u) {
-            const gphmm_unit &un = b->units[u];
-            if (un.read_end > un.read_begin) { r_lo = std::min(r_lo, un.read_begin); r_hi = std::max(r_hi, un.read_end); }
-        }
-        if (r_hi <= r_lo) r_lo = r_hi = 0;
-        const int64_t base_lo = b->n_reads ? b->read_off[r_lo] : 0, base_hi = b->n_reads ? b->read_off[r_hi] : 0;
-        const size_t span = (size_t)(base_hi - base_lo), stride = align_up(span, 16);
-        read_off.resize((size_t)(r_hi - r_lo) + 1);
-        for (int64_t r = 0; r <= r_hi - r_lo; ++r) read_off[r] = (uint32_t)(b->read_off[r_lo + r] - base_lo);
-        hap_bytes.clear(); hap_flags.clear(); unit_out_base.clear();
-        for (auto &v : tasks) v.clear();
-        uint32_t n_pairs = 0, max_h = 1;
-        int64_t cells = 0;
-        for (int64_t u = ch.first; u < ch.second; ++u) {
-            const gphmm_unit &un = b->units[u];
-            const uint32_t nr = (uint32_t)(un.read_end - un.read_begin), nh = (uint32_t)(un.hap_end - un.hap_begin);
-            unit_out_base.push_back(n_pairs);
-            struct HapInfo { uint32_t off, H, first_event, carry; };
-            std::vector<HapInfo> hi(nh);
-            for (uint32_t k = 0; k < nh; ++k) {
-                const int64_t ho = b->hap_off[un.hap_begin + k];
-                const uint32_t H = (uint32_t)(b->hap_off[un.hap_begin + k + 1] - ho);
-                hi[k].off = (uint32_t)hap_bytes.size(); hi[k].H = H;
-                hap_bytes.insert(hap_bytes.end(), b->hap_bases + ho, b->hap_bases + ho + H);
-                hap_flags.resize(hap_bytes.size());
-                encode_pd_columns(hap_pd + ho, H, hap_flags.data() + hi[k].off, hi[k].first_event, hi[k].carry);
-                max_h = std::max(max_h, H);
-            }
-            for (uint32_t r = 0; r < nr; ++r) {
-                const uint32_t rl = (uint32_t)(un.read_begin - r_lo) + r, R = read_off[rl + 1] - read_off[rl];
-                const int bucket = R <= 63 ? 0 : (R <= 127 ? 1 : 2);
-                for (uint32_t k = 0; k < nh; ++k) {
-                    PdTask t;
-                    t.read = rl; t.hap_off = hi[k].off; t.H = hi[k].H; t.out_slot = n_pairs + r * nh + k;
-                    t.first_event = hi[k].first_event; t.carry = hi[k].carry;
-                    t.c0_exp = 125 - ceil_log2(hi[k].H); t.pad = 0;
-                    tasks[bucket].push_back(t);
-                    cells += (int64_t)R * hi[k].H;
-                }
-            }
-            n_pairs += nr * nh;
-        }
-        if (n_pairs == 0) continue;
-        all.clear();
-        uint32_t first[4] = {0, 0, 0, 0};
-        for (int k = 0; k < 3; ++k) { first[k + 1] = first[k] + (uint32_t)tasks[k].size(); all.insert(all.end(), tasks[k].begin(), tasks[k].end()); }
-        // device image
-        size_t o = 0;
-        const size_t off_ro = o; o = align_up(o + read_off.size() * 4, 16);
-        const size_t off_hb = o; o = align_up(o + hap_bytes.size(), 16);
-        const size_t off_hf = o; o = align_up(o + hap_flags.size(), 16);
-        const size_t off_tk = o; o = align_up(o + all.size() * sizeof(PdTask), 16);
-        const size_t meta_bytes = o;
-        dev.pd_meta.reserve(meta_bytes); dev.pd_h_meta.reserve(meta_bytes);
-        uint8_t *hm = (uint8_t *)dev.pd_h_meta.p;
-        memcpy(hm + off_ro, read_off.data(), read_off.size() * 4);
-        memcpy(hm + off_hb, hap_bytes.data(), hap_bytes.size());
-        memcpy(hm + off_hf, hap_flags.data(), hap_flags.size());
-        memcpy(hm + off_tk, all.data(), all.size() * sizeof(PdTask));
-        o = 0;
-        const size_t off_out = o; o = align_up(o + (size_t)n_pairs * 8, 16);
-        const size_t off_cnt = o; o = align_up(o + 16 * 4, 16);
-        const size_t off_err = o; o = align_up(o + 16, 16);
-        const size_t dl_bytes = o;
-        const size_t off_s32 = o; o = align_up(o + (size_t)n_pairs * 4, 16);
-        const size_t off_redo = o; o = align_up(o + (size_t)n_pairs * 4, 16);
-        const size_t off_s64 = o; o = align_up(o + (size_t)n_pairs * 8, 16);
-        dev.pd_work.reserve(o); dev.pd_h_out.reserve(dl_bytes);
-        dev.pd_reads.reserve(std::max<size_t>(stride * 5, 16));
-        const uint32_t max_grid = (uint32_t)dev.n_sms * 32;
-        dev.pd_bnd.reserve((size_t)max_grid * (max_h + 1) * sizeof(BndPD<double>));
-        const uint8_t *src[5] = {b->read_bases, b->base_q, b->ins_q, b->del_q, b->gcp};
-        for (int a = 0; a < 5 && span; ++a)
-            CK(cudaMemcpyAsync((uint8_t *)dev.pd_reads.p + a * stride, src[a] + base_lo, span, cudaMemcpyHostToDevice, st));
-        CK(cudaMemcpyAsync(dev.pd_meta.p, dev.pd_h_meta.p, meta_bytes, cudaMemcpyHostToDevice, st));
-        h2d += (int64_t)(span * 5 + meta_bytes);
-        uint8_t *meta = (uint8_t *)dev.pd_meta.p, *work = (uint8_t *)dev.pd_work.p;
-        uint32_t *counters = (uint32_t *)(work + off_cnt);
-        CK(cudaMemsetAsync(work + off_cnt, 0, (off_err + 16) - off_cnt, st));
-        CK(cudaEventRecord(dev.ev_step0, st));
-        PdArgs pa;
-        memset(&pa, 0, sizeof pa);
-        pa.rd_bases = (const uint8_t *)dev.pd_reads.p;
-        pa.rd_q = pa.rd_bases + stride; pa.rd_i = pa.rd_q + stride; pa.rd_d = pa.rd_i + stride; pa.rd_c = pa.rd_d + stride;
-        pa.read_off = (const uint32_t *)(meta + off_ro);
-        pa.hap_bases = meta + off_hb; pa.hap_flags = meta + off_hf;
-        pa.tasks = (const PdTask *)(meta + off_tk);
-        pa.bnd = dev.pd_bnd.p; pa.bnd_stride = max_h + 1;
-        pa.m2m = (const double *)dev.m2m.p;
-        pa.err = (int *)(work + off_err);
-        pa.tristate_off = h->cfg.tristate_off != 0;
-        if (!h->cfg.force_fp64) {
-            for (int k = 0; k < 3; ++k) {
-                const uint32_t n = first[k + 1] - first[k];
-                if (!n) continue;
-                pa.first = first[k]; pa.n_tasks = n; pa.counter = counters + k;
-                pa.sums = work + off_s32 + (size_t)first[k] * 4;
-                const uint32_t grid = std::min<uint32_t>(n, std::min<uint32_t>(max_grid, (uint32_t)(dev.n_sms * kf[k].ctas_per_sm)));
-                void *args[] = {&pa};
-                CK(cudaLaunchKernel(kf[k].fn, dim3(grid), dim3(32), args, 0, st));
-                ++launches;
-            }
-        } else {
-            CK(cudaMemsetAsync(work + off_s32, 0xff, (size_t)n_pairs * 4, st));  // NaN: every pair goes to the fp64 list
-        }
-        phmm_pd_epilogue_f32<<<std::min<uint32_t>((n_pairs + 127) / 128, 2048), 128, 0, st>>>(
-            pa.tasks, n_pairs, (const float *)(work + off_s32), (double *)(work + off_out), (uint32_t *)(work + off_redo), counters + 8);
-        CK(cudaGetLastError());
-        {
-            pa.task_index = (const uint32_t *)(work + off_redo);
-            pa.n_tasks_ptr = counters + 8; pa.n_tasks = 0; pa.first = 0; pa.counter = counters + 4;
-            pa.sums = work + off_s64;
-            const uint32_t grid = std::min<uint32_t>(n_pairs, std::min<uint32_t>(max_grid, (uint32_t)(dev.n_sms * kd.ctas_per_sm)));
-            void *args[] = {&pa};
-            CK(cudaLaunchKernel(kd.fn, dim3(grid), dim3(32), args, 0, st));
-        }
-        phmm_pd_epilogue_f64<<<std::min<uint32_t>((n_pairs + 127) / 128, 2048), 128, 0, st>>>(
-            (const PdTask *)(meta + off_tk), (const uint32_t *)(work + off_redo), counters + 8, (const double *)(work + off_s64), (double *)(work + off_out));
-        CK(cudaGetLastError());
-        launches += 3;
-        CK(cudaEventRecord(dev.ev_step1, st));
-        CK(cudaMemcpyAsync(dev.pd_h_out.p, work + off_out, dl_bytes, cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
-        d2h += (int64_t)dl_bytes;
-        float ms = 0;
-        CK(cudaEventElapsedTime(&ms, dev.ev_step0, dev.ev_step1));
-        device_ms += ms;
-        const uint8_t *ho = (const uint8_t *)dev.pd_h_out.p;
-        const int err = *(const int *)(ho + off_err);
-        if (err == 1) throw Error(GPHMM_ERR_BAD_QUAL, "quality score out of range: ins/del/gcp > 127 or base qual 255");
-        if (err == 2) throw Error(GPHMM_ERR_INVALID_ARG, "read base other than ACGT on a SNP column of a partially determined haplotype (LoglessPDPairHMM.java:202)");
-        total_redo += ((const uint32_t *)(ho + off_cnt))[8];
-        const double *res = (const double *)ho;
-        for (int64_t u = ch.first; u < ch.second; ++u) {
-            const gphmm_unit &un = b->units[u];
-            const size_t n = (size_t)(un.read_end - un.read_begin) * (size_t)(un.hap_end - un.hap_begin);
-            if (n) memcpy(out + un.out_off, res + unit_out_base[u - ch.first], n * sizeof(double));
-        }
-        total_pairs += n_pairs; total_cells += cells;
-    }
-    std::lock_guard<std::mutex> lk(h->stats.mu);
-    h->stats.s.pairs += total_pairs; h->stats.s.cells += total_cells; h->stats.s.rescued_pairs += total_redo;
-    h->stats.s.kernel_launches += launches; h->stats.s.h2d_bytes += h2d; h->stats.s.d2h_bytes += d2h;
-    h->stats.s.device_ms += device_ms; h->stats.s.wall_ms += now_ms() - t0;
-    return GPHMM_OK;
-}
-
-// ---- Smith-Waterman (SmithWatermanJavaAligner) -------------------------------------------------------------------------
-int run_sw_batch(gphmm *h, const gphmm_sw_batch *b, const gphmm_sw_params *prm, int32_t capacity, int32_t *offsets, int32_t *n_elems,
-                 uint32_t *elems) {
-    std::lock_guard<std::mutex> run_lk(h->run_mu);
-    const double t0 = now_ms();
-    if (!b || !prm || prm->struct_size != (int32_t)sizeof(gphmm_sw_params)) throw Error(GPHMM_ERR_INVALID_ARG, "sw batch/params null or wrong struct_size");
-    if (b->n_pairs < 0 || capacity < 1) throw Error(GPHMM_ERR_INVALID_ARG, "negative pair count or capacity < 1");
-    if (b->n_pairs == 0) return GPHMM_OK;
-    if (!b->ref_bases || !b->ref_off || !b->alt_bases || !b->alt_off || !offsets || !n_elems || !elems) throw Error(GPHMM_ERR_INVALID_ARG, "null array");
-    if (prm->overhang_strategy < 0 || prm->overhang_strategy > 3) throw Error(GPHMM_ERR_INVALID_ARG, "unknown overhang strategy");
-    for (int64_t k = 0; k < b->n_pairs; ++k) {
-        const int64_t nr = b->ref_off[k + 1] - b->ref_off[k], na = b->alt_off[k + 1] - b->alt_off[k];
-        // SmithWatermanJavaAligner.java:64-66: non-null, non-empty sequences are required
-        if (nr <= 0 || na <= 0) throw Error(GPHMM_ERR_INVALID_ARG, "Non-null, non-empty sequences are required for the Smith-Waterman calculation");
-        if (nr > 32000 || na > 32000) throw Error(GPHMM_ERR_TOO_LARGE, "sequence longer than 32000 bases (backtrack entries are 16 bit)");
-    }
-    Device &dev = *h->devices[0];
-    CK(cudaSetDevice(dev.ordinal));
-    cudaStream_t st = dev.streams[0];
-    static int ctas_per_sm = 0;
-    if (!ctas_per_sm) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, phmm_sw_kernel, 32, 0));
-    constexpr uint64_t MAX_BT = (uint64_t)1 << 30;  // int16 entries per chunk (2 GB)
-    int64_t launches = 0, cells = 0;
-    double device_ms = 0;
-    bool overflow = false;
-    std::vector<SwTask> tasks;
-    for (int64_t k0 = 0; k0 < b->n_pairs;) {
-        tasks.clear();
-        uint64_t bt = 0, aux = 0;
-        int64_t k1 = k0;
-        const int64_t rb0 = b->ref_off[k0], ab0 = b->alt_off[k0];
-        while (k1 < b->n_pairs && (int64_t)tasks.size() < ((int64_t)1 << 20)) {
-            const uint32_t nr = (uint32_t)(b->ref_off[k1 + 1] - b->ref_off[k1]), na = (uint32_t)(b->alt_off[k1 + 1] - b->alt_off[k1]);
-            const uint64_t need = (uint64_t)((nr + SW_ROWS - 1) / SW_ROWS) * (na + 31) * SW_ROWS;
-            if (!tasks.empty() && (bt + need > MAX_BT || aux + (nr + 1) + 4 * (uint64_t)(na + 1) > ((uint64_t)1 << 30))) break;
-            SwTask t;
-            t.ref_off = (uint32_t)(b->ref_off[k1] - rb0); t.n_ref = nr;
-            t.alt_off = (uint32_t)(b->alt_off[k1] - ab0); t.n_alt = na;
-            t.bt_off = bt; t.aux_off = (uint32_t)aux; t.out_off = (uint32_t)tasks.size() * (uint32_t)capacity;
-            bt += need; aux += (nr + 1) + 4 * (uint64_t)(na + 1);
-            cells += (int64_t)nr * na;
-            tasks.push_back(t);
-            ++k1;
-        }
-        const size_t n = tasks.size();
-        const size_t ref_bytes = (size_t)(b->ref_off[k1] - rb0), alt_bytes = (size_t)(b->alt_off[k1] - ab0);
-        size_t o = 0;
-        const size_t off_ref = o; o = align_up(o + ref_bytes, 16);
-        const size_t off_alt = o; o = align_up(o + alt_bytes, 16);
-        const size_t off_tk = o; o = align_up(o + n * sizeof(SwTask), 16);
-        const size_t in_bytes = o;
-        dev.sw_in.reserve(in_bytes); dev.sw_h_in.reserve(in_bytes);
-        uint8_t *hi = (uint8_t *)dev.sw_h_in.p;
-        memcpy(hi + off_ref, b->ref_bases + rb0, ref_bytes);
-        memcpy(hi + off_alt, b->alt_bases + ab0, alt_bytes);
-        memcpy(hi + off_tk, tasks.data(), n * sizeof(SwTask));
-        o = 0;
-        const size_t off_el = o; o = align_up(o + n * (size_t)capacity * 4, 16);
-        const size_t off_ne = o; o = align_up(o + n * 4, 16);
-        const size_t off_of = o; o = align_up(o + n * 4, 16);
-        const size_t out_bytes = o;
-        const size_t off_cnt = o; o = align_up(o + 16, 16);
-        dev.sw_out.reserve(o); dev.sw_h_out.reserve(out_bytes);
-        dev.sw_bt.reserve(std::max<size_t>((size_t)bt * 2, 16));
-        dev.sw_aux.reserve(std::max<size_t>((size_t)aux * 4, 16));
-        CK(cudaMemcpyAsync(dev.sw_in.p, dev.sw_h_in.p, in_bytes, cudaMemcpyHostToDevice, st));
-        CK(cudaMemsetAsync((uint8_t *)dev.sw_out.p + off_cnt, 0, 16, st));
-        CK(cudaEventRecord(dev.ev_step0, st));
-        SwArgs a;
-        memset(&a, 0, sizeof a);
-        a.ref_bases = (const uint8_t *)dev.sw_in.p + off_ref; a.alt_bases = (const uint8_t *)dev.sw_in.p + off_alt;
-        a.tasks = (const SwTask *)((const uint8_t *)dev.sw_in.p + off_tk); a.n_tasks = (uint32_t)n;
-        a.counter = (uint32_t *)((uint8_t *)dev.sw_out.p + off_cnt);
-        a.bt = (int16_t *)dev.sw_bt.p; a.aux = (int32_t *)dev.sw_aux.p;
-        a.elems = (uint32_t *)((uint8_t *)dev.sw_out.p + off_el);
-        a.n_elems = (int32_t *)((uint8_t *)dev.sw_out.p + off_ne); a.offsets = (int32_t *)((uint8_t *)dev.sw_out.p + off_of);
-        a.capacity = (uint32_t)capacity;
-        a.w_match = prm->match_value; a.w_mismatch = prm->mismatch_penalty; a.w_open = prm->gap_open_penalty; a.w_extend = prm->gap_extend_penalty;
-        a.strategy = prm->overhang_strategy;
-        phmm_sw_kernel<<<(uint32_t)std::min<size_t>(n, (size_t)dev.n_sms * std::max(1, ctas_per_sm)), 32, 0, st>>>(a);
-        CK(cudaGetLastError());
-        ++launches;
-        CK(cudaEventRecord(dev.ev_step1, st));
-        CK(cudaMemcpyAsync(dev.sw_h_out.p, dev.sw_out.p, out_bytes, cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
-        float ms = 0;
-        CK(cudaEventElapsedTime(&ms, dev.ev_step0, dev.ev_step1));
-        device_ms += ms;
-        const uint8_t *ho = (const uint8_t *)dev.sw_h_out.p;
-        memcpy(elems + (size_t)k0 * capacity, ho + off_el, n * (size_t)capacity * 4);
-        memcpy(n_elems + k0, ho + off_ne, n * 4);
-        memcpy(offsets + k0, ho + off_of, n * 4);
-        for (size_t k = 0; k < n; ++k) overflow = overflow || n_elems[k0 + (int64_t)k] < 0;
-        {
-            std::lock_guard<std::mutex> lk(h->stats.mu);
-            h->stats.s.h2d_bytes += (int64_t)in_bytes; h->stats.s.d2h_bytes += (int64_t)out_bytes;
-        }
-        k0 = k1;
-    }
-    {
-        std::lock_guard<std::mutex> lk(h->stats.mu);
-        h->stats.s.pairs += b->n_pairs; h->stats.s.cells += cells; h->stats.s.kernel_launches += launches;
-        h->stats.s.device_ms += device_ms; h->stats.s.wall_ms += now_ms() - t0;
-    }
-    if (overflow) throw Error(GPHMM_ERR_TOO_LARGE, "a CIGAR has more elements than cigar_capacity (n_elems = -1 for those pairs)");
-    return GPHMM_OK;
-}
+#include "host_sw.inl"
 
 void validate_region_steps(const gphmm_batch *batch, const gphmm_region_steps *steps) {
     if (!steps || steps->struct_size != (int32_t)sizeof(gphmm_region_steps)) throw Error(GPHMM_ERR_INVALID_ARG, "steps is null or has the wrong struct_size");

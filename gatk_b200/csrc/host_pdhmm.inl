@@ -1,0 +1,204 @@
+// host_pdhmm.inl: host side of gphmm_pd_compute -- part of gpuphmm.cu (included inside its anonymous namespace; not a translation unit of its own).
+// ---- PD-HMM (LoglessPDPairHMM, DRAGEN-GATK mode) ---------------------------------------------------------------------
+// Column flags of one partially determined haplotype: alternative-base mask, DEL_END, the state in which row 1
+// processes the column, plus how rows >= 2 start (LoglessPDPairHMM.java:59 keeps the state across rows).
+void encode_pd_columns(const uint8_t *pd, uint32_t H, uint8_t *flags, uint32_t &first_event, uint32_t &carry) {
+    enum { SNP = 1, DEL_START = 2, DEL_END = 4 };  // PartiallyDeterminedHaplotype.java:59-61; A, C, G, T = 8, 16, 32, 64
+    uint32_t state = PD_NORMAL;
+    first_event = H + 1;
+    for (uint32_t j = 1; j <= H; ++j) {
+        const uint8_t f = pd[j - 1];
+        uint8_t v = (uint8_t)(state << PD_TYPE_SHIFT);
+        if (f & SNP) v |= (uint8_t)(PD_SNP_BIT | ((f >> 3) & PD_MASK_BITS));
+        if (f & DEL_END) v |= (uint8_t)PD_DEL_END_BIT;
+        flags[j - 1] = v;
+        if (state == PD_AFTER_DEL) state = PD_NORMAL;
+        if (f & DEL_START) state = PD_INSIDE_DEL;
+        if (f & DEL_END) state = PD_AFTER_DEL;
+        if ((f & (DEL_START | DEL_END)) && first_event == H + 1) first_event = j;
+    }
+    carry = state;
+}
+
+template <typename T, int K> KernelInfo pd_kernel_info() {
+    KernelInfo ki;
+    auto fn = phmm_pd_kernel<T, K>;
+    ki.fn = (const void *)fn;
+    ki.smem = 0;
+    int occ = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, 32, 0));
+    ki.ctas_per_sm = std::max(1, occ);
+    return ki;
+}
+
+int run_pd_batch(gphmm *h, const gphmm_batch *b, const uint8_t *hap_pd, double *out) {
+    std::lock_guard<std::mutex> run_lk(h->run_mu);
+    const double t0 = now_ms();
+    validate_batch(b);
+    if (b->n_units == 0) return GPHMM_OK;
+    if (!out) throw Error(GPHMM_ERR_INVALID_ARG, "out is null");
+    if (!hap_pd) throw Error(GPHMM_ERR_INVALID_ARG, "hap_pd_bases is null");
+    Device &dev = *h->devices[0];
+    CK(cudaSetDevice(dev.ordinal));
+    cudaStream_t st = dev.streams[0];
+    // reads of 128+ bases: 4 rows per lane in strips of 128 rows keeps 18 warps per SM resident (113 registers) where the
+    // 8-row variant (181 registers) keeps 11; GPHMM_PD_K8=1 selects the latter for comparison
+    static const bool k8 = getenv("GPHMM_PD_K8") != nullptr;
+    static const KernelInfo kf[3] = {pd_kernel_info<float, 2>(), pd_kernel_info<float, 4>(), k8 ? pd_kernel_info<float, 8>() : pd_kernel_info<float, 4>()};
+    static const KernelInfo kd = pd_kernel_info<double, 4>();
+    const auto chunks = split_units(b, h->chunk_cells() / 4, h->chunk_bytes(), false);
+    int64_t launches = 0, total_pairs = 0, total_cells = 0, total_redo = 0, h2d = 0, d2h = 0;
+    double device_ms = 0;
+    std::vector<uint32_t> read_off;
+    std::vector<uint8_t> hap_bytes, hap_flags;
+    std::vector<PdTask> tasks[3], all;
+    std::vector<uint32_t> unit_out_base;
+    for (const auto &ch : chunks) {
+        int64_t r_lo = INT64_MAX, r_hi = 0;
+        for (int64_t u = ch.first; u < ch.second; ++u) {
+            const gphmm_unit &un = b->units[u];
+            if (un.read_end > un.read_begin) { r_lo = std::min(r_lo, un.read_begin); r_hi = std::max(r_hi, un.read_end); }
+        }
+        if (r_hi <= r_lo) r_lo = r_hi = 0;
+        const int64_t base_lo = b->n_reads ? b->read_off[r_lo] : 0, base_hi = b->n_reads ? b->read_off[r_hi] : 0;
+        const size_t span = (size_t)(base_hi - base_lo), stride = align_up(span, 16);
+        read_off.resize((size_t)(r_hi - r_lo) + 1);
+        for (int64_t r = 0; r <= r_hi - r_lo; ++r) read_off[r] = (uint32_t)(b->read_off[r_lo + r] - base_lo);
+        hap_bytes.clear(); hap_flags.clear(); unit_out_base.clear();
+        for (auto &v : tasks) v.clear();
+        uint32_t n_pairs = 0, max_h = 1;
+        int64_t cells = 0;
+        for (int64_t u = ch.first; u < ch.second; ++u) {
+            const gphmm_unit &un = b->units[u];
+            const uint32_t nr = (uint32_t)(un.read_end - un.read_begin), nh = (uint32_t)(un.hap_end - un.hap_begin);
+            unit_out_base.push_back(n_pairs);
+            struct HapInfo { uint32_t off, H, first_event, carry; };
+            std::vector<HapInfo> hi(nh);
+            for (uint32_t k = 0; k < nh; ++k) {
+                const int64_t ho = b->hap_off[un.hap_begin + k];
+                const uint32_t H = (uint32_t)(b->hap_off[un.hap_begin + k + 1] - ho);
+                hi[k].off = (uint32_t)hap_bytes.size(); hi[k].H = H;
+                hap_bytes.insert(hap_bytes.end(), b->hap_bases + ho, b->hap_bases + ho + H);
+                hap_flags.resize(hap_bytes.size());
+                encode_pd_columns(hap_pd + ho, H, hap_flags.data() + hi[k].off, hi[k].first_event, hi[k].carry);
+                max_h = std::max(max_h, H);
+            }
+            for (uint32_t r = 0; r < nr; ++r) {
+                const uint32_t rl = (uint32_t)(un.read_begin - r_lo) + r, R = read_off[rl + 1] - read_off[rl];
+                const int bucket = R <= 63 ? 0 : (R <= 127 ? 1 : 2);
+                for (uint32_t k = 0; k < nh; ++k) {
+                    PdTask t;
+                    t.read = rl; t.hap_off = hi[k].off; t.H = hi[k].H; t.out_slot = n_pairs + r * nh + k;
+                    t.first_event = hi[k].first_event; t.carry = hi[k].carry;
+                    t.c0_exp = 125 - ceil_log2(hi[k].H); t.pad = 0;
+                    tasks[bucket].push_back(t);
+                    cells += (int64_t)R * hi[k].H;
+                }
+            }
+            n_pairs += nr * nh;
+        }
+        if (n_pairs == 0) continue;
+        all.clear();
+        uint32_t first[4] = {0, 0, 0, 0};
+        for (int k = 0; k < 3; ++k) { first[k + 1] = first[k] + (uint32_t)tasks[k].size(); all.insert(all.end(), tasks[k].begin(), tasks[k].end()); }
+        // device image
+        size_t o = 0;
+        const size_t off_ro = o; o = align_up(o + read_off.size() * 4, 16);
+        const size_t off_hb = o; o = align_up(o + hap_bytes.size(), 16);
+        const size_t off_hf = o; o = align_up(o + hap_flags.size(), 16);
+        const size_t off_tk = o; o = align_up(o + all.size() * sizeof(PdTask), 16);
+        const size_t meta_bytes = o;
+        dev.pd_meta.reserve(meta_bytes); dev.pd_h_meta.reserve(meta_bytes);
+        uint8_t *hm = (uint8_t *)dev.pd_h_meta.p;
+        memcpy(hm + off_ro, read_off.data(), read_off.size() * 4);
+        memcpy(hm + off_hb, hap_bytes.data(), hap_bytes.size());
+        memcpy(hm + off_hf, hap_flags.data(), hap_flags.size());
+        memcpy(hm + off_tk, all.data(), all.size() * sizeof(PdTask));
+        o = 0;
+        const size_t off_out = o; o = align_up(o + (size_t)n_pairs * 8, 16);
+        const size_t off_cnt = o; o = align_up(o + 16 * 4, 16);
+        const size_t off_err = o; o = align_up(o + 16, 16);
+        const size_t dl_bytes = o;
+        const size_t off_s32 = o; o = align_up(o + (size_t)n_pairs * 4, 16);
+        const size_t off_redo = o; o = align_up(o + (size_t)n_pairs * 4, 16);
+        const size_t off_s64 = o; o = align_up(o + (size_t)n_pairs * 8, 16);
+        dev.pd_work.reserve(o); dev.pd_h_out.reserve(dl_bytes);
+        dev.pd_reads.reserve(std::max<size_t>(stride * 5, 16));
+        const uint32_t max_grid = (uint32_t)dev.n_sms * 32;
+        dev.pd_bnd.reserve((size_t)max_grid * (max_h + 1) * sizeof(BndPD<double>));
+        const uint8_t *src[5] = {b->read_bases, b->base_q, b->ins_q, b->del_q, b->gcp};
+        for (int a = 0; a < 5 && span; ++a)
+            CK(cudaMemcpyAsync((uint8_t *)dev.pd_reads.p + a * stride, src[a] + base_lo, span, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(dev.pd_meta.p, dev.pd_h_meta.p, meta_bytes, cudaMemcpyHostToDevice, st));
+        h2d += (int64_t)(span * 5 + meta_bytes);
+        uint8_t *meta = (uint8_t *)dev.pd_meta.p, *work = (uint8_t *)dev.pd_work.p;
+        uint32_t *counters = (uint32_t *)(work + off_cnt);
+        CK(cudaMemsetAsync(work + off_cnt, 0, (off_err + 16) - off_cnt, st));
+        CK(cudaEventRecord(dev.ev_step0, st));
+        PdArgs pa;
+        memset(&pa, 0, sizeof pa);
+        pa.rd_bases = (const uint8_t *)dev.pd_reads.p;
+        pa.rd_q = pa.rd_bases + stride; pa.rd_i = pa.rd_q + stride; pa.rd_d = pa.rd_i + stride; pa.rd_c = pa.rd_d + stride;
+        pa.read_off = (const uint32_t *)(meta + off_ro);
+        pa.hap_bases = meta + off_hb; pa.hap_flags = meta + off_hf;
+        pa.tasks = (const PdTask *)(meta + off_tk);
+        pa.bnd = dev.pd_bnd.p; pa.bnd_stride = max_h + 1;
+        pa.m2m = (const double *)dev.m2m.p;
+        pa.err = (int *)(work + off_err);
+        pa.tristate_off = h->cfg.tristate_off != 0;
+        if (!h->cfg.force_fp64) {
+            for (int k = 0; k < 3; ++k) {
+                const uint32_t n = first[k + 1] - first[k];
+                if (!n) continue;
+                pa.first = first[k]; pa.n_tasks = n; pa.counter = counters + k;
+                pa.sums = work + off_s32 + (size_t)first[k] * 4;
+                const uint32_t grid = std::min<uint32_t>(n, std::min<uint32_t>(max_grid, (uint32_t)(dev.n_sms * kf[k].ctas_per_sm)));
+                void *args[] = {&pa};
+                CK(cudaLaunchKernel(kf[k].fn, dim3(grid), dim3(32), args, 0, st));
+                ++launches;
+            }
+        } else {
+            CK(cudaMemsetAsync(work + off_s32, 0xff, (size_t)n_pairs * 4, st));  // NaN: every pair goes to the fp64 list
+        }
+        phmm_pd_epilogue_f32<<<std::min<uint32_t>((n_pairs + 127) / 128, 2048), 128, 0, st>>>(
+            pa.tasks, n_pairs, (const float *)(work + off_s32), (double *)(work + off_out), (uint32_t *)(work + off_redo), counters + 8);
+        CK(cudaGetLastError());
+        {
+            pa.task_index = (const uint32_t *)(work + off_redo);
+            pa.n_tasks_ptr = counters + 8; pa.n_tasks = 0; pa.first = 0; pa.counter = counters + 4;
+            pa.sums = work + off_s64;
+            const uint32_t grid = std::min<uint32_t>(n_pairs, std::min<uint32_t>(max_grid, (uint32_t)(dev.n_sms * kd.ctas_per_sm)));
+            void *args[] = {&pa};
+            CK(cudaLaunchKernel(kd.fn, dim3(grid), dim3(32), args, 0, st));
+        }
+        phmm_pd_epilogue_f64<<<std::min<uint32_t>((n_pairs + 127) / 128, 2048), 128, 0, st>>>(
+            (const PdTask *)(meta + off_tk), (const uint32_t *)(work + off_redo), counters + 8, (const double *)(work + off_s64), (double *)(work + off_out));
+        CK(cudaGetLastError());
+        launches += 3;
+        CK(cudaEventRecord(dev.ev_step1, st));
+        CK(cudaMemcpyAsync(dev.pd_h_out.p, work + off_out, dl_bytes, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        d2h += (int64_t)dl_bytes;
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, dev.ev_step0, dev.ev_step1));
+        device_ms += ms;
+        const uint8_t *ho = (const uint8_t *)dev.pd_h_out.p;
+        const int err = *(const int *)(ho + off_err);
+        if (err == 1) throw Error(GPHMM_ERR_BAD_QUAL, "quality score out of range: ins/del/gcp > 127 or base qual 255");
+        if (err == 2) throw Error(GPHMM_ERR_INVALID_ARG, "read base other than ACGT on a SNP column of a partially determined haplotype (LoglessPDPairHMM.java:202)");
+        total_redo += ((const uint32_t *)(ho + off_cnt))[8];
+        const double *res = (const double *)ho;
+        for (int64_t u = ch.first; u < ch.second; ++u) {
+            const gphmm_unit &un = b->units[u];
+            const size_t n = (size_t)(un.read_end - un.read_begin) * (size_t)(un.hap_end - un.hap_begin);
+            if (n) memcpy(out + un.out_off, res + unit_out_base[u - ch.first], n * sizeof(double));
+        }
+        total_pairs += n_pairs; total_cells += cells;
+    }
+    std::lock_guard<std::mutex> lk(h->stats.mu);
+    h->stats.s.pairs += total_pairs; h->stats.s.cells += total_cells; h->stats.s.rescued_pairs += total_redo;
+    h->stats.s.kernel_launches += launches; h->stats.s.h2d_bytes += h2d; h->stats.s.d2h_bytes += d2h;
+    h->stats.s.device_ms += device_ms; h->stats.s.wall_ms += now_ms() - t0;
+    return GPHMM_OK;
+}
+

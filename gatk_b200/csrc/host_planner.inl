@@ -1,0 +1,392 @@
+// host_planner.inl: batch validation, chunking, haplotype-prefix sharing plan, chunk plan -- part of gpuphmm.cu (included inside its anonymous namespace; not a translation unit of its own).
+int ceil_log2(uint32_t v) {
+    int lg = 0;
+    while ((1u << lg) < v) ++lg;
+    return lg;
+}
+
+void validate_batch(const gphmm_batch *b) {
+    if (!b) throw Error(GPHMM_ERR_INVALID_ARG, "batch is null");
+    if (b->n_units < 0 || b->n_reads < 0 || b->n_haps < 0) throw Error(GPHMM_ERR_INVALID_ARG, "negative count");
+    if (b->n_units == 0) return;
+    if (!b->units || !b->read_off || !b->hap_off) throw Error(GPHMM_ERR_INVALID_ARG, "null offsets/units");
+    for (int64_t r = 0; r < b->n_reads; ++r)
+        if (b->read_off[r + 1] < b->read_off[r]) throw Error(GPHMM_ERR_INVALID_ARG, "read_off not monotone");
+    for (int64_t h = 0; h < b->n_haps; ++h)
+        if (b->hap_off[h + 1] <= b->hap_off[h])
+            throw Error(GPHMM_ERR_INVALID_ARG, "zero-length haplotype (PairHMM.initialize requires haplotypeMaxLength > 0)");
+    for (int64_t u = 0; u < b->n_units; ++u) {
+        const gphmm_unit &un = b->units[u];
+        if (un.read_begin < 0 || un.read_end < un.read_begin || un.read_end > b->n_reads || un.hap_begin < 0 ||
+            un.hap_end < un.hap_begin || un.hap_end > b->n_haps || un.out_off < 0)
+            throw Error(GPHMM_ERR_INVALID_ARG, "unit range out of bounds");
+        if (un.hap_end - un.hap_begin > 65535) throw Error(GPHMM_ERR_TOO_LARGE, "more than 65535 haplotypes in one unit");
+    }
+    if (b->n_reads > 0 && b->read_off[b->n_reads] > 0 &&
+        (!b->read_bases || !b->base_q || !b->ins_q || !b->del_q || !b->gcp))
+        throw Error(GPHMM_ERR_INVALID_ARG, "null read array");
+    if (b->n_haps > 0 && !b->hap_bases) throw Error(GPHMM_ERR_INVALID_ARG, "null hap_bases");
+}
+
+// Greedy split of the unit list into chunks bounded by cells and staged bytes.
+std::vector<std::pair<int64_t, int64_t>> split_units(const gphmm_batch *b, int64_t chunk_cells, int64_t chunk_bytes, bool ramp_up) {
+    std::vector<std::pair<int64_t, int64_t>> out;
+    int64_t u = 0;
+    const int64_t full_cells = chunk_cells;
+    while (u < b->n_units) {
+        // ramp up: the first chunks are small so that the GPU starts early while the host is still staging
+        const size_t ci = out.size();
+        // (2.5e8 cells = a handful of regions, then doubling: the planner threads stay ahead of the GPU from there on)
+        chunk_cells = (!ramp_up || ci >= 16) ? full_cells : std::min<int64_t>(full_cells, (int64_t)250000000 << ci);
+        int64_t cells = 0, bytes = 0, pairs = 0, u_end = u;
+        int64_t r_lo = INT64_MAX, r_hi = 0;
+        while (u_end < b->n_units) {
+            const gphmm_unit &un = b->units[u_end];
+            const int64_t nr = un.read_end - un.read_begin, nh = un.hap_end - un.hap_begin;
+            const int64_t rb = nr ? b->read_off[un.read_end] - b->read_off[un.read_begin] : 0;
+            const int64_t hb = nh ? b->hap_off[un.hap_end] - b->hap_off[un.hap_begin] : 0;
+            const int64_t n_lo = std::min(r_lo, nr ? un.read_begin : r_lo), n_hi = std::max(r_hi, nr ? un.read_end : r_hi);
+            const int64_t span = n_hi > n_lo ? b->read_off[n_hi] - b->read_off[n_lo] : 0;
+            const int64_t c = rb * hb;
+            if (u_end > u && (cells + c > chunk_cells || span * 5 + bytes + hb > chunk_bytes || pairs + nr * nh > (int64_t)1 << 25))
+                break;
+            cells += c; bytes += hb + nh; pairs += nr * nh;
+            r_lo = n_lo; r_hi = n_hi;
+            ++u_end;
+        }
+        const int64_t span = r_hi > r_lo ? b->read_off[r_hi] - b->read_off[r_lo] : 0;
+        if (span >= ((int64_t)1 << 31) || bytes >= ((int64_t)1 << 31) || pairs >= ((int64_t)1 << 28))
+            throw Error(GPHMM_ERR_TOO_LARGE, "a single unit exceeds the per-chunk device budget");
+        out.emplace_back(u, u_end);
+        u = u_end;
+    }
+    return out;
+}
+
+// Plans the shared (prefix-compressed) stream of one unit: haplotypes sorted lexicographically, pass i+1 resumes
+// from a snapshot taken at the last column it shares with its predecessors.  Appends to c.sstreams / pass_info /
+// segments and returns the unit's schedule.  With share == false every pass starts from column 1 in input order.
+// Lexicographic order of a unit's haplotypes (input order when sharing is off).
+std::vector<int> sorted_hap_order(const gphmm_batch *b, const gphmm_unit &un, bool share) {
+    const int n = (int)(un.hap_end - un.hap_begin);
+    auto hap_ptr = [&](int k) { return b->hap_bases + b->hap_off[un.hap_begin + k]; };
+    auto hap_len = [&](int k) { return (uint32_t)(b->hap_off[un.hap_begin + k + 1] - b->hap_off[un.hap_begin + k]); };
+    std::vector<int> order(n);
+    for (int k = 0; k < n; ++k) order[k] = k;
+    if (share)
+        std::sort(order.begin(), order.end(), [&](int x, int y) {
+            const uint32_t lx = hap_len(x), ly = hap_len(y);
+            const int cmp = memcmp(hap_ptr(x), hap_ptr(y), std::min(lx, ly));
+            if (cmp != 0) return cmp < 0;
+            if (lx != ly) return lx < ly;
+            return x < y;
+        });
+    return order;
+}
+
+UnitSched plan_unit_sharing(const gphmm_batch *b, const gphmm_unit &un, uint32_t hap_first_local, bool share, ChunkPlan &c,
+                            int64_t sum_read_len, const std::vector<int> &full_order, int g_first, int g_count) {
+    constexpr uint32_t SPACING = 32;
+    static const uint32_t MIN_DEPTH = getenv("GPHMM_MIN_DEPTH") ? (uint32_t)std::max(32, atoi(getenv("GPHMM_MIN_DEPTH"))) : 32u;  // tuning knob
+    UnitSched us;
+    memset(&us, 0, sizeof us);
+    const int n = g_count;  // haplotypes of this group: full_order[g_first .. g_first + g_count)
+    us.pass_first = (uint32_t)c.pass_info.size();
+    us.n_passes = (uint32_t)n;
+    us.seg_first = (uint32_t)c.segments.size();
+    c.sstreams.insert(c.sstreams.end(), STREAM_PAD, (uint8_t)CODE_NULL);
+    us.sstream_off = (uint32_t)c.sstreams.size();
+    if (n == 0) return us;
+    auto hap_ptr = [&](int k) { return b->hap_bases + b->hap_off[un.hap_begin + k]; };
+    auto hap_len = [&](int k) { return (uint32_t)(b->hap_off[un.hap_begin + k + 1] - b->hap_off[un.hap_begin + k]); };
+    std::vector<int> order(full_order.begin() + g_first, full_order.begin() + g_first + g_count);
+    struct Snap { int pass; uint32_t depth, pos; int slot; uint32_t free_after; };
+    std::vector<Snap> snaps;
+    int slot_owner[MAX_SNAP_SLOTS];
+    for (int k = 0; k < MAX_SNAP_SLOTS; ++k) slot_owner[k] = -1;
+    std::vector<uint32_t> r(n, 0), pass_start(n + 1, 1), end_pos(n, 0);
+    std::vector<int> snap_of_pass(n, -1);
+    std::vector<uint32_t> lcp(n, 0), n_pad(n, 0);
+    for (int i = 0; i < n; ++i) {
+        const uint32_t H = hap_len(order[i]);
+        // every pass spans at least 32 stream positions (NULL columns before its END if it is shorter), so that the
+        // 32-step END windows of consecutive passes never overlap
+        n_pad[i] = (H - r[i]) < 32u ? 32u - (H - r[i]) : 0u;
+        end_pos[i] = pass_start[i] + (H - r[i]) + n_pad[i];
+        pass_start[i + 1] = end_pos[i] + 1;
+        if (i + 1 >= n || !share) continue;
+        // longest common prefix with the next haplotype in sorted order
+        const uint8_t *x = hap_ptr(order[i]), *y = hap_ptr(order[i + 1]);
+        const uint32_t m = std::min(H, hap_len(order[i + 1]));
+        uint32_t d = 0;
+        while (d < m && x[d] == y[d]) ++d;
+        lcp[i] = d;
+        if (d < MIN_DEPTH) continue;
+        int k = -1;
+        {
+            // preferred: a snapshot at exactly the shared depth, taken by the latest pass that computed column d
+            int j = i;
+            while (r[j] >= d) --j;  // r[0] = 0 < d
+            const uint32_t pos = pass_start[j] + (d - r[j]) - 1;
+            for (size_t q = 0; q < snaps.size(); ++q)
+                if (snaps[q].pass == j && snaps[q].depth == d && slot_owner[snaps[q].slot] == (int)q) k = (int)q;
+            if (k < 0) {
+                bool ok = true;
+                for (const Snap &sn : snaps) ok = ok && (sn.pos + SPACING <= pos || pos + SPACING <= sn.pos);
+                int slot = -1;
+                for (int q = 0; q < MAX_SNAP_SLOTS && ok && slot < 0; ++q)
+                    if (slot_owner[q] < 0 || snaps[slot_owner[q]].free_after < pos) slot = q;
+                if (ok && slot >= 0) {
+                    snaps.push_back({j, d, pos, slot, 0});
+                    k = (int)snaps.size() - 1;
+                    slot_owner[slot] = k;
+                }
+            }
+        }
+        if (k < 0) {
+            // fallback: the deepest live snapshot whose prefix the next haplotype still shares
+            uint32_t best = 0;
+            for (size_t q = 0; q < snaps.size(); ++q) {
+                if (slot_owner[snaps[q].slot] != (int)q || snaps[q].depth < MIN_DEPTH || snaps[q].depth <= best) continue;
+                uint32_t shared_len = UINT32_MAX;  // LCP(haplotype of snaps[q].pass, haplotype i+1) = min lcp[pass..i]
+                for (int t = snaps[q].pass; t <= i; ++t) shared_len = std::min(shared_len, lcp[t]);
+                if (shared_len >= snaps[q].depth) { best = snaps[q].depth; k = (int)q; }
+            }
+            if (k < 0) continue;
+        }
+        snaps[k].free_after = end_pos[i];  // restored at the END column of pass i
+        r[i + 1] = snaps[k].depth;
+        snap_of_pass[i + 1] = k;
+    }
+    // stream + pass table
+    for (int i = 0; i < n; ++i) {
+        const uint32_t H = hap_len(order[i]);
+        const size_t w = c.sstreams.size();
+        c.sstreams.resize(w + (H - r[i]) + n_pad[i] + 1);
+        uint8_t *dst = c.sstreams.data() + w;
+        // the full stream of this unit was encoded a moment ago: copy the columns behind the shared prefix
+        memcpy(dst, c.streams.data() + c.hap_stream_off[hap_first_local + order[i]] + r[i], H - r[i]);
+        for (uint32_t q = 0; q < n_pad[i]; ++q) dst[H - r[i] + q] = (uint8_t)CODE_NULL;  // prior 0: no effect on the sum
+        dst[H - r[i] + n_pad[i]] = (uint8_t)CODE_END;
+        PassInfo pi;
+        pi.out_idx = (uint16_t)order[i];
+        pi.restore_slot = (int16_t)(snap_of_pass[i] >= 0 ? snaps[snap_of_pass[i]].slot : -1);
+        c.pass_info.push_back(pi);
+        c.skipped_cells += (int64_t)r[i] * sum_read_len;
+        c.computed_columns += H - r[i];
+    }
+    // schedule.  Lane l meets stream position q at step q + l, so an END column at e keeps some lane busy with it
+    // during steps [e, e+32) and a snapshot position s during [s, s+32).  END windows never overlap each other
+    // (passes span >= 32 positions), snapshot windows never overlap each other (SPACING), so at any step at most one
+    // of each is active.  A segment = branch-free steps, then checked steps with one constant (END, snapshot) pair.
+    std::vector<uint32_t> pts;
+    pts.push_back(1);
+    for (int i = 0; i < n; ++i) { pts.push_back(end_pos[i]); pts.push_back(end_pos[i] + 32); }
+    for (const Snap &sn : snaps) { pts.push_back(sn.pos); pts.push_back(sn.pos + 32); }
+    std::sort(pts.begin(), pts.end());
+    pts.erase(std::unique(pts.begin(), pts.end()), pts.end());
+    std::vector<int> snap_by_pos(snaps.size());
+    for (size_t q = 0; q < snaps.size(); ++q) snap_by_pos[q] = (int)q;
+    std::sort(snap_by_pos.begin(), snap_by_pos.end(), [&](int x, int y) { return snaps[x].pos < snaps[y].pos; });
+    Segment seg;
+    auto clear_seg = [&]() { seg.n_free = 0; seg.n_chk = 0; seg.snap_pos = INT32_MIN; seg.snap_slot = 0; seg.end_restore = MAX_SNAP_SLOTS; seg.end_out = 0; };
+    clear_seg();
+    size_t ie = 0, is = 0;  // first END / snapshot whose window has not expired yet
+    for (size_t k = 0; k + 1 < pts.size(); ++k) {
+        const uint32_t x = pts[k], y = pts[k + 1];
+        while (ie < (size_t)n && end_pos[ie] + 32 <= x) ++ie;
+        while (is < snaps.size() && snaps[snap_by_pos[is]].pos + 32 <= x) ++is;
+        const bool end_on = ie < (size_t)n && end_pos[ie] <= x;
+        const bool snap_on = is < snaps.size() && snaps[snap_by_pos[is]].pos <= x;
+        static const bool all_checked = getenv("GPHMM_ALL_CHECKED") != nullptr;  // experiment: cost of the checked loop
+        if (!end_on && !snap_on && !all_checked) {
+            if (seg.n_chk) { c.segments.push_back(seg); clear_seg(); }
+            seg.n_free += y - x;
+            continue;
+        }
+        if (seg.n_chk) { c.segments.push_back(seg); clear_seg(); }
+        seg.n_chk = y - x;
+        if (snap_on) { seg.snap_pos = (int32_t)snaps[snap_by_pos[is]].pos; seg.snap_slot = (uint8_t)snaps[snap_by_pos[is]].slot; }
+        if (end_on) {
+            seg.end_out = (uint16_t)order[ie];
+            seg.end_restore = (int8_t)(ie + 1 < (size_t)n && snap_of_pass[ie + 1] >= 0 ? snaps[snap_of_pass[ie + 1]].slot : MAX_SNAP_SLOTS);  // MAX_SNAP_SLOTS = pass-start state
+        }
+    }
+    if (seg.n_free || seg.n_chk) c.segments.push_back(seg);
+    us.n_segs = (uint32_t)c.segments.size() - us.seg_first;
+    return us;
+}
+
+// When a chunk has too few reads to fill the GPU with one warp per read (a single HaplotypeCaller region is ~100 reads),
+// each unit's haplotypes are split into groups and every (read, group) pair becomes a task of its own.
+constexpr int64_t TARGET_TASKS = 148 * 28 * 2;
+
+void plan_chunk(const gphmm_batch *b, int64_t u0, int64_t u1, bool force_fp64, bool share, ChunkPlan &c, bool pcr_hint = false) {
+    c.u0 = u0; c.u1 = u1;
+    c.r_lo = INT64_MAX; c.r_hi = 0;
+    for (int64_t u = u0; u < u1; ++u) {
+        const gphmm_unit &un = b->units[u];
+        if (un.read_end > un.read_begin) { c.r_lo = std::min(c.r_lo, un.read_begin); c.r_hi = std::max(c.r_hi, un.read_end); }
+    }
+    if (c.r_hi <= c.r_lo) { c.r_lo = c.r_hi = 0; }
+    c.base_lo = b->n_reads ? b->read_off[c.r_lo] : 0;
+    c.base_hi = b->n_reads ? b->read_off[c.r_hi] : 0;
+    const int64_t n_span = c.r_hi - c.r_lo;
+    c.read_off.resize(n_span + 1);
+    for (int64_t r = 0; r <= n_span; ++r) c.read_off[r] = (uint32_t)(b->read_off[c.r_lo + r] - c.base_lo);
+
+    // quality classes from a sample of the chunk's reads: flat (one (ins, del, gcp) triple on every base) and
+    // symmetric (ins == del per base, flat gcp).  The device decides per read which class it really belongs to
+    // (phmm_classify_kernel); a class that is missed here only means those reads take the general kernel.
+    c.n_classes = 0;
+    c.n_sym = 0;
+    if (!force_fp64 && n_span > 0) {
+        const int64_t stride = std::max<int64_t>(1, n_span / 256);
+        for (int64_t r = 0; r < n_span; r += stride) {
+            const int64_t o = b->read_off[c.r_lo + r], e = b->read_off[c.r_lo + r + 1];
+            if (e == o) continue;
+            const uint8_t qi = b->ins_q[o], qd = b->del_q[o], qc = b->gcp[o];
+            if (qi > 127 || qd > 127 || qc > 127) continue;
+            // an array is constant iff it equals itself shifted by one (memcmp is vectorised)
+            const size_t n1 = (size_t)(e - o - 1);
+            const bool flat_c = memcmp(b->gcp + o, b->gcp + o + 1, n1) == 0;
+            const bool flat = flat_c && memcmp(b->ins_q + o, b->ins_q + o + 1, n1) == 0 && memcmp(b->del_q + o, b->del_q + o + 1, n1) == 0;
+            bool sym = flat_c && memcmp(b->ins_q + o, b->del_q + o, n1 + 1) == 0;
+            if (sym && !flat) {
+                uint8_t mx = 0;
+                for (int64_t i = o; i < e; ++i) mx = std::max(mx, b->ins_q[i]);
+                sym = mx <= SYM_MAX_GAP_QUAL;
+            } else if (sym) {
+                sym = qi <= SYM_MAX_GAP_QUAL;
+            }
+            if (flat && !(pcr_hint && qi == qd)) {  // the PCR indel model (region steps) will lower ins and del together
+                bool seen = false;
+                for (int k = 0; k < c.n_classes; ++k) seen = seen || (c.class_qi[k] == qi && c.class_qd[k] == qd && c.class_qc[k] == qc);
+                if (seen) continue;
+                if (c.n_classes < MAX_FLAT_CLASSES) {
+                    c.class_qi[c.n_classes] = qi; c.class_qd[c.n_classes] = qd; c.class_qc[c.n_classes] = qc; ++c.n_classes;
+                    continue;
+                }
+            }
+            if (sym) {  // includes flat reads that found no free flat class
+                bool seen = false;
+                for (int k = 0; k < c.n_sym; ++k) seen = seen || c.sym_qc[k] == qc;
+                if (!seen && c.n_sym < MAX_SYM_CLASSES) c.sym_qc[c.n_sym++] = qc;
+            }
+        }
+    }
+
+    // haplotype alphabet of the chunk: A C G T N are fixed codes, any other byte value gets the next free code
+    int16_t lut[256];
+    for (int i = 0; i < 256; ++i) lut[i] = -1;
+    memset(c.code_byte, 0, sizeof c.code_byte);
+    const char fixed[5] = {'A', 'C', 'G', 'T', 'N'};
+    for (int i = 0; i < 5; ++i) { lut[(uint8_t)fixed[i]] = (int16_t)(CODE_FIRST_BASE + i); c.code_byte[CODE_FIRST_BASE + i] = (uint8_t)fixed[i]; }
+    c.n_codes = CODE_FIRST_BASE + 5;
+
+    c.streams.clear(); c.hap_len.clear(); c.hap_stream_off.clear(); c.units.clear(); c.tasks.clear();
+    c.sstreams.clear(); c.pass_info.clear(); c.segments.clear(); c.unit_sched.clear(); c.skipped_cells = 0; c.computed_columns = 0; c.n_keep = 0;
+    c.n_pairs = 0; c.cells = 0; c.max_stream_len = 0; c.max_hap_len = 0;
+    int64_t n_reads_with_work = 0;
+    for (int64_t u = u0; u < u1; ++u)
+        if (b->units[u].hap_end > b->units[u].hap_begin) n_reads_with_work += b->units[u].read_end - b->units[u].read_begin;
+    const int64_t want_groups = n_reads_with_work > 0 ? (TARGET_TASKS + n_reads_with_work - 1) / n_reads_with_work : 1;
+    std::vector<Task> raw;
+    std::vector<uint8_t> bucket_of;
+    raw.reserve((size_t)(c.r_hi - c.r_lo));
+    bucket_of.reserve((size_t)(c.r_hi - c.r_lo));
+    c.streams.reserve((size_t)(u1 - u0) * 64);
+    uint32_t bucket_count[N_FP32_BUCKETS] = {0};
+    for (int64_t u = u0; u < u1; ++u) {
+        const gphmm_unit &un = b->units[u];
+        const uint32_t nr = (uint32_t)(un.read_end - un.read_begin), nh = (uint32_t)(un.hap_end - un.hap_begin);
+        UnitDesc d;
+        d.read_first = nr ? (uint32_t)(un.read_begin - c.r_lo) : 0;
+        d.n_reads = nr;
+        d.hap_first = (uint32_t)c.hap_len.size();
+        d.n_haps = nh;
+        d.out_base = c.n_pairs;
+        d.ref_hap = -1;
+        d.keep_base = c.n_keep;
+        c.n_keep += nr;
+        c.streams.insert(c.streams.end(), STREAM_PAD, (uint8_t)CODE_NULL);  // fill/drain codes of the fast kernels
+        const uint32_t stream_off = (uint32_t)c.streams.size();
+        uint32_t max_h = 1;
+        int64_t sum_h = 0;
+        {
+            const int64_t hap_bytes = nh ? b->hap_off[un.hap_end] - b->hap_off[un.hap_begin] : 0;
+            size_t w = c.streams.size();
+            c.streams.resize(w + (size_t)hap_bytes + nh);
+            uint8_t *dst = c.streams.data();
+            for (int64_t h = un.hap_begin; h < un.hap_end; ++h) {
+                const int64_t ho = b->hap_off[h];
+                const uint32_t H = (uint32_t)(b->hap_off[h + 1] - ho);
+                c.hap_len.push_back(H);
+                c.hap_stream_off.push_back((uint32_t)w);
+                const uint8_t *src = b->hap_bases + ho;
+                for (uint32_t j = 0; j < H; ++j) {
+                    int16_t code = lut[src[j]];
+                    if (code < 0) {
+                        if (c.n_codes >= MAX_CODES) throw Error(GPHMM_ERR_ALPHABET, "too many distinct haplotype byte values");
+                        code = lut[src[j]] = (int16_t)c.n_codes;
+                        c.code_byte[c.n_codes++] = src[j];
+                    }
+                    dst[w + j] = (uint8_t)code;
+                }
+                w += H;
+                dst[w++] = (uint8_t)CODE_END;
+                max_h = std::max(max_h, H);
+                sum_h += H;
+            }
+        }
+        const uint32_t stream_len = (uint32_t)c.streams.size() - stream_off;
+        c.max_stream_len = std::max(c.max_stream_len, stream_len);
+        c.max_hap_len = std::max(c.max_hap_len, max_h);
+        d.c0_exp = (force_fp64 ? C0_BASE_EXP_F64 : C0_BASE_EXP_F32) - ceil_log2(max_h);
+        c.units.push_back(d);
+        // reads of 255+ bases run the striped kernel on the full stream: only shorter reads use the shared streams
+        int64_t fast_read_len = 0;
+        for (uint32_t r = 0; r < nr && nh; ++r) {
+            const uint32_t R = c.read_off[d.read_first + r + 1] - c.read_off[d.read_first + r];
+            if ((R + 1) / 32 + 1 <= 8) fast_read_len += R;
+        }
+        const int n_groups = force_fp64 ? 1 : (int)std::max<int64_t>(1, std::min<int64_t>(want_groups, nh));
+        const uint32_t sched_first = (uint32_t)c.unit_sched.size();
+        {
+            const std::vector<int> order = sorted_hap_order(b, un, share && !force_fp64);
+            for (int gi = 0; gi < n_groups; ++gi) {
+                const int g0 = (int)((int64_t)nh * gi / n_groups), g1 = (int)((int64_t)nh * (gi + 1) / n_groups);
+                c.unit_sched.push_back(plan_unit_sharing(b, un, d.hap_first, share && !force_fp64, c, fast_read_len, order, g0, g1 - g0));
+            }
+        }
+        if (nh == 0) continue;
+        for (uint32_t r = 0; r < nr; ++r) {
+            const uint32_t rl = d.read_first + r;
+            const uint32_t R = c.read_off[rl + 1] - c.read_off[rl];
+            Task t;
+            t.read = rl; t.stream_off = stream_off; t.stream_len = stream_len;
+            t.out_base = d.out_base + r * nh; t.c0_exp = d.c0_exp; t.n_haps = nh; t.hap_first = d.hap_first; t.unit = sched_first;
+            // fast kernels need two spare rows below the read (accumulator row + row-0 carrier): R + 2 <= 32 K
+            const uint32_t k = (R + 1) / 32 + 1;
+            const uint8_t bucket = force_fp64 ? 0 : (k <= 8 ? (uint8_t)(k - 1) : (uint8_t)8);
+            // one task per haplotype group for the fast kernels; the striped / fp64 kernels sweep the full stream once
+            const int n_t = bucket < 8 && !force_fp64 ? n_groups : 1;
+            for (int gi = 0; gi < n_t; ++gi) {
+                t.unit = sched_first + (uint32_t)gi;
+                raw.push_back(t);
+                bucket_of.push_back(bucket);
+                ++bucket_count[bucket];
+            }
+            c.cells += (int64_t)R * sum_h;
+        }
+        c.n_pairs += nr * nh;
+    }
+    // counting sort by bucket (stable: unit order is kept inside a bucket)
+    c.bucket_begin[0] = 0;
+    for (int k = 0; k < N_FP32_BUCKETS; ++k) c.bucket_begin[k + 1] = c.bucket_begin[k] + bucket_count[k];
+    c.tasks.resize(raw.size());
+    uint32_t cursor[N_FP32_BUCKETS];
+    for (int k = 0; k < N_FP32_BUCKETS; ++k) cursor[k] = c.bucket_begin[k];
+    for (size_t i = 0; i < raw.size(); ++i) c.tasks[cursor[bucket_of[i]]++] = raw[i];
+}
+
