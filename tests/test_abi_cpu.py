@@ -43,6 +43,7 @@ def test_struct_layouts_match_header():
     assert ctypes.sizeof(native._Unit) == 40 == native.UNIT_DTYPE.itemsize
     assert ctypes.sizeof(native._Batch) == 96
     assert ctypes.sizeof(native._RegionSteps) == 104
+    assert ctypes.sizeof(native._SwParams) == 24 and ctypes.sizeof(native._SwBatch) == 40
     assert ctypes.sizeof(native._Config) == 48
     assert ctypes.sizeof(native.Stats) == 12 * 8
 
