@@ -87,6 +87,7 @@ std::vector<int> sorted_hap_order(const gphmm_batch *b, const gphmm_unit &un, bo
 UnitSched plan_unit_sharing(const gphmm_batch *b, const gphmm_unit &un, uint32_t hap_first_local, bool share, ChunkPlan &c,
                             int64_t sum_read_len, const std::vector<int> &full_order, int g_first, int g_count) {
     constexpr uint32_t SPACING = 32;
+    static const uint32_t NEAR_DEPTHS = getenv("GPHMM_NEAR_DEPTHS") ? (uint32_t)std::max(1, atoi(getenv("GPHMM_NEAR_DEPTHS"))) : 96u;  // how far below the shared depth to look
     static const uint32_t MIN_DEPTH = getenv("GPHMM_MIN_DEPTH") ? (uint32_t)std::max(32, atoi(getenv("GPHMM_MIN_DEPTH"))) : 32u;  // tuning knob
     UnitSched us;
     memset(&us, 0, sizeof us);
@@ -123,24 +124,25 @@ UnitSched plan_unit_sharing(const gphmm_batch *b, const gphmm_unit &un, uint32_t
         lcp[i] = d;
         if (d < MIN_DEPTH) continue;
         int k = -1;
-        {
-            // preferred: a snapshot at exactly the shared depth, taken by the latest pass that computed column d
+        // preferred: a snapshot at exactly the shared depth, taken by the latest pass that computed that column; when its
+        // window would overlap another snapshot window (two variants less than 32 columns apart), the deepest shallower
+        // column that fits -- giving up a few columns beats falling back to a much earlier snapshot
+        for (uint32_t dd = d; k < 0 && dd >= MIN_DEPTH && dd + NEAR_DEPTHS > d; --dd) {
             int j = i;
-            while (r[j] >= d) --j;  // r[0] = 0 < d
-            const uint32_t pos = pass_start[j] + (d - r[j]) - 1;
+            while (r[j] >= dd) --j;  // r[0] = 0 < dd
+            const uint32_t pos = pass_start[j] + (dd - r[j]) - 1;
             for (size_t q = 0; q < snaps.size(); ++q)
-                if (snaps[q].pass == j && snaps[q].depth == d && slot_owner[snaps[q].slot] == (int)q) k = (int)q;
-            if (k < 0) {
-                bool ok = true;
-                for (const Snap &sn : snaps) ok = ok && (sn.pos + SPACING <= pos || pos + SPACING <= sn.pos);
-                int slot = -1;
-                for (int q = 0; q < MAX_SNAP_SLOTS && ok && slot < 0; ++q)
-                    if (slot_owner[q] < 0 || snaps[slot_owner[q]].free_after < pos) slot = q;
-                if (ok && slot >= 0) {
-                    snaps.push_back({j, d, pos, slot, 0});
-                    k = (int)snaps.size() - 1;
-                    slot_owner[slot] = k;
-                }
+                if (snaps[q].pass == j && snaps[q].depth == dd && slot_owner[snaps[q].slot] == (int)q) k = (int)q;
+            if (k >= 0) break;
+            bool ok = true;
+            for (const Snap &sn : snaps) ok = ok && (sn.pos + SPACING <= pos || pos + SPACING <= sn.pos);
+            int slot = -1;
+            for (int q = 0; q < MAX_SNAP_SLOTS && ok && slot < 0; ++q)
+                if (slot_owner[q] < 0 || snaps[slot_owner[q]].free_after < pos) slot = q;
+            if (ok && slot >= 0) {
+                snaps.push_back({j, dd, pos, slot, 0});
+                k = (int)snaps.size() - 1;
+                slot_owner[slot] = k;
             }
         }
         if (k < 0) {
