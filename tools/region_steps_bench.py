@@ -36,8 +36,8 @@ with GpuPhmm() as h:
         return best, h.stats(), r
 
     t_plain, s_plain, raw = timed(lambda: h.compute(mod))
-    t_reg, s_reg, res = timed(lambda: h.compute_regions(b, mapq, None, want_quals=False))
-    t_regq, s_regq, _ = timed(lambda: h.compute_regions(b, mapq, None, want_quals=True))
+    t_reg, s_reg, res = timed(lambda: h.compute_regions(b, mapq, None, want_quals=False, want_raw=False))
+    t_regq, s_regq, _ = timed(lambda: h.compute_regions(b, mapq, None, want_quals=True, want_raw=True))
 
 # CPU post steps on the device's raw likelihoods (bit-exact check + timing)
 t0 = time.perf_counter()
@@ -56,7 +56,7 @@ cells = s_plain["cells"]
 print("regions %d reads %d pairs %d cells %.3g" % (n_regions, n_reads, s_plain["pairs"], cells))
 print("gphmm_compute (qualities modified beforehand)      : %.1f ms  e2e %.0f GCUPS  launches %d" % (t_plain * 1e3, cells / t_plain / 1e9, s_plain["kernel_launches"]))
 print("gphmm_compute_regions (pre + post steps on device) : %.1f ms  e2e %.0f GCUPS  launches %d" % (t_reg * 1e3, cells / t_reg / 1e9, s_reg["kernel_launches"]))
-print("  ... also returning the three modified quality arrays: %.1f ms" % (t_regq * 1e3))
+print("  ... also returning the three modified quality arrays and the raw likelihoods: %.1f ms" % (t_regq * 1e3))
 print("CPU oracle (1 thread): modifyReadQualities %.2f us/read = %.1f ms for this batch; normalize+filter (python loop over units) %.1f ms"
       % (t_cpu_mod * 1e6, t_cpu_mod * n_reads * 1e3, t_cpu_post * 1e3))
 print("device result == oracle post steps on the device's likelihoods: %s; reads dropped %d of %d" % (ok, int((res["keep"] == 0).sum()), n_reads))
