@@ -969,8 +969,6 @@ struct gphmm {
 
 namespace {
 
-// Process chunks [ci, ...) of a batch on one device with two stream slots; chunks are claimed from a
-// shared cursor so that several devices drain the same batch (the host-side work queue of SURVEY 8e).
 // Host-side planning pool: chunk plans are built ahead of the GPU by a few threads (PairHMMNativeArguments.
 // maxNumberOfThreads -> gphmm_config.host_threads) and handed to the device loops in chunk order.
 struct PlanPool {

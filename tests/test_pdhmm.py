@@ -194,7 +194,7 @@ def test_pdhmm_special_cases():
         hmm.reset_stats()
         got, want = hmm.pd_compute(b, pd), _pd_oracle(b, pd)
         assert hmm.stats()["rescued_pairs"] >= 2 and want.min() < -300
-        _close(got, want, 1e-9 if False else 1e-4)
+        _close(got, want, 1e-4)
         assert np.abs(got[want < -100] - want[want < -100]).max() < 1e-9
         # a read base that is not ACGT on a SNP column: the reference throws (LoglessPDPairHMM.java:202)
         hap = np.frombuffer(b"ACGTACGTAC", dtype=np.uint8)
