@@ -418,6 +418,23 @@ def test_two_devices_one_process():
         assert np.array_equal(one.compute(b), two.compute(b))
 
 
+def test_two_devices_region_steps_and_queue():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from test_region_steps import _raw_batch
+    b, mapq = _raw_batch(77, n_units=40)
+    ref = np.zeros(len(b.units), np.int32)
+    with GpuPhmm(devices=[0]) as one, GpuPhmm(devices=[0, 1], chunk_cells=20_000_000) as two:
+        a, c = one.compute_regions(b, mapq, ref), two.compute_regions(b, mapq, ref)
+        for name in ("keep", "base_q", "ins_q", "del_q"):
+            assert np.array_equal(a[name], c[name]), name
+        assert np.abs(a["lk"] - c["lk"]).max() < 1e-5 and np.abs(a["raw"] - c["raw"]).max() < 1e-5
+        tickets = [two.submit_regions(b, mapq, ref) for _ in range(3)]
+        for t in tickets:
+            assert np.array_equal(two.wait(t)["keep"], a["keep"])
+
+
 def test_many_flat_quality_classes(hmm):
     # reads with flat (ins, del, gcp) triples: four classes get the constant-coefficient kernel, the rest and the
     # per-base reads fall back to the general kernel; every route must agree with the oracle
