@@ -556,7 +556,13 @@ int launch_chunk(Device &dev, DeviceChunk &dc, const ChunkPlan &c, cudaStream_t 
     int launches = 0;
     uint8_t *meta = (uint8_t *)dc.meta.p, *work = (uint8_t *)dc.work.p;
     uint32_t *counters = (uint32_t *)(work + dc.off_counters);
-    CK(cudaMemsetAsync(work + dc.off_counters, 0, (dc.off_err + 16) - dc.off_counters, st));
+    // counters and error flag start at 0; the keep flags and the alignment gaps of the downloaded block are cleared with them
+    // (compute-sanitizer initcheck then sees a fully initialised D2H source)
+    CK(cudaMemsetAsync(work + dc.off_keep, 0, (dc.off_err + 16) - dc.off_keep, st));
+    {
+        const size_t out_end = dc.off_out + (size_t)std::max<uint32_t>(c.n_pairs, 1) * 8;
+        if (dc.off_keep > out_end) CK(cudaMemsetAsync(work + out_end, 0, dc.off_keep - out_end, st));
+    }
     CK(cudaEventRecord(dc.ev_start, st));
 
     KernelArgs ka;
@@ -635,7 +641,10 @@ int launch_chunk(Device &dev, DeviceChunk &dc, const ChunkPlan &c, cudaStream_t 
             ++launches;
             if (opt.rs->hmm_base_q || opt.rs->hmm_ins_q || opt.rs->hmm_del_q) {
                 dc.h_modq.reserve(dc.read_stride * 3);
-                CK(cudaMemcpyAsync(dc.h_modq.p, (uint8_t *)dc.reads.p + dc.read_stride, dc.read_stride * 3, cudaMemcpyDeviceToHost, st));
+                const size_t span = (size_t)(c.base_hi - c.base_lo);  // without the alignment tail of each array
+                for (int a = 0; a < 3 && span; ++a)
+                    CK(cudaMemcpyAsync((uint8_t *)dc.h_modq.p + a * dc.read_stride, (uint8_t *)dc.reads.p + (a + 1) * dc.read_stride, span,
+                                       cudaMemcpyDeviceToHost, st));
             }
         }
         // 1. per-read flat-quality classification (device side; the host only sampled candidate classes)

@@ -133,7 +133,7 @@ int run_pd_batch(gphmm *h, const gphmm_batch *b, const uint8_t *hap_pd, double *
         h2d += (int64_t)(span * 5 + meta_bytes);
         uint8_t *meta = (uint8_t *)dev.pd_meta.p, *work = (uint8_t *)dev.pd_work.p;
         uint32_t *counters = (uint32_t *)(work + off_cnt);
-        CK(cudaMemsetAsync(work + off_cnt, 0, (off_err + 16) - off_cnt, st));
+        CK(cudaMemsetAsync(work + off_out + (size_t)n_pairs * 8, 0, (off_err + 16) - (off_out + (size_t)n_pairs * 8), st));  // alignment gap, counters, error flag
         CK(cudaEventRecord(dev.ev_step0, st));
         PdArgs pa;
         memset(&pa, 0, sizeof pa);

@@ -65,7 +65,7 @@ int run_sw_batch(gphmm *h, const gphmm_sw_batch *b, const gphmm_sw_params *prm, 
         dev.sw_bt.reserve(std::max<size_t>((size_t)bt * 2, 16));
         dev.sw_aux.reserve(std::max<size_t>((size_t)aux * 4, 16));
         CK(cudaMemcpyAsync(dev.sw_in.p, dev.sw_h_in.p, in_bytes, cudaMemcpyHostToDevice, st));
-        CK(cudaMemsetAsync((uint8_t *)dev.sw_out.p + off_cnt, 0, 16, st));
+        CK(cudaMemsetAsync(dev.sw_out.p, 0, off_cnt + 16, st));  // cursor; CIGAR slots beyond n_elems read back as 0
         CK(cudaEventRecord(dev.ev_step0, st));
         SwArgs a;
         memset(&a, 0, sizeof a);
