@@ -529,6 +529,37 @@ def test_likelihoods_near_the_double_underflow_limit(hmm, hmm64):
         _check(got, want, TOL)
 
 
+def test_closed_form_cases_of_the_reference_unit_test():
+    # PairHMMUnitTest.java:272-326 (one low-quality mismatch in every position, read centred in / hanging off the
+    # haplotype) and :390-418, 511-536 (an all-matching read: the likelihood is just the read's error probability);
+    # like the reference's test class with the tristate correction off (:34-38)
+    import math
+    with GpuPhmm(tristate_off=True) as hmm:
+        hap = b"TTCTCTTCTGTTGTGGCTGGTT"
+        reads, wants = [], []
+        for offset_end in (2, 0):
+            L = len(hap) - 2 - offset_end
+            for k in range(L):
+                quals = const_quals(L, 90)
+                quals[k] = 20
+                rd = bytearray(hap[2:2 + L])
+                rd[k] = ord("T") if rd[k] == ord("C") else ord("C")
+                gop = const_quals(L, 80)
+                reads.append((bytes(rd), quals, gop, gop, gop))
+                wants.append(math.log10(1.0 / len(hap) * (1 - 1e-9) ** (L - 1) * 1e-2))
+        got = hmm.compute(Batch.single_unit(reads, [hap]))
+        assert np.abs(got - np.array(wants)).max() <= 1e-2
+        for read_size in (1, 2, 5, 10):
+            for ref_size in (2, 5, 10, 20):
+                if ref_size <= read_size:
+                    continue
+                rd, ref = b"A" * read_size, b"A" * ref_size
+                got = hmm.compute(Batch.single_unit([(rd, const_quals(read_size, 20), const_quals(read_size, 100), const_quals(read_size, 100),
+                                                      const_quals(read_size, 100))], [ref]))
+                want = math.log10((abs(ref_size - read_size + 1) / ref_size) * 0.99 ** read_size)
+                assert abs(got[0] - want) <= 1e-3
+
+
 def test_full_size_config2_sample_against_oracle(hmm):
     # BASELINE.json configs[1] at full size (10 000 regions, ~6 M pairs, 5.8e11 cells): every output is a valid
     # log10 probability, the staged and the device-resident paths agree bit for bit, and a random sample of whole
