@@ -1124,13 +1124,17 @@ int run_batch(gphmm *h, const gphmm_batch *b, double *out, const gphmm_region_st
     validate_batch(b);
     if (b->n_units == 0) return GPHMM_OK;
     if (!out) throw Error(GPHMM_ERR_INVALID_ARG, "out is null");
-    auto chunks = split_units(b, h->chunk_cells(), h->chunk_bytes(), true);
+    // several devices drain one list of chunks: smaller chunks balance the end of the batch (unless the caller fixed the size)
+    const int64_t cells_per_chunk = h->cfg.chunk_cells > 0 ? h->chunk_cells() : h->chunk_cells() / (int64_t)std::min<size_t>(std::max<size_t>(h->devices.size(), 1), 4);
+    auto chunks = split_units(b, cells_per_chunk, h->chunk_bytes(), true);
     std::atomic<size_t> cursor{0};
     const size_t nd = h->devices.size();
     std::vector<std::string> errs(nd);
     std::vector<int> rcs(nd, GPHMM_OK);
     {
-        const int n_threads = h->cfg.host_threads > 0 ? h->cfg.host_threads : 4;  // GATK's --native-pair-hmm-threads default
+        // GATK's --native-pair-hmm-threads default is 4; one planner thread keeps about one B200 busy (12 us per configs[1]
+        // region on either side), so a handle over several devices asks for more when the caller did not say
+        const int n_threads = h->cfg.host_threads > 0 ? h->cfg.host_threads : std::max<int>(4, 3 * (int)h->devices.size());
         PlanPool pool(b, chunks, false, h->cfg.no_prefix_sharing == 0, n_threads, h->stats, rs && rs->pcr_rate_factor != 0.0);
         if (nd == 1 || chunks.size() == 1) {
             device_loop(h, *h->devices[0], b, chunks, pool, cursor, out, errs[0], rcs[0], rs);

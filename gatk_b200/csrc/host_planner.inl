@@ -120,7 +120,14 @@ UnitSched plan_unit_sharing(const gphmm_batch *b, const gphmm_unit &un, uint32_t
         const uint8_t *x = hap_ptr(order[i]), *y = hap_ptr(order[i + 1]);
         const uint32_t m = std::min(H, hap_len(order[i + 1]));
         uint32_t d = 0;
-        while (d < m && x[d] == y[d]) ++d;
+        while (d + 8 <= m) {  // eight bytes at a time
+            uint64_t wx, wy;
+            memcpy(&wx, x + d, 8); memcpy(&wy, y + d, 8);
+            if (wx != wy) { d += (uint32_t)(__builtin_ctzll(wx ^ wy) >> 3); break; }
+            d += 8;
+        }
+        if (d + 8 > m || x[d] == y[d])  // tail (or the loop ended without a difference)
+            while (d < m && x[d] == y[d]) ++d;
         lcp[i] = d;
         if (d < MIN_DEPTH) continue;
         int k = -1;
@@ -279,11 +286,11 @@ void plan_chunk(const gphmm_batch *b, int64_t u0, int64_t u1, bool force_fp64, b
     }
 
     // haplotype alphabet of the chunk: A C G T N are fixed codes, any other byte value gets the next free code
-    int16_t lut[256];
-    for (int i = 0; i < 256; ++i) lut[i] = -1;
+    uint8_t lut8[256];
+    memset(lut8, 0xff, sizeof lut8);
     memset(c.code_byte, 0, sizeof c.code_byte);
     const char fixed[5] = {'A', 'C', 'G', 'T', 'N'};
-    for (int i = 0; i < 5; ++i) { lut[(uint8_t)fixed[i]] = (int16_t)(CODE_FIRST_BASE + i); c.code_byte[CODE_FIRST_BASE + i] = (uint8_t)fixed[i]; }
+    for (int i = 0; i < 5; ++i) { lut8[(uint8_t)fixed[i]] = (uint8_t)(CODE_FIRST_BASE + i); c.code_byte[CODE_FIRST_BASE + i] = (uint8_t)fixed[i]; }
     c.n_codes = CODE_FIRST_BASE + 5;
 
     c.streams.clear(); c.hap_len.clear(); c.hap_stream_off.clear(); c.units.clear(); c.tasks.clear();
@@ -326,14 +333,22 @@ void plan_chunk(const gphmm_batch *b, int64_t u0, int64_t u1, bool force_fp64, b
                 c.hap_len.push_back(H);
                 c.hap_stream_off.push_back((uint32_t)w);
                 const uint8_t *src = b->hap_bases + ho;
-                for (uint32_t j = 0; j < H; ++j) {
-                    int16_t code = lut[src[j]];
-                    if (code < 0) {
-                        if (c.n_codes >= MAX_CODES) throw Error(GPHMM_ERR_ALPHABET, "too many distinct haplotype byte values");
-                        code = lut[src[j]] = (int16_t)c.n_codes;
-                        c.code_byte[c.n_codes++] = src[j];
+                // table lookup per byte with no branch in the loop; a byte value seen for the first time (0xff) is rare:
+                // give it a code and redo the haplotype
+                for (;;) {
+                    uint8_t unknown = 0;
+                    for (uint32_t j = 0; j < H; ++j) {
+                        const uint8_t code = lut8[src[j]];
+                        unknown |= (uint8_t)(code == 0xff);
+                        dst[w + j] = code;
                     }
-                    dst[w + j] = (uint8_t)code;
+                    if (!unknown) break;
+                    for (uint32_t j = 0; j < H; ++j)
+                        if (lut8[src[j]] == 0xff) {
+                            if (c.n_codes >= MAX_CODES) throw Error(GPHMM_ERR_ALPHABET, "too many distinct haplotype byte values");
+                            lut8[src[j]] = (uint8_t)c.n_codes;
+                            c.code_byte[c.n_codes++] = src[j];
+                        }
                 }
                 w += H;
                 dst[w++] = (uint8_t)CODE_END;
