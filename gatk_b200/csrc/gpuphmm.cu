@@ -1133,8 +1133,10 @@ int run_batch(gphmm *h, const gphmm_batch *b, double *out, const gphmm_region_st
     std::vector<int> rcs(nd, GPHMM_OK);
     {
         // GATK's --native-pair-hmm-threads default is 4; one planner thread keeps about one B200 busy (12 us per configs[1]
-        // region on either side), so a handle over several devices asks for more when the caller did not say
-        const int n_threads = h->cfg.host_threads > 0 ? h->cfg.host_threads : std::max<int>(4, 3 * (int)h->devices.size());
+        // region on either side), so a handle over several devices uses at least 3 per device
+        // (GATK passes its default of 4 explicitly: with several devices the floor applies to explicit values too)
+        const int asked = h->cfg.host_threads > 0 ? h->cfg.host_threads : 4;
+        const int n_threads = h->devices.size() > 1 ? std::max<int>(asked, 3 * (int)h->devices.size()) : asked;
         PlanPool pool(b, chunks, false, h->cfg.no_prefix_sharing == 0, n_threads, h->stats, rs && rs->pcr_rate_factor != 0.0);
         if (nd == 1 || chunks.size() == 1) {
             device_loop(h, *h->devices[0], b, chunks, pool, cursor, out, errs[0], rcs[0], rs);

@@ -55,7 +55,8 @@ typedef struct gphmm_config {
     int32_t n_devices;        /* 0: use the current CUDA device only; >0: devices[0..n) */
     const int32_t *devices;   /* CUDA ordinals, may be NULL when n_devices == 0 */
     int32_t force_fp64;       /* PairHMMNativeArguments.useDoublePrecision */
-    int32_t host_threads;     /* PairHMMNativeArguments.maxNumberOfThreads: staging threads, 0 = default */
+    int32_t host_threads;     /* PairHMMNativeArguments.maxNumberOfThreads: planner threads, 0 = 4; a handle over several
+                                 devices uses at least 3 per device */
     int32_t tristate_off;     /* PairHMM.doNotUseTristateCorrection() (tests only) */
     int32_t no_prefix_sharing; /* 1: recompute every haplotype from column 1 (A/B switch; results are bit-identical) */
     int64_t chunk_cells;      /* target DP cells per device chunk, 0 = default */
