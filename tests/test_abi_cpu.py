@@ -143,5 +143,17 @@ def test_planner_host_only():
     # every computed column is one step of lane 0; each unit's sweep drains 31 more steps
     assert steps(sp) == sp["total_columns"] + sp["passes"] + 31 * sp["units"]
     assert 0.15 < ss["skipped_columns"] / ss["total_columns"] < 0.6
+    # the near-depth rule of the snapshot planner: close to what the trie of the sorted haplotypes allows
+    trie = 0
+    for u in big.units:
+        haps = sorted(bytes(big.hap_bases[big.hap_off[h]:big.hap_off[h + 1]]) for h in range(int(u["hap_begin"]), int(u["hap_end"])))
+        prev = b""
+        for h in haps:
+            m = 0
+            while m < min(len(h), len(prev)) and h[m] == prev[m]:
+                m += 1
+            trie += m
+            prev = h
+    assert ss["skipped_columns"] <= trie and ss["skipped_columns"] >= 0.93 * trie
     assert steps(ss) < 0.9 * steps(sp)
     assert ss["checked_steps"] <= 32 * (ss["passes"] + ss["snapshots"]) + ss["units"]
