@@ -166,6 +166,50 @@ class CudaLoglessPairHMM:
         self._hmm.close()
 
 
+@dataclass
+class PartiallyDeterminedHaplotype:
+    """bases + PartiallyDeterminedHaplotype.getAlternateBases() (utils/haplotype/PartiallyDeterminedHaplotype.java:59-65:
+    SNP=1 DEL_START=2 DEL_END=4 A=8 C=16 G=32 T=64, one flag byte per base)"""
+    bases: bytes
+    alternate_bases: Sequence[int]
+
+
+class CudaLoglessPairPDHMM:
+    """Mirror of CudaLoglessPairPDHMM.java / VectorLoglessPairPDHMM.java:71-147 over gphmm_pd_compute.  The read-span filter
+    (rangeForReadOverlapToDeterminedBases) needs read and allele coordinates and stays with the caller, as in Java."""
+
+    def __init__(self, devices=None):
+        try:
+            self._hmm = GpuPhmm(devices=devices)
+        except GpuPhmmError as e:
+            if e.code == ERR_NO_DEVICE:
+                raise HardwareFeatureException("Machine does not support the CUDA PDHMM.") from e
+            raise
+        self.mLogLikelihoodArray = None
+
+    def computeLog10Likelihoods(self, logLikelihoods: LikelihoodMatrix, processedReads: List[Read], inputScoreImputator,
+                                alleles: List[PartiallyDeterminedHaplotype]):
+        if not processedReads:
+            return  # VectorLoglessPairPDHMM.java:77-79
+        rows = []
+        for r in processedReads:
+            ins, dele, gcp = inputScoreImputator.impute(r)
+            rows.append((r.bases, np.asarray(r.base_quals, dtype=np.uint8), ins, dele, gcp))
+        batch = Batch.single_unit(rows, [a.bases for a in alleles])
+        pd = np.concatenate([np.asarray(a.alternate_bases, dtype=np.uint8) for a in alleles])
+        self.mLogLikelihoodArray = self._hmm.pd_compute(batch, pd)
+        n = len(alleles)
+        for r in range(len(processedReads)):
+            for a in range(n):
+                logLikelihoods.set(a, r, self.mLogLikelihoodArray[r * n + a])
+
+    def getLogLikelihoodArray(self):
+        return self.mLogLikelihoodArray
+
+    def close(self):
+        self._hmm.close()
+
+
 class Implementation(enum.Enum):
     """PairHMM.Implementation (PairHMM.java:40-109).  Only the CUDA entry is constructible here; the Java/AVX entries
     belong to the reference and are listed so that the registry reads the same.  FASTEST_AVAILABLE does not include

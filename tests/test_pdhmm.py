@@ -207,3 +207,29 @@ def test_pdhmm_special_cases():
         assert e.value.code == native.ERR_INVALID_ARG
         with pytest.raises(ValueError):
             hmm.pd_compute(bad, pd[:5])
+
+
+@pytest.mark.gpu
+def test_pdhmm_plugin_mirror():
+    # the call PDPairHMMLikelihoodCalculationEngine makes through the plugin (VectorLoglessPairPDHMM.java:71-147)
+    from gatk_b200.pairhmm import (CudaLoglessPairPDHMM, LikelihoodMatrix, PartiallyDeterminedHaplotype, Read,
+                                   StandardPairHMMInputScoreImputator)
+    rng = np.random.default_rng(8)
+    hap = L[rng.integers(0, 4, 120)]
+    alleles = [PartiallyDeterminedHaplotype(hap.tobytes(), random_pd(rng, 120, 4)), PartiallyDeterminedHaplotype(hap[:100].tobytes(), random_pd(rng, 100, 2))]
+    reads = [Read(hap[o:o + 60].tobytes(), rng.integers(10, 41, 60).astype(np.uint8)) for o in (0, 17, 40, 60)]
+    hmm = CudaLoglessPairPDHMM()
+    try:
+        hmm.computeLog10Likelihoods(LikelihoodMatrix([], 0), [], StandardPairHMMInputScoreImputator(10), alleles)
+        assert hmm.getLogLikelihoodArray() is None
+        matrix = LikelihoodMatrix([a.bases for a in alleles], len(reads))
+        hmm.computeLog10Likelihoods(matrix, reads, StandardPairHMMInputScoreImputator(10), alleles)
+    finally:
+        hmm.close()
+    la = hmm.getLogLikelihoodArray()
+    assert la.shape == (8,)
+    for r, read in enumerate(reads):
+        for a, allele in enumerate(alleles):
+            want = oracle.pd_logless(allele.bases, allele.alternate_bases, read.bases, read.base_quals, np.full(60, 45, np.uint8),
+                                     np.full(60, 45, np.uint8), np.full(60, 10, np.uint8))
+            assert abs(la[r * 2 + a] - want) <= 1e-4 and matrix.values[a, r] == la[r * 2 + a]
