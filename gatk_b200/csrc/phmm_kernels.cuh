@@ -26,11 +26,16 @@
 //                                     the fp64 redo of reads that are not flat-quality.
 //   phmm_fast_f32_kernel<K>           per-base qualities, reads <= 254 bases: rotation hand-off, accumulator row,
 //                                     branch-free step loop, host-planned schedule with haplotype-prefix sharing.
-//   phmm_flat_f32_kernel<K>           the same for reads with flat insertion/deletion/GCP qualities: transition
+//   phmm_flat_f32_kernel<K,SYM>       the same for reads with flat insertion/deletion/GCP qualities: transition
 //                                     coefficients are kernel parameters (constant / uniform-register operands).
+//                                     SYM: ins == del per base with a flat GCP (the PCR indel model): two per-row
+//                                     coefficients left, the rest still constant operands.
 //   phmm_flat_f64_kernel              fp64 redo of flat-quality reads (one read x one haplotype per task).
-//   phmm_classify_kernel              per read: flat-quality class or general.
-//   phmm_epilogue_f32 / _rescue       raw sums -> log10 likelihoods; builds / consumes the fp64 redo list.
+//   phmm_classify_kernel              per read: flat class, symmetric class or general.
+//   phmm_epilogue_f32 / _rescue       raw sums -> log10 likelihoods; builds / consumes the fp64 redo list; the rescue
+//                                     epilogue puts sums it cannot trust on the deep list.
+//   phmm_exact_f64_kernel             last tier: the reference's own unscaled arithmetic for the deep list.
+// The kernels of the rows built around this path live in region_steps.cuh, pdhmm_kernels.cuh and sw_kernels.cuh.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
