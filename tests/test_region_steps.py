@@ -370,3 +370,45 @@ def test_region_pipeline_keeps_order_and_results():
             assert np.abs(res["lk"] - want["lk"]).max() < 1e-5
         with pytest.raises(ValueError):
             RegionPipeline(hmm, lookahead=0)
+
+
+@pytest.mark.gpu
+def test_region_steps_edge_shapes():
+    # units without reads / without haplotypes, a zero-length read, 1-base reads, a single haplotype (no normalisation:
+    # AlleleLikelihoods.java:427-431), an empty batch
+    e = np.zeros(0, np.uint8)
+    q1 = lambda n, v: np.full(n, v, np.uint8)
+    reads = [(b"A", q1(1, 30), q1(1, 45), q1(1, 45), q1(1, 10)),
+             (b"ACGTACGTACGTACGTACGTACGTACGTACGTACGT", q1(36, 25), q1(36, 40), q1(36, 40), q1(36, 10)),
+             (b"", e, e, e, e),
+             (b"TTTTTTTTTTTTTTTT", q1(16, 12), q1(16, 45), q1(16, 45), q1(16, 10))]
+    haps = [b"A", b"ACGT", b"ACGTACGTACGTACGTACGTACGTACGTACGTACGTACGTACGT"]
+    one = Batch.single_unit(reads, haps)
+    units = np.array([(0, 0, 0, 3, 0), (0, 4, 0, 0, 0), (0, 4, 0, 3, 0), (1, 4, 2, 3, 12), (0, 2, 0, 1, 15)], dtype=native.UNIT_DTYPE)
+    b = Batch(one.read_bases, one.base_q, one.ins_q, one.del_q, one.gcp, one.read_off, one.hap_bases, one.hap_off, units)
+    mapq = np.array([60, 20, 60, 60], np.uint8)
+    ref = np.array([0, -1, 1, 0, 0], np.int32)
+    with GpuPhmm() as hmm:
+        got = hmm.compute_regions(b, mapq, ref, pcr_rate_factor=2.0)
+        q, i, d = oracle.modify_reads(b.read_bases, b.base_q, b.ins_q, b.del_q, b.read_off, mapq, 2.0)
+        assert np.array_equal(got["base_q"], q) and np.array_equal(got["ins_q"], i) and np.array_equal(got["del_q"], d)
+        for k, u in enumerate(units):
+            r0, r1, h0, h1, o = (int(u[x]) for x in ("read_begin", "read_end", "hap_begin", "hap_end", "out_off"))
+            nr, nh = r1 - r0, h1 - h0
+            if nr == 0 or nh == 0:
+                continue
+            raw = got["raw"][o:o + nr * nh]
+            norm = oracle.normalize(raw, nr, nh, int(ref[k]), -4.5, False)
+            assert np.array_equal(got["lk"][o:o + nr * nh], norm, equal_nan=True), k
+        # flags of the last unit that owns each read (units must not share reads in production; here 4 writes reads 0-1, 3 writes 1-3)
+        last = {0: 4, 1: 4, 2: 3, 3: 3}
+        for r, k in last.items():
+            u = units[k]
+            r0, r1, h0, h1, o = (int(u[x]) for x in ("read_begin", "read_end", "hap_begin", "hap_end", "out_off"))
+            nr, nh = r1 - r0, h1 - h0
+            norm = oracle.normalize(got["raw"][o:o + nr * nh], nr, nh, int(ref[k]), -4.5, False)
+            keep = oracle.filter_poorly_modeled(norm, nr, nh, q, b.read_off[r0:r1 + 1])
+            assert got["keep"][r] == keep[r - r0], (r, k)
+        empty = Batch(e, e, e, e, e, [0], e, [0], np.zeros(0, dtype=native.UNIT_DTYPE))
+        res = hmm.compute_regions(empty, e, None)
+        assert res["lk"].size == 0 and res["keep"].size == 0
