@@ -732,13 +732,16 @@ int launch_chunk(Device &dev, DeviceChunk &dc, const ChunkPlan &c, cudaStream_t 
                     const int qi = c.class_qi[cl], qd = c.class_qd[cl], qc = c.class_qc[cl];
                     const double ei = tb.eps[qi], ed = tb.eps[qd], ec = tb.eps[qc], tIM = 1.0 - ec;
                     const int mn = std::min(qi, qd), mx = std::max(qi, qd);
-                    fc.a = (float)tb.m2m[((mx * (mx + 1)) >> 1) + mn];
-                    fc.b = (float)(tIM * ei);
-                    fc.c = (float)(tIM * ed);
+                    // tMM is folded into the kernel's prior table and divides the other coefficients of the match update
+                    // (plan_chunk registers no flat class with tMM = 0)
+                    const double a = tb.m2m[((mx * (mx + 1)) >> 1) + mn];
+                    fc.a = (float)a;
+                    fc.b = (float)(tIM * ei / a);
+                    fc.c = (float)(tIM * ed / a);
                     fc.g = (float)ec;
                     fc.d = (float)ec;
                     fc.tmi = (float)ei;
-                    fc.tim = (float)tIM;
+                    fc.tim = (float)(tIM / a);
                     fc.class_id = (uint32_t)cl;
                     fc.qi = qi; fc.qd = qd; fc.qc = qc;
                     ka.counter = counters + 16 + 8 * cl + k;

@@ -268,7 +268,9 @@ void plan_chunk(const gphmm_batch *b, int64_t u0, int64_t u1, bool force_fp64, b
             } else if (sym) {
                 sym = qi <= SYM_MAX_GAP_QUAL;
             }
-            if (flat && !(pcr_hint && qi == qd)) {  // the PCR indel model (region steps) will lower ins and del together
+            // (a flat class needs tMM > 0: the kernels factor it out of the match update)
+            const bool tmm_positive = tables().m2m[((std::max(qi, qd) * (std::max(qi, qd) + 1)) >> 1) + std::min(qi, qd)] > 0.0;
+            if (flat && tmm_positive && !(pcr_hint && qi == qd)) {  // the PCR indel model (region steps) will lower ins and del together
                 bool seen = false;
                 for (int k = 0; k < c.n_classes; ++k) seen = seen || (c.class_qi[k] == qi && c.class_qd[k] == qd && c.class_qc[k] == qc);
                 if (seen) continue;

@@ -382,7 +382,7 @@ template <int K> __device__ __forceinline__ void snap_restore(FastState<K> &st, 
 // run while no lane of the warp sits on an END column, which the caller guarantees from the haplotype
 // lengths -- that loop is branch-free.
 template <int K, bool CHECKED>
-__device__ __forceinline__ void fast_step(FastState<K> &st, const float (&ca)[K], const float (&cb)[K], const float (&cc)[K],
+__device__ __forceinline__ void fast_step(FastState<K> &st, const float (&cb)[K], const float (&cc)[K],
                                           const float (&cg)[K], const float (&cd)[K], uint32_t tab_lane, int src_lane, int lane,
                                           int acc_lane, int acc_slot, float c0, float *sums_task, float *slab, int snap_pos,
                                           int snap_slot, int end_restore, uint32_t end_out)
@@ -404,18 +404,18 @@ __device__ __forceinline__ void fast_step(FastState<K> &st, const float (&ca)[K]
             pr[v * 4 + 0] = q.x; pr[v * 4 + 1] = q.y; pr[v * 4 + 2] = q.z; pr[v * 4 + 3] = q.w;
         }
     }
+    // M = (prior * a) * (M_diag + (b/a) * I~_diag + (c/a) * D~_diag): tMM is folded into the prior table and into b, c,
+    // so the match update is 2 FFMA + 1 FMUL (5 FP instructions per cell in all)
     float Mn[K];
     {
-        float u = cc[0] * st.dgd;
+        float u = __fmaf_rn(cc[0], st.dgd, st.dgm);
         u = __fmaf_rn(cb[0], st.dgi, u);
-        u = __fmaf_rn(ca[0], st.dgm, u);
         Mn[0] = pr[0] * u;
     }
 #pragma unroll
     for (int k = 1; k < K; ++k) {
-        float u = cc[k] * st.D[k - 1];
+        float u = __fmaf_rn(cc[k], st.D[k - 1], st.M[k - 1]);
         u = __fmaf_rn(cb[k], st.I[k - 1], u);
-        u = __fmaf_rn(ca[k], st.M[k - 1], u);
         Mn[k] = pr[k] * u;
     }
 #pragma unroll
@@ -472,7 +472,7 @@ __global__ void __launch_bounds__(32) phmm_fast_f32_kernel(const KernelArgs g)
         const float c0 = (float)scalbn(1.0, t.c0_exp);
         const int acc_lane = R / K, acc_slot = R % K;  // accumulator row = 0-based row R
 
-        float ca[K], cb[K], cc[K], cg[K], cd[K];
+        float cb[K], cc[K], cg[K], cd[K];
         __syncwarp();
 #pragma unroll
         for (int k = 0; k < K; ++k) {
@@ -502,15 +502,18 @@ __global__ void __launch_bounds__(32) phmm_fast_f32_kernel(const KernelArgs g)
                 }
                 DD = ec;
                 const double e = c_eps[q];
-                pm = 1.0 - e;
-                px = g.tristate_off ? e : e / 3.0;
-            } else if (i == R + 1) {  // accumulator row
-                A = 1.0;
+                // tMM goes into the priors and divides b and c.  tMM = 0 (insertion + deletion error >= 1, qualities <= 3)
+                // cannot be factored out: NaN coefficients poison the sums and the pairs are redone by the fp64 kernels
+                const double inv = A > 0.0 ? 1.0 / A : __longlong_as_double(0x7ff8000000000000LL);
+                pm = (1.0 - e) * A;
+                px = (g.tristate_off ? e : e / 3.0) * A;
+                B *= inv; C *= inv;
+            } else if (i == R + 1) {  // accumulator row: M_acc = 1 * (M_R + tMI_R * I~_R) = (M + I)[R]
                 B = R >= 1 ? c_eps[min((uint32_t)g.rd_i[ro + R - 1], 127u)] : 0.0;
                 DD = 1.0;
             }
             if (lane == 31 && k == K - 1) DD = 1.0;  // carrier of the virtual row 0: keeps D~ = c0
-            ca[k] = (float)A; cb[k] = (float)B; cc[k] = (float)C; cg[k] = (float)G; cd[k] = (float)DD;
+            cb[k] = (float)B; cc[k] = (float)C; cg[k] = (float)G; cd[k] = (float)DD;
             const float pmf = (float)pm, pxf = (float)px;
             for (int y = 0; y < n_codes; ++y) {
                 float v = 0.f;
@@ -547,12 +550,12 @@ __global__ void __launch_bounds__(32) phmm_fast_f32_kernel(const KernelArgs g)
             const Segment seg = g.segments[us.seg_first + sg];
 #pragma unroll 2
             for (uint32_t s = 0; s < seg.n_free; ++s)
-                fast_step<K, false>(st, ca, cb, cc, cg, cd, tab_lane, src_lane, lane, acc_lane, acc_slot, c0, sums_task, slab, 0, 0, 0, 0);
+                fast_step<K, false>(st, cb, cc, cg, cd, tab_lane, src_lane, lane, acc_lane, acc_slot, c0, sums_task, slab, 0, 0, 0, 0);
             step += (int)seg.n_free;
             st.p = step - lane;
 #pragma unroll 1
             for (uint32_t s = 0; s < seg.n_chk; ++s)
-                fast_step<K, true>(st, ca, cb, cc, cg, cd, tab_lane, src_lane, lane, acc_lane, acc_slot, c0, sums_task, slab, seg.snap_pos,
+                fast_step<K, true>(st, cb, cc, cg, cd, tab_lane, src_lane, lane, acc_lane, acc_slot, c0, sums_task, slab, seg.snap_pos,
                                    seg.snap_slot, seg.end_restore, seg.end_out);
             step += (int)seg.n_chk;
         }
@@ -575,9 +578,9 @@ __global__ void __launch_bounds__(32) phmm_fast_f32_kernel(const KernelArgs g)
 //    parameter (the task's R picks the loop instance; warp-uniform switch outside the loops).
 // ---------------------------------------------------------------------------------------------
 struct FlatCoef {
-    float a, b, c, g, d;  // tMM, tIM*tMI, tIM*tMD, tII (= tII*tMI/tMI), tDD
+    float a, b, c, g, d;  // tMM (folded into the priors), tIM*tMI/tMM, tIM*tMD/tMM, tII (= tII*tMI/tMI), tDD
     float tmi;            // tMI: I = tMI * I~
-    float tim;            // tIM: row 1 sees c = tIM (tMD_0 = 1)
+    float tim;            // tIM/tMM: row 1 sees c = tIM (tMD_0 = 1)
     uint32_t class_id;    // reads whose read_class equals this are ours
     uint32_t qi, qd, qc;
 };
@@ -644,19 +647,19 @@ __device__ __forceinline__ void flat_step(FastState<K> &st, const FlatCoef &f, c
             pr[v * 4 + 0] = q.x; pr[v * 4 + 1] = q.y; pr[v * 4 + 2] = q.z; pr[v * 4 + 3] = q.w;
         }
     }
+    // The coefficient of M_diag is folded into the prior table and divides the other two (see fast_step): the match
+    // update is 2 FFMA + 1 FMUL.  SYM: the coefficients of I^ and D^ are per-row registers (A, C), the rest constant operands.
     float Mn[K];
     {
-        // SYM: the coefficients of M^ and D^ are per-row registers (A, C); everything else stays a constant operand
         float u = __fmaf_rn(SYM ? C[0] : f.c, st.dgd, E0);
         u = __fmaf_rn(B0, st.dgi, u);
-        u = __fmaf_rn(SYM ? A[0] : f.a, st.dgm, u);
+        u += st.dgm;
         Mn[0] = pr[0] * u;
     }
 #pragma unroll
     for (int k = 1; k < K; ++k) {
-        float u = (SYM ? C[k] : f.c) * st.D[k - 1];
-        u = __fmaf_rn(f.b, st.I[k - 1], u);
-        u = __fmaf_rn(SYM ? A[k] : f.a, st.M[k - 1], u);
+        float u = __fmaf_rn(SYM ? C[k] : f.c, st.D[k - 1], st.M[k - 1]);
+        u = __fmaf_rn(SYM ? A[k] : f.b, st.I[k - 1], u);
         Mn[k] = pr[k] * u;
     }
 #pragma unroll
@@ -768,11 +771,16 @@ __global__ void __launch_bounds__(32, SYM ? 22 : 28) phmm_flat_f32_kernel(const 
                     const double eps_i = c_eps[qe];
                     const double eps_prev = i > 1 ? c_eps[min((uint32_t)g.rd_i[ro + i - 2], 127u)] : 1.0;
                     const double eps_next = i < R ? c_eps[min((uint32_t)g.rd_i[ro + i], 127u)] : kappa;
-                    A[k] = (float)(__ldg(g.m2m + ((qe * (qe + 1)) >> 1) + qe) / eps_i);
-                    C[k] = (float)(T * eps_prev / eps_i);
-                    double scale = eps_next;
-                    if (i == 1) scale *= T / kappa;  // row 1: u is the injected constant E0 = c0 = kappa/T * (C_1 D^_0)
+                    // with A_i factored out of the bracket:  M^_i = (p_ij eps_{i+1} A_i) (M^_diag + (T/A_i) I^_diag + (C_i/A_i) D^_diag)
+                    const double Ai = __ldg(g.m2m + ((qe * (qe + 1)) >> 1) + qe) / eps_i;
+                    const double inv = Ai > 0.0 ? 1.0 / Ai : __longlong_as_double(0x7ff8000000000000LL);  // tMM = 0: poison -> fp64 redo
+                    A[k] = (float)(T * inv);
+                    C[k] = (float)(T * eps_prev / eps_i * inv);
+                    double scale = eps_next * Ai;
+                    if (i == 1) scale = eps_next * T / kappa;  // row 1: the bracket is the injected constant E0 = c0
                     pm *= scale; px *= scale;
+                } else {
+                    pm *= (double)f.a; px *= (double)f.a;  // flat: tMM folded into the priors; f.b, f.c, f.tim arrive divided by it
                 }
                 pmf = (float)pm;
                 pxf = (float)px;
@@ -799,7 +807,7 @@ __global__ void __launch_bounds__(32, SYM ? 22 : 28) phmm_flat_f32_kernel(const 
         st.sp = g.sstreams + us.sstream_off - lane;
         st.y = ldg_u8(st.sp);
         // slot 0: lane 0 holds row 1 (virtual row 0 above it: M = I~ = 0, c*D~ = tIM*c0; SYM: f.tim = 1, the rest is in row 1's table)
-        const float B0 = lane == 0 ? 0.f : f.b;
+        const float B0 = lane == 0 ? 0.f : (SYM ? A[0] : f.b);
         const float G0 = lane == 0 ? 0.f : f.g;
         const float E0 = lane == 0 ? f.tim * c0 : 0.f;
         const int acc_lane = (R - 1) / K, acc_slot = (R - 1) % K;
