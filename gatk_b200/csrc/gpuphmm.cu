@@ -514,7 +514,7 @@ int launch_rescue(Device &dev, DeviceChunk &dc, const ChunkPlan &c, KernelArgs k
                 const double ei = tb2.eps[qi], ed = tb2.eps[qd], ec = tb2.eps[qc], tIM = 1.0 - ec;
                 const int mn = std::min(qi, qd), mx = std::max(qi, qd);
                 fd.a = tb2.m2m[((mx * (mx + 1)) >> 1) + mn];
-                fd.b = tIM * ei; fd.c = tIM * ed; fd.g = ec; fd.d = ec; fd.tmi = ei; fd.tim = tIM;
+                fd.b = tIM * ei / fd.a; fd.c = tIM * ed / fd.a; fd.g = ec; fd.d = ec; fd.tmi = ei; fd.tim = tIM / fd.a;  // tMM folded into the priors
                 fd.class_id = (uint32_t)cl; fd.qi = qi; fd.qd = qd; fd.qc = qc;
                 const KernelInfo &kf = dev.info(FLAT_F64_KEY, c.n_codes);
                 ka.counter = counters + 12 + cl;

@@ -153,6 +153,9 @@ __global__ void __launch_bounds__(32) phmm_forward_kernel(const KernelArgs g)
     constexpr int KT = NV * W;
     constexpr unsigned FULL = 0xffffffffu;
     constexpr int ROWS_PER_STRIP = 32 * K;
+    // fp32: tMM folded into the prior table (5 FP instructions per cell, tMM = 0 poisons the pair); fp64: the redo tier keeps
+    // the multiply so that every legal quality, tMM = 0 included, is handled here and not by the one-thread-per-pair tier
+    constexpr bool FOLD = sizeof(T) == 4;
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     V *tab = reinterpret_cast<V *>(smem_raw);
@@ -215,6 +218,12 @@ __global__ void __launch_bounds__(32) phmm_forward_kernel(const KernelArgs g)
                     const double e = c_eps[q];
                     pm = 1.0 - e;
                     px = g.tristate_off ? e : e / 3.0;
+                    if (FOLD) {
+                        // tMM = 0 cannot be factored out: NaN coefficients, the pair is redone in double, where the multiply stays
+                        const double inv = A > 0.0 ? 1.0 / A : __longlong_as_double(0x7ff8000000000000LL);
+                        pm *= A; px *= A;
+                        B *= inv; C *= inv;
+                    }
                 } else if (i == R + 1) {
                     G = R >= 1 ? c_eps[min((uint32_t)g.rd_i[ro + R - 1], 127u)] : 1.0;
                 }
@@ -268,18 +277,28 @@ __global__ void __launch_bounds__(32) phmm_forward_kernel(const KernelArgs g)
                 }
                 // M of column p from column p-1 (old M/I/D of the row above)
                 T Mn[K];
-                {
+                if (FOLD) {  // tMM is folded into the prior table and divides b, c (see fast_step)
+                    T u = fma_(cc[0], dgd, dgm);
+                    u = fma_(cb[0], dgi, u);
+                    Mn[0] = pr[0] * u;
+#pragma unroll
+                    for (int k = 1; k < K; ++k) {
+                        u = fma_(cc[k], D[k - 1], M[k - 1]);
+                        u = fma_(cb[k], I[k - 1], u);
+                        Mn[k] = pr[k] * u;
+                    }
+                } else {
                     T u = cc[0] * dgd;
                     u = fma_(cb[0], dgi, u);
                     u = fma_(ca[0], dgm, u);
                     Mn[0] = pr[0] * u;
-                }
 #pragma unroll
-                for (int k = 1; k < K; ++k) {
-                    T u = cc[k] * D[k - 1];
-                    u = fma_(cb[k], I[k - 1], u);
-                    u = fma_(ca[k], M[k - 1], u);
-                    Mn[k] = pr[k] * u;
+                    for (int k = 1; k < K; ++k) {
+                        u = cc[k] * D[k - 1];
+                        u = fma_(cb[k], I[k - 1], u);
+                        u = fma_(ca[k], M[k - 1], u);
+                        Mn[k] = pr[k] * u;
+                    }
                 }
                 // D~ of column p from column p-1 of the same row
 #pragma unroll
@@ -864,18 +883,17 @@ __device__ __forceinline__ void flat64_step(F64State &st, const FlatCoefD &f, do
             pr[2 * v] = q.x; pr[2 * v + 1] = q.y;
         }
     }
-    double Mn[K];
+    double Mn[K];  // tMM is folded into the prior table and divides b, c (see fast_step): 5 DFMA-pipe instructions per cell
     {
         double u = __fma_rn(f.c, st.dgd, E0);
         u = __fma_rn(B0, st.dgi, u);
-        u = __fma_rn(f.a, st.dgm, u);
+        u += st.dgm;
         Mn[0] = pr[0] * u;
     }
 #pragma unroll
     for (int k = 1; k < K; ++k) {
-        double u = f.c * st.D[k - 1];
+        double u = __fma_rn(f.c, st.D[k - 1], st.M[k - 1]);
         u = __fma_rn(f.b, st.I[k - 1], u);
-        u = __fma_rn(f.a, st.M[k - 1], u);
         Mn[k] = pr[k] * u;
     }
 #pragma unroll
@@ -951,8 +969,8 @@ __global__ void __launch_bounds__(32) phmm_flat_f64_kernel(const KernelArgs g, c
                 if (q > (uint32_t)MAX_QUAL) { atomicExch(g.err, 1); q = MAX_QUAL; }  // QualityUtils.java:157 (forced-fp64 mode has no fp32 pass to flag it)
                 x = g.rd_bases[ro + i - 1];
                 const double e = c_eps[q];
-                pm = 1.0 - e;
-                px = g.tristate_off ? e : e / 3.0;
+                pm = (1.0 - e) * f.a;
+                px = (g.tristate_off ? e : e / 3.0) * f.a;
             }
             for (int y = 0; y < n_codes; ++y) {
                 double v = 0.0;
