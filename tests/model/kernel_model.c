@@ -8,11 +8,13 @@
  * exists.  See DESIGN.md "Kernel recurrence".
  *
  *   I~[i][j] = I[i][j] / tMI_i          D~[i][j] = D[i][j] / tMD_i
- *   u        = a_i*M[i-1][j-1] + b_i*I~[i-1][j-1] + c_i*D~[i-1][j-1]      M[i][j] = prior*u
+ *   u        = M[i-1][j-1] + b'_i*I~[i-1][j-1] + c'_i*D~[i-1][j-1]         M[i][j] = (prior*tMM_i)*u
  *   D~[i][j] = M[i][j-1] + tDD_i*D~[i][j-1]
  *   I~[i][j] = M[i-1][j] + g_i*I~[i-1][j]
- *   a=tMM_i  b=tIM_i*tMI_{i-1}  c=tIM_i*tMD_{i-1}  g=tII_i*tMI_{i-1}/tMI_i   (tMI_0=tMD_0=1)
- * Pad rows below the read: a=b=c=tDD=0, prior=0, g=tMI_R for row R+1 and 1 after it, so the last
+ *   b'=tIM_i*tMI_{i-1}/tMM_i  c'=tIM_i*tMD_{i-1}/tMM_i  g=tII_i*tMI_{i-1}/tMI_i   (tMI_0=tMD_0=1)
+ * (5 FP instructions per cell; tMM = 0 is not representable in this form -- the kernels redo such pairs in fp64 --
+ * and the model returns -2 for it.)
+ * Pad rows below the read: b'=c'=tDD=0, prior=0, g=tMI_R for row R+1 and 1 after it, so the last
  * row of the strip holds (M+I)[R][j].
  */
 #include <math.h>
@@ -49,9 +51,10 @@ int NAME(model_task)(const double *eps, const double *m2m, const uint8_t *read, 
             const int mn = qi < qd ? qi : qd, mx = qi < qd ? qd : qi;
             const double tIM = 1.0 - ec;
             A = m2m[((mx * (mx + 1)) >> 1) + mn];
-            B = tIM * tmi_prev; C = tIM * tmd_prev; G = ec * tmi_prev / ei; DD = ec;
+            if (!(A > 0.0)) { free(a); return -2; }
+            B = tIM * tmi_prev / A; C = tIM * tmd_prev / A; G = ec * tmi_prev / ei; DD = ec;
             const double e = eps[bq[i - 1]];
-            PM = 1.0 - e; PX = tristate_off ? e : e / 3.0;
+            PM = (1.0 - e) * A; PX = (tristate_off ? e : e / 3.0) * A;
         } else if (i == R + 1) {
             G = R >= 1 ? eps[iq[R - 1]] : 1.0;
         }
@@ -77,9 +80,8 @@ int NAME(model_task)(const double *eps, const double *m2m, const uint8_t *read, 
                     const uint8_t x = read[i - 1];
                     prior = (x == y || x == 'N' || y == 'N') ? pm[i - 1] : px[i - 1];
                 }
-                real u = c[i - 1] * Dp[i - 1];
+                real u = FMA(c[i - 1], Dp[i - 1], Mp[i - 1]);
                 u = FMA(b[i - 1], Ip[i - 1], u);
-                u = FMA(a[i - 1], Mp[i - 1], u);
                 Mc[i] = prior * u;
                 Dc[i] = FMA(dd[i - 1], Dp[i], Mp[i]);
                 Ic[i] = FMA(g[i - 1], Ic[i - 1], Mc[i - 1]);

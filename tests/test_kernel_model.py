@@ -1,0 +1,93 @@
+"""CPU model of the kernels' reformulated 5-instruction recurrence (tests/model/kernel_model.c) against the oracle.
+
+No GPU: this bounds, on the build box, the fp32 error of the arithmetic the CUDA kernels perform (scaled I~/D~ states,
+tMM folded into the prior table, power-of-two initial condition) on the reference's own fixtures. The model is test
+infrastructure -- it is neither the oracle nor product code.
+"""
+import ctypes
+import math
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import oracle
+from phmm_testutil import load_hmmresults, load_testdata
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = os.path.join(HERE, "model", "kernel_model.c")
+MAX_Q = 254
+F32_C0_EXP = 116      # DESIGN.md "Kernel recurrence": D[0][j] = 2^(116 - ceil(log2 Hmax)) in fp32
+F64_C0_EXP = 960
+BAR = 1e-4            # north_star: within 1e-4 absolute of LoglessPairHMM
+
+
+def _build(double):
+    out = os.path.join(HERE, "model", "libkernel_model_%s.so" % ("f64" if double else "f32"))
+    if not os.path.exists(out) or os.path.getmtime(out) < os.path.getmtime(SRC):
+        cmd = ["gcc", "-O2", "-fPIC", "-shared", "-ffp-contract=off", "-o", out, SRC, "-lm"]
+        if double:
+            cmd.insert(1, "-DMODEL_DOUBLE")
+        subprocess.check_call(cmd)
+    return ctypes.CDLL(out)
+
+
+@pytest.fixture(scope="module")
+def tables():
+    eps = np.array([oracle.qual_to_error_prob(q) for q in range(256)], dtype=np.float64)
+    m2m = np.zeros(((MAX_Q + 1) * (MAX_Q + 2)) // 2, dtype=np.float64)
+    for mx in range(MAX_Q + 1):
+        for mn in range(mx + 1):
+            m2m[((mx * (mx + 1)) >> 1) + mn] = oracle.match_to_match_prob(mn, mx)
+    return eps, m2m
+
+
+def _model(lib, double, tables, rec):
+    eps, m2m = tables
+    real = ctypes.c_double if double else ctypes.c_float
+    fn = lib.model_task_f64 if double else lib.model_task_f32
+    fn.restype = ctypes.c_int
+    read = np.frombuffer(rec["read"], dtype=np.uint8)
+    hap = np.frombuffer(rec["hap"], dtype=np.uint8)
+    R, H = len(read), len(hap)
+    c0_exp = (F64_C0_EXP if double else F32_C0_EXP) - max(0, math.ceil(math.log2(max(H, 1))))
+    hap_off = np.array([0, H], dtype=np.int32)
+    out = (real * 1)()
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    rows = ((R + 1 + 31) // 32) * 32
+    q = [np.ascontiguousarray(rec[k], dtype=np.uint8) for k in ("base_q", "ins_q", "del_q", "gcp")]
+    rc = fn(p(eps), p(m2m), p(read), p(q[0]), p(q[1]), p(q[2]), p(q[3]), ctypes.c_int(R), ctypes.c_int(rows),
+            p(hap), p(hap_off), ctypes.c_int(1), ctypes.c_int(c0_exp), ctypes.c_int(0), out)
+    if rc == -2:
+        return None            # tMM = 0: the kernels redo such pairs with the general fp64 kernel
+    assert rc == 0
+    s = float(out[0])
+    if not (s > 0.0) or math.isinf(s):
+        return float("nan")    # the kernels treat this like an under-flow: fp64 redo
+    return math.log10(s) - c0_exp * math.log10(2.0) - math.log10(H)   # initial condition c0 instead of 2^1020/H
+
+
+def _fixtures():
+    return load_testdata() + load_hmmresults()
+
+
+@pytest.mark.parametrize("double", [False, True])
+def test_model_within_bar_of_oracle(tables, double):
+    lib = _build(double)
+    worst, redo, n = 0.0, 0, 0
+    for rec in _fixtures():
+        if len(rec["read"]) == 0 or len(rec["hap"]) == 0:
+            continue
+        want = oracle.logless(rec["hap"], rec["read"], rec["base_q"], rec["ins_q"], rec["del_q"], rec["gcp"])
+        got = _model(lib, double, tables, rec)
+        if got is None or math.isnan(got):
+            redo += 1
+            assert not double or got is None, "fp64 model under-/over-flowed on a fixture"
+            continue
+        n += 1
+        worst = max(worst, abs(got - want))
+    assert n > 100
+    assert worst < (BAR if not double else 1e-9), worst
+    # the fp32 form may send a few fixtures to the fp64 redo, never the bulk of them
+    assert redo <= n // 10, (redo, n)
