@@ -19,6 +19,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <deque>
+#include <functional>
 #include <map>
 #include <memory>
 #include <mutex>
@@ -1359,6 +1360,19 @@ static int submit_job(gphmm_t *h, const gphmm_batch *b, const gphmm_region_steps
             j.unit0 = (int64_t)ar->units.size(); j.n_units = b->n_units;
             j.out_base = ar->out_len; j.out_len = 0;
             const int64_t h0 = (int64_t)ar->ho.size() - 1, hbase0 = ar->ho.back();
+            // a failed append (pinned or heap allocation) must leave the arena as it was: later jobs share its arrays
+            const size_t keep_rb = ar->rb.size, keep_hb = ar->hb.size, keep_ro = ar->ro.size(), keep_ho = ar->ho.size(),
+                         keep_units = ar->units.size(), keep_mapq = ar->mapq.size(), keep_ref = ar->ref_hap.size();
+            struct Rollback {
+                std::function<void()> undo;
+                bool armed = true;
+                ~Rollback() { if (armed) undo(); }
+            } rollback{[&] {
+                ar->rb.size = ar->bq.size = ar->iq.size = ar->dq.size = ar->gq.size = keep_rb;
+                ar->hb.size = keep_hb;
+                ar->ro.resize(keep_ro); ar->ho.resize(keep_ho); ar->units.resize(keep_units);
+                ar->mapq.resize(keep_mapq); ar->ref_hap.resize(keep_ref);
+            }};
             ar->rb.append(b->read_bases, (size_t)nb); ar->bq.append(b->base_q, (size_t)nb); ar->iq.append(b->ins_q, (size_t)nb);
             ar->dq.append(b->del_q, (size_t)nb); ar->gq.append(b->gcp, (size_t)nb); ar->hb.append(b->hap_bases, (size_t)hb);
             for (int64_t k = 1; k <= n_reads; ++k) ar->ro.push_back(j.base0 + b->read_off[k]);
@@ -1373,6 +1387,8 @@ static int submit_job(gphmm_t *h, const gphmm_batch *b, const gphmm_region_steps
                 if (n_reads) ar->mapq.insert(ar->mapq.end(), steps->mapq, steps->mapq + n_reads);
                 for (int64_t k = 0; k < b->n_units; ++k) ar->ref_hap.push_back(steps->ref_hap ? steps->ref_hap[k] : -1);
             }
+            ar->jobs.reserve(ar->jobs.size() + 1);
+            rollback.armed = false;  // nothing below throws
             ar->out_len += j.out_len;
             j.ticket = h->next_ticket++;
             ar->jobs.push_back(j);

@@ -130,13 +130,73 @@ public final class CudaLoglessPairHMM extends LoglessPairHMM {
     }
 
     /**
-     * Copies the read-major native result into the allele-major matrix. The matrix may list the haplotypes in another
-     * order than {@link #initialize} received them, so the column of each matrix allele is looked up once per call.
+     * A per-sample likelihood computation that has been handed to the native cross-region queue and not collected yet.
+     * It owns copies of everything {@link #initialize} will overwrite for the next region, so any number of regions can
+     * be in flight; {@link #complete()} blocks until the GPU has the result, then fills the matrix exactly as
+     * {@link #computeLog10Likelihoods} would have. Must be completed on the thread that submitted it (the tool thread).
      */
-    private void scatter(final double[] flat, final ReadDataHolder[] nativeReads,
-                         final LikelihoodMatrix<GATKRead, Haplotype> matrix) {
+    public final class PendingLikelihoods {
+        private final long ticket;
+        private final ReadDataHolder[] nativeReads;
+        private final int[] column;
+        private final int nHaplotypes;
+        private final LikelihoodMatrix<GATKRead, Haplotype> matrix;
+        private boolean completed;
+
+        private PendingLikelihoods(final long ticket, final ReadDataHolder[] nativeReads, final int[] column,
+                                   final int nHaplotypes, final LikelihoodMatrix<GATKRead, Haplotype> matrix) {
+            this.ticket = ticket;
+            this.nativeReads = nativeReads;
+            this.column = column;
+            this.nHaplotypes = nHaplotypes;
+            this.matrix = matrix;
+        }
+
+        /** Waits for the native result and writes it into the matrix; a second call is a no-op. */
+        public void complete() {
+            if (completed) {
+                return;
+            }
+            completed = true;
+            if (nativeReads.length == 0) {
+                return;
+            }
+            final long start = doProfiling ? System.nanoTime() : 0L;
+            final double[] flat = new double[nativeReads.length * nHaplotypes];
+            gpu.await(ticket, flat);   // throws GATKException if the batch failed on the device
+            mLogLikelihoodArray = flat;
+            scatter(flat, nativeReads, matrix, column, nHaplotypes);
+            if (doProfiling) {
+                threadLocalPairHMMComputeTimeDiff = System.nanoTime() - start;
+                pairHMMComputeTime += threadLocalPairHMMComputeTimeDiff;
+            }
+        }
+    }
+
+    /**
+     * Asynchronous form of {@link #computeLog10Likelihoods}: gathers the reads, submits them against the haplotypes of the
+     * last {@link #initialize} call to the native queue (gphmm_submit) and returns at once. Units submitted while the GPU
+     * is busy are merged into one batch by the native worker, which is what fills a B200 from 60-read regions.
+     */
+    public PendingLikelihoods submitLog10Likelihoods(final LikelihoodMatrix<GATKRead, Haplotype> logLikelihoods,
+                                                     final List<GATKRead> processedReads,
+                                                     final PairHMMInputScoreImputator inputScoreImputator) {
+        final int[] column = columnsOf(logLikelihoods);
+        if (processedReads.isEmpty()) {
+            return new PendingLikelihoods(0L, new ReadDataHolder[0], column, nativeHaplotypes.length, logLikelihoods);
+        }
+        final long start = doProfiling ? System.nanoTime() : 0L;
+        final ReadDataHolder[] nativeReads = gatherReads(processedReads, inputScoreImputator);
+        final long ticket = gpu.submit(nativeReads, nativeHaplotypes);   // copies the arrays into the pinned arena
+        if (doProfiling) {
+            nanosInSetup += System.nanoTime() - start;
+        }
+        return new PendingLikelihoods(ticket, nativeReads, column, nativeHaplotypes.length, logLikelihoods);
+    }
+
+    /** Column of each matrix allele in the native (read-major) result. */
+    private int[] columnsOf(final LikelihoodMatrix<GATKRead, Haplotype> matrix) {
         final List<Haplotype> matrixAlleles = matrix.alleles();
-        final int nHaplotypes = nativeHaplotypes.length;
         final int[] column = new int[matrixAlleles.size()];
         for (int a = 0; a < column.length; a++) {
             final Integer idx = nativeIndexOf.get(matrixAlleles.get(a));
@@ -145,6 +205,21 @@ public final class CudaLoglessPairHMM extends LoglessPairHMM {
             }
             column[a] = idx;
         }
+        return column;
+    }
+
+    /**
+     * Copies the read-major native result into the allele-major matrix. The matrix may list the haplotypes in another
+     * order than {@link #initialize} received them, so the column of each matrix allele is looked up once per call.
+     */
+    private void scatter(final double[] flat, final ReadDataHolder[] nativeReads,
+                         final LikelihoodMatrix<GATKRead, Haplotype> matrix) {
+        scatter(flat, nativeReads, matrix, columnsOf(matrix), nativeHaplotypes.length);
+    }
+
+    private void scatter(final double[] flat, final ReadDataHolder[] nativeReads,
+                         final LikelihoodMatrix<GATKRead, Haplotype> matrix, final int[] column, final int nHaplotypes) {
+        final List<Haplotype> matrixAlleles = matrix.alleles();
         for (int r = 0; r < nativeReads.length; r++) {
             final ReadDataHolder read = nativeReads[r];
             final int row = r * nHaplotypes;

@@ -111,6 +111,14 @@ def test_java_plugin_sources_present():
     assert "CUDA_LOGLESS_CACHING(args ->" in patch
     added = [l for l in patch.splitlines() if l.startswith("+") and not l.startswith("+++")]
     assert not any("FASTEST_AVAILABLE" in l for l in added)  # the default chain is untouched
+    # caller side of the cross-region queue: the plugin's async form and the patch that uses it agree on names
+    assert "public PendingLikelihoods submitLog10Likelihoods(" in hmm and "public void complete()" in hmm
+    pipelined = open(os.path.join(ROOT, "java/patches/HaplotypeCaller.pipelinedCallRegion.patch")).read()
+    for name in ("cuda.submitLog10Likelihoods(", "PendingLikelihoods::complete", "callRegionDeferred(", "onTraversalSuccess"):
+        assert name in pipelined
+    sw = open(os.path.join(ROOT, "java/org/broadinstitute/hellbender/utils/smithwaterman/CudaSmithWatermanAligner.java")).read()
+    realign = open(os.path.join(ROOT, "java/patches/AssemblyBasedCallerUtils.batchedRealign.patch")).read()
+    assert "public List<SmithWatermanAlignment> alignBatch(" in sw and "gpu.alignBatch(haplotypes, reads, parameters, SWOverhangStrategy.SOFTCLIP)" in realign
 
 
 def test_plugin_mirror_without_gpu():
