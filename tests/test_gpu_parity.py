@@ -579,3 +579,53 @@ def test_full_size_config2_sample_against_oracle(hmm):
     for u in sub.units:
         lo = int(u["out_off"]); n = int((u["read_end"] - u["read_begin"]) * (u["hap_end"] - u["hap_begin"]))
         assert np.abs(got[lo:lo + n] - want[lo:lo + n]).max() <= TOL
+
+
+def test_several_instances_and_threads_in_one_process():
+    # SURVEY 8b "Threading": Spark creates one engine (one PairHMM instance) per task, so several handles live in one
+    # process and are driven from different threads (J/tools/HaplotypeCallerSpark.java:175).  Three handles on the same
+    # device, one thread each, plus a fourth thread that uses the first handle's queue while its owner calls compute():
+    # every synchronous result is bit-identical with the same batch computed alone on a fresh handle.
+    import threading
+    batches = [synth.random_batch(900 + k, n_units=4) for k in range(6)]
+    with GpuPhmm() as solo:
+        alone = [solo.compute(b) for b in batches]
+    for got, b in zip(alone[:2], batches[:2]):
+        _check(got, oracle_batch(b), TOL)
+    handles = [GpuPhmm() for _ in range(3)]
+    results, errors = {}, []
+
+    def sync_worker(k):
+        try:
+            for rep in range(3):
+                for i, b in enumerate(batches):
+                    results[(k, rep, i)] = handles[k].compute(b)
+        except Exception as e:   # noqa: BLE001 -- reported by the main thread
+            errors.append(e)
+
+    def queue_worker():
+        try:
+            for rep in range(3):
+                tickets = [handles[0].submit(b) for b in batches]
+                for i, t in enumerate(tickets):
+                    results[("q", rep, i)] = handles[0].wait(t)
+        except Exception as e:   # noqa: BLE001
+            errors.append(e)
+
+    threads = [threading.Thread(target=sync_worker, args=(k,)) for k in range(3)] + [threading.Thread(target=queue_worker)]
+    try:
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join(120)
+        assert not any(t.is_alive() for t in threads), "a worker thread hung"
+        assert not errors, errors
+        assert len(results) == 4 * 3 * len(batches)
+        for (who, _, i), got in results.items():
+            if who == "q":   # queued batches are merged with whatever else was pending: other chunks, float noise only
+                assert np.abs(got - alone[i]).max() < 1e-5
+            else:
+                assert np.array_equal(got, alone[i])
+    finally:
+        for h in handles:
+            h.close()
