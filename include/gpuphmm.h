@@ -108,7 +108,10 @@ const char *gphmm_strerror(int code);
 
 int gphmm_create(const gphmm_config *cfg, gphmm_t **out);
 void gphmm_destroy(gphmm_t *h);
-/* Text of the last failure on this handle (never NULL). */
+/* Text of the last failure on this handle (never NULL).
+ * Threads: a handle may be used from several threads (calls that touch the device are serialised inside; several
+ * handles run independently -- one PairHMM instance per Spark task, J/tools/HaplotypeCallerSpark.java:175), but the
+ * error text is one slot per handle: read it on the thread whose call failed, before that handle fails again. */
 const char *gphmm_last_error(const gphmm_t *h);
 
 /* Synchronous: returns when every out[] slot of the batch is written. */
