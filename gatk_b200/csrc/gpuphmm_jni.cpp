@@ -101,6 +101,8 @@ bool pack(JNIEnv *env, Session *s, jobjectArray reads, jobjectArray haps, gphmm_
         return false;
     }
     const jsize n_reads = env->GetArrayLength(reads), n_haps = env->GetArrayLength(haps);
+    // the array references of every holder stay alive until pass 2: far more than the 16 local references JNI guarantees
+    if (env->EnsureLocalCapacity(5 * n_reads + n_haps + 16) != 0) return false;  // OutOfMemoryError is pending
     s->read_off.assign(1, 0);
     s->hap_off.assign(1, 0);
     // pass 1: lengths

@@ -38,6 +38,7 @@ struct JNIEnv {
     jclass FindClass(const char *);
     jint ThrowNew(jclass, const char *);
     jboolean ExceptionCheck();
+    jint EnsureLocalCapacity(jint);
     jfieldID GetFieldID(jclass, const char *, const char *);
     jobject GetObjectField(jobject, jfieldID);
     jsize GetArrayLength(jarray);
