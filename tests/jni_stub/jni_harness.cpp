@@ -215,6 +215,7 @@ extern "C" {
 jint JNIFN(nativeDeviceCount)(JNIEnv *, jclass);
 jlong JNIFN(nativeCreate)(JNIEnv *, jclass, jintArray, jboolean, jint);
 void JNIFN(nativeCompute)(JNIEnv *, jclass, jlong, jobjectArray, jobjectArray, jdoubleArray);
+void JNIFN(nativeComputePD)(JNIEnv *, jclass, jlong, jobjectArray, jobjectArray, jdoubleArray);
 void JNIFN(nativeComputeRegion)(JNIEnv *, jclass, jlong, jobjectArray, jbyteArray, jobjectArray, jintArray, jdoubleArray, jdoubleArray, jbyteArray, jbyteArray);
 jboolean JNIFN(nativeSwAlign)(JNIEnv *, jclass, jlong, jobjectArray, jobjectArray, jintArray, jint, jintArray, jintArray, jintArray);
 jlong JNIFN(nativeSubmit)(JNIEnv *, jclass, jlong, jobjectArray, jobjectArray);
@@ -446,6 +447,30 @@ int run_gpu(JNIEnv *env) {
         EXPECT(memcmp(ints_of(ne).data(), ne_want.data(), np * sizeof(int32_t)) == 0, "CIGAR lengths differ");
         for (int k = 0; k < np; ++k)
             EXPECT(ne_want[k] >= 1 && memcmp(ints_of(el).data() + k * cap, el_want.data() + static_cast<size_t>(k) * cap, static_cast<size_t>(ne_want[k]) * 4) == 0, "CIGAR %d differs", k);
+    }
+
+    // PD-HMM: HaplotypeDataHolder.haplotypePDBases travels as the flag array; shim == gphmm_pd_compute
+    {
+        const Region pg = make_region(8, 6, 2);
+        Flat pf(pg);
+        std::vector<uint8_t> pd(pf.hb.size(), 0);
+        pd[40] = 1 | 8;            // SNP site, alternative A
+        pd[80] = 2; pd[85] = 4;    // DEL_START .. DEL_END
+        std::vector<jobject> holders;
+        for (size_t k = 0; k < pg.haps.size(); ++k)
+            holders.push_back(new_holder("org/broadinstitute/gatk/nativebindings/pairhmm/HaplotypeDataHolder",
+                                         {{"haplotypeBases", new_bytes(pg.haps[k])},
+                                          {"haplotypePDBases", new_bytes(std::vector<uint8_t>(pd.begin() + pf.ho[k], pd.begin() + pf.ho[k + 1]))}}));
+        const size_t np = pg.read_bases.size() * pg.haps.size();
+        std::vector<double> pd_want(np, 1.0);
+        EXPECT(gphmm_pd_compute(direct, &pf.b, pd.data(), pd_want.data()) == GPHMM_OK, "gphmm_pd_compute: %s", gphmm_last_error(direct));
+        jdoubleArray pd_out = new_doubles(std::vector<double>(np, 1.0));
+        JNIFN(nativeComputePD)(env, nullptr, h, java_reads(pg), new_objects(holders), pd_out);
+        EXPECT(!env->ExceptionCheck(), "nativeComputePD raised %s: %s", g_pending_class.c_str(), g_pending_msg.c_str());
+        EXPECT(memcmp(doubles_of(pd_out).data(), pd_want.data(), np * sizeof(double)) == 0, "nativeComputePD differs from gphmm_pd_compute");
+        // a holder without the flag array is an argument error, not a crash
+        JNIFN(nativeComputePD)(env, nullptr, h, java_reads(pg), java_haps(pg), new_doubles(std::vector<double>(np)));
+        EXPECT(take_exception("java/lang/IllegalArgumentException", "haplotypePDBases"), "missing haplotypePDBases must raise");
     }
 
     // counters: pairs and launches were counted
