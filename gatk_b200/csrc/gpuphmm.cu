@@ -203,6 +203,21 @@ struct KernelInfo {
     size_t smem = 0;
 };
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is ONE value per (function, device): a later, smaller request must not
+// lower it under a cached KernelInfo that still launches with the larger size.  Keep a running maximum.
+void raise_dyn_smem(const void *fn, size_t bytes) {
+    if (bytes <= 48 * 1024) return;
+    static std::mutex mu;
+    static std::map<std::pair<int, const void *>, size_t> high;
+    int dev = 0;
+    CK(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lk(mu);
+    size_t &cur = high[{dev, fn}];
+    if (bytes <= cur) return;
+    CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    cur = bytes;
+}
+
 // Forward kernels are persistent and several of them (the K buckets of a chunk, the next chunk) are in flight at once;
 // the hardware would pack them until no SM has room for the small kernels that CLOSE a chunk (epilogue, rescue), so
 // chunks would only complete in groups and the host pipeline would stall.  Every forward CTA therefore asks for
@@ -215,7 +230,7 @@ void reserve_headroom(KernelInfo &ki, const void *fn) {
     const size_t want = (size_t)(227 * 1024) / (size_t)(occ - headroom) - 1024;  // 1 KB per CTA is reserved by the system
     if (want > ki.smem) {
         ki.smem = want & ~(size_t)15;
-        if (ki.smem > 48 * 1024) CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ki.smem));
+        raise_dyn_smem((const void *)fn, ki.smem);
     }
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ki.ctas_per_sm, fn, 32, ki.smem));
     if (ki.ctas_per_sm < 1) ki.ctas_per_sm = 1;
@@ -226,7 +241,7 @@ template <typename T, int K, bool S> KernelInfo kernel_info(int n_codes) {
     auto fn = phmm_forward_kernel<T, K, S>;
     ki.fn = (const void *)fn;
     ki.smem = prior_table_bytes<T, K>(n_codes);
-    if (ki.smem > 48 * 1024) CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ki.smem));
+    raise_dyn_smem((const void *)fn, ki.smem);
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ki.ctas_per_sm, fn, 32, ki.smem));
     if (ki.ctas_per_sm < 1) throw Error(GPHMM_ERR_ALPHABET, "prior table does not fit in shared memory");
     reserve_headroom(ki, (const void *)fn);
@@ -238,7 +253,7 @@ template <int K> KernelInfo fast_kernel_info(int n_codes) {
     auto fn = phmm_fast_f32_kernel<K>;
     ki.fn = (const void *)fn;
     ki.smem = prior_table_bytes<float, K>(n_codes);
-    if (ki.smem > 48 * 1024) CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ki.smem));
+    raise_dyn_smem((const void *)fn, ki.smem);
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ki.ctas_per_sm, fn, 32, ki.smem));
     if (ki.ctas_per_sm < 1) throw Error(GPHMM_ERR_ALPHABET, "prior table does not fit in shared memory");
     reserve_headroom(ki, (const void *)fn);
@@ -263,7 +278,7 @@ template <int K, bool SYM> KernelInfo flat_kernel_info(int n_codes) {
     auto fn = phmm_flat_f32_kernel<K, SYM>;
     ki.fn = (const void *)fn;
     ki.smem = prior_table_bytes<float, K>(n_codes);
-    if (ki.smem > 48 * 1024) CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ki.smem));
+    raise_dyn_smem((const void *)fn, ki.smem);
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ki.ctas_per_sm, fn, 32, ki.smem));
     if (ki.ctas_per_sm < 1) throw Error(GPHMM_ERR_ALPHABET, "prior table does not fit in shared memory");
     reserve_headroom(ki, (const void *)fn);
@@ -303,7 +318,7 @@ KernelInfo flat_fp64_kernel(int n_codes) {
     auto fn = phmm_flat_f64_kernel;
     ki.fn = (const void *)fn;
     ki.smem = prior_table_bytes<double, 8>(n_codes);
-    if (ki.smem > 48 * 1024) CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ki.smem));
+    raise_dyn_smem((const void *)fn, ki.smem);
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ki.ctas_per_sm, fn, 32, ki.smem));
     if (ki.ctas_per_sm < 1) throw Error(GPHMM_ERR_ALPHABET, "prior table does not fit in shared memory");
     return ki;
@@ -1299,7 +1314,7 @@ int gphmm_compute(gphmm_t *h, const gphmm_batch *batch, double *out) {
 int gphmm_compute_regions(gphmm_t *h, const gphmm_batch *batch, const gphmm_region_steps *steps, double *out) {
     if (!h) return GPHMM_ERR_INVALID_ARG;
     return guarded(h, [&]() -> int {
-        if (!batch) throw Error(GPHMM_ERR_INVALID_ARG, "batch is null");
+        validate_batch(batch);  // before anything indexes batch->units
         validate_region_steps(batch, steps);
         return run_batch(h, batch, out, steps);
     });
@@ -1427,6 +1442,7 @@ int gphmm_prepare(gphmm_t *h, const gphmm_batch *b, gphmm_prepared_t **out) {
     if (!h || !out) return GPHMM_ERR_INVALID_ARG;
     *out = nullptr;
     return guarded(h, [&]() -> int {
+        std::lock_guard<std::mutex> run_lk(h->run_mu);  // device-touching calls on one handle are serialised (include/gpuphmm.h)
         validate_batch(b);
         std::unique_ptr<gphmm_prepared> p(new gphmm_prepared());
         p->units.assign(b->units, b->units + b->n_units);
@@ -1456,6 +1472,7 @@ int gphmm_prepare(gphmm_t *h, const gphmm_batch *b, gphmm_prepared_t **out) {
 int gphmm_run_prepared(gphmm_t *h, gphmm_prepared_t *p, double *out) {
     if (!h || !p) return GPHMM_ERR_INVALID_ARG;
     return guarded(h, [&]() -> int {
+        std::lock_guard<std::mutex> run_lk(h->run_mu);
         const double t0 = now_ms();
         RunOptions opt;
         opt.force_fp64 = h->cfg.force_fp64 != 0;
@@ -1520,6 +1537,8 @@ int gphmm_run_prepared(gphmm_t *h, gphmm_prepared_t *p, double *out) {
 
 void gphmm_release_prepared(gphmm_t *h, gphmm_prepared_t *p) {
     if (!p) return;
+    std::unique_lock<std::mutex> run_lk;
+    if (h) run_lk = std::unique_lock<std::mutex>(h->run_mu);
     for (auto &part : p->parts) {
         if (h) cudaSetDevice(h->devices[part->device_index]->ordinal);
         part->dc.release();

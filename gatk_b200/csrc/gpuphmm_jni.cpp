@@ -47,7 +47,8 @@ struct Pinned {
 };
 
 struct Pending {
-    std::vector<double> out;
+    std::vector<double> out;  // never empty (gphmm_submit rejects a null out); `n` is what the caller gets back
+    size_t n = 0;
 };
 
 struct Session {
@@ -379,7 +380,9 @@ JNIEXPORT jlong JNICALL JNIFN(nativeSubmit)(JNIEnv *env, jclass, jlong handle, j
     gphmm_unit unit;
     if (!pack(env, s, reads, haps, &b, &unit)) return 0;
     Pending pend;
-    pend.out.assign(static_cast<size_t>(b.n_reads * b.n_haps), 0.0);
+    // an empty read or haplotype list is a no-op like in nativeCompute: the ticket completes with nothing to copy
+    pend.n = static_cast<size_t>(b.n_reads * b.n_haps);
+    pend.out.assign(std::max<size_t>(pend.n, 1), 0.0);
     uint64_t ticket = 0;
     // the vector's heap block does not move when the Pending is moved into the map
     const int rc = gphmm_submit(s->h, &b, pend.out.data(), &ticket);
@@ -404,7 +407,7 @@ JNIEXPORT void JNICALL JNIFN(nativeAwait)(JNIEnv *env, jclass, jlong handle, jlo
         throw_for(env, s, rc);
         return;
     }
-    const jsize n = static_cast<jsize>(it->second.out.size());
+    const jsize n = static_cast<jsize>(it->second.n);
     if (env->GetArrayLength(out) < n) {
         s->pending.erase(it);
         throw_java(env, "java/lang/IllegalArgumentException", "likelihood array is too small");

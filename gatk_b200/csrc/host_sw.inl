@@ -33,7 +33,8 @@ int run_sw_batch(gphmm *h, const gphmm_sw_batch *b, const gphmm_sw_params *prm, 
         while (k1 < b->n_pairs && (int64_t)tasks.size() < ((int64_t)1 << 20)) {
             const uint32_t nr = (uint32_t)(b->ref_off[k1 + 1] - b->ref_off[k1]), na = (uint32_t)(b->alt_off[k1 + 1] - b->alt_off[k1]);
             const uint64_t need = (uint64_t)((nr + SW_ROWS - 1) / SW_ROWS) * (na + 31) * SW_ROWS;
-            if (!tasks.empty() && (bt + need > MAX_BT || aux + (nr + 1) + 4 * (uint64_t)(na + 1) > ((uint64_t)1 << 30))) break;
+            if (!tasks.empty() && (bt + need > MAX_BT || aux + (nr + 1) + 4 * (uint64_t)(na + 1) > ((uint64_t)1 << 30) ||
+                                   (uint64_t)(tasks.size() + 1) * (uint64_t)capacity > (uint64_t)UINT32_MAX)) break;  // out_off is 32-bit
             SwTask t;
             t.ref_off = (uint32_t)(b->ref_off[k1] - rb0); t.n_ref = nr;
             t.alt_off = (uint32_t)(b->alt_off[k1] - ab0); t.n_alt = na;

@@ -107,6 +107,18 @@ def config2(n_regions=10000, seed=SEED, pinned=False, first_region=0):
     return _assemble(regions, pinned=pinned)
 
 
+def config4(n_regions=24, reads_per_region=4000, n_haps=32, seed=SEED, pinned=False):
+    """BASELINE.json configs[3] at the PairHMM boundary: Mutect2-like 500x depth -- thousands of 150 bp reads
+    (10 % clipped to U[100,150]) per region against many haplotypes of 300-500 bp (heavy batching per region)."""
+    regions = []
+    for k in range(n_regions):
+        rng = np.random.default_rng(seed + 104729 * k)
+        read_lens = np.where(rng.random(reads_per_region) < 0.1, rng.integers(100, 151, reads_per_region), 150).astype(np.int64)
+        haps, b, q, i, d, g = _region(rng, reads_per_region, read_lens, n_haps, int(rng.integers(300, 501)))
+        regions.append((haps, b, q, i, d, g, read_lens))
+    return _assemble(regions, pinned=pinned)
+
+
 def config5(hap_len=1000, n_regions=64, reads_per_region=64, n_haps=8, bad_fraction=0.1, seed=SEED, pinned=False):
     """BASELINE.json configs[4]: indel-heavy long-haplotype sweep.  250 bp reads against haplotypes of
     `hap_len`; a `bad_fraction` of the reads carries 3-10 indels of 1-20 bp plus 5 % mismatches at Q40 so

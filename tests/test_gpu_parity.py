@@ -131,6 +131,44 @@ def test_fp64_rescue_path(hmm):
     assert np.abs(got[low] - want[low]).max() <= 1e-9  # rescued pairs carry fp64 accuracy
 
 
+def test_config4_deep_coverage_every_pair(hmm):
+    # BASELINE.json configs[3] at the PairHMM boundary (Mutect2 500x: 4 000 reads x 32 haplotypes per region, 150 bp
+    # reads): EVERY pair of two full-size regions against the double-precision oracle (VectorPairHMMUnitTest.java:100
+    # compares every pair of its fixture the same way), through the synchronous call and through the queue
+    b = synth.config4(n_regions=2)
+    assert b.pairs() == 2 * 4000 * 32
+    want = oracle_batch(b)
+    hmm.reset_stats()
+    got = hmm.compute(b)
+    _check(got, want, TOL)
+    assert hmm.stats()["pairs"] == b.pairs()
+    t = hmm.submit(b)
+    assert np.array_equal(hmm.wait(t), got)
+    with GpuPhmm(no_prefix_sharing=True) as plain:
+        assert np.array_equal(plain.compute(b), got)
+
+
+@pytest.mark.parametrize("bad_fraction", [0.0, 0.1, 0.5])
+def test_config5_long_haplotypes_h1000(hmm, bad_fraction):
+    # BASELINE.json configs[4] at its largest haplotype length (250 bp reads x 1 000 bp haplotypes; reads of
+    # PairHMMUnitTest.java:420-457 "really big" shapes) with 0 / 10 / 50 % indel-heavy reads: every pair against the
+    # oracle, and the pairs that left the fp32 range come back from the fp64 redo with double accuracy
+    b = synth.config5(hap_len=1000, n_regions=6, reads_per_region=32, n_haps=8, bad_fraction=bad_fraction)
+    want = oracle_batch(b)
+    hmm.reset_stats()
+    got = hmm.compute(b)
+    s = hmm.stats()
+    _check(got, want, TOL)
+    low = want < -40   # 1e-28 on a sum that starts from 2^(116 - 10): far below the rescue threshold
+    if bad_fraction == 0.0:
+        assert not low.any()
+    else:
+        assert low.sum() >= 0.5 * bad_fraction * low.size * 0.5 and s["rescued_pairs"] >= low.sum()
+        assert np.abs(got[low] - want[low]).max() <= 1e-9
+    with GpuPhmm(chunk_cells=200_000_000) as small:   # several chunks: the redo list is per chunk
+        assert np.array_equal(small.compute(b), got)
+
+
 def test_really_big_reads(hmm, hmm64):
     # PairHMMUnitTest.java:420-457 : reads up to 800 bp x haplotypes up to 2000 bp
     read1, ref1 = b"ACCAAGTAGTCACCGT", b"ACCAAGTAGTCACCGTAACG"
@@ -496,9 +534,15 @@ def test_symmetric_quality_reads(hmm):
     with GpuPhmm(no_prefix_sharing=True) as plain:
         got = hmm.compute(big)
         ref = plain.compute(big)
-    # bit-identical, except where the wild-quality reads overflow fp32 in one mode only (state left behind by the
-    # previous haplotype differs) and are redone in fp64: those agree to float rounding
+        with GpuPhmm(force_fp64=True) as h64:
+            all64 = h64.compute(big)
+    # bit-identical, except where a wild-quality read overflows fp32 in one mode only (the state left behind by the
+    # previous haplotype differs between a restored snapshot and a full recompute) and is redone in fp64.  A pair that
+    # went through the fp64 redo carries exactly the forced-fp64 value (same kernels, same tasks), an fp32 pair never
+    # does: so the set of differing pairs must be EXACTLY the pairs redone in one mode and not in the other.
+    redone_shared, redone_plain = got == all64, ref == all64
     differs = got != ref
+    assert np.array_equal(differs, redone_shared ^ redone_plain)
     assert differs.mean() < 0.005
     assert not differs.any() or np.abs(got - ref)[differs].max() < 1e-5
     _check(got[:n], want, TOL)

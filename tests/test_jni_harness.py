@@ -29,7 +29,6 @@ def test_shim_without_a_gpu_raises_hardware_feature_exception():
 
 
 @pytest.mark.gpu
-@pytest.mark.xfail(strict=False, reason="written after the round's GPU budget was spent: its first run on a GPU is the driver's round-end run")
 def test_shim_agrees_with_the_c_abi_on_the_gpu():
     out = subprocess.run([_build(), "gpu"], capture_output=True, text=True, timeout=90)
     assert out.returncode == 0 and "jni_harness gpu: ok" in out.stdout, out.stdout + out.stderr

@@ -13,14 +13,8 @@ quick = "--quick" in sys.argv
 
 
 def deep_coverage(n_regions=24, reads=4000, n_haps=32, seed=synth.SEED):
-    """configs[3] at the PairHMM boundary: Mutect2-like 500x depth, thousands of reads per region, many haplotypes"""
-    regions = []
-    for k in range(n_regions):
-        rng = np.random.default_rng(seed + 104729 * k)
-        read_lens = np.where(rng.random(reads) < 0.1, rng.integers(100, 151, reads), 150).astype(np.int64)
-        haps, b, q, i, d, g = synth._region(rng, reads, read_lens, n_haps, int(rng.integers(300, 501)))
-        regions.append((haps, b, q, i, d, g, read_lens))
-    return synth._assemble(regions, pinned=True)
+    """configs[3] at the PairHMM boundary (synth.config4)"""
+    return synth.config4(n_regions, reads, n_haps, seed=seed, pinned=True)
 
 
 def measure(name, batch, hmm, sample_units=4, steps=3):
