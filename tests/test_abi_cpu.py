@@ -114,7 +114,10 @@ def test_java_plugin_sources_present():
     # caller side of the cross-region queue: the plugin's async form and the patch that uses it agree on names
     assert "public PendingLikelihoods submitLog10Likelihoods(" in hmm and "public void complete()" in hmm
     pipelined = open(os.path.join(ROOT, "java/patches/HaplotypeCaller.pipelinedCallRegion.patch")).read()
-    for name in ("cuda.submitLog10Likelihoods(", "PendingLikelihoods::complete", "callRegionDeferred(", "onTraversalSuccess"):
+    engine = open(os.path.join(ROOT, "java/patches/PairHMMLikelihoodCalculationEngine.regionSteps.patch")).read()
+    for name in ("cuda.submitLog10Likelihoods(", "PendingLikelihoods::complete", "submitReadLikelihoods("):
+        assert name in engine
+    for name in (".submitReadLikelihoods(", "callRegionDeferred(", "onTraversalSuccess"):
         assert name in pipelined
     sw = open(os.path.join(ROOT, "java/org/broadinstitute/hellbender/utils/smithwaterman/CudaSmithWatermanAligner.java")).read()
     realign = open(os.path.join(ROOT, "java/patches/AssemblyBasedCallerUtils.batchedRealign.patch")).read()
