@@ -123,6 +123,29 @@ constexpr int N_AUX = N_FP32_BUCKETS + 8 * (MAX_FLAT_CLASSES + MAX_SYM_CLASSES);
 constexpr int N_COUNTERS = 128;    // [0..8] general fp32 buckets, [9] fp64 queue, [10] n_rescue, [11] n_deep, [120] deep cursor,
                                    // [16 + 8*c + k] flat-quality kernels: class c, bucket k
 
+// Growable byte buffer without value-initialisation (std::vector<uint8_t>::resize would memset what is overwritten next).
+struct ByteBuf {
+    uint8_t *p = nullptr;
+    size_t n = 0, cap = 0;
+    ByteBuf() = default;
+    ByteBuf(const ByteBuf &) = delete;
+    ByteBuf &operator=(const ByteBuf &) = delete;
+    ~ByteBuf() { free(p); }
+    size_t size() const { return n; }
+    const uint8_t *data() const { return p; }
+    uint8_t *data() { return p; }
+    void clear() { n = 0; }
+    void reserve(size_t want) {
+        if (want <= cap) return;
+        want = std::max(want, cap + cap / 2 + 4096);
+        void *q = realloc(p, want);
+        if (!q) throw std::bad_alloc();
+        p = (uint8_t *)q; cap = want;
+    }
+    uint8_t *append_raw(size_t k) { reserve(n + k); uint8_t *at = p + n; n += k; return at; }  // caller fills [at, at + k)
+    void append_fill(size_t k, uint8_t v) { memset(append_raw(k), v, k); }
+};
+
 // Host-side plan of one device chunk: which units, and every metadata array the kernels need.
 struct ChunkPlan {
     int64_t u0 = 0, u1 = 0;          // unit range in the batch
@@ -134,12 +157,12 @@ struct ChunkPlan {
     int n_codes = 7;
     uint8_t code_byte[MAX_CODES];
     std::vector<uint32_t> read_off;        // span-local, n_reads_span + 1
-    std::vector<uint8_t> streams;
+    ByteBuf streams;
     std::vector<uint32_t> hap_len, hap_stream_off;
     std::vector<UnitDesc> units;
     std::vector<Task> tasks;               // bucket-sorted
     uint32_t bucket_begin[N_FP32_BUCKETS + 1];
-    std::vector<uint8_t> sstreams;         // prefix-compressed streams of the fast kernels
+    ByteBuf sstreams;                      // prefix-compressed streams of the fast kernels
     std::vector<PassInfo> pass_info;
     std::vector<Segment> segments;
     std::vector<UnitSched> unit_sched;
@@ -1588,6 +1611,45 @@ int gphmm_plan_stats(const gphmm_batch *b, int prefix_sharing, int64_t out[10]) 
             out[9] += (int64_t)c.tasks.size();
         }
         out[6] += out[7];
+        return GPHMM_OK;
+    });
+}
+
+int gphmm_measure_fp32_peak(gphmm_t *h, double millis, double *tflops) {
+    if (!h || !tflops) return GPHMM_ERR_INVALID_ARG;
+    return guarded(h, [&]() -> int {
+        std::lock_guard<std::mutex> run_lk(h->run_mu);
+        Device &dev = *h->devices[0];
+        CK(cudaSetDevice(dev.ordinal));
+        constexpr int THREADS = 256, ILP = 8, ITER = 4096;
+        const int grid = dev.n_sms * 8;  // 64 warps per SM: every scheduler always has an eligible warp
+        DevBuf sink;
+        sink.reserve((size_t)grid * THREADS * sizeof(float));
+        cudaStream_t st = dev.streams[0];
+        cudaEvent_t e0, e1;
+        CK(cudaEventCreate(&e0));
+        CK(cudaEventCreate(&e1));
+        auto run = [&](int reps) {
+            for (int r = 0; r < reps; ++r) phmm_ffma_peak_kernel<ILP, ITER><<<grid, THREADS, 0, st>>>((float *)sink.p, 0.999f, 1e-3f);
+        };
+        run(2);
+        CK(cudaEventRecord(e0, st));
+        run(1);
+        CK(cudaEventRecord(e1, st));
+        CK(cudaEventSynchronize(e1));
+        float ms1 = 0.f;
+        CK(cudaEventElapsedTime(&ms1, e0, e1));
+        const int reps = std::max(1, (int)(millis / std::max(ms1, 1e-3f)));
+        CK(cudaEventRecord(e0, st));
+        run(reps);
+        CK(cudaEventRecord(e1, st));
+        CK(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        CK(cudaGetLastError());
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+        sink.release();
+        *tflops = 2.0 * (double)grid * THREADS * ILP * ITER * reps / (ms * 1e-3) / 1e12;
         return GPHMM_OK;
     });
 }

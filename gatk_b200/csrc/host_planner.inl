@@ -67,11 +67,11 @@ std::vector<std::pair<int64_t, int64_t>> split_units(const gphmm_batch *b, int64
 // from a snapshot taken at the last column it shares with its predecessors.  Appends to c.sstreams / pass_info /
 // segments and returns the unit's schedule.  With share == false every pass starts from column 1 in input order.
 // Lexicographic order of a unit's haplotypes (input order when sharing is off).
-std::vector<int> sorted_hap_order(const gphmm_batch *b, const gphmm_unit &un, bool share) {
+void sorted_hap_order(const gphmm_batch *b, const gphmm_unit &un, bool share, std::vector<int> &order) {
     const int n = (int)(un.hap_end - un.hap_begin);
     auto hap_ptr = [&](int k) { return b->hap_bases + b->hap_off[un.hap_begin + k]; };
     auto hap_len = [&](int k) { return (uint32_t)(b->hap_off[un.hap_begin + k + 1] - b->hap_off[un.hap_begin + k]); };
-    std::vector<int> order(n);
+    order.resize(n);
     for (int k = 0; k < n; ++k) order[k] = k;
     if (share)
         std::sort(order.begin(), order.end(), [&](int x, int y) {
@@ -81,11 +81,18 @@ std::vector<int> sorted_hap_order(const gphmm_batch *b, const gphmm_unit &un, bo
             if (lx != ly) return lx < ly;
             return x < y;
         });
-    return order;
 }
 
+// Scratch of plan_unit_sharing, reused across the units of a chunk (no heap traffic per unit once warm).
+struct SharingScratch {
+    struct Snap { int pass; uint32_t depth, pos; int slot; uint32_t free_after; };
+    std::vector<Snap> snaps;
+    std::vector<uint32_t> r, pass_start, end_pos, lcp, n_pad, pts;
+    std::vector<int> snap_of_pass, snap_by_pos, order;
+};
+
 UnitSched plan_unit_sharing(const gphmm_batch *b, const gphmm_unit &un, uint32_t hap_first_local, bool share, ChunkPlan &c,
-                            int64_t sum_read_len, const std::vector<int> &full_order, int g_first, int g_count) {
+                            int64_t sum_read_len, const std::vector<int> &full_order, int g_first, int g_count, SharingScratch &ws) {
     constexpr uint32_t SPACING = 32;
     static const uint32_t NEAR_DEPTHS = getenv("GPHMM_NEAR_DEPTHS") ? (uint32_t)std::max(1, atoi(getenv("GPHMM_NEAR_DEPTHS"))) : 96u;  // how far below the shared depth to look
     static const uint32_t MIN_DEPTH = getenv("GPHMM_MIN_DEPTH") ? (uint32_t)std::max(32, atoi(getenv("GPHMM_MIN_DEPTH"))) : 32u;  // tuning knob
@@ -95,19 +102,22 @@ UnitSched plan_unit_sharing(const gphmm_batch *b, const gphmm_unit &un, uint32_t
     us.pass_first = (uint32_t)c.pass_info.size();
     us.n_passes = (uint32_t)n;
     us.seg_first = (uint32_t)c.segments.size();
-    c.sstreams.insert(c.sstreams.end(), STREAM_PAD, (uint8_t)CODE_NULL);
+    c.sstreams.append_fill(STREAM_PAD, (uint8_t)CODE_NULL);
     us.sstream_off = (uint32_t)c.sstreams.size();
     if (n == 0) return us;
     auto hap_ptr = [&](int k) { return b->hap_bases + b->hap_off[un.hap_begin + k]; };
     auto hap_len = [&](int k) { return (uint32_t)(b->hap_off[un.hap_begin + k + 1] - b->hap_off[un.hap_begin + k]); };
-    std::vector<int> order(full_order.begin() + g_first, full_order.begin() + g_first + g_count);
-    struct Snap { int pass; uint32_t depth, pos; int slot; uint32_t free_after; };
-    std::vector<Snap> snaps;
+    using Snap = SharingScratch::Snap;
+    std::vector<int> &order = ws.order;
+    order.assign(full_order.begin() + g_first, full_order.begin() + g_first + g_count);
+    std::vector<Snap> &snaps = ws.snaps;
+    snaps.clear();
     int slot_owner[MAX_SNAP_SLOTS];
     for (int k = 0; k < MAX_SNAP_SLOTS; ++k) slot_owner[k] = -1;
-    std::vector<uint32_t> r(n, 0), pass_start(n + 1, 1), end_pos(n, 0);
-    std::vector<int> snap_of_pass(n, -1);
-    std::vector<uint32_t> lcp(n, 0), n_pad(n, 0);
+    std::vector<uint32_t> &r = ws.r, &pass_start = ws.pass_start, &end_pos = ws.end_pos, &lcp = ws.lcp, &n_pad = ws.n_pad;
+    std::vector<int> &snap_of_pass = ws.snap_of_pass;
+    r.assign(n, 0); pass_start.assign(n + 1, 1); end_pos.assign(n, 0); lcp.assign(n, 0); n_pad.assign(n, 0);
+    snap_of_pass.assign(n, -1);
     for (int i = 0; i < n; ++i) {
         const uint32_t H = hap_len(order[i]);
         // every pass spans at least 32 stream positions (NULL columns before its END if it is shorter), so that the
@@ -170,9 +180,7 @@ UnitSched plan_unit_sharing(const gphmm_batch *b, const gphmm_unit &un, uint32_t
     // stream + pass table
     for (int i = 0; i < n; ++i) {
         const uint32_t H = hap_len(order[i]);
-        const size_t w = c.sstreams.size();
-        c.sstreams.resize(w + (H - r[i]) + n_pad[i] + 1);
-        uint8_t *dst = c.sstreams.data() + w;
+        uint8_t *dst = c.sstreams.append_raw((H - r[i]) + n_pad[i] + 1);
         // the full stream of this unit was encoded a moment ago: copy the columns behind the shared prefix
         memcpy(dst, c.streams.data() + c.hap_stream_off[hap_first_local + order[i]] + r[i], H - r[i]);
         for (uint32_t q = 0; q < n_pad[i]; ++q) dst[H - r[i] + q] = (uint8_t)CODE_NULL;  // prior 0: no effect on the sum
@@ -188,13 +196,15 @@ UnitSched plan_unit_sharing(const gphmm_batch *b, const gphmm_unit &un, uint32_t
     // during steps [e, e+32) and a snapshot position s during [s, s+32).  END windows never overlap each other
     // (passes span >= 32 positions), snapshot windows never overlap each other (SPACING), so at any step at most one
     // of each is active.  A segment = branch-free steps, then checked steps with one constant (END, snapshot) pair.
-    std::vector<uint32_t> pts;
+    std::vector<uint32_t> &pts = ws.pts;
+    pts.clear();
     pts.push_back(1);
     for (int i = 0; i < n; ++i) { pts.push_back(end_pos[i]); pts.push_back(end_pos[i] + 32); }
     for (const Snap &sn : snaps) { pts.push_back(sn.pos); pts.push_back(sn.pos + 32); }
     std::sort(pts.begin(), pts.end());
     pts.erase(std::unique(pts.begin(), pts.end()), pts.end());
-    std::vector<int> snap_by_pos(snaps.size());
+    std::vector<int> &snap_by_pos = ws.snap_by_pos;
+    snap_by_pos.resize(snaps.size());
     for (size_t q = 0; q < snaps.size(); ++q) snap_by_pos[q] = (int)q;
     std::sort(snap_by_pos.begin(), snap_by_pos.end(), [&](int x, int y) { return snaps[x].pos < snaps[y].pos; });
     Segment seg;
@@ -224,6 +234,22 @@ UnitSched plan_unit_sharing(const gphmm_batch *b, const gphmm_unit &un, uint32_t
     if (seg.n_free || seg.n_chk) c.segments.push_back(seg);
     us.n_segs = (uint32_t)c.segments.size() - us.seg_first;
     return us;
+}
+
+// Haplotype bytes -> column codes through a 256-entry table.  Returns false when a byte without a code (0xff) was met;
+// valid codes are < MAX_CODES = 64, so the OR of everything written has bit 7 set iff some byte was unknown.
+inline bool encode_hap(uint8_t *dst, const uint8_t *src, uint32_t H, const uint8_t *lut8) {
+    uint32_t acc = 0, j = 0;
+    for (; j + 8 <= H; j += 8) {
+        const uint8_t c0 = lut8[src[j]], c1 = lut8[src[j + 1]], c2 = lut8[src[j + 2]], c3 = lut8[src[j + 3]];
+        const uint8_t c4 = lut8[src[j + 4]], c5 = lut8[src[j + 5]], c6 = lut8[src[j + 6]], c7 = lut8[src[j + 7]];
+        acc |= c0 | c1 | c2 | c3 | c4 | c5 | c6 | c7;
+        const uint64_t w = (uint64_t)c0 | (uint64_t)c1 << 8 | (uint64_t)c2 << 16 | (uint64_t)c3 << 24 | (uint64_t)c4 << 32 |
+                           (uint64_t)c5 << 40 | (uint64_t)c6 << 48 | (uint64_t)c7 << 56;
+        memcpy(dst + j, &w, 8);
+    }
+    for (; j < H; ++j) { const uint8_t cd = lut8[src[j]]; acc |= cd; dst[j] = cd; }
+    return (acc & 0x80u) == 0;
 }
 
 // When a chunk has too few reads to fill the GPU with one warp per read (a single HaplotypeCaller region is ~100 reads),
@@ -306,7 +332,22 @@ void plan_chunk(const gphmm_batch *b, int64_t u0, int64_t u1, bool force_fp64, b
     std::vector<uint8_t> bucket_of;
     raw.reserve((size_t)(c.r_hi - c.r_lo));
     bucket_of.reserve((size_t)(c.r_hi - c.r_lo));
-    c.streams.reserve((size_t)(u1 - u0) * 64);
+    {
+        // exact size of the full streams, upper bound of the shared ones (every pass <= its haplotype + END + 32 pad columns)
+        size_t total = 0, n_h = 0;
+        for (int64_t u = u0; u < u1; ++u) {
+            const gphmm_unit &un = b->units[u];
+            const size_t nh = (size_t)(un.hap_end - un.hap_begin);
+            total += (nh ? (size_t)(b->hap_off[un.hap_end] - b->hap_off[un.hap_begin]) : 0) + nh + STREAM_PAD;
+            n_h += nh;
+        }
+        c.streams.reserve(total + 64);
+        c.sstreams.reserve(total + n_h * 32 + (size_t)(u1 - u0) * STREAM_PAD * (size_t)std::max<int64_t>(1, want_groups) + 64);
+        c.hap_len.reserve(n_h); c.hap_stream_off.reserve(n_h); c.pass_info.reserve(n_h);
+        c.units.reserve((size_t)(u1 - u0)); c.unit_sched.reserve((size_t)(u1 - u0)); c.segments.reserve(n_h * 5);
+    }
+    SharingScratch scratch;
+    std::vector<int> order;
     uint32_t bucket_count[N_FP32_BUCKETS] = {0};
     for (int64_t u = u0; u < u1; ++u) {
         const gphmm_unit &un = b->units[u];
@@ -320,14 +361,14 @@ void plan_chunk(const gphmm_batch *b, int64_t u0, int64_t u1, bool force_fp64, b
         d.ref_hap = -1;
         d.keep_base = c.n_keep;
         c.n_keep += nr;
-        c.streams.insert(c.streams.end(), STREAM_PAD, (uint8_t)CODE_NULL);  // fill/drain codes of the fast kernels
+        c.streams.append_fill(STREAM_PAD, (uint8_t)CODE_NULL);  // fill/drain codes of the fast kernels
         const uint32_t stream_off = (uint32_t)c.streams.size();
         uint32_t max_h = 1;
         int64_t sum_h = 0;
         {
             const int64_t hap_bytes = nh ? b->hap_off[un.hap_end] - b->hap_off[un.hap_begin] : 0;
             size_t w = c.streams.size();
-            c.streams.resize(w + (size_t)hap_bytes + nh);
+            c.streams.append_raw((size_t)hap_bytes + nh);
             uint8_t *dst = c.streams.data();
             for (int64_t h = un.hap_begin; h < un.hap_end; ++h) {
                 const int64_t ho = b->hap_off[h];
@@ -335,16 +376,8 @@ void plan_chunk(const gphmm_batch *b, int64_t u0, int64_t u1, bool force_fp64, b
                 c.hap_len.push_back(H);
                 c.hap_stream_off.push_back((uint32_t)w);
                 const uint8_t *src = b->hap_bases + ho;
-                // table lookup per byte with no branch in the loop; a byte value seen for the first time (0xff) is rare:
-                // give it a code and redo the haplotype
-                for (;;) {
-                    uint8_t unknown = 0;
-                    for (uint32_t j = 0; j < H; ++j) {
-                        const uint8_t code = lut8[src[j]];
-                        unknown |= (uint8_t)(code == 0xff);
-                        dst[w + j] = code;
-                    }
-                    if (!unknown) break;
+                // a byte value seen for the first time is rare: give it a code and redo the haplotype
+                while (!encode_hap(dst + w, src, H, lut8)) {
                     for (uint32_t j = 0; j < H; ++j)
                         if (lut8[src[j]] == 0xff) {
                             if (c.n_codes >= MAX_CODES) throw Error(GPHMM_ERR_ALPHABET, "too many distinct haplotype byte values");
@@ -372,10 +405,10 @@ void plan_chunk(const gphmm_batch *b, int64_t u0, int64_t u1, bool force_fp64, b
         const int n_groups = force_fp64 ? 1 : (int)std::max<int64_t>(1, std::min<int64_t>(want_groups, nh));
         const uint32_t sched_first = (uint32_t)c.unit_sched.size();
         {
-            const std::vector<int> order = sorted_hap_order(b, un, share && !force_fp64);
+            sorted_hap_order(b, un, share && !force_fp64, order);
             for (int gi = 0; gi < n_groups; ++gi) {
                 const int g0 = (int)((int64_t)nh * gi / n_groups), g1 = (int)((int64_t)nh * (gi + 1) / n_groups);
-                c.unit_sched.push_back(plan_unit_sharing(b, un, d.hap_first, share && !force_fp64, c, fast_read_len, order, g0, g1 - g0));
+                c.unit_sched.push_back(plan_unit_sharing(b, un, d.hap_first, share && !force_fp64, c, fast_read_len, order, g0, g1 - g0, scratch));
             }
         }
         if (nh == 0) continue;

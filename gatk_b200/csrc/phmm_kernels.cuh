@@ -1145,4 +1145,25 @@ __global__ void __launch_bounds__(32) phmm_exact_f64_kernel(const KernelArgs g, 
     }
 }
 
+// Measurement aid: independent FFMA chains with constant-bank multiplier and addend (kernel parameters), the operand form
+// of the flat-quality forward kernel.  gphmm_measure_fp32_peak times it; bench.py reports it as roofline.peak_measured.
+template <int ILP, int ITER>
+__global__ void __launch_bounds__(256) phmm_ffma_peak_kernel(float *sink, const float a, const float b)
+{
+    float x[ILP];
+#pragma unroll
+    for (int i = 0; i < ILP; ++i) x[i] = threadIdx.x * 1e-3f + i;
+#pragma unroll 1
+    for (int it = 0; it < ITER; it += 8) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+#pragma unroll
+            for (int i = 0; i < ILP; ++i) x[i] = __fmaf_rn(x[i], a, b);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < ILP; ++i) s += x[i];
+    sink[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 }  // namespace phmm_dev

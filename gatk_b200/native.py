@@ -78,7 +78,7 @@ UNIT_DTYPE = np.dtype([("read_begin", "<i8"), ("read_end", "<i8"), ("hap_begin",
 
 EXPORTS = ["gphmm_abi_version", "gphmm_device_count", "gphmm_strerror", "gphmm_create", "gphmm_destroy",
            "gphmm_last_error", "gphmm_compute", "gphmm_compute_regions", "gphmm_submit_regions", "gphmm_pd_compute", "gphmm_sw_align", "gphmm_submit", "gphmm_wait", "gphmm_prepare", "gphmm_run_prepared",
-           "gphmm_release_prepared", "gphmm_get_stats", "gphmm_reset_stats", "gphmm_plan_stats", "gphmm_host_alloc", "gphmm_host_free"]
+           "gphmm_release_prepared", "gphmm_get_stats", "gphmm_reset_stats", "gphmm_plan_stats", "gphmm_measure_fp32_peak", "gphmm_host_alloc", "gphmm_host_free"]
 
 
 def lib_path():
@@ -135,6 +135,8 @@ def load_library():
     L.gphmm_get_stats.argtypes = [ctypes.c_void_p, ctypes.POINTER(Stats)]
     L.gphmm_reset_stats.restype = None
     L.gphmm_reset_stats.argtypes = [ctypes.c_void_p]
+    L.gphmm_measure_fp32_peak.restype = ctypes.c_int
+    L.gphmm_measure_fp32_peak.argtypes = [ctypes.c_void_p, ctypes.c_double, ctypes.POINTER(ctypes.c_double)]
     L.gphmm_plan_stats.restype = ctypes.c_int
     L.gphmm_plan_stats.argtypes = [ctypes.POINTER(_Batch), ctypes.c_int, ctypes.POINTER(ctypes.c_int64)]
     L.gphmm_host_alloc.restype = ctypes.c_void_p
@@ -236,6 +238,24 @@ class Batch:
         b.units = self.units.ctypes.data
         b.n_units = len(self.units)
         return b
+
+    @staticmethod
+    def concat(batches, pinned=False):
+        """The batches back to back as one batch (units, reads, haplotypes and output slots renumbered): what one handle
+        over several GPUs is given when every shard of a sharded job is collected in one process."""
+        cat = lambda xs, dt: np.concatenate(xs) if len(xs) else np.zeros(0, dt)
+        read_off, hap_off, units = [np.zeros(1, np.int64)], [np.zeros(1, np.int64)], []
+        r0 = h0 = b0 = c0 = o0 = 0
+        for b in batches:
+            read_off.append(b.read_off[1:] + b0)
+            hap_off.append(b.hap_off[1:] + c0)
+            u = b.units.copy()
+            u["read_begin"] += r0; u["read_end"] += r0; u["hap_begin"] += h0; u["hap_end"] += h0; u["out_off"] += o0
+            units.append(u)
+            r0 += b.n_reads; h0 += b.n_haps; b0 += int(b.read_off[-1]); c0 += int(b.hap_off[-1]); o0 += b.n_out
+        cols = [cat([getattr(b, name) for b in batches], np.uint8) for name in ("read_bases", "base_q", "ins_q", "del_q", "gcp", "hap_bases")]
+        return Batch(cols[0], cols[1], cols[2], cols[3], cols[4], cat(read_off, np.int64), cols[5], cat(hap_off, np.int64),
+                     cat(units, UNIT_DTYPE), pinned=pinned)
 
     @staticmethod
     def single_unit(reads, haps):
@@ -463,3 +483,9 @@ class GpuPhmm:
 
     def reset_stats(self):
         self._L.gphmm_reset_stats(self._h)
+
+    def measure_fp32_peak(self, millis=20.0):
+        """Sustained FP32 FFMA rate of the handle's first device in TFLOP/s (gphmm_measure_fp32_peak; measurement aid)."""
+        v = ctypes.c_double(0.0)
+        self._check(self._L.gphmm_measure_fp32_peak(self._h, ctypes.c_double(millis), ctypes.byref(v)))
+        return v.value

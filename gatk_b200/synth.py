@@ -93,6 +93,17 @@ def config1(seed=SEED, pinned=False):
     return _assemble([(haps, b, q, i, d, g, read_lens)], pinned=pinned)
 
 
+def config1_many(n_regions, seed=SEED, pinned=False):
+    """n_regions regions of the configs[0] shape (128 reads x 150 bp x 8 haplotypes of 200-300 bp), region k seeded seed + k."""
+    regions = []
+    for k in range(n_regions):
+        rng = np.random.default_rng(seed + k)
+        read_lens = np.full(128, 150, dtype=np.int64)
+        haps, b, q, i, d, g = _region(rng, 128, read_lens, 8, int(rng.integers(200, 301)))
+        regions.append((haps, b, q, i, d, g, read_lens))
+    return _assemble(regions, pinned=pinned)
+
+
 def config2(n_regions=10000, seed=SEED, pinned=False, first_region=0):
     """BASELINE.json configs[1]: 30x WGS-like batch: n_regions active regions, reads/region ~ Poisson(60),
     250 bp reads (10 % clipped to U[100,250]), 4-16 haplotypes of 300-500 bp."""

@@ -220,6 +220,11 @@ void gphmm_reset_stats(gphmm_t *h);
  *   out[8] chunks, out[9] tasks.  Used by tests and for sizing; needs no device. */
 int gphmm_plan_stats(const gphmm_batch *batch, int prefix_sharing, int64_t out[10]);
 
+/* Measurement aid (bench.py "roofline.peak_measured"): runs a dense FFMA kernel with constant-bank operands -- the
+ * operand form of the flat-quality forward kernel -- on the handle's first device for about `millis` milliseconds and
+ * returns the sustained FP32 rate in TFLOP/s (2 flop per FFMA lane).  Not part of the likelihood path. */
+int gphmm_measure_fp32_peak(gphmm_t *h, double millis, double *tflops);
+
 /* Pinned host memory for callers that want zero-copy staging. */
 void *gphmm_host_alloc(size_t bytes);
 void gphmm_host_free(void *p);

@@ -26,6 +26,14 @@ def _worker(rank, world, port, q):
     b = synth.config2(n, first_region=first)
     secs, tot = sharding.reduce_timing([1.0 + rank, 5.0 - rank], [b.cells(), b.pairs()])
     lo, hi = sharding.split_units(7, rank, world)
+    whole = sharding.collect_shards(b, rank, world, tag="gphmm_test")
+    if rank == 0:
+        # the collected batch is the unsharded one, field by field
+        ref = synth.config2(n * world)
+        for name in ("read_bases", "base_q", "ins_q", "del_q", "gcp", "read_off", "hap_bases", "hap_off", "units"):
+            assert np.array_equal(getattr(whole, name), getattr(ref, name)), name
+    else:
+        assert whole is None
     q.put((rank, first, n, b.cells(), b.pairs(), secs, tot, lo, hi, bytes(b.read_bases[:16])))
     dist.destroy_process_group()
 
