@@ -173,6 +173,10 @@ struct ChunkPlan {
     uint32_t n_keep = 0;                   // region steps: keep flags of the chunk (sum of n_reads over its units)
     int n_sym = 0;                         // symmetric-quality classes (ins == del per base, flat gcp): their gcp values
     uint8_t sym_qc[MAX_SYM_CLASSES];
+    // small chunks (a per-region call): the host classifies every read itself, so the classify kernel and the forward
+    // launches that would find no read of theirs are skipped (launch latency is what such a call consists of)
+    std::vector<uint8_t> host_class;       // per span read: class id as phmm_classify_kernel would write it; empty = classify on the device
+    uint32_t class_count[N_FP32_BUCKETS][MAX_FLAT_CLASSES + MAX_SYM_CLASSES + 1];  // tasks per (bucket, class); last = general
 };
 
 #include "host_planner.inl"
@@ -186,11 +190,12 @@ struct DeviceChunk {
     DevBuf work;    // sums(float or double) | out(double) | rescue tasks | rescue sums | counters | err
     DevBuf bnd;     // boundary rows of striped kernels
     PinBuf h_meta;  // pinned image of meta
-    PinBuf h_reads; // pinned bounce buffer when the caller's arrays are pageable
     PinBuf h_out;   // pinned result buffer (out doubles + [keep flags] + counters + err)
     PinBuf h_modq;  // region steps: pinned image of the modified base/ins/del qualities (only when the caller wants them)
     PinBuf h_raw;   // region steps: pinned image of the un-normalised likelihoods (only when the caller wants them)
     size_t read_stride = 0;
+    uint8_t *reads_dev = nullptr;  // the five read arrays on the device: `reads`, or inside `meta` for small chunks (one DMA for everything)
+    size_t off_reads = 0, off_hclass = 0;
     size_t off_read_off = 0, off_streams = 0, off_hap_len = 0, off_hap_stream_off = 0, off_units = 0, off_tasks = 0, meta_bytes = 0;
     size_t off_sstreams = 0, off_pass = 0, off_segs = 0, off_sched = 0, off_mapq = 0;
     DevBuf snap;    // snapshot slabs of the fast kernels (prefix sharing)
@@ -209,7 +214,7 @@ struct DeviceChunk {
     struct Device *lazy_dev = nullptr;
     bool busy = false;
     void release() {
-        reads.release(); meta.release(); work.release(); bnd.release(); snap.release(); deep.release(); h_meta.release(); h_reads.release(); h_out.release(); h_modq.release(); h_raw.release();
+        reads.release(); meta.release(); work.release(); bnd.release(); snap.release(); deep.release(); h_meta.release(); h_out.release(); h_modq.release(); h_raw.release();
         if (ev_start) cudaEventDestroy(ev_start);
         if (ev_f32) cudaEventDestroy(ev_f32);
         if (ev_f64) cudaEventDestroy(ev_f64);
@@ -448,7 +453,14 @@ void upload_chunk(Device &dev, DeviceChunk &dc, const gphmm_batch *b, const Chun
     const double t0 = now_ms();
     const size_t span = (size_t)(c.base_hi - c.base_lo);
     dc.read_stride = align_up(span, 16);
-    dc.reads.reserve(std::max<size_t>(dc.read_stride * 5, 16));
+    const uint8_t *src[5] = {b->read_bases, b->base_q, b->ins_q, b->del_q, b->gcp};
+    bool pinned = true;
+    if (span > 0)
+        for (int a = 0; a < 5; ++a) pinned = pinned && is_pinned(src[a] + c.base_lo);
+    // pageable arrays need a pinned bounce copy anyway, and for a small chunk one copy + ONE DMA beats five DMAs:
+    // the read arrays then travel inside the metadata blob
+    const bool inline_reads = span > 0 && (!pinned || span * 5 <= ((size_t)256 << 10));
+    if (!inline_reads) dc.reads.reserve(std::max<size_t>(dc.read_stride * 5, 16));
     // metadata blob
     size_t o = 0;
     dc.off_read_off = o; o = align_up(o + c.read_off.size() * 4, 16);
@@ -462,6 +474,8 @@ void upload_chunk(Device &dev, DeviceChunk &dc, const gphmm_batch *b, const Chun
     dc.off_segs = o; o = align_up(o + c.segments.size() * sizeof(Segment), 16);
     dc.off_sched = o; o = align_up(o + c.unit_sched.size() * sizeof(UnitSched), 16);
     dc.off_mapq = o; o = align_up(o + (rs ? c.read_off.size() : 0), 16);
+    dc.off_hclass = o; o = align_up(o + c.host_class.size(), 16);
+    dc.off_reads = o; o = align_up(o + (inline_reads ? dc.read_stride * 5 : 0), 16);
     dc.meta_bytes = std::max<size_t>(o, 16);
     dc.meta.reserve(dc.meta_bytes);
     dc.h_meta.reserve(dc.meta_bytes);
@@ -478,6 +492,10 @@ void upload_chunk(Device &dev, DeviceChunk &dc, const gphmm_batch *b, const Chun
     memcpy(hm + dc.off_pass, c.pass_info.data(), c.pass_info.size() * sizeof(PassInfo));
     memcpy(hm + dc.off_segs, c.segments.data(), c.segments.size() * sizeof(Segment));
     memcpy(hm + dc.off_sched, c.unit_sched.data(), c.unit_sched.size() * sizeof(UnitSched));
+    if (!c.host_class.empty()) memcpy(hm + dc.off_hclass, c.host_class.data(), c.host_class.size());
+    if (inline_reads)
+        for (int a = 0; a < 5; ++a) memcpy(hm + dc.off_reads + a * dc.read_stride, src[a] + c.base_lo, span);
+    dc.reads_dev = inline_reads ? (uint8_t *)dc.meta.p + dc.off_reads : (uint8_t *)dc.reads.p;
     if (rs) {
         if (c.r_hi > c.r_lo) memcpy(hm + dc.off_mapq, rs->mapq + c.r_lo, (size_t)(c.r_hi - c.r_lo));
         if (rs->ref_hap) {
@@ -503,19 +521,10 @@ void upload_chunk(Device &dev, DeviceChunk &dc, const gphmm_batch *b, const Chun
     dc.work.reserve(dc.work_bytes);
     dc.h_out.reserve(d2h_bytes);
 
-    const uint8_t *src[5] = {b->read_bases, b->base_q, b->ins_q, b->del_q, b->gcp};
     int64_t h2d = 0;
-    if (span > 0) {
-        bool pinned = true;
-        for (int a = 0; a < 5; ++a) pinned = pinned && is_pinned(src[a] + c.base_lo);
-        if (!pinned) dc.h_reads.reserve(dc.read_stride * 5);
+    if (span > 0 && !inline_reads) {
         for (int a = 0; a < 5; ++a) {
-            const void *from = src[a] + c.base_lo;
-            if (!pinned) {
-                memcpy((uint8_t *)dc.h_reads.p + a * dc.read_stride, from, span);
-                from = (uint8_t *)dc.h_reads.p + a * dc.read_stride;
-            }
-            CK(cudaMemcpyAsync((uint8_t *)dc.reads.p + a * dc.read_stride, from, span, cudaMemcpyHostToDevice, st));
+            CK(cudaMemcpyAsync((uint8_t *)dc.reads.p + a * dc.read_stride, src[a] + c.base_lo, span, cudaMemcpyHostToDevice, st));
             h2d += (int64_t)span;
         }
     }
@@ -597,16 +606,17 @@ int launch_chunk(Device &dev, DeviceChunk &dc, const ChunkPlan &c, cudaStream_t 
     uint32_t *counters = (uint32_t *)(work + dc.off_counters);
     // counters and error flag start at 0; the keep flags and the alignment gaps of the downloaded block are cleared with them
     // (compute-sanitizer initcheck then sees a fully initialised D2H source)
-    CK(cudaMemsetAsync(work + dc.off_keep, 0, (dc.off_err + 16) - dc.off_keep, st));
     {
-        const size_t out_end = dc.off_out + (size_t)std::max<uint32_t>(c.n_pairs, 1) * 8;
-        if (dc.off_keep > out_end) CK(cudaMemsetAsync(work + out_end, 0, dc.off_keep - out_end, st));
+        const size_t out_end = dc.off_out + (size_t)std::max<uint32_t>(c.n_pairs, 1) * 8;  // <= off_keep: one memset covers the gap too
+        CK(cudaMemsetAsync(work + out_end, 0, (dc.off_err + 16) - out_end, st));
     }
+    // a small chunk is a chain of a few short kernels: keep it on ONE stream (a cross-stream event costs more than it hides)
+    if (c.cells < LAZY_RESCUE_CELLS) tail = st;
     CK(cudaEventRecord(dc.ev_start, st));
 
     KernelArgs ka;
     memset(&ka, 0, sizeof ka);
-    ka.rd_bases = (const uint8_t *)dc.reads.p;
+    ka.rd_bases = (const uint8_t *)dc.reads_dev;
     ka.rd_q = ka.rd_bases + dc.read_stride;
     ka.rd_i = ka.rd_q + dc.read_stride;
     ka.rd_d = ka.rd_i + dc.read_stride;
@@ -682,12 +692,16 @@ int launch_chunk(Device &dev, DeviceChunk &dc, const ChunkPlan &c, cudaStream_t 
                 dc.h_modq.reserve(dc.read_stride * 3);
                 const size_t span = (size_t)(c.base_hi - c.base_lo);  // without the alignment tail of each array
                 for (int a = 0; a < 3 && span; ++a)
-                    CK(cudaMemcpyAsync((uint8_t *)dc.h_modq.p + a * dc.read_stride, (uint8_t *)dc.reads.p + (a + 1) * dc.read_stride, span,
+                    CK(cudaMemcpyAsync((uint8_t *)dc.h_modq.p + a * dc.read_stride, dc.reads_dev + (a + 1) * dc.read_stride, span,
                                        cudaMemcpyDeviceToHost, st));
             }
         }
-        // 1. per-read flat-quality classification (device side; the host only sampled candidate classes)
-        {
+        // 1. per-read flat-quality classification: on the device (the host only sampled candidate classes), except for
+        // small chunks, which the planner classified itself
+        const bool host_classes = !c.host_class.empty() && !opt.rs;
+        if (host_classes) {
+            ka.read_class = meta + dc.off_hclass;
+        } else {
             ClassifyArgs ca;
             memset(&ca, 0, sizeof ca);
             ca.rd_i = ka.rd_i; ca.rd_d = ka.rd_d; ca.rd_c = ka.rd_c;
@@ -703,8 +717,10 @@ int launch_chunk(Device &dev, DeviceChunk &dc, const ChunkPlan &c, cudaStream_t 
                 CK(cudaGetLastError());
                 ++launches;
             }
+            ka.read_class = (const uint8_t *)(work + dc.off_class);
         }
-        ka.read_class = (const uint8_t *)(work + dc.off_class);
+        // with host-side classes the launches that would find no read of theirs are skipped
+        auto has_work = [&](int bucket, int cls) { return !host_classes || bucket >= 8 || c.class_count[bucket][cls] > 0; };
 
         if (opt.force_fp64) {
             // --native-pair-hmm-use-double-precision: no fp32 pass at all.  NaN sums make the epilogue put EVERY pair on
@@ -767,6 +783,7 @@ int launch_chunk(Device &dev, DeviceChunk &dc, const ChunkPlan &c, cudaStream_t 
             ka.bnd_stride = k == 8 ? c.max_stream_len : 0;
             if (k < 8) {
                 for (int cl = 0; cl < c.n_classes; ++cl) {
+                    if (!has_work(k, cl)) continue;
                     FlatCoef fc;
                     const int qi = c.class_qi[cl], qd = c.class_qd[cl], qc = c.class_qc[cl];
                     const double ei = tb.eps[qi], ed = tb.eps[qd], ec = tb.eps[qc], tIM = 1.0 - ec;
@@ -790,6 +807,7 @@ int launch_chunk(Device &dev, DeviceChunk &dc, const ChunkPlan &c, cudaStream_t 
                     launch_on(dev.info(FLAT_KEY + k, c.n_codes), n, N_FP32_BUCKETS + 8 * cl + k, args);
                 }
                 for (int cl = 0; cl < c.n_sym; ++cl) {
+                    if (!has_work(k, MAX_FLAT_CLASSES + cl)) continue;
                     // symmetric-quality reads (ins == del per base, flat gcp): b = tIM, g = d = eps(gcp), tmi = kappa
                     FlatCoef fc;
                     const int qc = c.sym_qc[cl];
@@ -809,6 +827,7 @@ int launch_chunk(Device &dev, DeviceChunk &dc, const ChunkPlan &c, cudaStream_t 
                     launch_on(dev.info(SYM_KEY + k, c.n_codes), n, N_FP32_BUCKETS + 8 * (MAX_FLAT_CLASSES + cl) + k, args);
                 }
             }
+            if (!has_work(k, MAX_FLAT_CLASSES + MAX_SYM_CLASSES)) continue;
             ka.counter = counters + k;
             if (k < 8) {
                 ka.snap = (float *)((uint8_t *)dc.snap.p + slab_cursor);
@@ -1025,7 +1044,8 @@ namespace {
 struct PlanPool {
     const gphmm_batch *b;
     const std::vector<std::pair<int64_t, int64_t>> &chunks;
-    bool f64, share, pcr_hint;
+    bool f64, share;
+    int steps_mode;  // 0 = plain likelihoods, 1 = region steps, 2 = region steps with the PCR indel model (plan_chunk)
     Stats &stats;
     std::vector<std::unique_ptr<ChunkPlan>> ready;
     std::vector<char> done;
@@ -1038,8 +1058,8 @@ struct PlanPool {
     std::vector<std::thread> threads;
 
     PlanPool(const gphmm_batch *b_, const std::vector<std::pair<int64_t, int64_t>> &c, bool f64_, bool share_, int n_threads, Stats &st,
-             bool pcr_hint_ = false)
-        : b(b_), chunks(c), f64(f64_), share(share_), pcr_hint(pcr_hint_), stats(st), ready(c.size()), done(c.size(), 0), err_code(c.size(), 0),
+             int steps_mode_ = 0)
+        : b(b_), chunks(c), f64(f64_), share(share_), steps_mode(steps_mode_), stats(st), ready(c.size()), done(c.size(), 0), err_code(c.size(), 0),
           err_text(c.size()) {
         n_threads = c.size() <= 1 ? 0 : std::max(1, std::min<int>(n_threads, (int)c.size()));  // one chunk: plan inline, no threads
         lookahead = (size_t)n_threads + N_SLOTS;
@@ -1067,7 +1087,7 @@ struct PlanPool {
             std::string text;
             const double t0 = now_ms();
             try {
-                plan_chunk(b, chunks[ci].first, chunks[ci].second, f64, share, *p, pcr_hint);
+                plan_chunk(b, chunks[ci].first, chunks[ci].second, f64, share, *p, steps_mode);
             } catch (const Error &e) {
                 code = e.code; text = e.what();
             } catch (const std::exception &e) {
@@ -1090,7 +1110,7 @@ struct PlanPool {
         if (threads.empty()) {  // synchronous planning (single-chunk batches: the per-region JNI call)
             std::unique_ptr<ChunkPlan> p(new ChunkPlan());
             const double t0 = now_ms();
-            plan_chunk(b, chunks[ci].first, chunks[ci].second, f64, share, *p, pcr_hint);
+            plan_chunk(b, chunks[ci].first, chunks[ci].second, f64, share, *p, steps_mode);
             std::lock_guard<std::mutex> lk(stats.mu);
             stats.s.host_stage_ms += now_ms() - t0;
             return p;
@@ -1179,7 +1199,7 @@ int run_batch(gphmm *h, const gphmm_batch *b, double *out, const gphmm_region_st
         // (GATK passes its default of 4 explicitly: with several devices the floor applies to explicit values too)
         const int asked = h->cfg.host_threads > 0 ? h->cfg.host_threads : 4;
         const int n_threads = h->devices.size() > 1 ? std::max<int>(asked, 3 * (int)h->devices.size()) : asked;
-        PlanPool pool(b, chunks, false, h->cfg.no_prefix_sharing == 0, n_threads, h->stats, rs && rs->pcr_rate_factor != 0.0);
+        PlanPool pool(b, chunks, false, h->cfg.no_prefix_sharing == 0, n_threads, h->stats, rs ? (rs->pcr_rate_factor != 0.0 ? 2 : 1) : 0);
         if (nd == 1 || chunks.size() == 1) {
             device_loop(h, *h->devices[0], b, chunks, pool, cursor, out, errs[0], rcs[0], rs);
         } else {
@@ -1483,7 +1503,6 @@ int gphmm_prepare(gphmm_t *h, const gphmm_batch *b, gphmm_prepared_t **out) {
             CK(cudaEventCreate(&part->dc.ev_done));
             upload_chunk(dev, part->dc, b, part->plan, dev.streams[0], f64, h->stats);
             CK(cudaStreamSynchronize(dev.streams[0]));
-            part->dc.h_reads.release();
             p->parts.push_back(std::move(part));
         }
         CK(cudaSetDevice(h->ordinals[0]));

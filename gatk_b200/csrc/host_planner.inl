@@ -255,8 +255,12 @@ inline bool encode_hap(uint8_t *dst, const uint8_t *src, uint32_t H, const uint8
 // When a chunk has too few reads to fill the GPU with one warp per read (a single HaplotypeCaller region is ~100 reads),
 // each unit's haplotypes are split into groups and every (read, group) pair becomes a task of its own.
 constexpr int64_t TARGET_TASKS = 148 * 28 * 2;
+constexpr int64_t HOST_CLASSIFY_MAX_READS = 512;  // chunks up to this many reads are classified on the host (per-region calls)
 
-void plan_chunk(const gphmm_batch *b, int64_t u0, int64_t u1, bool force_fp64, bool share, ChunkPlan &c, bool pcr_hint = false) {
+// steps_mode: 0 = plain likelihoods; 1 = the region steps run on the device first (they change the qualities, so only the
+// device can classify the reads); 2 = as 1 with the PCR indel model, which lowers ins and del together.
+void plan_chunk(const gphmm_batch *b, int64_t u0, int64_t u1, bool force_fp64, bool share, ChunkPlan &c, int steps_mode = 0) {
+    const bool pcr_hint = steps_mode == 2;
     c.u0 = u0; c.u1 = u1;
     c.r_lo = INT64_MAX; c.r_hi = 0;
     for (int64_t u = u0; u < u1; ++u) {
@@ -312,6 +316,33 @@ void plan_chunk(const gphmm_batch *b, int64_t u0, int64_t u1, bool force_fp64, b
             }
         }
     }
+
+    // a per-region call: classify every read here with the rules of phmm_classify_kernel (the sampling above visited every
+    // read of such a chunk), so that no classify launch and no forward launch without work is needed
+    c.host_class.clear();
+    if (!force_fp64 && steps_mode == 0 && n_span > 0 && n_span <= HOST_CLASSIFY_MAX_READS) {
+        c.host_class.assign((size_t)n_span, CLASS_GENERAL);
+        for (int64_t r = 0; r < n_span; ++r) {
+            const int64_t o = b->read_off[c.r_lo + r], e = b->read_off[c.r_lo + r + 1];
+            if (e == o) continue;
+            const uint8_t qi = b->ins_q[o], qd = b->del_q[o], qc = b->gcp[o];
+            const size_t n1 = (size_t)(e - o - 1);
+            const bool flat_c = memcmp(b->gcp + o, b->gcp + o + 1, n1) == 0;
+            uint8_t cls = CLASS_GENERAL;
+            if (flat_c && memcmp(b->ins_q + o, b->ins_q + o + 1, n1) == 0 && memcmp(b->del_q + o, b->del_q + o + 1, n1) == 0)
+                for (int k = 0; k < c.n_classes; ++k)
+                    if (c.class_qi[k] == qi && c.class_qd[k] == qd && c.class_qc[k] == qc) cls = (uint8_t)k;
+            if (cls == CLASS_GENERAL && flat_c && c.n_sym > 0 && memcmp(b->ins_q + o, b->del_q + o, n1 + 1) == 0) {
+                uint8_t mx = 0;
+                for (int64_t i = o; i < e; ++i) mx = std::max(mx, b->ins_q[i]);
+                if (mx <= SYM_MAX_GAP_QUAL)
+                    for (int k = 0; k < c.n_sym; ++k)
+                        if (c.sym_qc[k] == qc) cls = (uint8_t)(MAX_FLAT_CLASSES + k);
+            }
+            c.host_class[(size_t)r] = cls;
+        }
+    }
+    memset(c.class_count, 0, sizeof c.class_count);
 
     // haplotype alphabet of the chunk: A C G T N are fixed codes, any other byte value gets the next free code
     uint8_t lut8[256];
@@ -428,6 +459,10 @@ void plan_chunk(const gphmm_batch *b, int64_t u0, int64_t u1, bool force_fp64, b
                 raw.push_back(t);
                 bucket_of.push_back(bucket);
                 ++bucket_count[bucket];
+            }
+            if (!c.host_class.empty()) {
+                const uint8_t cls = c.host_class[rl];
+                c.class_count[bucket][cls == CLASS_GENERAL ? MAX_FLAT_CLASSES + MAX_SYM_CLASSES : cls] += (uint32_t)n_t;
             }
             c.cells += (int64_t)R * sum_h;
         }
