@@ -118,9 +118,20 @@ struct PinBuf {
 };
 
 constexpr int N_SLOTS = 3;         // chunks in flight per device: one computing, one finishing (epilogue/D2H), one being staged
-constexpr int N_FP32_BUCKETS = 9;  // K = 1..8 plain, bucket 8 = striped K=8 (reads of 256+ bases)
-constexpr int N_AUX = N_FP32_BUCKETS + 8 * (MAX_FLAT_CLASSES + MAX_SYM_CLASSES);  // side streams: general buckets + flat (class, bucket)
-constexpr int N_COUNTERS = 128;    // [0..8] general fp32 buckets, [9] fp64 queue, [10] n_rescue, [11] n_deep, [120] deep cursor,
+// Task buckets: 0..7 = K = 1..8 rows per lane (32 lanes per read), 8 = striped K=8 (reads of 255+ bases), 9..12 = half-warp
+// buckets (two reads per warp, 16 lanes each): K = 10, 12, 14, 16 rows per lane for reads of 128..159 / ..191 / ..223 / ..254 bases
+constexpr int FIRST_PAIR_BUCKET = 9;
+constexpr int N_PAIR_BUCKETS = 4;
+constexpr int N_FP32_BUCKETS = FIRST_PAIR_BUCKET + N_PAIR_BUCKETS;
+constexpr int N_CLASSES_MAX = MAX_FLAT_CLASSES + MAX_SYM_CLASSES;
+constexpr int N_AUX = N_FP32_BUCKETS + (8 + N_PAIR_BUCKETS) * N_CLASSES_MAX;  // side streams: general buckets + flat (class, bucket)
+inline bool is_pair_bucket(int k) { return k >= FIRST_PAIR_BUCKET; }
+inline int pair_bucket_rows(int k) { return 10 + 2 * (k - FIRST_PAIR_BUCKET); }
+// reads of a half-warp bucket that are not flat-quality run the full-warp general kernel with K = 6, 7, 8, 8 rows per lane
+inline int general_bucket_of(int k) { return !is_pair_bucket(k) ? k : std::min(7, 5 + (k - FIRST_PAIR_BUCKET)); }
+inline int pair_bucket_of_read(uint32_t R) { return R < 128 || R > 254 ? -1 : FIRST_PAIR_BUCKET + (R < 160 ? 0 : R < 192 ? 1 : R < 224 ? 2 : 3); }
+constexpr int N_COUNTERS = 256;    // [0..8] general fp32 buckets, [9] fp64 queue, [10] n_rescue, [11] n_deep, [120] deep cursor,
+                                   // [128 + p] general kernel on half-warp bucket p, [136 + 4*c + p] half-warp flat kernels: class c
                                    // [16 + 8*c + k] flat-quality kernels: class c, bucket k
 
 // Growable byte buffer without value-initialisation (std::vector<uint8_t>::resize would memset what is overwritten next).
@@ -339,6 +350,27 @@ KernelInfo sym_kernel(int bucket, int n_codes) {
     }
 }
 
+template <int K, bool SYM> KernelInfo flat16_kernel_info(int n_codes) {
+    KernelInfo ki;
+    auto fn = phmm_flat_f32_kernel<K, SYM, 16>;
+    ki.fn = (const void *)fn;
+    ki.smem = prior_table_bytes<float, K>(n_codes);
+    raise_dyn_smem((const void *)fn, ki.smem);
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ki.ctas_per_sm, fn, 32, ki.smem));
+    if (ki.ctas_per_sm < 1) throw Error(GPHMM_ERR_ALPHABET, "prior table does not fit in shared memory");
+    reserve_headroom(ki, (const void *)fn);
+    return ki;
+}
+
+KernelInfo flat16_kernel(int p, bool sym, int n_codes) {
+    switch (p) {
+        case 0: return sym ? flat16_kernel_info<10, true>(n_codes) : flat16_kernel_info<10, false>(n_codes);
+        case 1: return sym ? flat16_kernel_info<12, true>(n_codes) : flat16_kernel_info<12, false>(n_codes);
+        case 2: return sym ? flat16_kernel_info<14, true>(n_codes) : flat16_kernel_info<14, false>(n_codes);
+        default: return sym ? flat16_kernel_info<16, true>(n_codes) : flat16_kernel_info<16, false>(n_codes);
+    }
+}
+
 KernelInfo fp64_kernel(int n_codes) { return kernel_info<double, 4, true>(n_codes); }
 
 KernelInfo flat_fp64_kernel(int n_codes) {
@@ -357,9 +389,13 @@ struct Stats {
     gphmm_stats s{};
 };
 
-constexpr int FLAT_KEY = 16;      // Device::info key of the flat-quality kernel of bucket k is FLAT_KEY + k
-constexpr int FLAT_F64_KEY = 32;  // ... and of phmm_flat_f64_kernel
-constexpr int SYM_KEY = 48;       // symmetric-quality kernel of bucket k is SYM_KEY + k
+// Device::info keys: 0..8 = general fp32 kernel of bucket k, then
+constexpr int FP64_KEY = 9;       // phmm_forward_kernel<double, 4, striped>
+constexpr int FLAT_KEY = 16;      // flat-quality kernel of bucket k < 8 is FLAT_KEY + k, of half-warp bucket p FLAT_KEY + 8 + p
+constexpr int FLAT_F64_KEY = 32;  // phmm_flat_f64_kernel
+constexpr int SYM_KEY = 48;       // symmetric-quality kernel of bucket k < 8 is SYM_KEY + k, of half-warp bucket p SYM_KEY + 8 + p
+inline int flat_key(int bucket, bool sym) { return (sym ? SYM_KEY : FLAT_KEY) + (is_pair_bucket(bucket) ? 8 + bucket - FIRST_PAIR_BUCKET : bucket); }
+inline size_t slab_per_cta(int bucket) { return snap_slab_bytes(is_pair_bucket(bucket) ? pair_bucket_rows(bucket) : 8); }
 
 // One CTA per resident slot (the occupancy already includes the headroom of reserve_headroom()).
 inline uint32_t persistent_grid(uint32_t n_tasks, int n_sms, int ctas_per_sm) {
@@ -374,10 +410,13 @@ struct Device {
         const int key = bucket * 1024 + n_codes;
         auto it = kinfo.find(key);
         if (it == kinfo.end())
-            it = kinfo.emplace(key, bucket < N_FP32_BUCKETS ? fp32_kernel(bucket, n_codes)
-                                    : bucket == N_FP32_BUCKETS ? fp64_kernel(n_codes)
+            it = kinfo.emplace(key, bucket < FP64_KEY ? fp32_kernel(bucket, n_codes)
+                                    : bucket == FP64_KEY ? fp64_kernel(n_codes)
                                     : bucket == FLAT_F64_KEY ? flat_fp64_kernel(n_codes)
-                                    : bucket >= SYM_KEY ? sym_kernel(bucket - SYM_KEY, n_codes) : flat_kernel(bucket - FLAT_KEY, n_codes)).first;
+                                    : bucket >= SYM_KEY + 8 ? flat16_kernel(bucket - SYM_KEY - 8, true, n_codes)
+                                    : bucket >= SYM_KEY ? sym_kernel(bucket - SYM_KEY, n_codes)
+                                    : bucket >= FLAT_KEY + 8 ? flat16_kernel(bucket - FLAT_KEY - 8, false, n_codes)
+                                    : flat_kernel(bucket - FLAT_KEY, n_codes)).first;
         return it->second;
     }
     cudaStream_t streams[N_SLOTS] = {nullptr};
@@ -445,6 +484,7 @@ struct RunOptions {
     bool force_fp64 = false;
     bool tristate_off = false;
     const gphmm_region_steps *rs = nullptr;  // gphmm_compute_regions: the steps either side of the kernel
+    bool single_chunk = false;               // the whole batch is this chunk (a per-region call): nothing to overlap with
 };
 
 // Lay the chunk out on the device and copy its inputs (async on `st`).
@@ -545,7 +585,7 @@ int launch_rescue(Device &dev, DeviceChunk &dc, const ChunkPlan &c, KernelArgs k
     int launches = 0;
     uint8_t *work = (uint8_t *)dc.work.p;
     uint32_t *counters = (uint32_t *)(work + dc.off_counters);
-    constexpr int FP64_BUCKET = N_FP32_BUCKETS;
+    constexpr int FP64_BUCKET = FP64_KEY;
     {
         // fp64 redo of the rescue list: persistent grid, task count read on the device
             const KernelInfo &ki = dev.info(FP64_BUCKET, c.n_codes);
@@ -610,8 +650,9 @@ int launch_chunk(Device &dev, DeviceChunk &dc, const ChunkPlan &c, cudaStream_t 
         const size_t out_end = dc.off_out + (size_t)std::max<uint32_t>(c.n_pairs, 1) * 8;  // <= off_keep: one memset covers the gap too
         CK(cudaMemsetAsync(work + out_end, 0, (dc.off_err + 16) - out_end, st));
     }
-    // a small chunk is a chain of a few short kernels: keep it on ONE stream (a cross-stream event costs more than it hides)
-    if (c.cells < LAZY_RESCUE_CELLS) tail = st;
+    // a per-region call is a chain of a few short kernels: keep it on ONE stream (a cross-stream event costs more than it
+    // hides; with several chunks in flight the closing kernels need the high-priority stream, see reserve_headroom)
+    if (opt.single_chunk && c.cells < LAZY_RESCUE_CELLS) tail = st;
     CK(cudaEventRecord(dc.ev_start, st));
 
     KernelArgs ka;
@@ -647,7 +688,7 @@ int launch_chunk(Device &dev, DeviceChunk &dc, const ChunkPlan &c, cudaStream_t 
     ea.rescue_capacity = std::max<uint32_t>(c.n_pairs, 1);
 
     const uint32_t n_tasks_total = (uint32_t)c.tasks.size();
-    constexpr int FP64_BUCKET = N_FP32_BUCKETS;  // key of the <double, 4, striped> kernel in Device::info
+    constexpr int FP64_BUCKET = FP64_KEY;  // key of the <double, 4, striped> kernel in Device::info
 
     // Size the boundary buffer for every striped launch of this chunk before anything is queued.
     {
@@ -720,7 +761,7 @@ int launch_chunk(Device &dev, DeviceChunk &dc, const ChunkPlan &c, cudaStream_t 
             ka.read_class = (const uint8_t *)(work + dc.off_class);
         }
         // with host-side classes the launches that would find no read of theirs are skipped
-        auto has_work = [&](int bucket, int cls) { return !host_classes || bucket >= 8 || c.class_count[bucket][cls] > 0; };
+        auto has_work = [&](int bucket, int cls) { return !host_classes || bucket == 8 || c.class_count[bucket][cls] > 0; };
 
         if (opt.force_fp64) {
             // --native-pair-hmm-use-double-precision: no fp32 pass at all.  NaN sums make the epilogue put EVERY pair on
@@ -739,17 +780,16 @@ int launch_chunk(Device &dev, DeviceChunk &dc, const ChunkPlan &c, cudaStream_t 
             return c.bucket_begin[x + 1] - c.bucket_begin[x] > c.bucket_begin[y + 1] - c.bucket_begin[y];
         });
         // every concurrently running fast/flat launch gets its own snapshot slab (one region per CTA)
-        constexpr size_t SLAB_PER_CTA = (size_t)(MAX_SNAP_SLOTS + 1) * SNAP_REGS * 32 * sizeof(float);
         {
             size_t need = 0;
-            for (int k = 0; k < 8; ++k) {
+            for (int k = 0; k < N_FP32_BUCKETS; ++k) {
                 const uint32_t n = c.bucket_begin[k + 1] - c.bucket_begin[k];
-                if (!n) continue;
-                need += (size_t)persistent_grid(n, dev.n_sms, dev.info(k, c.n_codes).ctas_per_sm) * SLAB_PER_CTA;
+                if (!n || k == 8) continue;
+                need += (size_t)persistent_grid(n, dev.n_sms, dev.info(general_bucket_of(k), c.n_codes).ctas_per_sm) * slab_per_cta(0);
                 for (int cl = 0; cl < c.n_classes; ++cl)
-                    need += (size_t)persistent_grid(n, dev.n_sms, dev.info(FLAT_KEY + k, c.n_codes).ctas_per_sm) * SLAB_PER_CTA;
+                    need += (size_t)persistent_grid(n, dev.n_sms, dev.info(flat_key(k, false), c.n_codes).ctas_per_sm) * slab_per_cta(k);
                 for (int cl = 0; cl < c.n_sym; ++cl)
-                    need += (size_t)persistent_grid(n, dev.n_sms, dev.info(SYM_KEY + k, c.n_codes).ctas_per_sm) * SLAB_PER_CTA;
+                    need += (size_t)persistent_grid(n, dev.n_sms, dev.info(flat_key(k, true), c.n_codes).ctas_per_sm) * slab_per_cta(k);
             }
             dc.snap.reserve(std::max<size_t>(need, 16));
         }
@@ -775,13 +815,16 @@ int launch_chunk(Device &dev, DeviceChunk &dc, const ChunkPlan &c, cudaStream_t 
             const int k = order[oi];
             const uint32_t n = c.bucket_begin[k + 1] - c.bucket_begin[k];
             if (!n) continue;
+            const bool pair = is_pair_bucket(k);
+            const int kp = pair ? k - FIRST_PAIR_BUCKET : k;  // index of the bucket among its kind
             ka.tasks = (const Task *)(meta + dc.off_tasks) + c.bucket_begin[k];
             ka.n_tasks = n;
             ka.n_tasks_ptr = nullptr;
             ka.sums = work + dc.off_sums;
             ka.bnd = k == 8 ? dc.bnd.p : nullptr;
             ka.bnd_stride = k == 8 ? c.max_stream_len : 0;
-            if (k < 8) {
+            ka.pair_tasks = pair ? 1 : 0;
+            if (k != 8) {
                 for (int cl = 0; cl < c.n_classes; ++cl) {
                     if (!has_work(k, cl)) continue;
                     FlatCoef fc;
@@ -800,11 +843,12 @@ int launch_chunk(Device &dev, DeviceChunk &dc, const ChunkPlan &c, cudaStream_t 
                     fc.tim = (float)(tIM / a);
                     fc.class_id = (uint32_t)cl;
                     fc.qi = qi; fc.qd = qd; fc.qc = qc;
-                    ka.counter = counters + 16 + 8 * cl + k;
+                    ka.counter = pair ? counters + 136 + 4 * cl + kp : counters + 16 + 8 * cl + k;
                     ka.snap = (float *)((uint8_t *)dc.snap.p + slab_cursor);
-                    slab_cursor += (size_t)persistent_grid(n, dev.n_sms, dev.info(FLAT_KEY + k, c.n_codes).ctas_per_sm) * SLAB_PER_CTA;
+                    const KernelInfo &ki = dev.info(flat_key(k, false), c.n_codes);
+                    slab_cursor += (size_t)persistent_grid(n, dev.n_sms, ki.ctas_per_sm) * slab_per_cta(k);
                     void *args[] = {&ka, &fc};
-                    launch_on(dev.info(FLAT_KEY + k, c.n_codes), n, N_FP32_BUCKETS + 8 * cl + k, args);
+                    launch_on(ki, n, pair ? N_FP32_BUCKETS + 8 * N_CLASSES_MAX + N_PAIR_BUCKETS * cl + kp : N_FP32_BUCKETS + 8 * cl + k, args);
                 }
                 for (int cl = 0; cl < c.n_sym; ++cl) {
                     if (!has_work(k, MAX_FLAT_CLASSES + cl)) continue;
@@ -820,21 +864,24 @@ int launch_chunk(Device &dev, DeviceChunk &dc, const ChunkPlan &c, cudaStream_t 
                     fc.tim = 1.f;
                     fc.class_id = (uint32_t)(MAX_FLAT_CLASSES + cl);
                     fc.qi = 0; fc.qd = 0; fc.qc = qc;
-                    ka.counter = counters + 16 + 8 * (MAX_FLAT_CLASSES + cl) + k;
+                    const int ci = MAX_FLAT_CLASSES + cl;
+                    ka.counter = pair ? counters + 136 + 4 * ci + kp : counters + 16 + 8 * ci + k;
                     ka.snap = (float *)((uint8_t *)dc.snap.p + slab_cursor);
-                    slab_cursor += (size_t)persistent_grid(n, dev.n_sms, dev.info(SYM_KEY + k, c.n_codes).ctas_per_sm) * SLAB_PER_CTA;
+                    const KernelInfo &ki = dev.info(flat_key(k, true), c.n_codes);
+                    slab_cursor += (size_t)persistent_grid(n, dev.n_sms, ki.ctas_per_sm) * slab_per_cta(k);
                     void *args[] = {&ka, &fc};
-                    launch_on(dev.info(SYM_KEY + k, c.n_codes), n, N_FP32_BUCKETS + 8 * (MAX_FLAT_CLASSES + cl) + k, args);
+                    launch_on(ki, n, pair ? N_FP32_BUCKETS + 8 * N_CLASSES_MAX + N_PAIR_BUCKETS * ci + kp : N_FP32_BUCKETS + 8 * ci + k, args);
                 }
             }
             if (!has_work(k, MAX_FLAT_CLASSES + MAX_SYM_CLASSES)) continue;
-            ka.counter = counters + k;
-            if (k < 8) {
+            ka.counter = pair ? counters + 128 + kp : counters + k;
+            const KernelInfo &kg = dev.info(general_bucket_of(k), c.n_codes);
+            if (k != 8) {
                 ka.snap = (float *)((uint8_t *)dc.snap.p + slab_cursor);
-                slab_cursor += (size_t)persistent_grid(n, dev.n_sms, dev.info(k, c.n_codes).ctas_per_sm) * SLAB_PER_CTA;
+                slab_cursor += (size_t)persistent_grid(n, dev.n_sms, kg.ctas_per_sm) * slab_per_cta(0);
             }
             void *args[] = {&ka};
-            launch_on(dev.info(k, c.n_codes), n, k, args);
+            launch_on(kg, n, k, args);
         }
         }
         CK(cudaEventRecord(dc.ev_f32, st));
@@ -1135,6 +1182,7 @@ void device_loop(gphmm *h, Device &dev, const gphmm_batch *b, const std::vector<
         opt.force_fp64 = h->cfg.force_fp64 != 0;
         opt.tristate_off = h->cfg.tristate_off != 0;
         opt.rs = rs;
+        opt.single_chunk = chunks.size() == 1;
         std::unique_ptr<ChunkPlan> plans[N_SLOTS];
         bool inflight[N_SLOTS] = {false};
         const bool trace = getenv("GPHMM_TRACE") != nullptr;  // per-chunk host timeline on stderr

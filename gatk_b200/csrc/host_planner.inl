@@ -379,6 +379,8 @@ void plan_chunk(const gphmm_batch *b, int64_t u0, int64_t u1, bool force_fp64, b
     }
     SharingScratch scratch;
     std::vector<int> order;
+    std::vector<uint64_t> pair_reads[N_PAIR_BUCKETS];  // per half-warp bucket: (slot of the last row << 32) | unit-local read index
+    static const bool half_warp = getenv("GPHMM_NO_HALFWARP") == nullptr;  // A/B switch: every read on a full warp
     uint32_t bucket_count[N_FP32_BUCKETS] = {0};
     for (int64_t u = u0; u < u1; ++u) {
         const gphmm_unit &un = b->units[u];
@@ -443,17 +445,8 @@ void plan_chunk(const gphmm_batch *b, int64_t u0, int64_t u1, bool force_fp64, b
             }
         }
         if (nh == 0) continue;
-        for (uint32_t r = 0; r < nr; ++r) {
-            const uint32_t rl = d.read_first + r;
-            const uint32_t R = c.read_off[rl + 1] - c.read_off[rl];
-            Task t;
-            t.read = rl; t.stream_off = stream_off; t.stream_len = stream_len;
-            t.out_base = d.out_base + r * nh; t.c0_exp = d.c0_exp; t.n_haps = nh; t.hap_first = d.hap_first; t.unit = sched_first;
-            // fast kernels need two spare rows below the read (accumulator row + row-0 carrier): R + 2 <= 32 K
-            const uint32_t k = (R + 1) / 32 + 1;
-            const uint8_t bucket = force_fp64 ? 0 : (k <= 8 ? (uint8_t)(k - 1) : (uint8_t)8);
-            // one task per haplotype group for the fast kernels; the striped / fp64 kernels sweep the full stream once
-            const int n_t = bucket < 8 && !force_fp64 ? n_groups : 1;
+        for (auto &v : pair_reads) v.clear();
+        auto emit = [&](Task &t, uint8_t bucket, int n_t, uint32_t rl_a, uint32_t rl_b) {
             for (int gi = 0; gi < n_t; ++gi) {
                 t.unit = sched_first + (uint32_t)gi;
                 raw.push_back(t);
@@ -461,10 +454,49 @@ void plan_chunk(const gphmm_batch *b, int64_t u0, int64_t u1, bool force_fp64, b
                 ++bucket_count[bucket];
             }
             if (!c.host_class.empty()) {
-                const uint8_t cls = c.host_class[rl];
-                c.class_count[bucket][cls == CLASS_GENERAL ? MAX_FLAT_CLASSES + MAX_SYM_CLASSES : cls] += (uint32_t)n_t;
+                const uint8_t ca = c.host_class[rl_a];
+                c.class_count[bucket][ca == CLASS_GENERAL ? MAX_FLAT_CLASSES + MAX_SYM_CLASSES : ca] += (uint32_t)n_t;
+                if (rl_b != NO_READ && c.host_class[rl_b] != ca) {
+                    const uint8_t cb = c.host_class[rl_b];
+                    c.class_count[bucket][cb == CLASS_GENERAL ? MAX_FLAT_CLASSES + MAX_SYM_CLASSES : cb] += (uint32_t)n_t;
+                }
             }
+        };
+        for (uint32_t r = 0; r < nr; ++r) {
+            const uint32_t rl = d.read_first + r;
+            const uint32_t R = c.read_off[rl + 1] - c.read_off[rl];
             c.cells += (int64_t)R * sum_h;
+            const int pb = (half_warp && !force_fp64) ? pair_bucket_of_read(R) : -1;
+            if (pb >= 0) {  // paired below, once every read of the unit is known
+                pair_reads[pb - FIRST_PAIR_BUCKET].push_back(((uint64_t)((R - 1) % (uint32_t)pair_bucket_rows(pb)) << 32) | r);
+                continue;
+            }
+            Task t;
+            t.read = rl; t.stream_off = stream_off; t.stream_len = stream_len;
+            t.out_base = d.out_base + r * nh; t.c0_exp = d.c0_exp; t.n_haps = nh; t.hap_first = d.hap_first; t.unit = sched_first;
+            // fast kernels need two spare rows below the read (accumulator row + row-0 carrier): R + 2 <= 32 K
+            const uint32_t k = (R + 1) / 32 + 1;
+            const uint8_t bucket = force_fp64 ? 0 : (k <= 8 ? (uint8_t)(k - 1) : (uint8_t)8);
+            // one task per haplotype group for the fast kernels; the striped / fp64 kernels sweep the full stream once
+            emit(t, bucket, bucket < 8 && !force_fp64 ? n_groups : 1, rl, NO_READ);
+        }
+        // half-warp buckets: two reads per task, both with their last row on the same register slot (R - 1) mod K
+        // (phmm_flat_f32_kernel<K, SYM, 16>); a read that finds no partner travels alone
+        for (int p = 0; p < N_PAIR_BUCKETS; ++p) {
+            std::vector<uint64_t> &v = pair_reads[p];
+            if (v.empty()) continue;
+            std::sort(v.begin(), v.end());
+            for (size_t i = 0; i < v.size();) {
+                const uint32_t ra = (uint32_t)v[i];
+                const bool both = i + 1 < v.size() && (v[i + 1] >> 32) == (v[i] >> 32);
+                const uint32_t rb = both ? (uint32_t)v[i + 1] : NO_READ;
+                Task t;
+                t.read = d.read_first + ra; t.out_base = d.out_base + ra * nh;
+                t.stream_off = both ? d.read_first + rb : NO_READ; t.stream_len = both ? d.out_base + rb * nh : 0;
+                t.c0_exp = d.c0_exp; t.n_haps = nh; t.hap_first = d.hap_first; t.unit = sched_first;
+                emit(t, (uint8_t)(FIRST_PAIR_BUCKET + p), n_groups, d.read_first + ra, both ? d.read_first + rb : NO_READ);
+                i += both ? 2 : 1;
+            }
         }
         c.n_pairs += nr * nh;
     }

@@ -98,6 +98,9 @@ struct UnitSched {
 };
 constexpr int MAX_SNAP_SLOTS = 8;      // + 1 slot per CTA for the pass-start state
 constexpr int SNAP_REGS = 3 * 8 + 4;  // M, I~, D~ of up to 8 rows + hand-off triple + accumulator
+// rows per lane above 8 (half-warp kernels): the record grows with K (multiple of 4 floats: 128-bit accesses)
+__host__ __device__ constexpr int snap_regs(int K) { return K <= 8 ? SNAP_REGS : ((3 * K + 4 + 3) / 4) * 4; }
+__host__ __device__ constexpr size_t snap_slab_bytes(int K) { return (size_t)(MAX_SNAP_SLOTS + 1) * snap_regs(K) * 32 * sizeof(float); }
 
 struct KernelArgs {
     const uint8_t *rd_bases, *rd_q, *rd_i, *rd_d, *rd_c;  // raw per-base read arrays of the chunk
@@ -121,8 +124,10 @@ struct KernelArgs {
     float *snap;                  // snapshot slab: per CTA MAX_SNAP_SLOTS x SNAP_REGS x 32 floats
     int32_t n_codes;
     int32_t tristate_off;
+    int32_t pair_tasks;            // tasks of a half-warp bucket: a second read in stream_off (NO_READ = none), its out_base in stream_len
     uint8_t code_byte[MAX_CODES];  // code -> haplotype byte value
 };
+constexpr uint32_t NO_READ = 0xffffffffu;
 
 __constant__ double c_eps[256];  // QualityUtils.qualToErrorProb cache: 10^(-q/10), q = 0..254
 
@@ -372,11 +377,13 @@ template <int K> struct FastState {
 // lane's record of slot 0; slot MAX_SNAP_SLOTS holds the pass-start state (all zero except the row-0 carrier), so
 // that "start from scratch" and "resume from a snapshot" are the same seven loads.
 constexpr int ZERO_SLOT = MAX_SNAP_SLOTS;
-constexpr int SLOT_STRIDE = 32 * SNAP_REGS;  // floats between two slots of the same lane
+constexpr int SLOT_STRIDE = 32 * SNAP_REGS;  // floats between two slots of the same lane (K <= 8)
 template <int K> __device__ __forceinline__ void snap_save(const FastState<K> &st, float *rec, int slot) {
-    float v[SNAP_REGS];
+    constexpr int REGS = snap_regs(K);
+    constexpr int SLOT_STRIDE = 32 * REGS;
+    float v[REGS];
 #pragma unroll
-    for (int k = 0; k < SNAP_REGS; ++k) v[k] = 0.f;
+    for (int k = 0; k < REGS; ++k) v[k] = 0.f;
 #pragma unroll
     for (int k = 0; k < K; ++k) { v[3 * k + 0] = st.M[k]; v[3 * k + 1] = st.I[k]; v[3 * k + 2] = st.D[k]; }
     v[3 * K + 0] = st.dgm; v[3 * K + 1] = st.dgi; v[3 * K + 2] = st.dgd; v[3 * K + 3] = st.acc;
@@ -385,7 +392,9 @@ template <int K> __device__ __forceinline__ void snap_save(const FastState<K> &s
     for (int k = 0; k < (3 * K + 4 + 3) / 4; ++k) q[k] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
 }
 template <int K> __device__ __forceinline__ void snap_restore(FastState<K> &st, const float *rec, int slot) {
-    float v[SNAP_REGS];
+    constexpr int REGS = snap_regs(K);
+    constexpr int SLOT_STRIDE = 32 * REGS;
+    float v[REGS];
     const float4 *q = reinterpret_cast<const float4 *>(rec + (size_t)slot * SLOT_STRIDE);
 #pragma unroll
     for (int k = 0; k < (3 * K + 4 + 3) / 4; ++k) {
@@ -485,9 +494,14 @@ __global__ void __launch_bounds__(32) phmm_fast_f32_kernel(const KernelArgs g)
         ti = __shfl_sync(FULL, ti, 0);
         if (ti >= n_tasks) break;
         const Task t = g.tasks[ti];
-        if (g.read_class[t.read] != CLASS_GENERAL) continue;  // a flat-quality kernel owns this read
-        const uint32_t ro = g.read_off[t.read];
-        const int R = (int)(g.read_off[t.read + 1] - ro);  // host guarantees R + 2 <= 32 * K
+        // a task of a half-warp bucket carries two reads: this (full-warp) kernel takes them one after the other
+        for (int sub = 0; sub < (g.pair_tasks ? 2 : 1); ++sub) {
+        const uint32_t rd = sub ? t.stream_off : t.read;
+        if (rd == NO_READ) continue;
+        if (g.read_class[rd] != CLASS_GENERAL) continue;  // a flat-quality kernel owns this read
+        const uint32_t out_base = sub ? t.stream_len : t.out_base;
+        const uint32_t ro = g.read_off[rd];
+        const int R = (int)(g.read_off[rd + 1] - ro);  // host guarantees R + 2 <= 32 * K
         const float c0 = (float)scalbn(1.0, t.c0_exp);
         const int acc_lane = R / K, acc_slot = R % K;  // accumulator row = 0-based row R
 
@@ -560,7 +574,7 @@ __global__ void __launch_bounds__(32) phmm_fast_f32_kernel(const KernelArgs g)
         // lane l works on stream position (step - l); positions <= 0 and > P read the NULL padding around the stream
         st.sp = g.sstreams + us.sstream_off - lane;
         st.y = ldg_u8(st.sp);
-        float *const sums_task = sums + t.out_base;
+        float *const sums_task = sums + out_base;
         float *const slab = g.snap + (size_t)blockIdx.x * ((MAX_SNAP_SLOTS + 1) * SLOT_STRIDE) + lane * SNAP_REGS;
         snap_save<K>(st, slab, ZERO_SLOT);  // the pass-start state, restored at every END that begins a fresh pass
 
@@ -578,6 +592,7 @@ __global__ void __launch_bounds__(32) phmm_fast_f32_kernel(const KernelArgs g)
                                    seg.snap_slot, seg.end_restore, seg.end_out);
             step += (int)seg.n_chk;
         }
+        }  // sub
     }
 }
 
@@ -737,17 +752,33 @@ __device__ __forceinline__ void flat_dispatch(int slot, FastState<K> &st, const 
         flat_dispatch<K, SLOT + 1, SYM>(slot, st, f, A, C, B0, G0, E0, tab_lane, src_lane, lane, acc_lane, sums_task, slab, segs, n_segs);
 }
 
-// 28 one-warp CTAs per SM (the shared-memory limit of the K=8 prior table) need <= 73 registers per thread
-template <int K, bool SYM>
-__global__ void __launch_bounds__(32, SYM ? 22 : 28) phmm_flat_f32_kernel(const KernelArgs g, const FlatCoef f)
+// 28 one-warp CTAs per SM (the shared-memory limit of the K=8 prior table) need <= 73 registers per thread.
+// LANES = 16 (half-warp form, reads of 128..254 bases): the warp runs TWO reads of the same unit side by side, one per
+// 16-lane half, K <= 16 rows per lane.  Both halves sweep the same haplotype stream with the same schedule, so every
+// per-step cost that does not depend on the number of rows (hand-off shuffles, column-code load, address arithmetic,
+// loop control) is paid once per 2 x 16 x K cells instead of once per 32 x K' cells with K' = K/2: 150-base reads run 10
+// rows per lane instead of 5, 250-base reads 16 instead of 8.  The planner pairs reads whose last row falls on the same
+// register slot (R - 1) mod K, which keeps the slot of the likelihood sum a template parameter; a read without a partner
+// leaves its half idle (all rows pads).
+__host__ __device__ constexpr int flat_min_ctas(int K, bool SYM, int LANES) { return LANES == 32 ? (SYM ? 22 : 28) : (K > 12 ? 14 : (SYM ? 16 : 18)); }
+
+template <int K, bool SYM, int LANES = 32>
+__global__ void __launch_bounds__(32, flat_min_ctas(K, SYM, LANES)) phmm_flat_f32_kernel(const KernelArgs g, const FlatCoef f)
 {
     constexpr int NV = (K + 3) / 4;
     constexpr unsigned FULL = 0xffffffffu;
+    constexpr int REGS = snap_regs(K);
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float *tab_s = reinterpret_cast<float *>(smem_raw);
-    int lane, src_lane;
+    int lane, pl, src_lane;  // lane id; pipeline lane (this lane works on column step - pl); rotation source
     asm volatile("mov.u32 %0, %%laneid;" : "=r"(lane));
-    asm volatile("{ .reg .u32 t; add.u32 t, %1, 31; and.b32 %0, t, 31; }" : "=r"(src_lane) : "r"(lane));
+    if (LANES == 16) {
+        asm volatile("and.b32 %0, %1, 15;" : "=r"(pl) : "r"(lane));
+        asm volatile("{ .reg .u32 t, u; add.u32 t, %1, 15; and.b32 t, t, 15; and.b32 u, %1, 16; or.b32 %0, t, u; }" : "=r"(src_lane) : "r"(lane));
+    } else {
+        asm volatile("mov.u32 %0, %1;" : "=r"(pl) : "r"(lane));
+        asm volatile("{ .reg .u32 t; add.u32 t, %1, 31; and.b32 %0, t, 31; }" : "=r"(src_lane) : "r"(lane));
+    }
     const uint32_t tab_lane = (uint32_t)__cvta_generic_to_shared(smem_raw) + lane * 16;
     float *const sums = reinterpret_cast<float *>(g.sums);
     const uint32_t n_tasks = g.n_tasks;
@@ -759,16 +790,21 @@ __global__ void __launch_bounds__(32, SYM ? 22 : 28) phmm_flat_f32_kernel(const 
         ti = __shfl_sync(FULL, ti, 0);
         if (ti >= n_tasks) break;
         const Task t = g.tasks[ti];
-        if (g.read_class[t.read] != (uint8_t)f.class_id) continue;
-        const uint32_t ro = g.read_off[t.read];
-        const int R = (int)(g.read_off[t.read + 1] - ro);  // 1 <= R <= 32 * K - 1 (flat reads are never empty)
+        // this lane's read: the task's read, or (upper half of a half-warp task) its partner
+        const bool upper = LANES == 16 && lane >= 16;
+        const uint32_t rd = upper ? t.stream_off : t.read;
+        const bool mine = rd != NO_READ && g.read_class[rd] == (uint8_t)f.class_id;
+        if (!__any_sync(FULL, mine)) continue;
+        const uint32_t ro = mine ? g.read_off[rd] : 0u;
+        const int R = mine ? (int)(g.read_off[rd + 1] - ro) : 0;  // 1 <= R <= LANES * K - 1 (flat reads are never empty); 0 = idle half
+        const uint32_t out_base = upper ? t.stream_len : t.out_base;
         const float c0 = (float)scalbn(1.0, t.c0_exp);
 
         float A[K], C[K];  // SYM only: per-row coefficients of M^ and D^
         __syncwarp();
 #pragma unroll
         for (int k = 0; k < K; ++k) {
-            const int i = lane * K + k + 1;
+            const int i = pl * K + k + 1;
             const bool real = i <= R;
             float pmf = 0.f, pxf = 0.f;
             uint32_t x = 0;
@@ -823,16 +859,22 @@ __global__ void __launch_bounds__(32, SYM ? 22 : 28) phmm_flat_f32_kernel(const 
         st.acc = 0.f;
         st.p = 0;
         const UnitSched us = g.unit_sched[t.unit];
-        st.sp = g.sstreams + us.sstream_off - lane;
+        st.sp = g.sstreams + us.sstream_off - pl;
         st.y = ldg_u8(st.sp);
-        // slot 0: lane 0 holds row 1 (virtual row 0 above it: M = I~ = 0, c*D~ = tIM*c0; SYM: f.tim = 1, the rest is in row 1's table)
-        const float B0 = lane == 0 ? 0.f : (SYM ? A[0] : f.b);
-        const float G0 = lane == 0 ? 0.f : f.g;
-        const float E0 = lane == 0 ? f.tim * c0 : 0.f;
-        const int acc_lane = (R - 1) / K, acc_slot = (R - 1) % K;
-        float *const slab = g.snap + (size_t)blockIdx.x * ((MAX_SNAP_SLOTS + 1) * SLOT_STRIDE) + lane * SNAP_REGS;
+        // slot 0: pipeline lane 0 holds row 1 (virtual row 0 above it: M = I~ = 0, c*D~ = tIM*c0; SYM: f.tim = 1, the rest is in row 1's table)
+        const float B0 = pl == 0 ? 0.f : (SYM ? A[0] : f.b);
+        const float G0 = pl == 0 ? 0.f : f.g;
+        const float E0 = pl == 0 ? f.tim * c0 : 0.f;
+        const int acc_lane = mine ? (R - 1) / K : -1;
+        // the slot of the likelihood sum is warp-uniform: both reads of a pair share it (planner); an idle half defers to the other
+        int acc_slot = mine ? (R - 1) % K : -1;
+        if (LANES == 16) {
+            const int lo = __shfl_sync(FULL, acc_slot, 0), hi = __shfl_sync(FULL, acc_slot, 16);
+            acc_slot = lo >= 0 ? lo : hi;
+        }
+        float *const slab = g.snap + (size_t)blockIdx.x * ((MAX_SNAP_SLOTS + 1) * 32 * REGS) + lane * REGS;
         snap_save<K>(st, slab, ZERO_SLOT);  // the pass-start state (all zero), restored at every END that begins a fresh pass
-        flat_dispatch<K, 0, SYM>(acc_slot, st, f, A, C, B0, G0, E0, tab_lane, src_lane, lane, acc_lane, sums + t.out_base, slab,
+        flat_dispatch<K, 0, SYM>(acc_slot, st, f, A, C, B0, G0, E0, tab_lane, src_lane, pl, acc_lane, sums + out_base, slab,
                             g.segments + us.seg_first, us.n_segs);
     }
 }
