@@ -129,7 +129,15 @@ inline bool is_pair_bucket(int k) { return k >= FIRST_PAIR_BUCKET; }
 inline int pair_bucket_rows(int k) { return 10 + 2 * (k - FIRST_PAIR_BUCKET); }
 // reads of a half-warp bucket that are not flat-quality run the full-warp general kernel with K = 6, 7, 8, 8 rows per lane
 inline int general_bucket_of(int k) { return !is_pair_bucket(k) ? k : std::min(7, 5 + (k - FIRST_PAIR_BUCKET)); }
-inline int pair_bucket_of_read(uint32_t R) { return R < 128 || R > 254 ? -1 : FIRST_PAIR_BUCKET + (R < 160 ? 0 : R < 192 ? 1 : R < 224 ? 2 : 3); }
+// Longest read that takes the half-warp form.  Measured on B200 (profiles/r02_halfwarp_sweep.txt): 150-base reads gain 37 %
+// (10 rows per lane, 96 registers, 18+ warps per SM), 250-base reads lose 9 % (16 rows: 128 registers, 14 warps per SM).
+inline uint32_t half_warp_max_read() {
+    static const uint32_t v = getenv("GPHMM_HALFWARP_MAX_READ") ? (uint32_t)atoi(getenv("GPHMM_HALFWARP_MAX_READ")) : 191u;
+    return v;
+}
+inline int pair_bucket_of_read(uint32_t R) {
+    return R < 128 || R > 254 || R > half_warp_max_read() ? -1 : FIRST_PAIR_BUCKET + (R < 160 ? 0 : R < 192 ? 1 : R < 224 ? 2 : 3);
+}
 constexpr int N_COUNTERS = 256;    // [0..8] general fp32 buckets, [9] fp64 queue, [10] n_rescue, [11] n_deep, [120] deep cursor,
                                    // [128 + p] general kernel on half-warp bucket p, [136 + 4*c + p] half-warp flat kernels: class c
                                    // [16 + 8*c + k] flat-quality kernels: class c, bucket k
@@ -1028,6 +1036,7 @@ struct gphmm {
     std::string last_error = "";
     Stats stats;
     std::mutex run_mu;  // one batch at a time per handle (compute vs. the async worker)
+    std::unique_ptr<ChunkPlan> spare_plan;  // the plan of the last single-chunk call: its buffers serve the next one (under run_mu)
     // async queue.  gphmm_submit appends the caller's arrays to the open *arena* (pinned, reused, SoA like gphmm_batch);
     // the worker takes a whole arena as ONE batch: one host copy per byte, no merge step, DMA straight from the arena.
     struct PinVec {  // growable pinned byte array that keeps its contents
@@ -1153,9 +1162,10 @@ struct PlanPool {
             cv.notify_all();
         }
     }
+    std::unique_ptr<ChunkPlan> recycled;  // a plan of an earlier call whose buffers can be reused (per-region calls)
     std::unique_ptr<ChunkPlan> take(size_t ci) {
         if (threads.empty()) {  // synchronous planning (single-chunk batches: the per-region JNI call)
-            std::unique_ptr<ChunkPlan> p(new ChunkPlan());
+            std::unique_ptr<ChunkPlan> p = recycled ? std::move(recycled) : std::unique_ptr<ChunkPlan>(new ChunkPlan());
             const double t0 = now_ms();
             plan_chunk(b, chunks[ci].first, chunks[ci].second, f64, share, *p, steps_mode);
             std::lock_guard<std::mutex> lk(stats.mu);
@@ -1217,6 +1227,7 @@ void device_loop(gphmm *h, Device &dev, const gphmm_batch *b, const std::vector<
             slot = (slot + 1) % N_SLOTS;
         }
         if (trace) fprintf(stderr, "[gpuphmm] dev %d drained at t=%.2f ms\n", dev.ordinal, now_ms() - t_start);
+        if (chunks.size() == 1 && plans[0]) h->spare_plan = std::move(plans[0]);
         std::lock_guard<std::mutex> lk(h->stats.mu);
         h->stats.s.kernel_launches += launches;
     } catch (const Error &e) {
@@ -1248,6 +1259,7 @@ int run_batch(gphmm *h, const gphmm_batch *b, double *out, const gphmm_region_st
         const int asked = h->cfg.host_threads > 0 ? h->cfg.host_threads : 4;
         const int n_threads = h->devices.size() > 1 ? std::max<int>(asked, 3 * (int)h->devices.size()) : asked;
         PlanPool pool(b, chunks, false, h->cfg.no_prefix_sharing == 0, n_threads, h->stats, rs ? (rs->pcr_rate_factor != 0.0 ? 2 : 1) : 0);
+        if (chunks.size() == 1) pool.recycled = std::move(h->spare_plan);
         if (nd == 1 || chunks.size() == 1) {
             device_loop(h, *h->devices[0], b, chunks, pool, cursor, out, errs[0], rcs[0], rs);
         } else {

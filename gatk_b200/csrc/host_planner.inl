@@ -28,6 +28,24 @@ void validate_batch(const gphmm_batch *b) {
     if (b->n_haps > 0 && !b->hap_bases) throw Error(GPHMM_ERR_INVALID_ARG, "null hap_bases");
 }
 
+// Shape of a read's gap qualities in one pass over the three arrays (8 bytes at a time): bit 0 = insertion quality
+// constant, bit 1 = deletion quality constant, bit 2 = gap-continuation penalty constant, bit 3 = ins == del on every base.
+inline unsigned qual_shape(const uint8_t *qi, const uint8_t *qd, const uint8_t *qc, size_t n) {
+    const uint64_t ones = 0x0101010101010101ULL;
+    const uint64_t bi = ones * qi[0], bd = ones * qd[0], bc = ones * qc[0];
+    uint64_t ai = 0, ad = 0, ac = 0, as = 0;
+    size_t k = 0;
+    for (; k + 8 <= n; k += 8) {
+        uint64_t wi, wd, wc;
+        memcpy(&wi, qi + k, 8); memcpy(&wd, qd + k, 8); memcpy(&wc, qc + k, 8);
+        ai |= wi ^ bi; ad |= wd ^ bd; ac |= wc ^ bc; as |= wi ^ wd;
+    }
+    for (; k < n; ++k) {
+        ai |= (uint64_t)(qi[k] ^ qi[0]); ad |= (uint64_t)(qd[k] ^ qd[0]); ac |= (uint64_t)(qc[k] ^ qc[0]); as |= (uint64_t)(qi[k] ^ qd[k]);
+    }
+    return (ai == 0 ? 1u : 0u) | (ad == 0 ? 2u : 0u) | (ac == 0 ? 4u : 0u) | (as == 0 ? 8u : 0u);
+}
+
 // Greedy split of the unit list into chunks bounded by cells and staged bytes.
 std::vector<std::pair<int64_t, int64_t>> split_units(const gphmm_batch *b, int64_t chunk_cells, int64_t chunk_bytes, bool ramp_up) {
     std::vector<std::pair<int64_t, int64_t>> out;
@@ -279,18 +297,21 @@ void plan_chunk(const gphmm_batch *b, int64_t u0, int64_t u1, bool force_fp64, b
     // (phmm_classify_kernel); a class that is missed here only means those reads take the general kernel.
     c.n_classes = 0;
     c.n_sym = 0;
+    // a per-region call (few reads) looks at EVERY read and keeps what it saw: the reads are then classified here, with
+    // the rules of phmm_classify_kernel, so that no classify launch and no forward launch without work is needed
+    const bool classify_here = !force_fp64 && steps_mode == 0 && n_span > 0 && n_span <= HOST_CLASSIFY_MAX_READS;
+    std::vector<uint8_t> &shape = c.host_class;  // first the shape bits (| 0x10: symmetric and within range), then the class ids
+    shape.clear();
+    if (classify_here) shape.assign((size_t)n_span, 0);
     if (!force_fp64 && n_span > 0) {
-        const int64_t stride = std::max<int64_t>(1, n_span / 256);
+        const int64_t stride = classify_here ? 1 : std::max<int64_t>(1, n_span / 256);
         for (int64_t r = 0; r < n_span; r += stride) {
             const int64_t o = b->read_off[c.r_lo + r], e = b->read_off[c.r_lo + r + 1];
             if (e == o) continue;
             const uint8_t qi = b->ins_q[o], qd = b->del_q[o], qc = b->gcp[o];
-            if (qi > 127 || qd > 127 || qc > 127) continue;
-            // an array is constant iff it equals itself shifted by one (memcmp is vectorised)
-            const size_t n1 = (size_t)(e - o - 1);
-            const bool flat_c = memcmp(b->gcp + o, b->gcp + o + 1, n1) == 0;
-            const bool flat = flat_c && memcmp(b->ins_q + o, b->ins_q + o + 1, n1) == 0 && memcmp(b->del_q + o, b->del_q + o + 1, n1) == 0;
-            bool sym = flat_c && memcmp(b->ins_q + o, b->del_q + o, n1 + 1) == 0;
+            const unsigned sh = qual_shape(b->ins_q + o, b->del_q + o, b->gcp + o, (size_t)(e - o));
+            const bool flat = (sh & 7u) == 7u;
+            bool sym = (sh & 12u) == 12u;
             if (sym && !flat) {
                 uint8_t mx = 0;
                 for (int64_t i = o; i < e; ++i) mx = std::max(mx, b->ins_q[i]);
@@ -298,6 +319,8 @@ void plan_chunk(const gphmm_batch *b, int64_t u0, int64_t u1, bool force_fp64, b
             } else if (sym) {
                 sym = qi <= SYM_MAX_GAP_QUAL;
             }
+            if (classify_here) shape[(size_t)r] = (uint8_t)(sh | (sym ? 0x10u : 0u) | 0x20u);  // 0x20: not empty
+            if (qi > 127 || qd > 127 || qc > 127) continue;
             // (a flat class needs tMM > 0: the kernels factor it out of the match update)
             const bool tmm_positive = tables().m2m[((std::max(qi, qd) * (std::max(qi, qd) + 1)) >> 1) + std::min(qi, qd)] > 0.0;
             if (flat && tmm_positive && !(pcr_hint && qi == qd)) {  // the PCR indel model (region steps) will lower ins and del together
@@ -316,30 +339,21 @@ void plan_chunk(const gphmm_batch *b, int64_t u0, int64_t u1, bool force_fp64, b
             }
         }
     }
-
-    // a per-region call: classify every read here with the rules of phmm_classify_kernel (the sampling above visited every
-    // read of such a chunk), so that no classify launch and no forward launch without work is needed
-    c.host_class.clear();
-    if (!force_fp64 && steps_mode == 0 && n_span > 0 && n_span <= HOST_CLASSIFY_MAX_READS) {
-        c.host_class.assign((size_t)n_span, CLASS_GENERAL);
+    if (classify_here) {
         for (int64_t r = 0; r < n_span; ++r) {
-            const int64_t o = b->read_off[c.r_lo + r], e = b->read_off[c.r_lo + r + 1];
-            if (e == o) continue;
-            const uint8_t qi = b->ins_q[o], qd = b->del_q[o], qc = b->gcp[o];
-            const size_t n1 = (size_t)(e - o - 1);
-            const bool flat_c = memcmp(b->gcp + o, b->gcp + o + 1, n1) == 0;
+            const uint8_t sh = shape[(size_t)r];
             uint8_t cls = CLASS_GENERAL;
-            if (flat_c && memcmp(b->ins_q + o, b->ins_q + o + 1, n1) == 0 && memcmp(b->del_q + o, b->del_q + o + 1, n1) == 0)
-                for (int k = 0; k < c.n_classes; ++k)
-                    if (c.class_qi[k] == qi && c.class_qd[k] == qd && c.class_qc[k] == qc) cls = (uint8_t)k;
-            if (cls == CLASS_GENERAL && flat_c && c.n_sym > 0 && memcmp(b->ins_q + o, b->del_q + o, n1 + 1) == 0) {
-                uint8_t mx = 0;
-                for (int64_t i = o; i < e; ++i) mx = std::max(mx, b->ins_q[i]);
-                if (mx <= SYM_MAX_GAP_QUAL)
+            if (sh & 0x20u) {
+                const int64_t o = b->read_off[c.r_lo + r];
+                const uint8_t qi = b->ins_q[o], qd = b->del_q[o], qc = b->gcp[o];
+                if ((sh & 7u) == 7u)
+                    for (int k = 0; k < c.n_classes; ++k)
+                        if (c.class_qi[k] == qi && c.class_qd[k] == qd && c.class_qc[k] == qc) cls = (uint8_t)k;
+                if (cls == CLASS_GENERAL && (sh & 0x10u))
                     for (int k = 0; k < c.n_sym; ++k)
                         if (c.sym_qc[k] == qc) cls = (uint8_t)(MAX_FLAT_CLASSES + k);
             }
-            c.host_class[(size_t)r] = cls;
+            shape[(size_t)r] = cls;
         }
     }
     memset(c.class_count, 0, sizeof c.class_count);
