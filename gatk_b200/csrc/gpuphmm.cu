@@ -129,10 +129,10 @@ inline bool is_pair_bucket(int k) { return k >= FIRST_PAIR_BUCKET; }
 inline int pair_bucket_rows(int k) { return 10 + 2 * (k - FIRST_PAIR_BUCKET); }
 // reads of a half-warp bucket that are not flat-quality run the full-warp general kernel with K = 6, 7, 8, 8 rows per lane
 inline int general_bucket_of(int k) { return !is_pair_bucket(k) ? k : std::min(7, 5 + (k - FIRST_PAIR_BUCKET)); }
-// Longest read that takes the half-warp form.  Measured on B200 (profiles/r02_halfwarp_sweep.txt): 150-base reads gain 37 %
-// (10 rows per lane, 96 registers, 18+ warps per SM), 250-base reads lose 9 % (16 rows: 128 registers, 14 warps per SM).
+// Longest read that takes the half-warp form (A/B knob).  Measured on B200 (profiles/r02_halfwarp_sweep.txt), batches of
+// equal-length reads: +29 % at 130 bases, +29..38 % at 150..159, +25 % at 175..190, +17 % at 207..222, +14 % at 235..250.
 inline uint32_t half_warp_max_read() {
-    static const uint32_t v = getenv("GPHMM_HALFWARP_MAX_READ") ? (uint32_t)atoi(getenv("GPHMM_HALFWARP_MAX_READ")) : 191u;
+    static const uint32_t v = getenv("GPHMM_HALFWARP_MAX_READ") ? (uint32_t)atoi(getenv("GPHMM_HALFWARP_MAX_READ")) : 254u;
     return v;
 }
 inline int pair_bucket_of_read(uint32_t R) {

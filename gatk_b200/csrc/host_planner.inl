@@ -476,26 +476,31 @@ void plan_chunk(const gphmm_batch *b, int64_t u0, int64_t u1, bool force_fp64, b
                 }
             }
         };
-        for (uint32_t r = 0; r < nr; ++r) {
-            const uint32_t rl = d.read_first + r;
-            const uint32_t R = c.read_off[rl + 1] - c.read_off[rl];
-            c.cells += (int64_t)R * sum_h;
-            const int pb = (half_warp && !force_fp64) ? pair_bucket_of_read(R) : -1;
-            if (pb >= 0) {  // paired below, once every read of the unit is known
-                pair_reads[pb - FIRST_PAIR_BUCKET].push_back(((uint64_t)((R - 1) % (uint32_t)pair_bucket_rows(pb)) << 32) | r);
-                continue;
-            }
+        auto emit_single = [&](uint32_t r, uint32_t R) {  // one read per warp
             Task t;
-            t.read = rl; t.stream_off = stream_off; t.stream_len = stream_len;
+            t.read = d.read_first + r; t.stream_off = stream_off; t.stream_len = stream_len;
             t.out_base = d.out_base + r * nh; t.c0_exp = d.c0_exp; t.n_haps = nh; t.hap_first = d.hap_first; t.unit = sched_first;
             // fast kernels need two spare rows below the read (accumulator row + row-0 carrier): R + 2 <= 32 K
             const uint32_t k = (R + 1) / 32 + 1;
             const uint8_t bucket = force_fp64 ? 0 : (k <= 8 ? (uint8_t)(k - 1) : (uint8_t)8);
             // one task per haplotype group for the fast kernels; the striped / fp64 kernels sweep the full stream once
-            emit(t, bucket, bucket < 8 && !force_fp64 ? n_groups : 1, rl, NO_READ);
+            emit(t, bucket, bucket < 8 && !force_fp64 ? n_groups : 1, d.read_first + r, NO_READ);
+        };
+        for (uint32_t r = 0; r < nr; ++r) {
+            const uint32_t rl = d.read_first + r;
+            const uint32_t R = c.read_off[rl + 1] - c.read_off[rl];
+            c.cells += (int64_t)R * sum_h;
+            // (a chunk too small to fill the GPU keeps one read per warp: twice as many independent wavefronts hide latency
+            // better than fewer instructions per cell do)
+            const int pb = (half_warp && !force_fp64 && want_groups <= 1) ? pair_bucket_of_read(R) : -1;
+            if (pb >= 0) {  // paired below, once every read of the unit is known
+                pair_reads[pb - FIRST_PAIR_BUCKET].push_back(((uint64_t)((R - 1) % (uint32_t)pair_bucket_rows(pb)) << 32) | r);
+                continue;
+            }
+            emit_single(r, R);
         }
         // half-warp buckets: two reads per task, both with their last row on the same register slot (R - 1) mod K
-        // (phmm_flat_f32_kernel<K, SYM, 16>); a read that finds no partner travels alone
+        // (phmm_flat_f32_kernel<K, SYM, 16>); a read that finds no partner takes a full warp like the shorter ones
         for (int p = 0; p < N_PAIR_BUCKETS; ++p) {
             std::vector<uint64_t> &v = pair_reads[p];
             if (v.empty()) continue;
@@ -503,13 +508,18 @@ void plan_chunk(const gphmm_batch *b, int64_t u0, int64_t u1, bool force_fp64, b
             for (size_t i = 0; i < v.size();) {
                 const uint32_t ra = (uint32_t)v[i];
                 const bool both = i + 1 < v.size() && (v[i + 1] >> 32) == (v[i] >> 32);
-                const uint32_t rb = both ? (uint32_t)v[i + 1] : NO_READ;
+                if (!both) {
+                    emit_single(ra, c.read_off[d.read_first + ra + 1] - c.read_off[d.read_first + ra]);
+                    ++i;
+                    continue;
+                }
+                const uint32_t rb = (uint32_t)v[i + 1];
                 Task t;
                 t.read = d.read_first + ra; t.out_base = d.out_base + ra * nh;
-                t.stream_off = both ? d.read_first + rb : NO_READ; t.stream_len = both ? d.out_base + rb * nh : 0;
+                t.stream_off = d.read_first + rb; t.stream_len = d.out_base + rb * nh;
                 t.c0_exp = d.c0_exp; t.n_haps = nh; t.hap_first = d.hap_first; t.unit = sched_first;
-                emit(t, (uint8_t)(FIRST_PAIR_BUCKET + p), n_groups, d.read_first + ra, both ? d.read_first + rb : NO_READ);
-                i += both ? 2 : 1;
+                emit(t, (uint8_t)(FIRST_PAIR_BUCKET + p), n_groups, d.read_first + ra, d.read_first + rb);
+                i += 2;
             }
         }
         c.n_pairs += nr * nh;
