@@ -685,9 +685,10 @@ __device__ __forceinline__ void flat_step(FastState<K> &st, const FlatCoef &f, c
     // update is 2 FFMA + 1 FMUL.  SYM: the coefficients of I^ and D^ are per-row registers (A, C), the rest constant operands.
     float Mn[K];
     {
-        float u = __fmaf_rn(SYM ? C[0] : f.c, st.dgd, E0);
+        // same operation order as the rows below (E0 is 0 except on the lane that holds row 1, where dgm is 0): a row's
+        // arithmetic does not depend on the slot it lands on, so every lane layout gives bit-identical results
+        float u = __fmaf_rn(SYM ? C[0] : f.c, st.dgd, st.dgm + E0);
         u = __fmaf_rn(B0, st.dgi, u);
-        u += st.dgm;
         Mn[0] = pr[0] * u;
     }
 #pragma unroll

@@ -149,7 +149,9 @@ def test_planner_host_only():
     assert plain["passes"] == nh
     big = synth.config2(400)
     sp, ss = native.plan_stats(big, False), native.plan_stats(big, True)
-    assert sp["tasks"] == big.n_reads and ss["tasks"] == big.n_reads       # enough reads: one task per read
+    # enough reads: one task per read, or per PAIR of reads where two reads of a unit share a warp (half-warp kernels:
+    # reads of 128-254 bases whose last rows fall on the same register slot); 90 % of these reads are 250 bases long
+    assert sp["tasks"] == ss["tasks"] and big.n_reads // 2 <= ss["tasks"] <= int(0.62 * big.n_reads)
     steps = lambda st: st["free_steps"] + st["checked_steps"]
     # every computed column is one step of lane 0; each unit's sweep drains 31 more steps
     assert steps(sp) == sp["total_columns"] + sp["passes"] + 31 * sp["units"]
