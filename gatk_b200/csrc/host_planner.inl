@@ -358,13 +358,15 @@ void plan_chunk(const gphmm_batch *b, int64_t u0, int64_t u1, bool force_fp64, b
     }
     memset(c.class_count, 0, sizeof c.class_count);
 
-    // haplotype alphabet of the chunk: A C G T N are fixed codes, any other byte value gets the next free code
+    // haplotype alphabet of the chunk: A C G T are fixed codes, any other byte value (N included) gets the next free code
     uint8_t lut8[256];
     memset(lut8, 0xff, sizeof lut8);
     memset(c.code_byte, 0, sizeof c.code_byte);
-    const char fixed[5] = {'A', 'C', 'G', 'T', 'N'};
-    for (int i = 0; i < 5; ++i) { lut8[(uint8_t)fixed[i]] = (uint8_t)(CODE_FIRST_BASE + i); c.code_byte[CODE_FIRST_BASE + i] = (uint8_t)fixed[i]; }
-    c.n_codes = CODE_FIRST_BASE + 5;
+    // (N is not a fixed code: assembled haplotypes rarely contain it, and every code costs a row of each warp's prior table,
+    // i.e. shared memory and therefore resident warps)
+    const char fixed[4] = {'A', 'C', 'G', 'T'};
+    for (int i = 0; i < 4; ++i) { lut8[(uint8_t)fixed[i]] = (uint8_t)(CODE_FIRST_BASE + i); c.code_byte[CODE_FIRST_BASE + i] = (uint8_t)fixed[i]; }
+    c.n_codes = CODE_FIRST_BASE + 4;
 
     c.streams.clear(); c.hap_len.clear(); c.hap_stream_off.clear(); c.units.clear(); c.tasks.clear();
     c.sstreams.clear(); c.pass_info.clear(); c.segments.clear(); c.unit_sched.clear(); c.skipped_cells = 0; c.computed_columns = 0; c.n_keep = 0;

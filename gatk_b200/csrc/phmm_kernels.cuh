@@ -44,7 +44,7 @@ namespace phmm_dev {
 
 constexpr uint32_t CODE_END = 0;   // column after the last base of a haplotype
 constexpr uint32_t CODE_NULL = 1;  // outside the stream (pipeline fill / drain)
-constexpr uint32_t CODE_FIRST_BASE = 2;  // A C G T N = 2..6, further byte values 7..
+constexpr uint32_t CODE_FIRST_BASE = 2;  // A C G T = 2..5, further byte values (N included) 6..
 constexpr int MAX_CODES = 64;
 constexpr int MAX_QUAL = 254;      // QualityUtils.java:43
 constexpr float RESCUE_THRESHOLD_F32 = 1e-28f;
