@@ -1248,6 +1248,7 @@ int run_batch(gphmm *h, const gphmm_batch *b, double *out, const gphmm_region_st
     // several devices drain one list of chunks: smaller chunks balance the end of the batch (unless the caller fixed the size)
     const int64_t cells_per_chunk = h->cfg.chunk_cells > 0 ? h->chunk_cells() : h->chunk_cells() / (int64_t)std::min<size_t>(std::max<size_t>(h->devices.size(), 1), 4);
     auto chunks = split_units(b, cells_per_chunk, h->chunk_bytes(), true);
+    if (getenv("GPHMM_TRACE")) fprintf(stderr, "[gpuphmm] batch of %lld units: validated and split into %zu chunks in %.2f ms\n", (long long)b->n_units, chunks.size(), now_ms() - t0);
     std::atomic<size_t> cursor{0};
     const size_t nd = h->devices.size();
     std::vector<std::string> errs(nd);
@@ -1274,6 +1275,7 @@ int run_batch(gphmm *h, const gphmm_batch *b, double *out, const gphmm_region_st
         std::lock_guard<std::mutex> lk(h->stats.mu);
         h->stats.s.wall_ms += now_ms() - t0;
     }
+    if (getenv("GPHMM_TRACE")) fprintf(stderr, "[gpuphmm] batch done after %.2f ms\n", now_ms() - t0);
     for (size_t d = 0; d < nd; ++d)
         if (rcs[d] != GPHMM_OK) throw Error(rcs[d], errs[d]);
     return GPHMM_OK;

@@ -31,6 +31,38 @@ template <typename T, int K> KernelInfo pd_kernel_info() {
     return ki;
 }
 
+template <int K> KernelInfo pd_fast_kernel_info() {
+    KernelInfo ki;
+    auto fn = phmm_pd_fast_kernel<K>;
+    ki.fn = (const void *)fn;
+    ki.smem = (size_t)PD_MAX_CODES * ((K + 3) / 4) * 512;  // sized per launch from the chunk's alphabet; this is the ceiling
+    raise_dyn_smem((const void *)fn, ki.smem);
+    return ki;
+}
+
+// The steps of a haplotype's sweep (H + 33 of them: every lane gets past column H + 1) in which some lane of the warp is
+// on, or one column before, a column of the deletion state machine run the slow step; all others the fast one.
+// Appends (fast, slow) pairs to `segs`.
+void plan_pd_steps(const uint8_t *flags, uint32_t H, uint32_t first_event, uint32_t carry, std::vector<uint2> &segs,
+                   std::vector<uint8_t> &slow) {
+    const uint32_t T = H + 33;
+    slow.assign(T + 2, 0);
+    for (uint32_t j = 1; j <= H; ++j) {  // 1-based column
+        const uint8_t f = flags[j - 1];
+        const bool special = (f & PD_DEL_END_BIT) || ((f >> PD_TYPE_SHIFT) & PD_TYPE_BITS) || (carry == PD_INSIDE_DEL && j <= first_event) ||
+                             (carry == PD_AFTER_DEL && j == 1);
+        if (!special) continue;
+        // lane l meets column j at step j + l and needs its branch values refreshed one step earlier
+        for (uint32_t st = j > 1 ? j - 1 : 1; st <= std::min(T, j + 31); ++st) slow[st] = 1;
+    }
+    for (uint32_t st = 1; st <= T;) {
+        uint2 seg = make_uint2(0, 0);
+        while (st <= T && !slow[st]) { ++seg.x; ++st; }
+        while (st <= T && slow[st]) { ++seg.y; ++st; }
+        segs.push_back(seg);
+    }
+}
+
 int run_pd_batch(gphmm *h, const gphmm_batch *b, const uint8_t *hap_pd, double *out) {
     std::lock_guard<std::mutex> run_lk(h->run_mu);
     const double t0 = now_ms();
@@ -46,13 +78,20 @@ int run_pd_batch(gphmm *h, const gphmm_batch *b, const uint8_t *hap_pd, double *
     static const bool k8 = getenv("GPHMM_PD_K8") != nullptr;
     static const KernelInfo kf[3] = {pd_kernel_info<float, 2>(), pd_kernel_info<float, 4>(), k8 ? pd_kernel_info<float, 8>() : pd_kernel_info<float, 4>()};
     static const KernelInfo kd = pd_kernel_info<double, 4>();
+    // fast fp32 kernels for reads of up to 94 / 158 / 254 bases (3 / 5 / 8 rows per lane); GPHMM_PD_SLOW=1 keeps every read on
+    // the first-version kernels (A/B switch)
+    static const KernelInfo kfast[3] = {pd_fast_kernel_info<3>(), pd_fast_kernel_info<5>(), pd_fast_kernel_info<8>()};
+    static const bool no_fast = getenv("GPHMM_PD_SLOW") != nullptr;
     const auto chunks = split_units(b, h->chunk_cells() / 4, h->chunk_bytes(), false);
     int64_t launches = 0, total_pairs = 0, total_cells = 0, total_redo = 0, h2d = 0, d2h = 0;
     double device_ms = 0;
     std::vector<uint32_t> read_off;
     std::vector<uint8_t> hap_bytes, hap_flags;
-    std::vector<PdTask> tasks[3], all;
+    std::vector<PdTask> tasks[6], all;   // 0..2: first-version kernels by read length, 3..5: fast kernels
     std::vector<uint32_t> unit_out_base;
+    std::vector<uint8_t> code_stream, flag_stream, slow_scratch;
+    std::vector<PdHap> haps;
+    std::vector<uint2> segs;
     for (const auto &ch : chunks) {
         int64_t r_lo = INT64_MAX, r_hi = 0;
         for (int64_t u = ch.first; u < ch.second; ++u) {
@@ -66,13 +105,19 @@ int run_pd_batch(gphmm *h, const gphmm_batch *b, const uint8_t *hap_pd, double *
         for (int64_t r = 0; r <= r_hi - r_lo; ++r) read_off[r] = (uint32_t)(b->read_off[r_lo + r] - base_lo);
         hap_bytes.clear(); hap_flags.clear(); unit_out_base.clear();
         for (auto &v : tasks) v.clear();
+        code_stream.clear(); flag_stream.clear(); haps.clear(); segs.clear();
+        // column codes of the chunk: 0 = outside a haplotype, then one code per (haplotype byte, SNP mask) that occurs
+        uint8_t code_byte[PD_MAX_CODES] = {0}, code_mask[PD_MAX_CODES] = {0};
+        int n_codes = 1;
+        bool fast_ok = !no_fast && !h->cfg.force_fp64;
+        std::map<uint32_t, uint8_t> code_of;
         uint32_t n_pairs = 0, max_h = 1;
         int64_t cells = 0;
         for (int64_t u = ch.first; u < ch.second; ++u) {
             const gphmm_unit &un = b->units[u];
             const uint32_t nr = (uint32_t)(un.read_end - un.read_begin), nh = (uint32_t)(un.hap_end - un.hap_begin);
             unit_out_base.push_back(n_pairs);
-            struct HapInfo { uint32_t off, H, first_event, carry; };
+            struct HapInfo { uint32_t off, H, first_event, carry, index; };
             std::vector<HapInfo> hi(nh);
             for (uint32_t k = 0; k < nh; ++k) {
                 const int64_t ho = b->hap_off[un.hap_begin + k];
@@ -82,15 +127,53 @@ int run_pd_batch(gphmm *h, const gphmm_batch *b, const uint8_t *hap_pd, double *
                 hap_flags.resize(hap_bytes.size());
                 encode_pd_columns(hap_pd + ho, H, hap_flags.data() + hi[k].off, hi[k].first_event, hi[k].carry);
                 max_h = std::max(max_h, H);
+                // fast kernels: padded code and flag streams, the step schedule, the codes that occur
+                hi[k].index = (uint32_t)haps.size();
+                PdHap ph;
+                memset(&ph, 0, sizeof ph);
+                code_stream.insert(code_stream.end(), STREAM_PAD, 0);
+                flag_stream.insert(flag_stream.end(), STREAM_PAD, 0);
+                ph.code_off = (uint32_t)code_stream.size();
+                for (uint32_t j = 0; j < H && fast_ok; ++j) {
+                    const uint8_t f = hap_flags[hi[k].off + j];
+                    const uint32_t key = (uint32_t)b->hap_bases[ho + j] | ((f & PD_SNP_BIT) ? (uint32_t)(0x80u | (f & PD_MASK_BITS)) << 8 : 0u);
+                    auto it = code_of.find(key);
+                    if (it == code_of.end()) {
+                        if (n_codes >= PD_MAX_CODES) { fast_ok = false; break; }  // exotic alphabet: the first-version kernels take the chunk
+                        code_byte[n_codes] = (uint8_t)key; code_mask[n_codes] = (uint8_t)(key >> 8);
+                        it = code_of.emplace(key, (uint8_t)n_codes++).first;
+                    }
+                    const uint8_t code = it->second;
+                    code_stream.push_back(code);
+                    if (code < 32) ph.codes_lo |= 1u << code; else ph.codes_hi |= 1u << (code - 32);
+                }
+                code_stream.resize(ph.code_off + H, 0);
+                flag_stream.insert(flag_stream.end(), hap_flags.begin() + hi[k].off, hap_flags.begin() + hi[k].off + H);
+                code_stream.insert(code_stream.end(), 2 * STREAM_PAD, 0);
+                flag_stream.insert(flag_stream.end(), 2 * STREAM_PAD, 0);
+                ph.seg_first = (uint32_t)segs.size();
+                plan_pd_steps(hap_flags.data() + hi[k].off, H, hi[k].first_event, hi[k].carry, segs, slow_scratch);
+                ph.n_segs = (uint32_t)segs.size() - ph.seg_first;
+                haps.push_back(ph);
             }
             for (uint32_t r = 0; r < nr; ++r) {
                 const uint32_t rl = (uint32_t)(un.read_begin - r_lo) + r, R = read_off[rl + 1] - read_off[rl];
+                // (the choice between the kernel families is made once the whole chunk is known: see fast_ok below)
                 const int bucket = R <= 63 ? 0 : (R <= 127 ? 1 : 2);
+                const int fbucket = R <= 94 ? 3 : (R <= 158 ? 4 : (R <= 254 ? 5 : -1));
                 for (uint32_t k = 0; k < nh; ++k) {
                     PdTask t;
                     t.read = rl; t.hap_off = hi[k].off; t.H = hi[k].H; t.out_slot = n_pairs + r * nh + k;
                     t.first_event = hi[k].first_event; t.carry = hi[k].carry;
-                    t.c0_exp = 125 - ceil_log2(hi[k].H); t.pad = 0;
+                    t.c0_exp = 125 - ceil_log2(hi[k].H); t.pad = hi[k].index;
+                    if (fbucket >= 0) {
+                        // scaled states (I / tMI, D / tMD) need the head-room of the plain fp32 kernels
+                        PdTask tf = t;
+                        tf.c0_exp = C0_BASE_EXP_F32 - ceil_log2(hi[k].H);
+                        tasks[fbucket].push_back(tf);
+                        cells += (int64_t)R * hi[k].H;
+                        continue;
+                    }
                     tasks[bucket].push_back(t);
                     cells += (int64_t)R * hi[k].H;
                 }
@@ -98,15 +181,28 @@ int run_pd_batch(gphmm *h, const gphmm_batch *b, const uint8_t *hap_pd, double *
             n_pairs += nr * nh;
         }
         if (n_pairs == 0) continue;
+        if (!fast_ok)  // every read on the first-version kernels (initial value 2^(125 - ceil log2 H) again)
+            for (int k = 3; k < 6; ++k) {
+                for (PdTask t : tasks[k]) {
+                    const uint32_t R = read_off[t.read + 1] - read_off[t.read];
+                    t.c0_exp = 125 - ceil_log2(t.H);
+                    tasks[R <= 63 ? 0 : (R <= 127 ? 1 : 2)].push_back(t);
+                }
+                tasks[k].clear();
+            }
         all.clear();
-        uint32_t first[4] = {0, 0, 0, 0};
-        for (int k = 0; k < 3; ++k) { first[k + 1] = first[k] + (uint32_t)tasks[k].size(); all.insert(all.end(), tasks[k].begin(), tasks[k].end()); }
+        uint32_t first[7] = {0, 0, 0, 0, 0, 0, 0};
+        for (int k = 0; k < 6; ++k) { first[k + 1] = first[k] + (uint32_t)tasks[k].size(); all.insert(all.end(), tasks[k].begin(), tasks[k].end()); }
         // device image
         size_t o = 0;
         const size_t off_ro = o; o = align_up(o + read_off.size() * 4, 16);
         const size_t off_hb = o; o = align_up(o + hap_bytes.size(), 16);
         const size_t off_hf = o; o = align_up(o + hap_flags.size(), 16);
         const size_t off_tk = o; o = align_up(o + all.size() * sizeof(PdTask), 16);
+        const size_t off_cs = o; o = align_up(o + code_stream.size(), 16);
+        const size_t off_fs = o; o = align_up(o + flag_stream.size(), 16);
+        const size_t off_hp = o; o = align_up(o + haps.size() * sizeof(PdHap), 16);
+        const size_t off_sg = o; o = align_up(o + segs.size() * sizeof(uint2), 16);
         const size_t meta_bytes = o;
         dev.pd_meta.reserve(meta_bytes); dev.pd_h_meta.reserve(meta_bytes);
         uint8_t *hm = (uint8_t *)dev.pd_h_meta.p;
@@ -114,6 +210,10 @@ int run_pd_batch(gphmm *h, const gphmm_batch *b, const uint8_t *hap_pd, double *
         memcpy(hm + off_hb, hap_bytes.data(), hap_bytes.size());
         memcpy(hm + off_hf, hap_flags.data(), hap_flags.size());
         memcpy(hm + off_tk, all.data(), all.size() * sizeof(PdTask));
+        memcpy(hm + off_cs, code_stream.data(), code_stream.size());
+        memcpy(hm + off_fs, flag_stream.data(), flag_stream.size());
+        memcpy(hm + off_hp, haps.data(), haps.size() * sizeof(PdHap));
+        memcpy(hm + off_sg, segs.data(), segs.size() * sizeof(uint2));
         o = 0;
         const size_t off_out = o; o = align_up(o + (size_t)n_pairs * 8, 16);
         const size_t off_cnt = o; o = align_up(o + 16 * 4, 16);
@@ -147,6 +247,29 @@ int run_pd_batch(gphmm *h, const gphmm_batch *b, const uint8_t *hap_pd, double *
         pa.err = (int *)(work + off_err);
         pa.tristate_off = h->cfg.tristate_off != 0;
         if (!h->cfg.force_fp64) {
+            for (int k = 3; k < 6; ++k) {
+                const uint32_t n = first[k + 1] - first[k];
+                if (!n) continue;
+                PdFastArgs fa;
+                memset(&fa, 0, sizeof fa);
+                fa.rd_bases = pa.rd_bases; fa.rd_q = pa.rd_q; fa.rd_i = pa.rd_i; fa.rd_d = pa.rd_d; fa.rd_c = pa.rd_c;
+                fa.read_off = pa.read_off;
+                fa.codes = meta + off_cs; fa.flags = meta + off_fs;
+                fa.tasks = pa.tasks; fa.haps = (const PdHap *)(meta + off_hp); fa.segs = (const uint2 *)(meta + off_sg);
+                fa.first = first[k]; fa.n_tasks = n; fa.counter = counters + 10 + (k - 3);
+                fa.sums = (float *)(work + off_s32);
+                fa.m2m = pa.m2m; fa.err = pa.err; fa.tristate_off = pa.tristate_off; fa.n_codes = n_codes;
+                memcpy(fa.code_byte, code_byte, sizeof code_byte);
+                memcpy(fa.code_mask, code_mask, sizeof code_mask);
+                const int rows = k == 3 ? 3 : (k == 4 ? 5 : 8);
+                const size_t smem = (size_t)n_codes * ((rows + 3) / 4) * 512;
+                int occ = 0;
+                CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kfast[k - 3].fn, 32, smem));
+                const uint32_t grid = std::min<uint32_t>(n, (uint32_t)(dev.n_sms * std::max(1, occ)));
+                void *args[] = {&fa};
+                CK(cudaLaunchKernel(kfast[k - 3].fn, dim3(grid), dim3(32), args, smem, st));
+                ++launches;
+            }
             for (int k = 0; k < 3; ++k) {
                 const uint32_t n = first[k + 1] - first[k];
                 if (!n) continue;

@@ -10,17 +10,43 @@ void validate_batch(const gphmm_batch *b) {
     if (b->n_units < 0 || b->n_reads < 0 || b->n_haps < 0) throw Error(GPHMM_ERR_INVALID_ARG, "negative count");
     if (b->n_units == 0) return;
     if (!b->units || !b->read_off || !b->hap_off) throw Error(GPHMM_ERR_INVALID_ARG, "null offsets/units");
-    for (int64_t r = 0; r < b->n_reads; ++r)
-        if (b->read_off[r + 1] < b->read_off[r]) throw Error(GPHMM_ERR_INVALID_ARG, "read_off not monotone");
-    for (int64_t h = 0; h < b->n_haps; ++h)
-        if (b->hap_off[h + 1] <= b->hap_off[h])
-            throw Error(GPHMM_ERR_INVALID_ARG, "zero-length haplotype (PairHMM.initialize requires haplotypeMaxLength > 0)");
-    for (int64_t u = 0; u < b->n_units; ++u) {
-        const gphmm_unit &un = b->units[u];
-        if (un.read_begin < 0 || un.read_end < un.read_begin || un.read_end > b->n_reads || un.hap_begin < 0 ||
-            un.hap_end < un.hap_begin || un.hap_end > b->n_haps || un.out_off < 0)
-            throw Error(GPHMM_ERR_INVALID_ARG, "unit range out of bounds");
-        if (un.hap_end - un.hap_begin > 65535) throw Error(GPHMM_ERR_TOO_LARGE, "more than 65535 haplotypes in one unit");
+    // 0 = fine; the scans are linear in reads + haplotypes + units, which is milliseconds of serial time in front of a
+    // multi-GPU batch (millions of reads): large batches are checked by a few threads
+    auto scan = [b](int64_t r0, int64_t r1, int64_t h0, int64_t h1, int64_t u0, int64_t u1) -> int {
+        for (int64_t r = r0; r < r1; ++r)
+            if (b->read_off[r + 1] < b->read_off[r]) return 1;
+        for (int64_t h = h0; h < h1; ++h)
+            if (b->hap_off[h + 1] <= b->hap_off[h]) return 2;
+        for (int64_t u = u0; u < u1; ++u) {
+            const gphmm_unit &un = b->units[u];
+            if (un.read_begin < 0 || un.read_end < un.read_begin || un.read_end > b->n_reads || un.hap_begin < 0 ||
+                un.hap_end < un.hap_begin || un.hap_end > b->n_haps || un.out_off < 0)
+                return 3;
+            if (un.hap_end - un.hap_begin > 65535) return 4;
+        }
+        return 0;
+    };
+    int worst = 0;
+    const int n_threads = b->n_reads + b->n_haps + b->n_units < 400000 ? 1 : (int)std::min<int64_t>(8, std::max(1u, std::thread::hardware_concurrency()));
+    if (n_threads == 1) {
+        worst = scan(0, b->n_reads, 0, b->n_haps, 0, b->n_units);
+    } else {
+        std::vector<int> rc((size_t)n_threads, 0);
+        std::vector<std::thread> th;
+        for (int t = 0; t < n_threads; ++t)
+            th.emplace_back([&, t] {
+                rc[(size_t)t] = scan(b->n_reads * t / n_threads, b->n_reads * (t + 1) / n_threads, b->n_haps * t / n_threads,
+                                     b->n_haps * (t + 1) / n_threads, b->n_units * t / n_threads, b->n_units * (t + 1) / n_threads);
+            });
+        for (auto &t : th) t.join();
+        for (int v : rc) worst = worst ? worst : v;
+    }
+    switch (worst) {
+        case 1: throw Error(GPHMM_ERR_INVALID_ARG, "read_off not monotone");
+        case 2: throw Error(GPHMM_ERR_INVALID_ARG, "zero-length haplotype (PairHMM.initialize requires haplotypeMaxLength > 0)");
+        case 3: throw Error(GPHMM_ERR_INVALID_ARG, "unit range out of bounds");
+        case 4: throw Error(GPHMM_ERR_TOO_LARGE, "more than 65535 haplotypes in one unit");
+        default: break;
     }
     if (b->n_reads > 0 && b->read_off[b->n_reads] > 0 &&
         (!b->read_bases || !b->base_q || !b->ins_q || !b->del_q || !b->gcp))

@@ -219,6 +219,236 @@ __global__ void __launch_bounds__(32) phmm_pd_kernel(const PdArgs g)
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Fast fp32 PD-HMM kernel for reads of up to 254 bases (one strip).  Flags are sparse: a partially determined
+// haplotype carries a handful of SNP / deletion events, so for most steps every lane of the warp sits on a column
+// whose update is the plain LoglessPairHMM recurrence.  Those steps run fast_step<K, false> of phmm_kernels.cuh --
+// the scaled 5-instruction recurrence with rotation hand-off, accumulator row and shared-memory prior table -- and
+// do not touch the branch values at all.  The host marks, per haplotype, the steps in which some lane is on (or one
+// column before) a column that takes part in the NORMAL / INSIDE_DEL / AFTER_DEL state machine; only those run the
+// slow step below, which keeps the branch values and merges them with max() exactly where the reference does
+// (LoglessPDPairHMM.java:62-141).  The states are scaled per row by positive constants (I~ = I / tMI_i,
+// D~ = D / tMD_i), which commutes with max(): every comparison has the outcome it has in the reference.
+//   * SNP columns are plain columns with a wider match test: the column CODE (haplotype byte + alternative-base
+//     mask) indexes the prior table, so isBasePDMatching (:184-204) costs nothing per cell.
+//   * the row below the read accumulates sum_j (M + I)[R][j] (:149-152): no per-step work for the result.
+// ---------------------------------------------------------------------------------------------
+constexpr int PD_MAX_CODES = 64;   // column codes per chunk: 0 = outside the haplotype, then one per (byte, SNP mask)
+
+struct PdHap {
+    uint32_t code_off;             // first column of the haplotype in the padded code / flag streams
+    uint32_t seg_first, n_segs;    // schedule: into PdFastArgs::segs, (fast steps, slow steps) pairs covering H + 33 steps
+    uint32_t codes_lo, codes_hi;   // column codes that occur in this haplotype
+    uint32_t pad0, pad1, pad2;
+};
+
+struct PdFastArgs {
+    const uint8_t *rd_bases, *rd_q, *rd_i, *rd_d, *rd_c;
+    const uint32_t *read_off;
+    const uint8_t *codes, *flags;  // per column, STREAM_PAD zero columns in front of every haplotype and 2 * STREAM_PAD behind
+    const PdTask *tasks;           // PdTask::pad = index into haps
+    const PdHap *haps;
+    const uint2 *segs;
+    uint32_t first, n_tasks;
+    uint32_t *counter;
+    float *sums;                   // per task (same index as tasks)
+    const double *m2m;
+    int *err;
+    int32_t tristate_off, n_codes;
+    uint8_t code_byte[PD_MAX_CODES];   // code -> haplotype byte
+    uint8_t code_mask[PD_MAX_CODES];   // code -> 0x80 | alternative-base bits when the column carries a SNP flag, else 0
+};
+
+template <int K>
+__global__ void __launch_bounds__(32, K > 5 ? 12 : 16) phmm_pd_fast_kernel(const PdFastArgs g)
+{
+    constexpr int NV = (K + 3) / 4;
+    constexpr unsigned FULL = 0xffffffffu;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float *tab_s = reinterpret_cast<float *>(smem_raw);
+    int lane, src_lane;
+    asm volatile("mov.u32 %0, %%laneid;" : "=r"(lane));
+    asm volatile("{ .reg .u32 t; add.u32 t, %1, 31; and.b32 %0, t, 31; }" : "=r"(src_lane) : "r"(lane));
+    const uint32_t tab_lane = (uint32_t)__cvta_generic_to_shared(smem_raw) + lane * 16;
+    const ptrdiff_t flag_delta = g.flags - g.codes;
+
+    for (;;) {
+        uint32_t ti = 0;
+        if (lane == 0) ti = atomicAdd(g.counter, 1u);
+        ti = __shfl_sync(FULL, ti, 0);
+        if (ti >= g.n_tasks) break;
+        const PdTask t = g.tasks[g.first + ti];
+        const PdHap hp = g.haps[t.pad];
+        const uint32_t ro = g.read_off[t.read];
+        const int R = (int)(g.read_off[t.read + 1] - ro), H = (int)t.H;  // host guarantees R + 2 <= 32 * K
+        const float c0 = (float)scalbn(1.0, t.c0_exp);
+        const int acc_lane = R / K, acc_slot = R % K;  // accumulator row = 0-based row R
+
+        float cb[K], cc[K], cg[K], cd[K];
+        uint32_t real_mask = 0;  // bit k: slot k holds a read row (only those take part in the state machine)
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const int i = lane * K + k + 1;  // 1-based read row
+            double A = 0.0, B = 0.0, C = 0.0, G = 0.0, DD = 0.0, pm = 0.0, px = 0.0;
+            uint32_t x = 0, abit = 0;
+            const bool real = i <= R;
+            if (real) {
+                real_mask |= 1u << k;
+                uint32_t q = g.rd_q[ro + i - 1], qi = g.rd_i[ro + i - 1], qd = g.rd_d[ro + i - 1], qc = g.rd_c[ro + i - 1];
+                x = g.rd_bases[ro + i - 1];
+                if (q > (uint32_t)MAX_QUAL || qi > 127u || qd > 127u || qc > 127u) {
+                    atomicExch(g.err, 1);
+                    q = min(q, (uint32_t)MAX_QUAL); qi = min(qi, 127u); qd = min(qd, 127u); qc = min(qc, 127u);
+                }
+                const double ei = c_eps[qi], ec = c_eps[qc];
+                const uint32_t mn = min(qi, qd), mx = max(qi, qd);
+                const double tIM = 1.0 - ec;
+                A = __ldg(g.m2m + ((mx * (mx + 1)) >> 1) + mn);
+                if (i > 1) {
+                    const double tmi_prev = c_eps[min((uint32_t)g.rd_i[ro + i - 2], 127u)];
+                    const double tmd_prev = c_eps[min((uint32_t)g.rd_d[ro + i - 2], 127u)];
+                    B = tIM * tmi_prev;
+                    C = tIM * tmd_prev;
+                    G = ec * tmi_prev / ei;
+                } else {
+                    C = tIM;  // row 0: D~ = c0 (tMD_0 = 1); I~ of row 0 is 0, so b = g = 0 and the rotated-in value is ignored
+                }
+                DD = ec;
+                const double e = c_eps[q];
+                // tMM goes into the priors and divides b and c; tMM = 0 cannot be factored out: NaN -> fp64 redo
+                const double inv = A > 0.0 ? 1.0 / A : __longlong_as_double(0x7ff8000000000000LL);
+                pm = (1.0 - e) * A;
+                px = (g.tristate_off ? e : e / 3.0) * A;
+                B *= inv; C *= inv;
+                switch (x) {  // LoglessPDPairHMM.isBasePDMatching :184-204
+                    case 'A': case 'a': abit = 1; break;
+                    case 'C': case 'c': abit = 2; break;
+                    case 'G': case 'g': abit = 4; break;
+                    case 'T': case 't': abit = 8; break;
+                    case 'N': abit = 0; break;
+                    default: abit = 0x80000000u;  // the reference throws when such a base meets a SNP column it does not match
+                }
+            } else if (i == R + 1) {  // accumulator row: M_acc = 1 * (M_R + tMI_R * I~_R) = (M + I)[R]
+                B = R >= 1 ? c_eps[min((uint32_t)g.rd_i[ro + R - 1], 127u)] : 0.0;
+                DD = 1.0;
+            }
+            if (lane == 31 && k == K - 1) DD = 1.0;  // carrier of the virtual row 0: keeps D~ = c0
+            cb[k] = (float)B; cc[k] = (float)C; cg[k] = (float)G; cd[k] = (float)DD;
+            const float pmf = (float)pm, pxf = (float)px;
+            for (int y = 0; y < g.n_codes; ++y) {
+                float v = 0.f;
+                if (real) {
+                    if (y >= 1) {
+                        const uint32_t hb = g.code_byte[y], cm = g.code_mask[y];
+                        bool match = x == hb || x == (uint32_t)'N' || hb == (uint32_t)'N';
+                        if (!match && (cm & 0x80u)) {
+                            const bool here = ((y < 32 ? hp.codes_lo >> y : hp.codes_hi >> (y - 32)) & 1u) != 0;
+                            if ((abit & 0x80000000u) && here) atomicExch(g.err, 2);
+                            match = (cm & abit & PD_MASK_BITS) != 0;
+                        }
+                        v = match ? pmf : pxf;
+                    }
+                } else if (i == R + 1) {
+                    v = 1.f;
+                }
+                tab_s[((y * NV + k / 4) * 32 + lane) * 4 + (k % 4)] = v;
+            }
+        }
+        __syncwarp();
+
+        FastState<K> st;
+        float bM[K], bI[K], bD[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) { st.M[k] = 0.f; st.I[k] = 0.f; st.D[k] = 0.f; bM[k] = 0.f; bI[k] = 0.f; bD[k] = 0.f; }
+        if (lane == 31) st.D[K - 1] = c0;
+        st.dgm = 0.f; st.dgi = 0.f; st.dgd = lane == 0 ? c0 : 0.f;
+        float dgbm = 0.f, dgbi = 0.f, dgbd = 0.f;
+        st.acc = 0.f;
+        st.p = 0;
+        st.sp = g.codes + hp.code_off - lane;  // lane l works on column (step - l); columns <= 0 and > H read the zero padding
+        st.y = ldg_u8(st.sp);
+
+        int step = 1;
+        for (uint32_t sg = 0; sg < hp.n_segs; ++sg) {
+            const uint2 seg = g.segs[hp.seg_first + sg];
+#pragma unroll 2
+            for (uint32_t s = 0; s < seg.x; ++s)
+                fast_step<K, false>(st, cb, cc, cg, cd, tab_lane, src_lane, lane, 0, 0, c0, nullptr, nullptr, 0, 0, 0, 0);
+            step += (int)seg.x;
+            int p = step - lane;  // 1-based column of this lane
+#pragma unroll 1
+            for (uint32_t s = 0; s < seg.y; ++s, ++p) {
+                // ---- slow step: the full state machine, in the scaled representation ----
+                constexpr uint32_t CODE_STRIDE = NV * 32 * 16;
+                const uint32_t fl = ldg_u8(st.sp + flag_delta);
+                ++st.sp;
+                const uint32_t y_next = ldg_u8(st.sp);
+                const bool valid = p >= 1 && p <= H;
+                const float mu = __shfl_sync(FULL, st.M[K - 1], src_lane), iu = __shfl_sync(FULL, st.I[K - 1], src_lane);
+                const float du = __shfl_sync(FULL, st.D[K - 1], src_lane);
+                const float bmu = __shfl_sync(FULL, bM[K - 1], src_lane), biu = __shfl_sync(FULL, bI[K - 1], src_lane);
+                const float bdu = __shfl_sync(FULL, bD[K - 1], src_lane);
+                float pr[NV * 4];
+                {
+                    const uint32_t addr = st.y * CODE_STRIDE + tab_lane;
+#pragma unroll
+                    for (int v = 0; v < NV; ++v) {
+                        const float4 q = lds128(addr + v * 512);
+                        pr[v * 4 + 0] = q.x; pr[v * 4 + 1] = q.y; pr[v * 4 + 2] = q.z; pr[v * 4 + 3] = q.w;
+                    }
+                }
+                const bool del_end = (fl & PD_DEL_END_BIT) != 0;
+                const uint32_t t_row1 = (fl >> PD_TYPE_SHIFT) & PD_TYPE_BITS;
+                uint32_t t_rest = t_row1;
+                if (valid && (uint32_t)p <= t.first_event)
+                    t_rest = t.carry == PD_INSIDE_DEL ? PD_INSIDE_DEL : (t.carry == PD_AFTER_DEL && p == 1 ? PD_AFTER_DEL : PD_NORMAL);
+                float Mn[K], Dn[K], In[K], nbM[K], nbI[K], nbD[K];
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    const bool is_real = (real_mask >> k) & 1u;
+                    const uint32_t ty = !is_real ? PD_NORMAL : ((lane == 0 && k == 0) ? t_row1 : t_rest);
+                    const bool inside = ty == PD_INSIDE_DEL, after = ty == PD_AFTER_DEL;
+                    float am = k ? st.M[k - 1] : st.dgm, ai = k ? st.I[k - 1] : st.dgi, ad = k ? st.D[k - 1] : st.dgd;
+                    const float abm = k ? bM[k - 1] : dgbm, abi = k ? bI[k - 1] : dgbi, abd = k ? bD[k - 1] : dgbd;
+                    const float xm = pd_max(bM[k], st.M[k]), xi = pd_max(bI[k], st.I[k]), xd = pd_max(bD[k], st.D[k]);
+                    nbM[k] = inside ? bM[k] : (after ? xm : st.M[k]);
+                    nbI[k] = inside ? bI[k] : (after ? xi : st.I[k]);
+                    nbD[k] = inside ? bD[k] : (after ? xd : st.D[k]);
+                    am = after ? pd_max(abm, am) : am; ai = after ? pd_max(abi, ai) : ai; ad = after ? pd_max(abd, ad) : ad;
+                    const float lm = after ? xm : st.M[k], ld = after ? xd : st.D[k];  // this row, previous column
+                    float u = __fmaf_rn(cc[k], ad, am);
+                    u = __fmaf_rn(cb[k], ai, u);
+                    Mn[k] = pr[k] * u;
+                    Dn[k] = __fmaf_rn(cd[k], ld, lm);
+                }
+                // insertion: row above at THIS column -- chain down the lane's rows (DEL_END merges the branch in)
+                float um = mu, ui = iu, ubm = bmu, ubi = biu;
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    const bool is_real = (real_mask >> k) & 1u;
+                    const bool merge = del_end && is_real;
+                    const float xm = merge ? pd_max(ubm, um) : um, xi = merge ? pd_max(ubi, ui) : ui;
+                    In[k] = __fmaf_rn(cg[k], xi, xm);
+                    um = Mn[k]; ui = In[k]; ubm = nbM[k]; ubi = nbI[k];
+                }
+#pragma unroll
+                for (int k = 0; k < K; ++k) { st.M[k] = Mn[k]; st.I[k] = In[k]; st.D[k] = Dn[k]; bM[k] = nbM[k]; bI[k] = nbI[k]; bD[k] = nbD[k]; }
+                st.dgm = mu; st.dgi = iu; st.dgd = du; dgbm = bmu; dgbi = biu; dgbd = bdu;
+                st.y = y_next;
+            }
+            step += (int)seg.y;
+        }
+        // every lane is past column H + 1: the accumulator row holds sum_j (M + I)[R][j] as M + D~
+        float v = 0.f;
+#pragma unroll
+        for (int k = 0; k < K; ++k)
+            if (k == acc_slot) v = st.M[k] + st.D[k];
+        v = __shfl_sync(FULL, v, acc_lane);
+        if (lane == 0) g.sums[g.first + ti] = v;
+    }
+}
+
 constexpr float PD_RESCUE_THRESHOLD_F32 = 1e-28f;
 
 // fp32 sums -> log10 likelihoods, or onto the redo list
