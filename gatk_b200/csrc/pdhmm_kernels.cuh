@@ -260,7 +260,7 @@ struct PdFastArgs {
 };
 
 template <int K>
-__global__ void __launch_bounds__(32, K > 5 ? 12 : 16) phmm_pd_fast_kernel(const PdFastArgs g)
+__global__ void __launch_bounds__(32, K > 5 ? 16 : 20) phmm_pd_fast_kernel(const PdFastArgs g)
 {
     constexpr int NV = (K + 3) / 4;
     constexpr unsigned FULL = 0xffffffffu;
@@ -377,6 +377,12 @@ __global__ void __launch_bounds__(32, K > 5 ? 12 : 16) phmm_pd_fast_kernel(const
                 fast_step<K, false>(st, cb, cc, cg, cd, tab_lane, src_lane, lane, 0, 0, c0, nullptr, nullptr, 0, 0, 0, 0);
             step += (int)seg.x;
             int p = step - lane;  // 1-based column of this lane
+            // the branch values are dead between two slow windows: every lane refreshes them (NORMAL: branch = the value one
+            // column back) in the step before it reaches a column of the state machine, and that step is inside the window.
+            // Saying so here keeps them out of the registers the fast loop holds
+#pragma unroll
+            for (int k = 0; k < K; ++k) { bM[k] = 0.f; bI[k] = 0.f; bD[k] = 0.f; }
+            dgbm = 0.f; dgbi = 0.f; dgbd = 0.f;
 #pragma unroll 1
             for (uint32_t s = 0; s < seg.y; ++s, ++p) {
                 // ---- slow step: the full state machine, in the scaled representation ----
