@@ -117,7 +117,7 @@ int run_pd_batch(gphmm *h, const gphmm_batch *b, const uint8_t *hap_pd, double *
             const gphmm_unit &un = b->units[u];
             const uint32_t nr = (uint32_t)(un.read_end - un.read_begin), nh = (uint32_t)(un.hap_end - un.hap_begin);
             unit_out_base.push_back(n_pairs);
-            struct HapInfo { uint32_t off, H, first_event, carry, index; };
+            struct HapInfo { uint32_t off, H, first_event, carry, index; bool sparse; };
             std::vector<HapInfo> hi(nh);
             for (uint32_t k = 0; k < nh; ++k) {
                 const int64_t ho = b->hap_off[un.hap_begin + k];
@@ -154,6 +154,11 @@ int run_pd_batch(gphmm *h, const gphmm_batch *b, const uint8_t *hap_pd, double *
                 ph.seg_first = (uint32_t)segs.size();
                 plan_pd_steps(hap_flags.data() + hi[k].off, H, hi[k].first_event, hi[k].carry, segs, slow_scratch);
                 ph.n_segs = (uint32_t)segs.size() - ph.seg_first;
+                // densely flagged haplotypes (most steps inside a deletion window) stay with the first-version kernels,
+                // whose per-step fast path works column by column
+                uint32_t n_slow = 0;
+                for (uint32_t q = ph.seg_first; q < (uint32_t)segs.size(); ++q) n_slow += segs[q].y;
+                hi[k].sparse = 2 * n_slow <= H + 33;
                 haps.push_back(ph);
             }
             for (uint32_t r = 0; r < nr; ++r) {
@@ -166,7 +171,7 @@ int run_pd_batch(gphmm *h, const gphmm_batch *b, const uint8_t *hap_pd, double *
                     t.read = rl; t.hap_off = hi[k].off; t.H = hi[k].H; t.out_slot = n_pairs + r * nh + k;
                     t.first_event = hi[k].first_event; t.carry = hi[k].carry;
                     t.c0_exp = 125 - ceil_log2(hi[k].H); t.pad = hi[k].index;
-                    if (fbucket >= 0) {
+                    if (fbucket >= 0 && hi[k].sparse) {
                         // scaled states (I / tMI, D / tMD) need the head-room of the plain fp32 kernels
                         PdTask tf = t;
                         tf.c0_exp = C0_BASE_EXP_F32 - ceil_log2(hi[k].H);
