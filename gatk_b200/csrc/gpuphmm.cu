@@ -1245,9 +1245,10 @@ int run_batch(gphmm *h, const gphmm_batch *b, double *out, const gphmm_region_st
     validate_batch(b);
     if (b->n_units == 0) return GPHMM_OK;
     if (!out) throw Error(GPHMM_ERR_INVALID_ARG, "out is null");
-    // several devices drain one list of chunks: smaller chunks balance the end of the batch (unless the caller fixed the size)
-    const int64_t cells_per_chunk = h->cfg.chunk_cells > 0 ? h->chunk_cells() : h->chunk_cells() / (int64_t)std::min<size_t>(std::max<size_t>(h->devices.size(), 1), 4);
-    auto chunks = split_units(b, cells_per_chunk, h->chunk_bytes(), true);
+    // several devices drain one list of chunks: full-size chunks through the middle of the batch (their fixed costs weigh
+    // least), geometrically smaller ones at the end so that the devices finish together (unless the caller fixed the size)
+    const bool fixed_size = h->cfg.chunk_cells > 0;
+    auto chunks = split_units(b, h->chunk_cells(), h->chunk_bytes(), true, fixed_size ? 0 : (int)std::max<size_t>(h->devices.size(), 1));
     if (getenv("GPHMM_TRACE")) fprintf(stderr, "[gpuphmm] batch of %lld units: validated and split into %zu chunks in %.2f ms\n", (long long)b->n_units, chunks.size(), now_ms() - t0);
     std::atomic<size_t> cursor{0};
     const size_t nd = h->devices.size();

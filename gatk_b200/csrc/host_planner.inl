@@ -72,26 +72,40 @@ inline unsigned qual_shape(const uint8_t *qi, const uint8_t *qd, const uint8_t *
     return (ai == 0 ? 1u : 0u) | (ad == 0 ? 2u : 0u) | (ac == 0 ? 4u : 0u) | (as == 0 ? 8u : 0u);
 }
 
-// Greedy split of the unit list into chunks bounded by cells and staged bytes.
-std::vector<std::pair<int64_t, int64_t>> split_units(const gphmm_batch *b, int64_t chunk_cells, int64_t chunk_bytes, bool ramp_up) {
+// Greedy split of the unit list into chunks bounded by cells and staged bytes.  With `ramp_up` (staged batches) the first
+// chunks are small, so that the GPU starts while the host is still planning; with `taper_devices` > 0 the last chunks shrink
+// geometrically (remaining cells / (2 x devices), not below 2.5e9), so that the devices draining one chunk list finish
+// together and little is left after the last kernel -- the middle of the batch keeps full-size chunks, whose fixed costs
+// (drain of the persistent grids, closing kernels, download) weigh least.
+std::vector<std::pair<int64_t, int64_t>> split_units(const gphmm_batch *b, int64_t chunk_cells, int64_t chunk_bytes, bool ramp_up,
+                                                     int taper_devices = 0) {
     std::vector<std::pair<int64_t, int64_t>> out;
     int64_t u = 0;
     const int64_t full_cells = chunk_cells;
+    auto unit_cells = [b](const gphmm_unit &un) {
+        const int64_t nr = un.read_end - un.read_begin, nh = un.hap_end - un.hap_begin;
+        const int64_t rb = nr ? b->read_off[un.read_end] - b->read_off[un.read_begin] : 0;
+        const int64_t hb = nh ? b->hap_off[un.hap_end] - b->hap_off[un.hap_begin] : 0;
+        return rb * hb;
+    };
+    int64_t remaining = 0;
+    if (taper_devices > 0)
+        for (int64_t k = 0; k < b->n_units; ++k) remaining += unit_cells(b->units[k]);
     while (u < b->n_units) {
         // ramp up: the first chunks are small so that the GPU starts early while the host is still staging
         const size_t ci = out.size();
         // (2.5e8 cells = a handful of regions, then doubling: the planner threads stay ahead of the GPU from there on)
         chunk_cells = (!ramp_up || ci >= 16) ? full_cells : std::min<int64_t>(full_cells, (int64_t)250000000 << ci);
+        if (taper_devices > 0) chunk_cells = std::min(chunk_cells, std::max<int64_t>(2500000000LL, remaining / (2 * (int64_t)taper_devices)));
         int64_t cells = 0, bytes = 0, pairs = 0, u_end = u;
         int64_t r_lo = INT64_MAX, r_hi = 0;
         while (u_end < b->n_units) {
             const gphmm_unit &un = b->units[u_end];
             const int64_t nr = un.read_end - un.read_begin, nh = un.hap_end - un.hap_begin;
-            const int64_t rb = nr ? b->read_off[un.read_end] - b->read_off[un.read_begin] : 0;
             const int64_t hb = nh ? b->hap_off[un.hap_end] - b->hap_off[un.hap_begin] : 0;
             const int64_t n_lo = std::min(r_lo, nr ? un.read_begin : r_lo), n_hi = std::max(r_hi, nr ? un.read_end : r_hi);
             const int64_t span = n_hi > n_lo ? b->read_off[n_hi] - b->read_off[n_lo] : 0;
-            const int64_t c = rb * hb;
+            const int64_t c = unit_cells(un);
             if (u_end > u && (cells + c > chunk_cells || span * 5 + bytes + hb > chunk_bytes || pairs + nr * nh > (int64_t)1 << 25))
                 break;
             cells += c; bytes += hb + nh; pairs += nr * nh;
@@ -102,6 +116,7 @@ std::vector<std::pair<int64_t, int64_t>> split_units(const gphmm_batch *b, int64
         if (span >= ((int64_t)1 << 31) || bytes >= ((int64_t)1 << 31) || pairs >= ((int64_t)1 << 28))
             throw Error(GPHMM_ERR_TOO_LARGE, "a single unit exceeds the per-chunk device budget");
         out.emplace_back(u, u_end);
+        remaining -= cells;
         u = u_end;
     }
     return out;
@@ -400,7 +415,11 @@ void plan_chunk(const gphmm_batch *b, int64_t u0, int64_t u1, bool force_fp64, b
     int64_t n_reads_with_work = 0;
     for (int64_t u = u0; u < u1; ++u)
         if (b->units[u].hap_end > b->units[u].hap_begin) n_reads_with_work += b->units[u].read_end - b->units[u].read_begin;
-    const int64_t want_groups = n_reads_with_work > 0 ? (TARGET_TASKS + n_reads_with_work - 1) / n_reads_with_work : 1;
+    // two reads per warp (half-warp kernels) when the chunk still fills the GPU that way: 148 SMs x 16 resident warps, twice
+    // over; smaller chunks keep one read per warp and split the haplotypes of a unit into groups instead
+    static const bool half_warp = getenv("GPHMM_NO_HALFWARP") == nullptr;  // A/B switch: every read on a full warp
+    const bool pair_reads_ok = half_warp && !force_fp64 && n_reads_with_work >= 148 * 16 * 2 * 2;
+    const int64_t want_groups = pair_reads_ok ? 1 : (n_reads_with_work > 0 ? (TARGET_TASKS + n_reads_with_work - 1) / n_reads_with_work : 1);
     std::vector<Task> raw;
     std::vector<uint8_t> bucket_of;
     raw.reserve((size_t)(c.r_hi - c.r_lo));
@@ -422,7 +441,6 @@ void plan_chunk(const gphmm_batch *b, int64_t u0, int64_t u1, bool force_fp64, b
     SharingScratch scratch;
     std::vector<int> order;
     std::vector<uint64_t> pair_reads[N_PAIR_BUCKETS];  // per half-warp bucket: (slot of the last row << 32) | unit-local read index
-    static const bool half_warp = getenv("GPHMM_NO_HALFWARP") == nullptr;  // A/B switch: every read on a full warp
     uint32_t bucket_count[N_FP32_BUCKETS] = {0};
     for (int64_t u = u0; u < u1; ++u) {
         const gphmm_unit &un = b->units[u];
@@ -518,9 +536,7 @@ void plan_chunk(const gphmm_batch *b, int64_t u0, int64_t u1, bool force_fp64, b
             const uint32_t rl = d.read_first + r;
             const uint32_t R = c.read_off[rl + 1] - c.read_off[rl];
             c.cells += (int64_t)R * sum_h;
-            // (a chunk too small to fill the GPU keeps one read per warp: twice as many independent wavefronts hide latency
-            // better than fewer instructions per cell do)
-            const int pb = (half_warp && !force_fp64 && want_groups <= 1) ? pair_bucket_of_read(R) : -1;
+            const int pb = pair_reads_ok ? pair_bucket_of_read(R) : -1;
             if (pb >= 0) {  // paired below, once every read of the unit is known
                 pair_reads[pb - FIRST_PAIR_BUCKET].push_back(((uint64_t)((R - 1) % (uint32_t)pair_bucket_rows(pb)) << 32) | r);
                 continue;
