@@ -1677,11 +1677,14 @@ int gphmm_plan_stats(const gphmm_batch *b, int prefix_sharing, int64_t out[10]) 
             plan_chunk(b, ch.first, ch.second, false, prefix_sharing != 0, c);
             out[0] += (int64_t)c.units.size();
             out[1] += (int64_t)c.pass_info.size();
-            out[2] += (int64_t)c.segments.size();
-            for (const Segment &sg : c.segments) {
-                out[3] += sg.n_free;
-                out[4] += sg.n_chk;
-                out[5] += sg.snap_pos != INT32_MIN;
+            for (const UnitSched &us : c.unit_sched) {  // the full-warp schedule (half-warp tasks run a second one with 16-step windows)
+                out[2] += (int64_t)us.n_segs;
+                for (uint32_t q = us.seg_first; q < us.seg_first + us.n_segs; ++q) {
+                    const Segment &sg = c.segments[q];
+                    out[3] += sg.n_free;
+                    out[4] += sg.n_chk;
+                    out[5] += sg.snap_pos != INT32_MIN;
+                }
             }
             for (size_t u = 0; u < c.units.size(); ++u) {
                 int64_t cols = 0;

@@ -151,7 +151,8 @@ struct SharingScratch {
 };
 
 UnitSched plan_unit_sharing(const gphmm_batch *b, const gphmm_unit &un, uint32_t hap_first_local, bool share, ChunkPlan &c,
-                            int64_t sum_read_len, const std::vector<int> &full_order, int g_first, int g_count, SharingScratch &ws) {
+                            int64_t sum_read_len, const std::vector<int> &full_order, int g_first, int g_count, SharingScratch &ws,
+                            bool half_warp_schedule = false) {
     constexpr uint32_t SPACING = 32;
     static const uint32_t NEAR_DEPTHS = getenv("GPHMM_NEAR_DEPTHS") ? (uint32_t)std::max(1, atoi(getenv("GPHMM_NEAR_DEPTHS"))) : 96u;  // how far below the shared depth to look
     static const uint32_t MIN_DEPTH = getenv("GPHMM_MIN_DEPTH") ? (uint32_t)std::max(32, atoi(getenv("GPHMM_MIN_DEPTH"))) : 32u;  // tuning knob
@@ -252,46 +253,55 @@ UnitSched plan_unit_sharing(const gphmm_batch *b, const gphmm_unit &un, uint32_t
         c.computed_columns += H - r[i];
     }
     // schedule.  Lane l meets stream position q at step q + l, so an END column at e keeps some lane busy with it
-    // during steps [e, e+32) and a snapshot position s during [s, s+32).  END windows never overlap each other
-    // (passes span >= 32 positions), snapshot windows never overlap each other (SPACING), so at any step at most one
-    // of each is active.  A segment = branch-free steps, then checked steps with one constant (END, snapshot) pair.
-    std::vector<uint32_t> &pts = ws.pts;
-    pts.clear();
-    pts.push_back(1);
-    for (int i = 0; i < n; ++i) { pts.push_back(end_pos[i]); pts.push_back(end_pos[i] + 32); }
-    for (const Snap &sn : snaps) { pts.push_back(sn.pos); pts.push_back(sn.pos + 32); }
-    std::sort(pts.begin(), pts.end());
-    pts.erase(std::unique(pts.begin(), pts.end()), pts.end());
+    // during steps [e, e+W) and a snapshot position s during [s, s+W), W = lanes per read (32, or 16 for the half-warp
+    // kernels).  END windows never overlap each other (passes span >= 32 positions), snapshot windows never overlap each
+    // other (SPACING), so at any step at most one of each is active.  A segment = branch-free steps, then checked steps
+    // with one constant (END, snapshot) pair.
     std::vector<int> &snap_by_pos = ws.snap_by_pos;
     snap_by_pos.resize(snaps.size());
     for (size_t q = 0; q < snaps.size(); ++q) snap_by_pos[q] = (int)q;
     std::sort(snap_by_pos.begin(), snap_by_pos.end(), [&](int x, int y) { return snaps[x].pos < snaps[y].pos; });
-    Segment seg;
-    auto clear_seg = [&]() { seg.n_free = 0; seg.n_chk = 0; seg.snap_pos = INT32_MIN; seg.snap_slot = 0; seg.end_restore = MAX_SNAP_SLOTS; seg.end_out = 0; };
-    clear_seg();
-    size_t ie = 0, is = 0;  // first END / snapshot whose window has not expired yet
-    for (size_t k = 0; k + 1 < pts.size(); ++k) {
-        const uint32_t x = pts[k], y = pts[k + 1];
-        while (ie < (size_t)n && end_pos[ie] + 32 <= x) ++ie;
-        while (is < snaps.size() && snaps[snap_by_pos[is]].pos + 32 <= x) ++is;
-        const bool end_on = ie < (size_t)n && end_pos[ie] <= x;
-        const bool snap_on = is < snaps.size() && snaps[snap_by_pos[is]].pos <= x;
-        static const bool all_checked = getenv("GPHMM_ALL_CHECKED") != nullptr;  // experiment: cost of the checked loop
-        if (!end_on && !snap_on && !all_checked) {
+    auto build_schedule = [&](uint32_t W) {
+        std::vector<uint32_t> &pts = ws.pts;
+        pts.clear();
+        pts.push_back(1);
+        for (int i = 0; i < n; ++i) { pts.push_back(end_pos[i]); pts.push_back(end_pos[i] + W); }
+        for (const Snap &sn : snaps) { pts.push_back(sn.pos); pts.push_back(sn.pos + W); }
+        std::sort(pts.begin(), pts.end());
+        pts.erase(std::unique(pts.begin(), pts.end()), pts.end());
+        Segment seg;
+        auto clear_seg = [&]() { seg.n_free = 0; seg.n_chk = 0; seg.snap_pos = INT32_MIN; seg.snap_slot = 0; seg.end_restore = MAX_SNAP_SLOTS; seg.end_out = 0; };
+        clear_seg();
+        size_t ie = 0, is = 0;  // first END / snapshot whose window has not expired yet
+        for (size_t k = 0; k + 1 < pts.size(); ++k) {
+            const uint32_t x = pts[k], y = pts[k + 1];
+            while (ie < (size_t)n && end_pos[ie] + W <= x) ++ie;
+            while (is < snaps.size() && snaps[snap_by_pos[is]].pos + W <= x) ++is;
+            const bool end_on = ie < (size_t)n && end_pos[ie] <= x;
+            const bool snap_on = is < snaps.size() && snaps[snap_by_pos[is]].pos <= x;
+            static const bool all_checked = getenv("GPHMM_ALL_CHECKED") != nullptr;  // experiment: cost of the checked loop
+            if (!end_on && !snap_on && !all_checked) {
+                if (seg.n_chk) { c.segments.push_back(seg); clear_seg(); }
+                seg.n_free += y - x;
+                continue;
+            }
             if (seg.n_chk) { c.segments.push_back(seg); clear_seg(); }
-            seg.n_free += y - x;
-            continue;
+            seg.n_chk = y - x;
+            if (snap_on) { seg.snap_pos = (int32_t)snaps[snap_by_pos[is]].pos; seg.snap_slot = (uint8_t)snaps[snap_by_pos[is]].slot; }
+            if (end_on) {
+                seg.end_out = (uint16_t)order[ie];
+                seg.end_restore = (int8_t)(ie + 1 < (size_t)n && snap_of_pass[ie + 1] >= 0 ? snaps[snap_of_pass[ie + 1]].slot : MAX_SNAP_SLOTS);  // MAX_SNAP_SLOTS = pass-start state
+            }
         }
-        if (seg.n_chk) { c.segments.push_back(seg); clear_seg(); }
-        seg.n_chk = y - x;
-        if (snap_on) { seg.snap_pos = (int32_t)snaps[snap_by_pos[is]].pos; seg.snap_slot = (uint8_t)snaps[snap_by_pos[is]].slot; }
-        if (end_on) {
-            seg.end_out = (uint16_t)order[ie];
-            seg.end_restore = (int8_t)(ie + 1 < (size_t)n && snap_of_pass[ie + 1] >= 0 ? snaps[snap_of_pass[ie + 1]].slot : MAX_SNAP_SLOTS);  // MAX_SNAP_SLOTS = pass-start state
-        }
-    }
-    if (seg.n_free || seg.n_chk) c.segments.push_back(seg);
+        if (seg.n_free || seg.n_chk) c.segments.push_back(seg);
+    };
+    build_schedule(32);
     us.n_segs = (uint32_t)c.segments.size() - us.seg_first;
+    if (half_warp_schedule) {  // the same passes and snapshots with 16-step windows (the last window ends 16 steps earlier)
+        us.seg16_first = (uint32_t)c.segments.size();
+        build_schedule(16);
+        us.n_segs16 = (uint32_t)c.segments.size() - us.seg16_first;
+    }
     return us;
 }
 
@@ -501,7 +511,7 @@ void plan_chunk(const gphmm_batch *b, int64_t u0, int64_t u1, bool force_fp64, b
             sorted_hap_order(b, un, share && !force_fp64, order);
             for (int gi = 0; gi < n_groups; ++gi) {
                 const int g0 = (int)((int64_t)nh * gi / n_groups), g1 = (int)((int64_t)nh * (gi + 1) / n_groups);
-                c.unit_sched.push_back(plan_unit_sharing(b, un, d.hap_first, share && !force_fp64, c, fast_read_len, order, g0, g1 - g0, scratch));
+                c.unit_sched.push_back(plan_unit_sharing(b, un, d.hap_first, share && !force_fp64, c, fast_read_len, order, g0, g1 - g0, scratch, pair_reads_ok));
             }
         }
         if (nh == 0) continue;

@@ -94,7 +94,8 @@ struct UnitSched {
     uint32_t pass_first, n_passes;  // into pass_info
     uint32_t seg_first, n_segs;     // into segments
     uint32_t sstream_off;           // first column of the unit's shared (prefix-compressed) stream
-    uint32_t pad0, pad1, pad2;
+    uint32_t seg16_first, n_segs16; // the same schedule with 16-step windows (half-warp kernels); n_segs16 = 0: not planned
+    uint32_t pad2;
 };
 constexpr int MAX_SNAP_SLOTS = 8;      // + 1 slot per CTA for the pass-start state
 constexpr int SNAP_REGS = 3 * 8 + 4;  // M, I~, D~ of up to 8 rows + hand-off triple + accumulator
@@ -875,8 +876,9 @@ __global__ void __launch_bounds__(32, flat_min_ctas(K, SYM, LANES)) phmm_flat_f3
         }
         float *const slab = g.snap + (size_t)blockIdx.x * ((MAX_SNAP_SLOTS + 1) * 32 * REGS) + lane * REGS;
         snap_save<K>(st, slab, ZERO_SLOT);  // the pass-start state (all zero), restored at every END that begins a fresh pass
+        const bool narrow = LANES == 16 && us.n_segs16 != 0;  // 16 lanes per read: END / snapshot windows of 16 steps
         flat_dispatch<K, 0, SYM>(acc_slot, st, f, A, C, B0, G0, E0, tab_lane, src_lane, pl, acc_lane, sums + out_base, slab,
-                            g.segments + us.seg_first, us.n_segs);
+                            g.segments + (narrow ? us.seg16_first : us.seg_first), narrow ? us.n_segs16 : us.n_segs);
     }
 }
 
