@@ -425,10 +425,10 @@ void plan_chunk(const gphmm_batch *b, int64_t u0, int64_t u1, bool force_fp64, b
     int64_t n_reads_with_work = 0;
     for (int64_t u = u0; u < u1; ++u)
         if (b->units[u].hap_end > b->units[u].hap_begin) n_reads_with_work += b->units[u].read_end - b->units[u].read_begin;
-    // two reads per warp (half-warp kernels) when the chunk still fills the GPU that way: 148 SMs x 16 resident warps, twice
-    // over; smaller chunks keep one read per warp and split the haplotypes of a unit into groups instead
+    // two reads per warp (half-warp kernels) when the chunk still fills the GPU that way: one wave of 148 SMs x 16 resident
+    // warps; smaller chunks keep one read per warp and split the haplotypes of a unit into groups instead
     static const bool half_warp = getenv("GPHMM_NO_HALFWARP") == nullptr;  // A/B switch: every read on a full warp
-    const bool pair_reads_ok = half_warp && !force_fp64 && n_reads_with_work >= 148 * 16 * 2 * 2;
+    const bool pair_reads_ok = half_warp && !force_fp64 && n_reads_with_work >= 148 * 16 * 2;
     const int64_t want_groups = pair_reads_ok ? 1 : (n_reads_with_work > 0 ? (TARGET_TASKS + n_reads_with_work - 1) / n_reads_with_work : 1);
     std::vector<Task> raw;
     std::vector<uint8_t> bucket_of;

@@ -299,6 +299,31 @@ def test_chunking_is_invisible():
     assert np.array_equal(a, c)
 
 
+def test_lane_layout_is_invisible():
+    # a chunk with enough reads runs two reads of a unit per warp (half-warp kernels, 10-16 rows per lane) where their last
+    # rows fall on the same register slot; small chunks keep one read per warp (5-8 rows per lane) and split the haplotypes
+    # into groups.  A row's arithmetic does not depend on the slot it lands on, so both layouts give the same bits --
+    # for 250-base reads (configs[1]), 150-base reads (configs[0] shape) and PCR-indel-model-like per-base gap qualities
+    rng = np.random.default_rng(9)
+    for b in (synth.config2(200), synth.config1_many(48)):
+        assert b.n_reads >= 148 * 16 * 2
+        sym = b.ins_q.copy()
+        sym[rng.random(len(sym)) < 0.1] = 38
+        variants = (b, Batch(b.read_bases, b.base_q, sym, sym.copy(), b.gcp, b.read_off, b.hap_bases, b.hap_off, b.units))
+        with GpuPhmm() as paired, GpuPhmm(chunk_cells=400_000_000) as single:
+            for v in variants:
+                p = paired.prepare(v)   # one chunk holding every read (the staged path ramps its chunk sizes up from small ones)
+                a = np.full(v.n_out, np.nan)
+                paired.run_prepared(p, a)
+                paired.release_prepared(p)
+                c = single.compute(v)
+                assert np.array_equal(a, c)
+        sub = Batch(b.read_bases, b.base_q, sym, sym.copy(), b.gcp, b.read_off, b.hap_bases, b.hap_off, b.units[:6])
+        want = oracle_batch(sub)
+        n = sub.n_out
+        assert np.abs(a[:n] - want[:n]).max() <= TOL
+
+
 def test_invariants_at_scale(hmm):
     # size-independent properties on a larger slice of configs[1]:
     #  - permutation invariance: shuffling the unit order permutes the outputs, bit for bit
