@@ -95,7 +95,9 @@ std::vector<std::pair<int64_t, int64_t>> split_units(const gphmm_batch *b, int64
         // ramp up: the first chunks are small so that the GPU starts early while the host is still staging
         const size_t ci = out.size();
         // (2.5e8 cells = a handful of regions, then doubling: the planner threads stay ahead of the GPU from there on)
-        chunk_cells = (!ramp_up || ci >= 16) ? full_cells : std::min<int64_t>(full_cells, (int64_t)250000000 << ci);
+        // (with several devices every device gets a small first chunk, a larger second one, ...)
+        const size_t ramp_step = ci / (size_t)std::max(1, taper_devices);
+        chunk_cells = (!ramp_up || ramp_step >= 16) ? full_cells : std::min<int64_t>(full_cells, (int64_t)250000000 << ramp_step);
         if (taper_devices > 0) chunk_cells = std::min(chunk_cells, std::max<int64_t>(2500000000LL, remaining / (2 * (int64_t)taper_devices)));
         int64_t cells = 0, bytes = 0, pairs = 0, u_end = u;
         int64_t r_lo = INT64_MAX, r_hi = 0;
