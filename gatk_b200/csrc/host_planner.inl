@@ -239,6 +239,17 @@ UnitSched plan_unit_sharing(const gphmm_batch *b, const gphmm_unit &un, uint32_t
         r[i + 1] = snaps[k].depth;
         snap_of_pass[i + 1] = k;
     }
+    static const bool slot_histogram = getenv("GPHMM_SLOT_HISTOGRAM") != nullptr;
+    if (slot_histogram) {  // debugging aid: how many snapshot slots do units use?
+        static std::atomic<long> hist[MAX_SNAP_SLOTS + 1];
+        int mx = 0;
+        for (const Snap &sn : snaps) mx = std::max(mx, sn.slot + 1);
+        if (hist[mx].fetch_add(1) % 5000 == 4999 || mx == MAX_SNAP_SLOTS) {
+            fprintf(stderr, "[gpuphmm] snapshot slots used per unit:");
+            for (int k = 0; k <= MAX_SNAP_SLOTS; ++k) fprintf(stderr, " %d:%ld", k, hist[k].load());
+            fprintf(stderr, "\n");
+        }
+    }
     // stream + pass table
     for (int i = 0; i < n; ++i) {
         const uint32_t H = hap_len(order[i]);
