@@ -13,6 +13,7 @@
 // and lane 0 walks them back afterwards exactly like calculateCigar.
 #pragma once
 #include <stdint.h>
+#include <type_traits>
 
 namespace phmm_dev {
 
@@ -46,6 +47,52 @@ struct SwArgs {
 __device__ __forceinline__ int sw_edge(int idx, bool indel, int w_open, int w_extend) {
     // sw[0][j] and sw[i][0]: 0, or the leading-gap penalties of the INDEL strategies (:125-140)
     return (!indel || idx == 0) ? 0 : w_open + (idx - 1) * w_extend;
+}
+
+// One wavefront step of a lane: its K cells of the current column (SmithWatermanJavaAligner.java:160-215).  ALL_VALID
+// steps (every lane of the warp is on a column of the alternate) carry no per-cell predication; the pipeline fill and
+// drain run the guarded form.  The three-way choice keeps the reference's tie rules: diagonal if it is >= both gaps,
+// else the horizontal gap (insertion, -length) if it is >= the vertical one, else the vertical gap (deletion, +length).
+struct SwLane {
+    int a[SW_K], left[SW_K], bgh[SW_K], gsh[SW_K];
+    int last_sw, last_bgv, last_gsv;  // this lane's bottom row at its current column (what the lane below needs)
+    int diag0;                        // row above at the previous column
+};
+
+template <bool ALL_VALID>
+__device__ __forceinline__ void sw_step(SwLane &L, const bool valid, const int b, int up, int bgv, int gsv, const int w_match,
+                                        const int w_mismatch, const int w_open, const int w_extend, short4 &btv)
+{
+    constexpr int K = SW_K;
+    const int up_in = up;
+    int diag = L.diag0;
+    int16_t *btk = reinterpret_cast<int16_t *>(&btv);
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const int step_diag = diag + (L.a[k] == b ? w_match : w_mismatch);
+        // vertical gap ending here: open a new one from the cell above, or extend the best one of this column
+        const int open_v = up + w_open, ext_v = bgv + w_extend;
+        const bool new_v = open_v > ext_v;
+        bgv = max(open_v, ext_v);
+        gsv = new_v ? 1 : gsv + 1;
+        // horizontal gap ending here
+        const int open_h = L.left[k] + w_open, ext_h = L.bgh[k] + w_extend;
+        const bool new_h = open_h > ext_h;
+        const int nbgh = max(open_h, ext_h);
+        const int ngsh = new_h ? 1 : L.gsh[k] + 1;
+        const int gap = max(bgv, nbgh);
+        const bool take_diag = step_diag >= gap;
+        const int btr_gap = nbgh >= bgv ? -ngsh : gsv;
+        const int cur = max(max(step_diag, gap), SW_MATRIX_MIN_CUTOFF);
+        btk[k] = (int16_t)(take_diag ? 0 : btr_gap);
+        diag = L.left[k];  // sw[i][j-1] is the diagonal of the row below
+        if (ALL_VALID || valid) { L.left[k] = cur; L.bgh[k] = nbgh; L.gsh[k] = ngsh; }
+        up = cur;          // and this cell is "above" for the row below
+    }
+    if (ALL_VALID || valid) {
+        L.last_sw = up; L.last_bgv = bgv; L.last_gsv = gsv;
+        L.diag0 = up_in;   // row above at this column = diagonal of k = 0 at the next column
+    }
 }
 
 __global__ void __launch_bounds__(32) phmm_sw_kernel(const SwArgs g)
@@ -91,62 +138,55 @@ __global__ void __launch_bounds__(32) phmm_sw_kernel(const SwArgs g)
         for (int strip = 0; strip < n_strips; ++strip) {
             const bool first_strip = strip == 0, last_strip = strip == n_strips - 1;
             const int row0 = strip * SW_ROWS + lane * K;  // row of k = 0 is row0 + 1
-            int a[K], left[K], bgh[K], gsh[K];
+            SwLane L;
 #pragma unroll
             for (int k = 0; k < K; ++k) {
                 const int i = row0 + k + 1;
-                a[k] = i <= n_ref ? (int)ref[i - 1] : 0x100;
-                left[k] = sw_edge(i, indel, g.w_open, g.w_extend);  // sw[i][0]
-                bgh[k] = SW_LOW_INIT; gsh[k] = 0;
+                L.a[k] = i <= n_ref ? (int)ref[i - 1] : 0x100;
+                L.left[k] = sw_edge(i, indel, g.w_open, g.w_extend);  // sw[i][0]
+                L.bgh[k] = SW_LOW_INIT; L.gsh[k] = 0;
             }
-            int last_sw = 0, last_bgv = SW_LOW_INIT, last_gsv = 0;  // this lane's bottom row at its current column (what the lane below needs)
-            int diag0 = sw_edge(row0, indel, g.w_open, g.w_extend); // sw[row0][0]: row above at column 0
+            L.last_sw = 0; L.last_bgv = SW_LOW_INIT; L.last_gsv = 0;
+            L.diag0 = sw_edge(row0, indel, g.w_open, g.w_extend);  // sw[row0][0]: row above at column 0
+            // the row of the last reference base (bottom row of the matrix) lives in one slot of one lane of the last strip
+            const int k_last = last_strip && (n_ref - 1 - row0) >= 0 && (n_ref - 1 - row0) < K ? n_ref - 1 - row0 : -1;
             __syncwarp();
             int p = 1 - lane;
-            for (int s = 1; s <= n_steps; ++s, ++p) {
-                const bool valid = p >= 1 && p <= n_alt;
+            auto step = [&](auto all_valid) {
+                constexpr bool ALL = decltype(all_valid)::value;
+                const bool valid = ALL || (p >= 1 && p <= n_alt);
                 // row above at this column
-                int up = __shfl_up_sync(FULL, last_sw, 1), bgv = __shfl_up_sync(FULL, last_bgv, 1), gsv = __shfl_up_sync(FULL, last_gsv, 1);
+                int up = __shfl_up_sync(FULL, L.last_sw, 1), bgv = __shfl_up_sync(FULL, L.last_bgv, 1), gsv = __shfl_up_sync(FULL, L.last_gsv, 1);
                 if (lane == 0) {
                     if (first_strip) { up = sw_edge(p, indel, g.w_open, g.w_extend); bgv = SW_LOW_INIT; gsv = 0; }
                     else if (valid) { up = bnd[3 * p]; bgv = bnd[3 * p + 1]; gsv = bnd[3 * p + 2]; }
                 }
                 const int b = valid ? (int)alt[p - 1] : 0x200;
-                const int up_in = up;
-                int diag = diag0;
                 short4 btv;
-                int16_t *btk = reinterpret_cast<int16_t *>(&btv);
-#pragma unroll
-                for (int k = 0; k < K; ++k) {
-                    const int step_diag = diag + (a[k] == b ? g.w_match : g.w_mismatch);
-                    int prev_gap = up + g.w_open;
-                    bgv += g.w_extend;
-                    if (prev_gap > bgv) { bgv = prev_gap; gsv = 1; } else ++gsv;
-                    const int step_down = bgv, kd = gsv;
-                    prev_gap = left[k] + g.w_open;
-                    int nbgh = bgh[k] + g.w_extend, ngsh = gsh[k] + 1;
-                    if (prev_gap > nbgh) { nbgh = prev_gap; ngsh = 1; }
-                    const int step_right = nbgh, ki = ngsh;
-                    int cur, btr;
-                    if (step_diag >= step_down && step_diag >= step_right) { cur = step_diag; btr = 0; }
-                    else if (step_right >= step_down) { cur = step_right; btr = -ki; }
-                    else { cur = step_down; btr = kd; }
-                    cur = max(SW_MATRIX_MIN_CUTOFF, cur);
-                    btk[k] = (int16_t)btr;
-                    diag = left[k];          // sw[i][j-1] is the diagonal of the row below
-                    if (valid) { left[k] = cur; bgh[k] = nbgh; gsh[k] = ngsh; }
-                    up = cur;                // and this cell is "above" for the row below
-                    const int i = row0 + k + 1;
-                    if (valid && p == n_alt && i <= n_ref) lastcol[i] = cur;
-                    if (valid && i == n_ref) bottom[p] = cur;
-                }
+                sw_step<ALL>(L, valid, b, up, bgv, gsv, g.w_match, g.w_mismatch, g.w_open, g.w_extend, btv);
                 if (valid) {
+                    const int s = p + lane;  // step number (1-based): backtrack entries are stored in wavefront order
                     *reinterpret_cast<short4 *>(bt + (((size_t)strip * n_steps + (s - 1)) * 32 + lane) * K) = btv;
-                    last_sw = up; last_bgv = bgv; last_gsv = gsv;
-                    diag0 = up_in;           // row above at this column = diagonal of k = 0 at the next column
-                    if (!last_strip && lane == 31) { bnd[3 * p] = up; bnd[3 * p + 1] = bgv; bnd[3 * p + 2] = gsv; }
+                    if (!last_strip && lane == 31) { bnd[3 * p] = L.last_sw; bnd[3 * p + 1] = L.last_bgv; bnd[3 * p + 2] = L.last_gsv; }
+                    if (k_last >= 0) {  // bottom row, every column
+                        int v = L.left[0];
+#pragma unroll
+                        for (int k = 1; k < K; ++k) v = k == k_last ? L.left[k] : v;
+                        bottom[p] = v;
+                    }
+                    if (p == n_alt) {   // last column, every row of this lane
+#pragma unroll
+                        for (int k = 0; k < K; ++k)
+                            if (row0 + k + 1 <= n_ref) lastcol[row0 + k + 1] = L.left[k];
+                    }
                 }
-            }
+                ++p;
+            };
+            // fill (some lanes are still in front of column 1), steady state, drain (some lanes are past the last column)
+            int s = 1;
+            for (; s <= min(31, n_steps); ++s) step(std::false_type{});
+            for (; s <= n_alt; ++s) step(std::true_type{});
+            for (; s <= n_steps; ++s) step(std::false_type{});
             __syncwarp();
         }
         __threadfence_block();
