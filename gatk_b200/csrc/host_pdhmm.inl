@@ -63,56 +63,43 @@ void plan_pd_steps(const uint8_t *flags, uint32_t H, uint32_t first_event, uint3
     }
 }
 
-int run_pd_batch(gphmm *h, const gphmm_batch *b, const uint8_t *hap_pd, double *out) {
-    std::lock_guard<std::mutex> run_lk(h->run_mu);
-    const double t0 = now_ms();
-    validate_batch(b);
-    if (b->n_units == 0) return GPHMM_OK;
-    if (!out) throw Error(GPHMM_ERR_INVALID_ARG, "out is null");
-    if (!hap_pd) throw Error(GPHMM_ERR_INVALID_ARG, "hap_pd_bases is null");
-    Device &dev = *h->devices[0];
-    CK(cudaSetDevice(dev.ordinal));
-    cudaStream_t st = dev.streams[0];
-    // reads of 128+ bases: 4 rows per lane in strips of 128 rows keeps 18 warps per SM resident (113 registers) where the
-    // 8-row variant (181 registers) keeps 11; GPHMM_PD_K8=1 selects the latter for comparison
-    static const bool k8 = getenv("GPHMM_PD_K8") != nullptr;
-    static const KernelInfo kf[3] = {pd_kernel_info<float, 2>(), pd_kernel_info<float, 4>(), k8 ? pd_kernel_info<float, 8>() : pd_kernel_info<float, 4>()};
-    static const KernelInfo kd = pd_kernel_info<double, 4>();
-    // fast fp32 kernels for reads of up to 94 / 158 / 254 bases (3 / 5 / 8 rows per lane); GPHMM_PD_SLOW=1 keeps every read on
-    // the first-version kernels (A/B switch)
-    static const KernelInfo kfast[3] = {pd_fast_kernel_info<3>(), pd_fast_kernel_info<5>(), pd_fast_kernel_info<8>()};
-    static const bool no_fast = getenv("GPHMM_PD_SLOW") != nullptr;
-    const auto chunks = split_units(b, h->chunk_cells() / 4, h->chunk_bytes(), false);
-    int64_t launches = 0, total_pairs = 0, total_cells = 0, total_redo = 0, h2d = 0, d2h = 0;
-    double device_ms = 0;
-    std::vector<uint32_t> read_off;
-    std::vector<uint8_t> hap_bytes, hap_flags;
+// Host-side plan of one PD-HMM chunk (everything that needs no device): built ahead of the GPU by helper threads.
+struct PdChunkPlan {
+    std::pair<int64_t, int64_t> ch;
+    int64_t r_lo = 0, r_hi = 0, base_lo = 0, cells = 0;
+    size_t span = 0, stride = 0;
+    uint32_t n_pairs = 0, max_h = 1;
+    int n_codes = 1;
+    bool fast_ok = false;
+    uint8_t code_byte[PD_MAX_CODES], code_mask[PD_MAX_CODES];
+    uint32_t first[7];
+    std::vector<uint32_t> read_off, unit_out_base;
+    std::vector<uint8_t> hap_bytes, hap_flags, code_stream, flag_stream, slow_scratch;
     std::vector<PdTask> tasks[6], all;   // 0..2: first-version kernels by read length, 3..5: fast kernels
-    std::vector<uint32_t> unit_out_base;
-    std::vector<uint8_t> code_stream, flag_stream, slow_scratch;
     std::vector<PdHap> haps;
     std::vector<uint2> segs;
-    for (const auto &ch : chunks) {
-        int64_t r_lo = INT64_MAX, r_hi = 0;
+
+    void build(const gphmm_batch *b, const uint8_t *hap_pd, bool allow_fast) {
+        r_lo = INT64_MAX; r_hi = 0;
         for (int64_t u = ch.first; u < ch.second; ++u) {
             const gphmm_unit &un = b->units[u];
             if (un.read_end > un.read_begin) { r_lo = std::min(r_lo, un.read_begin); r_hi = std::max(r_hi, un.read_end); }
         }
         if (r_hi <= r_lo) r_lo = r_hi = 0;
-        const int64_t base_lo = b->n_reads ? b->read_off[r_lo] : 0, base_hi = b->n_reads ? b->read_off[r_hi] : 0;
-        const size_t span = (size_t)(base_hi - base_lo), stride = align_up(span, 16);
+        base_lo = b->n_reads ? b->read_off[r_lo] : 0;
+        const int64_t base_hi = b->n_reads ? b->read_off[r_hi] : 0;
+        span = (size_t)(base_hi - base_lo); stride = align_up(span, 16);
         read_off.resize((size_t)(r_hi - r_lo) + 1);
         for (int64_t r = 0; r <= r_hi - r_lo; ++r) read_off[r] = (uint32_t)(b->read_off[r_lo + r] - base_lo);
         hap_bytes.clear(); hap_flags.clear(); unit_out_base.clear();
         for (auto &v : tasks) v.clear();
         code_stream.clear(); flag_stream.clear(); haps.clear(); segs.clear();
         // column codes of the chunk: 0 = outside a haplotype, then one code per (haplotype byte, SNP mask) that occurs
-        uint8_t code_byte[PD_MAX_CODES] = {0}, code_mask[PD_MAX_CODES] = {0};
-        int n_codes = 1;
-        bool fast_ok = !no_fast && !h->cfg.force_fp64;
+        memset(code_byte, 0, sizeof code_byte); memset(code_mask, 0, sizeof code_mask);
+        n_codes = 1;
+        fast_ok = allow_fast;
         std::map<uint32_t, uint8_t> code_of;
-        uint32_t n_pairs = 0, max_h = 1;
-        int64_t cells = 0;
+        n_pairs = 0; max_h = 1; cells = 0;
         for (int64_t u = ch.first; u < ch.second; ++u) {
             const gphmm_unit &un = b->units[u];
             const uint32_t nr = (uint32_t)(un.read_end - un.read_begin), nh = (uint32_t)(un.hap_end - un.hap_begin);
@@ -185,7 +172,7 @@ int run_pd_batch(gphmm *h, const gphmm_batch *b, const uint8_t *hap_pd, double *
             }
             n_pairs += nr * nh;
         }
-        if (n_pairs == 0) continue;
+        if (n_pairs == 0) return;
         if (!fast_ok)  // every read on the first-version kernels (initial value 2^(125 - ceil log2 H) again)
             for (int k = 3; k < 6; ++k) {
                 for (PdTask t : tasks[k]) {
@@ -196,8 +183,64 @@ int run_pd_batch(gphmm *h, const gphmm_batch *b, const uint8_t *hap_pd, double *
                 tasks[k].clear();
             }
         all.clear();
-        uint32_t first[7] = {0, 0, 0, 0, 0, 0, 0};
+        memset(first, 0, sizeof first);
         for (int k = 0; k < 6; ++k) { first[k + 1] = first[k] + (uint32_t)tasks[k].size(); all.insert(all.end(), tasks[k].begin(), tasks[k].end()); }
+    }
+};
+
+int run_pd_batch(gphmm *h, const gphmm_batch *b, const uint8_t *hap_pd, double *out) {
+    std::lock_guard<std::mutex> run_lk(h->run_mu);
+    const double t0 = now_ms();
+    validate_batch(b);
+    if (b->n_units == 0) return GPHMM_OK;
+    if (!out) throw Error(GPHMM_ERR_INVALID_ARG, "out is null");
+    if (!hap_pd) throw Error(GPHMM_ERR_INVALID_ARG, "hap_pd_bases is null");
+    Device &dev = *h->devices[0];
+    CK(cudaSetDevice(dev.ordinal));
+    cudaStream_t st = dev.streams[0];
+    // reads of 128+ bases: 4 rows per lane in strips of 128 rows keeps 18 warps per SM resident (113 registers) where the
+    // 8-row variant (181 registers) keeps 11; GPHMM_PD_K8=1 selects the latter for comparison
+    static const bool k8 = getenv("GPHMM_PD_K8") != nullptr;
+    static const KernelInfo kf[3] = {pd_kernel_info<float, 2>(), pd_kernel_info<float, 4>(), k8 ? pd_kernel_info<float, 8>() : pd_kernel_info<float, 4>()};
+    static const KernelInfo kd = pd_kernel_info<double, 4>();
+    // fast fp32 kernels for reads of up to 94 / 158 / 254 bases (3 / 5 / 8 rows per lane); GPHMM_PD_SLOW=1 keeps every read on
+    // the first-version kernels (A/B switch)
+    static const KernelInfo kfast[3] = {pd_fast_kernel_info<3>(), pd_fast_kernel_info<5>(), pd_fast_kernel_info<8>()};
+    static const bool no_fast = getenv("GPHMM_PD_SLOW") != nullptr;
+    const auto chunks = split_units(b, h->chunk_cells() / 4, h->chunk_bytes(), false);
+    int64_t launches = 0, total_pairs = 0, total_cells = 0, total_redo = 0, h2d = 0, d2h = 0;
+    double device_ms = 0;
+    // chunk plans are built by helper threads a few chunks ahead of the GPU (the per-pair task list is the expensive part)
+    const bool allow_fast = !no_fast && !h->cfg.force_fp64;
+    const size_t lookahead = std::max<size_t>(2, std::min<size_t>(4, (size_t)(h->cfg.host_threads > 0 ? h->cfg.host_threads : 4)));
+    std::deque<std::future<std::unique_ptr<PdChunkPlan>>> ahead;
+    size_t next_chunk = 0;
+    auto start_plan = [&]() {
+        const auto ch = chunks[next_chunk++];
+        ahead.push_back(std::async(std::launch::async, [b, hap_pd, allow_fast, ch]() {
+            std::unique_ptr<PdChunkPlan> P(new PdChunkPlan());
+            P->ch = ch;
+            P->build(b, hap_pd, allow_fast);
+            return P;
+        }));
+    };
+    while (next_chunk < chunks.size() && ahead.size() < lookahead) start_plan();
+    while (!ahead.empty()) {
+        std::unique_ptr<PdChunkPlan> Pp = ahead.front().get();
+        ahead.pop_front();
+        if (next_chunk < chunks.size()) start_plan();
+        PdChunkPlan &P = *Pp;
+        const auto &ch = P.ch;
+        if (P.n_pairs == 0) continue;
+        const uint32_t n_pairs = P.n_pairs, max_h = P.max_h;
+        const int64_t base_lo = P.base_lo, cells = P.cells;
+        const size_t span = P.span, stride = P.stride;
+        const int n_codes = P.n_codes;
+        const uint32_t *first = P.first;
+        const uint8_t *code_byte = P.code_byte, *code_mask = P.code_mask;
+        auto &read_off = P.read_off; auto &hap_bytes = P.hap_bytes; auto &hap_flags = P.hap_flags; auto &all = P.all;
+        auto &code_stream = P.code_stream; auto &flag_stream = P.flag_stream; auto &haps = P.haps; auto &segs = P.segs;
+        auto &unit_out_base = P.unit_out_base;
         // device image
         size_t o = 0;
         const size_t off_ro = o; o = align_up(o + read_off.size() * 4, 16);
@@ -264,8 +307,8 @@ int run_pd_batch(gphmm *h, const gphmm_batch *b, const uint8_t *hap_pd, double *
                 fa.first = first[k]; fa.n_tasks = n; fa.counter = counters + 10 + (k - 3);
                 fa.sums = (float *)(work + off_s32);
                 fa.m2m = pa.m2m; fa.err = pa.err; fa.tristate_off = pa.tristate_off; fa.n_codes = n_codes;
-                memcpy(fa.code_byte, code_byte, sizeof code_byte);
-                memcpy(fa.code_mask, code_mask, sizeof code_mask);
+                memcpy(fa.code_byte, code_byte, sizeof fa.code_byte);
+                memcpy(fa.code_mask, code_mask, sizeof fa.code_mask);
                 const int rows = k == 3 ? 3 : (k == 4 ? 5 : 8);
                 const size_t smem = (size_t)n_codes * ((rows + 3) / 4) * 512;
                 int occ = 0;
