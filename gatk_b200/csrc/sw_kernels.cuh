@@ -192,8 +192,11 @@ __global__ void __launch_bounds__(32) phmm_sw_kernel(const SwArgs g)
         __threadfence_block();
         __syncwarp();
 
-        // ---- calculateCigar (:262-375), lane 0 ----
-        if (lane == 0) {
+        // ---- calculateCigar (:262-375) ----
+        // Every lane carries the same traceback state; lane 0 writes.  The walk is a chain of dependent loads (one
+        // backtrack entry tells where the next one is), so the warp reads 32 entries along the diagonal at once and
+        // consumes the leading run of zeros (diagonal moves) in one go: an alignment is mostly long match runs.
+        {
             auto BT = [&](int i, int j) -> int {
                 const int strip = (i - 1) / SW_ROWS, ln = ((i - 1) % SW_ROWS) / K, k = (i - 1) % K;
                 return (int)bt[(((size_t)strip * n_steps + (j + ln - 1)) * 32 + ln) * K + k];
@@ -203,40 +206,72 @@ __global__ void __launch_bounds__(32) phmm_sw_kernel(const SwArgs g)
                 p1 = n_ref; p2 = n_alt;
             } else {
                 p2 = n_alt;
-                for (int i = 1; i <= n_ref; ++i) {
+                // last column: the LAST row holding the maximum (`cur >= maxscore`, :283-289)
+                int best = INT32_MIN, bi = 0;
+                for (int i = 1 + lane; i <= n_ref; i += 32) {
                     const int cur = lastcol[i];
-                    if (cur >= maxscore) { p1 = i; maxscore = cur; }
+                    if (cur >= best) { best = cur; bi = i; }
                 }
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) {
+                    const int ob = __shfl_xor_sync(FULL, best, off), oi = __shfl_xor_sync(FULL, bi, off);
+                    if (ob > best || (ob == best && oi > bi)) { best = ob; bi = oi; }
+                }
+                p1 = bi; maxscore = best;
                 if (g.strategy != SW_LEADING_INDEL) {
-                    for (int j = 1; j <= n_alt; ++j) {
-                        const int cur = bottom[j];
-                        if (cur > maxscore || (cur == maxscore && abs(n_ref - j) < abs(p1 - p2))) {
-                            p1 = n_ref; p2 = j; maxscore = cur; segment_length = n_alt - j;
-                        }
+                    // bottom row (:291-300): a column replaces the incumbent when it scores higher, or equally with a
+                    // smaller |n_ref - j| -- i.e. the result is the FIRST candidate (incumbent, then j = 1, 2, ...) that
+                    // nothing after it beats strictly: per lane the first best of its columns, then the same rule across lanes
+                    int bs = INT32_MIN, bd = INT32_MAX, bj = 0;
+                    for (int j = 1 + lane; j <= n_alt; j += 32) {
+                        const int cur = bottom[j], d = abs(n_ref - j);
+                        if (cur > bs || (cur == bs && d < bd)) { bs = cur; bd = d; bj = j; }
+                    }
+#pragma unroll
+                    for (int off = 16; off > 0; off >>= 1) {
+                        const int os = __shfl_xor_sync(FULL, bs, off), od = __shfl_xor_sync(FULL, bd, off), oj = __shfl_xor_sync(FULL, bj, off);
+                        if (oj != 0 && (bj == 0 || os > bs || (os == bs && (od < bd || (od == bd && oj < bj))))) { bs = os; bd = od; bj = oj; }
+                    }
+                    if (bj != 0 && (bs > maxscore || (bs == maxscore && bd < abs(p1 - p2)))) {
+                        p1 = n_ref; p2 = bj; maxscore = bs; segment_length = n_alt - bj;
                     }
                 }
             }
             uint32_t n = 0;
             bool overflow = false;
             auto push = [&](uint32_t op, int len) {
-                if (n < g.capacity) out[n] = ((uint32_t)len << 4) | op; else overflow = true;
+                if (n < g.capacity) { if (lane == 0) out[n] = ((uint32_t)len << 4) | op; } else overflow = true;
                 ++n;
             };
             if (segment_length > 0 && g.strategy == SW_SOFTCLIP) { push(SW_OP_S, segment_length); segment_length = 0; }
             uint32_t state = SW_OP_M;
             do {
-                const int btr = BT(p1, p2);
-                uint32_t new_state;
-                int step_length = 1;
-                if (btr > 0) { new_state = SW_OP_D; step_length = btr; }
-                else if (btr < 0) { new_state = SW_OP_I; step_length = -btr; }
-                else new_state = SW_OP_M;
-                if (new_state == SW_OP_M) { --p1; --p2; } else if (new_state == SW_OP_I) p2 -= step_length; else p1 -= step_length;
-                if (new_state == state) segment_length += step_length;
-                else {
-                    if (segment_length > 0) push(state, segment_length);
-                    segment_length = step_length;
-                    state = new_state;
+                // entries along the diagonal from (p1, p2); outside the matrix: a non-zero sentinel that ends the run
+                const int q1 = p1 - lane, q2 = p2 - lane;
+                int my = 1;
+                if (q1 > 0 && q2 > 0) my = BT(q1, q2);
+                const unsigned nz = __ballot_sync(FULL, my != 0);
+                const int run = nz ? __ffs(nz) - 1 : 32;
+                if (run > 0) {  // `run` diagonal steps (state MATCH, length 1 each)
+                    if (state == SW_OP_M) segment_length += run;
+                    else {
+                        if (segment_length > 0) push(state, segment_length);
+                        segment_length = run;
+                        state = SW_OP_M;
+                    }
+                    p1 -= run; p2 -= run;
+                }
+                if (run < 32 && p1 > 0 && p2 > 0) {  // the entry that ended the run is a gap
+                    const int btr = __shfl_sync(FULL, my, run);
+                    const uint32_t new_state = btr > 0 ? SW_OP_D : SW_OP_I;
+                    const int step_length = btr > 0 ? btr : -btr;
+                    if (new_state == SW_OP_I) p2 -= step_length; else p1 -= step_length;
+                    if (new_state == state) segment_length += step_length;
+                    else {
+                        if (segment_length > 0) push(state, segment_length);
+                        segment_length = step_length;
+                        state = new_state;
+                    }
                 }
             } while (p1 > 0 && p2 > 0);
             int offset;
@@ -252,13 +287,15 @@ __global__ void __launch_bounds__(32) phmm_sw_kernel(const SwArgs g)
                 if (p1 > 0) push(SW_OP_D, p1); else if (p2 > 0) push(SW_OP_I, p2);
                 offset = 0;
             }
-            if (overflow) {
-                g.n_elems[ti] = -1;
-            } else {
-                for (uint32_t x = 0, y = n - 1; x < y; ++x, --y) { const uint32_t tmp = out[x]; out[x] = out[y]; out[y] = tmp; }  // Lists.reverse (:374)
-                g.n_elems[ti] = (int32_t)n;
+            if (lane == 0) {
+                if (overflow) {
+                    g.n_elems[ti] = -1;
+                } else {
+                    for (uint32_t x = 0, y = n - 1; x < y; ++x, --y) { const uint32_t tmp = out[x]; out[x] = out[y]; out[y] = tmp; }  // Lists.reverse (:374)
+                    g.n_elems[ti] = (int32_t)n;
+                }
+                g.offsets[ti] = offset;
             }
-            g.offsets[ti] = offset;
         }
         __syncwarp();
     }
