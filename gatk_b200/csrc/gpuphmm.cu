@@ -300,7 +300,7 @@ template <int K> KernelInfo fast_kernel_info(int n_codes) {
     KernelInfo ki;
     auto fn = phmm_fast_f32_kernel<K>;
     ki.fn = (const void *)fn;
-    ki.smem = prior_table_bytes<float, K>(n_codes - 1);  // END and NULL share a row (the shared streams carry no END code)
+    ki.smem = prior_table_bytes<float, K>(n_codes);
     raise_dyn_smem((const void *)fn, ki.smem);
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ki.ctas_per_sm, fn, 32, ki.smem));
     if (ki.ctas_per_sm < 1) throw Error(GPHMM_ERR_ALPHABET, "prior table does not fit in shared memory");
@@ -325,7 +325,7 @@ template <int K, bool SYM> KernelInfo flat_kernel_info(int n_codes) {
     KernelInfo ki;
     auto fn = phmm_flat_f32_kernel<K, SYM>;
     ki.fn = (const void *)fn;
-    ki.smem = prior_table_bytes<float, K>(n_codes - 1);
+    ki.smem = prior_table_bytes<float, K>(n_codes);
     raise_dyn_smem((const void *)fn, ki.smem);
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ki.ctas_per_sm, fn, 32, ki.smem));
     if (ki.ctas_per_sm < 1) throw Error(GPHMM_ERR_ALPHABET, "prior table does not fit in shared memory");
@@ -363,7 +363,7 @@ template <int K, bool SYM> KernelInfo flat16_kernel_info(int n_codes) {
     KernelInfo ki;
     auto fn = phmm_flat_f32_kernel<K, SYM, 16>;
     ki.fn = (const void *)fn;
-    ki.smem = prior_table_bytes<float, K>(n_codes - 1);
+    ki.smem = prior_table_bytes<float, K>(n_codes);
     raise_dyn_smem((const void *)fn, ki.smem);
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ki.ctas_per_sm, fn, 32, ki.smem));
     if (ki.ctas_per_sm < 1) throw Error(GPHMM_ERR_ALPHABET, "prior table does not fit in shared memory");

@@ -257,7 +257,7 @@ UnitSched plan_unit_sharing(const gphmm_batch *b, const gphmm_unit &un, uint32_t
         // the full stream of this unit was encoded a moment ago: copy the columns behind the shared prefix
         memcpy(dst, c.streams.data() + c.hap_stream_off[hap_first_local + order[i]] + r[i], H - r[i]);
         for (uint32_t q = 0; q < n_pad[i]; ++q) dst[H - r[i] + q] = (uint8_t)CODE_NULL;  // prior 0: no effect on the sum
-        dst[H - r[i] + n_pad[i]] = (uint8_t)CODE_NULL;  // the END column: prior 0 like NULL; the kernels know its position (Segment::end_pos)
+        dst[H - r[i] + n_pad[i]] = (uint8_t)CODE_END;
         PassInfo pi;
         pi.out_idx = (uint16_t)order[i];
         pi.restore_slot = (int16_t)(snap_of_pass[i] >= 0 ? snaps[snap_of_pass[i]].slot : -1);
@@ -283,7 +283,7 @@ UnitSched plan_unit_sharing(const gphmm_batch *b, const gphmm_unit &un, uint32_t
         std::sort(pts.begin(), pts.end());
         pts.erase(std::unique(pts.begin(), pts.end()), pts.end());
         Segment seg;
-        auto clear_seg = [&]() { seg.n_free = 0; seg.n_chk = 0; seg.snap_pos = INT32_MIN; seg.snap_slot = 0; seg.end_restore = MAX_SNAP_SLOTS; seg.end_out = 0; seg.end_pos = INT32_MIN; };
+        auto clear_seg = [&]() { seg.n_free = 0; seg.n_chk = 0; seg.snap_pos = INT32_MIN; seg.snap_slot = 0; seg.end_restore = MAX_SNAP_SLOTS; seg.end_out = 0; };
         clear_seg();
         size_t ie = 0, is = 0;  // first END / snapshot whose window has not expired yet
         for (size_t k = 0; k + 1 < pts.size(); ++k) {
@@ -302,7 +302,6 @@ UnitSched plan_unit_sharing(const gphmm_batch *b, const gphmm_unit &un, uint32_t
             seg.n_chk = y - x;
             if (snap_on) { seg.snap_pos = (int32_t)snaps[snap_by_pos[is]].pos; seg.snap_slot = (uint8_t)snaps[snap_by_pos[is]].slot; }
             if (end_on) {
-                seg.end_pos = (int32_t)end_pos[ie];
                 seg.end_out = (uint16_t)order[ie];
                 seg.end_restore = (int8_t)(ie + 1 < (size_t)n && snap_of_pass[ie + 1] >= 0 ? snaps[snap_of_pass[ie + 1]].slot : MAX_SNAP_SLOTS);  // MAX_SNAP_SLOTS = pass-start state
             }

@@ -374,7 +374,7 @@ __global__ void __launch_bounds__(32, K > 5 ? 16 : 20) phmm_pd_fast_kernel(const
             const uint2 seg = g.segs[hp.seg_first + sg];
 #pragma unroll 2
             for (uint32_t s = 0; s < seg.x; ++s)
-                fast_step<K, false>(st, cb, cc, cg, cd, tab_lane, src_lane, lane, 0, 0, c0, nullptr, nullptr, 0, 0, 0, 0, 0);
+                fast_step<K, false>(st, cb, cc, cg, cd, tab_lane, src_lane, lane, 0, 0, c0, nullptr, nullptr, 0, 0, 0, 0);
             step += (int)seg.x;
             int p = step - lane;  // 1-based column of this lane
             // the branch values are dead between two slow windows: every lane refreshes them (NORMAL: branch = the value one

@@ -89,9 +89,6 @@ struct Segment {
     uint8_t snap_slot;
     int8_t end_restore;    // the (single) END column met in this segment: snapshot slot the next pass restores, -1 = fresh start
     uint16_t end_out;      // ... and the output column of the pass that ends there
-    int32_t end_pos;       // ... and its stream position, INT32_MIN = none.  The shared streams carry NO END code: a pass ends
-                           // with a NULL column (prior 0 like END) and the kernels recognise it by position, so END and NULL
-                           // share one row of the prior table (shared memory = resident warps)
 };
 struct UnitSched {
     uint32_t pass_first, n_passes;  // into pass_info
@@ -417,7 +414,7 @@ template <int K, bool CHECKED>
 __device__ __forceinline__ void fast_step(FastState<K> &st, const float (&cb)[K], const float (&cc)[K],
                                           const float (&cg)[K], const float (&cd)[K], uint32_t tab_lane, int src_lane, int lane,
                                           int acc_lane, int acc_slot, float c0, float *sums_task, float *slab, int snap_pos,
-                                          int snap_slot, int end_restore, uint32_t end_out, int end_pos)
+                                          int snap_slot, int end_restore, uint32_t end_out)
 {
     constexpr int NV = (K + 3) / 4;
     constexpr unsigned FULL = 0xffffffffu;
@@ -460,7 +457,7 @@ __device__ __forceinline__ void fast_step(FastState<K> &st, const float (&cb)[K]
     st.dgm = mu; st.dgi = iu; st.dgd = du;
     if (CHECKED) {
         if (__builtin_expect(st.p == snap_pos, 0)) snap_save<K>(st, slab, snap_slot);
-        if (__builtin_expect(st.p == end_pos, 0)) {
+        if (__builtin_expect(st.y == CODE_END, 0)) {
             if (lane == acc_lane) {
                 float v = 0.f;
 #pragma unroll
@@ -487,8 +484,7 @@ __global__ void __launch_bounds__(32) phmm_fast_f32_kernel(const KernelArgs g)
     // opaque to the optimiser: keeps lane / rotation source in registers instead of re-deriving them every step
     asm volatile("mov.u32 %0, %%laneid;" : "=r"(lane));
     asm volatile("{ .reg .u32 t; add.u32 t, %1, 31; and.b32 %0, t, 31; }" : "=r"(src_lane) : "r"(lane));
-    // the shared streams have no code 0 (END travels as NULL = 1): the table starts at the row of code 1
-    const uint32_t tab_lane = (uint32_t)__cvta_generic_to_shared(smem_raw) + lane * 16 - NV * 32 * 16;
+    const uint32_t tab_lane = (uint32_t)__cvta_generic_to_shared(smem_raw) + lane * 16;
     float *const sums = reinterpret_cast<float *>(g.sums);
     const uint32_t n_tasks = g.n_tasks;
     const int n_codes = g.n_codes;
@@ -553,7 +549,7 @@ __global__ void __launch_bounds__(32) phmm_fast_f32_kernel(const KernelArgs g)
             if (lane == 31 && k == K - 1) DD = 1.0;  // carrier of the virtual row 0: keeps D~ = c0
             cb[k] = (float)B; cc[k] = (float)C; cg[k] = (float)G; cd[k] = (float)DD;
             const float pmf = (float)pm, pxf = (float)px;
-            for (int y = 1; y < n_codes; ++y) {
+            for (int y = 0; y < n_codes; ++y) {
                 float v = 0.f;
                 if (real) {
                     if (y >= (int)CODE_FIRST_BASE) {
@@ -563,7 +559,7 @@ __global__ void __launch_bounds__(32) phmm_fast_f32_kernel(const KernelArgs g)
                 } else if (i == R + 1) {
                     v = 1.f;
                 }
-                tab_s[(((y - 1) * NV + k / 4) * 32 + lane) * 4 + (k % 4)] = v;
+                tab_s[((y * NV + k / 4) * 32 + lane) * 4 + (k % 4)] = v;
             }
         }
         __syncwarp();
@@ -588,13 +584,13 @@ __global__ void __launch_bounds__(32) phmm_fast_f32_kernel(const KernelArgs g)
             const Segment seg = g.segments[us.seg_first + sg];
 #pragma unroll 2
             for (uint32_t s = 0; s < seg.n_free; ++s)
-                fast_step<K, false>(st, cb, cc, cg, cd, tab_lane, src_lane, lane, acc_lane, acc_slot, c0, sums_task, slab, 0, 0, 0, 0, 0);
+                fast_step<K, false>(st, cb, cc, cg, cd, tab_lane, src_lane, lane, acc_lane, acc_slot, c0, sums_task, slab, 0, 0, 0, 0);
             step += (int)seg.n_free;
             st.p = step - lane;
 #pragma unroll 1
             for (uint32_t s = 0; s < seg.n_chk; ++s)
                 fast_step<K, true>(st, cb, cc, cg, cd, tab_lane, src_lane, lane, acc_lane, acc_slot, c0, sums_task, slab, seg.snap_pos,
-                                   seg.snap_slot, seg.end_restore, seg.end_out, seg.end_pos);
+                                   seg.snap_slot, seg.end_restore, seg.end_out);
             step += (int)seg.n_chk;
         }
         }  // sub
@@ -667,7 +663,7 @@ __global__ void __launch_bounds__(128) phmm_classify_kernel(const ClassifyArgs a
 template <int K, int SLOT, bool CHECKED, bool SYM>
 __device__ __forceinline__ void flat_step(FastState<K> &st, const FlatCoef &f, const float (&A)[K], const float (&C)[K], float B0, float G0,
                                           float E0, uint32_t tab_lane, int src_lane, int lane, int acc_lane, float *sums_task,
-                                          float *slab, int snap_pos, int snap_slot, int end_restore, uint32_t end_out, int end_pos)
+                                          float *slab, int snap_pos, int snap_slot, int end_restore, uint32_t end_out)
 {
     constexpr int NV = (K + 3) / 4;
     constexpr unsigned FULL = 0xffffffffu;
@@ -718,7 +714,7 @@ __device__ __forceinline__ void flat_step(FastState<K> &st, const FlatCoef &f, c
     st.acc = __fmaf_rn(f.tmi, st.I[SLOT], st.acc);
     if (CHECKED) {
         if (__builtin_expect(st.p == snap_pos, 0)) snap_save<K>(st, slab, snap_slot);
-        if (__builtin_expect(st.p == end_pos, 0)) {
+        if (__builtin_expect(st.y == CODE_END, 0)) {
             if (lane == acc_lane) sums_task[end_out] = acc_before;
             snap_restore<K>(st, slab, end_restore);  // ZERO_SLOT = fresh start
         }
@@ -737,13 +733,13 @@ __device__ __forceinline__ void flat_sweep(FastState<K> &st, const FlatCoef &f, 
         const Segment seg = segs[sg];
 #pragma unroll 2
         for (uint32_t s = 0; s < seg.n_free; ++s)
-            flat_step<K, SLOT, false, SYM>(st, f, A, C, B0, G0, E0, tab_lane, src_lane, lane, acc_lane, sums_task, slab, 0, 0, 0, 0, 0);
+            flat_step<K, SLOT, false, SYM>(st, f, A, C, B0, G0, E0, tab_lane, src_lane, lane, acc_lane, sums_task, slab, 0, 0, 0, 0);
         step += (int)seg.n_free;
         st.p = step - lane;
 #pragma unroll 1
         for (uint32_t s = 0; s < seg.n_chk; ++s)
             flat_step<K, SLOT, true, SYM>(st, f, A, C, B0, G0, E0, tab_lane, src_lane, lane, acc_lane, sums_task, slab, seg.snap_pos,
-                                          seg.snap_slot, seg.end_restore, seg.end_out, seg.end_pos);
+                                          seg.snap_slot, seg.end_restore, seg.end_out);
         step += (int)seg.n_chk;
     }
 }
@@ -785,8 +781,7 @@ __global__ void __launch_bounds__(32, flat_min_ctas(K, SYM, LANES)) phmm_flat_f3
         asm volatile("mov.u32 %0, %1;" : "=r"(pl) : "r"(lane));
         asm volatile("{ .reg .u32 t; add.u32 t, %1, 31; and.b32 %0, t, 31; }" : "=r"(src_lane) : "r"(lane));
     }
-    // the shared streams have no code 0 (END travels as NULL = 1): the table starts at the row of code 1
-    const uint32_t tab_lane = (uint32_t)__cvta_generic_to_shared(smem_raw) + lane * 16 - NV * 32 * 16;
+    const uint32_t tab_lane = (uint32_t)__cvta_generic_to_shared(smem_raw) + lane * 16;
     float *const sums = reinterpret_cast<float *>(g.sums);
     const uint32_t n_tasks = g.n_tasks;
     const int n_codes = g.n_codes;
@@ -847,13 +842,13 @@ __global__ void __launch_bounds__(32, flat_min_ctas(K, SYM, LANES)) phmm_flat_f3
                 pmf = (float)pm;
                 pxf = (float)px;
             }
-            for (int y = 1; y < n_codes; ++y) {
+            for (int y = 0; y < n_codes; ++y) {
                 float v = 0.f;
                 if (real && y >= (int)CODE_FIRST_BASE) {
                     const uint32_t hb = g.code_byte[y];
                     v = (x == hb || x == (uint32_t)'N' || hb == (uint32_t)'N') ? pmf : pxf;  // LoglessPairHMM.java:89
                 }
-                tab_s[(((y - 1) * NV + k / 4) * 32 + lane) * 4 + (k % 4)] = v;
+                tab_s[((y * NV + k / 4) * 32 + lane) * 4 + (k % 4)] = v;
             }
         }
         if (f.qi > 127u || f.qd > 127u || f.qc > 127u) atomicExch(g.err, 1);
