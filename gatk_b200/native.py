@@ -82,7 +82,8 @@ EXPORTS = ["gphmm_abi_version", "gphmm_device_count", "gphmm_strerror", "gphmm_c
 
 
 def lib_path():
-    return os.path.join(_HERE, "lib", "libgpuphmm.so")
+    # GPHMM_LIB: another build of the same library (A/B measurements of two versions on one box)
+    return os.environ.get("GPHMM_LIB") or os.path.join(_HERE, "lib", "libgpuphmm.so")
 
 
 def load_library():
