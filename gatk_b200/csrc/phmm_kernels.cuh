@@ -42,6 +42,11 @@
 
 namespace phmm_dev {
 
+// Unroll factors of the flat kernels' step loops (branch-free / checked).  Measured on B200 (A/B builds on one box): with 16
+// rows per lane 2 / 1 is best (4 / 1 loses 22 %, 2 / 2 loses 12 %: the 16 sweep instances of a kernel outgrow the instruction
+// cache), with 10 rows per lane (half-warp form, 150-base reads) 4 / 2 gains 2-3 %; the full-warp kernels spill at 4.
+__host__ __device__ constexpr int flat_unroll(int K) { return K == 10 ? 4 : 2; }
+__host__ __device__ constexpr int flat_chk_unroll(int K) { return K == 10 ? 2 : 1; }
 constexpr uint32_t CODE_END = 0;   // column after the last base of a haplotype
 constexpr uint32_t CODE_NULL = 1;  // outside the stream (pipeline fill / drain)
 constexpr uint32_t CODE_FIRST_BASE = 2;  // A C G T = 2..5, further byte values (N included) 6..
@@ -731,12 +736,12 @@ __device__ __forceinline__ void flat_sweep(FastState<K> &st, const FlatCoef &f, 
     int step = 1;
     for (uint32_t sg = 0; sg < n_segs; ++sg) {
         const Segment seg = segs[sg];
-#pragma unroll 2
+#pragma unroll (flat_unroll(K))
         for (uint32_t s = 0; s < seg.n_free; ++s)
             flat_step<K, SLOT, false, SYM>(st, f, A, C, B0, G0, E0, tab_lane, src_lane, lane, acc_lane, sums_task, slab, 0, 0, 0, 0);
         step += (int)seg.n_free;
         st.p = step - lane;
-#pragma unroll 1
+#pragma unroll (flat_chk_unroll(K))
         for (uint32_t s = 0; s < seg.n_chk; ++s)
             flat_step<K, SLOT, true, SYM>(st, f, A, C, B0, G0, E0, tab_lane, src_lane, lane, acc_lane, sums_task, slab, seg.snap_pos,
                                           seg.snap_slot, seg.end_restore, seg.end_out);
