@@ -47,7 +47,9 @@ public final class CudaLoglessPairHMM extends LoglessPairHMM {
     private long nanosInSetup = 0L;
 
     public CudaLoglessPairHMM(final PairHMMNativeArguments args) throws UserException.HardwareFeatureException {
-        gpu.setDevices(parseDeviceList(System.getenv(DEVICES_ENV)));
+        // --cuda-pair-hmm-devices (PairHMMNativeArgumentCollection hands over a CudaPairHMMArguments), else the environment
+        final int[] fromCommandLine = args instanceof CudaPairHMMArguments ? ((CudaPairHMMArguments) args).devices : null;
+        gpu.setDevices(fromCommandLine != null ? fromCommandLine : parseDeviceList(System.getenv(DEVICES_ENV)));
         if (!gpu.load(null)) {
             throw new UserException.HardwareFeatureException(
                     "Machine does not support the CUDA PairHMM: libgpuphmm could not be loaded or no compute-capability 10.x GPU is visible.");
@@ -56,15 +58,7 @@ public final class CudaLoglessPairHMM extends LoglessPairHMM {
     }
 
     static int[] parseDeviceList(final String spec) {
-        if (spec == null || spec.trim().isEmpty()) {
-            return null;
-        }
-        final String[] fields = spec.split(",");
-        final int[] ordinals = new int[fields.length];
-        for (int k = 0; k < fields.length; k++) {
-            ordinals[k] = Integer.parseInt(fields[k].trim());
-        }
-        return ordinals;
+        return CudaPairHMMArguments.parseDeviceList(spec);
     }
 
     /**

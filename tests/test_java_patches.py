@@ -22,8 +22,8 @@ def _targets(patch):
     return re.findall(r"^\+\+\+ b/(\S+)", open(patch).read(), flags=re.M)
 
 
-def test_there_are_seven_patches_and_no_file_is_patched_twice():
-    assert len(PATCHES) == 7
+def test_there_are_eight_patches_and_no_file_is_patched_twice():
+    assert len(PATCHES) == 8
     seen = {}
     for p in PATCHES:
         for t in _targets(p):
@@ -95,6 +95,9 @@ def test_series_applies_together_and_brackets_stay_balanced(tmp_path):
     sw = open(os.path.join(ROOT, "java/org/broadinstitute/hellbender/utils/smithwaterman/CudaSmithWatermanAligner.java")).read()
     assert "List<SmithWatermanAlignment> alignBatch(" in sw
     assert os.path.isfile(os.path.join(ROOT, "java/org/broadinstitute/hellbender/utils/pairhmm/CudaLoglessPairPDHMM.java"))
+    args = open(os.path.join(ROOT, "java/org/broadinstitute/hellbender/utils/pairhmm/CudaPairHMMArguments.java")).read()
+    assert "extends PairHMMNativeArguments" in args and "public int[] devices" in args and "static int[] parseDeviceList(" in args
+    assert "args instanceof CudaPairHMMArguments" in cuda
 
 
 def test_our_java_sources_have_balanced_brackets():
