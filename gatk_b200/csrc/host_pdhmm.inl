@@ -31,13 +31,58 @@ template <typename T, int K> KernelInfo pd_kernel_info() {
     return ki;
 }
 
-template <int K> KernelInfo pd_fast_kernel_info() {
+template <int K, bool SIMPLE> KernelInfo pd_fast_kernel_info() {
     KernelInfo ki;
-    auto fn = phmm_pd_fast_kernel<K>;
+    auto fn = phmm_pd_fast_kernel<K, SIMPLE>;
     ki.fn = (const void *)fn;
-    ki.smem = (size_t)PD_MAX_CODES * ((K + 3) / 4) * 512;  // sized per launch from the chunk's alphabet; this is the ceiling
+    ki.smem = pd_fast_smem<K>(PD_MAX_CODES, SIMPLE);  // sized per launch from the chunk's alphabet; this is the ceiling
     raise_dyn_smem((const void *)fn, ki.smem);
     return ki;
+}
+
+// Deletion events of a haplotype for the SIMPLE kernels (pdhmm_kernels.cuh): (a, b) = first and last column of a deletion.
+// False when the haplotype does not have the simple shape -- a flag met in the AFTER_DEL state, events closer than three
+// columns, a deletion still open (or just closed) at the last column, which LoglessPDPairHMM.java:59 carries into the next row.
+bool pd_simple_events(const uint8_t *pd, uint32_t H, std::vector<uint2> &events) {
+    enum { DEL_START = 2, DEL_END = 4 };
+    const size_t n0 = events.size();
+    uint32_t state = PD_NORMAL, a = 0;
+    bool ok = true;
+    for (uint32_t j = 1; j <= H && ok; ++j) {
+        const bool ds = pd[j - 1] & DEL_START, de = pd[j - 1] & DEL_END;
+        if (state == PD_AFTER_DEL) {
+            if (ds || de) ok = false;
+            state = PD_NORMAL;
+        } else if (state == PD_NORMAL) {
+            if (ds || de) {
+                a = j;
+                if (events.size() > n0 && a < events.back().y + 3) ok = false;
+                if (de) { events.push_back(make_uint2(a, j)); state = PD_AFTER_DEL; } else state = PD_INSIDE_DEL;
+            }
+        } else if (de) {  // INSIDE_DEL: a further DEL_START changes nothing
+            events.push_back(make_uint2(a, j));
+            state = PD_AFTER_DEL;
+        }
+    }
+    if (state != PD_NORMAL) ok = false;
+    if (!ok) events.resize(n0);
+    return ok;
+}
+
+// Schedule of a SIMPLE haplotype: lane l is on column j at step j + l, and only the columns a, b, b + 1 of an event need the
+// window code.
+void plan_pd_steps_simple(const uint2 *events, size_t n_events, uint32_t H, std::vector<uint2> &segs, std::vector<uint8_t> &slow) {
+    const uint32_t T = H + 33;
+    slow.assign(T + 2, 0);
+    for (size_t e = 0; e < n_events; ++e)
+        for (uint32_t j : {events[e].x, events[e].y, events[e].y + 1})
+            for (uint32_t st = j; st <= std::min(T, j + 31); ++st) slow[st] = 1;
+    for (uint32_t st = 1; st <= T;) {
+        uint2 seg = make_uint2(0, 0);
+        while (st <= T && !slow[st]) { ++seg.x; ++st; }
+        while (st <= T && slow[st]) { ++seg.y; ++st; }
+        segs.push_back(seg);
+    }
 }
 
 // The steps of a haplotype's sweep (H + 33 of them: every lane gets past column H + 1) in which some lane of the warp is
@@ -69,17 +114,18 @@ struct PdChunkPlan {
     int64_t r_lo = 0, r_hi = 0, base_lo = 0, cells = 0;
     size_t span = 0, stride = 0;
     uint32_t n_pairs = 0, max_h = 1;
-    int n_codes = 1;
+    int n_plain = 0, max_snp = 0;
     bool fast_ok = false;
-    uint8_t code_byte[PD_MAX_CODES], code_mask[PD_MAX_CODES];
-    uint32_t first[7];
+    uint8_t code_byte[PD_MAX_CODES];
+    uint32_t first[10], group_first[7];
+    std::vector<PdGroup> groups;          // fast kernels: one task per read = its consecutive pairs of a bucket
     std::vector<uint32_t> read_off, unit_out_base;
     std::vector<uint8_t> hap_bytes, hap_flags, code_stream, flag_stream, slow_scratch;
-    std::vector<PdTask> tasks[6], all;   // 0..2: first-version kernels by read length, 3..5: fast kernels
+    std::vector<PdTask> tasks[9], all;   // 0..2: first-version kernels by read length, 3..5: fast kernels, 6..8: fast kernels, SIMPLE form
     std::vector<PdHap> haps;
-    std::vector<uint2> segs;
+    std::vector<uint2> segs, events;
 
-    void build(const gphmm_batch *b, const uint8_t *hap_pd, bool allow_fast) {
+    void build(const gphmm_batch *b, const uint8_t *hap_pd, bool allow_fast, bool allow_simple) {
         r_lo = INT64_MAX; r_hi = 0;
         for (int64_t u = ch.first; u < ch.second; ++u) {
             const gphmm_unit &un = b->units[u];
@@ -93,18 +139,21 @@ struct PdChunkPlan {
         for (int64_t r = 0; r <= r_hi - r_lo; ++r) read_off[r] = (uint32_t)(b->read_off[r_lo + r] - base_lo);
         hap_bytes.clear(); hap_flags.clear(); unit_out_base.clear();
         for (auto &v : tasks) v.clear();
-        code_stream.clear(); flag_stream.clear(); haps.clear(); segs.clear();
-        // column codes of the chunk: 0 = outside a haplotype, then one code per (haplotype byte, SNP mask) that occurs
-        memset(code_byte, 0, sizeof code_byte); memset(code_mask, 0, sizeof code_mask);
-        n_codes = 1;
+        code_stream.clear(); flag_stream.clear(); haps.clear(); segs.clear(); events.clear();
+        // prior-table rows of the chunk: 0 = outside a haplotype, 1 .. n_plain = one per haplotype byte on a column without a SNP
+        // flag, two source rows, then the SNP rows of the haplotype being swept (rebuilt per haplotype: at most PD_MAX_SNP_CODES
+        // distinct (byte, mask) pairs).  SNP columns enter the stream as 0xc0 + s and are renumbered once n_plain is known.
+        memset(code_byte, 0, sizeof code_byte);
+        n_plain = 0; max_snp = 0;
         fast_ok = allow_fast;
-        std::map<uint32_t, uint8_t> code_of;
+        uint8_t plain_of[256];
+        memset(plain_of, 0, sizeof plain_of);
         n_pairs = 0; max_h = 1; cells = 0;
         for (int64_t u = ch.first; u < ch.second; ++u) {
             const gphmm_unit &un = b->units[u];
             const uint32_t nr = (uint32_t)(un.read_end - un.read_begin), nh = (uint32_t)(un.hap_end - un.hap_begin);
             unit_out_base.push_back(n_pairs);
-            struct HapInfo { uint32_t off, H, first_event, carry, index; bool sparse; };
+            struct HapInfo { uint32_t off, H, first_event, carry, index; bool sparse, simple; };
             std::vector<HapInfo> hi(nh);
             for (uint32_t k = 0; k < nh; ++k) {
                 const int64_t ho = b->hap_off[un.hap_begin + k];
@@ -114,38 +163,51 @@ struct PdChunkPlan {
                 hap_flags.resize(hap_bytes.size());
                 encode_pd_columns(hap_pd + ho, H, hap_flags.data() + hi[k].off, hi[k].first_event, hi[k].carry);
                 max_h = std::max(max_h, H);
-                // fast kernels: padded code and flag streams, the step schedule, the codes that occur
+                // fast kernels: padded code and flag streams, the step schedule, the SNP codes of the haplotype
                 hi[k].index = (uint32_t)haps.size();
                 PdHap ph;
                 memset(&ph, 0, sizeof ph);
                 code_stream.insert(code_stream.end(), STREAM_PAD, 0);
                 flag_stream.insert(flag_stream.end(), STREAM_PAD, 0);
                 ph.code_off = (uint32_t)code_stream.size();
-                for (uint32_t j = 0; j < H && fast_ok; ++j) {
-                    const uint8_t f = hap_flags[hi[k].off + j];
-                    const uint32_t key = (uint32_t)b->hap_bases[ho + j] | ((f & PD_SNP_BIT) ? (uint32_t)(0x80u | (f & PD_MASK_BITS)) << 8 : 0u);
-                    auto it = code_of.find(key);
-                    if (it == code_of.end()) {
-                        if (n_codes >= PD_MAX_CODES) { fast_ok = false; break; }  // exotic alphabet: the first-version kernels take the chunk
-                        code_byte[n_codes] = (uint8_t)key; code_mask[n_codes] = (uint8_t)(key >> 8);
-                        it = code_of.emplace(key, (uint8_t)n_codes++).first;
+                bool hap_ok = fast_ok;
+                for (uint32_t j = 0; j < H && hap_ok; ++j) {
+                    const uint8_t f = hap_flags[hi[k].off + j], hb = b->hap_bases[ho + j];
+                    if (f & PD_SNP_BIT) {
+                        const uint16_t key = (uint16_t)(hb | (uint16_t)(f & PD_MASK_BITS) << 8);
+                        uint32_t sn = 0;
+                        while (sn < ph.n_snp && ph.snp[sn] != key) ++sn;
+                        if (sn == ph.n_snp) {
+                            if (ph.n_snp == PD_MAX_SNP_CODES) { hap_ok = false; break; }  // the first-version kernels take this haplotype
+                            ph.snp[ph.n_snp++] = key;
+                        }
+                        code_stream.push_back((uint8_t)(0xc0 + sn));
+                    } else {
+                        if (!plain_of[hb]) {
+                            if (n_plain + 3 + PD_MAX_SNP_CODES >= PD_MAX_CODES) { fast_ok = hap_ok = false; break; }  // exotic alphabet
+                            plain_of[hb] = (uint8_t)++n_plain;
+                            code_byte[n_plain] = hb;
+                        }
+                        code_stream.push_back(plain_of[hb]);
                     }
-                    const uint8_t code = it->second;
-                    code_stream.push_back(code);
-                    if (code < 32) ph.codes_lo |= 1u << code; else ph.codes_hi |= 1u << (code - 32);
                 }
+                max_snp = std::max(max_snp, (int)ph.n_snp);
                 code_stream.resize(ph.code_off + H, 0);
                 flag_stream.insert(flag_stream.end(), hap_flags.begin() + hi[k].off, hap_flags.begin() + hi[k].off + H);
                 code_stream.insert(code_stream.end(), 2 * STREAM_PAD, 0);
                 flag_stream.insert(flag_stream.end(), 2 * STREAM_PAD, 0);
                 ph.seg_first = (uint32_t)segs.size();
-                plan_pd_steps(hap_flags.data() + hi[k].off, H, hi[k].first_event, hi[k].carry, segs, slow_scratch);
+                ph.ev_first = (uint32_t)events.size();
+                hi[k].simple = allow_simple && pd_simple_events(hap_pd + ho, H, events);
+                ph.n_events = (uint32_t)events.size() - ph.ev_first;
+                if (hi[k].simple) plan_pd_steps_simple(events.data() + ph.ev_first, ph.n_events, H, segs, slow_scratch);
+                else plan_pd_steps(hap_flags.data() + hi[k].off, H, hi[k].first_event, hi[k].carry, segs, slow_scratch);
                 ph.n_segs = (uint32_t)segs.size() - ph.seg_first;
                 // densely flagged haplotypes (most steps inside a deletion window) stay with the first-version kernels,
                 // whose per-step fast path works column by column
                 uint32_t n_slow = 0;
                 for (uint32_t q = ph.seg_first; q < (uint32_t)segs.size(); ++q) n_slow += segs[q].y;
-                hi[k].sparse = 2 * n_slow <= H + 33;
+                hi[k].sparse = hap_ok && 2 * n_slow <= H + 33;
                 haps.push_back(ph);
             }
             for (uint32_t r = 0; r < nr; ++r) {
@@ -162,7 +224,7 @@ struct PdChunkPlan {
                         // scaled states (I / tMI, D / tMD) need the head-room of the plain fp32 kernels
                         PdTask tf = t;
                         tf.c0_exp = C0_BASE_EXP_F32 - ceil_log2(hi[k].H);
-                        tasks[fbucket].push_back(tf);
+                        tasks[fbucket + (hi[k].simple ? 3 : 0)].push_back(tf);
                         cells += (int64_t)R * hi[k].H;
                         continue;
                     }
@@ -174,7 +236,7 @@ struct PdChunkPlan {
         }
         if (n_pairs == 0) return;
         if (!fast_ok)  // every read on the first-version kernels (initial value 2^(125 - ceil log2 H) again)
-            for (int k = 3; k < 6; ++k) {
+            for (int k = 3; k < 9; ++k) {
                 for (PdTask t : tasks[k]) {
                     const uint32_t R = read_off[t.read + 1] - read_off[t.read];
                     t.c0_exp = 125 - ceil_log2(t.H);
@@ -184,7 +246,23 @@ struct PdChunkPlan {
             }
         all.clear();
         memset(first, 0, sizeof first);
-        for (int k = 0; k < 6; ++k) { first[k + 1] = first[k] + (uint32_t)tasks[k].size(); all.insert(all.end(), tasks[k].begin(), tasks[k].end()); }
+        for (int k = 0; k < 9; ++k) { first[k + 1] = first[k] + (uint32_t)tasks[k].size(); all.insert(all.end(), tasks[k].begin(), tasks[k].end()); }
+        groups.clear();
+        memset(group_first, 0, sizeof group_first);
+        for (int k = 3; k < 9; ++k) {
+            const std::vector<PdTask> &tk = tasks[k];
+            for (size_t i = 0; i < tk.size();) {
+                size_t j = i + 1;
+                while (j < tk.size() && tk[j].read == tk[i].read) ++j;
+                PdGroup gr;
+                gr.read = tk[i].read; gr.task_first = (uint32_t)i; gr.n = (uint32_t)(j - i); gr.pad = 0;
+                groups.push_back(gr);
+                i = j;
+            }
+            group_first[k - 3 + 1] = (uint32_t)groups.size();
+        }
+        for (uint8_t &c : code_stream)
+            if (c >= 0xc0) c = (uint8_t)(n_plain + 3 + (c - 0xc0));
     }
 };
 
@@ -205,8 +283,11 @@ int run_pd_batch(gphmm *h, const gphmm_batch *b, const uint8_t *hap_pd, double *
     static const KernelInfo kd = pd_kernel_info<double, 4>();
     // fast fp32 kernels for reads of up to 94 / 158 / 254 bases (3 / 5 / 8 rows per lane); GPHMM_PD_SLOW=1 keeps every read on
     // the first-version kernels (A/B switch)
-    static const KernelInfo kfast[3] = {pd_fast_kernel_info<3>(), pd_fast_kernel_info<5>(), pd_fast_kernel_info<8>()};
+    // SIMPLE form (kfast[3..5]): haplotypes with well-formed, separate deletions; GPHMM_PD_NO_SIMPLE=1 keeps them on the first form
+    static const KernelInfo kfast[6] = {pd_fast_kernel_info<3, false>(), pd_fast_kernel_info<5, false>(), pd_fast_kernel_info<8, false>(),
+                                        pd_fast_kernel_info<3, true>(), pd_fast_kernel_info<5, true>(), pd_fast_kernel_info<8, true>()};
     static const bool no_fast = getenv("GPHMM_PD_SLOW") != nullptr;
+    static const bool allow_simple = getenv("GPHMM_PD_NO_SIMPLE") == nullptr;
     const auto chunks = split_units(b, h->chunk_cells() / 4, h->chunk_bytes(), false);
     int64_t launches = 0, total_pairs = 0, total_cells = 0, total_redo = 0, h2d = 0, d2h = 0;
     double device_ms = 0;
@@ -220,7 +301,7 @@ int run_pd_batch(gphmm *h, const gphmm_batch *b, const uint8_t *hap_pd, double *
         ahead.push_back(std::async(std::launch::async, [b, hap_pd, allow_fast, ch]() {
             std::unique_ptr<PdChunkPlan> P(new PdChunkPlan());
             P->ch = ch;
-            P->build(b, hap_pd, allow_fast);
+            P->build(b, hap_pd, allow_fast, allow_simple);
             return P;
         }));
     };
@@ -235,11 +316,12 @@ int run_pd_batch(gphmm *h, const gphmm_batch *b, const uint8_t *hap_pd, double *
         const uint32_t n_pairs = P.n_pairs, max_h = P.max_h;
         const int64_t base_lo = P.base_lo, cells = P.cells;
         const size_t span = P.span, stride = P.stride;
-        const int n_codes = P.n_codes;
+        const int n_rows = P.n_plain + 3 + P.max_snp;
         const uint32_t *first = P.first;
-        const uint8_t *code_byte = P.code_byte, *code_mask = P.code_mask;
+        const uint8_t *code_byte = P.code_byte;
+        auto &groups = P.groups;
         auto &read_off = P.read_off; auto &hap_bytes = P.hap_bytes; auto &hap_flags = P.hap_flags; auto &all = P.all;
-        auto &code_stream = P.code_stream; auto &flag_stream = P.flag_stream; auto &haps = P.haps; auto &segs = P.segs;
+        auto &code_stream = P.code_stream; auto &flag_stream = P.flag_stream; auto &haps = P.haps; auto &segs = P.segs; auto &events = P.events;
         auto &unit_out_base = P.unit_out_base;
         // device image
         size_t o = 0;
@@ -251,6 +333,8 @@ int run_pd_batch(gphmm *h, const gphmm_batch *b, const uint8_t *hap_pd, double *
         const size_t off_fs = o; o = align_up(o + flag_stream.size(), 16);
         const size_t off_hp = o; o = align_up(o + haps.size() * sizeof(PdHap), 16);
         const size_t off_sg = o; o = align_up(o + segs.size() * sizeof(uint2), 16);
+        const size_t off_ev = o; o = align_up(o + events.size() * sizeof(uint2), 16);
+        const size_t off_gr = o; o = align_up(o + groups.size() * sizeof(PdGroup), 16);
         const size_t meta_bytes = o;
         dev.pd_meta.reserve(meta_bytes); dev.pd_h_meta.reserve(meta_bytes);
         uint8_t *hm = (uint8_t *)dev.pd_h_meta.p;
@@ -262,6 +346,8 @@ int run_pd_batch(gphmm *h, const gphmm_batch *b, const uint8_t *hap_pd, double *
         memcpy(hm + off_fs, flag_stream.data(), flag_stream.size());
         memcpy(hm + off_hp, haps.data(), haps.size() * sizeof(PdHap));
         memcpy(hm + off_sg, segs.data(), segs.size() * sizeof(uint2));
+        memcpy(hm + off_ev, events.data(), events.size() * sizeof(uint2));
+        memcpy(hm + off_gr, groups.data(), groups.size() * sizeof(PdGroup));
         o = 0;
         const size_t off_out = o; o = align_up(o + (size_t)n_pairs * 8, 16);
         const size_t off_cnt = o; o = align_up(o + 16 * 4, 16);
@@ -295,7 +381,7 @@ int run_pd_batch(gphmm *h, const gphmm_batch *b, const uint8_t *hap_pd, double *
         pa.err = (int *)(work + off_err);
         pa.tristate_off = h->cfg.tristate_off != 0;
         if (!h->cfg.force_fp64) {
-            for (int k = 3; k < 6; ++k) {
+            for (int k = 3; k < 9; ++k) {
                 const uint32_t n = first[k + 1] - first[k];
                 if (!n) continue;
                 PdFastArgs fa;
@@ -304,16 +390,18 @@ int run_pd_batch(gphmm *h, const gphmm_batch *b, const uint8_t *hap_pd, double *
                 fa.read_off = pa.read_off;
                 fa.codes = meta + off_cs; fa.flags = meta + off_fs;
                 fa.tasks = pa.tasks; fa.haps = (const PdHap *)(meta + off_hp); fa.segs = (const uint2 *)(meta + off_sg);
+                fa.events = (const uint2 *)(meta + off_ev);
+                fa.groups = (const PdGroup *)(meta + off_gr) + P.group_first[k - 3]; fa.n_groups = P.group_first[k - 3 + 1] - P.group_first[k - 3];
                 fa.first = first[k]; fa.n_tasks = n; fa.counter = counters + 10 + (k - 3);
                 fa.sums = (float *)(work + off_s32);
-                fa.m2m = pa.m2m; fa.err = pa.err; fa.tristate_off = pa.tristate_off; fa.n_codes = n_codes;
+                fa.m2m = pa.m2m; fa.err = pa.err; fa.tristate_off = pa.tristate_off; fa.n_plain = P.n_plain; fa.n_rows = n_rows;
                 memcpy(fa.code_byte, code_byte, sizeof fa.code_byte);
-                memcpy(fa.code_mask, code_mask, sizeof fa.code_mask);
-                const int rows = k == 3 ? 3 : (k == 4 ? 5 : 8);
-                const size_t smem = (size_t)n_codes * ((rows + 3) / 4) * 512;
+                const int rows = (k - 3) % 3 == 0 ? 3 : ((k - 3) % 3 == 1 ? 5 : 8);
+                const bool simple = k >= 6;
+                const size_t smem = rows == 3 ? pd_fast_smem<3>(n_rows, simple) : (rows == 5 ? pd_fast_smem<5>(n_rows, simple) : pd_fast_smem<8>(n_rows, simple));
                 int occ = 0;
                 CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kfast[k - 3].fn, 32, smem));
-                const uint32_t grid = std::min<uint32_t>(n, (uint32_t)(dev.n_sms * std::max(1, occ)));
+                const uint32_t grid = std::min<uint32_t>(fa.n_groups, (uint32_t)(dev.n_sms * std::max(1, occ)));
                 void *args[] = {&fa};
                 CK(cudaLaunchKernel(kfast[k - 3].fn, dim3(grid), dim3(32), args, smem, st));
                 ++launches;

@@ -233,13 +233,24 @@ __global__ void __launch_bounds__(32) phmm_pd_kernel(const PdArgs g)
 //     mask) indexes the prior table, so isBasePDMatching (:184-204) costs nothing per cell.
 //   * the row below the read accumulates sum_j (M + I)[R][j] (:149-152): no per-step work for the result.
 // ---------------------------------------------------------------------------------------------
-constexpr int PD_MAX_CODES = 64;   // column codes per chunk: 0 = outside the haplotype, then one per (byte, SNP mask)
+constexpr int PD_MAX_CODES = 64;   // prior-table rows per chunk
 
+constexpr int PD_MAX_SNP_CODES = 8;  // distinct (haplotype byte, alternative-base mask) pairs on the SNP columns of ONE haplotype (fast kernels)
 struct PdHap {
     uint32_t code_off;             // first column of the haplotype in the padded code / flag streams
     uint32_t seg_first, n_segs;    // schedule: into PdFastArgs::segs, (fast steps, slow steps) pairs covering H + 33 steps
-    uint32_t codes_lo, codes_hi;   // column codes that occur in this haplotype
-    uint32_t pad0, pad1, pad2;
+    uint32_t ev_first, n_events;   // SIMPLE kernels: deletion events (a, b) of the haplotype, into PdFastArgs::events
+    uint32_t n_snp;                // SNP column codes of this haplotype: prior-table rows n_plain + 3 + s
+    uint16_t snp[PD_MAX_SNP_CODES];  // haplotype byte | mask << 8 (mask: alternative-base bits A, C, G, T = 1, 2, 4, 8)
+    uint32_t pad0, pad1;
+};
+
+// one fast-kernel task: a read against consecutive pairs of its bucket (the haplotypes of its unit that run this kernel)
+struct PdGroup {
+    uint32_t read;        // chunk-local read
+    uint32_t task_first;  // first pair, relative to PdFastArgs::first
+    uint32_t n;           // pairs
+    uint32_t pad;
 };
 
 struct PdFastArgs {
@@ -247,22 +258,57 @@ struct PdFastArgs {
     const uint32_t *read_off;
     const uint8_t *codes, *flags;  // per column, STREAM_PAD zero columns in front of every haplotype and 2 * STREAM_PAD behind
     const PdTask *tasks;           // PdTask::pad = index into haps
+    const PdGroup *groups;
+    uint32_t n_groups;
     const PdHap *haps;
     const uint2 *segs;
+    const uint2 *events;           // SIMPLE kernels: (a, b) = first and last column of a deletion, 1-based, sorted by column
     uint32_t first, n_tasks;
     uint32_t *counter;
     float *sums;                   // per task (same index as tasks)
     const double *m2m;
     int *err;
-    int32_t tristate_off, n_codes;
-    uint8_t code_byte[PD_MAX_CODES];   // code -> haplotype byte
-    uint8_t code_mask[PD_MAX_CODES];   // code -> 0x80 | alternative-base bits when the column carries a SNP flag, else 0
+    int32_t tristate_off;
+    int32_t n_plain;                   // prior-table rows: 0 = outside the haplotype, 1 .. n_plain = haplotype bytes without a SNP flag,
+    int32_t n_rows;                    // n_plain + 1 / + 2 = match / mismatch prior of every row (source of the SNP rows), then the SNP rows
+    uint8_t code_byte[PD_MAX_CODES];   // plain code -> haplotype byte
 };
 
-template <int K>
+//
+// SIMPLE = true (round 2, second form of the slow window).  For a haplotype whose deletions are well formed and apart
+// (state NORMAL before the first flagged column a of an event, DEL_END only on its last column b, the next event starting
+// at b + 3 or later, state NORMAL again at the end of the haplotype so that every row sees the same column states), the
+// state machine reduces to three moments per lane and event:
+//   column a   (before the update): the branch matrices hold column a - 1 from here to the end of the deletion
+//              (:69-71 copy from the left in NORMAL, :90-92 hold in INSIDE_DEL)  ->  the lane SAVES its M, I~, D~ registers
+//              in a shared-memory record (zero for rows that are not read rows, so that a max() with them changes nothing);
+//   column b   (DEL_END, after the update): the insertion chain takes max(branch, value) of the row above (:80-82) ->
+//              the lane recomputes its K insertion values from the saved record;
+//   column b+1 (AFTER_DEL, before the update): every use of column b is max(branch, value) (:107-118) -> the lane takes
+//              the max IN PLACE and runs the plain step.  Only the accumulator row must not see the merged values (the sum
+//              :149-152 adds the stored M + I of column b): its input is computed before the merge and put back after it.
+// The row above a lane's first row belongs to the previous lane, which is one column ahead: its saved last row is read
+// from its record (row 0 above lane 0 has branch values 0).  Every other lane runs the plain fast step in the same
+// instruction stream; the three moments are divergent branches with one active lane each.
+template <int K> __host__ __device__ constexpr int pd_save_vecs() { return (3 * K + 3) / 4 + 2; }  // record of a lane: 3K floats + (M, I~, D~) of its last row + its unmerged (M, I~) at column b
+template <int K> constexpr size_t pd_fast_smem(int n_codes, bool simple) {
+    return (size_t)n_codes * ((K + 3) / 4) * 512 + (simple ? (size_t)pd_save_vecs<K>() * 512 : 0);
+}
+
+__device__ __forceinline__ void sts128(uint32_t addr, float a, float b, float c, float d) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" :: "r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ float4 lds128m(uint32_t addr) {  // like lds128, ordered against the stores above
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+
+template <int K, bool SIMPLE>
 __global__ void __launch_bounds__(32, K > 5 ? 16 : 20) phmm_pd_fast_kernel(const PdFastArgs g)
 {
     constexpr int NV = (K + 3) / 4;
+    constexpr int NS = (3 * K + 3) / 4;  // float4s of a saved record
     constexpr unsigned FULL = 0xffffffffu;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float *tab_s = reinterpret_cast<float *>(smem_raw);
@@ -273,30 +319,33 @@ __global__ void __launch_bounds__(32, K > 5 ? 16 : 20) phmm_pd_fast_kernel(const
     const ptrdiff_t flag_delta = g.flags - g.codes;
 
     for (;;) {
-        uint32_t ti = 0;
-        if (lane == 0) ti = atomicAdd(g.counter, 1u);
-        ti = __shfl_sync(FULL, ti, 0);
-        if (ti >= g.n_tasks) break;
-        const PdTask t = g.tasks[g.first + ti];
-        const PdHap hp = g.haps[t.pad];
-        const uint32_t ro = g.read_off[t.read];
-        const int R = (int)(g.read_off[t.read + 1] - ro), H = (int)t.H;  // host guarantees R + 2 <= 32 * K
-        const float c0 = (float)scalbn(1.0, t.c0_exp);
+        uint32_t gi = 0;
+        if (lane == 0) gi = atomicAdd(g.counter, 1u);
+        gi = __shfl_sync(FULL, gi, 0);
+        if (gi >= g.n_groups) break;
+        const PdGroup gr = g.groups[gi];
+        const uint32_t ro = g.read_off[gr.read];
+        const int R = (int)(g.read_off[gr.read + 1] - ro);  // host guarantees R + 2 <= 32 * K
         const int acc_lane = R / K, acc_slot = R % K;  // accumulator row = 0-based row R
 
+        // ---- once per read: transition coefficients, the static rows of the prior table ----
         float cb[K], cc[K], cg[K], cd[K];
         uint32_t real_mask = 0;  // bit k: slot k holds a read row (only those take part in the state machine)
+        uint32_t xs[NV];         // the read bases of this lane's rows, one byte each (SNP rows are built per haplotype)
+#pragma unroll
+        for (int v = 0; v < NV; ++v) xs[v] = 0;
         __syncwarp();
 #pragma unroll
         for (int k = 0; k < K; ++k) {
             const int i = lane * K + k + 1;  // 1-based read row
             double A = 0.0, B = 0.0, C = 0.0, G = 0.0, DD = 0.0, pm = 0.0, px = 0.0;
-            uint32_t x = 0, abit = 0;
+            uint32_t x = 0;
             const bool real = i <= R;
             if (real) {
                 real_mask |= 1u << k;
                 uint32_t q = g.rd_q[ro + i - 1], qi = g.rd_i[ro + i - 1], qd = g.rd_d[ro + i - 1], qc = g.rd_c[ro + i - 1];
                 x = g.rd_bases[ro + i - 1];
+                xs[k / 4] |= x << (8 * (k % 4));
                 if (q > (uint32_t)MAX_QUAL || qi > 127u || qd > 127u || qc > 127u) {
                     atomicExch(g.err, 1);
                     q = min(q, (uint32_t)MAX_QUAL); qi = min(qi, 127u); qd = min(qd, 127u); qc = min(qc, 127u);
@@ -321,14 +370,6 @@ __global__ void __launch_bounds__(32, K > 5 ? 16 : 20) phmm_pd_fast_kernel(const
                 pm = (1.0 - e) * A;
                 px = (g.tristate_off ? e : e / 3.0) * A;
                 B *= inv; C *= inv;
-                switch (x) {  // LoglessPDPairHMM.isBasePDMatching :184-204
-                    case 'A': case 'a': abit = 1; break;
-                    case 'C': case 'c': abit = 2; break;
-                    case 'G': case 'g': abit = 4; break;
-                    case 'T': case 't': abit = 8; break;
-                    case 'N': abit = 0; break;
-                    default: abit = 0x80000000u;  // the reference throws when such a base meets a SNP column it does not match
-                }
             } else if (i == R + 1) {  // accumulator row: M_acc = 1 * (M_R + tMI_R * I~_R) = (M + I)[R]
                 B = R >= 1 ? c_eps[min((uint32_t)g.rd_i[ro + R - 1], 127u)] : 0.0;
                 DD = 1.0;
@@ -336,23 +377,60 @@ __global__ void __launch_bounds__(32, K > 5 ? 16 : 20) phmm_pd_fast_kernel(const
             if (lane == 31 && k == K - 1) DD = 1.0;  // carrier of the virtual row 0: keeps D~ = c0
             cb[k] = (float)B; cc[k] = (float)C; cg[k] = (float)G; cd[k] = (float)DD;
             const float pmf = (float)pm, pxf = (float)px;
-            for (int y = 0; y < g.n_codes; ++y) {
-                float v = 0.f;
-                if (real) {
-                    if (y >= 1) {
-                        const uint32_t hb = g.code_byte[y], cm = g.code_mask[y];
+            const float other = (!real && i == R + 1) ? 1.f : 0.f;  // the accumulator row passes everything, pads nothing
+            tab_s[((0 * NV + k / 4) * 32 + lane) * 4 + (k % 4)] = other;  // outside the haplotype (its M input is 0 there)
+            for (int y = 1; y <= g.n_plain; ++y) {
+                const uint32_t hb = g.code_byte[y];
+                const bool match = x == hb || x == (uint32_t)'N' || hb == (uint32_t)'N';  // LoglessPDPairHMM.java:176-180
+                tab_s[((y * NV + k / 4) * 32 + lane) * 4 + (k % 4)] = real ? (match ? pmf : pxf) : other;
+            }
+            tab_s[(((g.n_plain + 1) * NV + k / 4) * 32 + lane) * 4 + (k % 4)] = real ? pmf : other;
+            tab_s[(((g.n_plain + 2) * NV + k / 4) * 32 + lane) * 4 + (k % 4)] = real ? pxf : other;
+        }
+
+        for (uint32_t hk = 0; hk < gr.n; ++hk) {
+        const uint32_t ti = gr.task_first + hk;
+        const PdTask t = g.tasks[g.first + ti];
+        const PdHap *const hpp = g.haps + t.pad;
+        const PdHap hp = *hpp;
+        const int H = (int)t.H;
+        const float c0 = (float)scalbn(1.0, t.c0_exp);
+        // ---- once per haplotype: the prior rows of its SNP columns (isBasePDMatching :184-204) ----
+        __syncwarp();  // the previous sweep is through with them
+        if (hp.n_snp) {
+            float pmv[NV * 4], pxv[NV * 4];
+#pragma unroll
+            for (int v = 0; v < NV; ++v) {
+                const float4 a4 = lds128m(tab_lane + ((g.n_plain + 1) * NV + v) * 512), b4 = lds128m(tab_lane + ((g.n_plain + 2) * NV + v) * 512);
+                pmv[4 * v] = a4.x; pmv[4 * v + 1] = a4.y; pmv[4 * v + 2] = a4.z; pmv[4 * v + 3] = a4.w;
+                pxv[4 * v] = b4.x; pxv[4 * v + 1] = b4.y; pxv[4 * v + 2] = b4.z; pxv[4 * v + 3] = b4.w;
+            }
+            for (uint32_t sn = 0; sn < hp.n_snp; ++sn) {
+                const uint32_t sc = hpp->snp[sn], hb = sc & 0xffu, cm = sc >> 8;
+                float v4[NV * 4];
+#pragma unroll
+                for (int k = 0; k < NV * 4; ++k) {
+                    v4[k] = 0.f;
+                    if (k < K) {
+                        const uint32_t x = (xs[k / 4] >> (8 * (k % 4))) & 0xffu;
                         bool match = x == hb || x == (uint32_t)'N' || hb == (uint32_t)'N';
-                        if (!match && (cm & 0x80u)) {
-                            const bool here = ((y < 32 ? hp.codes_lo >> y : hp.codes_hi >> (y - 32)) & 1u) != 0;
-                            if ((abit & 0x80000000u) && here) atomicExch(g.err, 2);
-                            match = (cm & abit & PD_MASK_BITS) != 0;
+                        if (!match && ((real_mask >> k) & 1u)) {
+                            uint32_t abit;
+                            switch (x) {
+                                case 'A': case 'a': abit = 1; break;
+                                case 'C': case 'c': abit = 2; break;
+                                case 'G': case 'g': abit = 4; break;
+                                case 'T': case 't': abit = 8; break;
+                                default: abit = 0; atomicExch(g.err, 2);  // the reference throws (:202)
+                            }
+                            match = (cm & abit) != 0;
                         }
-                        v = match ? pmf : pxf;
+                        v4[k] = match ? pmv[k] : pxv[k];  // rows that are not read rows: both hold the same value
                     }
-                } else if (i == R + 1) {
-                    v = 1.f;
                 }
-                tab_s[((y * NV + k / 4) * 32 + lane) * 4 + (k % 4)] = v;
+#pragma unroll
+                for (int v = 0; v < NV; ++v)
+                    sts128(tab_lane + ((g.n_plain + 3 + sn) * NV + v) * 512, v4[4 * v], v4[4 * v + 1], v4[4 * v + 2], v4[4 * v + 3]);
             }
         }
         __syncwarp();
@@ -368,6 +446,14 @@ __global__ void __launch_bounds__(32, K > 5 ? 16 : 20) phmm_pd_fast_kernel(const
         st.p = 0;
         st.sp = g.codes + hp.code_off - lane;  // lane l works on column (step - l); columns <= 0 and > H read the zero padding
         st.y = ldg_u8(st.sp);
+        // SIMPLE: this lane's next deletion event and its record behind the prior table
+        uint32_t ev = hp.ev_first;
+        const uint32_t ev_end = hp.ev_first + hp.n_events;
+        constexpr int NO_COL = -(1 << 30);  // no column matches (p >= -31)
+        int ea = NO_COL, eb = NO_COL;
+        if (SIMPLE && ev < ev_end) { const uint2 e = g.events[ev]; ea = (int)e.x; eb = (int)e.y; }
+        const uint32_t rec = tab_lane + (uint32_t)g.n_rows * (NV * 512);         // float4 v of this lane: rec + v * 512
+        const uint32_t rec_prev = rec + NS * 512 + (lane ? -16 : 31 * 16);        // (M, I~, D~) of the previous lane's last row
 
         int step = 1;
         for (uint32_t sg = 0; sg < hp.n_segs; ++sg) {
@@ -377,6 +463,85 @@ __global__ void __launch_bounds__(32, K > 5 ? 16 : 20) phmm_pd_fast_kernel(const
                 fast_step<K, false>(st, cb, cc, cg, cd, tab_lane, src_lane, lane, 0, 0, c0, nullptr, nullptr, 0, 0, 0, 0);
             step += (int)seg.x;
             int p = step - lane;  // 1-based column of this lane
+            if constexpr (SIMPLE) {
+#pragma unroll 1
+                for (uint32_t s = 0; s < seg.y; ++s, ++p) {
+                    if (p == ea) {  // column a: save column a - 1 (rows that are not read rows save 0)
+                        float v[NS * 4];
+#pragma unroll
+                        for (int k = 0; k < NS * 4; ++k) v[k] = 0.f;
+                        if (real_mask == (1u << K) - 1u) {
+#pragma unroll
+                            for (int k = 0; k < K; ++k) { v[k] = st.M[k]; v[K + k] = st.I[k]; v[2 * K + k] = st.D[k]; }
+                        } else {
+#pragma unroll
+                            for (int k = 0; k < K; ++k)
+                                if ((real_mask >> k) & 1u) { v[k] = st.M[k]; v[K + k] = st.I[k]; v[2 * K + k] = st.D[k]; }
+                        }
+#pragma unroll
+                        for (int q = 0; q < NS; ++q) sts128(rec + q * 512, v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                        sts128(rec + NS * 512, v[K - 1], v[2 * K - 1], v[3 * K - 1], 0.f);
+                    }
+                    __syncwarp();
+                    float acc_in = 0.f;
+                    if (p == eb + 1) {  // column b + 1 (AFTER_DEL): merge column b with the branch in place
+                        // the lane below takes this lane's last row at column b from the shuffle of THIS step, i.e. merged --
+                        // right for every use the reference makes of it (:80-82, :107-118) except the accumulator row
+                        sts128(rec + (NS + 1) * 512, st.M[K - 1], st.I[K - 1], 0.f, 0.f);
+                        if (lane == acc_lane) {  // the accumulator row adds the unmerged (M + I)[R][b]
+                            acc_in = __fmaf_rn(cb[0], st.dgi, st.dgm);  // (an empty read: row 0)
+                            if (acc_slot == 0 && lane != 0) {  // row R is the previous lane's last row: its unmerged values were left one step ago
+                                const float4 t4 = lds128m(rec_prev + 512);
+                                acc_in = __fmaf_rn(cb[0], t4.y, t4.x);
+                            }
+#pragma unroll
+                            for (int k = 1; k < K; ++k)
+                                if (k == acc_slot) acc_in = __fmaf_rn(cb[k], st.I[k - 1], st.M[k - 1]);
+                        }
+                        float v[NS * 4];
+#pragma unroll
+                        for (int q = 0; q < NS; ++q) {
+                            const float4 t4 = lds128m(rec + q * 512);
+                            v[4 * q] = t4.x; v[4 * q + 1] = t4.y; v[4 * q + 2] = t4.z; v[4 * q + 3] = t4.w;
+                        }
+#pragma unroll
+                        for (int k = 0; k < K; ++k) {
+                            st.M[k] = pd_max(v[k], st.M[k]); st.I[k] = pd_max(v[K + k], st.I[k]); st.D[k] = pd_max(v[2 * K + k], st.D[k]);
+                        }
+                        if (lane != 0) {  // row above this lane's first row; row 0 has no branch
+                            const float4 t4 = lds128m(rec_prev);
+                            st.dgm = pd_max(t4.x, st.dgm); st.dgi = pd_max(t4.y, st.dgi); st.dgd = pd_max(t4.z, st.dgd);
+                        }
+                    }
+                    fast_step<K, false>(st, cb, cc, cg, cd, tab_lane, src_lane, lane, 0, 0, c0, nullptr, nullptr, 0, 0, 0, 0);
+                    if (p == eb) {  // column b (DEL_END): the insertion chain sees max(branch, value) of the row above
+                        float v[NS * 4];
+#pragma unroll
+                        for (int q = 0; q < NS; ++q) {
+                            const float4 t4 = lds128m(rec + q * 512);
+                            v[4 * q] = t4.x; v[4 * q + 1] = t4.y; v[4 * q + 2] = t4.z; v[4 * q + 3] = t4.w;
+                        }
+                        float um = st.dgm, ui = st.dgi;  // row above at this column (fast_step leaves them here)
+                        if (lane != 0) {
+                            const float4 t4 = lds128m(rec_prev);
+                            um = pd_max(t4.x, um); ui = pd_max(t4.y, ui);
+                        }
+                        st.I[0] = __fmaf_rn(cg[0], ui, um);
+#pragma unroll
+                        for (int k = 1; k < K; ++k) st.I[k] = __fmaf_rn(cg[k], pd_max(v[K + k - 1], st.I[k - 1]), pd_max(v[k - 1], st.M[k - 1]));
+                    }
+                    if (p == eb + 1) {
+                        if (lane == acc_lane) {
+#pragma unroll
+                            for (int k = 0; k < K; ++k)
+                                if (k == acc_slot) st.M[k] = acc_in;
+                        }
+                        ++ev;  // this lane is through with the event
+                        ea = NO_COL; eb = NO_COL;
+                        if (ev < ev_end) { const uint2 e = g.events[ev]; ea = (int)e.x; eb = (int)e.y; }
+                    }
+                }
+            } else {
             // the branch values are dead between two slow windows: every lane refreshes them (NORMAL: branch = the value one
             // column back) in the step before it reaches a column of the state machine, and that step is inside the window.
             // Saying so here keeps them out of the registers the fast loop holds
@@ -443,6 +608,7 @@ __global__ void __launch_bounds__(32, K > 5 ? 16 : 20) phmm_pd_fast_kernel(const
                 st.dgm = mu; st.dgi = iu; st.dgd = du; dgbm = bmu; dgbi = biu; dgbd = bdu;
                 st.y = y_next;
             }
+            }  // !SIMPLE
             step += (int)seg.y;
         }
         // every lane is past column H + 1: the accumulator row holds sum_j (M + I)[R][j] as M + D~
@@ -452,6 +618,7 @@ __global__ void __launch_bounds__(32, K > 5 ? 16 : 20) phmm_pd_fast_kernel(const
             if (k == acc_slot) v = st.M[k] + st.D[k];
         v = __shfl_sync(FULL, v, acc_lane);
         if (lane == 0) g.sums[g.first + ti] = v;
+        }  // haplotypes of the group
     }
 }
 

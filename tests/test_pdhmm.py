@@ -13,8 +13,20 @@ SNP, DEL_START, DEL_END, A, C, G, T = 1, 2, 4, 8, 16, 32, 64
 
 def random_pd(rng, H, mode):
     """mode 0: no flags; 1: SNP sites; 2: SNPs + well-formed deletions; 3: arbitrary flag bytes; 4: sparse (a handful of
-    undetermined sites per haplotype, like the partially determined haplotypes of one assembly region)"""
+    undetermined sites per haplotype, like the partially determined haplotypes of one assembly region); 5: sparse with
+    several deletions of 1-40 columns, some of them adjacent, nested or cut off by the end of the haplotype"""
     pd = np.zeros(H, np.uint8)
+    if mode == 5:
+        for _ in range(int(rng.integers(0, 4))):
+            pd[int(rng.integers(0, H))] |= SNP | int(rng.choice([A, C, G, T]))
+        j = int(rng.integers(0, 30))
+        while j < H:
+            n = int(rng.choice([1, 1, 2, 5, 12, 40]))
+            pd[j] |= DEL_START
+            if j + n - 1 < H or rng.random() < 0.5:
+                pd[min(H - 1, j + n - 1)] |= DEL_END
+            j += n + int(rng.choice([0, 1, 2, 3, 30, 60, 60, 120, 120, 200]))
+        return pd
     if mode == 4:
         for _ in range(int(rng.integers(1, 5))):
             pd[int(rng.integers(0, H))] |= SNP | int(rng.choice([A, C, G, T]))
@@ -165,6 +177,37 @@ def test_pdhmm_matches_oracle(shape):
             _close(hmm.pd_compute(b, pd), want, 1e-4)
             _close(hmm64.pd_compute(b, pd), want, 1e-9)
             assert hmm64.stats()["rescued_pairs"] > 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("read_len", [(1, 94), (95, 158), (159, 254)])  # 3 / 5 / 8 rows per lane
+def test_pdhmm_sparse_flags_fast_kernels(read_len):
+    # sparsely flagged haplotypes run the fast kernels: plain steps between the deletion events, the SIMPLE window form for
+    # well-formed separate deletions (save at the first column, insertion merge at the last, in-place merge after it), the
+    # first form for everything else (events next to each other, a deletion open at the end of the haplotype)
+    from gatk_b200.native import GpuPhmm
+    with GpuPhmm() as hmm:
+        for seed in range(3):
+            b, pd = _pd_batch(100 + seed, 4, 10, 6, read_len, (150, 420), modes=(4, 5, 5))
+            want = _pd_oracle(b, pd)
+            _close(hmm.pd_compute(b, pd), want, 1e-4)
+        # reads that end inside / right after a deletion window and reads shorter than one lane's rows
+        rng = np.random.default_rng(9)
+        hap = L[rng.integers(0, 4, 300)]
+        pd = np.zeros(300, np.uint8)
+        pd[0] |= DEL_START | DEL_END
+        pd[40], pd[47] = DEL_START, DEL_END
+        pd[100] |= DEL_END                  # a DEL_END without a start: a one-column event
+        pd[200], pd[297] = DEL_START, DEL_END
+        reads = []
+        for R in (1, 2, 7, 8, 9, 39, 40, 41, 64, 94, 95, 150, 158, 159, 200, 247, 248, 249, 254):
+            off = int(rng.integers(0, 300 - R + 1))
+            reads.append((hap[off:off + R].copy(), rng.integers(6, 41, R).astype(np.uint8), rng.integers(10, 60, R).astype(np.uint8),
+                          rng.integers(10, 60, R).astype(np.uint8), rng.integers(5, 30, R).astype(np.uint8)))
+        from gatk_b200.native import Batch
+        b = Batch.single_unit(reads, [hap.tobytes(), hap[:299].tobytes()])
+        pd2 = np.concatenate([pd, pd[:299]])
+        _close(hmm.pd_compute(b, pd2), _pd_oracle(b, pd2), 1e-4)
 
 
 @pytest.mark.gpu

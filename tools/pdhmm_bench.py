@@ -17,8 +17,11 @@ b = synth.config2(n_regions, pinned=True)
 rng = np.random.default_rng(1)
 results = []
 with GpuPhmm() as h:
-    for label, mode in (("sparse flags (1-4 SNP sites and at most one deletion per haplotype)", 4), ("dense flags (12 % SNP columns, a deletion every ~12 columns)", 2)):
-        pd = np.concatenate([random_pd(rng, int(b.hap_off[k + 1] - b.hap_off[k]), mode) for k in range(len(b.hap_off) - 1)])
+    for label, mode in (("sparse flags (1-4 SNP sites and at most one deletion per haplotype)", 4), ("the same without the deletions (1-4 SNP sites)", -4),
+                        ("dense flags (12 % SNP columns, a deletion every ~12 columns)", 2)):
+        pd = np.concatenate([random_pd(rng, int(b.hap_off[k + 1] - b.hap_off[k]), abs(mode)) for k in range(len(b.hap_off) - 1)])
+        if mode < 0:
+            pd &= 0xf9  # clear DEL_START / DEL_END
         out = h.pd_compute(b, pd)
         best = 1e9
         for _ in range(3):
