@@ -433,8 +433,10 @@ struct Device {
     cudaStream_t aux[N_SLOTS][N_AUX] = {{nullptr}};  // side streams: the kernels of a chunk overlap their tails
     DeviceChunk slots[N_SLOTS];
     DevBuf m2m;
-    DevBuf pd_reads, pd_meta, pd_work, pd_bnd;  // PD-HMM path (gphmm_pd_compute): one chunk at a time on streams[0]
-    PinBuf pd_h_meta, pd_h_out;
+    // PD-HMM path (gphmm_pd_compute): two chunks in flight, slot k on streams[k]
+    DevBuf pd_reads[2], pd_meta[2], pd_work[2], pd_bnd[2];
+    PinBuf pd_h_meta[2], pd_h_out[2];
+    cudaEvent_t pd_ev0[2] = {nullptr, nullptr}, pd_ev1[2] = {nullptr, nullptr};
     DevBuf sw_in, sw_bt, sw_aux, sw_out;        // Smith-Waterman path (gphmm_sw_align)
     PinBuf sw_h_in, sw_h_out;
     cudaEvent_t ev_step0 = nullptr, ev_step1 = nullptr;  // bracket a whole run_prepared step on streams[0]
@@ -454,6 +456,7 @@ struct Device {
         CK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
         CK(cudaEventCreate(&ev_step0));
         CK(cudaEventCreate(&ev_step1));
+        for (int i = 0; i < 2; ++i) { CK(cudaEventCreate(&pd_ev0[i])); CK(cudaEventCreate(&pd_ev1[i])); }
         for (int i = 0; i < N_SLOTS; ++i) CK(cudaEventCreateWithFlags(&ev_slot_done[i], cudaEventDisableTiming));
         for (int i = 0; i < N_SLOTS; ++i) {
             CK(cudaStreamCreateWithPriority(&streams[i], cudaStreamNonBlocking, prio_lo));
@@ -475,6 +478,13 @@ struct Device {
             for (int k = 0; k < N_AUX; ++k) { if (aux[i][k]) cudaStreamDestroy(aux[i][k]); aux[i][k] = nullptr; }
         }
         m2m.release();
+        for (int i = 0; i < 2; ++i) {
+            pd_reads[i].release(); pd_meta[i].release(); pd_work[i].release(); pd_bnd[i].release();
+            pd_h_meta[i].release(); pd_h_out[i].release();
+            if (pd_ev0[i]) cudaEventDestroy(pd_ev0[i]);
+            if (pd_ev1[i]) cudaEventDestroy(pd_ev1[i]);
+            pd_ev0[i] = pd_ev1[i] = nullptr;
+        }
         if (ev_step0) cudaEventDestroy(ev_step0);
         if (ev_step1) cudaEventDestroy(ev_step1);
         for (auto &e : ev_slot_done) { if (e) cudaEventDestroy(e); e = nullptr; }
@@ -529,6 +539,15 @@ void upload_chunk(Device &dev, DeviceChunk &dc, const gphmm_batch *b, const Chun
     dc.meta.reserve(dc.meta_bytes);
     dc.h_meta.reserve(dc.meta_bytes);
     uint8_t *hm = (uint8_t *)dc.h_meta.p;
+    // a large pageable chunk (what a JVM caller's pack() hands over): four of the five read arrays are copied by helper threads
+    // while this thread -- which also launches the device's kernels -- copies the metadata and the fifth
+    std::future<void> side[4];
+    const bool parallel = inline_reads && span * 5 > ((size_t)4 << 20);
+    for (int a = 1; a < 5 && parallel; ++a) {
+        uint8_t *dst = hm + dc.off_reads + a * dc.read_stride;
+        const uint8_t *from = src[a] + c.base_lo;
+        side[a - 1] = std::async(std::launch::async, [dst, from, span]() { memcpy(dst, from, span); });
+    }
     memcpy(hm + dc.off_read_off, c.read_off.data(), c.read_off.size() * 4);
     memcpy(hm + dc.off_streams, c.streams.data(), c.streams.size());
     memset(hm + dc.off_streams + c.streams.size(), CODE_NULL, 64);
@@ -543,7 +562,8 @@ void upload_chunk(Device &dev, DeviceChunk &dc, const gphmm_batch *b, const Chun
     memcpy(hm + dc.off_sched, c.unit_sched.data(), c.unit_sched.size() * sizeof(UnitSched));
     if (!c.host_class.empty()) memcpy(hm + dc.off_hclass, c.host_class.data(), c.host_class.size());
     if (inline_reads)
-        for (int a = 0; a < 5; ++a) memcpy(hm + dc.off_reads + a * dc.read_stride, src[a] + c.base_lo, span);
+        for (int a = 0; a < (parallel ? 1 : 5); ++a) memcpy(hm + dc.off_reads + a * dc.read_stride, src[a] + c.base_lo, span);
+    for (auto &f : side) if (f.valid()) f.get();
     dc.reads_dev = inline_reads ? (uint8_t *)dc.meta.p + dc.off_reads : (uint8_t *)dc.reads.p;
     if (rs) {
         if (c.r_hi > c.r_lo) memcpy(hm + dc.off_mapq, rs->mapq + c.r_lo, (size_t)(c.r_hi - c.r_lo));

@@ -275,7 +275,6 @@ int run_pd_batch(gphmm *h, const gphmm_batch *b, const uint8_t *hap_pd, double *
     if (!hap_pd) throw Error(GPHMM_ERR_INVALID_ARG, "hap_pd_bases is null");
     Device &dev = *h->devices[0];
     CK(cudaSetDevice(dev.ordinal));
-    cudaStream_t st = dev.streams[0];
     // reads of 128+ bases: 4 rows per lane in strips of 128 rows keeps 18 warps per SM resident (113 registers) where the
     // 8-row variant (181 registers) keeps 11; GPHMM_PD_K8=1 selects the latter for comparison
     static const bool k8 = getenv("GPHMM_PD_K8") != nullptr;
@@ -288,7 +287,12 @@ int run_pd_batch(gphmm *h, const gphmm_batch *b, const uint8_t *hap_pd, double *
                                         pd_fast_kernel_info<3, true>(), pd_fast_kernel_info<5, true>(), pd_fast_kernel_info<8, true>()};
     static const bool no_fast = getenv("GPHMM_PD_SLOW") != nullptr;
     static const bool allow_simple = getenv("GPHMM_PD_NO_SIMPLE") == nullptr;
-    const auto chunks = split_units(b, h->chunk_cells() / 4, h->chunk_bytes(), false);
+    // two chunks in flight (slot k on streams[k]): the upload and the kernels of one overlap the download and the host-side
+    // scatter of the other; GPHMM_PD_SERIAL=1 runs them one after the other (device_ms is then the kernels' time alone)
+    static const bool serial = getenv("GPHMM_PD_SERIAL") != nullptr;
+    const int n_slots = serial ? 1 : 2;
+    // the first chunks are small (doubling from 2.5e8 cells): the GPU starts while the later plans are still being built
+    const auto chunks = split_units(b, h->chunk_cells() / 4, h->chunk_bytes(), !serial);
     int64_t launches = 0, total_pairs = 0, total_cells = 0, total_redo = 0, h2d = 0, d2h = 0;
     double device_ms = 0;
     // chunk plans are built by helper threads a few chunks ahead of the GPU (the per-pair task list is the expensive part)
@@ -305,24 +309,23 @@ int run_pd_batch(gphmm *h, const gphmm_batch *b, const uint8_t *hap_pd, double *
             return P;
         }));
     };
-    while (next_chunk < chunks.size() && ahead.size() < lookahead) start_plan();
-    while (!ahead.empty()) {
-        std::unique_ptr<PdChunkPlan> Pp = ahead.front().get();
-        ahead.pop_front();
-        if (next_chunk < chunks.size()) start_plan();
+    struct InFlight { std::unique_ptr<PdChunkPlan> P; size_t off_err = 0, off_cnt = 0; };
+    InFlight fl[2];
+    bool any_launched = false;
+    int last_slot = 0;
+
+    // everything of one chunk onto the slot's stream: upload, kernels, epilogues, download
+    auto launch = [&](int sl, std::unique_ptr<PdChunkPlan> Pp) {
         PdChunkPlan &P = *Pp;
-        const auto &ch = P.ch;
-        if (P.n_pairs == 0) continue;
+        cudaStream_t st = dev.streams[sl];
         const uint32_t n_pairs = P.n_pairs, max_h = P.max_h;
-        const int64_t base_lo = P.base_lo, cells = P.cells;
+        const int64_t base_lo = P.base_lo;
         const size_t span = P.span, stride = P.stride;
         const int n_rows = P.n_plain + 3 + P.max_snp;
         const uint32_t *first = P.first;
-        const uint8_t *code_byte = P.code_byte;
-        auto &groups = P.groups;
         auto &read_off = P.read_off; auto &hap_bytes = P.hap_bytes; auto &hap_flags = P.hap_flags; auto &all = P.all;
         auto &code_stream = P.code_stream; auto &flag_stream = P.flag_stream; auto &haps = P.haps; auto &segs = P.segs; auto &events = P.events;
-        auto &unit_out_base = P.unit_out_base;
+        auto &groups = P.groups;
         // device image
         size_t o = 0;
         const size_t off_ro = o; o = align_up(o + read_off.size() * 4, 16);
@@ -336,8 +339,8 @@ int run_pd_batch(gphmm *h, const gphmm_batch *b, const uint8_t *hap_pd, double *
         const size_t off_ev = o; o = align_up(o + events.size() * sizeof(uint2), 16);
         const size_t off_gr = o; o = align_up(o + groups.size() * sizeof(PdGroup), 16);
         const size_t meta_bytes = o;
-        dev.pd_meta.reserve(meta_bytes); dev.pd_h_meta.reserve(meta_bytes);
-        uint8_t *hm = (uint8_t *)dev.pd_h_meta.p;
+        dev.pd_meta[sl].reserve(meta_bytes); dev.pd_h_meta[sl].reserve(meta_bytes);
+        uint8_t *hm = (uint8_t *)dev.pd_h_meta[sl].p;
         memcpy(hm + off_ro, read_off.data(), read_off.size() * 4);
         memcpy(hm + off_hb, hap_bytes.data(), hap_bytes.size());
         memcpy(hm + off_hf, hap_flags.data(), hap_flags.size());
@@ -356,27 +359,29 @@ int run_pd_batch(gphmm *h, const gphmm_batch *b, const uint8_t *hap_pd, double *
         const size_t off_s32 = o; o = align_up(o + (size_t)n_pairs * 4, 16);
         const size_t off_redo = o; o = align_up(o + (size_t)n_pairs * 4, 16);
         const size_t off_s64 = o; o = align_up(o + (size_t)n_pairs * 8, 16);
-        dev.pd_work.reserve(o); dev.pd_h_out.reserve(dl_bytes);
-        dev.pd_reads.reserve(std::max<size_t>(stride * 5, 16));
+        dev.pd_work[sl].reserve(o); dev.pd_h_out[sl].reserve(dl_bytes);
+        dev.pd_reads[sl].reserve(std::max<size_t>(stride * 5, 16));
         const uint32_t max_grid = (uint32_t)dev.n_sms * 32;
-        dev.pd_bnd.reserve((size_t)max_grid * (max_h + 1) * sizeof(BndPD<double>));
+        dev.pd_bnd[sl].reserve((size_t)max_grid * (max_h + 1) * sizeof(BndPD<double>));
         const uint8_t *src[5] = {b->read_bases, b->base_q, b->ins_q, b->del_q, b->gcp};
         for (int a = 0; a < 5 && span; ++a)
-            CK(cudaMemcpyAsync((uint8_t *)dev.pd_reads.p + a * stride, src[a] + base_lo, span, cudaMemcpyHostToDevice, st));
-        CK(cudaMemcpyAsync(dev.pd_meta.p, dev.pd_h_meta.p, meta_bytes, cudaMemcpyHostToDevice, st));
+            CK(cudaMemcpyAsync((uint8_t *)dev.pd_reads[sl].p + a * stride, src[a] + base_lo, span, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(dev.pd_meta[sl].p, dev.pd_h_meta[sl].p, meta_bytes, cudaMemcpyHostToDevice, st));
         h2d += (int64_t)(span * 5 + meta_bytes);
-        uint8_t *meta = (uint8_t *)dev.pd_meta.p, *work = (uint8_t *)dev.pd_work.p;
+        uint8_t *meta = (uint8_t *)dev.pd_meta[sl].p, *work = (uint8_t *)dev.pd_work[sl].p;
         uint32_t *counters = (uint32_t *)(work + off_cnt);
         CK(cudaMemsetAsync(work + off_out + (size_t)n_pairs * 8, 0, (off_err + 16) - (off_out + (size_t)n_pairs * 8), st));  // alignment gap, counters, error flag
-        CK(cudaEventRecord(dev.ev_step0, st));
+        CK(cudaEventRecord(dev.pd_ev0[sl], st));
+        if (!any_launched) { CK(cudaEventRecord(dev.ev_step0, st)); any_launched = true; }
+        last_slot = sl;
         PdArgs pa;
         memset(&pa, 0, sizeof pa);
-        pa.rd_bases = (const uint8_t *)dev.pd_reads.p;
+        pa.rd_bases = (const uint8_t *)dev.pd_reads[sl].p;
         pa.rd_q = pa.rd_bases + stride; pa.rd_i = pa.rd_q + stride; pa.rd_d = pa.rd_i + stride; pa.rd_c = pa.rd_d + stride;
         pa.read_off = (const uint32_t *)(meta + off_ro);
         pa.hap_bases = meta + off_hb; pa.hap_flags = meta + off_hf;
         pa.tasks = (const PdTask *)(meta + off_tk);
-        pa.bnd = dev.pd_bnd.p; pa.bnd_stride = max_h + 1;
+        pa.bnd = dev.pd_bnd[sl].p; pa.bnd_stride = max_h + 1;
         pa.m2m = (const double *)dev.m2m.p;
         pa.err = (int *)(work + off_err);
         pa.tristate_off = h->cfg.tristate_off != 0;
@@ -395,7 +400,7 @@ int run_pd_batch(gphmm *h, const gphmm_batch *b, const uint8_t *hap_pd, double *
                 fa.first = first[k]; fa.n_tasks = n; fa.counter = counters + 10 + (k - 3);
                 fa.sums = (float *)(work + off_s32);
                 fa.m2m = pa.m2m; fa.err = pa.err; fa.tristate_off = pa.tristate_off; fa.n_plain = P.n_plain; fa.n_rows = n_rows;
-                memcpy(fa.code_byte, code_byte, sizeof fa.code_byte);
+                memcpy(fa.code_byte, P.code_byte, sizeof fa.code_byte);
                 const int rows = (k - 3) % 3 == 0 ? 3 : ((k - 3) % 3 == 1 ? 5 : 8);
                 const bool simple = k >= 6;
                 const size_t smem = rows == 3 ? pd_fast_smem<3>(n_rows, simple) : (rows == 5 ? pd_fast_smem<5>(n_rows, simple) : pd_fast_smem<8>(n_rows, simple));
@@ -434,25 +439,58 @@ int run_pd_batch(gphmm *h, const gphmm_batch *b, const uint8_t *hap_pd, double *
             (const PdTask *)(meta + off_tk), (const uint32_t *)(work + off_redo), counters + 8, (const double *)(work + off_s64), (double *)(work + off_out));
         CK(cudaGetLastError());
         launches += 3;
-        CK(cudaEventRecord(dev.ev_step1, st));
-        CK(cudaMemcpyAsync(dev.pd_h_out.p, work + off_out, dl_bytes, cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
+        CK(cudaEventRecord(dev.pd_ev1[sl], st));
+        CK(cudaMemcpyAsync(dev.pd_h_out[sl].p, work + off_out, dl_bytes, cudaMemcpyDeviceToHost, st));
         d2h += (int64_t)dl_bytes;
-        float ms = 0;
-        CK(cudaEventElapsedTime(&ms, dev.ev_step0, dev.ev_step1));
-        device_ms += ms;
-        const uint8_t *ho = (const uint8_t *)dev.pd_h_out.p;
-        const int err = *(const int *)(ho + off_err);
+        fl[sl].P = std::move(Pp); fl[sl].off_err = off_err; fl[sl].off_cnt = off_cnt;
+    };
+    // wait for the slot's chunk, check its error flag, scatter its results
+    auto finish = [&](int sl) {
+        if (!fl[sl].P) return;
+        std::unique_ptr<PdChunkPlan> Pp = std::move(fl[sl].P);
+        PdChunkPlan &P = *Pp;
+        CK(cudaStreamSynchronize(dev.streams[sl]));
+        if (serial) {
+            float ms = 0;
+            CK(cudaEventElapsedTime(&ms, dev.pd_ev0[sl], dev.pd_ev1[sl]));
+            device_ms += ms;
+        }
+        const uint8_t *ho = (const uint8_t *)dev.pd_h_out[sl].p;
+        const int err = *(const int *)(ho + fl[sl].off_err);
         if (err == 1) throw Error(GPHMM_ERR_BAD_QUAL, "quality score out of range: ins/del/gcp > 127 or base qual 255");
         if (err == 2) throw Error(GPHMM_ERR_INVALID_ARG, "read base other than ACGT on a SNP column of a partially determined haplotype (LoglessPDPairHMM.java:202)");
-        total_redo += ((const uint32_t *)(ho + off_cnt))[8];
+        total_redo += ((const uint32_t *)(ho + fl[sl].off_cnt))[8];
         const double *res = (const double *)ho;
-        for (int64_t u = ch.first; u < ch.second; ++u) {
+        for (int64_t u = P.ch.first; u < P.ch.second; ++u) {
             const gphmm_unit &un = b->units[u];
             const size_t n = (size_t)(un.read_end - un.read_begin) * (size_t)(un.hap_end - un.hap_begin);
-            if (n) memcpy(out + un.out_off, res + unit_out_base[u - ch.first], n * sizeof(double));
+            if (n) memcpy(out + un.out_off, res + P.unit_out_base[u - P.ch.first], n * sizeof(double));
         }
-        total_pairs += n_pairs; total_cells += cells;
+        total_pairs += P.n_pairs; total_cells += P.cells;
+    };
+    try {
+        while (next_chunk < chunks.size() && ahead.size() < lookahead) start_plan();
+        int sl = 0;
+        while (!ahead.empty()) {
+            std::unique_ptr<PdChunkPlan> Pp = ahead.front().get();
+            ahead.pop_front();
+            if (next_chunk < chunks.size()) start_plan();
+            if (Pp->n_pairs == 0) continue;
+            finish(sl);  // the chunk that used this slot two chunks ago
+            launch(sl, std::move(Pp));
+            sl = (sl + 1) % n_slots;
+        }
+        for (int k = 0; k < n_slots; ++k) { finish(sl); sl = (sl + 1) % n_slots; }
+        if (!serial && any_launched) {  // overlapping chunks: the span from the first kernel to the last epilogue
+            float ms = 0;
+            CK(cudaEventElapsedTime(&ms, dev.ev_step0, dev.pd_ev1[last_slot]));
+            device_ms = ms;
+        }
+    } catch (...) {
+        // nothing of this call may still be running (or planning) when the error reaches the caller
+        for (auto &f : ahead) if (f.valid()) f.wait();
+        for (int k = 0; k < 2; ++k) { cudaStreamSynchronize(dev.streams[k]); fl[k].P.reset(); }
+        throw;
     }
     std::lock_guard<std::mutex> lk(h->stats.mu);
     h->stats.s.pairs += total_pairs; h->stats.s.cells += total_cells; h->stats.s.rescued_pairs += total_redo;

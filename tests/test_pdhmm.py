@@ -110,6 +110,99 @@ def test_snp_and_deletion_semantics():
         oracle.pd_logless(hap, pd, np.frombuffer(b"ACGRACGT", dtype=np.uint8), q, i, i, g)
 
 
+# ---- the SIMPLE window form of the fast kernels, modelled on the CPU ------------------------------------------------------
+def simple_events(pd):
+    """host_pdhmm.inl pd_simple_events: the (a, b) column pairs (1-based) of a haplotype whose deletions are well formed and
+    at least three columns apart, or None"""
+    H, state, a, ev = len(pd), "N", 0, []
+    for j in range(1, H + 1):
+        ds, de = bool(pd[j - 1] & DEL_START), bool(pd[j - 1] & DEL_END)
+        if state == "A":
+            if ds or de:
+                return None
+            state = "N"
+        elif state == "N":
+            if ds or de:
+                a = j
+                if ev and a < ev[-1][1] + 3:
+                    return None
+                if de:
+                    ev.append((a, j))
+                    state = "A"
+                else:
+                    state = "I"
+        elif de:
+            ev.append((a, j))
+            state = "A"
+    return ev if state == "N" else None
+
+
+def simple_model(hap, pd, read, base_q, ins_q, del_q, gcp):
+    """What phmm_pd_fast_kernel<K, SIMPLE> does, column by column in double: the plain LoglessPairHMM update on every column,
+    plus, per deletion event (a, b): SAVE column a - 1; on column b recompute the insertions from max(saved, value) of the row
+    above; before column b + 1 take max(saved, value) of column b IN PLACE.  The likelihood sum adds the unmerged M + I."""
+    H, R = len(hap), len(read)
+    ev = simple_events(pd)
+    assert ev is not None
+    first, last, after = {a for a, _ in ev}, {b for _, b in ev}, {b + 1 for _, b in ev}
+    eps = lambda q: 10.0 ** (q / -10.0)
+    bit = {ord("A"): A, ord("C"): C, ord("G"): G, ord("T"): T}
+    M, I, D = np.zeros(R + 1), np.zeros(R + 1), np.zeros(R + 1)
+    D[0] = 2.0 ** 1020 / H
+    tMM = np.array([0.0] + [max(0.0, 1.0 - eps(ins_q[i]) - eps(del_q[i])) for i in range(R)])
+    tMI = np.array([0.0] + [eps(q) for q in ins_q])
+    tMD = np.array([0.0] + [eps(q) for q in del_q])
+    tII = np.array([0.0] + [eps(q) for q in gcp])
+    tIM = 1.0 - tII
+    saved, total = None, 0.0
+    for j in range(1, H + 1):
+        if j in first:
+            saved = (M.copy(), I.copy(), D.copy())
+            saved[2][0] = 0.0  # row 0 has no branch (Java's branch matrices are 0.0 there)
+        if j in after:
+            M, I, D = np.maximum(M, saved[0]), np.maximum(I, saved[1]), np.maximum(D, saved[2])
+        y, f = hap[j - 1], pd[j - 1]
+        prior = np.zeros(R + 1)
+        for i in range(1, R + 1):
+            x, e = read[i - 1], eps(base_q[i - 1])
+            match = x == y or x == ord("N") or y == ord("N") or ((f & SNP) and (f & bit[x]))
+            prior[i] = 1.0 - e if match else e / 3.0
+        Mn, In, Dn = np.zeros(R + 1), np.zeros(R + 1), np.zeros(R + 1)
+        Dn[0] = 2.0 ** 1020 / H
+        Mn[1:] = prior[1:] * (M[:-1] * tMM[1:] + I[:-1] * tIM[1:] + D[:-1] * tIM[1:])
+        Dn[1:] = M[1:] * tMD[1:] + D[1:] * tII[1:]
+        for i in range(1, R + 1):
+            um, ui = Mn[i - 1], In[i - 1]
+            if j in last:
+                um, ui = max(um, saved[0][i - 1]), max(ui, saved[1][i - 1])
+            In[i] = um * tMI[i] + ui * tII[i]
+        M, I, D = Mn, In, Dn
+        total += M[R] + I[R]
+    return (np.log10(total) if total > 0 else -np.inf) - np.log10(2.0 ** 1020)
+
+
+def test_simple_window_form_equals_the_reference_state_machine():
+    # the reduction the SIMPLE kernels rest on, checked against the oracle without a GPU
+    rng = np.random.default_rng(21)
+    n = 0
+    assert simple_events(np.array([0, DEL_START, 0, DEL_END, 0, 0], np.uint8)) == [(2, 4)]
+    assert simple_events(np.array([0, DEL_END, 0, 0, DEL_START | DEL_END, 0], np.uint8)) == [(2, 2), (5, 5)]
+    assert simple_events(np.array([0, DEL_END, 0, DEL_START | DEL_END, 0], np.uint8)) is None   # two columns apart
+    assert simple_events(np.array([0, DEL_START, DEL_END, DEL_END, 0], np.uint8)) is None       # a flag met in AFTER_DEL
+    assert simple_events(np.array([0, 0, DEL_START, 0], np.uint8)) is None                      # still open at the end
+    assert simple_events(np.array([0, 0, DEL_START, DEL_END], np.uint8)) is None                # AFTER_DEL carried into the next row
+    while n < 150:
+        hap, read, q = random_pair(rng, 90, 60)
+        pd = random_pd(rng, len(hap), int(rng.choice([4, 5])))
+        if simple_events(pd) is None or not simple_events(pd):
+            continue
+        read[read == ord("N")] = ord("A")
+        want = oracle.pd_logless(hap, pd, read, *q)
+        got = simple_model(hap, pd, read, *q)
+        assert abs(got - want) < 1e-9, (n, got, want)
+        n += 1
+
+
 # ---- device ---------------------------------------------------------------------------------------------------------
 def _pd_batch(seed, n_units, max_reads, max_haps, read_len, hap_len, modes=(0, 1, 2, 3)):
     from gatk_b200.native import Batch
