@@ -540,6 +540,7 @@ __global__ void __launch_bounds__(32, K > 5 ? 16 : 20) phmm_pd_fast_kernel(const
                         ea = NO_COL; eb = NO_COL;
                         if (ev < ev_end) { const uint2 e = g.events[ev]; ea = (int)e.x; eb = (int)e.y; }
                     }
+                    __syncwarp();  // the records read in this step may be overwritten in the next one (next event three columns on)
                 }
             } else {
             // the branch values are dead between two slow windows: every lane refreshes them (NORMAL: branch = the value one
