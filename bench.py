@@ -375,7 +375,7 @@ def main():
                     "ms_per_step": 1e3 * e2e_wall / steps, "api": "gphmm_compute (C ABI) with pinned host arrays"},
             "gpu_launches": int(st["kernel_launches"]),
             "roofline": {"bound": "fp32", "achieved": achieved_tflops, "peak": peak_tflops, "unit": "TFLOP/s", "frac": achieved_tflops / peak_tflops,
-                         "traffic": 223994368, "kernel": "phmm_flat_f32_kernel<K> (+ phmm_fast_f32_kernel<K> for non-flat reads), all K buckets of the step",
+                         "traffic": 220070400, "kernel": "phmm_flat_f32_kernel<K> (+ phmm_fast_f32_kernel<K> for non-flat reads), all K buckets of the step",
                          "peak_source": "2 x %d SMs x 128 lanes x %.0f MHz (SM clock sampled during the timed region); MEASURED_PEAKS.json has no FP32 entry" % (props.multi_processor_count, sm_for_peak),
                          "flops_per_cell": 12, "kernel_ms_per_step": 1e3 * f32_s / steps,
                          "executed_frac": 12.0 * (cells - st["skipped_cells"] / steps) * steps / f32_s / 1e12 / peak_tflops,
@@ -383,7 +383,7 @@ def main():
                          "peak_measured": peak_measured, "frac_of_peak_measured": (achieved_tflops / peak_measured) if peak_measured else None,
                          "executed_frac_of_peak_measured": (12.0 * (cells - st["skipped_cells"] / steps) * steps / f32_s / 1e12 / peak_measured) if peak_measured else None,
                          "peak_measured_source": "gphmm_measure_fp32_peak: dense FFMA with constant-bank operands, 64 warps/SM, ~30 ms, same process and clocks",
-                         "traffic_note": "bytes per launch of phmm_flat_f32_kernel<8> from one ncu --set full capture (22.5 MB DRAM read + 201.5 MB written -- write-back of the snapshot slabs -- in a 5.8 ms launch): the kernel is FP32-issue bound, HBM carries 39 GB/s; profiles/r01_flat_k8_final_ncu_full.txt",
+                         "traffic_note": "bytes per launch of the dominant kernel phmm_flat_f32_kernel<16,0,16> (two 250-base reads per warp) from one ncu --set full capture: 20.8 MB DRAM read + 199.3 MB written in a 4.5 ms launch = 49 GB/s.  The reads are the inputs; the writes are write-back of the per-CTA snapshot slabs (scratch that is re-read from L2, 73 KB stored per task), not result traffic: the kernel is FP32-issue bound and HBM is 0.7 % busy; profiles/r02_flat16_k16_final_ncu_full.txt",
                          "hbm_gbs_staging": (batch.input_bytes() + 8 * pairs) * steps / f32_s / 1e9},
         }
         if pageable:
