@@ -323,7 +323,7 @@ KernelInfo fp32_kernel(int bucket, int n_codes) {
 }
 template <int K, bool SYM> KernelInfo flat_kernel_info(int n_codes) {
     KernelInfo ki;
-    auto fn = phmm_flat_f32_kernel<K, SYM>;
+    auto fn = phmm_flat_f32_kernel<K, SYM ? MODE_SYM : MODE_FLAT>;
     ki.fn = (const void *)fn;
     ki.smem = prior_table_bytes<float, K>(n_codes);
     raise_dyn_smem((const void *)fn, ki.smem);
@@ -361,7 +361,7 @@ KernelInfo sym_kernel(int bucket, int n_codes) {
 
 template <int K, bool SYM> KernelInfo flat16_kernel_info(int n_codes) {
     KernelInfo ki;
-    auto fn = phmm_flat_f32_kernel<K, SYM, 16>;
+    auto fn = phmm_flat_f32_kernel<K, SYM ? MODE_SYM : MODE_FLAT, 16>;
     ki.fn = (const void *)fn;
     ki.smem = prior_table_bytes<float, K>(n_codes);
     raise_dyn_smem((const void *)fn, ki.smem);
@@ -378,6 +378,22 @@ KernelInfo flat16_kernel(int p, bool sym, int n_codes) {
         case 2: return sym ? flat16_kernel_info<14, true>(n_codes) : flat16_kernel_info<14, false>(n_codes);
         default: return sym ? flat16_kernel_info<16, true>(n_codes) : flat16_kernel_info<16, false>(n_codes);
     }
+}
+
+// half-warp form of the general (per-base quality) kernel: reads of 128..191 bases, 10 / 12 rows per lane
+template <int K> KernelInfo gen16_kernel_info(int n_codes) {
+    KernelInfo ki;
+    auto fn = phmm_flat_f32_kernel<K, MODE_GEN, 16>;
+    ki.fn = (const void *)fn;
+    ki.smem = prior_table_bytes<float, K>(n_codes);
+    raise_dyn_smem((const void *)fn, ki.smem);
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ki.ctas_per_sm, fn, 32, ki.smem));
+    if (ki.ctas_per_sm < 1) throw Error(GPHMM_ERR_ALPHABET, "prior table does not fit in shared memory");
+    reserve_headroom(ki, (const void *)fn);
+    return ki;
+}
+KernelInfo gen16_kernel(int p, int n_codes) {
+    return p == 0 ? gen16_kernel_info<10>(n_codes) : p == 1 ? gen16_kernel_info<12>(n_codes) : p == 2 ? gen16_kernel_info<14>(n_codes) : gen16_kernel_info<16>(n_codes);
 }
 
 KernelInfo fp64_kernel(int n_codes) { return kernel_info<double, 4, true>(n_codes); }
@@ -403,6 +419,16 @@ constexpr int FP64_KEY = 9;       // phmm_forward_kernel<double, 4, striped>
 constexpr int FLAT_KEY = 16;      // flat-quality kernel of bucket k < 8 is FLAT_KEY + k, of half-warp bucket p FLAT_KEY + 8 + p
 constexpr int FLAT_F64_KEY = 32;  // phmm_flat_f64_kernel
 constexpr int SYM_KEY = 48;       // symmetric-quality kernel of bucket k < 8 is SYM_KEY + k, of half-warp bucket p SYM_KEY + 8 + p
+constexpr int GEN16_KEY = 80;     // half-warp form of the general kernel for half-warp bucket p < N_GEN16 is GEN16_KEY + p
+constexpr int N_GEN16 = 4;        // ... exists for 10 and 12 rows per lane (four coefficient registers per row)
+inline bool gen16_bucket(int bucket) {
+    static const bool off = getenv("GPHMM_NO_GEN16") != nullptr;  // A/B switch: general reads of half-warp buckets on full warps
+    static const int n = getenv("GPHMM_N_GEN16") ? atoi(getenv("GPHMM_N_GEN16")) : N_GEN16;
+    return !off && is_pair_bucket(bucket) && bucket - FIRST_PAIR_BUCKET < n;
+}
+// key of the kernel that takes the general (per-base quality) reads of a bucket, and the rows per lane its snapshot slab is sized for
+inline int general_key(int bucket) { return gen16_bucket(bucket) ? GEN16_KEY + bucket - FIRST_PAIR_BUCKET : general_bucket_of(bucket); }
+inline int general_slab_bucket(int bucket) { return gen16_bucket(bucket) ? bucket : 0; }
 inline int flat_key(int bucket, bool sym) { return (sym ? SYM_KEY : FLAT_KEY) + (is_pair_bucket(bucket) ? 8 + bucket - FIRST_PAIR_BUCKET : bucket); }
 inline size_t slab_per_cta(int bucket) { return snap_slab_bytes(is_pair_bucket(bucket) ? pair_bucket_rows(bucket) : 8); }
 
@@ -419,7 +445,8 @@ struct Device {
         const int key = bucket * 1024 + n_codes;
         auto it = kinfo.find(key);
         if (it == kinfo.end())
-            it = kinfo.emplace(key, bucket < FP64_KEY ? fp32_kernel(bucket, n_codes)
+            it = kinfo.emplace(key, bucket >= GEN16_KEY ? gen16_kernel(bucket - GEN16_KEY, n_codes)
+                                    : bucket < FP64_KEY ? fp32_kernel(bucket, n_codes)
                                     : bucket == FP64_KEY ? fp64_kernel(n_codes)
                                     : bucket == FLAT_F64_KEY ? flat_fp64_kernel(n_codes)
                                     : bucket >= SYM_KEY + 8 ? flat16_kernel(bucket - SYM_KEY - 8, true, n_codes)
@@ -814,7 +841,7 @@ int launch_chunk(Device &dev, DeviceChunk &dc, const ChunkPlan &c, cudaStream_t 
             for (int k = 0; k < N_FP32_BUCKETS; ++k) {
                 const uint32_t n = c.bucket_begin[k + 1] - c.bucket_begin[k];
                 if (!n || k == 8) continue;
-                need += (size_t)persistent_grid(n, dev.n_sms, dev.info(general_bucket_of(k), c.n_codes).ctas_per_sm) * slab_per_cta(0);
+                need += (size_t)persistent_grid(n, dev.n_sms, dev.info(general_key(k), c.n_codes).ctas_per_sm) * slab_per_cta(general_slab_bucket(k));
                 for (int cl = 0; cl < c.n_classes; ++cl)
                     need += (size_t)persistent_grid(n, dev.n_sms, dev.info(flat_key(k, false), c.n_codes).ctas_per_sm) * slab_per_cta(k);
                 for (int cl = 0; cl < c.n_sym; ++cl)
@@ -904,12 +931,15 @@ int launch_chunk(Device &dev, DeviceChunk &dc, const ChunkPlan &c, cudaStream_t 
             }
             if (!has_work(k, MAX_FLAT_CLASSES + MAX_SYM_CLASSES)) continue;
             ka.counter = pair ? counters + 128 + kp : counters + k;
-            const KernelInfo &kg = dev.info(general_bucket_of(k), c.n_codes);
+            const KernelInfo &kg = dev.info(general_key(k), c.n_codes);
             if (k != 8) {
                 ka.snap = (float *)((uint8_t *)dc.snap.p + slab_cursor);
-                slab_cursor += (size_t)persistent_grid(n, dev.n_sms, kg.ctas_per_sm) * slab_per_cta(0);
+                slab_cursor += (size_t)persistent_grid(n, dev.n_sms, kg.ctas_per_sm) * slab_per_cta(general_slab_bucket(k));
             }
-            void *args[] = {&ka};
+            FlatCoef gc;  // half-warp form of the general kernel: the flat-kernel family with every coefficient per row
+            memset(&gc, 0, sizeof gc);
+            gc.class_id = CLASS_GENERAL;
+            void *args[] = {&ka, &gc};  // (the full-warp kernels take the first argument only)
             launch_on(kg, n, k, args);
         }
         }

@@ -665,11 +665,18 @@ __global__ void __launch_bounds__(128) phmm_classify_kernel(const ClassifyArgs a
     }
 }
 
-template <int K, int SLOT, bool CHECKED, bool SYM>
-__device__ __forceinline__ void flat_step(FastState<K> &st, const FlatCoef &f, const float (&A)[K], const float (&C)[K], float B0, float G0,
-                                          float E0, uint32_t tab_lane, int src_lane, int lane, int acc_lane, float *sums_task,
-                                          float *slab, int snap_pos, int snap_slot, int end_restore, uint32_t end_out)
+// MODE of the flat-kernel family: how many of the five transition coefficients are per-row registers instead of constant operands
+constexpr int MODE_FLAT = 0;  // none: flat insertion / deletion / GCP qualities
+constexpr int MODE_SYM = 1;   // two (A, C): ins == del per base with a flat GCP (the PCR indel model)
+constexpr int MODE_GEN = 2;   // four (A, C, G, Dd): any per-base qualities (DRAGstr, BI/BD tags) -- the half-warp form of the general kernel
+
+template <int K, int SLOT, bool CHECKED, int MODE>
+__device__ __forceinline__ void flat_step(FastState<K> &st, const FlatCoef &f, const float (&A)[K], const float (&C)[K], const float (&G)[K],
+                                          const float (&Dd)[K], float B0, float G0, float E0, float tmi, uint32_t tab_lane, int src_lane, int lane,
+                                          int acc_lane, float *sums_task, float *slab, int snap_pos, int snap_slot, int end_restore, uint32_t end_out)
 {
+    constexpr bool SYM = MODE != MODE_FLAT;   // per-row coefficients of I^ and D^ in the match update
+    constexpr bool GEN = MODE == MODE_GEN;    // ... and of the gap recurrences
     constexpr int NV = (K + 3) / 4;
     constexpr unsigned FULL = 0xffffffffu;
     constexpr uint32_t CODE_STRIDE = NV * 32 * 16;
@@ -704,10 +711,10 @@ __device__ __forceinline__ void flat_step(FastState<K> &st, const FlatCoef &f, c
         Mn[k] = pr[k] * u;
     }
 #pragma unroll
-    for (int k = 0; k < K; ++k) st.D[k] = __fmaf_rn(f.d, st.D[k], st.M[k]);
+    for (int k = 0; k < K; ++k) st.D[k] = __fmaf_rn(GEN ? Dd[k] : f.d, st.D[k], st.M[k]);
     st.I[0] = __fmaf_rn(G0, iu, mu);
 #pragma unroll
-    for (int k = 1; k < K; ++k) st.I[k] = __fmaf_rn(f.g, st.I[k - 1], Mn[k - 1]);
+    for (int k = 1; k < K; ++k) st.I[k] = __fmaf_rn(GEN ? G[k] : f.g, st.I[k - 1], Mn[k - 1]);
 #pragma unroll
     for (int k = 0; k < K; ++k) st.M[k] = Mn[k];
     st.dgm = mu; st.dgi = iu; st.dgd = du;
@@ -716,7 +723,7 @@ __device__ __forceinline__ void flat_step(FastState<K> &st, const FlatCoef &f, c
     // values: the haplotype's sum is therefore the accumulator BEFORE this step.
     const float acc_before = st.acc;
     st.acc += st.M[SLOT];
-    st.acc = __fmaf_rn(f.tmi, st.I[SLOT], st.acc);
+    st.acc = __fmaf_rn(GEN ? tmi : f.tmi, st.I[SLOT], st.acc);
     if (CHECKED) {
         if (__builtin_expect(st.p == snap_pos, 0)) snap_save<K>(st, slab, snap_slot);
         if (__builtin_expect(st.y == CODE_END, 0)) {
@@ -728,35 +735,38 @@ __device__ __forceinline__ void flat_step(FastState<K> &st, const FlatCoef &f, c
     st.y = y_next;
 }
 
-template <int K, int SLOT, bool SYM>
-__device__ __forceinline__ void flat_sweep(FastState<K> &st, const FlatCoef &f, const float (&A)[K], const float (&C)[K], float B0, float G0,
-                                           float E0, uint32_t tab_lane, int src_lane, int lane, int acc_lane, float *sums_task,
-                                           float *slab, const Segment *segs, uint32_t n_segs)
+template <int K, int SLOT, int MODE>
+__device__ __forceinline__ void flat_sweep(FastState<K> &st, const FlatCoef &f, const float (&A)[K], const float (&C)[K], const float (&G)[K],
+                                           const float (&Dd)[K], float B0, float G0, float E0, float tmi, uint32_t tab_lane, int src_lane, int lane,
+                                           int acc_lane, float *sums_task, float *slab, const Segment *segs, uint32_t n_segs)
 {
+    // the general form carries four coefficient registers per row: a shorter unrolled body keeps it at 16 resident warps
+    constexpr int UNROLL = MODE == MODE_GEN ? 2 : flat_unroll(K), CHK_UNROLL = MODE == MODE_GEN ? 1 : flat_chk_unroll(K);
     int step = 1;
     for (uint32_t sg = 0; sg < n_segs; ++sg) {
         const Segment seg = segs[sg];
-#pragma unroll (flat_unroll(K))
+#pragma unroll (UNROLL)
         for (uint32_t s = 0; s < seg.n_free; ++s)
-            flat_step<K, SLOT, false, SYM>(st, f, A, C, B0, G0, E0, tab_lane, src_lane, lane, acc_lane, sums_task, slab, 0, 0, 0, 0);
+            flat_step<K, SLOT, false, MODE>(st, f, A, C, G, Dd, B0, G0, E0, tmi, tab_lane, src_lane, lane, acc_lane, sums_task, slab, 0, 0, 0, 0);
         step += (int)seg.n_free;
         st.p = step - lane;
-#pragma unroll (flat_chk_unroll(K))
+#pragma unroll (CHK_UNROLL)
         for (uint32_t s = 0; s < seg.n_chk; ++s)
-            flat_step<K, SLOT, true, SYM>(st, f, A, C, B0, G0, E0, tab_lane, src_lane, lane, acc_lane, sums_task, slab, seg.snap_pos,
-                                          seg.snap_slot, seg.end_restore, seg.end_out);
+            flat_step<K, SLOT, true, MODE>(st, f, A, C, G, Dd, B0, G0, E0, tmi, tab_lane, src_lane, lane, acc_lane, sums_task, slab, seg.snap_pos,
+                                           seg.snap_slot, seg.end_restore, seg.end_out);
         step += (int)seg.n_chk;
     }
 }
 
-template <int K, int SLOT, bool SYM>
+template <int K, int SLOT, int MODE>
 __device__ __forceinline__ void flat_dispatch(int slot, FastState<K> &st, const FlatCoef &f, const float (&A)[K], const float (&C)[K],
-                                              float B0, float G0, float E0, uint32_t tab_lane, int src_lane, int lane, int acc_lane,
-                                              float *sums_task, float *slab, const Segment *segs, uint32_t n_segs)
+                                              const float (&G)[K], const float (&Dd)[K], float B0, float G0, float E0, float tmi,
+                                              uint32_t tab_lane, int src_lane, int lane, int acc_lane, float *sums_task, float *slab,
+                                              const Segment *segs, uint32_t n_segs)
 {
-    if (slot == SLOT) flat_sweep<K, SLOT, SYM>(st, f, A, C, B0, G0, E0, tab_lane, src_lane, lane, acc_lane, sums_task, slab, segs, n_segs);
+    if (slot == SLOT) flat_sweep<K, SLOT, MODE>(st, f, A, C, G, Dd, B0, G0, E0, tmi, tab_lane, src_lane, lane, acc_lane, sums_task, slab, segs, n_segs);
     else if constexpr (SLOT + 1 < K)
-        flat_dispatch<K, SLOT + 1, SYM>(slot, st, f, A, C, B0, G0, E0, tab_lane, src_lane, lane, acc_lane, sums_task, slab, segs, n_segs);
+        flat_dispatch<K, SLOT + 1, MODE>(slot, st, f, A, C, G, Dd, B0, G0, E0, tmi, tab_lane, src_lane, lane, acc_lane, sums_task, slab, segs, n_segs);
 }
 
 // 28 one-warp CTAs per SM (the shared-memory limit of the K=8 prior table) need <= 73 registers per thread.
@@ -767,11 +777,14 @@ __device__ __forceinline__ void flat_dispatch(int slot, FastState<K> &st, const 
 // rows per lane instead of 5, 250-base reads 16 instead of 8.  The planner pairs reads whose last row falls on the same
 // register slot (R - 1) mod K, which keeps the slot of the likelihood sum a template parameter; a read without a partner
 // leaves its half idle (all rows pads).
-__host__ __device__ constexpr int flat_min_ctas(int K, bool SYM, int LANES) { return LANES == 32 ? (SYM ? 22 : 28) : (K > 12 ? 14 : (SYM ? 16 : 18)); }
+__host__ __device__ constexpr int flat_min_ctas(int K, int MODE, int LANES) {
+    return LANES == 32 ? (MODE != MODE_FLAT ? 22 : 28) : (MODE == MODE_GEN ? (K > 12 ? 10 : 14) : (K > 12 ? 14 : (MODE != MODE_FLAT ? 16 : 18)));
+}
 
-template <int K, bool SYM, int LANES = 32>
-__global__ void __launch_bounds__(32, flat_min_ctas(K, SYM, LANES)) phmm_flat_f32_kernel(const KernelArgs g, const FlatCoef f)
+template <int K, int MODE, int LANES = 32>
+__global__ void __launch_bounds__(32, flat_min_ctas(K, MODE, LANES)) phmm_flat_f32_kernel(const KernelArgs g, const FlatCoef f)
 {
+    constexpr bool SYM = MODE == MODE_SYM, GEN = MODE == MODE_GEN;
     constexpr int NV = (K + 3) / 4;
     constexpr unsigned FULL = 0xffffffffu;
     constexpr int REGS = snap_regs(K);
@@ -807,7 +820,9 @@ __global__ void __launch_bounds__(32, flat_min_ctas(K, SYM, LANES)) phmm_flat_f3
         const uint32_t out_base = upper ? t.stream_len : t.out_base;
         const float c0 = (float)scalbn(1.0, t.c0_exp);
 
-        float A[K], C[K];  // SYM only: per-row coefficients of M^ and D^
+        float A[K], C[K];    // SYM, GEN: per-row coefficients of I^ and D^ in the match update
+        float G[K], Dd[K];   // GEN: per-row coefficients of the insertion and deletion recurrences
+        float tmi_r = 0.f, tim_1 = 0.f;  // GEN: tMI of the read's last row (the sum adds tMI * I~), tIM / tMM of row 1
         __syncwarp();
 #pragma unroll
         for (int k = 0; k < K; ++k) {
@@ -815,14 +830,34 @@ __global__ void __launch_bounds__(32, flat_min_ctas(K, SYM, LANES)) phmm_flat_f3
             const bool real = i <= R;
             float pmf = 0.f, pxf = 0.f;
             uint32_t x = 0;
-            A[k] = 0.f; C[k] = 0.f;
+            A[k] = 0.f; C[k] = 0.f; G[k] = 0.f; Dd[k] = 0.f;
             if (real) {
                 uint32_t q = g.rd_q[ro + i - 1];
                 x = g.rd_bases[ro + i - 1];
                 if (q > (uint32_t)MAX_QUAL) { atomicExch(g.err, 1); q = MAX_QUAL; }
                 const double e = c_eps[q];
                 double pm = 1.0 - e, px = g.tristate_off ? e : e / 3.0;
-                if (SYM) {
+                if (GEN) {
+                    // any per-base qualities: the recurrence of phmm_fast_f32_kernel (I~ = I / tMI_i, D~ = D / tMD_i, tMM folded into
+                    // the priors) in this kernel's layout -- row 1 on slot 0 of pipeline lane 0, pads below the read, the sum taken
+                    // from row R directly
+                    uint32_t qi = g.rd_i[ro + i - 1], qd = g.rd_d[ro + i - 1], qc = g.rd_c[ro + i - 1];
+                    if (qi > 127u || qd > 127u || qc > 127u) { atomicExch(g.err, 1); qi = min(qi, 127u); qd = min(qd, 127u); qc = min(qc, 127u); }
+                    const double ei = c_eps[qi], ec = c_eps[qc];
+                    const uint32_t mn = min(qi, qd), mx = max(qi, qd);
+                    const double tIM = 1.0 - ec;
+                    const double Am = __ldg(g.m2m + ((mx * (mx + 1)) >> 1) + mn);
+                    // tMM = 0 cannot be factored out: NaN coefficients poison the sums and the pairs are redone by the fp64 kernels
+                    const double inv = Am > 0.0 ? 1.0 / Am : __longlong_as_double(0x7ff8000000000000LL);
+                    double Bc = 0.0, Cc = tIM, Gc = 0.0;  // row 1: D~ of row 0 is c0 (tMD_0 = 1), I~ of row 0 is 0
+                    if (i > 1) {
+                        const double tmi_prev = c_eps[min((uint32_t)g.rd_i[ro + i - 2], 127u)];
+                        const double tmd_prev = c_eps[min((uint32_t)g.rd_d[ro + i - 2], 127u)];
+                        Bc = tIM * tmi_prev; Cc = tIM * tmd_prev; Gc = ec * tmi_prev / ei;
+                    }
+                    A[k] = (float)(Bc * inv); C[k] = (float)(Cc * inv); G[k] = (float)Gc; Dd[k] = (float)ec;
+                    pm *= Am; px *= Am;
+                } else if (SYM) {
                     // ins == del = e_i on every base, flat gcp (DESIGN.md "Symmetric-quality kernel"):
                     //   M^_i = M_i eps_{i+1}/kappa,  I^_i = I_i/kappa,  D^_i = D_i eps_{i+1}/(eps_i kappa),  eps_{R+1} := kappa
                     //   M^_i = (p_ij eps_{i+1}) (A_i M^_{i-1} + T I^_{i-1} + C_i D^_{i-1}),  A_i = tMM_i/eps_i,  C_i = T eps_{i-1}/eps_i
@@ -856,7 +891,13 @@ __global__ void __launch_bounds__(32, flat_min_ctas(K, SYM, LANES)) phmm_flat_f3
                 tab_s[((y * NV + k / 4) * 32 + lane) * 4 + (k % 4)] = v;
             }
         }
-        if (f.qi > 127u || f.qd > 127u || f.qc > 127u) atomicExch(g.err, 1);
+        if (GEN && mine) {
+            tmi_r = (float)c_eps[min((uint32_t)g.rd_i[ro + R - 1], 127u)];
+            const uint32_t qi = min((uint32_t)g.rd_i[ro], 127u), qd = min((uint32_t)g.rd_d[ro], 127u), qc = min((uint32_t)g.rd_c[ro], 127u);
+            const double Am = __ldg(g.m2m + ((max(qi, qd) * (max(qi, qd) + 1)) >> 1) + min(qi, qd));
+            tim_1 = (float)((1.0 - c_eps[qc]) * (Am > 0.0 ? 1.0 / Am : __longlong_as_double(0x7ff8000000000000LL)));
+        }
+        if (!GEN && (f.qi > 127u || f.qd > 127u || f.qc > 127u)) atomicExch(g.err, 1);
         __syncwarp();
 
         FastState<K> st;
@@ -869,9 +910,9 @@ __global__ void __launch_bounds__(32, flat_min_ctas(K, SYM, LANES)) phmm_flat_f3
         st.sp = g.sstreams + us.sstream_off - pl;
         st.y = ldg_u8(st.sp);
         // slot 0: pipeline lane 0 holds row 1 (virtual row 0 above it: M = I~ = 0, c*D~ = tIM*c0; SYM: f.tim = 1, the rest is in row 1's table)
-        const float B0 = pl == 0 ? 0.f : (SYM ? A[0] : f.b);
-        const float G0 = pl == 0 ? 0.f : f.g;
-        const float E0 = pl == 0 ? f.tim * c0 : 0.f;
+        const float B0 = pl == 0 ? 0.f : (SYM || GEN ? A[0] : f.b);
+        const float G0 = pl == 0 ? 0.f : (GEN ? G[0] : f.g);
+        const float E0 = pl == 0 ? (GEN ? tim_1 : f.tim) * c0 : 0.f;
         const int acc_lane = mine ? (R - 1) / K : -1;
         // the slot of the likelihood sum is warp-uniform: both reads of a pair share it (planner); an idle half defers to the other
         int acc_slot = mine ? (R - 1) % K : -1;
@@ -882,8 +923,8 @@ __global__ void __launch_bounds__(32, flat_min_ctas(K, SYM, LANES)) phmm_flat_f3
         float *const slab = g.snap + (size_t)blockIdx.x * ((MAX_SNAP_SLOTS + 1) * 32 * REGS) + lane * REGS;
         snap_save<K>(st, slab, ZERO_SLOT);  // the pass-start state (all zero), restored at every END that begins a fresh pass
         const bool narrow = LANES == 16 && us.n_segs16 != 0;  // 16 lanes per read: END / snapshot windows of 16 steps
-        flat_dispatch<K, 0, SYM>(acc_slot, st, f, A, C, B0, G0, E0, tab_lane, src_lane, pl, acc_lane, sums + out_base, slab,
-                            g.segments + (narrow ? us.seg16_first : us.seg_first), narrow ? us.n_segs16 : us.n_segs);
+        flat_dispatch<K, 0, MODE>(acc_slot, st, f, A, C, G, Dd, B0, G0, E0, tmi_r, tab_lane, src_lane, pl, acc_lane, sums + out_base, slab,
+                                  g.segments + (narrow ? us.seg16_first : us.seg_first), narrow ? us.n_segs16 : us.n_segs);
     }
 }
 

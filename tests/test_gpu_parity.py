@@ -324,6 +324,35 @@ def test_lane_layout_is_invisible():
         assert np.abs(a[:n] - want[:n]).max() <= TOL
 
 
+def test_half_warp_general_kernel():
+    # per-base gap-open AND gap-continuation qualities (DRAGstr: DragstrPairHMMInputScoreImputator.java:57-66; BI/BD tags): in a
+    # chunk large enough to pair reads, reads of 128-191 bases run the half-warp form of the general kernel (the flat-kernel
+    # family with four coefficient registers per row), longer ones the full-warp kernel.  Against the oracle on a sample of
+    # units, and against the one-read-per-warp layout (small chunks) on every pair.
+    rng = np.random.default_rng(17)
+    for b0, n_units in ((synth.config1_many(48), 3), (synth.config2(200), 4)):
+        n = len(b0.read_bases)
+        r = rng.random(n)
+        gop = np.full(n, 40, np.uint8)
+        gop[r < 0.25] = rng.integers(30, 40, int((r < 0.25).sum()))
+        gop[r < 0.05] = rng.integers(15, 30, int((r < 0.05).sum()))
+        gcp = np.full(n, 10, np.uint8)
+        gcp[r < 0.25] = rng.integers(6, 12, int((r < 0.25).sum()))
+        for ins, dele in ((gop, gop.copy()), (gop, np.minimum(gop + rng.integers(0, 6, n), 60).astype(np.uint8))):
+            b = Batch(b0.read_bases, b0.base_q, ins, dele, gcp, b0.read_off, b0.hap_bases, b0.hap_off, b0.units)
+            assert b.n_reads >= 148 * 16 * 2
+            with GpuPhmm() as paired, GpuPhmm(chunk_cells=400_000_000) as single:
+                p = paired.prepare(b)   # one chunk holding every read
+                a = np.full(b.n_out, np.nan)
+                paired.run_prepared(p, a)
+                paired.release_prepared(p)
+                c = single.compute(b)
+            assert np.all(np.isfinite(a)) and np.abs(a - c).max() <= 1e-5
+            sub = Batch(b.read_bases, b.base_q, ins, dele, gcp, b.read_off, b.hap_bases, b.hap_off, b.units[:n_units])
+            want = oracle_batch(sub)
+            assert np.abs(a[:sub.n_out] - want).max() <= TOL
+
+
 def test_invariants_at_scale(hmm):
     # size-independent properties on a larger slice of configs[1]:
     #  - permutation invariance: shuffling the unit order permutes the outputs, bit for bit
