@@ -14,7 +14,8 @@ A step = one pass of the hot path over one synthetic batch of BASELINE.json conf
   e2e_from_pageable  the same call with ordinary (pageable) host arrays: the library copies them into pinned bounce buffers
            first -- the copy a JVM caller pays when the JNI shim packs heap arrays (gpuphmm_jni.cpp pack())
   read_150bp  the device-resident metric on 1 500 regions of the configs[0] shape (128 reads x 150 bp x 8 haplotypes),
-           flat Q45 gap penalties and PCR-indel-model-like ones -- the read length of configs[0], [2], [3]
+           flat Q45 gap penalties, PCR-indel-model-like ones (ins == del per base) and DRAGstr-like ones (per-base gap-open and
+           gap-continuation: the general kernel) -- the read length of configs[0], [2], [3]
   one_handle  (N > 1, rank 0) ONE gphmm handle over all N devices on the N x regions batch of all ranks: the in-process
            multi-GPU mode a JVM gets (host work queue, one stream set per GPU, no collective)
 `--impl reference` times the CPU restatements with all host threads instead: value = the fp32 AVX-512 port with double redo
@@ -140,12 +141,27 @@ def _pcr_like(b, np, seed=3):
     return Batch(b.read_bases, b.base_q, q, q.copy(), b.gcp, b.read_off, b.hap_bases, b.hap_off, b.units, pinned=True)
 
 
+def _dragstr_like(b, np, seed=4):
+    """per-base gap-open (ins == del) AND gap-continuation qualities from the STR context, as --dragstr-params-path leaves them
+    (DragstrPairHMMInputScoreImputator.java:57-66): the general kernel's input"""
+    from gatk_b200.native import Batch
+    rng = np.random.default_rng(seed)
+    n = len(b.read_bases)
+    r = rng.random(n)
+    gop = np.full(n, 40, np.uint8)
+    gop[r < 0.25] = rng.integers(30, 40, int((r < 0.25).sum())).astype(np.uint8)
+    gop[r < 0.05] = rng.integers(15, 30, int((r < 0.05).sum())).astype(np.uint8)
+    gcp = np.full(n, 10, np.uint8)
+    gcp[r < 0.25] = rng.integers(6, 12, int((r < 0.25).sum())).astype(np.uint8)
+    return Batch(b.read_bases, b.base_q, gop, gop.copy(), gcp, b.read_off, b.hap_bases, b.hap_off, b.units, pinned=True)
+
+
 def measure_read150(hmm, synth, np, n_regions=1500, steps=3):
     """device-resident GCUPS on n_regions regions of the configs[0] shape (128 reads x 150 bp x 8 haplotypes of 200-300 bp)"""
     flat = synth.config1_many(n_regions, pinned=True)
     res = {"workload": "configs[0] shape x %d regions: 128 reads x 150 bp x 8 haplotypes (200-300 bp); inputs resident in HBM, CUDA-event time" % n_regions,
            "cells_per_step": flat.cells(), "unit": "GCUPS"}
-    for name, b in (("flat_q45", flat), ("pcr_model_quals", _pcr_like(flat, np))):
+    for name, b in (("flat_q45", flat), ("pcr_model_quals", _pcr_like(flat, np)), ("dragstr_quals", _dragstr_like(flat, np))):
         out = np.zeros(b.n_out)
         p = hmm.prepare(b)
         for _ in range(2):

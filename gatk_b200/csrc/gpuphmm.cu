@@ -119,17 +119,19 @@ struct PinBuf {
 };
 
 constexpr int N_SLOTS = 3;         // chunks in flight per device: one computing, one finishing (epilogue/D2H), one being staged
-// Task buckets: 0..7 = K = 1..8 rows per lane (32 lanes per read), 8 = striped K=8 (reads of 255+ bases), 9..12 = half-warp
-// buckets (two reads per warp, 16 lanes each): K = 10, 12, 14, 16 rows per lane for reads of 128..159 / ..191 / ..223 / ..254 bases
+// Task buckets: 0..7 = K = 1..8 rows per lane (32 lanes per read), 8 = striped K=8 (reads of 255+ bases), 9..16 = half-warp
+// buckets (two reads per warp, 16 lanes each): K = PAIR_ROWS[p] rows per lane for reads of 64..79 / ..95 / ..111 / ..127 / ..159 / ..191 / ..223 / ..254 bases
 constexpr int FIRST_PAIR_BUCKET = 9;
-constexpr int N_PAIR_BUCKETS = 4;
+constexpr int N_PAIR_BUCKETS = 8;
+constexpr int PAIR_ROWS[N_PAIR_BUCKETS] = {5, 6, 7, 8, 10, 12, 14, 16};  // rows per lane; 16 x rows hold R + 1 (76-, 100- and 150-base reads fill 95 / 90 / 94 % of them)
 constexpr int N_FP32_BUCKETS = FIRST_PAIR_BUCKET + N_PAIR_BUCKETS;
 constexpr int N_CLASSES_MAX = MAX_FLAT_CLASSES + MAX_SYM_CLASSES;
 constexpr int N_AUX = N_FP32_BUCKETS + (8 + N_PAIR_BUCKETS) * N_CLASSES_MAX;  // side streams: general buckets + flat (class, bucket)
 inline bool is_pair_bucket(int k) { return k >= FIRST_PAIR_BUCKET; }
-inline int pair_bucket_rows(int k) { return 10 + 2 * (k - FIRST_PAIR_BUCKET); }
+inline int pair_bucket_rows(int k) { return PAIR_ROWS[k - FIRST_PAIR_BUCKET]; }
 // reads of a half-warp bucket that are not flat-quality run the full-warp general kernel with K = 6, 7, 8, 8 rows per lane
-inline int general_bucket_of(int k) { return !is_pair_bucket(k) ? k : std::min(7, 5 + (k - FIRST_PAIR_BUCKET)); }
+// full-warp kernel (index K - 1) for the general reads of a bucket: 32 K rows hold R + 2
+inline int general_bucket_of(int k) { return !is_pair_bucket(k) ? k : std::min(7, (16 * pair_bucket_rows(k) - 1 + 2 + 31) / 32 - 1); }
 // Longest read that takes the half-warp form (A/B knob).  Measured on B200 (profiles/r02_halfwarp_sweep.txt), batches of
 // equal-length reads: +29 % at 130 bases, +29..38 % at 150..159, +25 % at 175..190, +17 % at 207..222, +14 % at 235..250.
 inline uint32_t half_warp_max_read() {
@@ -137,10 +139,13 @@ inline uint32_t half_warp_max_read() {
     return v;
 }
 inline int pair_bucket_of_read(uint32_t R) {
-    return R < 128 || R > 254 || R > half_warp_max_read() ? -1 : FIRST_PAIR_BUCKET + (R < 160 ? 0 : R < 192 ? 1 : R < 224 ? 2 : 3);
+    if (R < 64 || R > 254 || R > half_warp_max_read()) return -1;
+    int p = 0;
+    while (16u * (uint32_t)PAIR_ROWS[p] < R + 1) ++p;
+    return FIRST_PAIR_BUCKET + p;
 }
 constexpr int N_COUNTERS = 256;    // [0..8] general fp32 buckets, [9] fp64 queue, [10] n_rescue, [11] n_deep, [120] deep cursor,
-                                   // [128 + p] general kernel on half-warp bucket p, [136 + 4*c + p] half-warp flat kernels: class c
+                                   // [128 + p] general kernel on half-warp bucket p, [136 + 8*c + p] half-warp flat kernels: class c
                                    // [16 + 8*c + k] flat-quality kernels: class c, bucket k
 
 // Growable byte buffer without value-initialisation (std::vector<uint8_t>::resize would memset what is overwritten next).
@@ -373,14 +378,18 @@ template <int K, bool SYM> KernelInfo flat16_kernel_info(int n_codes) {
 
 KernelInfo flat16_kernel(int p, bool sym, int n_codes) {
     switch (p) {
-        case 0: return sym ? flat16_kernel_info<10, true>(n_codes) : flat16_kernel_info<10, false>(n_codes);
-        case 1: return sym ? flat16_kernel_info<12, true>(n_codes) : flat16_kernel_info<12, false>(n_codes);
-        case 2: return sym ? flat16_kernel_info<14, true>(n_codes) : flat16_kernel_info<14, false>(n_codes);
+        case 0: return sym ? flat16_kernel_info<5, true>(n_codes) : flat16_kernel_info<5, false>(n_codes);
+        case 1: return sym ? flat16_kernel_info<6, true>(n_codes) : flat16_kernel_info<6, false>(n_codes);
+        case 2: return sym ? flat16_kernel_info<7, true>(n_codes) : flat16_kernel_info<7, false>(n_codes);
+        case 3: return sym ? flat16_kernel_info<8, true>(n_codes) : flat16_kernel_info<8, false>(n_codes);
+        case 4: return sym ? flat16_kernel_info<10, true>(n_codes) : flat16_kernel_info<10, false>(n_codes);
+        case 5: return sym ? flat16_kernel_info<12, true>(n_codes) : flat16_kernel_info<12, false>(n_codes);
+        case 6: return sym ? flat16_kernel_info<14, true>(n_codes) : flat16_kernel_info<14, false>(n_codes);
         default: return sym ? flat16_kernel_info<16, true>(n_codes) : flat16_kernel_info<16, false>(n_codes);
     }
 }
 
-// half-warp form of the general (per-base quality) kernel: reads of 128..191 bases, 10 / 12 rows per lane
+// half-warp form of the general (per-base quality) kernel: 6-16 rows per lane like the flat half-warp kernels
 template <int K> KernelInfo gen16_kernel_info(int n_codes) {
     KernelInfo ki;
     auto fn = phmm_flat_f32_kernel<K, MODE_GEN, 16>;
@@ -393,7 +402,16 @@ template <int K> KernelInfo gen16_kernel_info(int n_codes) {
     return ki;
 }
 KernelInfo gen16_kernel(int p, int n_codes) {
-    return p == 0 ? gen16_kernel_info<10>(n_codes) : p == 1 ? gen16_kernel_info<12>(n_codes) : p == 2 ? gen16_kernel_info<14>(n_codes) : gen16_kernel_info<16>(n_codes);
+    switch (p) {
+        case 0: return gen16_kernel_info<5>(n_codes);
+        case 1: return gen16_kernel_info<6>(n_codes);
+        case 2: return gen16_kernel_info<7>(n_codes);
+        case 3: return gen16_kernel_info<8>(n_codes);
+        case 4: return gen16_kernel_info<10>(n_codes);
+        case 5: return gen16_kernel_info<12>(n_codes);
+        case 6: return gen16_kernel_info<14>(n_codes);
+        default: return gen16_kernel_info<16>(n_codes);
+    }
 }
 
 KernelInfo fp64_kernel(int n_codes) { return kernel_info<double, 4, true>(n_codes); }
@@ -420,7 +438,7 @@ constexpr int FLAT_KEY = 16;      // flat-quality kernel of bucket k < 8 is FLAT
 constexpr int FLAT_F64_KEY = 32;  // phmm_flat_f64_kernel
 constexpr int SYM_KEY = 48;       // symmetric-quality kernel of bucket k < 8 is SYM_KEY + k, of half-warp bucket p SYM_KEY + 8 + p
 constexpr int GEN16_KEY = 80;     // half-warp form of the general kernel for half-warp bucket p < N_GEN16 is GEN16_KEY + p
-constexpr int N_GEN16 = 4;        // ... exists for 10 and 12 rows per lane (four coefficient registers per row)
+constexpr int N_GEN16 = N_PAIR_BUCKETS;        // ... (four coefficient registers per row: 168 registers at 14 / 16 rows per lane)
 inline bool gen16_bucket(int bucket) {
     static const bool off = getenv("GPHMM_NO_GEN16") != nullptr;  // A/B switch: general reads of half-warp buckets on full warps
     static const int n = getenv("GPHMM_N_GEN16") ? atoi(getenv("GPHMM_N_GEN16")) : N_GEN16;
@@ -899,7 +917,7 @@ int launch_chunk(Device &dev, DeviceChunk &dc, const ChunkPlan &c, cudaStream_t 
                     fc.tim = (float)(tIM / a);
                     fc.class_id = (uint32_t)cl;
                     fc.qi = qi; fc.qd = qd; fc.qc = qc;
-                    ka.counter = pair ? counters + 136 + 4 * cl + kp : counters + 16 + 8 * cl + k;
+                    ka.counter = pair ? counters + 136 + 8 * cl + kp : counters + 16 + 8 * cl + k;
                     ka.snap = (float *)((uint8_t *)dc.snap.p + slab_cursor);
                     const KernelInfo &ki = dev.info(flat_key(k, false), c.n_codes);
                     slab_cursor += (size_t)persistent_grid(n, dev.n_sms, ki.ctas_per_sm) * slab_per_cta(k);
@@ -921,7 +939,7 @@ int launch_chunk(Device &dev, DeviceChunk &dc, const ChunkPlan &c, cudaStream_t 
                     fc.class_id = (uint32_t)(MAX_FLAT_CLASSES + cl);
                     fc.qi = 0; fc.qd = 0; fc.qc = qc;
                     const int ci = MAX_FLAT_CLASSES + cl;
-                    ka.counter = pair ? counters + 136 + 4 * ci + kp : counters + 16 + 8 * ci + k;
+                    ka.counter = pair ? counters + 136 + 8 * ci + kp : counters + 16 + 8 * ci + k;
                     ka.snap = (float *)((uint8_t *)dc.snap.p + slab_cursor);
                     const KernelInfo &ki = dev.info(flat_key(k, true), c.n_codes);
                     slab_cursor += (size_t)persistent_grid(n, dev.n_sms, ki.ctas_per_sm) * slab_per_cta(k);

@@ -47,6 +47,7 @@ namespace phmm_dev {
 // cache), with 10 rows per lane (half-warp form, 150-base reads) 4 / 2 gains 2-3 %; the full-warp kernels spill at 4.
 __host__ __device__ constexpr int flat_unroll(int K) { return K == 10 ? 4 : 2; }
 __host__ __device__ constexpr int flat_chk_unroll(int K) { return K == 10 ? 2 : 1; }
+// (the full-warp kernels use K <= 8 and spill at 4; the half-warp kernels of 6 and 8 rows per lane are separate instantiations)
 constexpr uint32_t CODE_END = 0;   // column after the last base of a haplotype
 constexpr uint32_t CODE_NULL = 1;  // outside the stream (pipeline fill / drain)
 constexpr uint32_t CODE_FIRST_BASE = 2;  // A C G T = 2..5, further byte values (N included) 6..
@@ -770,7 +771,7 @@ __device__ __forceinline__ void flat_dispatch(int slot, FastState<K> &st, const 
 }
 
 // 28 one-warp CTAs per SM (the shared-memory limit of the K=8 prior table) need <= 73 registers per thread.
-// LANES = 16 (half-warp form, reads of 128..254 bases): the warp runs TWO reads of the same unit side by side, one per
+// LANES = 16 (half-warp form, reads of 64..254 bases): the warp runs TWO reads of the same unit side by side, one per
 // 16-lane half, K <= 16 rows per lane.  Both halves sweep the same haplotype stream with the same schedule, so every
 // per-step cost that does not depend on the number of rows (hand-off shuffles, column-code load, address arithmetic,
 // loop control) is paid once per 2 x 16 x K cells instead of once per 32 x K' cells with K' = K/2: 150-base reads run 10
@@ -778,7 +779,9 @@ __device__ __forceinline__ void flat_dispatch(int slot, FastState<K> &st, const 
 // register slot (R - 1) mod K, which keeps the slot of the likelihood sum a template parameter; a read without a partner
 // leaves its half idle (all rows pads).
 __host__ __device__ constexpr int flat_min_ctas(int K, int MODE, int LANES) {
-    return LANES == 32 ? (MODE != MODE_FLAT ? 22 : 28) : (MODE == MODE_GEN ? (K > 12 ? 10 : 14) : (K > 12 ? 14 : (MODE != MODE_FLAT ? 16 : 18)));
+    return LANES == 32 ? (MODE != MODE_FLAT ? 22 : 28)
+         : K <= 8 ? (MODE == MODE_GEN ? 18 : MODE == MODE_SYM ? 22 : 28)  // half-warp form for reads of 64..127 bases
+         : (MODE == MODE_GEN ? (K > 12 ? 10 : 14) : (K > 12 ? 14 : (MODE != MODE_FLAT ? 16 : 18)));
 }
 
 template <int K, int MODE, int LANES = 32>

@@ -35,11 +35,12 @@ print("%.0f" % (s["cells"] / s["device_ms"] / 1e6))
 
 if __name__ == "__main__":
     print("read length | full warp (GCUPS) | half warp (GCUPS) | rows per lane full / half")
-    for L in (130, 150, 159, 175, 190, 207, 222, 235, 250):
+    lengths = [int(x) for x in sys.argv[1:]] or [70, 76, 90, 100, 101, 125, 130, 150, 159, 175, 190, 207, 222, 235, 250]
+    for L in lengths:
         res = []
         for mx in ("0", "254"):
             env = dict(os.environ, GPHMM_HALFWARP_MAX_READ=mx)
             r = subprocess.run([sys.executable, "-c", CHILD, str(L)], env=env, capture_output=True, text=True)
             res.append(r.stdout.strip() or ("ERR " + r.stderr[-200:]))
-        k16 = 10 if L < 160 else 12 if L < 192 else 14 if L < 224 else 16
+        k16 = next(k for k in (5, 6, 7, 8, 10, 12, 14, 16) if 16 * k >= L + 1)
         print("%d | %s | %s | %d / %d" % (L, res[0], res[1], (L + 1) // 32 + 1, k16), flush=True)
