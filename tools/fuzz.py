@@ -33,6 +33,11 @@ def requalify(b, rng, mode):
             t = [(45, 45, 10), (40, 42, 10), (30, 30, 8), (45, 40, 20), (35, 45, 12), (20, 25, 6)][int(rng.integers(0, 6))]
             s = slice(b.read_off[r], b.read_off[r + 1])
             ins[s], dele[s], gcp[s] = t
+    elif mode == "dragstr":    # per-base gap-open and gap-continuation qualities (general kernel; half-warp form: MODE_GEN)
+        r = rng.random(n)
+        ins = np.where(r < 0.3, rng.integers(12, 41, n), 40).astype(np.uint8)
+        dele = ins.copy() if rng.random() < 0.5 else np.minimum(ins + rng.integers(0, 8, n), 60).astype(np.uint8)
+        gcp = np.where(r < 0.3, rng.integers(4, 14, n), 10).astype(np.uint8)
     elif mode == "extreme":    # the whole legal range
         ins = rng.integers(0, 128, n).astype(np.uint8)
         dele = rng.integers(0, 128, n).astype(np.uint8)
@@ -71,8 +76,8 @@ try:
         elif shape == 2:
             b = synth.random_batch(seed, n_units=int(rng.integers(1, 30)), max_reads=4, max_haps=3, read_len=(1, 40), hap_len=(1, 60))
         else:
-            b = synth.random_batch(seed, n_units=3, max_reads=40, max_haps=16, read_len=(100, 254), hap_len=(250, 500))
-        mode = ["keep", "sym", "flatmix", "extreme"][int(rng.integers(0, 4))]
+            b = synth.random_batch(seed, n_units=3, max_reads=40, max_haps=16, read_len=(int(rng.choice([50, 64, 100])), 254), hap_len=(250, 500))
+        mode = ["keep", "sym", "flatmix", "extreme", "dragstr"][int(rng.integers(0, 5))]
         b = requalify(b, rng, mode)
         if rng.random() < 0.2:   # exotic haplotype bytes
             hb = b.hap_bases.copy()
@@ -102,7 +107,9 @@ try:
                 # wild qualities may overflow fp32 in one layout's neighbourhood only (prefix-sharing state): those pairs
                 # come back from the fp64 redo; anything else must be bit-identical
                 diff = rep != np.broadcast_to(first, rep.shape)
-                assert mode in ("extreme", "sym") and np.abs(rep - first)[diff].max() < 1e-5, "seed %d %s half-warp layout differs" % (seed, mode)
+                # general reads -- "dragstr", "extreme", and the classes of "flatmix" beyond the four flat classes a chunk keeps --
+                # run different kernels in the two layouts: the same recurrence, the sum taken differently
+                assert mode != "keep" and np.abs(rep - first)[diff].max() < 1e-5, "seed %d %s half-warp layout differs" % (seed, mode)
             check(out[:b.n_out], want, "seed %d %s half-warp" % (seed, mode))
             n_paired += 1
         if mode != "extreme":
