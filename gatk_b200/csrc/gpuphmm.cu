@@ -119,19 +119,26 @@ struct PinBuf {
 };
 
 constexpr int N_SLOTS = 3;         // chunks in flight per device: one computing, one finishing (epilogue/D2H), one being staged
-// Task buckets: 0..7 = K = 1..8 rows per lane (32 lanes per read), 8 = striped K=8 (reads of 255+ bases), 9..16 = half-warp
-// buckets (two reads per warp, 16 lanes each): K = PAIR_ROWS[p] rows per lane for reads of 64..79 / ..95 / ..111 / ..127 / ..159 / ..191 / ..223 / ..254 bases
+// Task buckets: 0..7 = K = 1..8 rows per lane (32 lanes per read), 8 = striped K=8 (reads of 255+ bases), then the buckets
+// that put several reads of a unit on one warp: 9..16 = half-warp buckets (two reads, 16 lanes each) for reads of 64..79 /
+// ..95 / ..111 / ..127 / ..159 / ..191 / ..223 / ..254 bases, 17..20 = quarter-warp buckets (four reads of EQUAL length, 8 lanes
+// each) for reads of up to 79 / 103 / 127 / 159 bases.  MULTI_ROWS = rows per lane (lanes x rows hold R + 1).
 constexpr int FIRST_PAIR_BUCKET = 9;
 constexpr int N_PAIR_BUCKETS = 8;
-constexpr int PAIR_ROWS[N_PAIR_BUCKETS] = {5, 6, 7, 8, 10, 12, 14, 16};  // rows per lane; 16 x rows hold R + 1 (76-, 100- and 150-base reads fill 95 / 90 / 94 % of them)
-constexpr int N_FP32_BUCKETS = FIRST_PAIR_BUCKET + N_PAIR_BUCKETS;
+constexpr int N_QUAD_BUCKETS = 4;
+constexpr int N_MULTI_BUCKETS = N_PAIR_BUCKETS + N_QUAD_BUCKETS;
+constexpr int FIRST_QUAD_BUCKET = FIRST_PAIR_BUCKET + N_PAIR_BUCKETS;
+constexpr int MULTI_ROWS[N_MULTI_BUCKETS] = {5, 6, 7, 8, 10, 12, 14, 16, /* quarter-warp */ 10, 13, 16, 20};
+// half-warp bucket whose general-kernel form (MODE_GEN) takes the non-flat reads of a quarter-warp bucket, two by two
+constexpr int QUAD_GEN_PAIR[N_QUAD_BUCKETS] = {0, 2, 3, 4};  // 5, 7, 8, 10 rows per lane: 16 x rows hold the bucket's longest read + 1
+constexpr int N_FP32_BUCKETS = FIRST_PAIR_BUCKET + N_MULTI_BUCKETS;
 constexpr int N_CLASSES_MAX = MAX_FLAT_CLASSES + MAX_SYM_CLASSES;
-constexpr int N_AUX = N_FP32_BUCKETS + (8 + N_PAIR_BUCKETS) * N_CLASSES_MAX;  // side streams: general buckets + flat (class, bucket)
-inline bool is_pair_bucket(int k) { return k >= FIRST_PAIR_BUCKET; }
-inline int pair_bucket_rows(int k) { return PAIR_ROWS[k - FIRST_PAIR_BUCKET]; }
-// reads of a half-warp bucket that are not flat-quality run the full-warp general kernel with K = 6, 7, 8, 8 rows per lane
-// full-warp kernel (index K - 1) for the general reads of a bucket: 32 K rows hold R + 2
-inline int general_bucket_of(int k) { return !is_pair_bucket(k) ? k : std::min(7, (16 * pair_bucket_rows(k) - 1 + 2 + 31) / 32 - 1); }
+constexpr int N_AUX = N_FP32_BUCKETS + (8 + N_MULTI_BUCKETS) * N_CLASSES_MAX;  // side streams: general buckets + flat (class, bucket)
+inline bool is_pair_bucket(int k) { return k >= FIRST_PAIR_BUCKET; }   // any bucket with several reads per warp
+inline bool is_quad_bucket(int k) { return k >= FIRST_QUAD_BUCKET; }
+inline int pair_bucket_rows(int k) { return MULTI_ROWS[k - FIRST_PAIR_BUCKET]; }
+// full-warp kernel (index K - 1) for the general reads of a half-warp bucket when MODE_GEN is switched off: 32 K rows hold R + 2
+inline int general_bucket_of(int k) { return !is_pair_bucket(k) ? k : std::min(7, ((is_quad_bucket(k) ? 8 : 16) * pair_bucket_rows(k) - 1 + 2 + 31) / 32 - 1); }
 // Longest read that takes the half-warp form (A/B knob).  Measured on B200 (profiles/r02_halfwarp_sweep.txt), batches of
 // equal-length reads: +29 % at 130 bases, +29..38 % at 150..159, +25 % at 175..190, +17 % at 207..222, +14 % at 235..250.
 inline uint32_t half_warp_max_read() {
@@ -141,11 +148,19 @@ inline uint32_t half_warp_max_read() {
 inline int pair_bucket_of_read(uint32_t R) {
     if (R < 64 || R > 254 || R > half_warp_max_read()) return -1;
     int p = 0;
-    while (16u * (uint32_t)PAIR_ROWS[p] < R + 1) ++p;
+    while (16u * (uint32_t)MULTI_ROWS[p] < R + 1) ++p;
     return FIRST_PAIR_BUCKET + p;
 }
-constexpr int N_COUNTERS = 256;    // [0..8] general fp32 buckets, [9] fp64 queue, [10] n_rescue, [11] n_deep, [120] deep cursor,
-                                   // [128 + p] general kernel on half-warp bucket p, [136 + 8*c + p] half-warp flat kernels: class c
+// Quarter-warp bucket of a read length (four reads of this length on one warp), or -1.  GPHMM_NO_QUAD=1: A/B switch.
+inline int quad_bucket_of_read(uint32_t R) {
+    static const bool off = getenv("GPHMM_NO_QUAD") != nullptr || getenv("GPHMM_NO_GEN16") != nullptr;
+    if (off || R < 64 || R > 159 || R > half_warp_max_read()) return -1;
+    int q = 0;
+    while (8u * (uint32_t)MULTI_ROWS[N_PAIR_BUCKETS + q] < R + 1) ++q;
+    return FIRST_QUAD_BUCKET + q;
+}
+constexpr int N_COUNTERS = 512;    // [0..8] general fp32 buckets, [9] fp64 queue, [10] n_rescue, [11] n_deep, [120] deep cursor,
+                                   // [128 + p] general kernel on half- / quarter-warp bucket p, [160 + 16*c + p] their flat kernels: class c
                                    // [16 + 8*c + k] flat-quality kernels: class c, bucket k
 
 // Growable byte buffer without value-initialisation (std::vector<uint8_t>::resize would memset what is overwritten next).
@@ -376,8 +391,24 @@ template <int K, bool SYM> KernelInfo flat16_kernel_info(int n_codes) {
     return ki;
 }
 
-KernelInfo flat16_kernel(int p, bool sym, int n_codes) {
+template <int K, bool SYM> KernelInfo flat8_kernel_info(int n_codes) {  // quarter-warp form: four reads per warp
+    KernelInfo ki;
+    auto fn = phmm_flat_f32_kernel<K, SYM ? MODE_SYM : MODE_FLAT, 8>;
+    ki.fn = (const void *)fn;
+    ki.smem = prior_table_bytes<float, K>(n_codes);
+    raise_dyn_smem((const void *)fn, ki.smem);
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ki.ctas_per_sm, fn, 32, ki.smem));
+    if (ki.ctas_per_sm < 1) throw Error(GPHMM_ERR_ALPHABET, "prior table does not fit in shared memory");
+    reserve_headroom(ki, (const void *)fn);
+    return ki;
+}
+
+KernelInfo flat16_kernel(int p, bool sym, int n_codes) {  // p: index among the half- (0..7) and quarter-warp (8..11) buckets
     switch (p) {
+        case 8: return sym ? flat8_kernel_info<10, true>(n_codes) : flat8_kernel_info<10, false>(n_codes);
+        case 9: return sym ? flat8_kernel_info<13, true>(n_codes) : flat8_kernel_info<13, false>(n_codes);
+        case 10: return sym ? flat8_kernel_info<16, true>(n_codes) : flat8_kernel_info<16, false>(n_codes);
+        case 11: return sym ? flat8_kernel_info<20, true>(n_codes) : flat8_kernel_info<20, false>(n_codes);
         case 0: return sym ? flat16_kernel_info<5, true>(n_codes) : flat16_kernel_info<5, false>(n_codes);
         case 1: return sym ? flat16_kernel_info<6, true>(n_codes) : flat16_kernel_info<6, false>(n_codes);
         case 2: return sym ? flat16_kernel_info<7, true>(n_codes) : flat16_kernel_info<7, false>(n_codes);
@@ -402,6 +433,7 @@ template <int K> KernelInfo gen16_kernel_info(int n_codes) {
     return ki;
 }
 KernelInfo gen16_kernel(int p, int n_codes) {
+    if (p >= N_PAIR_BUCKETS) p = QUAD_GEN_PAIR[p - N_PAIR_BUCKETS];  // quarter-warp tasks: the half-warp kernel takes their reads two by two
     switch (p) {
         case 0: return gen16_kernel_info<5>(n_codes);
         case 1: return gen16_kernel_info<6>(n_codes);
@@ -433,20 +465,22 @@ struct Stats {
 };
 
 // Device::info keys: 0..8 = general fp32 kernel of bucket k, then
+// Device::info keys: 0..8 = general fp32 kernel of bucket k, then
 constexpr int FP64_KEY = 9;       // phmm_forward_kernel<double, 4, striped>
-constexpr int FLAT_KEY = 16;      // flat-quality kernel of bucket k < 8 is FLAT_KEY + k, of half-warp bucket p FLAT_KEY + 8 + p
 constexpr int FLAT_F64_KEY = 32;  // phmm_flat_f64_kernel
-constexpr int SYM_KEY = 48;       // symmetric-quality kernel of bucket k < 8 is SYM_KEY + k, of half-warp bucket p SYM_KEY + 8 + p
-constexpr int GEN16_KEY = 80;     // half-warp form of the general kernel for half-warp bucket p < N_GEN16 is GEN16_KEY + p
-constexpr int N_GEN16 = N_PAIR_BUCKETS;        // ... (four coefficient registers per row: 168 registers at 14 / 16 rows per lane)
+constexpr int FLAT_KEY = 100;     // flat-quality kernel of bucket k < 8 is FLAT_KEY + k, of half- / quarter-warp bucket p FLAT_KEY + 8 + p
+constexpr int SYM_KEY = 130;      // symmetric-quality kernel: SYM_KEY + k, SYM_KEY + 8 + p
+constexpr int GEN16_KEY = 160;    // half-warp form of the general kernel for half- / quarter-warp bucket p is GEN16_KEY + p
 inline bool gen16_bucket(int bucket) {
     static const bool off = getenv("GPHMM_NO_GEN16") != nullptr;  // A/B switch: general reads of half-warp buckets on full warps
-    static const int n = getenv("GPHMM_N_GEN16") ? atoi(getenv("GPHMM_N_GEN16")) : N_GEN16;
-    return !off && is_pair_bucket(bucket) && bucket - FIRST_PAIR_BUCKET < n;
+    return !off && is_pair_bucket(bucket);
 }
 // key of the kernel that takes the general (per-base quality) reads of a bucket, and the rows per lane its snapshot slab is sized for
 inline int general_key(int bucket) { return gen16_bucket(bucket) ? GEN16_KEY + bucket - FIRST_PAIR_BUCKET : general_bucket_of(bucket); }
-inline int general_slab_bucket(int bucket) { return gen16_bucket(bucket) ? bucket : 0; }
+inline int general_rows(int bucket) {
+    if (!gen16_bucket(bucket)) return 8;
+    return is_quad_bucket(bucket) ? MULTI_ROWS[QUAD_GEN_PAIR[bucket - FIRST_QUAD_BUCKET]] : pair_bucket_rows(bucket);
+}
 inline int flat_key(int bucket, bool sym) { return (sym ? SYM_KEY : FLAT_KEY) + (is_pair_bucket(bucket) ? 8 + bucket - FIRST_PAIR_BUCKET : bucket); }
 inline size_t slab_per_cta(int bucket) { return snap_slab_bytes(is_pair_bucket(bucket) ? pair_bucket_rows(bucket) : 8); }
 
@@ -464,13 +498,13 @@ struct Device {
         auto it = kinfo.find(key);
         if (it == kinfo.end())
             it = kinfo.emplace(key, bucket >= GEN16_KEY ? gen16_kernel(bucket - GEN16_KEY, n_codes)
-                                    : bucket < FP64_KEY ? fp32_kernel(bucket, n_codes)
-                                    : bucket == FP64_KEY ? fp64_kernel(n_codes)
-                                    : bucket == FLAT_F64_KEY ? flat_fp64_kernel(n_codes)
                                     : bucket >= SYM_KEY + 8 ? flat16_kernel(bucket - SYM_KEY - 8, true, n_codes)
                                     : bucket >= SYM_KEY ? sym_kernel(bucket - SYM_KEY, n_codes)
                                     : bucket >= FLAT_KEY + 8 ? flat16_kernel(bucket - FLAT_KEY - 8, false, n_codes)
-                                    : flat_kernel(bucket - FLAT_KEY, n_codes)).first;
+                                    : bucket >= FLAT_KEY ? flat_kernel(bucket - FLAT_KEY, n_codes)
+                                    : bucket == FLAT_F64_KEY ? flat_fp64_kernel(n_codes)
+                                    : bucket == FP64_KEY ? fp64_kernel(n_codes)
+                                    : fp32_kernel(bucket, n_codes)).first;
         return it->second;
     }
     cudaStream_t streams[N_SLOTS] = {nullptr};
@@ -859,7 +893,7 @@ int launch_chunk(Device &dev, DeviceChunk &dc, const ChunkPlan &c, cudaStream_t 
             for (int k = 0; k < N_FP32_BUCKETS; ++k) {
                 const uint32_t n = c.bucket_begin[k + 1] - c.bucket_begin[k];
                 if (!n || k == 8) continue;
-                need += (size_t)persistent_grid(n, dev.n_sms, dev.info(general_key(k), c.n_codes).ctas_per_sm) * slab_per_cta(general_slab_bucket(k));
+                need += (size_t)persistent_grid(n, dev.n_sms, dev.info(general_key(k), c.n_codes).ctas_per_sm) * snap_slab_bytes(general_rows(k));
                 for (int cl = 0; cl < c.n_classes; ++cl)
                     need += (size_t)persistent_grid(n, dev.n_sms, dev.info(flat_key(k, false), c.n_codes).ctas_per_sm) * slab_per_cta(k);
                 for (int cl = 0; cl < c.n_sym; ++cl)
@@ -897,7 +931,7 @@ int launch_chunk(Device &dev, DeviceChunk &dc, const ChunkPlan &c, cudaStream_t 
             ka.sums = work + dc.off_sums;
             ka.bnd = k == 8 ? dc.bnd.p : nullptr;
             ka.bnd_stride = k == 8 ? c.max_stream_len : 0;
-            ka.pair_tasks = pair ? 1 : 0;
+            ka.pair_tasks = is_quad_bucket(k) ? 2 : (pair ? 1 : 0);
             if (k != 8) {
                 for (int cl = 0; cl < c.n_classes; ++cl) {
                     if (!has_work(k, cl)) continue;
@@ -917,12 +951,12 @@ int launch_chunk(Device &dev, DeviceChunk &dc, const ChunkPlan &c, cudaStream_t 
                     fc.tim = (float)(tIM / a);
                     fc.class_id = (uint32_t)cl;
                     fc.qi = qi; fc.qd = qd; fc.qc = qc;
-                    ka.counter = pair ? counters + 136 + 8 * cl + kp : counters + 16 + 8 * cl + k;
+                    ka.counter = pair ? counters + 160 + 16 * cl + kp : counters + 16 + 8 * cl + k;
                     ka.snap = (float *)((uint8_t *)dc.snap.p + slab_cursor);
                     const KernelInfo &ki = dev.info(flat_key(k, false), c.n_codes);
                     slab_cursor += (size_t)persistent_grid(n, dev.n_sms, ki.ctas_per_sm) * slab_per_cta(k);
                     void *args[] = {&ka, &fc};
-                    launch_on(ki, n, pair ? N_FP32_BUCKETS + 8 * N_CLASSES_MAX + N_PAIR_BUCKETS * cl + kp : N_FP32_BUCKETS + 8 * cl + k, args);
+                    launch_on(ki, n, pair ? N_FP32_BUCKETS + 8 * N_CLASSES_MAX + N_MULTI_BUCKETS * cl + kp : N_FP32_BUCKETS + 8 * cl + k, args);
                 }
                 for (int cl = 0; cl < c.n_sym; ++cl) {
                     if (!has_work(k, MAX_FLAT_CLASSES + cl)) continue;
@@ -939,12 +973,12 @@ int launch_chunk(Device &dev, DeviceChunk &dc, const ChunkPlan &c, cudaStream_t 
                     fc.class_id = (uint32_t)(MAX_FLAT_CLASSES + cl);
                     fc.qi = 0; fc.qd = 0; fc.qc = qc;
                     const int ci = MAX_FLAT_CLASSES + cl;
-                    ka.counter = pair ? counters + 136 + 8 * ci + kp : counters + 16 + 8 * ci + k;
+                    ka.counter = pair ? counters + 160 + 16 * ci + kp : counters + 16 + 8 * ci + k;
                     ka.snap = (float *)((uint8_t *)dc.snap.p + slab_cursor);
                     const KernelInfo &ki = dev.info(flat_key(k, true), c.n_codes);
                     slab_cursor += (size_t)persistent_grid(n, dev.n_sms, ki.ctas_per_sm) * slab_per_cta(k);
                     void *args[] = {&ka, &fc};
-                    launch_on(ki, n, pair ? N_FP32_BUCKETS + 8 * N_CLASSES_MAX + N_PAIR_BUCKETS * ci + kp : N_FP32_BUCKETS + 8 * ci + k, args);
+                    launch_on(ki, n, pair ? N_FP32_BUCKETS + 8 * N_CLASSES_MAX + N_MULTI_BUCKETS * ci + kp : N_FP32_BUCKETS + 8 * ci + k, args);
                 }
             }
             if (!has_work(k, MAX_FLAT_CLASSES + MAX_SYM_CLASSES)) continue;
@@ -952,7 +986,7 @@ int launch_chunk(Device &dev, DeviceChunk &dc, const ChunkPlan &c, cudaStream_t 
             const KernelInfo &kg = dev.info(general_key(k), c.n_codes);
             if (k != 8) {
                 ka.snap = (float *)((uint8_t *)dc.snap.p + slab_cursor);
-                slab_cursor += (size_t)persistent_grid(n, dev.n_sms, kg.ctas_per_sm) * slab_per_cta(general_slab_bucket(k));
+                slab_cursor += (size_t)persistent_grid(n, dev.n_sms, kg.ctas_per_sm) * snap_slab_bytes(general_rows(k));
             }
             FlatCoef gc;  // half-warp form of the general kernel: the flat-kernel family with every coefficient per row
             memset(&gc, 0, sizeof gc);

@@ -154,7 +154,7 @@ struct SharingScratch {
 
 UnitSched plan_unit_sharing(const gphmm_batch *b, const gphmm_unit &un, uint32_t hap_first_local, bool share, ChunkPlan &c,
                             int64_t sum_read_len, const std::vector<int> &full_order, int g_first, int g_count, SharingScratch &ws,
-                            bool half_warp_schedule = false) {
+                            int narrow_schedules = 0) {  // 1: also the 16-step-window schedule, 2: the 16- and the 8-step-window ones
     constexpr uint32_t SPACING = 32;
     static const uint32_t NEAR_DEPTHS = getenv("GPHMM_NEAR_DEPTHS") ? (uint32_t)std::max(1, atoi(getenv("GPHMM_NEAR_DEPTHS"))) : 96u;  // how far below the shared depth to look
     static const uint32_t MIN_DEPTH = getenv("GPHMM_MIN_DEPTH") ? (uint32_t)std::max(32, atoi(getenv("GPHMM_MIN_DEPTH"))) : 32u;  // tuning knob
@@ -310,10 +310,15 @@ UnitSched plan_unit_sharing(const gphmm_batch *b, const gphmm_unit &un, uint32_t
     };
     build_schedule(32);
     us.n_segs = (uint32_t)c.segments.size() - us.seg_first;
-    if (half_warp_schedule) {  // the same passes and snapshots with 16-step windows (the last window ends 16 steps earlier)
+    if (narrow_schedules >= 1) {  // the same passes and snapshots with 16-step windows (the last window ends 16 steps earlier)
         us.seg16_first = (uint32_t)c.segments.size();
         build_schedule(16);
         us.n_segs16 = (uint32_t)c.segments.size() - us.seg16_first;
+    }
+    if (narrow_schedules >= 2) {  // quarter-warp tasks: 8-step windows
+        us.seg8_first = (uint32_t)c.segments.size();
+        build_schedule(8);
+        us.n_segs8 = (uint32_t)c.segments.size() - us.seg8_first;
     }
     return us;
 }
@@ -464,6 +469,8 @@ void plan_chunk(const gphmm_batch *b, int64_t u0, int64_t u1, bool force_fp64, b
     SharingScratch scratch;
     std::vector<int> order;
     std::vector<uint64_t> pair_reads[N_PAIR_BUCKETS];  // per half-warp bucket: (slot of the last row << 32) | unit-local read index
+    std::vector<uint64_t> quad_cand;                   // (read length << 32) | unit-local read index
+    std::vector<uint8_t> in_quad;
     uint32_t bucket_count[N_FP32_BUCKETS] = {0};
     for (int64_t u = u0; u < u1; ++u) {
         const gphmm_unit &un = b->units[u];
@@ -520,15 +527,60 @@ void plan_chunk(const gphmm_batch *b, int64_t u0, int64_t u1, bool force_fp64, b
         }
         const int n_groups = force_fp64 ? 1 : (int)std::max<int64_t>(1, std::min<int64_t>(want_groups, nh));
         const uint32_t sched_first = (uint32_t)c.unit_sched.size();
+        // quarter-warp tasks: four (or three) reads of the same length, up to 159 bases, on one warp
+        quad_cand.clear();
+        bool any_quad = false;
+        if (pair_reads_ok && nh) {
+            for (uint32_t r = 0; r < nr; ++r) {
+                const uint32_t R = c.read_off[d.read_first + r + 1] - c.read_off[d.read_first + r];
+                if (quad_bucket_of_read(R) >= 0) quad_cand.push_back(((uint64_t)R << 32) | r);
+            }
+            std::sort(quad_cand.begin(), quad_cand.end());
+            for (size_t i = 0; i + 2 < quad_cand.size() && !any_quad; ++i) any_quad = (quad_cand[i] >> 32) == (quad_cand[i + 2] >> 32);
+        }
         {
             sorted_hap_order(b, un, share && !force_fp64, order);
             for (int gi = 0; gi < n_groups; ++gi) {
                 const int g0 = (int)((int64_t)nh * gi / n_groups), g1 = (int)((int64_t)nh * (gi + 1) / n_groups);
-                c.unit_sched.push_back(plan_unit_sharing(b, un, d.hap_first, share && !force_fp64, c, fast_read_len, order, g0, g1 - g0, scratch, pair_reads_ok));
+                c.unit_sched.push_back(plan_unit_sharing(b, un, d.hap_first, share && !force_fp64, c, fast_read_len, order, g0, g1 - g0, scratch,
+                                                         pair_reads_ok ? (any_quad ? 2 : 1) : 0));
             }
         }
         if (nh == 0) continue;
         for (auto &v : pair_reads) v.clear();
+        in_quad.assign(nr, 0);
+        for (size_t i = 0; any_quad && i < quad_cand.size();) {
+            size_t j = i;
+            while (j < quad_cand.size() && (quad_cand[j] >> 32) == (quad_cand[i] >> 32)) ++j;
+            const uint32_t R = (uint32_t)(quad_cand[i] >> 32);
+            const int qb = quad_bucket_of_read(R);
+            // groups of four; a remainder of three still beats a pair plus a single (two or one left over: the half-warp path)
+            for (; j - i >= 3; i += std::min<size_t>(4, j - i)) {
+                const size_t m = std::min<size_t>(4, j - i);
+                uint32_t rr[4] = {NO_READ, NO_READ, NO_READ, NO_READ};
+                for (size_t q = 0; q < m; ++q) { rr[q] = d.read_first + (uint32_t)quad_cand[i + q]; in_quad[(uint32_t)quad_cand[i + q]] = 1; }
+                Task t;
+                t.read = rr[0]; t.stream_off = rr[1]; t.n_haps = rr[2]; t.hap_first = rr[3];
+                t.out_base = d.out_base - d.read_first * nh;  // sums of read r (chunk-local) start at out_base + r * nh (mod 2^32)
+                t.stream_len = nh;
+                t.c0_exp = d.c0_exp; t.unit = sched_first;
+                raw.push_back(t);
+                bucket_of.push_back((uint8_t)qb);
+                ++bucket_count[qb];
+                for (size_t q = 0; q < m; ++q) c.cells += (int64_t)R * sum_h;
+                if (!c.host_class.empty()) {  // reads classified on the host: which kernels find work in this bucket
+                    int seen[4], n_seen = 0;
+                    for (size_t q = 0; q < m; ++q) {
+                        const uint8_t cq = c.host_class[rr[q]];
+                        const int ci = cq == CLASS_GENERAL ? MAX_FLAT_CLASSES + MAX_SYM_CLASSES : cq;
+                        bool dup = false;
+                        for (int w = 0; w < n_seen; ++w) dup = dup || seen[w] == ci;
+                        if (!dup) { seen[n_seen++] = ci; ++c.class_count[qb][ci]; }
+                    }
+                }
+            }
+            i = j;
+        }
         auto emit = [&](Task &t, uint8_t bucket, int n_t, uint32_t rl_a, uint32_t rl_b) {
             for (int gi = 0; gi < n_t; ++gi) {
                 t.unit = sched_first + (uint32_t)gi;
@@ -556,6 +608,7 @@ void plan_chunk(const gphmm_batch *b, int64_t u0, int64_t u1, bool force_fp64, b
             emit(t, bucket, bucket < 8 && !force_fp64 ? n_groups : 1, d.read_first + r, NO_READ);
         };
         for (uint32_t r = 0; r < nr; ++r) {
+            if (in_quad[r]) continue;  // on a quarter-warp task
             const uint32_t rl = d.read_first + r;
             const uint32_t R = c.read_off[rl + 1] - c.read_off[rl];
             c.cells += (int64_t)R * sum_h;

@@ -101,6 +101,7 @@ struct UnitSched {
     uint32_t seg_first, n_segs;     // into segments
     uint32_t sstream_off;           // first column of the unit's shared (prefix-compressed) stream
     uint32_t seg16_first, n_segs16; // the same schedule with 16-step windows (half-warp kernels); n_segs16 = 0: not planned
+    uint32_t seg8_first, n_segs8;   // ... with 8-step windows (quarter-warp kernels)
     uint32_t pad2;
 };
 constexpr int MAX_SNAP_SLOTS = 8;      // + 1 slot per CTA for the pass-start state
@@ -131,7 +132,9 @@ struct KernelArgs {
     float *snap;                  // snapshot slab: per CTA MAX_SNAP_SLOTS x SNAP_REGS x 32 floats
     int32_t n_codes;
     int32_t tristate_off;
-    int32_t pair_tasks;            // tasks of a half-warp bucket: a second read in stream_off (NO_READ = none), its out_base in stream_len
+    int32_t pair_tasks;            // 1: tasks of a half-warp bucket: a second read in stream_off (NO_READ = none), its out_base in stream_len
+                                   // 2: tasks of a quarter-warp bucket: reads in read, stream_off, n_haps, hap_first (NO_READ = none), the sums of
+                                   //    read r start at out_base + r * stream_len (stream_len = haplotypes of the unit, arithmetic mod 2^32)
     uint8_t code_byte[MAX_CODES];  // code -> haplotype byte value
 };
 constexpr uint32_t NO_READ = 0xffffffffu;
@@ -780,6 +783,7 @@ __device__ __forceinline__ void flat_dispatch(int slot, FastState<K> &st, const 
 // leaves its half idle (all rows pads).
 __host__ __device__ constexpr int flat_min_ctas(int K, int MODE, int LANES) {
     return LANES == 32 ? (MODE != MODE_FLAT ? 22 : 28)
+         : LANES == 8 ? (K <= 10 ? (MODE != MODE_FLAT ? 16 : 18) : K <= 16 ? 14 : (MODE != MODE_FLAT ? 10 : 12))  // quarter-warp form
          : K <= 8 ? (MODE == MODE_GEN ? 18 : MODE == MODE_SYM ? 22 : 28)  // half-warp form for reads of 64..127 bases
          : (MODE == MODE_GEN ? (K > 12 ? 10 : 14) : (K > 12 ? 14 : (MODE != MODE_FLAT ? 16 : 18)));
 }
@@ -798,6 +802,9 @@ __global__ void __launch_bounds__(32, flat_min_ctas(K, MODE, LANES)) phmm_flat_f
     if (LANES == 16) {
         asm volatile("and.b32 %0, %1, 15;" : "=r"(pl) : "r"(lane));
         asm volatile("{ .reg .u32 t, u; add.u32 t, %1, 15; and.b32 t, t, 15; and.b32 u, %1, 16; or.b32 %0, t, u; }" : "=r"(src_lane) : "r"(lane));
+    } else if (LANES == 8) {
+        asm volatile("and.b32 %0, %1, 7;" : "=r"(pl) : "r"(lane));
+        asm volatile("{ .reg .u32 t, u; add.u32 t, %1, 7; and.b32 t, t, 7; and.b32 u, %1, 24; or.b32 %0, t, u; }" : "=r"(src_lane) : "r"(lane));
     } else {
         asm volatile("mov.u32 %0, %1;" : "=r"(pl) : "r"(lane));
         asm volatile("{ .reg .u32 t; add.u32 t, %1, 31; and.b32 %0, t, 31; }" : "=r"(src_lane) : "r"(lane));
@@ -813,14 +820,24 @@ __global__ void __launch_bounds__(32, flat_min_ctas(K, MODE, LANES)) phmm_flat_f
         ti = __shfl_sync(FULL, ti, 0);
         if (ti >= n_tasks) break;
         const Task t = g.tasks[ti];
-        // this lane's read: the task's read, or (upper half of a half-warp task) its partner
-        const bool upper = LANES == 16 && lane >= 16;
-        const uint32_t rd = upper ? t.stream_off : t.read;
+        // this lane's read: the task's read, (upper half of a half-warp task) its partner, or (quarter-warp task) one of four.
+        // A half-warp kernel that meets a quarter-warp task takes its reads two by two.
+        const int part = LANES == 32 ? 0 : lane / LANES;
+        const bool quad = LANES != 32 && g.pair_tasks == 2;
+        for (int sub = 0; sub < (LANES == 16 && quad ? 2 : 1); ++sub) {
+        const int idx = LANES == 16 && quad ? 2 * sub + part : part;
+        uint32_t rd, out_base;
+        if (quad) {
+            rd = idx == 0 ? t.read : idx == 1 ? t.stream_off : idx == 2 ? t.n_haps : t.hap_first;
+            out_base = t.out_base + rd * t.stream_len;
+        } else {
+            rd = idx ? t.stream_off : t.read;
+            out_base = idx ? t.stream_len : t.out_base;
+        }
         const bool mine = rd != NO_READ && g.read_class[rd] == (uint8_t)f.class_id;
         if (!__any_sync(FULL, mine)) continue;
         const uint32_t ro = mine ? g.read_off[rd] : 0u;
-        const int R = mine ? (int)(g.read_off[rd + 1] - ro) : 0;  // 1 <= R <= LANES * K - 1 (flat reads are never empty); 0 = idle half
-        const uint32_t out_base = upper ? t.stream_len : t.out_base;
+        const int R = mine ? (int)(g.read_off[rd + 1] - ro) : 0;  // 1 <= R <= LANES * K - 1 (flat reads are never empty); 0 = idle part
         const float c0 = (float)scalbn(1.0, t.c0_exp);
 
         float A[K], C[K];    // SYM, GEN: per-row coefficients of I^ and D^ in the match update
@@ -919,15 +936,24 @@ __global__ void __launch_bounds__(32, flat_min_ctas(K, MODE, LANES)) phmm_flat_f
         const int acc_lane = mine ? (R - 1) / K : -1;
         // the slot of the likelihood sum is warp-uniform: both reads of a pair share it (planner); an idle half defers to the other
         int acc_slot = mine ? (R - 1) % K : -1;
-        if (LANES == 16) {
-            const int lo = __shfl_sync(FULL, acc_slot, 0), hi = __shfl_sync(FULL, acc_slot, 16);
-            acc_slot = lo >= 0 ? lo : hi;
+        if (LANES < 32) {
+            int agreed = -1;
+#pragma unroll
+            for (int q = 0; q < 32; q += LANES) {
+                const int v = __shfl_sync(FULL, acc_slot, q);
+                if (agreed < 0) agreed = v;
+            }
+            acc_slot = agreed;
         }
         float *const slab = g.snap + (size_t)blockIdx.x * ((MAX_SNAP_SLOTS + 1) * 32 * REGS) + lane * REGS;
         snap_save<K>(st, slab, ZERO_SLOT);  // the pass-start state (all zero), restored at every END that begins a fresh pass
-        const bool narrow = LANES == 16 && us.n_segs16 != 0;  // 16 lanes per read: END / snapshot windows of 16 steps
+        // 16 / 8 lanes per read: END / snapshot windows of 16 / 8 steps (the 32-step schedule is correct for any width)
+        uint32_t seg_first = us.seg_first, n_segs = us.n_segs;
+        if (LANES == 16 && us.n_segs16 != 0) { seg_first = us.seg16_first; n_segs = us.n_segs16; }
+        if (LANES == 8 && us.n_segs8 != 0) { seg_first = us.seg8_first; n_segs = us.n_segs8; }
         flat_dispatch<K, 0, MODE>(acc_slot, st, f, A, C, G, Dd, B0, G0, E0, tmi_r, tab_lane, src_lane, pl, acc_lane, sums + out_base, slab,
-                                  g.segments + (narrow ? us.seg16_first : us.seg_first), narrow ? us.n_segs16 : us.n_segs);
+                                  g.segments + seg_first, n_segs);
+        }  // sub
     }
 }
 

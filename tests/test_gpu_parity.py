@@ -314,8 +314,10 @@ def test_lane_layout_is_invisible():
             for v in variants:
                 p = paired.prepare(v)   # one chunk holding every read (the staged path ramps its chunk sizes up from small ones)
                 a = np.full(v.n_out, np.nan)
+                paired.reset_stats()
                 paired.run_prepared(p, a)
                 paired.release_prepared(p)
+                assert paired.stats()["rescued_pairs"] == 0   # (a task no kernel ran would come back from the fp64 redo)
                 c = single.compute(v)
                 assert np.array_equal(a, c)
         sub = Batch(b.read_bases, b.base_q, sym, sym.copy(), b.gcp, b.read_off, b.hap_bases, b.hap_off, b.units[:6])
@@ -351,6 +353,50 @@ def test_half_warp_general_kernel():
             sub = Batch(b.read_bases, b.base_q, ins, dele, gcp, b.read_off, b.hap_bases, b.hap_off, b.units[:n_units])
             want = oracle_batch(sub)
             assert np.abs(a[:sub.n_out] - want).max() <= TOL
+
+
+def test_quarter_warp_tasks():
+    # three or four reads of EQUAL length (up to 159 bases) of a unit share a warp, 8 lanes each (quarter-warp buckets); the
+    # other reads of the unit keep their half-warp / full-warp tasks.  Every quality class, mixed classes inside one task, a
+    # remainder of three, a haplotype that is a prefix of another (snapshot next to an END column, 8-step windows).  The fp64
+    # redo would hide a task that no kernel ran (its sums stay zero), so the redo count is checked too.
+    rng = np.random.default_rng(5)
+    L4 = np.frombuffer(b"ACGT", dtype=np.uint8)
+    hap = L4[rng.integers(0, 4, 300)]
+    haps = [hap.tobytes(), hap[:250].tobytes(), hap[10:].tobytes()]
+    with GpuPhmm() as hmm:
+        for N, L, mixed in ((4, 150, False), (3, 151, False), (7, 150, True), (4, 119, False), (3, 100, True), (5, 76, False), (4, 64, True), (4, 159, True)):
+            reads = []
+            for k in range(N):
+                off = int(rng.integers(0, 300 - L + 1))
+                rd = hap[off:off + L].copy()
+                rd[L // 3] = ord("T") if rd[L // 3] != ord("T") else ord("A")
+                q = np.clip(rng.normal(30, 8, L), 6, 41).astype(np.uint8)
+                kind = k % 4 if mixed else 0
+                if kind == 3:    # per-base qualities: the general kernel takes the task's reads two by two
+                    iq, dq, gq = (rng.integers(20, 50, L).astype(np.uint8) for _ in range(3))
+                elif kind == 2:  # ins == del per base, flat gcp
+                    iq = rng.integers(30, 45, L).astype(np.uint8)
+                    dq, gq = iq.copy(), const_quals(L, 10)
+                else:
+                    t = [(45, 45, 10), (40, 42, 10)][kind]
+                    iq, dq, gq = const_quals(L, t[0]), const_quals(L, t[1]), const_quals(L, t[2])
+                reads.append((rd, q, iq, dq, gq))
+            for k in range(5):   # reads of other lengths in the same unit
+                R = 200 + k
+                off = int(rng.integers(0, 300 - R + 1))
+                reads.append((hap[off:off + R].copy(), np.full(R, 30, np.uint8), const_quals(R, 45), const_quals(R, 45), const_quals(R, 10)))
+            one = Batch.single_unit(reads, haps)
+            want = oracle_batch(one)
+            copies = 6000 // len(reads) + 1
+            big, n = _replicate(one, copies)
+            p = hmm.prepare(big)
+            out = np.full(big.n_out, np.nan)
+            hmm.reset_stats()
+            hmm.run_prepared(p, out)
+            hmm.release_prepared(p)
+            assert hmm.stats()["rescued_pairs"] == 0
+            assert np.abs(out.reshape(copies, n) - want).max() <= TOL
 
 
 def test_invariants_at_scale(hmm):
