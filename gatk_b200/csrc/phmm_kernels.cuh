@@ -822,10 +822,11 @@ __global__ void __launch_bounds__(32, flat_min_ctas(K, MODE, LANES)) phmm_flat_f
         const Task t = g.tasks[ti];
         // this lane's read: the task's read, (upper half of a half-warp task) its partner, or (quarter-warp task) one of four.
         // A half-warp kernel that meets a quarter-warp task takes its reads two by two.
+        // (quarter-warp tasks reach the quarter-warp kernels and, of the half-warp kernels, only the general form)
         const int part = LANES == 32 ? 0 : lane / LANES;
-        const bool quad = LANES != 32 && g.pair_tasks == 2;
-        for (int sub = 0; sub < (LANES == 16 && quad ? 2 : 1); ++sub) {
-        const int idx = LANES == 16 && quad ? 2 * sub + part : part;
+        const bool quad = LANES == 8 || (LANES == 16 && MODE == MODE_GEN && g.pair_tasks == 2);
+        for (int sub = 0; sub < (LANES == 16 && MODE == MODE_GEN && quad ? 2 : 1); ++sub) {
+        const int idx = LANES == 16 && MODE == MODE_GEN && quad ? 2 * sub + part : part;
         uint32_t rd, out_base;
         if (quad) {
             rd = idx == 0 ? t.read : idx == 1 ? t.stream_off : idx == 2 ? t.n_haps : t.hap_first;
@@ -936,10 +937,13 @@ __global__ void __launch_bounds__(32, flat_min_ctas(K, MODE, LANES)) phmm_flat_f
         const int acc_lane = mine ? (R - 1) / K : -1;
         // the slot of the likelihood sum is warp-uniform: both reads of a pair share it (planner); an idle half defers to the other
         int acc_slot = mine ? (R - 1) % K : -1;
-        if (LANES < 32) {
+        if (LANES == 16) {
+            const int lo = __shfl_sync(FULL, acc_slot, 0), hi = __shfl_sync(FULL, acc_slot, 16);
+            acc_slot = lo >= 0 ? lo : hi;
+        } else if (LANES == 8) {
             int agreed = -1;
 #pragma unroll
-            for (int q = 0; q < 32; q += LANES) {
+            for (int q = 0; q < 32; q += 8) {
                 const int v = __shfl_sync(FULL, acc_slot, q);
                 if (agreed < 0) agreed = v;
             }
