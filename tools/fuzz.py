@@ -76,7 +76,9 @@ try:
         elif shape == 2:
             b = synth.random_batch(seed, n_units=int(rng.integers(1, 30)), max_reads=4, max_haps=3, read_len=(1, 40), hap_len=(1, 60))
         else:
-            b = synth.random_batch(seed, n_units=3, max_reads=40, max_haps=16, read_len=(int(rng.choice([50, 64, 100])), 254), hap_len=(250, 500))
+            lo = int(rng.choice([50, 64, 100]))
+            # (a narrow length range gives reads of equal length: quarter-warp tasks, four reads per warp)
+            b = synth.random_batch(seed, n_units=3, max_reads=40, max_haps=16, read_len=(lo, lo + 6) if rng.random() < 0.4 else (lo, 254), hap_len=(250, 500))
         mode = ["keep", "sym", "flatmix", "extreme", "dragstr"][int(rng.integers(0, 5))]
         b = requalify(b, rng, mode)
         if rng.random() < 0.2:   # exotic haplotype bytes
