@@ -530,7 +530,8 @@ void plan_chunk(const gphmm_batch *b, int64_t u0, int64_t u1, bool force_fp64, b
         // quarter-warp tasks: four (or three) reads of the same length, up to 159 bases, on one warp
         quad_cand.clear();
         bool any_quad = false;
-        if (pair_reads_ok && nh) {
+        // (only where the sampled reads showed a flat or symmetric quality class: general reads gain nothing from it)
+        if (pair_reads_ok && nh && c.n_classes + c.n_sym > 0) {
             for (uint32_t r = 0; r < nr; ++r) {
                 const uint32_t R = c.read_off[d.read_first + r + 1] - c.read_off[d.read_first + r];
                 if (quad_bucket_of_read(R) >= 0) quad_cand.push_back(((uint64_t)R << 32) | r);

@@ -783,7 +783,7 @@ __device__ __forceinline__ void flat_dispatch(int slot, FastState<K> &st, const 
 // leaves its half idle (all rows pads).
 __host__ __device__ constexpr int flat_min_ctas(int K, int MODE, int LANES) {
     return LANES == 32 ? (MODE != MODE_FLAT ? 22 : 28)
-         : LANES == 8 ? (K <= 10 ? (MODE != MODE_FLAT ? 16 : 18) : K <= 16 ? 14 : (MODE != MODE_FLAT ? 10 : 12))  // quarter-warp form
+         : LANES == 8 ? (K <= 10 ? (MODE != MODE_FLAT ? 16 : 18) : K <= 16 ? 14 : (MODE != MODE_FLAT ? 12 : 14))  // quarter-warp form (20 rows: 128 / 168 registers; with 12 CTAs the flat kernel took 158 and ran 5 % slower)
          : K <= 8 ? (MODE == MODE_GEN ? 18 : MODE == MODE_SYM ? 22 : 28)  // half-warp form for reads of 64..127 bases
          : (MODE == MODE_GEN ? (K > 12 ? 10 : 14) : (K > 12 ? 14 : (MODE != MODE_FLAT ? 16 : 18)));
 }
