@@ -170,3 +170,8 @@ def test_planner_host_only():
     assert ss["skipped_columns"] <= trie and ss["skipped_columns"] >= 0.93 * trie
     assert steps(ss) < 0.9 * steps(sp)
     assert ss["checked_steps"] <= 32 * (ss["passes"] + ss["snapshots"]) + ss["units"]
+    # equal-length reads of up to 159 bases: four per warp (quarter-warp tasks) once the chunk is large enough
+    quad = synth.config1_many(48)   # 48 regions x 128 reads x 150 bases
+    assert native.plan_stats(quad)["tasks"] == quad.n_reads // 4
+    few = synth.config1_many(8)     # too few reads to fill the GPU that way: one read per warp, haplotypes split into groups
+    assert native.plan_stats(few)["tasks"] >= few.n_reads
