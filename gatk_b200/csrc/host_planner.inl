@@ -154,7 +154,7 @@ struct SharingScratch {
 
 UnitSched plan_unit_sharing(const gphmm_batch *b, const gphmm_unit &un, uint32_t hap_first_local, bool share, ChunkPlan &c,
                             int64_t sum_read_len, const std::vector<int> &full_order, int g_first, int g_count, SharingScratch &ws,
-                            int narrow_schedules = 0) {  // 1: also the 16-step-window schedule, 2: the 16- and the 8-step-window ones
+                            int narrow_schedules = 0) {  // bit 0: also the 16-step-window schedule, bit 1: the 8-step-window one
     constexpr uint32_t SPACING = 32;
     static const uint32_t NEAR_DEPTHS = getenv("GPHMM_NEAR_DEPTHS") ? (uint32_t)std::max(1, atoi(getenv("GPHMM_NEAR_DEPTHS"))) : 96u;  // how far below the shared depth to look
     static const uint32_t MIN_DEPTH = getenv("GPHMM_MIN_DEPTH") ? (uint32_t)std::max(32, atoi(getenv("GPHMM_MIN_DEPTH"))) : 32u;  // tuning knob
@@ -310,12 +310,12 @@ UnitSched plan_unit_sharing(const gphmm_batch *b, const gphmm_unit &un, uint32_t
     };
     build_schedule(32);
     us.n_segs = (uint32_t)c.segments.size() - us.seg_first;
-    if (narrow_schedules >= 1) {  // the same passes and snapshots with 16-step windows (the last window ends 16 steps earlier)
+    if (narrow_schedules & 1) {  // the same passes and snapshots with 16-step windows (the last window ends 16 steps earlier)
         us.seg16_first = (uint32_t)c.segments.size();
         build_schedule(16);
         us.n_segs16 = (uint32_t)c.segments.size() - us.seg16_first;
     }
-    if (narrow_schedules >= 2) {  // quarter-warp tasks: 8-step windows
+    if (narrow_schedules & 2) {  // quarter-warp tasks: 8-step windows
         us.seg8_first = (uint32_t)c.segments.size();
         build_schedule(8);
         us.n_segs8 = (uint32_t)c.segments.size() - us.seg8_first;
@@ -539,12 +539,32 @@ void plan_chunk(const gphmm_batch *b, int64_t u0, int64_t u1, bool force_fp64, b
             std::sort(quad_cand.begin(), quad_cand.end());
             for (size_t i = 0; i + 2 < quad_cand.size() && !any_quad; ++i) any_quad = (quad_cand[i] >> 32) == (quad_cand[i + 2] >> 32);
         }
+        // which of the narrow-window schedules the unit's tasks will use: 16-step windows for half-warp tasks (two or more
+        // reads are left for them), 8-step windows for quarter-warp tasks.  (The 32-step schedule is always built; a kernel
+        // that finds no narrower one falls back to it.)
+        int narrow = 0;
+        if (pair_reads_ok && nh) {
+            uint32_t n_pair_cand = 0;
+            size_t qi = 0;  // quad_cand is sorted by (length, read): runs of equal length leave len % 4 reads (0 if that is 3)
+            uint32_t in_quads = 0;
+            while (any_quad && qi < quad_cand.size()) {
+                size_t qj = qi;
+                while (qj < quad_cand.size() && (quad_cand[qj] >> 32) == (quad_cand[qi] >> 32)) ++qj;
+                const size_t len = qj - qi, left = len % 4 == 3 ? 0 : (len >= 3 ? len % 4 : len);
+                in_quads += (uint32_t)(len - left);
+                qi = qj;
+            }
+            for (uint32_t r = 0; r < nr; ++r) {
+                const uint32_t R = c.read_off[d.read_first + r + 1] - c.read_off[d.read_first + r];
+                if (pair_bucket_of_read(R) >= 0) ++n_pair_cand;
+            }
+            narrow = (n_pair_cand - std::min(n_pair_cand, in_quads) >= 2 ? 1 : 0) | (any_quad ? 2 : 0);
+        }
         {
             sorted_hap_order(b, un, share && !force_fp64, order);
             for (int gi = 0; gi < n_groups; ++gi) {
                 const int g0 = (int)((int64_t)nh * gi / n_groups), g1 = (int)((int64_t)nh * (gi + 1) / n_groups);
-                c.unit_sched.push_back(plan_unit_sharing(b, un, d.hap_first, share && !force_fp64, c, fast_read_len, order, g0, g1 - g0, scratch,
-                                                         pair_reads_ok ? (any_quad ? 2 : 1) : 0));
+                c.unit_sched.push_back(plan_unit_sharing(b, un, d.hap_first, share && !force_fp64, c, fast_read_len, order, g0, g1 - g0, scratch, narrow));
             }
         }
         if (nh == 0) continue;
