@@ -41,32 +41,28 @@ template <int K, bool SIMPLE> KernelInfo pd_fast_kernel_info() {
 }
 
 // Deletion events of a haplotype for the SIMPLE kernels (pdhmm_kernels.cuh): (a, b) = first and last column of a deletion.
-// False when the haplotype does not have the simple shape -- a flag met in the AFTER_DEL state, events closer than three
-// columns, a deletion still open (or just closed) at the last column, which LoglessPDPairHMM.java:59 carries into the next row.
+// Events may touch: a flag met in the AFTER_DEL state starts the next event on that very column.  False when a deletion is
+// still open (or just closed) at the last column, which LoglessPDPairHMM.java:59 carries into the next row.
 bool pd_simple_events(const uint8_t *pd, uint32_t H, std::vector<uint2> &events) {
     enum { DEL_START = 2, DEL_END = 4 };
     const size_t n0 = events.size();
     uint32_t state = PD_NORMAL, a = 0;
-    bool ok = true;
-    for (uint32_t j = 1; j <= H && ok; ++j) {
+    for (uint32_t j = 1; j <= H; ++j) {
         const bool ds = pd[j - 1] & DEL_START, de = pd[j - 1] & DEL_END;
-        if (state == PD_AFTER_DEL) {
-            if (ds || de) ok = false;
-            state = PD_NORMAL;
-        } else if (state == PD_NORMAL) {
+        if (state != PD_INSIDE_DEL) {  // NORMAL or AFTER_DEL
             if (ds || de) {
                 a = j;
-                if (events.size() > n0 && a < events.back().y + 3) ok = false;
                 if (de) { events.push_back(make_uint2(a, j)); state = PD_AFTER_DEL; } else state = PD_INSIDE_DEL;
+            } else {
+                state = PD_NORMAL;
             }
         } else if (de) {  // INSIDE_DEL: a further DEL_START changes nothing
             events.push_back(make_uint2(a, j));
             state = PD_AFTER_DEL;
         }
     }
-    if (state != PD_NORMAL) ok = false;
-    if (!ok) events.resize(n0);
-    return ok;
+    if (state != PD_NORMAL) { events.resize(n0); return false; }
+    return true;
 }
 
 // Schedule of a SIMPLE haplotype: lane l is on column j at step j + l, and only the columns a, b, b + 1 of an event need the
@@ -207,7 +203,8 @@ struct PdChunkPlan {
                 // whose per-step fast path works column by column
                 uint32_t n_slow = 0;
                 for (uint32_t q = ph.seg_first; q < (uint32_t)segs.size(); ++q) n_slow += segs[q].y;
-                hi[k].sparse = hap_ok && 2 * n_slow <= H + 33;
+                // (the SIMPLE window form costs ~3 plain steps per window step: still ahead of the first-version kernels when every step is one)
+                hi[k].sparse = hap_ok && (hi[k].simple || 2 * n_slow <= H + 33);
                 haps.push_back(ph);
             }
             for (uint32_t r = 0; r < nr; ++r) {

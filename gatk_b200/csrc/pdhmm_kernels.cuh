@@ -290,7 +290,7 @@ struct PdFastArgs {
 // The row above a lane's first row belongs to the previous lane, which is one column ahead: its saved last row is read
 // from its record (row 0 above lane 0 has branch values 0).  Every other lane runs the plain fast step in the same
 // instruction stream; the three moments are divergent branches with one active lane each.
-template <int K> __host__ __device__ constexpr int pd_save_vecs() { return (3 * K + 3) / 4 + 2; }  // record of a lane: 3K floats + (M, I~, D~) of its last row + its unmerged (M, I~) at column b
+template <int K> __host__ __device__ constexpr int pd_save_vecs() { return (3 * K + 3) / 4 + 4; }  // record of a lane: 3K floats; by event parity: (M, I~, D~) of its last row, its unmerged (M, I~) at column b
 template <int K> constexpr size_t pd_fast_smem(int n_codes, bool simple) {
     return (size_t)n_codes * ((K + 3) / 4) * 512 + (simple ? (size_t)pd_save_vecs<K>() * 512 : 0);
 }
@@ -446,14 +446,18 @@ __global__ void __launch_bounds__(32, K > 5 ? 16 : 20) phmm_pd_fast_kernel(const
         st.p = 0;
         st.sp = g.codes + hp.code_off - lane;  // lane l works on column (step - l); columns <= 0 and > H read the zero padding
         st.y = ldg_u8(st.sp);
-        // SIMPLE: this lane's next deletion event and its record behind the prior table
+        // SIMPLE: this lane's next deletion event, the column after the previous one, and its record behind the prior table
         uint32_t ev = hp.ev_first;
         const uint32_t ev_end = hp.ev_first + hp.n_events;
         constexpr int NO_COL = -(1 << 30);  // no column matches (p >= -31)
-        int ea = NO_COL, eb = NO_COL;
+        int ea = NO_COL, eb = NO_COL, after_col = NO_COL;
+        uint32_t after_par = 0;
         if (SIMPLE && ev < ev_end) { const uint2 e = g.events[ev]; ea = (int)e.x; eb = (int)e.y; }
         const uint32_t rec = tab_lane + (uint32_t)g.n_rows * (NV * 512);         // float4 v of this lane: rec + v * 512
-        const uint32_t rec_prev = rec + NS * 512 + (lane ? -16 : 31 * 16);        // (M, I~, D~) of the previous lane's last row
+        // what the next lane reads -- (M, I~, D~) of this lane's last row as saved, its unmerged (M, I~) at column b -- is kept
+        // twice, by event parity: events may touch, and the next lane is one column behind
+        const uint32_t hand0 = rec + NS * 512, unm0 = rec + (NS + 2) * 512;
+        const int prev_delta = lane ? -16 : 31 * 16;
 
         int step = 1;
         for (uint32_t sg = 0; sg < hp.n_segs; ++sg) {
@@ -466,32 +470,16 @@ __global__ void __launch_bounds__(32, K > 5 ? 16 : 20) phmm_pd_fast_kernel(const
             if constexpr (SIMPLE) {
 #pragma unroll 1
                 for (uint32_t s = 0; s < seg.y; ++s, ++p) {
-                    if (p == ea) {  // column a: save column a - 1 (rows that are not read rows save 0)
-                        float v[NS * 4];
-#pragma unroll
-                        for (int k = 0; k < NS * 4; ++k) v[k] = 0.f;
-                        if (real_mask == (1u << K) - 1u) {
-#pragma unroll
-                            for (int k = 0; k < K; ++k) { v[k] = st.M[k]; v[K + k] = st.I[k]; v[2 * K + k] = st.D[k]; }
-                        } else {
-#pragma unroll
-                            for (int k = 0; k < K; ++k)
-                                if ((real_mask >> k) & 1u) { v[k] = st.M[k]; v[K + k] = st.I[k]; v[2 * K + k] = st.D[k]; }
-                        }
-#pragma unroll
-                        for (int q = 0; q < NS; ++q) sts128(rec + q * 512, v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-                        sts128(rec + NS * 512, v[K - 1], v[2 * K - 1], v[3 * K - 1], 0.f);
-                    }
-                    __syncwarp();
                     float acc_in = 0.f;
-                    if (p == eb + 1) {  // column b + 1 (AFTER_DEL): merge column b with the branch in place
+                    const bool is_after = p == after_col;
+                    if (is_after) {  // column b + 1 of the previous event (AFTER_DEL): merge column b with the branch in place
                         // the lane below takes this lane's last row at column b from the shuffle of THIS step, i.e. merged --
                         // right for every use the reference makes of it (:80-82, :107-118) except the accumulator row
-                        sts128(rec + (NS + 1) * 512, st.M[K - 1], st.I[K - 1], 0.f, 0.f);
+                        sts128(unm0 + after_par * 512, st.M[K - 1], st.I[K - 1], 0.f, 0.f);
                         if (lane == acc_lane) {  // the accumulator row adds the unmerged (M + I)[R][b]
                             acc_in = __fmaf_rn(cb[0], st.dgi, st.dgm);  // (an empty read: row 0)
                             if (acc_slot == 0 && lane != 0) {  // row R is the previous lane's last row: its unmerged values were left one step ago
-                                const float4 t4 = lds128m(rec_prev + 512);
+                                const float4 t4 = lds128m(unm0 + after_par * 512 + prev_delta);
                                 acc_in = __fmaf_rn(cb[0], t4.y, t4.x);
                             }
 #pragma unroll
@@ -509,11 +497,37 @@ __global__ void __launch_bounds__(32, K > 5 ? 16 : 20) phmm_pd_fast_kernel(const
                             st.M[k] = pd_max(v[k], st.M[k]); st.I[k] = pd_max(v[K + k], st.I[k]); st.D[k] = pd_max(v[2 * K + k], st.D[k]);
                         }
                         if (lane != 0) {  // row above this lane's first row; row 0 has no branch
-                            const float4 t4 = lds128m(rec_prev);
+                            const float4 t4 = lds128m(hand0 + after_par * 512 + prev_delta);
                             st.dgm = pd_max(t4.x, st.dgm); st.dgi = pd_max(t4.y, st.dgi); st.dgd = pd_max(t4.z, st.dgd);
                         }
                     }
+                    __syncwarp();  // (the lane above may start its next event in this step: its save comes after these reads)
+                    if (p == ea) {  // column a: save column a - 1 -- merged a moment ago if the events touch -- (rows that are not read rows save 0)
+                        float v[NS * 4];
+#pragma unroll
+                        for (int k = 0; k < NS * 4; ++k) v[k] = 0.f;
+                        if (real_mask == (1u << K) - 1u) {
+#pragma unroll
+                            for (int k = 0; k < K; ++k) { v[k] = st.M[k]; v[K + k] = st.I[k]; v[2 * K + k] = st.D[k]; }
+                        } else {
+#pragma unroll
+                            for (int k = 0; k < K; ++k)
+                                if ((real_mask >> k) & 1u) { v[k] = st.M[k]; v[K + k] = st.I[k]; v[2 * K + k] = st.D[k]; }
+                        }
+#pragma unroll
+                        for (int q = 0; q < NS; ++q) sts128(rec + q * 512, v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                        sts128(hand0 + (ev & 1u) * 512, v[K - 1], v[2 * K - 1], v[3 * K - 1], 0.f);
+                    }
+                    __syncwarp();
                     fast_step<K, false>(st, cb, cc, cg, cd, tab_lane, src_lane, lane, 0, 0, c0, nullptr, nullptr, 0, 0, 0, 0);
+                    if (is_after) {
+                        if (lane == acc_lane) {
+#pragma unroll
+                            for (int k = 0; k < K; ++k)
+                                if (k == acc_slot) st.M[k] = acc_in;
+                        }
+                        after_col = NO_COL;
+                    }
                     if (p == eb) {  // column b (DEL_END): the insertion chain sees max(branch, value) of the row above
                         float v[NS * 4];
 #pragma unroll
@@ -523,24 +537,19 @@ __global__ void __launch_bounds__(32, K > 5 ? 16 : 20) phmm_pd_fast_kernel(const
                         }
                         float um = st.dgm, ui = st.dgi;  // row above at this column (fast_step leaves them here)
                         if (lane != 0) {
-                            const float4 t4 = lds128m(rec_prev);
+                            const float4 t4 = lds128m(hand0 + (ev & 1u) * 512 + prev_delta);
                             um = pd_max(t4.x, um); ui = pd_max(t4.y, ui);
                         }
                         st.I[0] = __fmaf_rn(cg[0], ui, um);
 #pragma unroll
                         for (int k = 1; k < K; ++k) st.I[k] = __fmaf_rn(cg[k], pd_max(v[K + k - 1], st.I[k - 1]), pd_max(v[k - 1], st.M[k - 1]));
-                    }
-                    if (p == eb + 1) {
-                        if (lane == acc_lane) {
-#pragma unroll
-                            for (int k = 0; k < K; ++k)
-                                if (k == acc_slot) st.M[k] = acc_in;
-                        }
-                        ++ev;  // this lane is through with the event
+                        // the next column is the event's AFTER_DEL column; the lane moves on to the next event (which may start there)
+                        after_col = eb + 1; after_par = ev & 1u;
+                        ++ev;
                         ea = NO_COL; eb = NO_COL;
                         if (ev < ev_end) { const uint2 e = g.events[ev]; ea = (int)e.x; eb = (int)e.y; }
                     }
-                    __syncwarp();  // the records read in this step may be overwritten in the next one (next event three columns on)
+                    __syncwarp();  // the records read in this step may be overwritten in the next one
                 }
             } else {
             // the branch values are dead between two slow windows: every lane refreshes them (NORMAL: branch = the value one

@@ -14,8 +14,22 @@ SNP, DEL_START, DEL_END, A, C, G, T = 1, 2, 4, 8, 16, 32, 64
 def random_pd(rng, H, mode):
     """mode 0: no flags; 1: SNP sites; 2: SNPs + well-formed deletions; 3: arbitrary flag bytes; 4: sparse (a handful of
     undetermined sites per haplotype, like the partially determined haplotypes of one assembly region); 5: sparse with
-    several deletions of 1-40 columns, some of them adjacent, nested or cut off by the end of the haplotype"""
+    several deletions of 1-40 columns, some of them adjacent, nested or cut off by the end of the haplotype; 6: sparse SNP
+    sites with a deletion every ~12 columns"""
     pd = np.zeros(H, np.uint8)
+    if mode == 6:   # a handful of SNP sites, a well-formed deletion of 1-6 columns every ~12 columns (touching ones included)
+        for _ in range(int(rng.integers(1, 5))):
+            pd[int(rng.integers(0, H))] |= SNP | int(rng.choice([A, C, G, T]))
+        j = 0
+        while j < H:
+            if rng.random() < 0.08:
+                e = min(H - 1, j + int(rng.integers(1, 7)) - 1)
+                pd[j] |= DEL_START
+                pd[e] |= DEL_END
+                j = e + 1
+            else:
+                j += 1
+        return pd
     if mode == 5:
         for _ in range(int(rng.integers(0, 4))):
             pd[int(rng.integers(0, H))] |= SNP | int(rng.choice([A, C, G, T]))
@@ -112,25 +126,22 @@ def test_snp_and_deletion_semantics():
 
 # ---- the SIMPLE window form of the fast kernels, modelled on the CPU ------------------------------------------------------
 def simple_events(pd):
-    """host_pdhmm.inl pd_simple_events: the (a, b) column pairs (1-based) of a haplotype whose deletions are well formed and
-    at least three columns apart, or None"""
+    """host_pdhmm.inl pd_simple_events: the (a, b) column pairs (1-based) of a haplotype whose deletions are well formed
+    (they may touch: a flag met in the AFTER_DEL state starts the next event on that very column), or None when a deletion is
+    still open or just closed at the last column (LoglessPDPairHMM.java:59 carries that state into the next row)"""
     H, state, a, ev = len(pd), "N", 0, []
     for j in range(1, H + 1):
         ds, de = bool(pd[j - 1] & DEL_START), bool(pd[j - 1] & DEL_END)
-        if state == "A":
-            if ds or de:
-                return None
-            state = "N"
-        elif state == "N":
+        if state in ("N", "A"):
             if ds or de:
                 a = j
-                if ev and a < ev[-1][1] + 3:
-                    return None
                 if de:
                     ev.append((a, j))
                     state = "A"
                 else:
                     state = "I"
+            else:
+                state = "N"
         elif de:
             ev.append((a, j))
             state = "A"
@@ -139,8 +150,9 @@ def simple_events(pd):
 
 def simple_model(hap, pd, read, base_q, ins_q, del_q, gcp):
     """What phmm_pd_fast_kernel<K, SIMPLE> does, column by column in double: the plain LoglessPairHMM update on every column,
-    plus, per deletion event (a, b): SAVE column a - 1; on column b recompute the insertions from max(saved, value) of the row
-    above; before column b + 1 take max(saved, value) of column b IN PLACE.  The likelihood sum adds the unmerged M + I."""
+    plus, per deletion event (a, b), in this order within a column: before column b + 1 take max(saved, value) of column b IN
+    PLACE; on column a SAVE the state (= column a - 1, merged if a is the column after the previous event); after the update
+    of column b recompute the insertions from max(saved, value) of the row above.  The likelihood sum adds the unmerged M + I."""
     H, R = len(hap), len(read)
     ev = simple_events(pd)
     assert ev is not None
@@ -156,11 +168,11 @@ def simple_model(hap, pd, read, base_q, ins_q, del_q, gcp):
     tIM = 1.0 - tII
     saved, total = None, 0.0
     for j in range(1, H + 1):
+        if j in after:
+            M, I, D = np.maximum(M, saved[0]), np.maximum(I, saved[1]), np.maximum(D, saved[2])
         if j in first:
             saved = (M.copy(), I.copy(), D.copy())
             saved[2][0] = 0.0  # row 0 has no branch (Java's branch matrices are 0.0 there)
-        if j in after:
-            M, I, D = np.maximum(M, saved[0]), np.maximum(I, saved[1]), np.maximum(D, saved[2])
         y, f = hap[j - 1], pd[j - 1]
         prior = np.zeros(R + 1)
         for i in range(1, R + 1):
@@ -187,13 +199,14 @@ def test_simple_window_form_equals_the_reference_state_machine():
     n = 0
     assert simple_events(np.array([0, DEL_START, 0, DEL_END, 0, 0], np.uint8)) == [(2, 4)]
     assert simple_events(np.array([0, DEL_END, 0, 0, DEL_START | DEL_END, 0], np.uint8)) == [(2, 2), (5, 5)]
-    assert simple_events(np.array([0, DEL_END, 0, DEL_START | DEL_END, 0], np.uint8)) is None   # two columns apart
-    assert simple_events(np.array([0, DEL_START, DEL_END, DEL_END, 0], np.uint8)) is None       # a flag met in AFTER_DEL
+    assert simple_events(np.array([0, DEL_END, 0, DEL_START | DEL_END, 0], np.uint8)) == [(2, 2), (4, 4)]
+    assert simple_events(np.array([0, DEL_START, DEL_END, DEL_END, 0], np.uint8)) == [(2, 3), (4, 4)]    # a flag met in AFTER_DEL
+    assert simple_events(np.array([0, DEL_END, DEL_START, 0, DEL_END, 0], np.uint8)) == [(2, 2), (3, 5)]
     assert simple_events(np.array([0, 0, DEL_START, 0], np.uint8)) is None                      # still open at the end
     assert simple_events(np.array([0, 0, DEL_START, DEL_END], np.uint8)) is None                # AFTER_DEL carried into the next row
     while n < 150:
         hap, read, q = random_pair(rng, 90, 60)
-        pd = random_pd(rng, len(hap), int(rng.choice([4, 5])))
+        pd = random_pd(rng, len(hap), int(rng.choice([2, 3, 4, 5])))   # dense, arbitrary, sparse, touching events
         if simple_events(pd) is None or not simple_events(pd):
             continue
         read[read == ord("N")] = ord("A")
@@ -281,7 +294,7 @@ def test_pdhmm_sparse_flags_fast_kernels(read_len):
     from gatk_b200.native import GpuPhmm
     with GpuPhmm() as hmm:
         for seed in range(3):
-            b, pd = _pd_batch(100 + seed, 4, 10, 6, read_len, (150, 420), modes=(4, 5, 5))
+            b, pd = _pd_batch(100 + seed, 4, 10, 6, read_len, (150, 420), modes=(4, 5, 5, 6))
             want = _pd_oracle(b, pd)
             _close(hmm.pd_compute(b, pd), want, 1e-4)
         # reads that end inside / right after a deletion window and reads shorter than one lane's rows

@@ -142,7 +142,7 @@ try:
             rb = b.read_bases.copy()
             rb[rb == ord("N")] = ord("A")
             bp = Batch(rb, b.base_q, b.ins_q, b.del_q, b.gcp, b.read_off, b.hap_bases, b.hap_off, b.units)
-            pd = np.concatenate([random_pd(rng, int(b.hap_off[k + 1] - b.hap_off[k]), int(rng.integers(0, 6))) for k in range(len(b.hap_off) - 1)])
+            pd = np.concatenate([random_pd(rng, int(b.hap_off[k + 1] - b.hap_off[k]), int(rng.integers(0, 7))) for k in range(len(b.hap_off) - 1)])
             want_pd = _pd_oracle(bp, pd)
             for name in ("default", "fp64"):
                 worst = max(worst, check(handles[name].pd_compute(bp, pd), want_pd, "seed %d pd %s" % (seed, name)))

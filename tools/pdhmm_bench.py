@@ -18,6 +18,7 @@ rng = np.random.default_rng(1)
 results = []
 with GpuPhmm() as h:
     for label, mode in (("sparse flags (1-4 SNP sites and at most one deletion per haplotype)", 4), ("the same without the deletions (1-4 SNP sites)", -4),
+                        ("1-4 SNP sites, a deletion every ~12 columns (every step a window step of the SIMPLE form)", 6),
                         ("dense flags (12 % SNP columns, a deletion every ~12 columns)", 2)):
         pd = np.concatenate([random_pd(rng, int(b.hap_off[k + 1] - b.hap_off[k]), abs(mode)) for k in range(len(b.hap_off) - 1)])
         if mode < 0:
