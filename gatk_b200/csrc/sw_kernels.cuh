@@ -5,7 +5,7 @@
 // :262-375 calculateCigar() (end point per overhang strategy, traceback, clips).  Native counterpart in the reference:
 // SmithWatermanIntelAligner (GKL) behind SWNativeAlignerWrapper.java:33-60.  Integer work: results are bit-exact.
 //
-// One warp per (reference, alternate) pair.  Lane l owns 4 consecutive reference rows of a 128-row strip and sweeps the
+// One warp per (reference, alternate) pair.  Lane l owns 8 consecutive reference rows of a 256-row strip and sweeps the
 // alternate's columns one per step, lane l on column step-l (the same anti-diagonal wavefront as the PairHMM kernels):
 // the row state (cell to the left, best horizontal gap and its length) stays in registers, the column state (cell
 // above, best vertical gap and its length) is handed down the lanes by three shuffles, strips hand it over through a
@@ -17,7 +17,8 @@
 
 namespace phmm_dev {
 
-constexpr int SW_K = 4, SW_ROWS = 32 * SW_K;
+constexpr int SW_K = 8, SW_ROWS = 32 * SW_K;   // 8 rows per lane: the per-step overhead (hand-off, boundary, stores, loop) is paid per 8 cells
+struct __align__(16) SwBt { int16_t v[SW_K]; };  // the backtrack entries of a lane's step: one 16-byte store
 constexpr int SW_SOFTCLIP = 0, SW_INDEL = 1, SW_LEADING_INDEL = 2, SW_IGNORE = 3;  // SWOverhangStrategy
 constexpr uint32_t SW_OP_M = 0, SW_OP_I = 1, SW_OP_D = 2, SW_OP_S = 3;
 constexpr int SW_MATRIX_MIN_CUTOFF = -100000000;   // SmithWatermanJavaAligner.java:114
@@ -61,12 +62,12 @@ struct SwLane {
 
 template <bool ALL_VALID>
 __device__ __forceinline__ void sw_step(SwLane &L, const bool valid, const int b, int up, int bgv, int gsv, const int w_match,
-                                        const int w_mismatch, const int w_open, const int w_extend, short4 &btv)
+                                        const int w_mismatch, const int w_open, const int w_extend, SwBt &btv)
 {
     constexpr int K = SW_K;
     const int up_in = up;
     int diag = L.diag0;
-    int16_t *btk = reinterpret_cast<int16_t *>(&btv);
+    int16_t *btk = btv.v;
 #pragma unroll
     for (int k = 0; k < K; ++k) {
         const int step_diag = diag + (L.a[k] == b ? w_match : w_mismatch);
@@ -162,11 +163,11 @@ __global__ void __launch_bounds__(32) phmm_sw_kernel(const SwArgs g)
                     else if (valid) { up = bnd[3 * p]; bgv = bnd[3 * p + 1]; gsv = bnd[3 * p + 2]; }
                 }
                 const int b = valid ? (int)alt[p - 1] : 0x200;
-                short4 btv;
+                SwBt btv;
                 sw_step<ALL>(L, valid, b, up, bgv, gsv, g.w_match, g.w_mismatch, g.w_open, g.w_extend, btv);
                 if (valid) {
                     const int s = p + lane;  // step number (1-based): backtrack entries are stored in wavefront order
-                    *reinterpret_cast<short4 *>(bt + (((size_t)strip * n_steps + (s - 1)) * 32 + lane) * K) = btv;
+                    *reinterpret_cast<SwBt *>(bt + (((size_t)strip * n_steps + (s - 1)) * 32 + lane) * K) = btv;
                     if (!last_strip && lane == 31) { bnd[3 * p] = L.last_sw; bnd[3 * p + 1] = L.last_bgv; bnd[3 * p + 2] = L.last_gsv; }
                     if (k_last >= 0) {  // bottom row, every column
                         int v = L.left[0];
