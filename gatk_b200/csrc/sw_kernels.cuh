@@ -72,19 +72,20 @@ __device__ __forceinline__ void sw_step(SwLane &L, const bool valid, const int b
     for (int k = 0; k < K; ++k) {
         const int step_diag = diag + (L.a[k] == b ? w_match : w_mismatch);
         // vertical gap ending here: open a new one from the cell above, or extend the best one of this column
-        const int open_v = up + w_open, ext_v = bgv + w_extend;
-        const bool new_v = open_v > ext_v;
-        bgv = max(open_v, ext_v);
+        // (DPX add-max: max(a + b, c) in one instruction; "opened a new gap" = the opening won strictly)
+        const int ext_v = bgv + w_extend;
+        bgv = __viaddmax_s32(up, w_open, ext_v);
+        const bool new_v = bgv > ext_v;
         gsv = new_v ? 1 : gsv + 1;
         // horizontal gap ending here
-        const int open_h = L.left[k] + w_open, ext_h = L.bgh[k] + w_extend;
-        const bool new_h = open_h > ext_h;
-        const int nbgh = max(open_h, ext_h);
+        const int ext_h = L.bgh[k] + w_extend;
+        const int nbgh = __viaddmax_s32(L.left[k], w_open, ext_h);
+        const bool new_h = nbgh > ext_h;
         const int ngsh = new_h ? 1 : L.gsh[k] + 1;
         const int gap = max(bgv, nbgh);
         const bool take_diag = step_diag >= gap;
         const int btr_gap = nbgh >= bgv ? -ngsh : gsv;
-        const int cur = max(max(step_diag, gap), SW_MATRIX_MIN_CUTOFF);
+        const int cur = __vimax3_s32(step_diag, gap, SW_MATRIX_MIN_CUTOFF);
         btk[k] = (int16_t)(take_diag ? 0 : btr_gap);
         diag = L.left[k];  // sw[i][j-1] is the diagonal of the row below
         if (ALL_VALID || valid) { L.left[k] = cur; L.bgh[k] = nbgh; L.gsh[k] = ngsh; }
