@@ -532,11 +532,15 @@ void plan_chunk(const gphmm_batch *b, int64_t u0, int64_t u1, bool force_fp64, b
         bool any_quad = false;
         // (only where the sampled reads showed a flat or symmetric quality class: general reads gain nothing from it)
         if (pair_reads_ok && nh && c.n_classes + c.n_sym > 0) {
+            bool in_order = true;  // reads of one length (the usual case) arrive sorted
             for (uint32_t r = 0; r < nr; ++r) {
                 const uint32_t R = c.read_off[d.read_first + r + 1] - c.read_off[d.read_first + r];
-                if (quad_bucket_of_read(R) >= 0) quad_cand.push_back(((uint64_t)R << 32) | r);
+                if (quad_bucket_of_read(R) < 0) continue;
+                const uint64_t key = ((uint64_t)R << 32) | r;
+                in_order = in_order && (quad_cand.empty() || quad_cand.back() < key);
+                quad_cand.push_back(key);
             }
-            std::sort(quad_cand.begin(), quad_cand.end());
+            if (!in_order) std::sort(quad_cand.begin(), quad_cand.end());
             for (size_t i = 0; i + 2 < quad_cand.size() && !any_quad; ++i) any_quad = (quad_cand[i] >> 32) == (quad_cand[i + 2] >> 32);
         }
         // which of the narrow-window schedules the unit's tasks will use: 16-step windows for half-warp tasks (two or more
