@@ -26,10 +26,12 @@
 //                                     the fp64 redo of reads that are not flat-quality.
 //   phmm_fast_f32_kernel<K>           per-base qualities, reads <= 254 bases: rotation hand-off, accumulator row,
 //                                     branch-free step loop, host-planned schedule with haplotype-prefix sharing.
-//   phmm_flat_f32_kernel<K,SYM>       the same for reads with flat insertion/deletion/GCP qualities: transition
+//   phmm_flat_f32_kernel<K,MODE,LANES> the same for reads with flat insertion/deletion/GCP qualities (MODE_FLAT): transition
 //                                     coefficients are kernel parameters (constant / uniform-register operands).
-//                                     SYM: ins == del per base with a flat GCP (the PCR indel model): two per-row
-//                                     coefficients left, the rest still constant operands.
+//                                     MODE_SYM: ins == del per base with a flat GCP (the PCR indel model): two per-row
+//                                     coefficients left, the rest still constant operands.  MODE_GEN: four per-row
+//                                     coefficients (any per-base qualities; LANES = 16 only).  LANES = 32 / 16 / 8: one,
+//                                     two or four reads of a unit per warp (full- / half- / quarter-warp form).
 //   phmm_flat_f64_kernel              fp64 redo of flat-quality reads (one read x one haplotype per task).
 //   phmm_classify_kernel              per read: flat class, symmetric class or general.
 //   phmm_epilogue_f32 / _rescue       raw sums -> log10 likelihoods; builds / consumes the fp64 redo list; the rescue
