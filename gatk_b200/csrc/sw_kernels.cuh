@@ -18,7 +18,10 @@
 namespace phmm_dev {
 
 constexpr int SW_K = 8, SW_ROWS = 32 * SW_K;   // 8 rows per lane: the per-step overhead (hand-off, boundary, stores, loop) is paid per 8 cells
-struct __align__(16) SwBt { int16_t v[SW_K]; };  // the backtrack entries of a lane's step: one 16-byte store
+template <int K> struct __align__(2 * K) SwBt { int16_t v[K]; };  // the backtrack entries of a lane's step: one 16- / 8- / 4-byte store
+// The last strip of a reference runs with as few rows per lane as hold its rows (a 300-row reference leaves 44 rows for its
+// second strip): 32 x rows >= remaining rows, rows in {2, 4, 8}.
+__host__ __device__ constexpr int sw_last_rows(int remaining) { return remaining <= 64 ? 2 : (remaining <= 128 ? 4 : SW_K); }
 constexpr int SW_SOFTCLIP = 0, SW_INDEL = 1, SW_LEADING_INDEL = 2, SW_IGNORE = 3;  // SWOverhangStrategy
 constexpr uint32_t SW_OP_M = 0, SW_OP_I = 1, SW_OP_D = 2, SW_OP_S = 3;
 constexpr int SW_MATRIX_MIN_CUTOFF = -100000000;   // SmithWatermanJavaAligner.java:114
@@ -54,17 +57,16 @@ __device__ __forceinline__ int sw_edge(int idx, bool indel, int w_open, int w_ex
 // steps (every lane of the warp is on a column of the alternate) carry no per-cell predication; the pipeline fill and
 // drain run the guarded form.  The three-way choice keeps the reference's tie rules: diagonal if it is >= both gaps,
 // else the horizontal gap (insertion, -length) if it is >= the vertical one, else the vertical gap (deletion, +length).
-struct SwLane {
-    int a[SW_K], left[SW_K], bgh[SW_K], gsh[SW_K];
+template <int K> struct SwLane {
+    int a[K], left[K], bgh[K], gsh[K];
     int last_sw, last_bgv, last_gsv;  // this lane's bottom row at its current column (what the lane below needs)
     int diag0;                        // row above at the previous column
 };
 
-template <bool ALL_VALID>
-__device__ __forceinline__ void sw_step(SwLane &L, const bool valid, const int b, int up, int bgv, int gsv, const int w_match,
-                                        const int w_mismatch, const int w_open, const int w_extend, SwBt &btv)
+template <bool ALL_VALID, int K>
+__device__ __forceinline__ void sw_step(SwLane<K> &L, const bool valid, const int b, int up, int bgv, int gsv, const int w_match,
+                                        const int w_mismatch, const int w_open, const int w_extend, SwBt<K> &btv)
 {
-    constexpr int K = SW_K;
     const int up_in = up;
     int diag = L.diag0;
     int16_t *btk = btv.v;
@@ -95,6 +97,66 @@ __device__ __forceinline__ void sw_step(SwLane &L, const bool valid, const int b
         L.last_sw = up; L.last_bgv = bgv; L.last_gsv = gsv;
         L.diag0 = up_in;   // row above at this column = diagonal of k = 0 at the next column
     }
+}
+
+// One strip of the matrix: 32 x K reference rows against every column of the alternate.  bt_strip = this strip's backtrack area.
+template <int K>
+__device__ __forceinline__ void sw_strip(const SwArgs &g, const uint8_t *__restrict__ ref, const uint8_t *__restrict__ alt, const int n_ref,
+                                         const int n_alt, const int strip_row0, const bool first_strip, const bool last_strip, const bool indel,
+                                         const int lane, const int n_steps, int32_t *lastcol, int32_t *bottom, int32_t *bnd, int16_t *bt_strip)
+{
+    constexpr unsigned FULL = 0xffffffffu;
+    const int row0 = strip_row0 + lane * K;  // row of k = 0 is row0 + 1
+    SwLane<K> L;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const int i = row0 + k + 1;
+        L.a[k] = i <= n_ref ? (int)ref[i - 1] : 0x100;
+        L.left[k] = sw_edge(i, indel, g.w_open, g.w_extend);  // sw[i][0]
+        L.bgh[k] = SW_LOW_INIT; L.gsh[k] = 0;
+    }
+    L.last_sw = 0; L.last_bgv = SW_LOW_INIT; L.last_gsv = 0;
+    L.diag0 = sw_edge(row0, indel, g.w_open, g.w_extend);  // sw[row0][0]: row above at column 0
+    // the row of the last reference base (bottom row of the matrix) lives in one slot of one lane of the last strip
+    const int k_last = last_strip && (n_ref - 1 - row0) >= 0 && (n_ref - 1 - row0) < K ? n_ref - 1 - row0 : -1;
+    __syncwarp();
+    int p = 1 - lane;
+    auto step = [&](auto all_valid) {
+        constexpr bool ALL = decltype(all_valid)::value;
+        const bool valid = ALL || (p >= 1 && p <= n_alt);
+        // row above at this column
+        int up = __shfl_up_sync(FULL, L.last_sw, 1), bgv = __shfl_up_sync(FULL, L.last_bgv, 1), gsv = __shfl_up_sync(FULL, L.last_gsv, 1);
+        if (lane == 0) {
+            if (first_strip) { up = sw_edge(p, indel, g.w_open, g.w_extend); bgv = SW_LOW_INIT; gsv = 0; }
+            else if (valid) { up = bnd[3 * p]; bgv = bnd[3 * p + 1]; gsv = bnd[3 * p + 2]; }
+        }
+        const int b = valid ? (int)alt[p - 1] : 0x200;
+        SwBt<K> btv;
+        sw_step<ALL, K>(L, valid, b, up, bgv, gsv, g.w_match, g.w_mismatch, g.w_open, g.w_extend, btv);
+        if (valid) {
+            const int s = p + lane;  // step number (1-based): backtrack entries are stored in wavefront order
+            *reinterpret_cast<SwBt<K> *>(bt_strip + ((size_t)(s - 1) * 32 + lane) * K) = btv;
+            if (!last_strip && lane == 31) { bnd[3 * p] = L.last_sw; bnd[3 * p + 1] = L.last_bgv; bnd[3 * p + 2] = L.last_gsv; }
+            if (k_last >= 0) {  // bottom row, every column
+                int v = L.left[0];
+#pragma unroll
+                for (int k = 1; k < K; ++k) v = k == k_last ? L.left[k] : v;
+                bottom[p] = v;
+            }
+            if (p == n_alt) {   // last column, every row of this lane
+#pragma unroll
+                for (int k = 0; k < K; ++k)
+                    if (row0 + k + 1 <= n_ref) lastcol[row0 + k + 1] = L.left[k];
+            }
+        }
+        ++p;
+    };
+    // fill (some lanes are still in front of column 1), steady state, drain (some lanes are past the last column)
+    int s = 1;
+    for (; s <= min(31, n_steps); ++s) step(std::false_type{});
+    for (; s <= n_alt; ++s) step(std::true_type{});
+    for (; s <= n_steps; ++s) step(std::false_type{});
+    __syncwarp();
 }
 
 __global__ void __launch_bounds__(32) phmm_sw_kernel(const SwArgs g)
@@ -137,59 +199,16 @@ __global__ void __launch_bounds__(32) phmm_sw_kernel(const SwArgs g)
         int32_t *lastcol = g.aux + t.aux_off, *bottom = lastcol + (n_ref + 1), *bnd = bottom + (n_alt + 1);
         int16_t *bt = g.bt + t.bt_off;
         const int n_strips = (n_ref + SW_ROWS - 1) / SW_ROWS, n_steps = n_alt + 31;
+        const int k_tail = sw_last_rows(n_ref - (n_strips - 1) * SW_ROWS);  // rows per lane of the last strip
         for (int strip = 0; strip < n_strips; ++strip) {
             const bool first_strip = strip == 0, last_strip = strip == n_strips - 1;
-            const int row0 = strip * SW_ROWS + lane * K;  // row of k = 0 is row0 + 1
-            SwLane L;
-#pragma unroll
-            for (int k = 0; k < K; ++k) {
-                const int i = row0 + k + 1;
-                L.a[k] = i <= n_ref ? (int)ref[i - 1] : 0x100;
-                L.left[k] = sw_edge(i, indel, g.w_open, g.w_extend);  // sw[i][0]
-                L.bgh[k] = SW_LOW_INIT; L.gsh[k] = 0;
-            }
-            L.last_sw = 0; L.last_bgv = SW_LOW_INIT; L.last_gsv = 0;
-            L.diag0 = sw_edge(row0, indel, g.w_open, g.w_extend);  // sw[row0][0]: row above at column 0
-            // the row of the last reference base (bottom row of the matrix) lives in one slot of one lane of the last strip
-            const int k_last = last_strip && (n_ref - 1 - row0) >= 0 && (n_ref - 1 - row0) < K ? n_ref - 1 - row0 : -1;
-            __syncwarp();
-            int p = 1 - lane;
-            auto step = [&](auto all_valid) {
-                constexpr bool ALL = decltype(all_valid)::value;
-                const bool valid = ALL || (p >= 1 && p <= n_alt);
-                // row above at this column
-                int up = __shfl_up_sync(FULL, L.last_sw, 1), bgv = __shfl_up_sync(FULL, L.last_bgv, 1), gsv = __shfl_up_sync(FULL, L.last_gsv, 1);
-                if (lane == 0) {
-                    if (first_strip) { up = sw_edge(p, indel, g.w_open, g.w_extend); bgv = SW_LOW_INIT; gsv = 0; }
-                    else if (valid) { up = bnd[3 * p]; bgv = bnd[3 * p + 1]; gsv = bnd[3 * p + 2]; }
-                }
-                const int b = valid ? (int)alt[p - 1] : 0x200;
-                SwBt btv;
-                sw_step<ALL>(L, valid, b, up, bgv, gsv, g.w_match, g.w_mismatch, g.w_open, g.w_extend, btv);
-                if (valid) {
-                    const int s = p + lane;  // step number (1-based): backtrack entries are stored in wavefront order
-                    *reinterpret_cast<SwBt *>(bt + (((size_t)strip * n_steps + (s - 1)) * 32 + lane) * K) = btv;
-                    if (!last_strip && lane == 31) { bnd[3 * p] = L.last_sw; bnd[3 * p + 1] = L.last_bgv; bnd[3 * p + 2] = L.last_gsv; }
-                    if (k_last >= 0) {  // bottom row, every column
-                        int v = L.left[0];
-#pragma unroll
-                        for (int k = 1; k < K; ++k) v = k == k_last ? L.left[k] : v;
-                        bottom[p] = v;
-                    }
-                    if (p == n_alt) {   // last column, every row of this lane
-#pragma unroll
-                        for (int k = 0; k < K; ++k)
-                            if (row0 + k + 1 <= n_ref) lastcol[row0 + k + 1] = L.left[k];
-                    }
-                }
-                ++p;
-            };
-            // fill (some lanes are still in front of column 1), steady state, drain (some lanes are past the last column)
-            int s = 1;
-            for (; s <= min(31, n_steps); ++s) step(std::false_type{});
-            for (; s <= n_alt; ++s) step(std::true_type{});
-            for (; s <= n_steps; ++s) step(std::false_type{});
-            __syncwarp();
+            int16_t *bt_strip = bt + (size_t)strip * n_steps * SW_ROWS;
+            if (!last_strip || k_tail == SW_K)
+                sw_strip<SW_K>(g, ref, alt, n_ref, n_alt, strip * SW_ROWS, first_strip, last_strip, indel, lane, n_steps, lastcol, bottom, bnd, bt_strip);
+            else if (k_tail == 4)
+                sw_strip<4>(g, ref, alt, n_ref, n_alt, strip * SW_ROWS, first_strip, last_strip, indel, lane, n_steps, lastcol, bottom, bnd, bt_strip);
+            else
+                sw_strip<2>(g, ref, alt, n_ref, n_alt, strip * SW_ROWS, first_strip, last_strip, indel, lane, n_steps, lastcol, bottom, bnd, bt_strip);
         }
         __threadfence_block();
         __syncwarp();
@@ -200,8 +219,9 @@ __global__ void __launch_bounds__(32) phmm_sw_kernel(const SwArgs g)
         // consumes the leading run of zeros (diagonal moves) in one go: an alignment is mostly long match runs.
         {
             auto BT = [&](int i, int j) -> int {
-                const int strip = (i - 1) / SW_ROWS, ln = ((i - 1) % SW_ROWS) / K, k = (i - 1) % K;
-                return (int)bt[(((size_t)strip * n_steps + (j + ln - 1)) * 32 + ln) * K + k];
+                const int strip = (i - 1) / SW_ROWS, r = (i - 1) % SW_ROWS, ks = strip == n_strips - 1 ? k_tail : SW_K;
+                const int ln = r / ks, k = r % ks;
+                return (int)bt[(size_t)strip * n_steps * SW_ROWS + ((size_t)(j + ln - 1) * 32 + ln) * ks + k];
             };
             int p1 = 0, p2 = 0, maxscore = INT32_MIN, segment_length = 0;
             if (g.strategy == SW_INDEL) {
