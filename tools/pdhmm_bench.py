@@ -13,7 +13,8 @@ from oracle import oracle
 from test_pdhmm import random_pd
 
 n_regions = int(sys.argv[1]) if len(sys.argv) > 1 else 1000
-b = synth.config2(n_regions, pinned=True)
+# second argument 150: the configs[0] shape (128 reads x 150 bases x 8 haplotypes of 200-300 bases) instead of configs[1]
+b = synth.config1_many(n_regions, pinned=True) if len(sys.argv) > 2 and sys.argv[2] == "150" else synth.config2(n_regions, pinned=True)
 rng = np.random.default_rng(1)
 results = []
 with GpuPhmm() as h:
